@@ -1,0 +1,287 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT -- see oracle/tloam_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may import this module.
+PARITY UNPINNED: the reference ships no tests or golden vectors for this path and cannot be built here.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libtloam_oracle.so")
+
+MAX_OUTER = 16
+MAX_INNER = 8
+CLOUDS = ("edge", "sphere", "planar", "ground")
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("k_corr", C.c_int), ("factor_num", C.c_int),
+        ("edge_dist_thres", C.c_double), ("sphere_dist_thres", C.c_double),
+        ("planar_dist_thres", C.c_double), ("ground_dist_thres", C.c_double),
+        ("edge_dir_thres", C.c_double),
+        ("edge_maxnum", C.c_int), ("sphere_maxnum", C.c_int), ("planar_maxnum", C.c_int), ("ground_maxnum", C.c_int),
+        ("max_iterations", C.c_int),
+        ("cost_threshold", C.c_double), ("gnc_factor", C.c_double), ("noise_bound", C.c_double),
+        ("fitness_thres", C.c_double),
+        ("ceres_max_num_iterations", C.c_int),
+        ("reinit_dir", C.c_double * 3),
+        ("threads_mode", C.c_int), ("num_threads", C.c_int),
+    ]
+
+
+class InnerTrace(C.Structure):
+    _fields_ = [
+        ("x_candidate", C.c_double * 6), ("candidate_cost", C.c_double), ("model_cost_change", C.c_double),
+        ("relative_decrease", C.c_double), ("step_norm_scaled", C.c_double), ("radius", C.c_double),
+        ("accepted", C.c_int), ("used_gauss_newton", C.c_int),
+    ]
+
+
+class OuterTrace(C.Structure):
+    _fields_ = [
+        ("x_start", C.c_double * 6), ("x_end", C.c_double * 6),
+        ("initial_cost", C.c_double), ("final_cost", C.c_double),
+        ("H0", C.c_double * 36), ("g0", C.c_double * 6),
+        ("mu", C.c_double), ("th1", C.c_double), ("th2", C.c_double),
+        ("slot_sum", C.c_double * 4), ("n_factors", C.c_int * 4),
+        ("n_inner", C.c_int), ("termination", C.c_int),
+        ("inner", InnerTrace * MAX_INNER),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_outer", C.c_int), ("converged_early", C.c_int),
+        ("x_init", C.c_double * 6), ("x_final", C.c_double * 6),
+        ("t_kdtree", C.c_double), ("t_factors", C.c_double), ("t_solve", C.c_double),
+        ("t_weights", C.c_double), ("t_total", C.c_double),
+        ("outer", OuterTrace * MAX_OUTER),
+    ]
+
+
+def build(force=False):
+    """Compile oracle/_build/libtloam_oracle.so with the system g++ (the image's $CXX has no OpenMP)."""
+    src = [os.path.join(_HERE, "tloam_oracle.cpp"), os.path.join(_HERE, "tloam_oracle.h")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        L.oracle_default_config.argtypes = [C.POINTER(Config)]
+        L.oracle_create.argtypes = [C.POINTER(Config)]
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        for f in (L.oracle_set_source, L.oracle_set_target):
+            f.argtypes = [C.c_void_p, C.POINTER(dp), C.POINTER(C.c_size_t)]
+            f.restype = C.c_int
+        L.oracle_scan_match.argtypes = [C.c_void_p, dp, dp, C.POINTER(Stats)]
+        L.oracle_scan_match.restype = C.c_int
+        L.oracle_fitness.argtypes = [C.c_void_p, dp, dp]
+        L.oracle_get_pose_increment.argtypes = [C.c_void_p, dp]
+        L.oracle_get_weights.argtypes = [C.c_void_p, C.c_int, dp, C.c_size_t]
+        L.oracle_get_weights.restype = C.c_int
+        L.oracle_se3_exp.argtypes = [dp, dp]
+        L.oracle_se3_log.argtypes = [dp, dp]
+        L.oracle_se3_plus.argtypes = [dp, dp, dp]
+        L.oracle_se3_exp_quat.argtypes = [dp, dp]
+        L.oracle_knn.argtypes = [dp, C.c_size_t, dp, C.c_size_t, C.c_double, C.c_int,
+                                 C.POINTER(C.c_int), dp, C.POINTER(C.c_int), C.c_int]
+        L.oracle_fit_plane.argtypes = [dp, C.c_int, dp]
+        L.oracle_fit_line.argtypes = [dp, C.c_int, C.c_double, dp, dp, dp, dp, dp]
+        L.oracle_fit_line.restype = C.c_int
+        L.oracle_sym_eig3.argtypes = [dp, dp, dp]
+        L.oracle_eval_point_to_point.argtypes = [dp, dp, dp, C.c_double, dp, dp, dp]
+        L.oracle_eval_point_to_line.argtypes = [dp, dp, dp, dp, C.c_double, dp, dp, dp]
+        L.oracle_eval_point_to_plane.argtypes = [dp, dp, dp, C.c_double, C.c_double, dp, dp, dp]
+        L.oracle_build_factors.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_int), dp, C.c_size_t]
+        L.oracle_build_factors.restype = C.c_int
+        L.oracle_update_weight.argtypes = [dp, dp, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def default_config(**overrides):
+    cfg = Config()
+    lib().oracle_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if k == "reinit_dir":
+            for i in range(3):
+                cfg.reinit_dir[i] = float(v[i])
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _cloud_args(clouds):
+    arrs = [_f64(clouds[i] if not isinstance(clouds, dict) else clouds[CLOUDS[i]]).reshape(-1, 3) for i in range(4)]
+    ptrs = (C.POINTER(C.c_double) * 4)(*[_dp(a) for a in arrs])
+    ns = (C.c_size_t * 4)(*[a.shape[0] for a in arrs])
+    return arrs, ptrs, ns
+
+
+class Oracle:
+    """Mirror of tloam::LocalRegistration (ref: include/tloam/models/registration/registration.hpp:142-165)."""
+
+    def __init__(self, cfg=None, **overrides):
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        self._h = lib().oracle_create(C.byref(self.cfg))
+        self._n_src = [0, 0, 0, 0]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_destroy(self._h)
+            self._h = None
+
+    def set_input_source(self, clouds):
+        arrs, ptrs, ns = _cloud_args(clouds)
+        self._n_src = [a.shape[0] for a in arrs]
+        return lib().oracle_set_source(self._h, ptrs, ns)
+
+    def set_input_target(self, clouds):
+        arrs, ptrs, ns = _cloud_args(clouds)
+        return lib().oracle_set_target(self._h, ptrs, ns)
+
+    def scan_matching(self, predict):
+        """predict: 4x4 (row-major numpy). Returns (status, result 4x4, Stats)."""
+        p = _f64(np.asarray(predict).T).reshape(16)  # column-major
+        out = np.zeros(16)
+        st = Stats()
+        rc = lib().oracle_scan_match(self._h, _dp(p), _dp(out), C.byref(st))
+        return rc, out.reshape(4, 4).T.copy(), st
+
+    def fitness(self):
+        a = C.c_double(0)
+        b = C.c_double(0)
+        lib().oracle_fitness(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def pose_increment(self):
+        out = np.zeros(16)
+        lib().oracle_get_pose_increment(self._h, _dp(out))
+        return out.reshape(4, 4).T.copy()
+
+    def weights(self, cloud):
+        w = np.zeros(self._n_src[cloud])
+        rc = lib().oracle_get_weights(self._h, cloud, _dp(w), w.size)
+        assert rc == 0
+        return w
+
+    def build_factors(self, cloud, x):
+        n = self._n_src[cloud]
+        valid = np.zeros(n, dtype=np.int32)
+        prim = np.zeros((n, 6))
+        x = _f64(x)
+        rc = lib().oracle_build_factors(self._h, cloud, _dp(x), valid.ctypes.data_as(C.POINTER(C.c_int)), _dp(prim), n)
+        assert rc == 0
+        return valid, prim
+
+
+def se3_exp(a):
+    a = _f64(a)
+    T = np.zeros(16)
+    lib().oracle_se3_exp(_dp(a), _dp(T))
+    return T.reshape(4, 4).T.copy()
+
+
+def se3_log(T):
+    t = _f64(np.asarray(T).T).reshape(16)
+    a = np.zeros(6)
+    lib().oracle_se3_log(_dp(t), _dp(a))
+    return a
+
+
+def se3_plus(x, d):
+    x = _f64(x)
+    d = _f64(d)
+    out = np.zeros(6)
+    lib().oracle_se3_plus(_dp(x), _dp(d), _dp(out))
+    return out
+
+
+def knn(pts, queries, radius, k, brute_force=False):
+    pts = _f64(pts).reshape(-1, 3)
+    q = _f64(queries).reshape(-1, 3)
+    nq = q.shape[0]
+    idx = np.full((nq, k), -1, dtype=np.int32)
+    d2 = np.full((nq, k), np.inf)
+    cnt = np.zeros(nq, dtype=np.int32)
+    lib().oracle_knn(_dp(pts), pts.shape[0], _dp(q), nq, float(radius), int(k),
+                     idx.ctypes.data_as(C.POINTER(C.c_int)), _dp(d2), cnt.ctypes.data_as(C.POINTER(C.c_int)),
+                     1 if brute_force else 0)
+    return idx, d2, cnt
+
+
+def fit_plane(pts):
+    pts = _f64(pts).reshape(-1, 3)
+    out = np.zeros(4)
+    lib().oracle_fit_plane(_dp(pts), pts.shape[0], _dp(out))
+    return out
+
+
+def fit_line(pts, dir_thres=0.85):
+    pts = _f64(pts).reshape(-1, 3)
+    a, b, mean, d, eig = (np.zeros(3) for _ in range(5))
+    ok = lib().oracle_fit_line(_dp(pts), pts.shape[0], float(dir_thres), _dp(a), _dp(b), _dp(mean), _dp(d), _dp(eig))
+    return ok, a, b, mean, d, eig
+
+
+def sym_eig3(cov):
+    cov = _f64(cov).reshape(9)
+    eig = np.zeros(3)
+    vec = np.zeros(9)
+    lib().oracle_sym_eig3(_dp(cov), _dp(eig), _dp(vec))
+    return eig, vec.reshape(3, 3).T.copy()  # columns = eigenvectors
+
+
+def eval_point_to_point(x, p, q, w):
+    x, p, q = _f64(x), _f64(p), _f64(q)
+    r, J, c = np.zeros(3), np.zeros(18), C.c_double(0)
+    lib().oracle_eval_point_to_point(_dp(x), _dp(p), _dp(q), float(w), _dp(r), _dp(J), C.byref(c))
+    return r, J.reshape(3, 6), c.value
+
+
+def eval_point_to_line(x, p, a, b, w):
+    x, p, a, b = _f64(x), _f64(p), _f64(a), _f64(b)
+    r, J, c = np.zeros(3), np.zeros(18), C.c_double(0)
+    lib().oracle_eval_point_to_line(_dp(x), _dp(p), _dp(a), _dp(b), float(w), _dp(r), _dp(J), C.byref(c))
+    return r, J.reshape(3, 6), c.value
+
+
+def eval_point_to_plane(x, p, n, d, w):
+    x, p, n = _f64(x), _f64(p), _f64(n)
+    r, J, c = np.zeros(1), np.zeros(6), C.c_double(0)
+    lib().oracle_eval_point_to_plane(_dp(x), _dp(p), _dp(n), float(d), float(w), _dp(r), _dp(J), C.byref(c))
+    return r, J.reshape(1, 6), c.value
+
+
+def update_weight(weights, slots, noise_bound_sq, th1, th2, mu):
+    w = _f64(weights).copy()
+    s = _f64(slots)
+    lib().oracle_update_weight(_dp(w), _dp(s), w.size, noise_bound_sq, th1, th2, mu)
+    return w
