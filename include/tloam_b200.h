@@ -1,0 +1,166 @@
+/*
+ * tloam_b200.h -- C ABI of the B200-native TLS scan-to-map registration library (libtloam_b200.so).
+ *
+ * This is the drop-in boundary for T-LOAM's pose-optimisation hot path.  Each entry point names the
+ * reference interface it replaces ("ref:" paths are relative to the zhoupengwei/tloam tree):
+ *
+ *   tloam_b200_create           <- LocalRegistration::LocalRegistration(YAML::Node) + initConfig
+ *                                  ref: src/models/registration/registration.cpp:182-230
+ *   tloam_b200_set_source       <- RegistrationInterface::setInputSource(Frame&)
+ *                                  ref: include/tloam/models/registration/registration_interface.hpp:44,
+ *                                       registration.cpp:232-239
+ *   tloam_b200_set_target       <- RegistrationInterface::setInputTarget(Frame&)   (+ the per-call KD-tree
+ *                                  rebuild of registration.cpp:888-915, done ONCE per map here)
+ *                                  ref: registration_interface.hpp:45, registration.cpp:241-248
+ *   tloam_b200_scan_match       <- RegistrationInterface::scanMatching(Frame&, Isometry3d&, Isometry3d&)
+ *                                  ref: registration_interface.hpp:46, registration.cpp:879-1133
+ *   tloam_b200_fitness          <- RegistrationInterface::getFitnessScore()
+ *                                  ref: registration_interface.hpp:47, registration.cpp:257-296
+ *   tloam_b200_get_transform / _get_pose_increment <- getTransform() / getPoseIncrement()
+ *                                  ref: registration.cpp:370-376
+ *   tloam_b200_eval_point_to_{point,line,plane}    <- PointTo{Point,Line,Plane}Err::Evaluate
+ *                                  ref: registration.cpp:19-47, 55-88, 96-117
+ *
+ * Conventions
+ *   - clouds: contiguous AoS FP64 xyz (the layout of std::vector<Eigen::Vector3d>,
+ *     ref: include/tloam/open3d/PointCloud2.hpp:396); array index 0..3 = edge, sphere, planar, ground
+ *     (order of registration.cpp:233-236).
+ *   - poses: 4x4 FP64 COLUMN-major (Eigen::Isometry3d::matrix().data()).
+ *   - the library copies inputs at set_*(); caller buffers may be freed on return.
+ *   - one handle = one CUDA device + one stream, single caller, not re-entrant (like the reference,
+ *     ref: registration.hpp:327-329).  Distinct handles are independent.
+ *   - no function aborts or throws; all return a tloam_b200_status.  There is NO CPU fallback: without a
+ *     CUDA device tloam_b200_create returns TLOAM_B200_ERR_NO_DEVICE.
+ */
+#ifndef TLOAM_B200_H
+#define TLOAM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLOAM_B200_MAX_OUTER 16
+#define TLOAM_B200_MAX_INNER 8
+
+typedef struct tloam_b200_handle tloam_b200_handle;
+
+typedef enum tloam_b200_status {
+  TLOAM_B200_OK = 0,
+  TLOAM_B200_ERR_INVALID_ARG = 1,
+  TLOAM_B200_ERR_TOO_FEW_POINTS = 2, /* a cloud has < 10 points: the reference asserts (registration.cpp:928-929) */
+  TLOAM_B200_ERR_BAD_POSE = 3,       /* predict is not a rigid transform: Sophus would abort (so3.hpp:469-472) */
+  TLOAM_B200_ERR_CUDA = 4,
+  TLOAM_B200_ERR_NO_DEVICE = 5,
+  TLOAM_B200_ERR_NOT_READY = 6,      /* scan_match before set_source / set_target */
+  TLOAM_B200_ERR_NUMERIC = 7         /* non-finite value met inside the solve */
+} tloam_b200_status;
+
+/* The "TLS:" YAML block (ref: config/mapping/lidar_odometry.yaml:23-39, read at registration.cpp:212-230)
+ * as a POD, same names, same defaults, plus explicit switches for reference quirks. */
+typedef struct tloam_tls_config {
+  int k_corr;            /* on the API surface, unused by the executed path */
+  int factor_num;        /* 2 = planar+ground, 3 = +edge, 4 = +sphere (registration.hpp:144-148) */
+  double edge_dist_thres, sphere_dist_thres, planar_dist_thres, ground_dist_thres;
+  double edge_dir_thres;
+  int edge_maxnum, sphere_maxnum, planar_maxnum, ground_maxnum;
+  int max_iterations;    /* outer GNC iterations */
+  double cost_threshold, gnc_factor, noise_bound, fitness_thres;
+  /* extras */
+  int ceres_max_num_iterations; /* options.max_num_iterations, registration.cpp:1043 */
+  double reinit_dir[3];  /* replaces the unseeded Eigen::Vector3d::Random() of registration.cpp:885 */
+} tloam_tls_config;
+
+typedef struct tloam_b200_inner_trace {
+  double x_candidate[6];
+  double candidate_cost, model_cost_change, relative_decrease, step_norm_scaled, radius;
+  int accepted;          /* 1 accepted, 0 rejected, -1 invalid step, 2 terminated by a tolerance */
+  int used_gauss_newton;
+} tloam_b200_inner_trace;
+
+typedef struct tloam_b200_outer_trace {
+  double x_start[6], x_end[6];
+  double initial_cost, final_cost;
+  double H0[36], g0[6];  /* J^T J / J^T r (robustified) at x_start, row-major */
+  double mu, th1, th2;
+  double slot_sum[4];
+  int n_factors[4];
+  int n_inner, termination; /* 0 max-iter, 1 function tol, 2 parameter tol, 3 gradient tol, 4 radius, 5 no residuals, 6 invalid steps */
+  tloam_b200_inner_trace inner[TLOAM_B200_MAX_INNER];
+} tloam_b200_outer_trace;
+
+typedef struct tloam_b200_stats {
+  int n_outer, converged_early;
+  double x_init[6], x_final[6];
+  int gpu_launches;      /* kernels launched by this scan_match call */
+  float gpu_ms;          /* device time of the call (CUDA events on the handle's stream) */
+  tloam_b200_outer_trace outer[TLOAM_B200_MAX_OUTER];
+} tloam_b200_stats;
+
+void tloam_b200_default_config(tloam_tls_config* cfg);
+const char* tloam_b200_status_string(int status);
+const char* tloam_b200_last_error(tloam_b200_handle* h); /* text of the last CUDA failure of this handle */
+
+/* device: CUDA ordinal. stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL to let
+ * the handle create its own non-blocking stream. */
+int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tloam_b200_handle** out);
+int tloam_b200_destroy(tloam_b200_handle* h);
+
+/* HOST buffers (pageable or pinned). set_target also builds the voxel-hash grids on the device. */
+int tloam_b200_set_source(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]);
+int tloam_b200_set_target(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]);
+/* DEVICE buffers (inputs already resident in HBM), same layout. Enqueued on the handle's stream. */
+int tloam_b200_set_source_device(tloam_b200_handle* h, const double* const d_xyz[4], const size_t n[4]);
+int tloam_b200_set_target_device(tloam_b200_handle* h, const double* const d_xyz[4], const size_t n[4]);
+
+/* Blocking: enqueues the frame, waits, returns the pose (and optionally the trace). */
+int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double result[16], tloam_b200_stats* stats);
+/* Split form: enqueue only / wait + fetch. Lets one host thread drive several handles (one per GPU). */
+int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]);
+int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_stats* stats);
+
+int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse);
+int tloam_b200_get_transform(tloam_b200_handle* h, double pose[16]);
+int tloam_b200_get_pose_increment(tloam_b200_handle* h, double pose[16]);
+int tloam_b200_synchronize(tloam_b200_handle* h);
+/* total kernels launched by this handle so far */
+long long tloam_b200_launch_count(tloam_b200_handle* h);
+
+/* ---- shared-map transport (multi-GPU, config 4): the built map (cell-sorted float4 points + hash
+ * tables + header) is one contiguous device blob so that a single ncclBroadcast moves it. ---- */
+int tloam_b200_map_blob_size(tloam_b200_handle* h, size_t* bytes);
+int tloam_b200_map_export(tloam_b200_handle* h, void* d_dst, size_t bytes);       /* D2D copy out */
+int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes); /* D2D copy in, adopt */
+int tloam_b200_get_map_origin(tloam_b200_handle* h, double origin[3]);
+
+/* ---- piecewise entry points (parity tests; host arrays in, host arrays out, computed on the GPU) ---- */
+/* Exact radius-truncated kNN on the built map of `cloud` (KDTreeFlann::SearchHybrid semantics): idx/d2 are
+ * nq*k, ascending (d2, index), padded with -1 / +inf; count[i] = neighbours strictly inside the radius. */
+int tloam_b200_knn(tloam_b200_handle* h, int cloud, const double* queries, size_t nq, double radius, int k,
+                   int* idx, double* d2, int* count);
+/* Correspondence search + primitive fit + caps for one cloud at tangent x (all weights 1):
+ * valid[i] in {0,1}; prim = n*6 doubles: plane (n,d,0,0), line (a,b), point (q,0,0,0). */
+int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6], int* valid, double* prim, size_t n);
+/* Batched cost functors: arrays of m factors; r is m*3 (m*1 for plane), J is m*18 (m*6), cost is m. */
+int tloam_b200_eval_point_to_point(tloam_b200_handle* h, const double x[6], size_t m, const double* p,
+                                   const double* q, const double* w, double* r, double* J, double* cost);
+int tloam_b200_eval_point_to_line(tloam_b200_handle* h, const double x[6], size_t m, const double* p,
+                                  const double* a, const double* b, const double* w, double* r, double* J,
+                                  double* cost);
+int tloam_b200_eval_point_to_plane(tloam_b200_handle* h, const double x[6], size_t m, const double* p,
+                                   const double* n, const double* d, const double* w, double* r, double* J,
+                                   double* cost);
+/* SE(3) helpers evaluated on the device (exp: tangent -> 4x4 col-major; log: inverse; plus: left update). */
+int tloam_b200_se3_exp(tloam_b200_handle* h, const double a[6], double T[16]);
+int tloam_b200_se3_log(tloam_b200_handle* h, const double T[16], double a[6]);
+int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double delta[6], double out[6]);
+
+/* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
+int tloam_b200_host_alloc(void** p, size_t bytes);
+int tloam_b200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

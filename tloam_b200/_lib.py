@@ -1,0 +1,123 @@
+"""ctypes loader for libtloam_b200.so (the C-ABI CUDA library). Fails loudly: there is no CPU fallback."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtloam_b200.so")
+
+MAX_OUTER = 16
+MAX_INNER = 8
+
+OK, ERR_INVALID_ARG, ERR_TOO_FEW_POINTS, ERR_BAD_POSE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC = range(8)
+
+
+class TlsConfig(C.Structure):
+    """tloam_tls_config (include/tloam_b200.h) = the YAML "TLS:" block of the reference."""
+    _fields_ = [
+        ("k_corr", C.c_int), ("factor_num", C.c_int),
+        ("edge_dist_thres", C.c_double), ("sphere_dist_thres", C.c_double),
+        ("planar_dist_thres", C.c_double), ("ground_dist_thres", C.c_double),
+        ("edge_dir_thres", C.c_double),
+        ("edge_maxnum", C.c_int), ("sphere_maxnum", C.c_int), ("planar_maxnum", C.c_int), ("ground_maxnum", C.c_int),
+        ("max_iterations", C.c_int),
+        ("cost_threshold", C.c_double), ("gnc_factor", C.c_double), ("noise_bound", C.c_double),
+        ("fitness_thres", C.c_double),
+        ("ceres_max_num_iterations", C.c_int),
+        ("reinit_dir", C.c_double * 3),
+    ]
+
+
+class InnerTrace(C.Structure):
+    _fields_ = [
+        ("x_candidate", C.c_double * 6), ("candidate_cost", C.c_double), ("model_cost_change", C.c_double),
+        ("relative_decrease", C.c_double), ("step_norm_scaled", C.c_double), ("radius", C.c_double),
+        ("accepted", C.c_int), ("used_gauss_newton", C.c_int),
+    ]
+
+
+class OuterTrace(C.Structure):
+    _fields_ = [
+        ("x_start", C.c_double * 6), ("x_end", C.c_double * 6),
+        ("initial_cost", C.c_double), ("final_cost", C.c_double),
+        ("H0", C.c_double * 36), ("g0", C.c_double * 6),
+        ("mu", C.c_double), ("th1", C.c_double), ("th2", C.c_double),
+        ("slot_sum", C.c_double * 4), ("n_factors", C.c_int * 4),
+        ("n_inner", C.c_int), ("termination", C.c_int),
+        ("inner", InnerTrace * MAX_INNER),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_outer", C.c_int), ("converged_early", C.c_int),
+        ("x_init", C.c_double * 6), ("x_final", C.c_double * 6),
+        ("gpu_launches", C.c_int), ("gpu_ms", C.c_float),
+        ("outer", OuterTrace * MAX_OUTER),
+    ]
+
+
+EXPORTS = [
+    "tloam_b200_default_config", "tloam_b200_status_string", "tloam_b200_last_error", "tloam_b200_create",
+    "tloam_b200_destroy", "tloam_b200_set_source", "tloam_b200_set_target", "tloam_b200_set_source_device",
+    "tloam_b200_set_target_device", "tloam_b200_scan_match", "tloam_b200_scan_match_async", "tloam_b200_get_result",
+    "tloam_b200_fitness", "tloam_b200_get_transform", "tloam_b200_get_pose_increment", "tloam_b200_synchronize",
+    "tloam_b200_launch_count", "tloam_b200_map_blob_size", "tloam_b200_map_export", "tloam_b200_map_import",
+    "tloam_b200_get_map_origin", "tloam_b200_knn", "tloam_b200_build_factors", "tloam_b200_eval_point_to_point",
+    "tloam_b200_eval_point_to_line", "tloam_b200_eval_point_to_plane", "tloam_b200_se3_exp", "tloam_b200_se3_log",
+    "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library. Raises if it has not been built (python -m tloam_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m tloam_b200.build` "
+                           "(there is no CPU fallback for the registration path)")
+    L = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int)
+    vp = C.c_void_p
+    L.tloam_b200_default_config.argtypes = [C.POINTER(TlsConfig)]
+    L.tloam_b200_default_config.restype = None
+    L.tloam_b200_status_string.argtypes = [C.c_int]
+    L.tloam_b200_status_string.restype = C.c_char_p
+    L.tloam_b200_last_error.argtypes = [vp]
+    L.tloam_b200_last_error.restype = C.c_char_p
+    L.tloam_b200_create.argtypes = [C.POINTER(TlsConfig), C.c_int, vp, C.POINTER(vp)]
+    L.tloam_b200_destroy.argtypes = [vp]
+    for name in ("set_source", "set_target"):
+        f = getattr(L, "tloam_b200_" + name)
+        f.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_size_t)]
+    for name in ("set_source_device", "set_target_device"):
+        f = getattr(L, "tloam_b200_" + name)
+        f.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.tloam_b200_scan_match.argtypes = [vp, dp, dp, C.POINTER(Stats)]
+    L.tloam_b200_scan_match_async.argtypes = [vp, dp]
+    L.tloam_b200_get_result.argtypes = [vp, dp, C.POINTER(Stats)]
+    L.tloam_b200_fitness.argtypes = [vp, dp, dp]
+    L.tloam_b200_get_transform.argtypes = [vp, dp]
+    L.tloam_b200_get_pose_increment.argtypes = [vp, dp]
+    L.tloam_b200_synchronize.argtypes = [vp]
+    L.tloam_b200_launch_count.argtypes = [vp]
+    L.tloam_b200_launch_count.restype = C.c_longlong
+    L.tloam_b200_map_blob_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.tloam_b200_map_export.argtypes = [vp, vp, C.c_size_t]
+    L.tloam_b200_map_import.argtypes = [vp, vp, C.c_size_t]
+    L.tloam_b200_get_map_origin.argtypes = [vp, dp]
+    L.tloam_b200_knn.argtypes = [vp, C.c_int, dp, C.c_size_t, C.c_double, C.c_int, ip, dp, ip]
+    L.tloam_b200_build_factors.argtypes = [vp, C.c_int, dp, ip, dp, C.c_size_t]
+    L.tloam_b200_eval_point_to_point.argtypes = [vp, dp, C.c_size_t, dp, dp, dp, dp, dp, dp]
+    L.tloam_b200_eval_point_to_line.argtypes = [vp, dp, C.c_size_t, dp, dp, dp, dp, dp, dp, dp]
+    L.tloam_b200_eval_point_to_plane.argtypes = [vp, dp, C.c_size_t, dp, dp, dp, dp, dp, dp, dp]
+    L.tloam_b200_se3_exp.argtypes = [vp, dp, dp]
+    L.tloam_b200_se3_log.argtypes = [vp, dp, dp]
+    L.tloam_b200_se3_plus.argtypes = [vp, dp, dp, dp]
+    L.tloam_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.tloam_b200_host_free.argtypes = [vp]
+    _lib = L
+    return L

@@ -1,0 +1,48 @@
+"""In-tree build of libtloam_b200.so (hand-written CUDA for sm_100a; no torch, no CPU fallback).
+
+    python -m tloam_b200.build [--force]
+
+nvcc cross-compiles here without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libtloam_b200.so")
+SOURCES = [os.path.join(CSRC, "tloam_b200.cu")]
+HEADERS = [os.path.join(CSRC, f) for f in ("registration.cuh", "solver.cuh", "map_grid.cuh", "se3.cuh")] + [
+    os.path.join(HERE, "..", "include", "tloam_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", LIB] + SOURCES
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose and (res.stdout or res.stderr):
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True,
+                extra=("-Xptxas", "-v") if "--ptxas" in sys.argv else ()))

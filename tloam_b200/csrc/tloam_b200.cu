@@ -1,0 +1,1200 @@
+// tloam_b200.cu -- kernels + C ABI of libtloam_b200.so (sm_100a). See include/tloam_b200.h for the boundary
+// and registration.cuh for the execution model.  No CPU fallback exists anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "registration.cuh"
+#include "solver.cuh"
+
+namespace tloam {
+
+// =================================================================================================
+// Map build kernels (voxel hash, once per set_target)
+// =================================================================================================
+struct MapBuildArgs {
+  const double* stage;          // AoS xyz of the 4 clouds, concatenated
+  unsigned stage_off[5];        // point offsets of each cloud in `stage`
+  unsigned char* blob;          // MapHeader + pts + tables
+  unsigned* slot_of;            // scratch [total]
+  unsigned* rank_of;            // scratch [total]
+};
+
+__device__ __forceinline__ int cloud_of_point(const MapBuildArgs& a, unsigned i) {
+  return (i >= a.stage_off[3]) ? 3 : (i >= a.stage_off[2]) ? 2 : (i >= a.stage_off[1]) ? 1 : 0;
+}
+
+__global__ void k_map_bbox(MapBuildArgs a) {
+  const unsigned total = a.stage_off[4];
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double v = a.stage[3ull * i + d];
+      mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+    MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(&h->bbox_enc[d], enc_ordered(mn[d]));
+      atomicMax(&h->bbox_enc[3 + d], enc_ordered(mx[d]));
+    }
+  }
+}
+
+// origin = integer-rounded centre of the bounding box (exactly representable; |rel| stays small so the
+// FP32 storage keeps ~8e-6 m resolution at 100 m)
+__global__ void k_map_origin(MapBuildArgs a) {
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  if (threadIdx.x < 3) {
+    const double lo = dec_ordered(h->bbox_enc[threadIdx.x]), hi = dec_ordered(h->bbox_enc[3 + threadIdx.x]);
+    h->origin[threadIdx.x] = (a.stage_off[4] > 0) ? rint(0.5 * (lo + hi)) : 0.0;
+  }
+}
+
+__device__ __forceinline__ float3 rel_of(const MapBuildArgs& a, const MapHeader* h, unsigned i) {
+  return make_float3((float)(a.stage[3ull * i] - h->origin[0]), (float)(a.stage[3ull * i + 1] - h->origin[1]),
+                     (float)(a.stage[3ull * i + 2] - h->origin[2]));
+}
+
+__global__ void k_map_insert(MapBuildArgs a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.stage_off[4]) return;
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  const int c = cloud_of_point(a, i);
+  const float3 r = rel_of(a, h, i);
+  const double inv = 1.0 / h->cell[c];
+  // cell of the STORED (FP32-rounded) coordinates, so that the 27-cell search is exact for what is stored
+  const int cx = (int)floor((double)r.x * inv), cy = (int)floor((double)r.y * inv), cz = (int)floor((double)r.z * inv);
+  const unsigned long long key = cell_key(cx, cy, cz);
+  uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
+  const unsigned mask = h->tsize[c] - 1u;
+  unsigned s = hash_key(key) & mask;
+  while (true) {
+    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&table[s]);
+    const unsigned long long prev = atomicCAS(kp, 0ull, key);
+    if (prev == 0ull || prev == key) break;
+    s = (s + 1u) & mask;
+  }
+  a.slot_of[i] = s;
+  a.rank_of[i] = atomicAdd(&table[s].w, 1u);
+}
+
+__global__ void k_map_offsets(MapBuildArgs a) {
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = 0;
+  while (c < 4 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
+  if (c >= 4) return;
+  uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
+  const unsigned cnt = table[s].w;
+  if (cnt > 0u) table[s].z = atomicAdd(&h->cursor[c], cnt);
+}
+
+__global__ void k_map_scatter(MapBuildArgs a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.stage_off[4]) return;
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  const int c = cloud_of_point(a, i);
+  const float3 r = rel_of(a, h, i);
+  const uint4* table = reinterpret_cast<const uint4*>(a.blob + h->table_off[c]);
+  float4* pts = reinterpret_cast<float4*>(a.blob + h->pts_off[c]);
+  const unsigned dst = table[a.slot_of[i]].z + a.rank_of[i];
+  pts[dst] = make_float4(r.x, r.y, r.z, __int_as_float((int)(i - a.stage_off[c])));
+}
+
+// AoS FP64 staging -> padded SoA feature arrays
+__global__ void k_stage_source(const double* stage, DeviceCtx ctx, double* px, double* py, double* pz, unsigned soff0,
+                               unsigned soff1, unsigned soff2, unsigned soff3) {
+  const int b = blockIdx.x;
+  const int c = cloud_of_block(ctx, b);
+  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  const int gi = ctx.pad_off[c] + il;
+  const unsigned soff = (c == 0) ? soff0 : (c == 1) ? soff1 : (c == 2) ? soff2 : soff3;
+  double x = 0, y = 0, z = 0;
+  if (il < ctx.n[c]) {
+    const double* p = stage + 3ull * (soff + il);
+    x = p[0]; y = p[1]; z = p[2];
+  }
+  px[gi] = x; py[gi] = y; pz[gi] = z;
+}
+
+// =================================================================================================
+// Frame kernels
+// =================================================================================================
+struct Predict { double m[16]; };
+
+// scanMatching prologue, ref: registration.cpp:879-886, 961-964, 1027-1033.
+__global__ void k_begin_frame(DeviceCtx ctx, Predict pr) {
+  // zero the trace
+  {
+    unsigned* w = reinterpret_cast<unsigned*>(ctx.stats);
+    for (unsigned i = threadIdx.x; i < sizeof(tloam_b200_stats) / 4; i += blockDim.x) w[i] = 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  FrameState* st = ctx.st;
+  st->status = TLOAM_B200_OK;
+  st->frame_done = 0;
+  *ctx.counter = 0u;
+  for (int i = 0; i < 16; ++i) st->last_pose[i] = st->curr_pose[i];            // :882
+  Pose7 p;
+  if (!pose_from_matrix(pr.m, p)) {
+    st->status = TLOAM_B200_ERR_BAD_POSE;
+    for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
+    st->frame_done = 1;
+    return;
+  }
+  se3_log(p, st->x);                                                            // :881
+  const double wn = sqrt(st->x[3] * st->x[3] + st->x[4] * st->x[4] + st->x[5] * st->x[5]);
+  if (wn < 1e-2) {                                                              // :884-886 (explicit direction)
+    const double* d = ctx.reinit_dir;
+    const double nn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int j = 0; j < 3; ++j) st->x[3 + j] = d[j] / nn * 1e-4;
+  }
+  for (int i = 0; i < 6; ++i) ctx.stats->x_init[i] = st->x[i];
+  st->xq = se3_exp(st->x);
+  st->evalq = st->xq;
+  st->phase = kPhaseIter0;
+  st->outer = 0;
+  st->planar_prev = __longlong_as_double(0x7FF0000000000000ll);                 // +inf, :956
+  double c2 = ctx.noise_bound * ctx.noise_bound;                                // :962-964
+  if (c2 < 1e-16) c2 = 1e-2;
+  st->c2 = c2;
+  // :1027-1033 -- mu is derived from the residual slots BEFORE the first solve, when they are all zero
+  const double max_residual = 0.0;
+  double mu = 1.0 / (2.0 * max_residual / c2 - 1.0);
+  if (mu <= 0.0) mu = 1e-10;
+  st->mu = mu; st->mu_used = mu; st->th1 = 0.0; st->th2 = 0.0;
+  for (int k = 0; k < 4; ++k) st->slot_sum[k] = 0.0;
+}
+
+// One feature of one cloud: GNC weight update (lazy), T*p, kNN, primitive fit.
+// ref: registration.cpp:440-493 (edge), 531-551 (sphere), 584-625 (planar), 727-768 (ground), 858-876.
+__device__ __forceinline__ unsigned char correspond_one(const DeviceCtx& ctx, int c, const Rt& T, double px, double py,
+                                                        double pz, double prim[6]) {
+  double qx, qy, qz;
+  rt_apply(T, px, py, pz, qx, qy, qz);
+  const double rx = qx - ctx.origin[0], ry = qy - ctx.origin[1], rz = qz - ctx.origin[2];
+  const GridDesc& g = ctx.grid[c];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) prim[j] = 0.0;
+  if (c == kSphere) {
+    TopK<1> t;
+    knn_search<1>(g, rx, ry, rz, ctx.r2[c], t);
+    if (t.pos[0] < 0) return kFlagCounted;                 // not found: sphere_sum++ (:551)
+    if (t.d2[0] > 0.2) return 0;                           // squared distance vs 0.2, `continue` (:536)
+    const float4 m = __ldg(&g.pts[t.pos[0]]);
+    prim[0] = ctx.origin[0] + (double)m.x; prim[1] = ctx.origin[1] + (double)m.y; prim[2] = ctx.origin[2] + (double)m.z;
+    return kFlagCand | kFlagCounted;
+  }
+  TopK<5> t;
+  knn_search<5>(g, rx, ry, rz, ctx.r2[c], t);
+  const int k = t.count();
+  if (k <= 0) return 0;
+  double nb[5][3];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (j < k) {
+      const float4 m = __ldg(&g.pts[t.pos[j]]);
+      nb[j][0] = ctx.origin[0] + (double)m.x; nb[j][1] = ctx.origin[1] + (double)m.y; nb[j][2] = ctx.origin[2] + (double)m.z;
+    } else {
+      nb[j][0] = nb[j][1] = nb[j][2] = 0.0;
+    }
+  }
+  if (c == kEdge) {
+    if (k <= 3) return 0;                                  // :445
+    // mean + covariance from raw cumulants (:451-474)
+    double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < k; ++j) {
+      const double x = nb[j][0], y = nb[j][1], z = nb[j][2];
+      cu[0] += x; cu[1] += y; cu[2] += z;
+      cu[3] += x * x; cu[4] += x * y; cu[5] += x * z; cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
+    }
+    const double kn = (double)k;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) cu[j] /= kn;
+    double ev[3], dir[3];
+    sym_eig3_max(cu[3] - cu[0] * cu[0], cu[4] - cu[0] * cu[1], cu[5] - cu[0] * cu[2], cu[6] - cu[1] * cu[1],
+                 cu[7] - cu[1] * cu[2], cu[8] - cu[2] * cu[2], ev, dir);
+    if (!(ev[2] > 3.0 * ev[1] && fabs(dir[2]) > ctx.edge_dir_thres)) return 0;   // :481
+    prim[0] = 0.1 * dir[0] + cu[0]; prim[1] = 0.1 * dir[1] + cu[1]; prim[2] = 0.1 * dir[2] + cu[2];
+    prim[3] = -0.1 * dir[0] + cu[0]; prim[4] = -0.1 * dir[1] + cu[1]; prim[5] = -0.1 * dir[2] + cu[2];
+    return kFlagCand | kFlagCounted;                        // edge_num++ (:492)
+  }
+  if (k <= 4) return 0;                                     // :589 / :732
+  double nd[4];
+  fit_best_plane(nb, 5, nd);                                // :600 / :743
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+    if (nd[0] * nb[j][0] + nd[1] * nb[j][1] + nd[2] * nb[j][2] + nd[3] > 0.2) return 0;   // one-sided, :605-613
+  prim[0] = nd[0]; prim[1] = nd[1]; prim[2] = nd[2]; prim[3] = nd[3];
+  return kFlagCand | kFlagCounted;                          // surf_num++ / ground_num++
+}
+
+__global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ DeviceCtx ctx) {
+  const FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != kPhaseIter0) return;
+  const int b = blockIdx.x;
+  const int c = cloud_of_block(ctx, b);
+  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  const int gi = ctx.pad_off[c] + il;
+  const bool live = (il < ctx.n[c]) && cloud_enabled(ctx, c);
+  unsigned char flag = 0;
+  if (live) {
+    // lazy updateWeight of the previous outer iteration (:858-876) + slot reset (:1118-1121)
+    if (st->outer == 0) {
+      ctx.w[gi] = 1.0;                                                            // :931-949
+    } else {
+      const double res = ctx.slot[gi];
+      if (res != 0.0) {
+        double wv;
+        if (res >= st->th1) wv = 0.0;
+        else if (res <= st->th2) wv = 1.0;
+        else wv = sqrt(st->c2 * st->mu_used * (st->mu_used + 1.0) / res) - st->mu_used;
+        ctx.w[gi] = wv;
+      }
+    }
+    ctx.slot[gi] = 0.0;
+    const Rt T = pose_to_rt(st->xq);
+    double prim[6];
+    flag = correspond_one(ctx, c, T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], prim);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ctx.prim[j][gi] = prim[j];
+  }
+  ctx.flags[gi] = flag;
+  const int cnt = __syncthreads_count((flag & kFlagCounted) != 0);
+  if (threadIdx.x == 0) ctx.blk_count[b] = cnt;
+}
+
+// `*_maxnum` caps in feature-index order (Q8): factor i is active iff it is a candidate and the number of
+// counted features before it is < maxnum (the reference `return`s at the first cap-checked feature
+// after the counter reached the cap, ref: :448-449, 538-539, 592-593, 735-736).
+__device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int c, unsigned char flag, int* s_warp) {
+  // counted features in previous blocks of this cloud
+  int before = 0;
+  if (threadIdx.x < 32) {
+    for (int bb = ctx.blk_off[c] + (int)threadIdx.x; bb < b; bb += 32) before += ctx.blk_count[bb];
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, (flag & kFlagCounted) != 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[1 + warp] = __popc(ballot);
+  if (threadIdx.x == 0) s_warp[0] = before;
+  __syncthreads();
+  int prefix = s_warp[0];
+  for (int wi = 0; wi < warp; ++wi) prefix += s_warp[1 + wi];
+  prefix += __popc(ballot & ((1u << lane) - 1u));
+  return (flag & kFlagCand) && (prefix < ctx.maxnum[c]);
+}
+
+template <bool kFirst>
+__global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
+  FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;
+  __shared__ double s_red[kBlk / 32][30];
+  __shared__ double s_tot[kNRed];
+  __shared__ int s_warp[1 + kBlk / 32];
+  __shared__ bool s_last;
+  const int b = blockIdx.x;
+  const int c = cloud_of_block(ctx, b);
+  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  const int gi = ctx.pad_off[c] + il;
+  bool act;
+  if (kFirst) {
+    act = compute_active(ctx, b, c, ctx.flags[gi], s_warp);
+    ctx.active[gi] = act ? 1 : 0;
+  } else {
+    act = ctx.active[gi] != 0;
+  }
+  // per-thread contribution: H (21), g (6), cost, slot, count
+  double v[30];
+#pragma unroll
+  for (int i = 0; i < 30; ++i) v[i] = 0.0;
+  if (act) {
+    const Rt T = pose_to_rt(st->evalq);
+    double cpt[3];
+    rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], cpt[0], cpt[1], cpt[2]);
+    const double w = ctx.w[gi];
+    double r[3], J[18];
+    int nr;
+    double slot;
+    if (c == kPlanar || c == kGround) {
+      const double n[3] = {ctx.prim[0][gi], ctx.prim[1][gi], ctx.prim[2][gi]};
+      functor_plane(cpt, n, ctx.prim[3][gi], w, r[0], J);
+      nr = 1;
+      slot = r[0] * r[0];                                                    // :101
+    } else if (c == kEdge) {
+      const double a[3] = {ctx.prim[0][gi], ctx.prim[1][gi], ctx.prim[2][gi]};
+      const double bb[3] = {ctx.prim[3][gi], ctx.prim[4][gi], ctx.prim[5][gi]};
+      functor_line(cpt, a, bb, w, r, J);
+      nr = 3;
+      const double s3 = r[0] + r[1] + r[2];
+      slot = s3 * s3;                                                        // :69 (Q3)
+    } else {
+      const double q[3] = {ctx.prim[0][gi], ctx.prim[1][gi], ctx.prim[2][gi]};
+      functor_point(cpt, q, w, r, J);
+      nr = 3;
+      const double s3 = r[0] + r[1] + r[2];
+      slot = s3 * s3;                                                        // :32 (Q3)
+    }
+    ctx.slot[gi] = slot;                                                     // *cost side effect (Q5)
+    double sq = 0.0;
+    for (int k = 0; k < nr; ++k) sq += r[k] * r[k];
+    // CauchyLoss(1.0): rho = log(1+s), rho' = 1/(1+s), rho'' < 0 => residual and Jacobian scaled by sqrt(rho')
+    const double sum = 1.0 + sq;
+    const double rho1 = fmax(DBL_MIN, 1.0 / sum);
+    const double sc = sqrt(rho1);
+    v[27] = 0.5 * log(sum);
+    v[28] = slot;
+    v[29] = 1.0;
+    for (int k = 0; k < nr; ++k) {
+      double row[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) row[j] = J[k * 6 + j] * sc;
+      const double rk = r[k] * sc;
+      int t = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = i; j < 6; ++j) v[t++] += row[i] * row[j];
+        v[21 + i] += row[i] * rk;
+      }
+    }
+  }
+  // ---- block reduction (fixed shape => run-to-run bit-reproducible) ----
+#pragma unroll
+  for (int i = 0; i < 30; ++i)
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 30; ++i) s_red[warp][i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNRed) {
+    const int t = threadIdx.x;
+    double s = 0.0;
+    if (t < 28) {
+      for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][t];
+    } else if (t < 32) {
+      if (t - 28 == c) for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][28];
+    } else {
+      if (t - 32 == c) for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][29];
+    }
+    ctx.partial[(size_t)b * kNRed + t] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(ctx.counter, 1u);
+    s_last = (ticket == gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last block: deterministic sum of the per-block partials, then the solver state machine ----
+  __threadfence();
+  if (threadIdx.x < kNRed) {
+    const int t = threadIdx.x;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const int nb = gridDim.x;
+    int bb = 0;
+    for (; bb + 3 < nb; bb += 4) {
+      a0 += ctx.partial[(size_t)(bb + 0) * kNRed + t];
+      a1 += ctx.partial[(size_t)(bb + 1) * kNRed + t];
+      a2 += ctx.partial[(size_t)(bb + 2) * kNRed + t];
+      a3 += ctx.partial[(size_t)(bb + 3) * kNRed + t];
+    }
+    for (; bb < nb; ++bb) a0 += ctx.partial[(size_t)bb * kNRed + t];
+    s_tot[t] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *ctx.counter = 0u;
+    solver_on_eval(ctx, s_tot);
+  }
+}
+
+// ---- standalone caps kernel (used by the build_factors test entry point) ----
+__global__ void __launch_bounds__(kBlk) k_caps(const __grid_constant__ DeviceCtx ctx) {
+  __shared__ int s_warp[1 + kBlk / 32];
+  const int b = blockIdx.x;
+  const int c = cloud_of_block(ctx, b);
+  const int gi = ctx.pad_off[c] + (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  ctx.active[gi] = compute_active(ctx, b, c, ctx.flags[gi], s_warp) ? 1 : 0;
+}
+
+__global__ void k_set_pose(DeviceCtx ctx, Predict x6) {   // x6.m[0..5] = tangent
+  if (threadIdx.x != 0) return;
+  FrameState* st = ctx.st;
+  for (int i = 0; i < 6; ++i) st->x[i] = x6.m[i];
+  st->xq = se3_exp(st->x);
+  st->evalq = st->xq;
+  st->frame_done = 0; st->phase = kPhaseIter0; st->outer = 0; st->status = 0;
+}
+
+// ---- piecewise test kernels ----
+template <int K>
+__global__ void k_knn(GridDesc g, const double* origin, const double* q, unsigned nq, double r2, int* idx,
+                      double* d2, int* count) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  TopK<K> t;
+  knn_search<K>(g, q[3ull * i] - origin[0], q[3ull * i + 1] - origin[1], q[3ull * i + 2] - origin[2], r2, t);
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    idx[(size_t)i * K + j] = (t.pos[j] >= 0) ? t.idx[j] : -1;
+    d2[(size_t)i * K + j] = t.d2[j];
+  }
+  count[i] = t.count();
+}
+
+// getFitnessScore, ref: registration.cpp:257-296: 1-NN of the UNTRANSFORMED scan points within fitness_thres.
+__global__ void __launch_bounds__(kBlk) k_fitness(const __grid_constant__ DeviceCtx ctx, double r2, double* out /*[blocks][2]*/) {
+  const int b = blockIdx.x;
+  const int c = cloud_of_block(ctx, b);
+  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  const int gi = ctx.pad_off[c] + il;
+  double err = 0.0, cnt = 0.0;
+  if (il < ctx.n[c]) {
+    TopK<1> t;
+    knn_search<1>(ctx.grid[c], ctx.px[gi] - ctx.origin[0], ctx.py[gi] - ctx.origin[1], ctx.pz[gi] - ctx.origin[2], r2, t);
+    if (t.pos[0] >= 0) { err = t.d2[0]; cnt = 1.0; }
+  }
+  __shared__ double s_e[kBlk / 32], s_c[kBlk / 32];
+  for (int o = 16; o > 0; o >>= 1) { err += __shfl_xor_sync(0xffffffffu, err, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if ((threadIdx.x & 31) == 0) { s_e[threadIdx.x >> 5] = err; s_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0, n = 0;
+    for (int wi = 0; wi < kBlk / 32; ++wi) { e += s_e[wi]; n += s_c[wi]; }
+    out[2 * b] = e; out[2 * b + 1] = n;
+  }
+}
+
+__global__ void k_functor(int type, Predict x6, unsigned m, const double* p, const double* a, const double* bq,
+                          const double* w, double* r, double* J, double* cost) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const Rt T = pose_to_rt(se3_exp(x6.m));
+  double c[3];
+  rt_apply(T, p[3ull * i], p[3ull * i + 1], p[3ull * i + 2], c[0], c[1], c[2]);
+  if (type == 0) {          // point-to-point: a = target q
+    double rr[3], JJ[18];
+    const double q[3] = {a[3ull * i], a[3ull * i + 1], a[3ull * i + 2]};
+    functor_point(c, q, w[i], rr, JJ);
+    for (int k = 0; k < 3; ++k) r[3ull * i + k] = rr[k];
+    for (int k = 0; k < 18; ++k) J[18ull * i + k] = JJ[k];
+    cost[i] = (rr[0] + rr[1] + rr[2]) * (rr[0] + rr[1] + rr[2]);
+  } else if (type == 1) {   // point-to-line: a, bq = line points
+    double rr[3], JJ[18];
+    const double la[3] = {a[3ull * i], a[3ull * i + 1], a[3ull * i + 2]};
+    const double lb[3] = {bq[3ull * i], bq[3ull * i + 1], bq[3ull * i + 2]};
+    functor_line(c, la, lb, w[i], rr, JJ);
+    for (int k = 0; k < 3; ++k) r[3ull * i + k] = rr[k];
+    for (int k = 0; k < 18; ++k) J[18ull * i + k] = JJ[k];
+    cost[i] = (rr[0] + rr[1] + rr[2]) * (rr[0] + rr[1] + rr[2]);
+  } else {                  // point-to-plane: a = normal, bq = d
+    double rr, JJ[6];
+    const double n[3] = {a[3ull * i], a[3ull * i + 1], a[3ull * i + 2]};
+    functor_plane(c, n, bq[i], w[i], rr, JJ);
+    r[i] = rr;
+    for (int k = 0; k < 6; ++k) J[6ull * i + k] = JJ[k];
+    cost[i] = rr * rr;
+  }
+}
+
+__global__ void k_se3(int op, Predict in, double* out) {
+  if (threadIdx.x != 0) return;
+  if (op == 0) { pose_to_matrix(se3_exp(in.m), out); }
+  else if (op == 1) { Pose7 p; const bool ok = pose_from_matrix(in.m, p); se3_log(p, out); out[6] = ok ? 1.0 : 0.0; }
+  else { se3_log(se3_mul(se3_exp(in.m + 6), se3_exp(in.m)), out); }   // plus: in.m[0..5] = x, in.m[6..11] = delta
+}
+
+}  // namespace tloam
+
+// =================================================================================================
+// Host side: handle + C ABI
+// =================================================================================================
+using namespace tloam;
+
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      snprintf(h->last_error, sizeof(h->last_error), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+               __FILE__, __LINE__);                                                                    \
+      return TLOAM_B200_ERR_CUDA;                                                                      \
+    }                                                                                                  \
+  } while (0)
+
+struct tloam_b200_handle {
+  tloam_tls_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  char last_error[512] = {0};
+  long long launches = 0;
+  int launches_frame = 0;
+  // source
+  size_t n_src[4] = {0, 0, 0, 0};
+  bool have_src = false, have_tgt = false, frame_pending = false;
+  double* d_stage_src = nullptr; size_t cap_stage_src = 0;      // points
+  double* d_feat = nullptr; size_t cap_pad = 0;                 // 3 + 2 + 6 arrays of cap_pad doubles
+  unsigned char* d_flags = nullptr;                             // flags + active
+  int* d_blk_count = nullptr; double* d_partial = nullptr; size_t cap_blocks = 0;
+  unsigned* d_counter = nullptr;
+  FrameState* d_state = nullptr;
+  tloam_b200_stats* d_stats = nullptr;
+  // target
+  size_t n_tgt[4] = {0, 0, 0, 0};
+  double* d_stage_tgt = nullptr; size_t cap_stage_tgt = 0;
+  unsigned* d_scratch = nullptr; size_t cap_scratch = 0;        // slot_of + rank_of
+  unsigned char* d_blob = nullptr; size_t cap_blob = 0, blob_bytes = 0;
+  MapHeader hdr;                                                // host copy of the layout (origin filled lazily)
+  bool origin_known = false;
+  // pinned host staging for results
+  double* h_result = nullptr;                                   // 16 result + 2 (status, done)
+  tloam_b200_stats* h_stats = nullptr;
+  DeviceCtx ctx;
+  int total_blocks = 0;
+};
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+extern "C" {
+
+void tloam_b200_default_config(tloam_tls_config* c) {   // ref: config/mapping/lidar_odometry.yaml:23-39
+  c->k_corr = 10; c->factor_num = 4;
+  c->edge_dist_thres = 1.0; c->sphere_dist_thres = 0.5; c->planar_dist_thres = 0.5; c->ground_dist_thres = 0.5;
+  c->edge_dir_thres = 0.85;
+  c->edge_maxnum = 1200; c->sphere_maxnum = 200; c->planar_maxnum = 2500; c->ground_maxnum = 2000;
+  c->max_iterations = 4; c->cost_threshold = 0.000000005; c->gnc_factor = 11.8; c->noise_bound = 0.01;
+  c->fitness_thres = 0.02;
+  c->ceres_max_num_iterations = 4;
+  c->reinit_dir[0] = 1.0; c->reinit_dir[1] = 1.0; c->reinit_dir[2] = 1.0;
+}
+
+const char* tloam_b200_status_string(int s) {
+  switch (s) {
+    case TLOAM_B200_OK: return "ok";
+    case TLOAM_B200_ERR_INVALID_ARG: return "invalid argument";
+    case TLOAM_B200_ERR_TOO_FEW_POINTS: return "a cloud has fewer than 10 points";
+    case TLOAM_B200_ERR_BAD_POSE: return "predicted pose is not a rigid transform";
+    case TLOAM_B200_ERR_CUDA: return "CUDA error";
+    case TLOAM_B200_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case TLOAM_B200_ERR_NOT_READY: return "source or target not set";
+    case TLOAM_B200_ERR_NUMERIC: return "non-finite value in the solve";
+    default: return "unknown status";
+  }
+}
+
+static double radius_of(const tloam_tls_config& c, int cloud) {
+  return cloud == 0 ? c.edge_dist_thres : cloud == 1 ? c.sphere_dist_thres : cloud == 2 ? c.planar_dist_thres : c.ground_dist_thres;
+}
+
+int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tloam_b200_handle** out) {
+  if (!cfg || !out) return TLOAM_B200_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->factor_num < 2 || cfg->factor_num > 4 || cfg->max_iterations < 1 ||
+      cfg->max_iterations > TLOAM_B200_MAX_OUTER || cfg->ceres_max_num_iterations < 0 ||
+      cfg->ceres_max_num_iterations > TLOAM_B200_MAX_INNER)
+    return TLOAM_B200_ERR_INVALID_ARG;
+  for (int c = 0; c < 4; ++c) if (!(radius_of(*cfg, c) > 0.0)) return TLOAM_B200_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return TLOAM_B200_ERR_NO_DEVICE;
+  }
+  tloam_b200_handle* h = new (std::nothrow) tloam_b200_handle();
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  h->cfg = *cfg;
+  h->device = device;
+  auto fail = [&](int code) { tloam_b200_destroy(h); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+    h->own_stream = true;
+  }
+  if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMalloc(&h->d_state, sizeof(FrameState)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMalloc(&h->d_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMalloc(&h->d_counter, 256) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMallocHost(&h->h_result, 32 * sizeof(double)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMallocHost(&h->h_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
+  FrameState init;
+  memset(&init, 0, sizeof(init));
+  for (int i = 0; i < 16; ++i) init.curr_pose[i] = init.last_pose[i] = init.result[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  init.frame_done = 1;
+  if (cudaMemcpy(h->d_state, &init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMemset(h->d_counter, 0, 256) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  memset(&h->ctx, 0, sizeof(h->ctx));
+  memset(&h->hdr, 0, sizeof(h->hdr));
+  *out = h;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_destroy(tloam_b200_handle* h) {
+  if (!h) return TLOAM_B200_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_stage_src); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
+  cudaFree(h->d_partial); cudaFree(h->d_counter); cudaFree(h->d_state); cudaFree(h->d_stats);
+  cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob);
+  if (h->h_result) cudaFreeHost(h->h_result);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return TLOAM_B200_OK;
+}
+
+// fills the configuration part of the device context
+static void fill_ctx_config(tloam_b200_handle* h) {
+  DeviceCtx& c = h->ctx;
+  const tloam_tls_config& f = h->cfg;
+  for (int k = 0; k < 4; ++k) { const double r = radius_of(f, k); c.r2[k] = r * r; }
+  c.maxnum[0] = f.edge_maxnum; c.maxnum[1] = f.sphere_maxnum; c.maxnum[2] = f.planar_maxnum; c.maxnum[3] = f.ground_maxnum;
+  c.factor_num = f.factor_num; c.max_iterations = f.max_iterations; c.ceres_max_it = f.ceres_max_num_iterations;
+  c.edge_dir_thres = f.edge_dir_thres; c.cost_threshold = f.cost_threshold; c.gnc_factor = f.gnc_factor;
+  c.noise_bound = f.noise_bound; c.fitness_thres = f.fitness_thres;
+  for (int k = 0; k < 3; ++k) c.reinit_dir[k] = f.reinit_dir[k];
+  c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;
+}
+
+static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
+  if (!h || !xyz || !n) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  size_t total = 0, pad = 0;
+  int blocks = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (n[c] > 0 && !xyz[c]) return TLOAM_B200_ERR_INVALID_ARG;
+    if (n[c] > (size_t)1 << 30) return TLOAM_B200_ERR_INVALID_ARG;
+    total += n[c];
+    pad += round_up(n[c], kBlk);
+  }
+  if (pad == 0) pad = kBlk;
+  blocks = (int)(pad / kBlk);
+  if (total > h->cap_stage_src) {
+    cudaFree(h->d_stage_src);
+    h->cap_stage_src = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_stage_src, h->cap_stage_src * 3 * sizeof(double)));
+  }
+  if (pad > h->cap_pad) {
+    cudaFree(h->d_feat); cudaFree(h->d_flags);
+    h->cap_pad = round_up(pad + pad / 4, kBlk);
+    CU_TRY(cudaMalloc(&h->d_feat, h->cap_pad * 11 * sizeof(double)));
+    CU_TRY(cudaMalloc(&h->d_flags, h->cap_pad * 2));
+  }
+  if ((size_t)blocks > h->cap_blocks) {
+    cudaFree(h->d_blk_count); cudaFree(h->d_partial);
+    h->cap_blocks = h->cap_pad / kBlk + 8;
+    CU_TRY(cudaMalloc(&h->d_blk_count, h->cap_blocks * sizeof(int)));
+    CU_TRY(cudaMalloc(&h->d_partial, h->cap_blocks * kNRed * sizeof(double)));
+  }
+  DeviceCtx& c = h->ctx;
+  fill_ctx_config(h);
+  size_t off = 0, poff = 0;
+  unsigned soff[4];
+  c.blk_off[0] = 0;
+  for (int k = 0; k < 4; ++k) {
+    soff[k] = (unsigned)off;
+    if (n[k] > 0)
+      CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    c.n[k] = (int)n[k];
+    c.pad_off[k] = (int)poff;
+    off += n[k];
+    poff += round_up(n[k], kBlk);
+    c.blk_off[k + 1] = (int)(poff / kBlk);
+    h->n_src[k] = n[k];
+  }
+  double* f = h->d_feat;
+  const size_t cp = h->cap_pad;
+  c.px = f; c.py = f + cp; c.pz = f + 2 * cp; c.w = f + 3 * cp; c.slot = f + 4 * cp;
+  for (int j = 0; j < 6; ++j) c.prim[j] = f + (5 + j) * cp;
+  c.flags = h->d_flags; c.active = h->d_flags + cp;
+  c.blk_count = h->d_blk_count; c.partial = h->d_partial;
+  h->total_blocks = c.blk_off[4];
+  if (h->total_blocks > 0) {
+    k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(h->d_stage_src, c, f, f + cp, f + 2 * cp, soff[0], soff[1], soff[2], soff[3]);
+    h->launches++;
+    CU_TRY(cudaGetLastError());
+  }
+  h->have_src = true;
+  if (!on_device) CU_TRY(cudaStreamSynchronize(h->stream));   // caller buffers may be freed on return
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_set_source(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]) {
+  return set_source_impl(h, xyz, n, false);
+}
+int tloam_b200_set_source_device(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]) {
+  return set_source_impl(h, xyz, n, true);
+}
+
+static unsigned next_pow2(size_t v) { unsigned p = 64; while ((size_t)p < v) p <<= 1; return p; }
+
+static int layout_map(tloam_b200_handle* h, const size_t n[4]) {
+  MapHeader& hd = h->hdr;
+  memset(&hd, 0, sizeof(hd));
+  hd.magic = kMapMagic;
+  size_t off = sizeof(MapHeader);
+  for (int c = 0; c < 4; ++c) {
+    hd.n[c] = (unsigned)n[c];
+    hd.tsize[c] = next_pow2(2 * n[c] + 1);
+    hd.cell[c] = radius_of(h->cfg, c);
+    hd.pts_off[c] = off; off += round_up(n[c] * sizeof(float4), 256);
+  }
+  for (int c = 0; c < 4; ++c) { hd.table_off[c] = off; off += (size_t)hd.tsize[c] * sizeof(uint4); }
+  for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
+  h->blob_bytes = off;
+  if (off > h->cap_blob) {
+    cudaFree(h->d_blob);
+    h->cap_blob = off + off / 4;
+    CU_TRY(cudaMalloc(&h->d_blob, h->cap_blob));
+  }
+  return TLOAM_B200_OK;
+}
+
+static void bind_map(tloam_b200_handle* h) {
+  DeviceCtx& c = h->ctx;
+  for (int k = 0; k < 4; ++k) {
+    c.grid[k].pts = reinterpret_cast<const float4*>(h->d_blob + h->hdr.pts_off[k]);
+    c.grid[k].table = reinterpret_cast<const uint4*>(h->d_blob + h->hdr.table_off[k]);
+    c.grid[k].mask = h->hdr.tsize[k] - 1u;
+    c.grid[k].n = h->hdr.n[k];
+    c.grid[k].cell = h->hdr.cell[k];
+    c.grid[k].inv_cell = 1.0 / h->hdr.cell[k];
+  }
+  c.origin = reinterpret_cast<const double*>(h->d_blob + offsetof(MapHeader, origin));
+}
+
+// the origin lives in the device header; fetch it once per map (tiny D2H) so that it can be passed by value
+static int fetch_origin(tloam_b200_handle* h) {
+  if (h->origin_known) return TLOAM_B200_OK;
+  CU_TRY(cudaMemcpyAsync(h->h_result + 24, h->d_blob + offsetof(MapHeader, origin), 3 * sizeof(double),
+                         cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  for (int d = 0; d < 3; ++d) h->hdr.origin[d] = h->h_result[24 + d];
+  h->origin_known = true;
+  return TLOAM_B200_OK;
+}
+
+static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
+  if (!h || !xyz || !n) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  size_t total = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (n[c] > 0 && !xyz[c]) return TLOAM_B200_ERR_INVALID_ARG;
+    if (n[c] > (size_t)1 << 30) return TLOAM_B200_ERR_INVALID_ARG;
+    total += n[c];
+  }
+  if (total > h->cap_stage_tgt) {
+    cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch);
+    h->cap_stage_tgt = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_stage_tgt, h->cap_stage_tgt * 3 * sizeof(double)));
+    CU_TRY(cudaMalloc(&h->d_scratch, h->cap_stage_tgt * 2 * sizeof(unsigned)));
+  }
+  int rc = layout_map(h, n);
+  if (rc != TLOAM_B200_OK) return rc;
+  MapBuildArgs a;
+  a.stage = h->d_stage_tgt; a.blob = h->d_blob; a.slot_of = h->d_scratch; a.rank_of = h->d_scratch + h->cap_stage_tgt;
+  size_t off = 0;
+  for (int c = 0; c < 4; ++c) {
+    a.stage_off[c] = (unsigned)off;
+    if (n[c] > 0)
+      CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * off, xyz[c], n[c] * 3 * sizeof(double),
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    off += n[c];
+    h->n_tgt[c] = n[c];
+  }
+  a.stage_off[4] = (unsigned)off;
+  // header + zeroed tables (key 0 == empty)
+  CU_TRY(cudaMemcpyAsync(h->d_blob, &h->hdr, sizeof(MapHeader), cudaMemcpyHostToDevice, h->stream));
+  const size_t tables_bytes = h->blob_bytes - h->hdr.table_off[0];
+  CU_TRY(cudaMemsetAsync(h->d_blob + h->hdr.table_off[0], 0, tables_bytes, h->stream));
+  if (total > 0) {
+    const unsigned tb = 256;
+    const unsigned gb = (unsigned)((total + tb - 1) / tb);
+    unsigned tslots = 0;
+    for (int c = 0; c < 4; ++c) tslots += h->hdr.tsize[c];
+    k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a);
+    k_map_origin<<<1, 32, 0, h->stream>>>(a);
+    k_map_insert<<<gb, tb, 0, h->stream>>>(a);
+    k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(a);
+    k_map_scatter<<<gb, tb, 0, h->stream>>>(a);
+    h->launches += 5;
+    CU_TRY(cudaGetLastError());
+  } else {
+    k_map_origin<<<1, 32, 0, h->stream>>>(a);
+    h->launches += 1;
+  }
+  bind_map(h);
+  h->origin_known = false;
+  h->have_tgt = true;
+  if (!on_device) CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_set_target(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]) {
+  return set_target_impl(h, xyz, n, false);
+}
+int tloam_b200_set_target_device(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]) {
+  return set_target_impl(h, xyz, n, true);
+}
+
+int tloam_b200_get_map_origin(tloam_b200_handle* h, double origin[3]) {
+  if (!h || !origin) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  CU_TRY(cudaSetDevice(h->device));
+  int rc = fetch_origin(h);
+  if (rc != TLOAM_B200_OK) return rc;
+  for (int d = 0; d < 3; ++d) origin[d] = h->hdr.origin[d];
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_map_blob_size(tloam_b200_handle* h, size_t* bytes) {
+  if (!h || !bytes) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  *bytes = h->blob_bytes;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_map_export(tloam_b200_handle* h, void* d_dst, size_t bytes) {
+  if (!h || !d_dst) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  if (bytes < h->blob_bytes) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaMemcpyAsync(d_dst, h->d_blob, h->blob_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes) {
+  if (!h || !d_src || bytes < sizeof(MapHeader)) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  MapHeader hd;
+  CU_TRY(cudaMemcpy(&hd, d_src, sizeof(hd), cudaMemcpyDeviceToHost));
+  if (hd.magic != kMapMagic) return TLOAM_B200_ERR_INVALID_ARG;
+  size_t need = hd.table_off[3] + (size_t)hd.tsize[3] * sizeof(uint4);
+  if (bytes < need) return TLOAM_B200_ERR_INVALID_ARG;
+  for (int c = 0; c < 4; ++c)
+    if (hd.cell[c] != radius_of(h->cfg, c)) return TLOAM_B200_ERR_INVALID_ARG;   // grid cell must equal this handle's radius
+  if (need > h->cap_blob) {
+    cudaFree(h->d_blob);
+    h->cap_blob = need + need / 4;
+    CU_TRY(cudaMalloc(&h->d_blob, h->cap_blob));
+  }
+  CU_TRY(cudaMemcpyAsync(h->d_blob, d_src, need, cudaMemcpyDeviceToDevice, h->stream));
+  h->hdr = hd;
+  h->blob_bytes = need;
+  for (int c = 0; c < 4; ++c) h->n_tgt[c] = hd.n[c];
+  fill_ctx_config(h);
+  bind_map(h);
+  h->origin_known = true;
+  h->have_tgt = true;
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+static int check_ready(tloam_b200_handle* h) {
+  if (!h->have_src || !h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  for (int c = 0; c < 4; ++c)
+    if (h->n_src[c] < 10 || h->n_tgt[c] < 10) return TLOAM_B200_ERR_TOO_FEW_POINTS;   // ref: :928-929
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) {
+  if (!h || !predict) return TLOAM_B200_ERR_INVALID_ARG;
+  const int rc = check_ready(h);
+  if (rc != TLOAM_B200_OK) return rc;
+  CU_TRY(cudaSetDevice(h->device));
+  Predict pr;
+  memcpy(pr.m, predict, sizeof(pr.m));
+  const DeviceCtx& c = h->ctx;
+  const int nb = h->total_blocks;
+  int launches = 0;
+  CU_TRY(cudaEventRecord(h->ev0, h->stream));
+  k_begin_frame<<<1, 256, 0, h->stream>>>(c, pr); ++launches;
+  for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
+    k_correspond<<<nb, kBlk, 0, h->stream>>>(c); ++launches;
+    k_eval<true><<<nb, kBlk, 0, h->stream>>>(c); ++launches;
+    for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it) { k_eval<false><<<nb, kBlk, 0, h->stream>>>(c); ++launches; }
+  }
+  CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
+                         cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->h_result + 16, (const char*)h->d_state + offsetof(FrameState, frame_done), 2 * sizeof(int),
+                         cudaMemcpyDeviceToHost, h->stream));
+  h->launches += launches;
+  h->launches_frame = launches;
+  h->frame_pending = true;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_stats* stats) {
+  if (!h || !result) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->frame_pending) return TLOAM_B200_ERR_NOT_READY;
+  CU_TRY(cudaSetDevice(h->device));
+  if (stats) CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(tloam_b200_stats), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->frame_pending = false;
+  memcpy(result, h->h_result, 16 * sizeof(double));
+  int flags[2];
+  memcpy(flags, h->h_result + 16, sizeof(flags));   // frame_done, status
+  if (stats) {
+    *stats = *h->h_stats;
+    stats->gpu_launches = h->launches_frame;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) stats->gpu_ms = ms;
+  }
+  if (flags[1] != TLOAM_B200_OK) return flags[1];
+  if (!flags[0]) { snprintf(h->last_error, sizeof(h->last_error), "frame did not complete"); return TLOAM_B200_ERR_CUDA; }
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double result[16], tloam_b200_stats* stats) {
+  int rc = tloam_b200_scan_match_async(h, predict);
+  if (rc != TLOAM_B200_OK) return rc;
+  return tloam_b200_get_result(h, result, stats);
+}
+
+int tloam_b200_synchronize(tloam_b200_handle* h) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+long long tloam_b200_launch_count(tloam_b200_handle* h) { return h ? h->launches : 0; }
+
+static int read_state_pose(tloam_b200_handle* h, size_t offset, double out[16]) {
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offset, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_result, 16 * sizeof(double));
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_get_transform(tloam_b200_handle* h, double pose[16]) {   // ref: registration.cpp:370-372
+  if (!h || !pose) return TLOAM_B200_ERR_INVALID_ARG;
+  return read_state_pose(h, offsetof(FrameState, curr_pose), pose);
+}
+
+int tloam_b200_get_pose_increment(tloam_b200_handle* h, double pose[16]) {   // ref: registration.cpp:374-376
+  if (!h || !pose) return TLOAM_B200_ERR_INVALID_ARG;
+  double L[16], C[16];
+  int rc = read_state_pose(h, offsetof(FrameState, last_pose), L);
+  if (rc != TLOAM_B200_OK) return rc;
+  rc = read_state_pose(h, offsetof(FrameState, curr_pose), C);
+  if (rc != TLOAM_B200_OK) return rc;
+  double Li[16];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Li[c * 4 + r] = L[r * 4 + c];
+  for (int r = 0; r < 3; ++r) Li[12 + r] = -(Li[0 * 4 + r] * L[12] + Li[1 * 4 + r] * L[13] + Li[2 * 4 + r] * L[14]);
+  Li[3] = Li[7] = Li[11] = 0.0; Li[15] = 1.0;
+  for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) {
+    double s = 0.0;
+    for (int k = 0; k < 4; ++k) s += Li[k * 4 + r] * C[c * 4 + k];
+    pose[c * 4 + r] = s;
+  }
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse) {
+  if (!h || !fitness || !rmse) return TLOAM_B200_ERR_INVALID_ARG;
+  *fitness = 0.0; *rmse = 0.0;
+  if (!h->have_src || !h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  if (h->cfg.fitness_thres <= 0.0) return TLOAM_B200_OK;                 // ref: :258-261
+  for (int c = 0; c < 4; ++c) if (h->cfg.fitness_thres > radius_of(h->cfg, c)) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  const int nb = h->total_blocks;
+  double* d_out = nullptr;
+  CU_TRY(cudaMalloc(&d_out, (size_t)nb * 2 * sizeof(double)));
+  k_fitness<<<nb, kBlk, 0, h->stream>>>(h->ctx, h->cfg.fitness_thres * h->cfg.fitness_thres, d_out);
+  h->launches++;
+  std::vector<double> out((size_t)nb * 2);
+  cudaError_t e = cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "fitness: %s", cudaGetErrorString(e)); return TLOAM_B200_ERR_CUDA; }
+  for (int c = 0; c < 4; ++c) {
+    double err = 0.0, cnt = 0.0;
+    for (int b = h->ctx.blk_off[c]; b < h->ctx.blk_off[c + 1]; ++b) { err += out[2 * b]; cnt += out[2 * b + 1]; }
+    if (cnt > 0.0) { *fitness += cnt / (double)h->n_src[c]; *rmse += sqrt(err / cnt); }   // ref: :278-284, 292-293
+  }
+  return TLOAM_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// piecewise entry points (tests)
+// ---------------------------------------------------------------------------------------------
+int tloam_b200_knn(tloam_b200_handle* h, int cloud, const double* queries, size_t nq, double radius, int k, int* idx,
+                   double* d2, int* count) {
+  if (!h || cloud < 0 || cloud > 3 || !queries || !idx || !d2 || !count) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  if (!(radius > 0.0) || radius > h->hdr.cell[cloud] || (k != 1 && k != 3 && k != 5)) return TLOAM_B200_ERR_INVALID_ARG;
+  if (nq == 0) return TLOAM_B200_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  double *dq = nullptr, *dd = nullptr; int *di = nullptr, *dc = nullptr;
+  cudaError_t e = cudaMalloc(&dq, nq * 3 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dd, nq * k * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&di, nq * k * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&dc, nq * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dq, queries, nq * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    const unsigned tb = 128, gb = (unsigned)((nq + tb - 1) / tb);
+    const GridDesc g = h->ctx.grid[cloud];
+    const double* o = h->ctx.origin;
+    if (k == 1) k_knn<1><<<gb, tb, 0, h->stream>>>(g, o, dq, (unsigned)nq, radius * radius, di, dd, dc);
+    else if (k == 3) k_knn<3><<<gb, tb, 0, h->stream>>>(g, o, dq, (unsigned)nq, radius * radius, di, dd, dc);
+    else k_knn<5><<<gb, tb, 0, h->stream>>>(g, o, dq, (unsigned)nq, radius * radius, di, dd, dc);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idx, di, nq * k * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d2, dd, nq * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(count, dc, nq * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(dq); cudaFree(dd); cudaFree(di); cudaFree(dc);
+  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "knn: %s", cudaGetErrorString(e)); return TLOAM_B200_ERR_CUDA; }
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6], int* valid, double* prim, size_t n) {
+  if (!h || cloud < 0 || cloud > 3 || !x || !valid || !prim) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->have_src || !h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  if (n != h->n_src[cloud]) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  Predict pr;
+  memset(&pr, 0, sizeof(pr));
+  memcpy(pr.m, x, 6 * sizeof(double));
+  DeviceCtx c = h->ctx;
+  c.factor_num = 4;   // build every cloud regardless of the configured subset
+  k_set_pose<<<1, 32, 0, h->stream>>>(c, pr);
+  k_correspond<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
+  k_caps<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
+  h->launches += 3;
+  CU_TRY(cudaGetLastError());
+  std::vector<unsigned char> act(n);
+  std::vector<double> col(n);
+  const size_t off = (size_t)h->ctx.pad_off[cloud];
+  CU_TRY(cudaMemcpyAsync(act.data(), h->ctx.active + off, n, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < n; ++i) valid[i] = act[i];
+  for (int j = 0; j < 6; ++j) {
+    CU_TRY(cudaMemcpyAsync(col.data(), h->ctx.prim[j] + off, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i) prim[6 * i + j] = act[i] ? col[i] : 0.0;
+  }
+  // leave the handle idle
+  int one = 1;
+  CU_TRY(cudaMemcpyAsync((char*)h->d_state + offsetof(FrameState, frame_done), &one, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+static int run_functor(tloam_b200_handle* h, int type, const double x[6], size_t m, const double* p, const double* a,
+                       const double* b, size_t b_stride, const double* w, double* r, size_t r_stride, double* J,
+                       size_t j_stride, double* cost) {
+  if (!h || !x || !p || !a || !b || !w || !r || !J || !cost) return TLOAM_B200_ERR_INVALID_ARG;
+  if (m == 0) return TLOAM_B200_OK;
+  CU_TRY(cudaSetDevice(h->device));
+  Predict pr;
+  memset(&pr, 0, sizeof(pr));
+  memcpy(pr.m, x, 6 * sizeof(double));
+  const size_t in_doubles = m * (3 + 3 + b_stride + 1), out_doubles = m * (r_stride + j_stride + 1);
+  double* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, (in_doubles + out_doubles) * sizeof(double));
+  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "functor: %s", cudaGetErrorString(e)); return TLOAM_B200_ERR_CUDA; }
+  double *dp = d, *da = dp + 3 * m, *db = da + 3 * m, *dw = db + b_stride * m, *dr = dw + m, *dJ = dr + r_stride * m, *dc = dJ + j_stride * m;
+  e = cudaMemcpyAsync(dp, p, 3 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(da, a, 3 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(db, b, b_stride * m * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dw, w, m * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    k_functor<<<(unsigned)((m + 127) / 128), 128, 0, h->stream>>>(type, pr, (unsigned)m, dp, da, db, dw, dr, dJ, dc);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r, dr, r_stride * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(J, dJ, j_stride * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cost, dc, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "functor: %s", cudaGetErrorString(e)); return TLOAM_B200_ERR_CUDA; }
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_eval_point_to_point(tloam_b200_handle* h, const double x[6], size_t m, const double* p, const double* q,
+                                   const double* w, double* r, double* J, double* cost) {
+  return run_functor(h, 0, x, m, p, q, q, 3, w, r, 3, J, 18, cost);
+}
+int tloam_b200_eval_point_to_line(tloam_b200_handle* h, const double x[6], size_t m, const double* p, const double* a,
+                                  const double* b, const double* w, double* r, double* J, double* cost) {
+  return run_functor(h, 1, x, m, p, a, b, 3, w, r, 3, J, 18, cost);
+}
+int tloam_b200_eval_point_to_plane(tloam_b200_handle* h, const double x[6], size_t m, const double* p, const double* n,
+                                   const double* d, const double* w, double* r, double* J, double* cost) {
+  return run_functor(h, 2, x, m, p, n, d, 1, w, r, 1, J, 6, cost);
+}
+
+static int run_se3(tloam_b200_handle* h, int op, const double* in, int nin, double* out, int nout, double* extra) {
+  if (!h || !in || !out) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  Predict pr;
+  memset(&pr, 0, sizeof(pr));
+  memcpy(pr.m, in, nin * sizeof(double));
+  double* d = nullptr;
+  CU_TRY(cudaMalloc(&d, 32 * sizeof(double)));
+  k_se3<<<1, 32, 0, h->stream>>>(op, pr, d);
+  h->launches++;
+  double tmp[32];
+  cudaError_t e = cudaMemcpyAsync(tmp, d, 32 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "se3: %s", cudaGetErrorString(e)); return TLOAM_B200_ERR_CUDA; }
+  memcpy(out, tmp, nout * sizeof(double));
+  if (extra) *extra = tmp[6];
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_se3_exp(tloam_b200_handle* h, const double a[6], double T[16]) { return run_se3(h, 0, a, 6, T, 16, nullptr); }
+int tloam_b200_se3_log(tloam_b200_handle* h, const double T[16], double a[6]) {
+  double ok = 1.0;
+  int rc = run_se3(h, 1, T, 16, a, 6, &ok);
+  if (rc != TLOAM_B200_OK) return rc;
+  return ok != 0.0 ? TLOAM_B200_OK : TLOAM_B200_ERR_BAD_POSE;
+}
+int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double delta[6], double out[6]) {
+  double in[12];
+  memcpy(in, x, 48); memcpy(in + 6, delta, 48);
+  return run_se3(h, 2, in, 12, out, 6, nullptr);
+}
+
+int tloam_b200_host_alloc(void** p, size_t bytes) {
+  if (!p) return TLOAM_B200_ERR_INVALID_ARG;
+  return cudaMallocHost(p, bytes) == cudaSuccess ? TLOAM_B200_OK : TLOAM_B200_ERR_CUDA;
+}
+int tloam_b200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? TLOAM_B200_OK : TLOAM_B200_ERR_CUDA; }
+
+const char* tloam_b200_last_error(tloam_b200_handle* h) { return h ? h->last_error : ""; }
+
+}  // extern "C"

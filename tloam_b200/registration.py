@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's registration interface, over the C-ABI CUDA library.
+
+`LocalRegistration` mirrors tloam::LocalRegistration / RegistrationInterface
+(ref: include/tloam/models/registration/registration_interface.hpp:40-48,
+      include/tloam/models/registration/registration.hpp:142-165): same method names
+(snake_case), same argument meaning, status codes instead of aborts.  It is a thin ctypes shell:
+all arithmetic happens in libtloam_b200.so on the GPU.  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+CLOUDS = ("edge", "sphere", "planar", "ground")  # ABI order (ref: registration.cpp:233-236)
+
+
+class RegistrationError(RuntimeError):
+    def __init__(self, status, where, detail=""):
+        self.status = status
+        msg = _lib.load().tloam_b200_status_string(status).decode()
+        super().__init__(f"{where}: {msg} (status {status}) {detail}")
+
+
+def default_config(**overrides):
+    """The "TLS:" block defaults (ref: config/mapping/lidar_odometry.yaml:23-39)."""
+    cfg = _lib.TlsConfig()
+    _lib.load().tloam_b200_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if k == "reinit_dir":
+            for i in range(3):
+                cfg.reinit_dir[i] = float(v[i])
+        else:
+            if not hasattr(cfg, k):
+                raise KeyError(k)
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Frame:
+    """Mirror of tloam::Frame (ref: registration_interface.hpp:19-38): the four feature clouds, (n,3) float64.
+    scan_cloud is accepted and ignored, as in the reference (registration.cpp:232-239)."""
+
+    def __init__(self, edge_feature, sphere_feature, planar_feature, ground_feature, scan_cloud=None):
+        self.edge_feature = edge_feature
+        self.sphere_feature = sphere_feature
+        self.planar_feature = planar_feature
+        self.ground_feature = ground_feature
+        self.scan_cloud = scan_cloud
+
+    def clouds(self):
+        return [self.edge_feature, self.sphere_feature, self.planar_feature, self.ground_feature]
+
+
+class LocalRegistration:
+    def __init__(self, config=None, device=0, stream=None, **overrides):
+        self._L = _lib.load()
+        self.cfg = config if config is not None else default_config(**overrides)
+        h = C.c_void_p()
+        rc = self._L.tloam_b200_create(C.byref(self.cfg), int(device), C.c_void_p(stream or 0), C.byref(h))
+        if rc != _lib.OK:
+            raise RegistrationError(rc, "tloam_b200_create")
+        self._h = h
+        self._keep = []
+        self.n_source = [0, 0, 0, 0]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tloam_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, where):
+        if rc != _lib.OK:
+            detail = self._L.tloam_b200_last_error(self._h).decode() if rc == _lib.ERR_CUDA else ""
+            raise RegistrationError(rc, where, detail)
+
+    # ---- RegistrationInterface ----
+    @staticmethod
+    def _host_args(frame):
+        clouds = frame.clouds() if isinstance(frame, Frame) else list(frame)
+        arrs = [_f64(c).reshape(-1, 3) for c in clouds]
+        ptrs = (C.POINTER(C.c_double) * 4)(*[_dp(a) for a in arrs])
+        ns = (C.c_size_t * 4)(*[a.shape[0] for a in arrs])
+        return arrs, ptrs, ns
+
+    def set_input_source(self, frame):
+        arrs, ptrs, ns = self._host_args(frame)
+        self._check(self._L.tloam_b200_set_source(self._h, ptrs, ns), "set_input_source")
+        self.n_source = [a.shape[0] for a in arrs]
+        return True
+
+    def set_input_target(self, frame):
+        arrs, ptrs, ns = self._host_args(frame)
+        self._check(self._L.tloam_b200_set_target(self._h, ptrs, ns), "set_input_target")
+        return True
+
+    @staticmethod
+    def _device_args(tensors):
+        ptrs = (C.c_void_p * 4)(*[int(t.data_ptr()) for t in tensors])
+        ns = (C.c_size_t * 4)(*[int(t.shape[0]) for t in tensors])
+        return ptrs, ns
+
+    def set_input_source_device(self, tensors):
+        """tensors: 4 CUDA float64 (n,3) contiguous torch tensors on this handle's device."""
+        ptrs, ns = self._device_args(tensors)
+        self._check(self._L.tloam_b200_set_source_device(self._h, ptrs, ns), "set_input_source_device")
+        self.n_source = [int(t.shape[0]) for t in tensors]
+        return True
+
+    def set_input_target_device(self, tensors):
+        ptrs, ns = self._device_args(tensors)
+        self._check(self._L.tloam_b200_set_target_device(self._h, ptrs, ns), "set_input_target_device")
+        return True
+
+    def scan_matching(self, predict_pose, want_stats=False):
+        """predict_pose: 4x4 numpy (row-major view of the Isometry3d). Returns result 4x4 [, Stats]."""
+        p = _f64(np.asarray(predict_pose).T).reshape(16)
+        out = np.zeros(16)
+        st = _lib.Stats() if want_stats else None
+        rc = self._L.tloam_b200_scan_match(self._h, _dp(p), _dp(out), C.byref(st) if st is not None else None)
+        self._check(rc, "scan_matching")
+        T = out.reshape(4, 4).T.copy()
+        return (T, st) if want_stats else T
+
+    def scan_matching_async(self, predict_pose):
+        p = _f64(np.asarray(predict_pose).T).reshape(16)
+        self._check(self._L.tloam_b200_scan_match_async(self._h, _dp(p)), "scan_matching_async")
+
+    def get_result(self, want_stats=False):
+        out = np.zeros(16)
+        st = _lib.Stats() if want_stats else None
+        rc = self._L.tloam_b200_get_result(self._h, _dp(out), C.byref(st) if st is not None else None)
+        self._check(rc, "get_result")
+        T = out.reshape(4, 4).T.copy()
+        return (T, st) if want_stats else T
+
+    def get_fitness_score(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._L.tloam_b200_fitness(self._h, C.byref(a), C.byref(b)), "get_fitness_score")
+        return a.value, b.value
+
+    def get_transform(self):
+        out = np.zeros(16)
+        self._check(self._L.tloam_b200_get_transform(self._h, _dp(out)), "get_transform")
+        return out.reshape(4, 4).T.copy()
+
+    def get_pose_increment(self):
+        out = np.zeros(16)
+        self._check(self._L.tloam_b200_get_pose_increment(self._h, _dp(out)), "get_pose_increment")
+        return out.reshape(4, 4).T.copy()
+
+    def synchronize(self):
+        self._check(self._L.tloam_b200_synchronize(self._h), "synchronize")
+
+    def launch_count(self):
+        return int(self._L.tloam_b200_launch_count(self._h))
+
+    # ---- shared map (multi-GPU) ----
+    def map_blob_size(self):
+        n = C.c_size_t(0)
+        self._check(self._L.tloam_b200_map_blob_size(self._h, C.byref(n)), "map_blob_size")
+        return n.value
+
+    def map_export(self, dev_ptr, nbytes):
+        self._check(self._L.tloam_b200_map_export(self._h, C.c_void_p(dev_ptr), nbytes), "map_export")
+
+    def map_import(self, dev_ptr, nbytes):
+        self._check(self._L.tloam_b200_map_import(self._h, C.c_void_p(dev_ptr), nbytes), "map_import")
+
+    def map_origin(self):
+        o = np.zeros(3)
+        self._check(self._L.tloam_b200_get_map_origin(self._h, _dp(o)), "map_origin")
+        return o
+
+    # ---- piecewise (parity tests) ----
+    def knn(self, cloud, queries, radius, k):
+        q = _f64(queries).reshape(-1, 3)
+        nq = q.shape[0]
+        idx = np.full((nq, k), -1, dtype=np.int32)
+        d2 = np.full((nq, k), np.inf)
+        cnt = np.zeros(nq, dtype=np.int32)
+        rc = self._L.tloam_b200_knn(self._h, cloud, _dp(q), nq, float(radius), int(k),
+                                    idx.ctypes.data_as(C.POINTER(C.c_int)), _dp(d2),
+                                    cnt.ctypes.data_as(C.POINTER(C.c_int)))
+        self._check(rc, "knn")
+        return idx, d2, cnt
+
+    def build_factors(self, cloud, x):
+        n = self.n_source[cloud]
+        valid = np.zeros(n, dtype=np.int32)
+        prim = np.zeros((n, 6))
+        x = _f64(x)
+        rc = self._L.tloam_b200_build_factors(self._h, cloud, _dp(x), valid.ctypes.data_as(C.POINTER(C.c_int)),
+                                              _dp(prim), n)
+        self._check(rc, "build_factors")
+        return valid, prim
+
+    def eval_point_to_point(self, x, p, q, w):
+        x, p, q, w = _f64(x), _f64(p).reshape(-1, 3), _f64(q).reshape(-1, 3), _f64(w).reshape(-1)
+        m = p.shape[0]
+        r, J, c = np.zeros((m, 3)), np.zeros((m, 3, 6)), np.zeros(m)
+        self._check(self._L.tloam_b200_eval_point_to_point(self._h, _dp(x), m, _dp(p), _dp(q), _dp(w), _dp(r), _dp(J), _dp(c)),
+                    "eval_point_to_point")
+        return r, J, c
+
+    def eval_point_to_line(self, x, p, a, b, w):
+        x, p, a, b, w = _f64(x), _f64(p).reshape(-1, 3), _f64(a).reshape(-1, 3), _f64(b).reshape(-1, 3), _f64(w).reshape(-1)
+        m = p.shape[0]
+        r, J, c = np.zeros((m, 3)), np.zeros((m, 3, 6)), np.zeros(m)
+        self._check(self._L.tloam_b200_eval_point_to_line(self._h, _dp(x), m, _dp(p), _dp(a), _dp(b), _dp(w), _dp(r), _dp(J), _dp(c)),
+                    "eval_point_to_line")
+        return r, J, c
+
+    def eval_point_to_plane(self, x, p, n, d, w):
+        x, p, n, d, w = _f64(x), _f64(p).reshape(-1, 3), _f64(n).reshape(-1, 3), _f64(d).reshape(-1), _f64(w).reshape(-1)
+        m = p.shape[0]
+        r, J, c = np.zeros((m, 1)), np.zeros((m, 1, 6)), np.zeros(m)
+        self._check(self._L.tloam_b200_eval_point_to_plane(self._h, _dp(x), m, _dp(p), _dp(n), _dp(d), _dp(w), _dp(r), _dp(J), _dp(c)),
+                    "eval_point_to_plane")
+        return r, J, c
+
+    def se3_exp(self, a):
+        a = _f64(a)
+        T = np.zeros(16)
+        self._check(self._L.tloam_b200_se3_exp(self._h, _dp(a), _dp(T)), "se3_exp")
+        return T.reshape(4, 4).T.copy()
+
+    def se3_log(self, T):
+        t = _f64(np.asarray(T).T).reshape(16)
+        a = np.zeros(6)
+        self._check(self._L.tloam_b200_se3_log(self._h, _dp(t), _dp(a)), "se3_log")
+        return a
+
+    def se3_plus(self, x, d):
+        x, d = _f64(x), _f64(d)
+        out = np.zeros(6)
+        self._check(self._L.tloam_b200_se3_plus(self._h, _dp(x), _dp(d), _dp(out)), "se3_plus")
+        return out
