@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the TLS scan-to-map registration hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE config 2 -- a KITTI-seq00-shaped synthetic stream, 64-beam / 120k-pt
+scans reduced to F = 40 000 features (edge 8 000 / sphere 1 600 / planar 16 800 / ground 13 600) against an
+M = 500 000-point local map that changes EVERY frame, full TLS (all three residual types + ground, 4 outer GNC
+iterations x <= 4 trust-region iterations, caps raised to F).  One "step" = one frame =
+set_target (map upload + voxel-hash build) + set_source + scan_match, as the reference's front end does per
+frame (ref: src/front_end/front_end.cpp:278-337).
+
+  value : frames/s with every frame's inputs already resident in HBM when the timed region starts
+          (tloam_b200_set_*_device).  Each frame reads its own buffers (13 MB/frame, K+W frames > L2).
+  e2e   : the same metric through the reference-facing C ABI with PINNED HOST buffers: H2D of map + scan and
+          D2H of the pose inside the timed region.
+  N > 1 : one process per GPU (torchrun), rank r runs its own independent stream (sequence r of
+          00,02,05,08,01,06,07,09) -- frames of different sequences shard with no data-path collective;
+          value = all ranks' frames / max-over-ranks device time ("weak" scaling).  The shared-map
+          ncclBroadcast of config 4 is timed separately and reported under "shared_map_broadcast".
+  --impl reference : the CPU restatement of the reference path (oracle, kind "port" -- the reference itself
+          cannot be built in this image) on the box's host cores, same workload / metric / unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec (120k-pt HDL-64 scan, 40k features) at 1/2/4/8 B200 vs CPU ref"
+UNIT = "frames/s"
+SEQS = ["00", "02", "05", "08", "01", "06", "07", "09"]
+BIG = 10 ** 9
+CAPS = dict(edge_maxnum=BIG, sphere_maxnum=BIG, planar_maxnum=BIG, ground_maxnum=BIG)
+HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def workload_config(world):
+    return {"workload": "config2: KITTI-seq00-shaped synthetic stream, F=40000 features (8000/1600/16800/13600) vs "
+                        "M=500000-pt local map rebuilt every frame, full TLS (4 outer x <=4 inner), caps=F",
+            "features_per_frame": 40000, "map_points": 500000, "scan_points_nominal": 120000,
+            "l2_policy": "inputs larger than L2: every frame reads its own 13 MB input buffers",
+            "parallelism": f"{world} independent streams, one per GPU" if world > 1 else "1 stream, 1 GPU"}
+
+
+def gen_frames(seq, count, start=100):
+    from tloam_b200 import synth
+    st = synth.Stream(cfg=synth.SceneConfig(seed=20260924 + 1000 * 2 + int(seq)), seq=seq, start=start)
+    prev_gt = st.T @ np.linalg.inv(synth.se3_exp(st.motion[(start - 1) % len(st.motion)])) if start > 0 else st.T.copy()
+    frames = [st.frame() for _ in range(count)]
+    return frames, prev_gt
+
+
+def predict_next(last, cur):
+    """constant-velocity model of the reference front end (ref: front_end.cpp:329-330)."""
+    return cur @ (np.linalg.inv(last) @ cur)
+
+
+def first_predict(fr):
+    """first frame of a stream: ground truth perturbed like config 1."""
+    from tloam_b200 import synth
+    return fr["T_gt"] @ synth.se3_exp(synth.CONFIG1_PERTURB)
+
+
+def pose_err(A, B):
+    d = np.linalg.inv(A) @ B
+    return float(np.linalg.norm(d[:3, 3])), float(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["reasons"] = sorted(reasons)
+            out["samples"] = len(sm)
+        return out
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(path))
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBps"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# algorithmic bytes per unit, DESIGN.md "Kernels" 
+def algorithmic_bytes(n_feat, n_map):
+    f_k5 = n_feat[0] + n_feat[2] + n_feat[3]
+    f_k1 = n_feat[1]
+    return {"correspond": f_k5 * 132 + f_k1 * 68,                  # stage B, per launch (one outer iteration)
+            "eval": sum(n_feat) * 52, "eval_first": sum(n_feat) * 52,  # stage C, per launch (one GN evaluation)
+            "map_build": sum(n_map) * 44}                          # stage A, per map
+
+
+def run_stream(reg, frames, prev_gt, mode, torch, warmup, steps):
+    """mode 'device': inputs resident in HBM; 'host': pinned host buffers through the ABI.
+    Returns (ms_total_timed, poses, launches_timed)."""
+    dev_frames = []
+    for fr in frames:
+        if mode == "device":
+            dev_frames.append(([torch.from_numpy(c).cuda() for c in fr["map"]], [torch.from_numpy(c).cuda() for c in fr["scan"]]))
+        else:
+            dev_frames.append(([torch.from_numpy(c).pin_memory().numpy() for c in fr["map"]],
+                               [torch.from_numpy(c).pin_memory().numpy() for c in fr["scan"]]))
+    torch.cuda.synchronize()
+    last, cur = prev_gt.copy(), None
+    poses = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = 0
+    for k, fr in enumerate(frames):
+        if k == warmup:
+            torch.cuda.synchronize()
+            launches0 = reg.launch_count()
+            e0.record()
+        predict = first_predict(fr) if cur is None else predict_next(last, cur)
+        mp, sc = dev_frames[k]
+        if mode == "device":
+            reg.set_input_target_device(mp)
+            reg.set_input_source_device(sc)
+        else:
+            reg.set_input_target(mp)
+            reg.set_input_source(sc)
+        T = reg.scan_matching(predict)
+        poses.append(T)
+        last, cur = (cur if cur is not None else prev_gt), T
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), poses, reg.launch_count() - launches0
+
+
+def reference_arm(args, rank, world):
+    """CPU restatement of the reference path on the host cores (kind 'port')."""
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    ncores = os.cpu_count()
+    frames, prev_gt = gen_frames(SEQS[0], args.warmup + args.steps)
+    results = {}
+    for mode in (0, 1):
+        o = pyoracle.Oracle(threads_mode=mode, **CAPS)
+        last, cur = prev_gt.copy(), None
+        t_timed = 0.0
+        stage = np.zeros(4)
+        for k, fr in enumerate(frames):
+            predict = first_predict(fr) if cur is None else predict_next(last, cur)
+            t0 = time.perf_counter()
+            o.set_input_target(fr["map"])
+            o.set_input_source(fr["scan"])
+            rc, T, st = o.scan_matching(predict)
+            dt = time.perf_counter() - t0
+            assert rc == 0
+            if k >= args.warmup:
+                t_timed += dt
+                stage += [st.t_kdtree, st.t_factors, st.t_solve, st.t_weights]
+            last, cur = (cur if cur is not None else prev_gt), T
+        results[mode] = (args.steps / t_timed, 1e3 * t_timed / args.steps, (1e3 * stage / args.steps).tolist())
+        if mode == 0 and args.steps * results[0][1] > 120e3:
+            break
+    fps, ms, stage = results[0]
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(1),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
+                             "sample": f"{args.steps} frames of the config-2 stream after {args.warmup} warm-up; "
+                                       "reference thread structure: 4 KD-build + 4 factor-build threads, cores/2 solver threads",
+                             "stage_ms": dict(zip(("kdtree", "factors", "solve", "weights"), stage))},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if 1 in results:
+        line["cpu_baseline"]["all_cores_variant"] = {"value": results[1][0], "ms_per_step": results[1][1],
+                                                     "note": "same port, kNN/fit parallel over all cores (stronger than the reference's 4 builder threads)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import tloam_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the registration path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seq = SEQS[rank % len(SEQS)]
+    total = args.warmup + args.steps
+    frames, prev_gt = gen_frames(seq, total)
+    n_feat = [int(c.shape[0]) for c in frames[0]["scan"]]
+    n_map = [int(c.shape[0]) for c in frames[0]["map"]]
+    reg = tloam_b200.LocalRegistration(device=local_rank, stream=torch.cuda.current_stream().cuda_stream, **CAPS)
+
+    # ---- value: inputs resident in HBM ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms_dev, poses, launches = run_stream(reg, frames, prev_gt, "device", torch, args.warmup, args.steps)
+    barrier()
+    clocks = sampler.stop()
+    # ---- e2e: pinned host buffers through the ABI ----
+    barrier()
+    ms_e2e, poses_e2e, _ = run_stream(reg, frames, prev_gt, "host", torch, args.warmup, args.steps)
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    for a, b in zip(poses, poses_e2e):
+        assert np.array_equal(a, b), "host-buffer and device-buffer paths disagree"
+    gt_err = max(pose_err(T, fr["T_gt"])[0] for T, fr in zip(poses, frames))
+
+    # ---- per-kernel durations (CUDA events around every launch, separate pass) ----
+    reg.set_profiling(True)
+    nprof = min(6, total)
+    run_stream(reg, frames[:nprof], prev_gt, "device", torch, 0, nprof)
+    prof = reg.get_profile()
+    reg.set_profiling(False)
+    alg = algorithmic_bytes(n_feat, n_map)
+    kern = {}
+    for k, (n, ms) in prof.items():
+        if n > 0:
+            kern[k] = {"launches_per_frame": n / nprof, "avg_us": 1e3 * ms / n, "ms_per_frame": ms / nprof}
+    map_ms = sum(kern[k]["ms_per_frame"] for k in kern if k.startswith("map_"))
+    dominant = max(("correspond", "eval", "eval_first"), key=lambda k: kern.get(k, {}).get("ms_per_frame", 0.0))
+    peak, peak_src = measured_peak_hbm()
+    dom_us = kern[dominant]["avg_us"]
+    achieved = alg[dominant] / (dom_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"correspond": "k_correspond", "eval": "k_eval<false>", "eval_first": "k_eval<true>"}[dominant],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dominant], "avg_launch_us": dom_us,
+                "note": "single-frame launches at F=40k are latency-bound (working set is L2-resident); see DESIGN.md",
+                "kernels": kern, "map_build": {"ms_per_frame": map_ms, "achieved_GBps": alg["map_build"] / (map_ms * 1e-3) / 1e9 if map_ms > 0 else None}}
+
+    # ---- shared-map broadcast of config 4 (NCCL), timed separately ----
+    bcast = None
+    if world > 1:
+        n = reg.map_blob_size()
+        buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            reg.map_export(buf.data_ptr(), n)
+        for _ in range(3):
+            dist.broadcast(buf, src=0)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.broadcast(buf, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        tb = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        reg.map_import(buf.data_ptr(), n)
+        bcast = {"bytes": n, "ms": float(tb[0]), "GBps": n / (float(tb[0]) * 1e-3) / 1e9}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle
+        o = pyoracle.Oracle(threads_mode=0, **CAPS)
+        nb = min(4, total)
+        t_acc, last, cur = 0.0, prev_gt.copy(), None
+        worst = 0.0
+        for k, fr in enumerate(frames[:nb]):
+            predict = first_predict(fr) if cur is None else predict_next(last, cur)
+            t0 = time.perf_counter()
+            o.set_input_target(fr["map"])
+            o.set_input_source(fr["scan"])
+            rc, T, _ = o.scan_matching(predict)
+            dt = time.perf_counter() - t0
+            if k >= 1:
+                t_acc += dt
+            worst = max(worst, pose_err(T, poses[k])[0])
+            last, cur = (cur if cur is not None else prev_gt), T
+        cpu = {"value": (nb - 1) / t_acc, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"frames 1..{nb - 1} of the same stream (1 warm-up), reference thread structure "
+                         "(4 KD-build + 4 factor threads, cores/2 solver threads)",
+               "max_pose_diff_vs_gpu_m": worst}
+
+    if rank == 0:
+        fps = world * args.steps / (ms_dev * 1e-3)
+        fps_e2e = world * args.steps / (ms_e2e * 1e-3)
+        h2d = (sum(n_map) + sum(n_feat)) * 24
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 128,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "max_err_vs_ground_truth_m": gt_err}
+        if bcast:
+            line["shared_map_broadcast"] = bcast
+        print(json.dumps(line))
+    reg.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

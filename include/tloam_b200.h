@@ -156,6 +156,20 @@ int tloam_b200_se3_exp(tloam_b200_handle* h, const double a[6], double T[16]);
 int tloam_b200_se3_log(tloam_b200_handle* h, const double T[16], double a[6]);
 int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double delta[6], double out[6]);
 
+/* ---- per-kernel timing (off by default): CUDA events on the handle's stream around EVERY launch.  The
+ * bracketing adds ~1-2 us of event overhead per launch, so profiled durations are upper bounds. ---- */
+enum {
+  TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
+  TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
+  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_COUNT
+};
+typedef struct tloam_b200_profile {
+  long long launches[TLOAM_B200_K_COUNT];
+  double total_ms[TLOAM_B200_K_COUNT];
+} tloam_b200_profile;
+int tloam_b200_set_profiling(tloam_b200_handle* h, int on);   /* also clears the accumulated profile */
+int tloam_b200_get_profile(tloam_b200_handle* h, tloam_b200_profile* out);
+
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);
 int tloam_b200_host_free(void* p);

@@ -56,6 +56,14 @@ class Stats(C.Structure):
     ]
 
 
+KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
+                  "begin_frame", "correspond", "eval_first", "eval")
+
+
+class Profile(C.Structure):
+    _fields_ = [("launches", C.c_longlong * len(KERNEL_CLASSES)), ("total_ms", C.c_double * len(KERNEL_CLASSES))]
+
+
 EXPORTS = [
     "tloam_b200_default_config", "tloam_b200_status_string", "tloam_b200_last_error", "tloam_b200_create",
     "tloam_b200_destroy", "tloam_b200_set_source", "tloam_b200_set_target", "tloam_b200_set_source_device",
@@ -64,7 +72,8 @@ EXPORTS = [
     "tloam_b200_launch_count", "tloam_b200_map_blob_size", "tloam_b200_map_export", "tloam_b200_map_import",
     "tloam_b200_get_map_origin", "tloam_b200_knn", "tloam_b200_build_factors", "tloam_b200_eval_point_to_point",
     "tloam_b200_eval_point_to_line", "tloam_b200_eval_point_to_plane", "tloam_b200_se3_exp", "tloam_b200_se3_log",
-    "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free",
+    "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
+    "tloam_b200_get_profile",
 ]
 
 _lib = None
@@ -119,5 +128,7 @@ def load():
     L.tloam_b200_se3_plus.argtypes = [vp, dp, dp, dp]
     L.tloam_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.tloam_b200_host_free.argtypes = [vp]
+    L.tloam_b200_set_profiling.argtypes = [vp, C.c_int]
+    L.tloam_b200_get_profile.argtypes = [vp, C.POINTER(Profile)]
     _lib = L
     return L

@@ -571,7 +571,31 @@ struct tloam_b200_handle {
   tloam_b200_stats* h_stats = nullptr;
   DeviceCtx ctx;
   int total_blocks = 0;
+  // optional per-kernel-class timing (CUDA events around every launch; off by default)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  size_t ev_next = 0;
+  tloam_b200_profile prof;
 };
+
+// launch bookkeeping: counts the kernel and, in profiling mode, brackets it with events
+struct LaunchScope {
+  tloam_b200_handle* h; int cls; cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(tloam_b200_handle* hh, int c) : h(hh), cls(c) {
+    h->launches++;
+    if (h->profiling) {
+      while (h->ev_pool.size() < h->ev_next + 2) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+      a = h->ev_pool[h->ev_next++]; b = h->ev_pool[h->ev_next++];
+      cudaEventRecord(a, h->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (h->profiling) { cudaEventRecord(b, h->stream); h->spans.push_back({cls, a, b}); }
+  }
+};
+#define TL_LAUNCH(cls, ...) do { LaunchScope ls__(h, cls); __VA_ARGS__; } while (0)
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
@@ -658,6 +682,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -733,8 +758,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   c.blk_count = h->d_blk_count; c.partial = h->d_partial;
   h->total_blocks = c.blk_off[4];
   if (h->total_blocks > 0) {
-    k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(h->d_stage_src, c, f, f + cp, f + 2 * cp, soff[0], soff[1], soff[2], soff[3]);
-    h->launches++;
+    TL_LAUNCH(TLOAM_B200_K_STAGE_SOURCE, (k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(h->d_stage_src, c, f, f + cp, f + 2 * cp, soff[0], soff[1], soff[2], soff[3])));
     CU_TRY(cudaGetLastError());
   }
   h->have_src = true;
@@ -835,16 +859,14 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     const unsigned gb = (unsigned)((total + tb - 1) / tb);
     unsigned tslots = 0;
     for (int c = 0; c < 4; ++c) tslots += h->hdr.tsize[c];
-    k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a);
-    k_map_origin<<<1, 32, 0, h->stream>>>(a);
-    k_map_insert<<<gb, tb, 0, h->stream>>>(a);
-    k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(a);
-    k_map_scatter<<<gb, tb, 0, h->stream>>>(a);
-    h->launches += 5;
+    TL_LAUNCH(TLOAM_B200_K_MAP_BBOX, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));
+    TL_LAUNCH(TLOAM_B200_K_MAP_ORIGIN, (k_map_origin<<<1, 32, 0, h->stream>>>(a)));
+    TL_LAUNCH(TLOAM_B200_K_MAP_INSERT, (k_map_insert<<<gb, tb, 0, h->stream>>>(a)));
+    TL_LAUNCH(TLOAM_B200_K_MAP_OFFSETS, (k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(a)));
+    TL_LAUNCH(TLOAM_B200_K_MAP_SCATTER, (k_map_scatter<<<gb, tb, 0, h->stream>>>(a)));
     CU_TRY(cudaGetLastError());
   } else {
-    k_map_origin<<<1, 32, 0, h->stream>>>(a);
-    h->launches += 1;
+    TL_LAUNCH(TLOAM_B200_K_MAP_ORIGIN, (k_map_origin<<<1, 32, 0, h->stream>>>(a)));
   }
   bind_map(h);
   h->origin_known = false;
@@ -930,21 +952,22 @@ int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) 
   memcpy(pr.m, predict, sizeof(pr.m));
   const DeviceCtx& c = h->ctx;
   const int nb = h->total_blocks;
-  int launches = 0;
+  const long long launches0 = h->launches;
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
-  k_begin_frame<<<1, 256, 0, h->stream>>>(c, pr); ++launches;
+  TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, pr)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
-    k_correspond<<<nb, kBlk, 0, h->stream>>>(c); ++launches;
-    k_eval<true><<<nb, kBlk, 0, h->stream>>>(c); ++launches;
-    for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it) { k_eval<false><<<nb, kBlk, 0, h->stream>>>(c); ++launches; }
+    TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<<<nb, kBlk, 0, h->stream>>>(c)));
+    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true><<<nb, kBlk, 0, h->stream>>>(c)));
+    for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
+      TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false><<<nb, kBlk, 0, h->stream>>>(c)));
   }
   CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  const int launches = (int)(h->launches - launches0);
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaMemcpyAsync(h->h_result + 16, (const char*)h->d_state + offsetof(FrameState, frame_done), 2 * sizeof(int),
                          cudaMemcpyDeviceToHost, h->stream));
-  h->launches += launches;
   h->launches_frame = launches;
   h->frame_pending = true;
   return TLOAM_B200_OK;
@@ -1196,5 +1219,31 @@ int tloam_b200_host_alloc(void** p, size_t bytes) {
 int tloam_b200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? TLOAM_B200_OK : TLOAM_B200_ERR_CUDA; }
 
 const char* tloam_b200_last_error(tloam_b200_handle* h) { return h ? h->last_error : ""; }
+
+int tloam_b200_set_profiling(tloam_b200_handle* h, int on) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->profiling = on != 0;
+  h->spans.clear(); h->ev_next = 0;
+  memset(&h->prof, 0, sizeof(h->prof));
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_get_profile(tloam_b200_handle* h, tloam_b200_profile* out) {
+  if (!h || !out) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  for (const auto& sp : h->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.cls >= 0 && sp.cls < TLOAM_B200_K_COUNT) {
+      h->prof.launches[sp.cls] += 1;
+      h->prof.total_ms[sp.cls] += ms;
+    }
+  }
+  h->spans.clear(); h->ev_next = 0;
+  *out = h->prof;
+  return TLOAM_B200_OK;
+}
 
 }  // extern "C"

@@ -169,6 +169,15 @@ class LocalRegistration:
     def launch_count(self):
         return int(self._L.tloam_b200_launch_count(self._h))
 
+    def set_profiling(self, on):
+        self._check(self._L.tloam_b200_set_profiling(self._h, 1 if on else 0), "set_profiling")
+
+    def get_profile(self):
+        """dict kernel-class -> (launches, total_ms), from CUDA events around every launch."""
+        p = _lib.Profile()
+        self._check(self._L.tloam_b200_get_profile(self._h, C.byref(p)), "get_profile")
+        return {k: (int(p.launches[i]), float(p.total_ms[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):
         n = C.c_size_t(0)
