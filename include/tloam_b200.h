@@ -119,6 +119,9 @@ int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double
 /* Split form: enqueue only / wait + fetch. Lets one host thread drive several handles (one per GPU). */
 int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]);
 int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_stats* stats);
+/* The per-iteration trace in tloam_b200_stats costs device time; scan_match records it iff stats != NULL, the
+ * async form iff it was switched on here (default off; without it get_result fills only gpu_launches / gpu_ms). */
+int tloam_b200_set_trace(tloam_b200_handle* h, int on);
 
 int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse);
 int tloam_b200_get_transform(tloam_b200_handle* h, double pose[16]);
@@ -166,6 +169,10 @@ enum {
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
   double total_ms[TLOAM_B200_K_COUNT];
+  /* in-kernel timers (profiling mode): [1] ns k_eval parallel phase, [2] ns final partial sum, [3] ns solver state
+   * machine, [4] number of active k_eval launches, [8] SM cycles k_correspond kNN phase summed over thread blocks,
+   * [9] number of k_correspond thread blocks */
+  unsigned long long dbg[16];
 } tloam_b200_profile;
 int tloam_b200_set_profiling(tloam_b200_handle* h, int on);   /* also clears the accumulated profile */
 int tloam_b200_get_profile(tloam_b200_handle* h, tloam_b200_profile* out);

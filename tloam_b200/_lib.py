@@ -61,7 +61,8 @@ KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_sc
 
 
 class Profile(C.Structure):
-    _fields_ = [("launches", C.c_longlong * len(KERNEL_CLASSES)), ("total_ms", C.c_double * len(KERNEL_CLASSES))]
+    _fields_ = [("launches", C.c_longlong * len(KERNEL_CLASSES)), ("total_ms", C.c_double * len(KERNEL_CLASSES)),
+                ("dbg", C.c_ulonglong * 16)]
 
 
 EXPORTS = [
@@ -73,7 +74,7 @@ EXPORTS = [
     "tloam_b200_get_map_origin", "tloam_b200_knn", "tloam_b200_build_factors", "tloam_b200_eval_point_to_point",
     "tloam_b200_eval_point_to_line", "tloam_b200_eval_point_to_plane", "tloam_b200_se3_exp", "tloam_b200_se3_log",
     "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
-    "tloam_b200_get_profile",
+    "tloam_b200_get_profile", "tloam_b200_set_trace",
 ]
 
 _lib = None
@@ -130,5 +131,6 @@ def load():
     L.tloam_b200_host_free.argtypes = [vp]
     L.tloam_b200_set_profiling.argtypes = [vp, C.c_int]
     L.tloam_b200_get_profile.argtypes = [vp, C.POINTER(Profile)]
+    L.tloam_b200_set_trace.argtypes = [vp, C.c_int]
     _lib = L
     return L

@@ -29,6 +29,8 @@
 namespace tloam {
 
 constexpr int kBlk = 128;     // threads per block for all per-feature kernels
+constexpr int kLpq = 8;       // lanes cooperating on one feature's kNN in k_correspond
+constexpr int kQpb = 32;      // features per k_correspond thread block (kNN in kQpb*kLpq/kBlk rounds, fit by warp 0)
 constexpr int kNRed = 36;     // 21 (H upper) + 6 (g) + 1 (cost) + 4 (slot sum per cloud) + 4 (factors per cloud)
 constexpr int kEdge = 0, kSphere = 1, kPlanar = 2, kGround = 3;
 
@@ -37,6 +39,12 @@ constexpr unsigned char kFlagCand = 1;     // passes every test of the factor bu
 constexpr unsigned char kFlagCounted = 2;  // advances the builder's counter (edge_num / sphere_sum / ...)
 
 enum Phase : int { kPhaseIter0 = 0, kPhaseCand = 1 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct FrameState {
   // ---- pose ----
@@ -48,11 +56,12 @@ struct FrameState {
   // ---- trust-region state (Ceres TrustRegionMinimizer + DoglegStrategy) ----
   int phase, iter, num_invalid, reuse;
   int frame_done, status, sub_1d, used_gn;
-  int last_cand_valid, outer, pad0, pad1;
+  int last_cand_valid, outer, sub_valid, model_ok;
   double radius, mu_lm, x_cost, x_norm, model_cost_change, step_norm, gn_norm;
   double scale[6], H[21], g[6];
   double D[6], sgrad[6], gn[6], sub_basis[12], sub_g[2], sub_B[4];
   double last_cand[6], last_cand_cost;
+  Pose7 last_candq;
   // ---- GNC state ----
   double mu, mu_used, th1, th2, c2, planar_prev;
   double slot_sum[4];
@@ -69,7 +78,7 @@ struct DeviceCtx {
   int pad_off[4];               // first padded feature index of each cloud (multiple of kBlk)
   int blk_off[5];               // block ranges per cloud
   int maxnum[4];
-  int factor_num, max_iterations, ceres_max_it, pad;
+  int factor_num, max_iterations, ceres_max_it, pad_;
   double edge_dir_thres, cost_threshold, gnc_factor, noise_bound, fitness_thres;
   double reinit_dir[3];
   // per-feature SoA (padded)
@@ -77,9 +86,11 @@ struct DeviceCtx {
   double *w, *slot;
   double* prim[6];
   unsigned char *flags, *active;
-  int* blk_count;               // per block: number of `counted` features
+  int* blk_count;               // [2][blocks] (double-buffered by outer&1): `counted` features per 128-feature block
   double* partial;              // [blocks][kNRed]
   unsigned* counter;            // last-block ticket
+  int blk_cap;                  // stride between the two blk_count buffers
+  unsigned long long* dbg;      // in-kernel timers (profiling mode only, else nullptr)
   FrameState* st;
   tloam_b200_stats* stats;      // device copy of the trace
 };
@@ -221,10 +232,12 @@ __device__ __forceinline__ void functor_line(const double c[3], const double a[3
   const double ux = c[0] - a[0], uy = c[1] - a[1], uz = c[2] - a[2];
   const double vx = c[0] - b[0], vy = c[1] - b[1], vz = c[2] - b[2];
   const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-  const double den = sqrt(dx * dx + dy * dy + dz * dz);
-  r[0] = (uy * vz - uz * vy) / den * w;
-  r[1] = (uz * vx - ux * vz) / den * w;
-  r[2] = (ux * vy - uy * vx) / den * w;
+  // NOTE the reference divides every entry by |a-b| (x / den * w); here one reciprocal is shared, which differs
+  // from the reference's rounding by <= 1 ulp per entry.
+  const double inv = 1.0 / sqrt(dx * dx + dy * dy + dz * dz);
+  r[0] = (uy * vz - uz * vy) * inv * w;
+  r[1] = (uz * vx - ux * vz) * inv * w;
+  r[2] = (ux * vy - uy * vx) * inv * w;
   // S = hat(b - a) ; M = [I*w | -hat(c)*w] ; J = S*M/den
   const double ex = -dx, ey = -dy, ez = -dz;  // b - a
   const double S[9] = {0.0, -ez, ey, ez, 0.0, -ex, -ey, ex, 0.0};
@@ -235,7 +248,7 @@ __device__ __forceinline__ void functor_line(const double c[3], const double a[3
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 6; ++j)
-      J[i * 6 + j] = (S[i * 3 + 0] * M[0 * 6 + j] + S[i * 3 + 1] * M[1 * 6 + j] + S[i * 3 + 2] * M[2 * 6 + j]) / den;
+      J[i * 6 + j] = (S[i * 3 + 0] * M[0 * 6 + j] + S[i * 3 + 1] * M[1 * 6 + j] + S[i * 3 + 2] * M[2 * 6 + j]) * inv;
 }
 
 // upper-triangle index of (i,j), i <= j, row-major packed (21 entries)

@@ -77,9 +77,10 @@ TL_HD Pose7 se3_exp(const double a[6]) {
     p.ty = r[3] * ux + r[4] * uy + r[5] * uz;
     p.tz = r[6] * ux + r[7] * uy + r[8] * uz;
   } else {
-    double s, c;
-    sincos(theta, &s, &c);
-    const double c1 = (1.0 - c) / th2;
+    // sin(theta), 1 - cos(theta) from the half-angle values already at hand (one sincos per exp)
+    const double sh = kim * theta, ch = kre;
+    const double s = 2.0 * sh * ch;
+    const double c1 = 2.0 * sh * sh / th2;          // (1 - cos theta) / theta^2
     const double c2 = (theta - s) / (th2 * theta);
     const double wx = oy * uz - oz * uy, wy = oz * ux - ox * uz, wz = ox * uy - oy * ux;      // W u
     const double vx = oy * wz - oz * wy, vy = oz * wx - ox * wz, vz = ox * wy - oy * wx;      // W^2 u
@@ -113,9 +114,8 @@ TL_HD void se3_log(const Pose7& p, double out[6]) {
   if (fabs(theta) < kLieEps) {
     c = 1.0 / 12.0;
   } else {
-    double sh, ch;
-    sincos(0.5 * theta, &sh, &ch);
-    c = (1.0 - theta * ch / (2.0 * sh)) / (theta * theta);
+    // cos(theta/2) / sin(theta/2) == w / n for a unit quaternion with theta = 2 atan(n / w): no sincos needed
+    c = (1.0 - 0.5 * theta * w / sqrt(n2)) / (theta * theta);
   }
   const double tx = p.tx, ty = p.ty, tz = p.tz;
   const double wx = oy * tz - oz * ty, wy = oz * tx - ox * tz, wz = ox * ty - oy * tx;

@@ -1,4 +1,4 @@
-// solver.cuh -- on-device trust-region state machine (single thread of the last block of k_eval).
+// solver.cuh -- on-device trust-region state machine, run by the LAST block of k_eval.
 //
 // Restates, for ONE 6-parameter block, the control flow of Ceres Solver 2.0
 //   TrustRegionMinimizer::Minimize / IterationZero / ComputeTrustRegionStep / HandleSuccessfulStep /
@@ -12,6 +12,16 @@
 //   J_s^T J_s = S H S,  J_s^T r = S g,  ||J_s col||^2 = (S H S)_jj,
 //   model_cost_change = -(g_s . step + step^T H_s step / 2),
 //   DENSE_QR on [J_s ; sqrt(mu) D] y = [r ; 0]  ==  (H_s + mu D^2) y = g_s  (solved by Cholesky, FP64).
+//
+// The work is one long chain of dependent FP64 operations (~15 cycles each), so it is split over the warps of
+// the block (measured: 29k cycles single-threaded):
+//   phase A, concurrently   warp 1: gradient-tolerance quantity |x - Plus(x,-g)|_inf for the state that would
+//                                   be current if this evaluation is accepted
+//                           warp 2: Gauss-Newton model (diagonal, scaled gradient, Cholesky solve) from the
+//                                   freshly reduced H, g  -- speculative, used iff the step is accepted
+//                           warp 3: cand = log(candidate pose) (the candidate was handed to the kernels as a
+//                                   pose; its tangent is only needed for tolerance tests and the trace)
+//   phase B, thread 0       accept / reject / convergence logic, dogleg step, next candidate pose.
 #pragma once
 #include "registration.cuh"
 
@@ -23,34 +33,41 @@ __device__ __forceinline__ double norm6(const double* v) {
   return sqrt(s);
 }
 
-// Cholesky solve of the SPD 6x6 system A y = b. Returns false if a pivot is not positive / finite.
-__device__ __forceinline__ bool chol_solve6(const double A[36], const double b[6], double y[6]) {
+// Cholesky solve of the SPD 6x6 system A y = b (fully unrolled: everything stays in registers).
+// Returns false if a pivot is not positive / finite.
+__device__ __noinline__ bool chol_solve6(const double A[36], const double b[6], double y[6]) {
   double L[36];
+  double inv[6];
+  bool ok = true;
   for (int i = 0; i < 6; ++i) {
     for (int j = 0; j <= i; ++j) {
       double s = A[i * 6 + j];
       for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
       if (i == j) {
-        if (!(s > 0.0) || !isfinite(s)) return false;
-        L[i * 6 + i] = sqrt(s);
+        ok = ok && (s > 0.0) && isfinite(s);
+        const double d = sqrt(s);
+        L[i * 6 + i] = d;
+        inv[i] = 1.0 / d;
       } else {
-        L[i * 6 + j] = s / L[j * 6 + j];
+        L[i * 6 + j] = s * inv[j];
       }
     }
   }
+  if (!ok) return false;
   double z[6];
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * z[k];
-    z[i] = s / L[i * 6 + i];
+    z[i] = s * inv[i];
   }
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
-    y[i] = s / L[i * 6 + i];
+    y[i] = s * inv[i];
   }
-  for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) return false;
-  return true;
+  bool fin = true;
+  for (int i = 0; i < 6; ++i) fin = fin && isfinite(y[i]);
+  return fin;
 }
 
 // minimise 0.5 y^T B y + g^T y on |y| = radius (2-D): the boundary problem of the subspace dogleg
@@ -90,14 +107,69 @@ __device__ __noinline__ void min_on_boundary_2d(const double B[4], const double 
   y[0] = radius * c; y[1] = radius * s;
 }
 
+// Gauss-Newton model of DoglegStrategy::ComputeStep (first call after an accepted / invalid step):
+// diagonal, scaled gradient, regularised Gauss-Newton step.  All inputs by value (registers).
+struct GnModel {
+  double scale[6];     // jacobi scaling used
+  double D[6], sgrad[6], gn[6];
+  double gn_norm, mu_lm;
+  int ok;              // 0 = LINEAR_SOLVER_FAILURE
+  int pad;
+};
+
+__device__ __noinline__ void gn_model(const double H[21], const double g[6], const double scale[6], double mu_lm,
+                                         GnModel& m) {
+  double Hs[36], gs[6];
+  for (int i = 0; i < 6; ++i) {
+    m.scale[i] = scale[i];
+    gs[i] = scale[i] * g[i];
+    for (int j = 0; j < 6; ++j) {
+      const double h = (i <= j) ? H[tri(i, j)] : H[tri(j, i)];
+      Hs[i * 6 + j] = scale[i] * h * scale[j];
+    }
+  }
+  for (int i = 0; i < 6; ++i) {
+    m.D[i] = sqrt(fmin(fmax(Hs[i * 6 + i], 1e-6), 1e32));      // min/max_lm_diagonal
+    m.sgrad[i] = gs[i] / m.D[i];
+  }
+  bool ok = false;
+  double y[6] = {0, 0, 0, 0, 0, 0};
+  while (mu_lm < 1.0) {                                         // kMaxMu
+    double A[36];
+    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
+    for (int i = 0; i < 6; ++i) A[i * 6 + i] += mu_lm * m.D[i] * m.D[i];
+    if (chol_solve6(A, gs, y)) { ok = true; break; }
+    mu_lm *= 10.0;                                              // mu_increase_factor_
+  }
+  m.mu_lm = mu_lm;
+  m.ok = ok ? 1 : 0;
+  for (int i = 0; i < 6; ++i) m.gn[i] = ok ? -m.D[i] * y[i] : 0.0;
+  m.gn_norm = norm6(m.gn);
+}
+
+// single out-of-line copies of the Lie-group routines (the solver is instruction-fetch bound: keep it small)
+__device__ __noinline__ void s_exp(const double a[6], Pose7* out) { *out = se3_exp(a); }
+__device__ __noinline__ void s_log(const Pose7* p, double out[6]) { se3_log(*p, out); }
+__device__ __noinline__ void s_mul(const Pose7* a, const Pose7* b, Pose7* out) { *out = se3_mul(*a, *b); }
+
 struct SolverIO {
   const DeviceCtx* ctx;
   FrameState* st;
   tloam_b200_stats* tr;
 };
 
+// profiling-mode stage timer: accumulates SM cycles since the previous stamp into dbg[slot]
+#define TL_STAMP(io, slot)                                                        \
+  do {                                                                            \
+    if ((io).ctx->dbg) {                                                          \
+      const long long now__ = clock64();                                          \
+      (io).ctx->dbg[slot] += (unsigned long long)(now__ - (long long)(io).ctx->dbg[15]); \
+      (io).ctx->dbg[15] = (unsigned long long)now__;                              \
+    }                                                                             \
+  } while (0)
+
 __device__ __forceinline__ tloam_b200_outer_trace* outer_trace(const SolverIO& io) {
-  return (io.st->outer < TLOAM_B200_MAX_OUTER) ? &io.tr->outer[io.st->outer] : nullptr;
+  return (io.tr && io.st->outer < TLOAM_B200_MAX_OUTER) ? &io.tr->outer[io.st->outer] : nullptr;
 }
 __device__ __forceinline__ tloam_b200_inner_trace* inner_trace(const SolverIO& io) {
   tloam_b200_outer_trace* ot = outer_trace(io);
@@ -105,27 +177,31 @@ __device__ __forceinline__ tloam_b200_inner_trace* inner_trace(const SolverIO& i
   return (ot && it >= 1 && it <= TLOAM_B200_MAX_INNER) ? &ot->inner[it - 1] : nullptr;
 }
 
-// |x - Plus(x, -g)|_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian)
-__device__ __forceinline__ double gradient_max_norm(const FrameState* st, const double g[6]) {
+// |x - Plus(x, -g)|_inf  (TrustRegionMinimizer::EvaluateGradientAndJacobian), for pose P with tangent x
+__device__ __noinline__ double gradient_max_norm(const Pose7& P, const double x[6], const double g[6]) {
   double ng[6], proj[6];
   for (int i = 0; i < 6; ++i) ng[i] = -g[i];
-  se3_log(se3_mul(se3_exp(ng), st->xq), proj);
+  Pose7 e, em;
+  s_exp(ng, &e);
+  s_mul(&e, &P, &em);
+  s_log(&em, proj);
   double m = 0.0;
-  for (int i = 0; i < 6; ++i) m = fmax(m, fabs(st->x[i] - proj[i]));
+  for (int i = 0; i < 6; ++i) m = fmax(m, fabs(x[i] - proj[i]));
   return m;
 }
 
-__device__ void finish_frame(const SolverIO& io) {
+__device__ __noinline__ void finish_frame(const SolverIO& io) {
   FrameState* st = io.st;
-  const Pose7 fin = se3_exp(st->x);                     // ref: registration.cpp:1124
+  Pose7 fin;
+  s_exp(st->x, &fin);                                   // ref: registration.cpp:1124
   pose_to_matrix(fin, st->result);
   for (int i = 0; i < 16; ++i) st->curr_pose[i] = st->result[i];
-  for (int i = 0; i < 6; ++i) io.tr->x_final[i] = st->x[i];
+  if (io.tr) for (int i = 0; i < 6; ++i) io.tr->x_final[i] = st->x[i];
   st->frame_done = 1;
 }
 
 // The Ceres solve of this outer iteration is over: GNC bookkeeping, ref: registration.cpp:1049-1121.
-__device__ void end_of_solve(const SolverIO& io, int termination) {
+__device__ __noinline__ void end_of_solve(const SolverIO& io, int termination) {
   FrameState* st = io.st;
   const DeviceCtx& c = *io.ctx;
   tloam_b200_outer_trace* ot = outer_trace(io);
@@ -142,11 +218,11 @@ __device__ void end_of_solve(const SolverIO& io, int termination) {
     for (int k = 0; k < 4; ++k) ot->slot_sum[k] = st->slot_sum[k];
   }
   st->mu = mu * exp((double)(st->outer + 1) * c.gnc_factor);   // :1089
-  io.tr->n_outer = st->outer + 1;
+  if (io.tr) io.tr->n_outer = st->outer + 1;
   const double planar_cost = st->slot_sum[kPlanar];            // :1094
   const double diff = fabs(planar_cost - st->planar_prev);     // :1096
   if (diff < c.cost_threshold) {                               // :1108
-    io.tr->converged_early = 1;
+    if (io.tr) io.tr->converged_early = 1;
     finish_frame(io);
     return;
   }
@@ -157,34 +233,16 @@ __device__ void end_of_solve(const SolverIO& io, int termination) {
   st->evalq = st->xq;
 }
 
-// DoglegStrategy::ComputeStep (first call after an accepted / invalid step): diagonal, scaled gradient,
-// Gauss-Newton step, subspace model.  Returns false on LINEAR_SOLVER_FAILURE.
-__device__ __noinline__ bool compute_model(FrameState* st) {
-  double Hs[36], gs[6];
-  for (int i = 0; i < 6; ++i) {
-    gs[i] = st->scale[i] * st->g[i];
-    for (int j = 0; j < 6; ++j) {
-      const double h = (i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)];
-      Hs[i * 6 + j] = st->scale[i] * h * st->scale[j];
-    }
-  }
-  for (int i = 0; i < 6; ++i) {
-    st->D[i] = sqrt(fmin(fmax(Hs[i * 6 + i], 1e-6), 1e32));    // min/max_lm_diagonal
-    st->sgrad[i] = gs[i] / st->D[i];
-  }
-  bool ok = false;
-  double y[6];
-  while (st->mu_lm < 1.0) {                                     // kMaxMu
-    double A[36];
-    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
-    for (int i = 0; i < 6; ++i) A[i * 6 + i] += st->mu_lm * st->D[i] * st->D[i];
-    if (chol_solve6(A, gs, y)) { ok = true; break; }
-    st->mu_lm *= 10.0;                                          // mu_increase_factor_
-  }
-  if (!ok) return false;
-  for (int i = 0; i < 6; ++i) st->gn[i] = -st->D[i] * y[i];
-  st->gn_norm = norm6(st->gn);
-  // subspace model (ComputeSubspaceModel): orthonormal basis of span{sgrad, gn}
+__device__ __noinline__ void install_model(FrameState* st, const GnModel& m) {
+  for (int i = 0; i < 6; ++i) { st->D[i] = m.D[i]; st->sgrad[i] = m.sgrad[i]; st->gn[i] = m.gn[i]; }
+  st->gn_norm = m.gn_norm;
+  st->mu_lm = m.mu_lm;
+  st->sub_valid = 0;
+}
+
+// subspace model (DoglegStrategy::ComputeSubspaceModel): orthonormal basis of span{sgrad, gn} and the 2x2
+// model in it.  Only needed when the Gauss-Newton step leaves the trust region, so it is computed lazily.
+__device__ __noinline__ bool compute_subspace(FrameState* st) {
   const double n0 = norm6(st->sgrad), n1 = st->gn_norm;
   const double* first = (n0 >= n1) ? st->sgrad : st->gn;
   const double* second = (n0 >= n1) ? st->gn : st->sgrad;
@@ -207,12 +265,14 @@ __device__ __noinline__ bool compute_model(FrameState* st) {
     double b00 = 0, b01 = 0, b11 = 0;
     for (int i = 0; i < 6; ++i)
       for (int j = 0; j < 6; ++j) {
-        b00 += t0[i] * Hs[i * 6 + j] * t0[j];
-        b01 += t0[i] * Hs[i * 6 + j] * t1[j];
-        b11 += t1[i] * Hs[i * 6 + j] * t1[j];
+        const double h = ((i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)]) * st->scale[i] * st->scale[j];
+        b00 += t0[i] * h * t0[j];
+        b01 += t0[i] * h * t1[j];
+        b11 += t1[i] * h * t1[j];
       }
     st->sub_B[0] = b00; st->sub_B[1] = st->sub_B[2] = b01; st->sub_B[3] = b11;
   }
+  st->sub_valid = 1;
   return true;
 }
 
@@ -225,39 +285,46 @@ __device__ __noinline__ void advance(const SolverIO& io) {
     if (st->iter >= c.ceres_max_it) { end_of_solve(io, 0); return; }   // MaxSolverIterationsReached
     st->iter += 1;
     tloam_b200_inner_trace* it = inner_trace(io);
-    bool solver_ok = true;
-    if (!st->reuse) {
+    bool solver_ok = st->model_ok != 0;
+    if (!st->reuse) {                                                  // only after an invalid step
       st->reuse = 1;
-      solver_ok = compute_model(st);
+      GnModel m;
+      double H[21], g[6], sc[6];
+      for (int i = 0; i < 21; ++i) H[i] = st->H[i];
+      for (int i = 0; i < 6; ++i) { g[i] = st->g[i]; sc[i] = st->scale[i]; }
+      gn_model(H, g, sc, st->mu_lm, m);
+      install_model(st, m);
+      st->model_ok = m.ok;
+      solver_ok = m.ok != 0;
     }
     double step[6] = {0, 0, 0, 0, 0, 0};
     if (solver_ok) {                                                   // ComputeSubspaceDoglegStep
       if (st->gn_norm <= st->radius) {
         for (int i = 0; i < 6; ++i) step[i] = st->gn[i] / st->D[i];
         st->step_norm = st->gn_norm; st->used_gn = 1;
-      } else if (st->sub_1d) {
-        const double gnm = norm6(st->sgrad);
-        for (int i = 0; i < 6; ++i) step[i] = -(st->radius / gnm) * st->sgrad[i] / st->D[i];
-        st->step_norm = st->radius; st->used_gn = 0;
       } else {
-        double y2[2];
-        min_on_boundary_2d(st->sub_B, st->sub_g, st->radius, y2);
-        for (int i = 0; i < 6; ++i) step[i] = (st->sub_basis[i] * y2[0] + st->sub_basis[6 + i] * y2[1]) / st->D[i];
-        st->step_norm = st->radius; st->used_gn = 0;
+        if (!st->sub_valid) solver_ok = compute_subspace(st);
+        if (solver_ok) {
+          if (st->sub_1d) {
+            const double gnm = norm6(st->sgrad);
+            for (int i = 0; i < 6; ++i) step[i] = -(st->radius / gnm) * st->sgrad[i] / st->D[i];
+          } else {
+            double y2[2];
+            min_on_boundary_2d(st->sub_B, st->sub_g, st->radius, y2);
+            for (int i = 0; i < 6; ++i) step[i] = (st->sub_basis[i] * y2[0] + st->sub_basis[6 + i] * y2[1]) / st->D[i];
+          }
+          st->step_norm = st->radius; st->used_gn = 0;
+        }
       }
     }
     // model cost change = -(g_s.step + step^T H_s step / 2)
     double mcc = 0.0;
     bool valid = false;
     if (solver_ok) {
-      double lin = 0.0, quad = 0.0;
-      for (int i = 0; i < 6; ++i) {
-        lin += st->scale[i] * st->g[i] * step[i];
-        for (int j = 0; j < 6; ++j) {
-          const double h = (i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)];
-          quad += step[i] * st->scale[i] * h * st->scale[j] * step[j];
-        }
-      }
+      double v[6], lin = 0.0, quad = 0.0;
+      for (int i = 0; i < 6; ++i) { v[i] = st->scale[i] * step[i]; lin += st->g[i] * v[i]; }
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) quad += v[i] * ((i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)]) * v[j];
       mcc = -(lin + 0.5 * quad);
       valid = mcc > 0.0;
     }
@@ -276,16 +343,19 @@ __device__ __noinline__ void advance(const SolverIO& io) {
     st->num_invalid = 0;
     double delta[6];
     for (int i = 0; i < 6; ++i) delta[i] = step[i] * st->scale[i];     // undo the Jacobi scaling
-    st->candq = se3_mul(se3_exp(delta), st->xq);                       // Plus: exp(delta) * exp(x)
-    se3_log(st->candq, st->cand);
-    if (it) for (int i = 0; i < 6; ++i) it->x_candidate[i] = st->cand[i];
+    Pose7 ed, cq;
+    s_exp(delta, &ed);
+    s_mul(&ed, &st->xq, &cq);                                          // Plus: exp(delta) * exp(x)
     bool same = st->last_cand_valid != 0;
-    for (int i = 0; i < 6 && same; ++i) same = (st->cand[i] == st->last_cand[i]);
+    same = same && cq.qw == st->last_candq.qw && cq.qx == st->last_candq.qx && cq.qy == st->last_candq.qy &&
+           cq.qz == st->last_candq.qz && cq.tx == st->last_candq.tx && cq.ty == st->last_candq.ty &&
+           cq.tz == st->last_candq.tz;
     if (same) {
       // identical to the candidate that was just evaluated and rejected (reuse_ = true and the
       // Gauss-Newton step still fits the halved radius): the evaluation, both tolerance tests and the step
       // quality repeat exactly, so the step is rejected again without re-running the kernel.
       if (it) {
+        for (int i = 0; i < 6; ++i) it->x_candidate[i] = st->last_cand[i];
         it->candidate_cost = st->last_cand_cost;
         it->relative_decrease = (st->x_cost - st->last_cand_cost) / mcc;
         it->accepted = 0;
@@ -294,53 +364,103 @@ __device__ __noinline__ void advance(const SolverIO& io) {
       if (st->radius <= 1e-32) { end_of_solve(io, 4); return; }
       continue;
     }
-    st->evalq = st->candq;
+    st->candq = cq;            // its tangent (cand) is computed by warp 3 of the next evaluation
+    st->evalq = cq;
     st->phase = kPhaseCand;
     return;
   }
 }
 
-// Called by one thread after the per-block partials have been summed into tot[kNRed].
-__device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, const double* tot) {
-  SolverIO io{&ctx, ctx.st, ctx.stats};
+struct SolverShared {
+  GnModel model;
+  double gmax;
+  double cand[6];
+};
+
+// Entered by ALL threads of the last block after the per-block partials have been summed into tot[kNRed].
+// `state` is a shared-memory copy of ctx.st (the caller writes it back).
+__device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* state, const double* tot,
+                                               SolverShared* sh) {
+  SolverIO io{&ctx, state, ctx.stats};
   FrameState* st = io.st;
+  const bool iter0 = st->phase == kPhaseIter0;
+  // ---------------- phase A: three independent chains on three warps ----------------
+  long long ta0 = 0;
+  if (ctx.dbg) ta0 = clock64();
+  if (threadIdx.x == 32) {
+    double g[6], x[6];
+    for (int i = 0; i < 6; ++i) g[i] = tot[21 + i];
+    const Pose7 P = iter0 ? st->xq : st->candq;
+    if (iter0) {
+      for (int i = 0; i < 6; ++i) x[i] = st->x[i];
+    } else {
+      s_log(&P, x);
+    }
+    sh->gmax = gradient_max_norm(P, x, g);
+    if (ctx.dbg) ctx.dbg[5] += (unsigned long long)(clock64() - ta0);
+  } else if (threadIdx.x == 64) {
+    double H[21], g[6], sc[6];
+    for (int i = 0; i < 21; ++i) H[i] = tot[i];
+    for (int i = 0; i < 6; ++i) {
+      g[i] = tot[21 + i];
+      sc[i] = iter0 ? 1.0 / (1.0 + sqrt(H[tri(i, i)])) : st->scale[i];          // jacobi scaling (iteration 0 only)
+    }
+    const double mu0 = iter0 ? 1e-8 : fmax(1e-8, 2.0 * st->mu_lm / 10.0);        // kMinMu / StepAccepted
+    gn_model(H, g, sc, mu0, sh->model);
+    if (ctx.dbg) ctx.dbg[6] += (unsigned long long)(clock64() - ta0);
+  } else if (threadIdx.x == 96) {
+    if (!iter0) s_log(&st->candq, sh->cand);
+    if (ctx.dbg) ctx.dbg[7] += (unsigned long long)(clock64() - ta0);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  // ---------------- phase B: the state machine proper ----------------
+  if (ctx.dbg) ctx.dbg[15] = (unsigned long long)clock64();
   const double cost = tot[27];
   for (int k = 0; k < 4; ++k) st->slot_sum[k] = tot[28 + k];
   tloam_b200_outer_trace* ot = outer_trace(io);
   if (!isfinite(cost)) { st->status = TLOAM_B200_ERR_NUMERIC; finish_frame(io); return; }
 
-  if (st->phase == kPhaseIter0) {
+  if (iter0) {
     // ---- IterationZero ----
-    st->iter = 0; st->num_invalid = 0; st->reuse = 0; st->last_cand_valid = 0;
-    st->radius = 1e4; st->mu_lm = 1e-8;                                 // initial_trust_region_radius, kMinMu
+    st->iter = 0; st->num_invalid = 0; st->last_cand_valid = 0;
+    st->radius = 1e4;                                                    // initial_trust_region_radius
     int nf_total = 0;
     for (int k = 0; k < 4; ++k) {
       const int nf = (int)(tot[32 + k] + 0.5);
       nf_total += nf;
       if (ot) ot->n_factors[k] = nf;
     }
-    if (ot) for (int i = 0; i < 6; ++i) ot->x_start[i] = st->x[i];
     st->x_cost = cost;
     for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
-    for (int i = 0; i < 6; ++i) st->g[i] = tot[21 + i];
+    for (int i = 0; i < 6; ++i) { st->g[i] = tot[21 + i]; st->scale[i] = sh->model.scale[i]; }
     if (ot) {
       ot->initial_cost = cost;
       for (int i = 0; i < 6; ++i) {
+        ot->x_start[i] = st->x[i];
         ot->g0[i] = st->g[i];
         for (int j = 0; j < 6; ++j) ot->H0[i * 6 + j] = (i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)];
       }
     }
+    st->mu_lm = 1e-8; st->reuse = 0; st->model_ok = 0;
     if (nf_total == 0) { end_of_solve(io, 5); return; }                  // no residual blocks
-    for (int i = 0; i < 6; ++i) st->scale[i] = 1.0 / (1.0 + sqrt(st->H[tri(i, i)]));   // jacobi scaling
     st->x_norm = norm6(st->x);
-    if (gradient_max_norm(st, st->g) <= 1e-10) { end_of_solve(io, 3); return; }
+    if (sh->gmax <= 1e-10) { end_of_solve(io, 3); return; }              // GradientToleranceReached
+    install_model(st, sh->model);
+    st->model_ok = sh->model.ok; st->reuse = 1;
+    TL_STAMP(io, 11);
     advance(io);
+    TL_STAMP(io, 12);
     return;
   }
 
   // ---- the evaluation was at the candidate ----
+  for (int i = 0; i < 6; ++i) st->cand[i] = sh->cand[i];
   tloam_b200_inner_trace* it = inner_trace(io);
-  if (it) it->candidate_cost = cost;
+  if (it) {
+    it->candidate_cost = cost;
+    for (int i = 0; i < 6; ++i) it->x_candidate[i] = st->cand[i];
+  }
   {
     double d[6];
     for (int i = 0; i < 6; ++i) d[i] = st->x[i] - st->cand[i];
@@ -365,18 +485,22 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, const double* 
     for (int i = 0; i < 6; ++i) st->g[i] = tot[21 + i];
     if (rel < 0.25) st->radius *= 0.5;                                 // DoglegStrategy::StepAccepted
     if (rel > 0.75) st->radius = fmax(st->radius, 3.0 * st->step_norm);
-    st->mu_lm = fmax(1e-8, 2.0 * st->mu_lm / 10.0);
-    st->reuse = 0; st->last_cand_valid = 0;
+    st->last_cand_valid = 0;
     if (it) it->accepted = 1;
-    if (gradient_max_norm(st, st->g) <= 1e-10) { end_of_solve(io, 3); return; }
+    if (sh->gmax <= 1e-10) { st->mu_lm = fmax(1e-8, 2.0 * st->mu_lm / 10.0); end_of_solve(io, 3); return; }
+    install_model(st, sh->model);                                      // speculative model becomes current
+    st->model_ok = sh->model.ok; st->reuse = 1;
   } else {
     st->radius *= 0.5; st->reuse = 1;                                  // StepRejected
     for (int i = 0; i < 6; ++i) st->last_cand[i] = st->cand[i];
+    st->last_candq = st->candq;
     st->last_cand_cost = cost; st->last_cand_valid = 1;
     if (it) it->accepted = 0;
   }
   if (st->radius <= 1e-32) { end_of_solve(io, 4); return; }           // MinTrustRegionRadiusReached
+  TL_STAMP(io, 13);
   advance(io);
+  TL_STAMP(io, 14);
 }
 
 }  // namespace tloam

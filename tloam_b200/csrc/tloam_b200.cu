@@ -44,13 +44,19 @@ __global__ void k_map_bbox(MapBuildArgs a) {
       mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
       mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
+  __shared__ double s_mn[8][3], s_mx[8][3];
   if ((threadIdx.x & 31) == 0) {
-    MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      atomicMin(&h->bbox_enc[d], enc_ordered(mn[d]));
-      atomicMax(&h->bbox_enc[3 + d], enc_ordered(mx[d]));
-    }
+    for (int d = 0; d < 3; ++d) { s_mn[threadIdx.x >> 5][d] = mn[d]; s_mx[threadIdx.x >> 5][d] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {                       // 6 atomics per block (same-address atomics serialise in L2)
+    const int d = threadIdx.x;
+    double lo = s_mn[0][d], hi = s_mx[0][d];
+    for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) { lo = fmin(lo, s_mn[wi][d]); hi = fmax(hi, s_mx[wi][d]); }
+    MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+    atomicMin(&h->bbox_enc[d], enc_ordered(lo));
+    atomicMax(&h->bbox_enc[3 + d], enc_ordered(hi));
   }
 }
 
@@ -92,15 +98,30 @@ __global__ void k_map_insert(MapBuildArgs a) {
   a.rank_of[i] = atomicAdd(&table[s].w, 1u);
 }
 
-__global__ void k_map_offsets(MapBuildArgs a) {
+// start offsets of the occupied cells: block-level exclusive scan of the counts + ONE atomic per block on the
+// cloud's bump allocator (table sizes are multiples of the block size, so a block never straddles two clouds)
+__global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0;
-  while (c < 4 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
-  if (c >= 4) return;
+  while (c < 3 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
   uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
-  const unsigned cnt = table[s].w;
-  if (cnt > 0u) table[s].z = atomicAdd(&h->cursor[c], cnt);
+  const unsigned cnt = (s < h->tsize[c]) ? table[s].w : 0u;
+  // warp inclusive scan
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  __shared__ unsigned s_w[8];
+  __shared__ unsigned s_base;
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+    for (int wi = 0; wi < 8; ++wi) { const unsigned v = s_w[wi]; s_w[wi] = tot; tot += v; }
+    s_base = (tot > 0u) ? atomicAdd(&h->cursor[c], tot) : 0u;
+  }
+  __syncthreads();
+  if (cnt > 0u) table[s].z = s_base + s_w[warp] + (incl - cnt);
 }
 
 __global__ void k_map_scatter(MapBuildArgs a) {
@@ -137,11 +158,13 @@ __global__ void k_stage_source(const double* stage, DeviceCtx ctx, double* px, d
 struct Predict { double m[16]; };
 
 // scanMatching prologue, ref: registration.cpp:879-886, 961-964, 1027-1033.
-__global__ void k_begin_frame(DeviceCtx ctx, Predict pr) {
+__global__ void k_begin_frame(DeviceCtx ctx, const Predict* prp) {
+  const Predict pr = *prp;
   // zero the trace
   {
     unsigned* w = reinterpret_cast<unsigned*>(ctx.stats);
-    for (unsigned i = threadIdx.x; i < sizeof(tloam_b200_stats) / 4; i += blockDim.x) w[i] = 0u;
+    if (w) for (unsigned i = threadIdx.x; i < sizeof(tloam_b200_stats) / 4; i += blockDim.x) w[i] = 0u;
+    for (int i = threadIdx.x; i < ctx.blk_off[4]; i += blockDim.x) ctx.blk_count[i] = 0;   // buffer 0 (outer 0)
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -164,7 +187,7 @@ __global__ void k_begin_frame(DeviceCtx ctx, Predict pr) {
     const double nn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     for (int j = 0; j < 3; ++j) st->x[3 + j] = d[j] / nn * 1e-4;
   }
-  for (int i = 0; i < 6; ++i) ctx.stats->x_init[i] = st->x[i];
+  if (ctx.stats) for (int i = 0; i < 6; ++i) ctx.stats->x_init[i] = st->x[i];
   st->xq = se3_exp(st->x);
   st->evalq = st->xq;
   st->phase = kPhaseIter0;
@@ -181,35 +204,29 @@ __global__ void k_begin_frame(DeviceCtx ctx, Predict pr) {
   for (int k = 0; k < 4; ++k) st->slot_sum[k] = 0.0;
 }
 
-// One feature of one cloud: GNC weight update (lazy), T*p, kNN, primitive fit.
-// ref: registration.cpp:440-493 (edge), 531-551 (sphere), 584-625 (planar), 727-768 (ground), 858-876.
-__device__ __forceinline__ unsigned char correspond_one(const DeviceCtx& ctx, int c, const Rt& T, double px, double py,
-                                                        double pz, double prim[6]) {
-  double qx, qy, qz;
-  rt_apply(T, px, py, pz, qx, qy, qz);
-  const double rx = qx - ctx.origin[0], ry = qy - ctx.origin[1], rz = qz - ctx.origin[2];
+// Primitive fit + validity tests of one feature given its (already merged) neighbour list.
+// ref: registration.cpp:445-493 (edge), 536-551 (sphere), 589-625 (planar), 732-768 (ground).
+template <int K>
+__device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, const TopK<K>& t, double prim[6]) {
   const GridDesc& g = ctx.grid[c];
+  const double o0 = ctx.origin[0], o1 = ctx.origin[1], o2 = ctx.origin[2];
 #pragma unroll
   for (int j = 0; j < 6; ++j) prim[j] = 0.0;
-  if (c == kSphere) {
-    TopK<1> t;
-    knn_search<1>(g, rx, ry, rz, ctx.r2[c], t);
+  if (K == 1) {                                            // sphere
     if (t.pos[0] < 0) return kFlagCounted;                 // not found: sphere_sum++ (:551)
     if (t.d2[0] > 0.2) return 0;                           // squared distance vs 0.2, `continue` (:536)
     const float4 m = __ldg(&g.pts[t.pos[0]]);
-    prim[0] = ctx.origin[0] + (double)m.x; prim[1] = ctx.origin[1] + (double)m.y; prim[2] = ctx.origin[2] + (double)m.z;
+    prim[0] = o0 + (double)m.x; prim[1] = o1 + (double)m.y; prim[2] = o2 + (double)m.z;
     return kFlagCand | kFlagCounted;
   }
-  TopK<5> t;
-  knn_search<5>(g, rx, ry, rz, ctx.r2[c], t);
   const int k = t.count();
   if (k <= 0) return 0;
-  double nb[5][3];
+  double nb[K][3];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
+  for (int j = 0; j < K; ++j) {
     if (j < k) {
       const float4 m = __ldg(&g.pts[t.pos[j]]);
-      nb[j][0] = ctx.origin[0] + (double)m.x; nb[j][1] = ctx.origin[1] + (double)m.y; nb[j][2] = ctx.origin[2] + (double)m.z;
+      nb[j][0] = o0 + (double)m.x; nb[j][1] = o1 + (double)m.y; nb[j][2] = o2 + (double)m.z;
     } else {
       nb[j][0] = nb[j][1] = nb[j][2] = 0.0;
     }
@@ -236,25 +253,49 @@ __device__ __forceinline__ unsigned char correspond_one(const DeviceCtx& ctx, in
   }
   if (k <= 4) return 0;                                     // :589 / :732
   double nd[4];
-  fit_best_plane(nb, 5, nd);                                // :600 / :743
+  fit_best_plane(nb, K, nd);                                // :600 / :743
 #pragma unroll
-  for (int j = 0; j < 5; ++j)
+  for (int j = 0; j < K; ++j)
     if (nd[0] * nb[j][0] + nd[1] * nb[j][1] + nd[2] * nb[j][2] + nd[3] > 0.2) return 0;   // one-sided, :605-613
   prim[0] = nd[0]; prim[1] = nd[1]; prim[2] = nd[2]; prim[3] = nd[3];
   return kFlagCand | kFlagCounted;                          // surf_num++ / ground_num++
 }
 
+// Correspondence search + primitive fit, one feature per thread (block = one 128-feature block of one cloud).
+// Also applies the lazy GNC weight update of the previous outer iteration (ref: registration.cpp:858-876) and
+// resets the residual slot (:1118-1121).  (Lane-group variants -- 8 lanes per feature with shuffle-merged or
+// rank-counted candidate lists, see map_grid.cuh -- were measured slower on B200: 47-62 us vs 35 us.)
 __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ DeviceCtx ctx) {
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != kPhaseIter0) return;
-  const int b = blockIdx.x;
-  const int c = cloud_of_block(ctx, b);
-  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  __shared__ unsigned s_beg[27][kBlk];
+  __shared__ unsigned s_cnt[27][kBlk];
+  const int fb = blockIdx.x;
+  const int c = cloud_of_block(ctx, fb);
+  const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
   const int gi = ctx.pad_off[c] + il;
   const bool live = (il < ctx.n[c]) && cloud_enabled(ctx, c);
+  const int buf = st->outer & 1;
+  long long tk0 = 0, tk1 = 0;
+  if (ctx.dbg) tk0 = clock64();
   unsigned char flag = 0;
   if (live) {
-    // lazy updateWeight of the previous outer iteration (:858-876) + slot reset (:1118-1121)
+    const Rt T = pose_to_rt(st->xq);
+    double qx, qy, qz;
+    rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
+    const double rx = qx - ctx.origin[0], ry = qy - ctx.origin[1], rz = qz - ctx.origin[2];
+    double prim[6];
+    if (c == kSphere) {
+      TopK<1> t;
+      knn_search_mlp<1, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, t);
+      if (ctx.dbg) tk1 = clock64();
+      flag = fit_one<1>(ctx, c, t, prim);
+    } else {
+      TopK<5> t;
+      knn_search_mlp<5, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, t);
+      if (ctx.dbg) tk1 = clock64();
+      flag = fit_one<5>(ctx, c, t, prim);
+    }
     if (st->outer == 0) {
       ctx.w[gi] = 1.0;                                                            // :931-949
     } else {
@@ -268,15 +309,17 @@ __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ Dev
       }
     }
     ctx.slot[gi] = 0.0;
-    const Rt T = pose_to_rt(st->xq);
-    double prim[6];
-    flag = correspond_one(ctx, c, T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], prim);
 #pragma unroll
     for (int j = 0; j < 6; ++j) ctx.prim[j][gi] = prim[j];
   }
   ctx.flags[gi] = flag;
+  if (ctx.dbg && threadIdx.x == 0 && live) {
+    atomicAdd(&ctx.dbg[8], (unsigned long long)(tk1 - tk0));
+    atomicAdd(&ctx.dbg[10], (unsigned long long)(clock64() - tk1));
+    atomicAdd(&ctx.dbg[9], 1ull);
+  }
   const int cnt = __syncthreads_count((flag & kFlagCounted) != 0);
-  if (threadIdx.x == 0) ctx.blk_count[b] = cnt;
+  if (threadIdx.x == 0) ctx.blk_count[buf * ctx.blk_cap + fb] = cnt;
 }
 
 // `*_maxnum` caps in feature-index order (Q8): factor i is active iff it is a candidate and the number of
@@ -286,7 +329,8 @@ __device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int 
   // counted features in previous blocks of this cloud
   int before = 0;
   if (threadIdx.x < 32) {
-    for (int bb = ctx.blk_off[c] + (int)threadIdx.x; bb < b; bb += 32) before += ctx.blk_count[bb];
+    const int* cntbuf = ctx.blk_count + (ctx.st->outer & 1) * ctx.blk_cap;
+    for (int bb = ctx.blk_off[c] + (int)threadIdx.x; bb < b; bb += 32) before += cntbuf[bb];
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
   }
   const unsigned ballot = __ballot_sync(0xffffffffu, (flag & kFlagCounted) != 0);
@@ -308,6 +352,8 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
   __shared__ double s_tot[kNRed];
   __shared__ int s_warp[1 + kBlk / 32];
   __shared__ bool s_last;
+  unsigned long long tg0 = 0;
+  if (ctx.dbg && threadIdx.x == 0) { tg0 = gtime_ns(); atomicMin(&ctx.dbg[0], tg0); }
   const int b = blockIdx.x;
   const int c = cloud_of_block(ctx, b);
   const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
@@ -375,13 +421,24 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
     }
   }
   // ---- block reduction (fixed shape => run-to-run bit-reproducible) ----
-#pragma unroll
-  for (int i = 0; i < 30; ++i)
-    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  // warp level: butterfly "transpose" reduction -- 32 values across 32 lanes in 16+8+4+2+1 = 31 shuffles
+  // (instead of 5 per value); afterwards lane L holds the warp total of value L.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
+  {
+    double u[32];
 #pragma unroll
-    for (int i = 0; i < 30; ++i) s_red[warp][i] = v[i];
+    for (int i = 0; i < 32; ++i) u[i] = (i < 30) ? v[i] : 0.0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const double send = up ? u[i] : u[i + o];
+        const double keep = up ? u[i + o] : u[i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    if (lane < 30) s_red[warp][lane] = u[0];
   }
   __syncthreads();
   if (threadIdx.x < kNRed) {
@@ -406,24 +463,54 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
   if (!s_last) return;
   // ---- last block: deterministic sum of the per-block partials, then the solver state machine ----
   __threadfence();
-  if (threadIdx.x < kNRed) {
-    const int t = threadIdx.x;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    const int nb = gridDim.x;
-    int bb = 0;
-    for (; bb + 3 < nb; bb += 4) {
-      a0 += ctx.partial[(size_t)(bb + 0) * kNRed + t];
-      a1 += ctx.partial[(size_t)(bb + 1) * kNRed + t];
-      a2 += ctx.partial[(size_t)(bb + 2) * kNRed + t];
-      a3 += ctx.partial[(size_t)(bb + 3) * kNRed + t];
-    }
-    for (; bb < nb; ++bb) a0 += ctx.partial[(size_t)bb * kNRed + t];
-    s_tot[t] = (a0 + a1) + (a2 + a3);
+  unsigned long long tg1 = 0, tg2 = 0, tg3 = 0;
+  if (ctx.dbg && threadIdx.x == 0) tg1 = gtime_ns();
+  __shared__ double s_part[3][kNRed];
+  __shared__ FrameState s_state;
+  __shared__ SolverShared s_solver;
+  {
+    // the state machine is a long dependent chain: run it on a shared-memory copy of the state
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_state);
+    for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = src[i];
   }
+  if (threadIdx.x < 3 * kNRed) {
+    // 3 row groups x 36 columns, 8 independent accumulators each; the summation tree is fixed => deterministic
+    const int col = threadIdx.x % kNRed, grp = threadIdx.x / kNRed;
+    const int nb = gridDim.x;
+    const double* P = ctx.partial + col;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int r = grp;
+    for (; r + 21 < nb; r += 24) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldcg(P + (size_t)(r + 3 * u) * kNRed);
+    }
+    for (; r < nb; r += 3) a[0] += __ldcg(P + (size_t)r * kNRed);
+    s_part[grp][col] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+  __syncthreads();
+  if (threadIdx.x < kNRed) s_tot[threadIdx.x] = (s_part[0][threadIdx.x] + s_part[1][threadIdx.x]) + s_part[2][threadIdx.x];
   __syncthreads();
   if (threadIdx.x == 0) {
     *ctx.counter = 0u;
-    solver_on_eval(ctx, s_tot);
+    if (ctx.dbg) tg2 = gtime_ns();
+  }
+  solver_on_eval(ctx, &s_state, s_tot, &s_solver);      // all threads enter (3 helper warps + thread 0)
+  if (threadIdx.x == 0) {
+    if (ctx.dbg) {
+      tg3 = gtime_ns();
+      ctx.dbg[1] += tg1 - ctx.dbg[0];   // parallel phase: first block start -> last block arrives
+      ctx.dbg[2] += tg2 - tg1;          // final partial sum
+      ctx.dbg[3] += tg3 - tg2;          // solver state machine
+      ctx.dbg[4] += 1ull;
+      ctx.dbg[0] = ~0ull;
+    }
+  }
+  __syncthreads();
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_state);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
+    for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = src[i];
   }
 }
 
@@ -437,6 +524,7 @@ __global__ void __launch_bounds__(kBlk) k_caps(const __grid_constant__ DeviceCtx
 }
 
 __global__ void k_set_pose(DeviceCtx ctx, Predict x6) {   // x6.m[0..5] = tangent
+  for (int i = threadIdx.x; i < ctx.blk_off[4]; i += blockDim.x) ctx.blk_count[i] = 0;
   if (threadIdx.x != 0) return;
   FrameState* st = ctx.st;
   for (int i = 0; i < 6; ++i) st->x[i] = x6.m[i];
@@ -571,13 +659,19 @@ struct tloam_b200_handle {
   tloam_b200_stats* h_stats = nullptr;
   DeviceCtx ctx;
   int total_blocks = 0;
+  // whole-frame CUDA graph (re-captured only when the device context changes)
+  Predict* h_predict = nullptr; Predict* d_predict = nullptr;
+  cudaGraphExec_t gexec = nullptr; DeviceCtx gctx; bool gvalid = false; int glaunches = 0; bool use_graph = true;
   // optional per-kernel-class timing (CUDA events around every launch; off by default)
   bool profiling = false;
+  bool traced_last = false;
+  bool trace = false;                                           // record tloam_b200_stats traces
   std::vector<cudaEvent_t> ev_pool;
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> spans;
   size_t ev_next = 0;
   tloam_b200_profile prof;
+  unsigned long long* d_dbg = nullptr;
 };
 
 // launch bookkeeping: counts the kernel and, in profiling mode, brackets it with events
@@ -660,6 +754,9 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMalloc(&h->d_counter, 256) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMallocHost(&h->h_result, 32 * sizeof(double)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMallocHost(&h->h_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMallocHost(&h->h_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
   FrameState init;
   memset(&init, 0, sizeof(init));
@@ -679,9 +776,12 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_stage_src); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
   cudaFree(h->d_partial); cudaFree(h->d_counter); cudaFree(h->d_state); cudaFree(h->d_stats);
-  cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob);
+  cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->h_predict) cudaFreeHost(h->h_predict);
+  cudaFree(h->d_predict);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -700,7 +800,7 @@ static void fill_ctx_config(tloam_b200_handle* h) {
   c.edge_dir_thres = f.edge_dir_thres; c.cost_threshold = f.cost_threshold; c.gnc_factor = f.gnc_factor;
   c.noise_bound = f.noise_bound; c.fitness_thres = f.fitness_thres;
   for (int k = 0; k < 3; ++k) c.reinit_dir[k] = f.reinit_dir[k];
-  c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;
+  c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;   // stats may be nulled per call (no trace)
 }
 
 static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
@@ -730,7 +830,8 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   if ((size_t)blocks > h->cap_blocks) {
     cudaFree(h->d_blk_count); cudaFree(h->d_partial);
     h->cap_blocks = h->cap_pad / kBlk + 8;
-    CU_TRY(cudaMalloc(&h->d_blk_count, h->cap_blocks * sizeof(int)));
+    CU_TRY(cudaMalloc(&h->d_blk_count, 2 * h->cap_blocks * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(h->d_blk_count, 0, 2 * h->cap_blocks * sizeof(int), h->stream));
     CU_TRY(cudaMalloc(&h->d_partial, h->cap_blocks * kNRed * sizeof(double)));
   }
   DeviceCtx& c = h->ctx;
@@ -755,7 +856,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   c.px = f; c.py = f + cp; c.pz = f + 2 * cp; c.w = f + 3 * cp; c.slot = f + 4 * cp;
   for (int j = 0; j < 6; ++j) c.prim[j] = f + (5 + j) * cp;
   c.flags = h->d_flags; c.active = h->d_flags + cp;
-  c.blk_count = h->d_blk_count; c.partial = h->d_partial;
+  c.blk_count = h->d_blk_count; c.blk_cap = (int)h->cap_blocks; c.partial = h->d_partial;
   h->total_blocks = c.blk_off[4];
   if (h->total_blocks > 0) {
     TL_LAUNCH(TLOAM_B200_K_STAGE_SOURCE, (k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(h->d_stage_src, c, f, f + cp, f + 2 * cp, soff[0], soff[1], soff[2], soff[3])));
@@ -773,7 +874,7 @@ int tloam_b200_set_source_device(tloam_b200_handle* h, const double* const xyz[4
   return set_source_impl(h, xyz, n, true);
 }
 
-static unsigned next_pow2(size_t v) { unsigned p = 64; while ((size_t)p < v) p <<= 1; return p; }
+static unsigned next_pow2(size_t v) { unsigned p = 256; while ((size_t)p < v) p <<= 1; return p; }
 
 static int layout_map(tloam_b200_handle* h, const size_t n[4]) {
   MapHeader& hd = h->hdr;
@@ -943,32 +1044,67 @@ static int check_ready(tloam_b200_handle* h) {
   return TLOAM_B200_OK;
 }
 
-int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) {
-  if (!h || !predict) return TLOAM_B200_ERR_INVALID_ARG;
-  const int rc = check_ready(h);
-  if (rc != TLOAM_B200_OK) return rc;
-  CU_TRY(cudaSetDevice(h->device));
-  Predict pr;
-  memcpy(pr.m, predict, sizeof(pr.m));
-  const DeviceCtx& c = h->ctx;
+// enqueues the frame's fixed launch sequence on h->stream (also used under stream capture)
+static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   const int nb = h->total_blocks;
-  const long long launches0 = h->launches;
-  CU_TRY(cudaEventRecord(h->ev0, h->stream));
-  TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, pr)));
+  CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
+  TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, h->d_predict)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
     TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<<<nb, kBlk, 0, h->stream>>>(c)));
     TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true><<<nb, kBlk, 0, h->stream>>>(c)));
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
       TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false><<<nb, kBlk, 0, h->stream>>>(c)));
   }
-  CU_TRY(cudaEventRecord(h->ev1, h->stream));
-  const int launches = (int)(h->launches - launches0);
-  CU_TRY(cudaGetLastError());
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaMemcpyAsync(h->h_result + 16, (const char*)h->d_state + offsetof(FrameState, frame_done), 2 * sizeof(int),
                          cudaMemcpyDeviceToHost, h->stream));
-  h->launches_frame = launches;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) {
+  if (!h || !predict) return TLOAM_B200_ERR_INVALID_ARG;
+  const int rc = check_ready(h);
+  if (rc != TLOAM_B200_OK) return rc;
+  CU_TRY(cudaSetDevice(h->device));
+  memcpy(h->h_predict->m, predict, sizeof(Predict));
+  DeviceCtx c = h->ctx;
+  if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
+  const int per_frame = 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);
+  CU_TRY(cudaEventRecord(h->ev0, h->stream));
+  if (h->use_graph && !h->profiling) {
+    // one graph launch per frame; the graph is re-captured only when the device context changed
+    if (!h->gvalid || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0) {
+      if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+      h->gvalid = false;
+      cudaGraph_t graph = nullptr;
+      CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const long long l0 = h->launches;
+      const int erc = enqueue_frame(h, c);
+      h->launches = l0;                           // capture does not execute anything
+      cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+      if (erc != TLOAM_B200_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        snprintf(h->last_error, sizeof(h->last_error), "graph capture failed: %s", cudaGetErrorString(ce));
+        return TLOAM_B200_ERR_CUDA;
+      }
+      ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
+      h->gctx = c;
+      h->gvalid = true;
+    }
+    CU_TRY(cudaGraphLaunch(h->gexec, h->stream));
+    h->launches += per_frame;
+  } else {
+    const int erc = enqueue_frame(h, c);
+    if (erc != TLOAM_B200_OK) return erc;
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  h->launches_frame = per_frame;
+  h->traced_last = h->trace;
   h->frame_pending = true;
   return TLOAM_B200_OK;
 }
@@ -977,7 +1113,8 @@ int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_st
   if (!h || !result) return TLOAM_B200_ERR_INVALID_ARG;
   if (!h->frame_pending) return TLOAM_B200_ERR_NOT_READY;
   CU_TRY(cudaSetDevice(h->device));
-  if (stats) CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(tloam_b200_stats), cudaMemcpyDeviceToHost, h->stream));
+  if (stats && !h->traced_last) memset(h->h_stats, 0, sizeof(tloam_b200_stats));
+  if (stats && h->traced_last) CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(tloam_b200_stats), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   h->frame_pending = false;
   memcpy(result, h->h_result, 16 * sizeof(double));
@@ -995,9 +1132,19 @@ int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_st
 }
 
 int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double result[16], tloam_b200_stats* stats) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  const bool saved = h->trace;
+  if (stats) h->trace = true;                   // the blocking form knows whether the caller wants the trace
   int rc = tloam_b200_scan_match_async(h, predict);
+  h->trace = saved;
   if (rc != TLOAM_B200_OK) return rc;
   return tloam_b200_get_result(h, result, stats);
+}
+
+int tloam_b200_set_trace(tloam_b200_handle* h, int on) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  h->trace = on != 0;
+  return TLOAM_B200_OK;
 }
 
 int tloam_b200_synchronize(tloam_b200_handle* h) {
@@ -1111,7 +1258,7 @@ int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6],
   memcpy(pr.m, x, 6 * sizeof(double));
   DeviceCtx c = h->ctx;
   c.factor_num = 4;   // build every cloud regardless of the configured subset
-  k_set_pose<<<1, 32, 0, h->stream>>>(c, pr);
+  k_set_pose<<<1, 256, 0, h->stream>>>(c, pr);
   k_correspond<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
   k_caps<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
   h->launches += 3;
@@ -1227,6 +1374,14 @@ int tloam_b200_set_profiling(tloam_b200_handle* h, int on) {
   h->profiling = on != 0;
   h->spans.clear(); h->ev_next = 0;
   memset(&h->prof, 0, sizeof(h->prof));
+  if (on && !h->d_dbg) CU_TRY(cudaMalloc(&h->d_dbg, 16 * sizeof(unsigned long long)));
+  if (h->d_dbg) {
+    unsigned long long init[16];
+    memset(init, 0, sizeof(init));
+    init[0] = ~0ull;
+    CU_TRY(cudaMemcpy(h->d_dbg, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  h->ctx.dbg = on ? h->d_dbg : nullptr;
   return TLOAM_B200_OK;
 }
 
@@ -1242,6 +1397,7 @@ int tloam_b200_get_profile(tloam_b200_handle* h, tloam_b200_profile* out) {
     }
   }
   h->spans.clear(); h->ev_next = 0;
+  if (h->d_dbg) CU_TRY(cudaMemcpy(h->prof.dbg, h->d_dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   *out = h->prof;
   return TLOAM_B200_OK;
 }

@@ -176,7 +176,9 @@ class LocalRegistration:
         """dict kernel-class -> (launches, total_ms), from CUDA events around every launch."""
         p = _lib.Profile()
         self._check(self._L.tloam_b200_get_profile(self._h, C.byref(p)), "get_profile")
-        return {k: (int(p.launches[i]), float(p.total_ms[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+        out = {k: (int(p.launches[i]), float(p.total_ms[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+        self.last_dbg = [int(v) for v in p.dbg]
+        return out
 
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):

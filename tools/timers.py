@@ -1,0 +1,25 @@
+"""In-kernel timer breakdown (profiling mode) for a few frames of the bench workload."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import bench, tloam_b200
+
+frames, prev_gt = bench.gen_frames("00", 5)
+reg = tloam_b200.LocalRegistration(**bench.CAPS)
+last, cur = prev_gt.copy(), None
+for k, fr in enumerate(frames):
+    if k == 2:
+        reg.set_profiling(True)
+    predict = bench.first_predict(fr) if cur is None else bench.predict_next(last, cur)
+    reg.set_input_target(fr["map"]); reg.set_input_source(fr["scan"])
+    T, st = reg.scan_matching(predict, want_stats=True)
+    last, cur = (cur if cur is not None else prev_gt), T
+    print("frame", k, "gpu_ms", round(st.gpu_ms, 3))
+prof = reg.get_profile()
+d = reg.last_dbg
+n = max(d[4], 1)
+print({k: (v[0], round(1e3 * v[1] / max(v[0], 1), 2)) for k, v in prof.items()})
+print(f"k_eval active launches={d[4]}: parallel {d[1]/n/1e3:.2f} us, partial-sum {d[2]/n/1e3:.2f} us, solver {d[3]/n/1e3:.2f} us")
+print(f"k_correspond: blocks={d[9]} avg kNN-phase cycles/block={d[8]/max(d[9],1):.0f} fit-phase cycles/block={d[10]/max(d[9],1):.0f}")
+print("solver stages (avg SM cycles per active eval): pre-model(decision+gradcheck+trace) %.0f, compute_model %.0f, dogleg+mcc %.0f, plus(exp,mul,log) %.0f" % tuple(d[i] / n for i in (11, 12, 13, 14)))
+print("phase A chains (avg SM cycles): gmax %.0f, gn_model %.0f, log(cand) %.0f" % tuple(d[i] / n for i in (5, 6, 7)))
