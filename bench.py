@@ -247,6 +247,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the registration path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -254,7 +257,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seq = SEQS[rank % len(SEQS)]
+    from tloam_b200 import multi
+    seq = multi.sequence_for_rank(rank)
     total = args.warmup + args.steps
     frames, prev_gt = gen_frames(seq, total)
     n_feat = [int(c.shape[0]) for c in frames[0]["scan"]]
@@ -305,23 +309,20 @@ def main():
     # ---- shared-map broadcast of config 4 (NCCL), timed separately ----
     bcast = None
     if world > 1:
-        n = reg.map_blob_size()
-        buf = torch.empty(n, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            reg.map_export(buf.data_ptr(), n)
+        dev = torch.device("cuda", local_rank)
         for _ in range(3):
-            dist.broadcast(buf, src=0)
+            multi.broadcast_shared_map(reg, src=0, device=dev)        # warm-up (rank 0's last map)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            dist.broadcast(buf, src=0)
+            n = multi.broadcast_shared_map(reg, src=0, device=dev)    # size handshake + export + ncclBroadcast + import
         e1.record()
         torch.cuda.synchronize()
         tb = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        reg.map_import(buf.data_ptr(), n)
-        bcast = {"bytes": n, "ms": float(tb[0]), "GBps": n / (float(tb[0]) * 1e-3) / 1e9}
+        bcast = {"bytes": n, "ms": float(tb[0]), "GBps": n / (float(tb[0]) * 1e-3) / 1e9,
+                 "what": "export (D2D) + ncclBroadcast + import (D2D) of the built map blob, max over ranks"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None
