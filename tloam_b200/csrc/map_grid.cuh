@@ -157,25 +157,37 @@ __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double 
 // ------------------------------------------------------------------------------------------------
 template <int K, int kThreads>
 __device__ __forceinline__ void knn_search_mlp(const GridDesc& g, double rx, double ry, double rz, double r2,
-                                               unsigned (*s_beg)[kThreads], unsigned (*s_cnt)[kThreads], TopK<K>& t) {
+                                               unsigned (*s_beg)[kThreads], unsigned (*s_cnt)[kThreads],
+                                               float (*s_md)[kThreads], TopK<K>& t) {
   t.init();
   if (g.n == 0u) return;
   const int tid = threadIdx.x;
   const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
+  // position of the query inside its cell -> lower bound of the distance to each neighbour cell
+  // (FP32 is enough for a bound that is rounded down by 1e-4 before use)
+  const float cellf = (float)g.cell, r2f = (float)r2;
+  const float fx = (float)(rx - (double)cx * g.cell), fy = (float)(ry - (double)cy * g.cell), fz = (float)(rz - (double)cz * g.cell);
+  const float lo[3] = {fx, fy, fz};
+  const float hi[3] = {cellf - fx, cellf - fy, cellf - fz};
   int m = 0;
+  // visiting order: centre cell first, then by slab; the lower bounds let stage 2 skip cells that cannot
+  // improve a full list (dense maps: the centre cell alone usually fills it)
 #pragma unroll
-  for (int dz = -1; dz <= 1; ++dz) {
+  for (int slab = 0; slab < 3; ++slab) {
+    const int dz = (slab == 0) ? 0 : (slab == 1 ? -1 : 1);
     unsigned long long key[9];
     uint4 e[9];
     unsigned slot[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      key[j] = cell_key(cx + (j % 3) - 1, cy + (j / 3) - 1, cz + dz);
+      const int jj = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);       // centre column first
+      key[j] = cell_key(cx + (jj % 3) - 1, cy + (jj / 3) - 1, cz + dz);
       slot[j] = hash_key(key[j]) & g.mask;
       e[j] = __ldg(&g.table[slot[j]]);
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
+      const int jj = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);
       unsigned long long k = ((unsigned long long)e[j].y << 32) | e[j].x;
       while (k != key[j] && k != 0ull) {          // collision (rare): keep probing
         slot[j] = (slot[j] + 1u) & g.mask;
@@ -183,9 +195,18 @@ __device__ __forceinline__ void knn_search_mlp(const GridDesc& g, double rx, dou
         k = ((unsigned long long)e[j].y << 32) | e[j].x;
       }
       if (k == key[j] && e[j].w != 0u) {
-        s_beg[m][tid] = e[j].z;
-        s_cnt[m][tid] = e[j].w;
-        ++m;
+        const int ox = (jj % 3) - 1, oy = (jj / 3) - 1;
+        const float mx = ox < 0 ? lo[0] : (ox > 0 ? hi[0] : 0.0f);
+        const float my = oy < 0 ? lo[1] : (oy > 0 ? hi[1] : 0.0f);
+        const float mz = dz < 0 ? lo[2] : (dz > 0 ? hi[2] : 0.0f);
+        // rounded DOWN so that FP32 arithmetic can never overstate the bound
+        const float md = fmaxf(mx * mx + my * my + mz * mz, 0.0f) * 0.9999f - 1e-12f;
+        if (md < r2f) {                           // otherwise no point of the cell lies inside the radius
+          s_md[m][tid] = md;
+          s_beg[m][tid] = e[j].z;
+          s_cnt[m][tid] = e[j].w;
+          ++m;
+        }
       }
     }
   }
@@ -196,6 +217,7 @@ __device__ __forceinline__ void knn_search_mlp(const GridDesc& g, double rx, dou
   while (ci < m) {
     float4 pt[8];
     int pos[8];
+    const double worst = t.d2[K - 1];             // +inf until the list is full
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       pos[q] = -1;
@@ -204,6 +226,7 @@ __device__ __forceinline__ void knn_search_mlp(const GridDesc& g, double rx, dou
         pt[q] = __ldg(&g.pts[pos[q]]);
         if (++off == cc) {
           ++ci; off = 0u;
+          while (ci < m && (double)s_md[ci][tid] > worst) ++ci;   // no point of that cell can enter the list
           if (ci < m) { cb = s_beg[ci][tid]; cc = s_cnt[ci][tid]; }
         }
       }

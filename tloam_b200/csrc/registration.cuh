@@ -32,6 +32,7 @@ constexpr int kBlk = 128;     // threads per block for all per-feature kernels
 constexpr int kLpq = 8;       // lanes cooperating on one feature's kNN in k_correspond
 constexpr int kQpb = 32;      // features per k_correspond thread block (kNN in kQpb*kLpq/kBlk rounds, fit by warp 0)
 constexpr int kNRed = 36;     // 21 (H upper) + 6 (g) + 1 (cost) + 4 (slot sum per cloud) + 4 (factors per cloud)
+constexpr int kEvalGridCap = 592;   // 148 SMs x 4: caps the rows of the final partial sum
 constexpr int kEdge = 0, kSphere = 1, kPlanar = 2, kGround = 3;
 
 // flags per feature written by k_correspond
@@ -59,7 +60,8 @@ struct FrameState {
   int last_cand_valid, outer, sub_valid, model_ok;
   double radius, mu_lm, x_cost, x_norm, model_cost_change, step_norm, gn_norm;
   double scale[6], H[21], g[6];
-  double D[6], sgrad[6], gn[6], sub_basis[12], sub_g[2], sub_B[4];
+  double d2[6], y[6];                        // Gauss-Newton model (see solver.cuh: GnModel)
+  double D[6], sgrad[6], gn[6], sub_basis[12], sub_g[2], sub_B[4];   // filled lazily (subspace dogleg only)
   double last_cand[6], last_cand_cost;
   Pose7 last_candq;
   // ---- GNC state ----

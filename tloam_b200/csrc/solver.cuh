@@ -33,39 +33,45 @@ __device__ __forceinline__ double norm6(const double* v) {
   return sqrt(s);
 }
 
-// Cholesky solve of the SPD 6x6 system A y = b (fully unrolled: everything stays in registers).
-// Returns false if a pivot is not positive / finite.
-__device__ __noinline__ bool chol_solve6(const double A[36], const double b[6], double y[6]) {
-  double L[36];
-  double inv[6];
+// LDL^T solve of the SPD 6x6 system A y = b, fully unrolled (registers only, ~160 FP64 instructions, six
+// reciprocals, no square roots).  Returns false if a pivot is not positive / finite.
+__device__ __forceinline__ bool ldlt_solve6(const double A[36], const double b[6], double y[6]) {
+  double L[36], d[6], dinv[6];
   bool ok = true;
-  for (int i = 0; i < 6; ++i) {
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-      if (i == j) {
-        ok = ok && (s > 0.0) && isfinite(s);
-        const double d = sqrt(s);
-        L[i * 6 + i] = d;
-        inv[i] = 1.0 / d;
-      } else {
-        L[i * 6 + j] = s * inv[j];
-      }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j * 6 + k] * L[j * 6 + k] * d[k];
+    d[j] = s;
+    ok = ok && (s > 0.0) && isfinite(s);
+    dinv[j] = 1.0 / s;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i * 6 + k] * L[j * 6 + k] * d[k];
+      L[i * 6 + j] = t * dinv[j];
     }
   }
   if (!ok) return false;
   double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
-    double s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * z[k];
-    z[i] = s * inv[i];
+    double t = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= L[i * 6 + k] * z[k];
+    z[i] = t;
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
-    double s = z[i];
-    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
-    y[i] = s * inv[i];
+    double t = z[i] * dinv[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) t -= L[k * 6 + i] * y[k];
+    y[i] = t;
   }
   bool fin = true;
+#pragma unroll
   for (int i = 0; i < 6; ++i) fin = fin && isfinite(y[i]);
   return fin;
 }
@@ -107,44 +113,56 @@ __device__ __noinline__ void min_on_boundary_2d(const double B[4], const double 
   y[0] = radius * c; y[1] = radius * s;
 }
 
-// Gauss-Newton model of DoglegStrategy::ComputeStep (first call after an accepted / invalid step):
-// diagonal, scaled gradient, regularised Gauss-Newton step.  All inputs by value (registers).
+// Gauss-Newton model of DoglegStrategy::ComputeStep (first call after an accepted / invalid step), reduced to
+// what the common path needs.  With D^2_i = clamp((S H S)_ii), the regularised Gauss-Newton solve is
+//   (S H S + mu D^2) y = S g,   gauss_newton_step = -D.y,   dogleg step inside the radius = gn / D = -y,
+// so neither D nor the scaled gradient is needed unless the step leaves the trust region (computed lazily in
+// compute_subspace).  |D.y| = sqrt(sum D^2_i y_i^2): one square root.
 struct GnModel {
   double scale[6];     // jacobi scaling used
-  double D[6], sgrad[6], gn[6];
+  double d2[6];        // clamped squared column norms of the scaled Jacobian (= D^2)
+  double y[6];         // solution of the regularised normal equations
   double gn_norm, mu_lm;
   int ok;              // 0 = LINEAR_SOLVER_FAILURE
   int pad;
 };
 
-__device__ __noinline__ void gn_model(const double H[21], const double g[6], const double scale[6], double mu_lm,
+__device__ __forceinline__ void gn_model(const double H[21], const double g[6], const double scale[6], double mu_lm,
                                          GnModel& m) {
-  double Hs[36], gs[6];
+  double Hs[36], gs[6], d2[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
-    m.scale[i] = scale[i];
     gs[i] = scale[i] * g[i];
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
       const double h = (i <= j) ? H[tri(i, j)] : H[tri(j, i)];
       Hs[i * 6 + j] = scale[i] * h * scale[j];
     }
   }
-  for (int i = 0; i < 6; ++i) {
-    m.D[i] = sqrt(fmin(fmax(Hs[i * 6 + i], 1e-6), 1e32));      // min/max_lm_diagonal
-    m.sgrad[i] = gs[i] / m.D[i];
-  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d2[i] = fmin(fmax(Hs[i * 6 + i], 1e-6), 1e32);     // min/max_lm_diagonal
   bool ok = false;
   double y[6] = {0, 0, 0, 0, 0, 0};
   while (mu_lm < 1.0) {                                         // kMaxMu
     double A[36];
+#pragma unroll
     for (int i = 0; i < 36; ++i) A[i] = Hs[i];
-    for (int i = 0; i < 6; ++i) A[i * 6 + i] += mu_lm * m.D[i] * m.D[i];
-    if (chol_solve6(A, gs, y)) { ok = true; break; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[i * 6 + i] += mu_lm * d2[i];
+    if (ldlt_solve6(A, gs, y)) { ok = true; break; }
     mu_lm *= 10.0;                                              // mu_increase_factor_
   }
+  double n2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    m.scale[i] = scale[i];
+    m.d2[i] = d2[i];
+    m.y[i] = ok ? y[i] : 0.0;
+    n2 += d2[i] * m.y[i] * m.y[i];
+  }
+  m.gn_norm = sqrt(n2);
   m.mu_lm = mu_lm;
   m.ok = ok ? 1 : 0;
-  for (int i = 0; i < 6; ++i) m.gn[i] = ok ? -m.D[i] * y[i] : 0.0;
-  m.gn_norm = norm6(m.gn);
 }
 
 // single out-of-line copies of the Lie-group routines (the solver is instruction-fetch bound: keep it small)
@@ -234,7 +252,7 @@ __device__ __noinline__ void end_of_solve(const SolverIO& io, int termination) {
 }
 
 __device__ __noinline__ void install_model(FrameState* st, const GnModel& m) {
-  for (int i = 0; i < 6; ++i) { st->D[i] = m.D[i]; st->sgrad[i] = m.sgrad[i]; st->gn[i] = m.gn[i]; }
+  for (int i = 0; i < 6; ++i) { st->d2[i] = m.d2[i]; st->y[i] = m.y[i]; }
   st->gn_norm = m.gn_norm;
   st->mu_lm = m.mu_lm;
   st->sub_valid = 0;
@@ -243,6 +261,11 @@ __device__ __noinline__ void install_model(FrameState* st, const GnModel& m) {
 // subspace model (DoglegStrategy::ComputeSubspaceModel): orthonormal basis of span{sgrad, gn} and the 2x2
 // model in it.  Only needed when the Gauss-Newton step leaves the trust region, so it is computed lazily.
 __device__ __noinline__ bool compute_subspace(FrameState* st) {
+  for (int i = 0; i < 6; ++i) {               // the lazily needed vectors of the full model
+    st->D[i] = sqrt(st->d2[i]);
+    st->sgrad[i] = st->scale[i] * st->g[i] / st->D[i];
+    st->gn[i] = -st->D[i] * st->y[i];
+  }
   const double n0 = norm6(st->sgrad), n1 = st->gn_norm;
   const double* first = (n0 >= n1) ? st->sgrad : st->gn;
   const double* second = (n0 >= n1) ? st->gn : st->sgrad;
@@ -300,7 +323,7 @@ __device__ __noinline__ void advance(const SolverIO& io) {
     double step[6] = {0, 0, 0, 0, 0, 0};
     if (solver_ok) {                                                   // ComputeSubspaceDoglegStep
       if (st->gn_norm <= st->radius) {
-        for (int i = 0; i < 6; ++i) step[i] = st->gn[i] / st->D[i];
+        for (int i = 0; i < 6; ++i) step[i] = -st->y[i];              // gauss_newton_step / D
         st->step_norm = st->gn_norm; st->used_gn = 1;
       } else {
         if (!st->sub_valid) solver_ok = compute_subspace(st);
@@ -373,134 +396,196 @@ __device__ __noinline__ void advance(const SolverIO& io) {
 
 struct SolverShared {
   GnModel model;
-  double gmax;
-  double cand[6];
+  double proj[6];      // Plus(x, -g) for the state that becomes current if this evaluation is accepted
+  double cand[6];      // log(candidate pose)
+  FrameState backup;   // state before advance(), for the (practically never taken) gradient-tolerance exit
 };
 
-// Entered by ALL threads of the last block after the per-block partials have been summed into tot[kNRed].
-// `state` is a shared-memory copy of ctx.st (the caller writes it back).
-__device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* state, const double* tot,
-                                               SolverShared* sh) {
-  SolverIO io{&ctx, state, ctx.stats};
-  FrameState* st = io.st;
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Entered by ALL threads of the last block (kBlk = 128 = 4 warps) after the per-block partials have been summed
+// into tot[kNRed].  `st` is a shared-memory copy of ctx.st (the caller writes it back).
+//
+//   warp 3 : cand = log(candidate pose)                                    -> named barrier 1
+//   warp 1 : proj = Plus(x', -g') = log(exp(-g') * P')                     -> named barrier 2
+//            (x', P', g' = tangent, pose, gradient of the state that is current after an accepted step)
+//   warp 0 : Gauss-Newton model from the fresh H, g (speculative)  | wait 1 | accept / reject / tolerances |
+//            advance(): dogleg step + next candidate pose           | wait 2 | gradient-tolerance test
+// The gradient-tolerance test (|x' - proj|_inf <= 1e-10) comes BEFORE advance() in Ceres; it practically never
+// fires (it needs |g| ~ 1e-10), so advance() runs first on a backed-up state and is undone if it does fire.
+__device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st, const double* tot, SolverShared* sh) {
+  SolverIO io{&ctx, st, ctx.stats};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool iter0 = st->phase == kPhaseIter0;
-  // ---------------- phase A: three independent chains on three warps ----------------
+  // inputs of the helper warps are copied to registers before anybody mutates the state
+  Pose7 P = iter0 ? st->xq : st->candq;
+  double g[6];
+  for (int i = 0; i < 6; ++i) g[i] = tot[21 + i];
+  __syncthreads();
   long long ta0 = 0;
   if (ctx.dbg) ta0 = clock64();
-  if (threadIdx.x == 32) {
-    double g[6], x[6];
-    for (int i = 0; i < 6; ++i) g[i] = tot[21 + i];
-    const Pose7 P = iter0 ? st->xq : st->candq;
-    if (iter0) {
-      for (int i = 0; i < 6; ++i) x[i] = st->x[i];
-    } else {
-      s_log(&P, x);
-    }
-    sh->gmax = gradient_max_norm(P, x, g);
-    if (ctx.dbg) ctx.dbg[5] += (unsigned long long)(clock64() - ta0);
-  } else if (threadIdx.x == 64) {
-    double H[21], g[6], sc[6];
-    for (int i = 0; i < 21; ++i) H[i] = tot[i];
-    for (int i = 0; i < 6; ++i) {
-      g[i] = tot[21 + i];
-      sc[i] = iter0 ? 1.0 / (1.0 + sqrt(H[tri(i, i)])) : st->scale[i];          // jacobi scaling (iteration 0 only)
-    }
-    const double mu0 = iter0 ? 1e-8 : fmax(1e-8, 2.0 * st->mu_lm / 10.0);        // kMinMu / StepAccepted
-    gn_model(H, g, sc, mu0, sh->model);
-    if (ctx.dbg) ctx.dbg[6] += (unsigned long long)(clock64() - ta0);
-  } else if (threadIdx.x == 96) {
-    if (!iter0) s_log(&st->candq, sh->cand);
-    if (ctx.dbg) ctx.dbg[7] += (unsigned long long)(clock64() - ta0);
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  // ---------------- phase B: the state machine proper ----------------
-  if (ctx.dbg) ctx.dbg[15] = (unsigned long long)clock64();
-  const double cost = tot[27];
-  for (int k = 0; k < 4; ++k) st->slot_sum[k] = tot[28 + k];
-  tloam_b200_outer_trace* ot = outer_trace(io);
-  if (!isfinite(cost)) { st->status = TLOAM_B200_ERR_NUMERIC; finish_frame(io); return; }
 
-  if (iter0) {
-    // ---- IterationZero ----
-    st->iter = 0; st->num_invalid = 0; st->last_cand_valid = 0;
-    st->radius = 1e4;                                                    // initial_trust_region_radius
-    int nf_total = 0;
-    for (int k = 0; k < 4; ++k) {
-      const int nf = (int)(tot[32 + k] + 0.5);
-      nf_total += nf;
-      if (ot) ot->n_factors[k] = nf;
+  if (warp == 3) {
+    if (lane == 0 && !iter0) {
+      s_log(&P, sh->cand);
+      if (ctx.dbg) ctx.dbg[7] += (unsigned long long)(clock64() - ta0);
     }
-    st->x_cost = cost;
-    for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
-    for (int i = 0; i < 6; ++i) { st->g[i] = tot[21 + i]; st->scale[i] = sh->model.scale[i]; }
-    if (ot) {
-      ot->initial_cost = cost;
-      for (int i = 0; i < 6; ++i) {
-        ot->x_start[i] = st->x[i];
-        ot->g0[i] = st->g[i];
-        for (int j = 0; j < 6; ++j) ot->H0[i * 6 + j] = (i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)];
-      }
-    }
-    st->mu_lm = 1e-8; st->reuse = 0; st->model_ok = 0;
-    if (nf_total == 0) { end_of_solve(io, 5); return; }                  // no residual blocks
-    st->x_norm = norm6(st->x);
-    if (sh->gmax <= 1e-10) { end_of_solve(io, 3); return; }              // GradientToleranceReached
-    install_model(st, sh->model);
-    st->model_ok = sh->model.ok; st->reuse = 1;
-    TL_STAMP(io, 11);
-    advance(io);
-    TL_STAMP(io, 12);
+    __syncwarp();
+    bar_arrive(1, 64);
     return;
   }
-
-  // ---- the evaluation was at the candidate ----
-  for (int i = 0; i < 6; ++i) st->cand[i] = sh->cand[i];
-  tloam_b200_inner_trace* it = inner_trace(io);
-  if (it) {
-    it->candidate_cost = cost;
-    for (int i = 0; i < 6; ++i) it->x_candidate[i] = st->cand[i];
-  }
-  {
-    double d[6];
-    for (int i = 0; i < 6; ++i) d[i] = st->x[i] - st->cand[i];
-    if (norm6(d) <= 1e-8 * (st->x_norm + 1e-8)) {                      // ParameterToleranceReached
-      if (it) it->accepted = 2;
-      end_of_solve(io, 2); return;
+  if (warp == 1) {
+    if (lane == 0) {
+      double ng[6];
+      for (int i = 0; i < 6; ++i) ng[i] = -g[i];
+      Pose7 e, em;
+      s_exp(ng, &e);
+      s_mul(&e, &P, &em);
+      s_log(&em, sh->proj);
+      if (ctx.dbg) ctx.dbg[5] += (unsigned long long)(clock64() - ta0);
     }
+    __syncwarp();
+    bar_arrive(2, 64);
+    return;
   }
-  if (fabs(st->x_cost - cost) <= 1e-6 * st->x_cost) {                  // FunctionToleranceReached
-    if (it) it->accepted = 2;
-    end_of_solve(io, 1); return;
+  if (warp != 0) return;
+
+  // ------------------------------- warp 0 -------------------------------
+  if (lane == 0) {
+    double H[21], sc[6];
+    for (int i = 0; i < 21; ++i) H[i] = tot[i];
+    for (int i = 0; i < 6; ++i)
+      sc[i] = iter0 ? 1.0 / (1.0 + sqrt(H[tri(i, i)])) : st->scale[i];          // jacobi scaling (iteration 0 only)
+    const double mu0 = iter0 ? 1e-8 : fmax(1e-8, 2.0 * st->mu_lm / 10.0);        // kMinMu / StepAccepted
+    gn_model(H, g, sc, mu0, sh->model);
+    if (ctx.dbg) { ctx.dbg[6] += (unsigned long long)(clock64() - ta0); ctx.dbg[15] = (unsigned long long)clock64(); }
   }
-  const double rel = (st->x_cost - cost) / st->model_cost_change;      // StepQuality (monotonic)
-  if (it) it->relative_decrease = rel;
-  if (rel > 1e-3) {                                                    // min_relative_decrease
-    // HandleSuccessfulStep
-    for (int i = 0; i < 6; ++i) st->x[i] = st->cand[i];
-    st->xq = st->candq;
-    st->x_norm = norm6(st->x);
-    st->x_cost = cost;
-    for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
-    for (int i = 0; i < 6; ++i) st->g[i] = tot[21 + i];
-    if (rel < 0.25) st->radius *= 0.5;                                 // DoglegStrategy::StepAccepted
-    if (rel > 0.75) st->radius = fmax(st->radius, 3.0 * st->step_norm);
-    st->last_cand_valid = 0;
-    if (it) it->accepted = 1;
-    if (sh->gmax <= 1e-10) { st->mu_lm = fmax(1e-8, 2.0 * st->mu_lm / 10.0); end_of_solve(io, 3); return; }
-    install_model(st, sh->model);                                      // speculative model becomes current
-    st->model_ok = sh->model.ok; st->reuse = 1;
-  } else {
-    st->radius *= 0.5; st->reuse = 1;                                  // StepRejected
-    for (int i = 0; i < 6; ++i) st->last_cand[i] = st->cand[i];
-    st->last_candq = st->candq;
-    st->last_cand_cost = cost; st->last_cand_valid = 1;
-    if (it) it->accepted = 0;
+  __syncwarp();
+  bar_sync(1, 64);                                                       // cand is ready
+
+  // 0 = solve ended, 1 = go on with advance() and then the deferred gradient-tolerance test,
+  // 2 = go on with advance(), no gradient test (step rejected)
+  int go = 0;
+  if (lane == 0) {
+    const double cost = tot[27];
+    for (int k = 0; k < 4; ++k) st->slot_sum[k] = tot[28 + k];
+    tloam_b200_outer_trace* ot = outer_trace(io);
+    if (!isfinite(cost)) {
+      st->status = TLOAM_B200_ERR_NUMERIC;
+      finish_frame(io);
+    } else if (iter0) {
+      // ---- IterationZero ----
+      st->iter = 0; st->num_invalid = 0; st->last_cand_valid = 0;
+      st->radius = 1e4;                                                  // initial_trust_region_radius
+      int nf_total = 0;
+      for (int k = 0; k < 4; ++k) {
+        const int nf = (int)(tot[32 + k] + 0.5);
+        nf_total += nf;
+        if (ot) ot->n_factors[k] = nf;
+      }
+      st->x_cost = cost;
+      for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
+      for (int i = 0; i < 6; ++i) { st->g[i] = g[i]; st->scale[i] = sh->model.scale[i]; }
+      if (ot) {
+        ot->initial_cost = cost;
+        for (int i = 0; i < 6; ++i) {
+          ot->x_start[i] = st->x[i];
+          ot->g0[i] = st->g[i];
+          for (int j = 0; j < 6; ++j) ot->H0[i * 6 + j] = (i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)];
+        }
+      }
+      st->mu_lm = 1e-8; st->reuse = 0; st->model_ok = 0;
+      if (nf_total == 0) {
+        end_of_solve(io, 5);                                             // no residual blocks
+      } else {
+        st->x_norm = norm6(st->x);
+        install_model(st, sh->model);
+        st->model_ok = sh->model.ok; st->reuse = 1;
+        go = 1;
+      }
+    } else {
+      // ---- the evaluation was at the candidate ----
+      for (int i = 0; i < 6; ++i) st->cand[i] = sh->cand[i];
+      tloam_b200_inner_trace* it = inner_trace(io);
+      if (it) {
+        it->candidate_cost = cost;
+        for (int i = 0; i < 6; ++i) it->x_candidate[i] = st->cand[i];
+      }
+      double d[6];
+      for (int i = 0; i < 6; ++i) d[i] = st->x[i] - st->cand[i];
+      if (norm6(d) <= 1e-8 * (st->x_norm + 1e-8)) {                      // ParameterToleranceReached
+        if (it) it->accepted = 2;
+        end_of_solve(io, 2);
+      } else if (fabs(st->x_cost - cost) <= 1e-6 * st->x_cost) {         // FunctionToleranceReached
+        if (it) it->accepted = 2;
+        end_of_solve(io, 1);
+      } else {
+        const double rel = (st->x_cost - cost) / st->model_cost_change;  // StepQuality (monotonic)
+        if (it) it->relative_decrease = rel;
+        if (rel > 1e-3) {                                                // min_relative_decrease
+          // HandleSuccessfulStep
+          for (int i = 0; i < 6; ++i) st->x[i] = st->cand[i];
+          st->xq = st->candq;
+          st->x_norm = norm6(st->x);
+          st->x_cost = cost;
+          for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
+          for (int i = 0; i < 6; ++i) st->g[i] = g[i];
+          if (rel < 0.25) st->radius *= 0.5;                             // DoglegStrategy::StepAccepted
+          if (rel > 0.75) st->radius = fmax(st->radius, 3.0 * st->step_norm);
+          st->last_cand_valid = 0;
+          if (it) it->accepted = 1;
+          install_model(st, sh->model);                                  // speculative model becomes current
+          st->model_ok = sh->model.ok; st->reuse = 1;
+          go = 1;
+        } else {
+          st->radius *= 0.5; st->reuse = 1;                              // StepRejected
+          for (int i = 0; i < 6; ++i) st->last_cand[i] = st->cand[i];
+          st->last_candq = st->candq;
+          st->last_cand_cost = cost; st->last_cand_valid = 1;
+          if (it) it->accepted = 0;
+          go = 2;
+        }
+        if (go != 0 && st->radius <= 1e-32 && go == 2) { end_of_solve(io, 4); go = 0; }   // MinTrustRegionRadiusReached
+      }
+    }
+    TL_STAMP(io, 11);
   }
-  if (st->radius <= 1e-32) { end_of_solve(io, 4); return; }           // MinTrustRegionRadiusReached
-  TL_STAMP(io, 13);
-  advance(io);
-  TL_STAMP(io, 14);
+  go = __shfl_sync(0xffffffffu, go, 0);
+  if (go == 1) {                                                         // back up the state (warp-wide copy)
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh->backup);
+    for (unsigned i = lane; i < sizeof(FrameState) / 8; i += 32) dst[i] = src[i];
+    __syncwarp();
+  }
+  if (lane == 0 && go != 0) {
+    // after an accepted step Ceres tests the radius AFTER the gradient tolerance; the gradient test is deferred
+    // (below), so the radius test of the accepted branch is applied there as well
+    if (go == 2 || st->radius > 1e-32) advance(io);
+    TL_STAMP(io, 12);
+  }
+  __syncwarp();
+  bar_sync(2, 64);                                                       // proj is ready
+  int undo = 0;
+  if (lane == 0 && go == 1) {
+    const FrameState* b = &sh->backup;                                   // x' = tangent of the accepted state
+    double gmax = 0.0;
+    for (int i = 0; i < 6; ++i) gmax = fmax(gmax, fabs(b->x[i] - sh->proj[i]));
+    if (gmax <= 1e-10) undo = 3;                                         // GradientToleranceReached
+    else if (b->radius <= 1e-32) undo = 4;                               // MinTrustRegionRadiusReached
+  }
+  undo = __shfl_sync(0xffffffffu, undo, 0);
+  if (undo != 0) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sh->backup);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
+    for (unsigned i = lane; i < sizeof(FrameState) / 8; i += 32) dst[i] = src[i];
+    __syncwarp();
+    if (lane == 0) end_of_solve(io, undo);
+  }
 }
 
 }  // namespace tloam

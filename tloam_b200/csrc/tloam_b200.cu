@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ Dev
   if (st->frame_done || st->phase != kPhaseIter0) return;
   __shared__ unsigned s_beg[27][kBlk];
   __shared__ unsigned s_cnt[27][kBlk];
+  __shared__ float s_md[27][kBlk];
   const int fb = blockIdx.x;
   const int c = cloud_of_block(ctx, fb);
   const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
@@ -287,12 +288,12 @@ __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ Dev
     double prim[6];
     if (c == kSphere) {
       TopK<1> t;
-      knn_search_mlp<1, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, t);
+      knn_search_mlp<1, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t);
       if (ctx.dbg) tk1 = clock64();
       flag = fit_one<1>(ctx, c, t, prim);
     } else {
       TopK<5> t;
-      knn_search_mlp<5, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, t);
+      knn_search_mlp<5, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t);
       if (ctx.dbg) tk1 = clock64();
       flag = fit_one<5>(ctx, c, t, prim);
     }
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ Dev
 // counted features before it is < maxnum (the reference `return`s at the first cap-checked feature
 // after the counter reached the cap, ref: :448-449, 538-539, 592-593, 735-736).
 __device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int c, unsigned char flag, int* s_warp) {
+  if (ctx.maxnum[c] >= ctx.n[c]) return (flag & kFlagCand) != 0;   // the cap cannot bind (block-uniform branch)
   // counted features in previous blocks of this cloud
   int before = 0;
   if (threadIdx.x < 32) {
@@ -341,6 +343,7 @@ __device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int 
   int prefix = s_warp[0];
   for (int wi = 0; wi < warp; ++wi) prefix += s_warp[1 + wi];
   prefix += __popc(ballot & ((1u << lane) - 1u));
+  __syncthreads();                                   // s_warp is reused by the next feature block of the caller's loop
   return (flag & kFlagCand) && (prefix < ctx.maxnum[c]);
 }
 
@@ -348,29 +351,33 @@ template <bool kFirst>
 __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
   FrameState* st = ctx.st;
   if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;
-  __shared__ double s_red[kBlk / 32][30];
+  __shared__ double s_red[kBlk / 32][32];
+  __shared__ int s_cnt[kBlk / 32][4];
   __shared__ double s_tot[kNRed];
   __shared__ int s_warp[1 + kBlk / 32];
   __shared__ bool s_last;
   unsigned long long tg0 = 0;
   if (ctx.dbg && threadIdx.x == 0) { tg0 = gtime_ns(); atomicMin(&ctx.dbg[0], tg0); }
   const int b = blockIdx.x;
-  const int c = cloud_of_block(ctx, b);
-  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
-  const int gi = ctx.pad_off[c] + il;
-  bool act;
-  if (kFirst) {
-    act = compute_active(ctx, b, c, ctx.flags[gi], s_warp);
-    ctx.active[gi] = act ? 1 : 0;
-  } else {
-    act = ctx.active[gi] != 0;
-  }
-  // per-thread contribution: H (21), g (6), cost, slot, count
-  double v[30];
+  // per-thread accumulators: H (21), g (6), cost, slot sum per cloud (4); factor count per cloud (ints)
+  double v[32];
+  int nact[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int i = 0; i < 30; ++i) v[i] = 0.0;
-  if (act) {
-    const Rt T = pose_to_rt(st->evalq);
+  for (int i = 0; i < 32; ++i) v[i] = 0.0;
+  const Rt T = pose_to_rt(st->evalq);
+  // grid-stride over the 128-feature blocks (the grid is capped so that the final partial sum stays short)
+  for (int fb = b; fb < ctx.blk_off[4]; fb += gridDim.x) {
+    const int c = cloud_of_block(ctx, fb);
+    const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
+    const int gi = ctx.pad_off[c] + il;
+    bool act;
+    if (kFirst) {
+      act = compute_active(ctx, fb, c, ctx.flags[gi], s_warp);
+      ctx.active[gi] = act ? 1 : 0;
+    } else {
+      act = ctx.active[gi] != 0;
+    }
+    if (!act) continue;
     double cpt[3];
     rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], cpt[0], cpt[1], cpt[2]);
     const double w = ctx.w[gi];
@@ -403,9 +410,9 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
     const double sum = 1.0 + sq;
     const double rho1 = fmax(DBL_MIN, 1.0 / sum);
     const double sc = sqrt(rho1);
-    v[27] = 0.5 * log(sum);
-    v[28] = slot;
-    v[29] = 1.0;
+    v[27] += 0.5 * log(sum);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[28 + k] += (k == c) ? slot : 0.0; nact[k] += (k == c) ? 1 : 0; }
     for (int k = 0; k < nr; ++k) {
       double row[6];
 #pragma unroll
@@ -425,31 +432,33 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
   // (instead of 5 per value); afterwards lane L holds the warp total of value L.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
-    double u[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) u[i] = (i < 30) ? v[i] : 0.0;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       const bool up = (lane & o) != 0;
 #pragma unroll
       for (int i = 0; i < o; ++i) {
-        const double send = up ? u[i] : u[i + o];
-        const double keep = up ? u[i + o] : u[i];
-        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        const double send = up ? v[i] : v[i + o];
+        const double keep = up ? v[i + o] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
-    if (lane < 30) s_red[warp][lane] = u[0];
+    s_red[warp][lane] = v[0];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int tot_k = __reduce_add_sync(0xffffffffu, nact[k]);
+      if (lane == 0) s_cnt[warp][k] = tot_k;
+    }
   }
   __syncthreads();
   if (threadIdx.x < kNRed) {
     const int t = threadIdx.x;
     double s = 0.0;
-    if (t < 28) {
+    if (t < 32) {
       for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][t];
-    } else if (t < 32) {
-      if (t - 28 == c) for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][28];
     } else {
-      if (t - 32 == c) for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][29];
+      int n = 0;
+      for (int wi = 0; wi < kBlk / 32; ++wi) n += s_cnt[wi][t - 32];
+      s = (double)n;
     }
     ctx.partial[(size_t)b * kNRed + t] = s;
   }
@@ -1047,13 +1056,14 @@ static int check_ready(tloam_b200_handle* h) {
 // enqueues the frame's fixed launch sequence on h->stream (also used under stream capture)
 static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   const int nb = h->total_blocks;
+  const int ne = nb < kEvalGridCap ? nb : kEvalGridCap;   // k_eval is grid-stride over the feature blocks
   CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
   TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, h->d_predict)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
     TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<<<nb, kBlk, 0, h->stream>>>(c)));
-    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true><<<nb, kBlk, 0, h->stream>>>(c)));
+    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true><<<ne, kBlk, 0, h->stream>>>(c)));
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
-      TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false><<<nb, kBlk, 0, h->stream>>>(c)));
+      TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false><<<ne, kBlk, 0, h->stream>>>(c)));
   }
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));

@@ -282,6 +282,53 @@ def config1(cfg=None):
     return dict(cfg=cfg, T_gt=T_gt, predict=predict, map=make_map(cfg, T_gt), scan=make_scan(cfg, T_gt, 0))
 
 
+def config3(n_feat=500_000, n_map=2_000_000, seed=20260924 + 3000, noise=0.01, outlier_frac=0.10):
+    """BASELINE config 3: dense indoor scan, planar-only residuals (factor_num = 2: the planar and
+    ground builders, ref: registration.hpp:144-148), room 20 x 30 x 4 m.  ground cloud = floor, planar cloud = walls +
+    ceiling, each half of the points; the edge / sphere clouds only carry the 16 dummy points the >= 10-point
+    rule needs.  Surfaces are sampled uniformly at random (no lattice), spacing ~0.03 m at the full size."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    LX, LY, LZ = 20.0, 30.0, 4.0
+
+    def floor(n):
+        return np.stack([rng.uniform(0, LX, n), rng.uniform(0, LY, n), np.zeros(n)], axis=1)
+
+    def shell(n):                                  # 4 walls + ceiling, area-proportional
+        areas = np.array([LX * LZ, LX * LZ, LY * LZ, LY * LZ, LX * LY])
+        which = rng.choice(5, size=n, p=areas / areas.sum())
+        u, v = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+        pts = np.zeros((n, 3))
+        for k in range(5):
+            m = which == k
+            if k == 0:
+                pts[m] = np.stack([u[m] * LX, np.zeros(m.sum()), v[m] * LZ], axis=1)
+            elif k == 1:
+                pts[m] = np.stack([u[m] * LX, np.full(m.sum(), LY), v[m] * LZ], axis=1)
+            elif k == 2:
+                pts[m] = np.stack([np.zeros(m.sum()), u[m] * LY, v[m] * LZ], axis=1)
+            elif k == 3:
+                pts[m] = np.stack([np.full(m.sum(), LX), u[m] * LY, v[m] * LZ], axis=1)
+            else:
+                pts[m] = np.stack([u[m] * LX, v[m] * LY, np.full(m.sum(), LZ)], axis=1)
+        return pts
+
+    T_gt = se3_exp([9.0, 14.0, 1.5, 0.01, -0.015, 0.6])
+    predict = T_gt @ se3_exp([0.04, -0.03, 0.02, 0.004, -0.003, 0.006])
+    dummy = np.array([[LX / 2, LY / 2, 1.0]]) + rng.normal(0, 0.05, (16, 3))
+    mp = [dummy.copy(), dummy.copy(), shell(n_map // 2) + rng.normal(0, 0.003, (n_map // 2, 3)),
+          floor(n_map - n_map // 2) + rng.normal(0, 0.003, (n_map - n_map // 2, 3))]
+    Tinv = np.linalg.inv(T_gt)
+
+    def to_scan(p):
+        q = p @ Tinv[:3, :3].T + Tinv[:3, 3] + rng.normal(0, noise, p.shape)
+        m = rng.random(len(q)) < outlier_frac
+        q[m] += rng.uniform(-0.3, 0.3, (int(m.sum()), 3))
+        return np.ascontiguousarray(q)
+
+    scan = [to_scan(dummy), to_scan(dummy), to_scan(shell(n_feat // 2)), to_scan(floor(n_feat - n_feat // 2))]
+    return dict(T_gt=T_gt, predict=predict, map=mp, scan=scan, factor_num=2)
+
+
 def load_motion(seq="00"):
     here = os.path.dirname(os.path.abspath(__file__))
     path = os.path.join(here, "..", "tests", "golden", f"motion_seq{seq}.npy")

@@ -21,5 +21,4 @@ n = max(d[4], 1)
 print({k: (v[0], round(1e3 * v[1] / max(v[0], 1), 2)) for k, v in prof.items()})
 print(f"k_eval active launches={d[4]}: parallel {d[1]/n/1e3:.2f} us, partial-sum {d[2]/n/1e3:.2f} us, solver {d[3]/n/1e3:.2f} us")
 print(f"k_correspond: blocks={d[9]} avg kNN-phase cycles/block={d[8]/max(d[9],1):.0f} fit-phase cycles/block={d[10]/max(d[9],1):.0f}")
-print("solver stages (avg SM cycles per active eval): pre-model(decision+gradcheck+trace) %.0f, compute_model %.0f, dogleg+mcc %.0f, plus(exp,mul,log) %.0f" % tuple(d[i] / n for i in (11, 12, 13, 14)))
-print("phase A chains (avg SM cycles): gmax %.0f, gn_model %.0f, log(cand) %.0f" % tuple(d[i] / n for i in (5, 6, 7)))
+print("warp 0 (avg SM cycles per active eval): gn_model %.0f, decision %.0f, advance %.0f | warp 1 proj %.0f | warp 3 log(cand) %.0f" % tuple(d[i] / n for i in (6, 11, 12, 5, 7)))
