@@ -243,6 +243,112 @@ __device__ __forceinline__ void knn_search_mlp(const GridDesc& g, double rx, dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lane-pair variant of knn_search_mlp: lanes 2q and 2q+1 share query q, each visits every other cell of the
+// 27-cell neighbourhood (14 / 13 cells, centre first) with its own sorted list; lane 2q then merges the two
+// lists (K steps).  Twice the warps of the thread-per-query form for the same work: the kernel is latency-bound
+// at F = 40k (8.5 warps per SM), so the extra warps buy issue slots.  All 32 lanes must call this together.
+// On return the even lane holds the exact top-K.
+// ------------------------------------------------------------------------------------------------
+template <int K, int kThreads>
+__device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, double rx, double ry, double rz, double r2,
+                                                unsigned (*s_beg)[kThreads], unsigned (*s_cnt)[kThreads],
+                                                float (*s_md)[kThreads], TopK<K>& t, long long* stamps = nullptr) {
+  t.init();
+  const int tid = threadIdx.x;
+  const int half = tid & 1;
+  if (stamps) stamps[0] = clock64();
+  int m = 0;
+  if (live && g.n != 0u) {
+    const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
+    const float cellf = (float)g.cell, r2f = (float)r2;
+    const float fx = (float)(rx - (double)cx * g.cell), fy = (float)(ry - (double)cy * g.cell), fz = (float)(rz - (double)cz * g.cell);
+#pragma unroll
+    for (int batch = 0; batch < 2; ++batch) {
+      unsigned long long key[7];
+      uint4 e[7];
+      unsigned slot[7];
+      int off3[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int n = 2 * (batch * 7 + j) + half;               // 0..27 ; 27 = none
+        const int mcell = (n + 13) % 27;                        // visiting order starts at the centre cell (13)
+        off3[j] = (n < 27) ? mcell : -1;
+        key[j] = 0ull; slot[j] = 0u; e[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (n < 27) {
+          key[j] = cell_key(cx + (mcell % 3) - 1, cy + ((mcell / 3) % 3) - 1, cz + (mcell / 9) - 1);
+          slot[j] = hash_key(key[j]) & g.mask;
+          e[j] = __ldg(&g.table[slot[j]]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (off3[j] < 0) continue;
+        unsigned long long k = ((unsigned long long)e[j].y << 32) | e[j].x;
+        while (k != key[j] && k != 0ull) {          // collision (rare): keep probing
+          slot[j] = (slot[j] + 1u) & g.mask;
+          e[j] = __ldg(&g.table[slot[j]]);
+          k = ((unsigned long long)e[j].y << 32) | e[j].x;
+        }
+        if (stamps && j == 6) stamps[1 + batch] = clock64();
+        if (k == key[j] && e[j].w != 0u) {
+          const int ox = (off3[j] % 3) - 1, oy = ((off3[j] / 3) % 3) - 1, oz = (off3[j] / 9) - 1;
+          const float mx = ox < 0 ? fx : (ox > 0 ? cellf - fx : 0.0f);
+          const float my = oy < 0 ? fy : (oy > 0 ? cellf - fy : 0.0f);
+          const float mz = oz < 0 ? fz : (oz > 0 ? cellf - fz : 0.0f);
+          const float md = fmaxf(mx * mx + my * my + mz * mz, 0.0f) * 0.9999f - 1e-12f;   // rounded DOWN
+          if (md < r2f) {
+            s_md[m][tid] = md;
+            s_beg[m][tid] = e[j].z;
+            s_cnt[m][tid] = e[j].w;
+            ++m;
+          }
+        }
+      }
+    }
+  }
+  int ci = 0;
+  unsigned off = 0u, cb = 0u, cc = 0u;
+  if (m > 0) { cb = s_beg[0][tid]; cc = s_cnt[0][tid]; }
+  while (ci < m) {
+    float4 pt[8];
+    int pos[8];
+    const double worst = t.d2[K - 1];             // +inf until the list is full
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      pos[q] = -1;
+      if (ci < m) {
+        pos[q] = (int)(cb + off);
+        pt[q] = __ldg(&g.pts[pos[q]]);
+        if (++off == cc) {
+          ++ci; off = 0u;
+          while (ci < m && (double)s_md[ci][tid] > worst) ++ci;   // no point of that cell can enter the list
+          if (ci < m) { cb = s_beg[ci][tid]; cc = s_cnt[ci][tid]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (pos[q] >= 0) {
+        const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
+        const double d = ddx * ddx + ddy * ddy + ddz * ddz;
+        if (d < r2) t.insert(d, __float_as_int(pt[q].w), pos[q]);
+      }
+    }
+  }
+  if (stamps) stamps[3] = clock64();
+  // merge: the even lane pulls the odd lane's list (sorted) and inserts its entries until one fails
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const double od = __shfl_xor_sync(0xffffffffu, t.d2[j], 1);
+    const int oi = __shfl_xor_sync(0xffffffffu, t.idx[j], 1);
+    const int op = __shfl_xor_sync(0xffffffffu, t.pos[j], 1);
+    if (half == 0 && op >= 0) t.insert(od, oi, op);
+  }
+  if (stamps) stamps[4] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Cooperative variant: kLpq (8/16/32) consecutive lanes share one query. Lane `sub` probes cells
 // sub, sub+kLpq, ... of the 27-cell neighbourhood and scans their points into a private sorted list; the
 // lists are then merged with K rounds of a butterfly arg-min over the lane group.  Every lane of the group

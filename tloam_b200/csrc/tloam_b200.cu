@@ -261,66 +261,84 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
   return kFlagCand | kFlagCounted;                          // surf_num++ / ground_num++
 }
 
-// Correspondence search + primitive fit, one feature per thread (block = one 128-feature block of one cloud).
-// Also applies the lazy GNC weight update of the previous outer iteration (ref: registration.cpp:858-876) and
-// resets the residual slot (:1118-1121).  (Lane-group variants -- 8 lanes per feature with shuffle-merged or
-// rank-counted candidate lists, see map_grid.cuh -- were measured slower on B200: 47-62 us vs 35 us.)
+// Correspondence search + primitive fit.  A LANE PAIR serves one feature (knn_search_pair: each lane visits
+// every other cell, the even lane merges and fits), so a 128-thread block serves 64 features and a 128-feature
+// block of one cloud is served by two thread blocks.  Also applies the lazy GNC weight update of the previous
+// outer iteration (ref: registration.cpp:858-876) and resets the residual slot (:1118-1121).
+// Measured alternatives (config 2, us per launch): thread per feature 35-39; 8 lanes per feature with shuffle
+// merge 47, with shared-memory append + rank counting 54; two-pass selection in local memory 43.
 __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ DeviceCtx ctx) {
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != kPhaseIter0) return;
-  __shared__ unsigned s_beg[27][kBlk];
-  __shared__ unsigned s_cnt[27][kBlk];
-  __shared__ float s_md[27][kBlk];
-  const int fb = blockIdx.x;
+  __shared__ unsigned s_beg[14][kBlk];
+  __shared__ unsigned s_cnt[14][kBlk];
+  __shared__ float s_md[14][kBlk];
+  constexpr int kQ = kBlk / 2;                 // features per thread block
+  const int fb = blockIdx.x / 2, sb = blockIdx.x % 2;
   const int c = cloud_of_block(ctx, fb);
-  const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  const int il = (fb - ctx.blk_off[c]) * kBlk + sb * kQ + (int)(threadIdx.x >> 1);
   const int gi = ctx.pad_off[c] + il;
   const bool live = (il < ctx.n[c]) && cloud_enabled(ctx, c);
+  const bool even = (threadIdx.x & 1) == 0;
   const int buf = st->outer & 1;
+  if (threadIdx.x == 0 && sb == 0) ctx.blk_count[(buf ^ 1) * ctx.blk_cap + fb] = 0;   // for the next outer iteration
   long long tk0 = 0, tk1 = 0;
   if (ctx.dbg) tk0 = clock64();
-  unsigned char flag = 0;
+  double rx = 0.0, ry = 0.0, rz = 0.0;
   if (live) {
     const Rt T = pose_to_rt(st->xq);
     double qx, qy, qz;
     rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
-    const double rx = qx - ctx.origin[0], ry = qy - ctx.origin[1], rz = qz - ctx.origin[2];
-    double prim[6];
-    if (c == kSphere) {
-      TopK<1> t;
-      knn_search_mlp<1, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t);
-      if (ctx.dbg) tk1 = clock64();
-      flag = fit_one<1>(ctx, c, t, prim);
-    } else {
-      TopK<5> t;
-      knn_search_mlp<5, kBlk>(ctx.grid[c], rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t);
-      if (ctx.dbg) tk1 = clock64();
-      flag = fit_one<5>(ctx, c, t, prim);
-    }
-    if (st->outer == 0) {
-      ctx.w[gi] = 1.0;                                                            // :931-949
-    } else {
-      const double res = ctx.slot[gi];
-      if (res != 0.0) {
-        double wv;
-        if (res >= st->th1) wv = 0.0;
-        else if (res <= st->th2) wv = 1.0;
-        else wv = sqrt(st->c2 * st->mu_used * (st->mu_used + 1.0) / res) - st->mu_used;
-        ctx.w[gi] = wv;
-      }
-    }
-    ctx.slot[gi] = 0.0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) ctx.prim[j][gi] = prim[j];
+    rx = qx - ctx.origin[0]; ry = qy - ctx.origin[1]; rz = qz - ctx.origin[2];
   }
-  ctx.flags[gi] = flag;
+  unsigned char flag = 0;
+  double prim[6];
+  if (c == kSphere) {
+    TopK<1> t;
+    knn_search_pair<1, kBlk>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t);
+    if (ctx.dbg) tk1 = clock64();
+    if (live && even) flag = fit_one<1>(ctx, c, t, prim);
+  } else {
+    TopK<5> t;
+    long long stamps[5] = {0, 0, 0, 0, 0};
+    knn_search_pair<5, kBlk>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t,
+                             (ctx.dbg && threadIdx.x == 0) ? stamps : nullptr);
+    if (ctx.dbg) tk1 = clock64();
+    if (ctx.dbg && threadIdx.x == 0 && live) {
+      atomicAdd(&ctx.dbg[11], (unsigned long long)(stamps[1] - stamps[0]));   // probe batch 1
+      atomicAdd(&ctx.dbg[12], (unsigned long long)(stamps[2] - stamps[1]));   // probe batch 2
+      atomicAdd(&ctx.dbg[13], (unsigned long long)(stamps[3] - stamps[2]));   // candidate streaming
+      atomicAdd(&ctx.dbg[14], (unsigned long long)(stamps[4] - stamps[3]));   // merge
+    }
+    if (live && even) flag = fit_one<5>(ctx, c, t, prim);
+  }
+  if (even) {
+    if (live) {
+      if (st->outer == 0) {
+        ctx.w[gi] = 1.0;                                                          // :931-949
+      } else {
+        const double res = ctx.slot[gi];
+        if (res != 0.0) {
+          double wv;
+          if (res >= st->th1) wv = 0.0;
+          else if (res <= st->th2) wv = 1.0;
+          else wv = sqrt(st->c2 * st->mu_used * (st->mu_used + 1.0) / res) - st->mu_used;
+          ctx.w[gi] = wv;
+        }
+      }
+      ctx.slot[gi] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) ctx.prim[j][gi] = prim[j];
+    }
+    ctx.flags[gi] = flag;
+  }
   if (ctx.dbg && threadIdx.x == 0 && live) {
     atomicAdd(&ctx.dbg[8], (unsigned long long)(tk1 - tk0));
     atomicAdd(&ctx.dbg[10], (unsigned long long)(clock64() - tk1));
     atomicAdd(&ctx.dbg[9], 1ull);
   }
-  const int cnt = __syncthreads_count((flag & kFlagCounted) != 0);
-  if (threadIdx.x == 0) ctx.blk_count[buf * ctx.blk_cap + fb] = cnt;
+  const int cnt = __syncthreads_count(even && (flag & kFlagCounted) != 0);
+  if (threadIdx.x == 0 && cnt > 0) atomicAdd(&ctx.blk_count[buf * ctx.blk_cap + fb], cnt);
 }
 
 // `*_maxnum` caps in feature-index order (Q8): factor i is active iff it is a candidate and the number of
@@ -1060,7 +1078,7 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
   TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, h->d_predict)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
-    TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<<<nb, kBlk, 0, h->stream>>>(c)));
+    TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<<<nb * 2, kBlk, 0, h->stream>>>(c)));
     TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true><<<ne, kBlk, 0, h->stream>>>(c)));
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
       TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false><<<ne, kBlk, 0, h->stream>>>(c)));
@@ -1269,7 +1287,7 @@ int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6],
   DeviceCtx c = h->ctx;
   c.factor_num = 4;   // build every cloud regardless of the configured subset
   k_set_pose<<<1, 256, 0, h->stream>>>(c, pr);
-  k_correspond<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
+  k_correspond<<<h->total_blocks * 2, kBlk, 0, h->stream>>>(c);
   k_caps<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
   h->launches += 3;
   CU_TRY(cudaGetLastError());
