@@ -164,7 +164,7 @@ int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double de
 enum {
   TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
-  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
@@ -176,6 +176,36 @@ typedef struct tloam_b200_profile {
 } tloam_b200_profile;
 int tloam_b200_set_profiling(tloam_b200_handle* h, int on);   /* also clears the accumulated profile */
 int tloam_b200_get_profile(tloam_b200_handle* h, tloam_b200_profile* out);
+
+/* ---- device-side local-map maintenance ("next" row (f)-1): FrontEnd::updateSubmap on the GPU
+ * (ref: src/front_end/front_end.cpp:201-267, first frame :285-305; PointCloud2 Transform / += / Crop /
+ * VoxelDownSample, ref: src/open3d/PointCloud2.cpp:71-75, 96-132, 358-403, 551-559).  The map stays in HBM between
+ * frames; each call ends with the same voxel-hash build as tloam_b200_set_target. ---- */
+typedef struct tloam_submap_config {   /* ref: config/mapping/lidar_odometry.yaml:6-17 */
+  double ground_down_sample;           /* 0.3  */
+  double ground_down_sample_submap;    /* 0.45 */
+  double edge_down_sample_submap;      /* 0.3  */
+  int planar_frame_size;               /* 3 */
+  int sphere_frame_size;               /* 3 (kept for parity; the reference builds the sphere submap from the planar buffer) */
+  double edge_crop_box_length, ground_crop_box_length;   /* 100, 100 */
+} tloam_submap_config;
+void tloam_b200_submap_default_config(tloam_submap_config* c);
+/* First frame: edge = raw edge cloud, ground_raw = raw ground cloud (voxel-down-sampled at ground_down_sample
+ * inside), planar_sub / sphere_sub = the "submap index" selections of the general cloud.  HOST pointers. */
+int tloam_b200_submap_init(tloam_b200_handle* h, const tloam_submap_config* cfg, const double* edge, size_t ne,
+                           const double* ground_raw, size_t ng, const double* planar_sub, size_t np,
+                           const double* sphere_sub, size_t ns);
+/* Later frames, after scan_match: pose = the new lidar_odom_pose (4x4 column-major).  The edge and ground
+ * features appended to the map are the ones of the CURRENT SOURCE (tloam_b200_set_source), already on the device;
+ * planar_sub is this frame's planar submap selection (HOST pointer, sensor frame); sphere_sub is accepted for
+ * interface parity and ignored, as in the reference (front_end.cpp:220-230 iterates the planar buffer). */
+int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const double* planar_sub, size_t np,
+                             const double* sphere_sub, size_t ns);
+int tloam_b200_submap_sizes(tloam_b200_handle* h, size_t n[4]);
+/* copies map cloud `cloud` (0 edge, 1 sphere, 2 planar, 3 ground; world frame, FP64 AoS) to the host */
+int tloam_b200_submap_download(tloam_b200_handle* h, int cloud, double* out, size_t capacity_points);
+/* PointCloud2::VoxelDownSample on the device (HOST in / out; out must hold n points). */
+int tloam_b200_voxel_down_sample(tloam_b200_handle* h, const double* pts, size_t n, double voxel, double* out, size_t* n_out);
 
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);

@@ -33,6 +33,12 @@ class Config(C.Structure):
     ]
 
 
+class SubmapConfig(C.Structure):
+    _fields_ = [("ground_down_sample", C.c_double), ("ground_down_sample_submap", C.c_double),
+                ("edge_down_sample_submap", C.c_double), ("planar_frame_size", C.c_int), ("sphere_frame_size", C.c_int),
+                ("edge_crop_box_length", C.c_double), ("ground_crop_box_length", C.c_double)]
+
+
 class InnerTrace(C.Structure):
     _fields_ = [
         ("x_candidate", C.c_double * 6), ("candidate_cost", C.c_double), ("model_cost_change", C.c_double),
@@ -111,6 +117,20 @@ def lib():
         L.oracle_build_factors.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_int), dp, C.c_size_t]
         L.oracle_build_factors.restype = C.c_int
         L.oracle_update_weight.argtypes = [dp, dp, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.oracle_submap_default_config.argtypes = [C.POINTER(SubmapConfig)]
+        L.oracle_voxel_down_sample.argtypes = [dp, C.c_size_t, C.c_double, dp]
+        L.oracle_voxel_down_sample.restype = C.c_size_t
+        L.oracle_crop.argtypes = [dp, C.c_size_t, dp, dp, dp]
+        L.oracle_crop.restype = C.c_size_t
+        L.oracle_submap_create.argtypes = [C.POINTER(SubmapConfig)]
+        L.oracle_submap_create.restype = C.c_void_p
+        L.oracle_submap_destroy.argtypes = [C.c_void_p]
+        L.oracle_submap_init.argtypes = [C.c_void_p, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t]
+        L.oracle_submap_update.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t]
+        L.oracle_submap_size.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_submap_size.restype = C.c_size_t
+        L.oracle_submap_data.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_submap_data.restype = dp
         _lib = L
     return _lib
 
@@ -285,3 +305,55 @@ def update_weight(weights, slots, noise_bound_sq, th1, th2, mu):
     s = _f64(slots)
     lib().oracle_update_weight(_dp(w), _dp(s), w.size, noise_bound_sq, th1, th2, mu)
     return w
+
+
+def voxel_down_sample(pts, voxel):
+    a = _f64(pts).reshape(-1, 3)
+    out = np.zeros_like(a)
+    n = lib().oracle_voxel_down_sample(_dp(a), a.shape[0], float(voxel), _dp(out))
+    return out[:n].copy()
+
+
+def crop(pts, lo, hi):
+    a = _f64(pts).reshape(-1, 3)
+    out = np.zeros_like(a)
+    lo, hi = _f64(lo), _f64(hi)
+    n = lib().oracle_crop(_dp(a), a.shape[0], _dp(lo), _dp(hi), _dp(out))
+    return out[:n].copy()
+
+
+class Submap:
+    """Mirror of FrontEnd's submap handling (ref: src/front_end/front_end.cpp:201-267, 285-305)."""
+
+    def __init__(self, **overrides):
+        self.cfg = SubmapConfig()
+        lib().oracle_submap_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            setattr(self.cfg, k, v)
+        self._s = lib().oracle_submap_create(C.byref(self.cfg))
+
+    def __del__(self):
+        if getattr(self, "_s", None):
+            lib().oracle_submap_destroy(self._s)
+            self._s = None
+
+    def init(self, edge, ground_raw, planar_sub, sphere_sub):
+        a = [_f64(x).reshape(-1, 3) for x in (edge, ground_raw, planar_sub, sphere_sub)]
+        lib().oracle_submap_init(self._s, _dp(a[0]), a[0].shape[0], _dp(a[1]), a[1].shape[0], _dp(a[2]), a[2].shape[0],
+                                 _dp(a[3]), a[3].shape[0])
+
+    def update(self, pose, edge_scan, ground_scan, planar_sub, sphere_sub):
+        p = _f64(np.asarray(pose).T).reshape(16)
+        a = [_f64(x).reshape(-1, 3) for x in (edge_scan, ground_scan, planar_sub, sphere_sub)]
+        lib().oracle_submap_update(self._s, _dp(p), _dp(a[0]), a[0].shape[0], _dp(a[1]), a[1].shape[0], _dp(a[2]),
+                                   a[2].shape[0], _dp(a[3]), a[3].shape[0])
+
+    def cloud(self, c):
+        n = lib().oracle_submap_size(self._s, c)
+        if n == 0:
+            return np.zeros((0, 3))
+        ptr = lib().oracle_submap_data(self._s, c)
+        return np.ctypeslib.as_array(ptr, shape=(n * 3,)).reshape(n, 3).copy()
+
+    def clouds(self):
+        return [self.cloud(c) for c in range(4)]

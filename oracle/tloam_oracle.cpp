@@ -17,6 +17,7 @@
 #include "tloam_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -1295,5 +1296,127 @@ void oracle_update_weight(double* weights, const double* slots, size_t n, double
     else weights[i] = std::sqrt(noise_bound_sq * mu * (mu + 1) / slots[i]) - mu;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// (f)-1 submap maintenance
+// ---------------------------------------------------------------------------------------------
+void oracle_submap_default_config(oracle_submap_config* c) {   // ref: config/mapping/lidar_odometry.yaml:6-17
+  c->ground_down_sample = 0.3; c->ground_down_sample_submap = 0.45; c->edge_down_sample_submap = 0.3;
+  c->planar_frame_size = 3; c->sphere_frame_size = 3;
+  c->edge_crop_box_length = 100.0; c->ground_crop_box_length = 100.0;
+}
+
+// PointCloud2::VoxelDownSample, ref: src/open3d/PointCloud2.cpp:358-403.
+size_t oracle_voxel_down_sample(const double* pts, size_t n, double voxel, double* out) {
+  if (n == 0) return 0;
+  double mn[3] = {pts[0], pts[1], pts[2]};
+  for (size_t i = 1; i < n; ++i) for (int d = 0; d < 3; ++d) mn[d] = std::min(mn[d], pts[3 * i + d]);
+  for (int d = 0; d < 3; ++d) mn[d] -= voxel * 0.5;                        // voxel_min_bound (:367)
+  struct Acc { long long key[3]; double s[3]; long long cnt; };
+  std::vector<std::pair<std::array<long long, 3>, size_t>> keyed(n);
+  for (size_t i = 0; i < n; ++i) {
+    std::array<long long, 3> k;
+    for (int d = 0; d < 3; ++d) k[d] = (long long)std::floor((pts[3 * i + d] - mn[d]) / voxel);   // :381-383
+    keyed[i] = {k, i};
+  }
+  std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  size_t m = 0;
+  for (size_t i = 0; i < n;) {
+    size_t j = i;
+    double s[3] = {0, 0, 0};
+    while (j < n && keyed[j].first == keyed[i].first) {                   // AddPoint in input order (:254)
+      for (int d = 0; d < 3; ++d) s[d] += pts[3 * keyed[j].second + d];
+      ++j;
+    }
+    for (int d = 0; d < 3; ++d) out[3 * m + d] = s[d] / double(j - i);     // GetAveragePoint (:271-273)
+    ++m;
+    i = j;
+  }
+  return m;
+}
+
+// PointCloud2::Crop(AxisAlignedBoundingBox), ref: PointCloud2.cpp:551-559 (bounds inclusive, order kept).
+size_t oracle_crop(const double* pts, size_t n, const double lo[3], const double hi[3], double* out) {
+  size_t m = 0;
+  for (size_t i = 0; i < n; ++i) {
+    bool in = true;
+    for (int d = 0; d < 3; ++d) in = in && pts[3 * i + d] >= lo[d] && pts[3 * i + d] <= hi[d];
+    if (in) { for (int d = 0; d < 3; ++d) out[3 * m + d] = pts[3 * i + d]; ++m; }
+  }
+  return m;
+}
+
+namespace {
+struct SubmapOracle {
+  oracle_submap_config cfg;
+  std::vector<double> cloud[4];                       // edge, sphere, planar, ground (world frame)
+  std::vector<std::vector<double>> planar_buf, sphere_buf;   // per-frame clouds, already transformed? no: raw + pose
+  std::vector<std::array<double, 16>> planar_pose, sphere_pose;
+};
+void transform_into(const double T[16], const double* in, size_t n, std::vector<double>& out) {   // Transform + operator+=
+  for (size_t i = 0; i < n; ++i) {
+    const double x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+    out.push_back(T[0] * x + T[4] * y + T[8] * z + T[12]);
+    out.push_back(T[1] * x + T[5] * y + T[9] * z + T[13]);
+    out.push_back(T[2] * x + T[6] * y + T[10] * z + T[14]);
+  }
+}
+}  // namespace
+
+void* oracle_submap_create(const oracle_submap_config* c) { auto* s = new SubmapOracle(); s->cfg = *c; return s; }
+void oracle_submap_destroy(void* s) { delete static_cast<SubmapOracle*>(s); }
+
+// first frame, ref: front_end.cpp:285-305 (clouds stay in the sensor frame of frame 0).
+int oracle_submap_init(void* sp, const double* edge, size_t ne, const double* ground_raw, size_t ng,
+                       const double* planar_sub, size_t np, const double* sphere_sub, size_t ns) {
+  SubmapOracle& S = *static_cast<SubmapOracle*>(sp);
+  S.cloud[0].assign(edge, edge + 3 * ne);                                              // :286
+  std::vector<double> g(3 * ng);
+  const size_t m = oracle_voxel_down_sample(ground_raw, ng, S.cfg.ground_down_sample, g.data());   // :287
+  S.cloud[3].assign(g.begin(), g.begin() + 3 * m);
+  S.cloud[2].assign(planar_sub, planar_sub + 3 * np);                                  // :291
+  S.cloud[1].assign(sphere_sub, sphere_sub + 3 * ns);                                  // :292
+  // NOTE: the reference does NOT push frame 0 into the sliding-window buffers (:285-305)
+  return 0;
+}
+
+// ref: front_end.cpp:201-267.
+int oracle_submap_update(void* sp, const double pose[16], const double* edge_scan, size_t ne, const double* ground_scan,
+                         size_t ng, const double* planar_sub, size_t np, const double* sphere_sub, size_t ns) {
+  SubmapOracle& S = *static_cast<SubmapOracle*>(sp);
+  std::array<double, 16> P;
+  std::copy(pose, pose + 16, P.begin());
+  S.sphere_buf.emplace_back(sphere_sub, sphere_sub + 3 * ns); S.sphere_pose.push_back(P);        // :202-205
+  S.planar_buf.emplace_back(planar_sub, planar_sub + 3 * np); S.planar_pose.push_back(P);        // :207-210
+  while ((int)S.sphere_buf.size() > S.cfg.sphere_frame_size) { S.sphere_buf.erase(S.sphere_buf.begin()); S.sphere_pose.erase(S.sphere_pose.begin()); }
+  while ((int)S.planar_buf.size() > S.cfg.planar_frame_size) { S.planar_buf.erase(S.planar_buf.begin()); S.planar_pose.erase(S.planar_pose.begin()); }
+  // :220-230 -- the SPHERE submap is rebuilt from the PLANAR buffer (sic)
+  S.cloud[1].clear();
+  for (size_t f = 0; f < S.planar_buf.size(); ++f) transform_into(S.planar_pose[f].data(), S.planar_buf[f].data(), S.planar_buf[f].size() / 3, S.cloud[1]);
+  S.cloud[2].clear();                                                                              // :232-242
+  for (size_t f = 0; f < S.planar_buf.size(); ++f) transform_into(S.planar_pose[f].data(), S.planar_buf[f].data(), S.planar_buf[f].size() / 3, S.cloud[2]);
+  transform_into(pose, edge_scan, ne, S.cloud[0]);                                                 // :245
+  transform_into(pose, ground_scan, ng, S.cloud[3]);                                               // :246
+  const double c[3] = {pose[12], pose[13], pose[14]};                                              // :250
+  {
+    const double L = S.cfg.edge_crop_box_length;
+    const double lo[3] = {c[0] - L, c[1] - L, c[2] - L}, hi[3] = {c[0] + L, c[1] + L, c[2] + L};
+    std::vector<double> cr(S.cloud[0].size()), ds(S.cloud[0].size());
+    const size_t m = oracle_crop(S.cloud[0].data(), S.cloud[0].size() / 3, lo, hi, cr.data());     // :257
+    const size_t k = oracle_voxel_down_sample(cr.data(), m, S.cfg.edge_down_sample_submap, ds.data());
+    S.cloud[0].assign(ds.begin(), ds.begin() + 3 * k);
+  }
+  {
+    const double L = S.cfg.ground_crop_box_length;
+    const double lo[3] = {c[0] - L, c[1] - L, c[2] - L}, hi[3] = {c[0] + L, c[1] + L, c[2] + L};
+    std::vector<double> cr(S.cloud[3].size()), ds(S.cloud[3].size());
+    const size_t m = oracle_crop(S.cloud[3].data(), S.cloud[3].size() / 3, lo, hi, cr.data());     // :264
+    const size_t k = oracle_voxel_down_sample(cr.data(), m, S.cfg.ground_down_sample_submap, ds.data());
+    S.cloud[3].assign(ds.begin(), ds.begin() + 3 * k);
+  }
+  return 0;
+}
+size_t oracle_submap_size(void* s, int cloud) { return static_cast<SubmapOracle*>(s)->cloud[cloud].size() / 3; }
+const double* oracle_submap_data(void* s, int cloud) { return static_cast<SubmapOracle*>(s)->cloud[cloud].data(); }
 
 }  // extern "C"

@@ -133,6 +133,36 @@ int oracle_build_factors(void* h, int cloud, const double x[6], int* valid, doub
 void oracle_update_weight(double* weights, const double* slots, size_t n, double noise_bound_sq, double th1,
                           double th2, double mu);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row (f)-1: submap maintenance, FrontEnd::updateSubmap (ref: src/front_end/front_end.cpp:201-267) and the
+ * first-frame seeding (ref: front_end.cpp:285-305), with PointCloud2::Transform / operator+= / Crop /
+ * VoxelDownSample (ref: src/open3d/PointCloud2.cpp:71-75, 96-132, 358-403, 551-559).
+ * VoxelDownSample's output order in the reference is std::unordered_map iteration order (implementation
+ * defined); the oracle emits voxels in ascending (ix,iy,iz) order and tests compare as sets. */
+typedef struct oracle_submap_config {
+  double ground_down_sample;          /* 0.3  (scan ground, processCloud, front_end.cpp:183) */
+  double ground_down_sample_submap;   /* 0.45 */
+  double edge_down_sample_submap;     /* 0.3  */
+  int planar_frame_size;              /* 3 */
+  int sphere_frame_size;              /* 3 (maintained but unused by the reference) */
+  double edge_crop_box_length, ground_crop_box_length;   /* 100, 100 */
+} oracle_submap_config;
+void oracle_submap_default_config(oracle_submap_config* c);
+/* out must hold n points; returns the number of voxels. */
+size_t oracle_voxel_down_sample(const double* pts, size_t n, double voxel, double* out);
+size_t oracle_crop(const double* pts, size_t n, const double lo[3], const double hi[3], double* out);
+void* oracle_submap_create(const oracle_submap_config* c);
+void oracle_submap_destroy(void* s);
+/* first frame: edge = raw edge cloud, ground = raw ground cloud (down-sampled inside), planar / sphere = the
+ * "submap index" selections of the general cloud. */
+int oracle_submap_init(void* s, const double* edge, size_t ne, const double* ground_raw, size_t ng,
+                       const double* planar_sub, size_t np, const double* sphere_sub, size_t ns);
+/* later frames: pose = lidar_odom_pose (4x4 column-major); edge_scan / ground_scan = current_scan features. */
+int oracle_submap_update(void* s, const double pose[16], const double* edge_scan, size_t ne, const double* ground_scan,
+                         size_t ng, const double* planar_sub, size_t np, const double* sphere_sub, size_t ns);
+size_t oracle_submap_size(void* s, int cloud);
+const double* oracle_submap_data(void* s, int cloud);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,121 @@
+"""(f)-1: device-side submap maintenance vs the CPU restatement of FrontEnd::updateSubmap
+(ref: src/front_end/front_end.cpp:201-267, 285-305; PointCloud2::VoxelDownSample / Crop / Transform / +=)."""
+import numpy as np
+import pytest
+
+from tloam_b200 import synth
+
+
+def sort_rows(a):
+    a = np.asarray(a).reshape(-1, 3)
+    return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def numpy_voxel_down_sample(p, voxel):
+    """Independent restatement: np.unique over the integer voxel indices."""
+    mb = p.min(0) - 0.5 * voxel
+    idx = np.floor((p - mb) / voxel).astype(np.int64)
+    _, inv, cnt = np.unique(idx, axis=0, return_inverse=True, return_counts=True)
+    out = np.zeros((cnt.size, 3))
+    np.add.at(out, inv.reshape(-1), p)
+    return out / cnt[:, None]
+
+
+def test_oracle_voxel_down_sample_vs_numpy(oracle):
+    rng = np.random.default_rng(0)
+    p = rng.uniform(-20, 20, (5000, 3)) * [1, 1, 0.1]
+    for voxel in (0.3, 0.45, 2.0):
+        a = sort_rows(oracle.voxel_down_sample(p, voxel))
+        b = sort_rows(numpy_voxel_down_sample(p, voxel))
+        assert a.shape == b.shape and np.allclose(a, b, atol=1e-12)
+    assert oracle.voxel_down_sample(np.zeros((0, 3)), 0.3).shape == (0, 3)
+
+
+def test_oracle_crop_is_inclusive_and_order_preserving(oracle):
+    p = np.array([[0, 0, 0], [1, 1, 1], [1.0000001, 0, 0], [-1, -1, -1], [0.5, 0.5, 0.5]], dtype=float)
+    c = oracle.crop(p, [-1, -1, -1], [1, 1, 1])
+    assert np.array_equal(c, p[[0, 1, 3, 4]])
+
+
+def stream_inputs(nframes=4, scale=0.04):
+    st = synth.Stream(cfg=synth.scaled(scale, seed=808), seq="05", start=50)
+    dense = synth.scaled(scale * 2.0, seed=808)
+    frames = []
+    for _ in range(nframes):
+        T = st.T.copy()
+        fr = st.frame()
+        sub = synth.make_scan(dense, T, fr["frame_id"] + 1000)     # the "submap index" selections (denser)
+        fr["planar_sub"], fr["sphere_sub"] = sub[2], sub[1]
+        fr["ground_raw"] = synth.make_scan(dense, T, fr["frame_id"] + 2000)[3]
+        frames.append(fr)
+    return frames
+
+
+def test_oracle_submap_sliding_window_semantics(oracle):
+    frames = stream_inputs(5)
+    sm = oracle.Submap()
+    f0 = frames[0]
+    sm.init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    assert np.array_equal(sm.cloud(0), f0["scan"][0]) and np.array_equal(sm.cloud(1), f0["sphere_sub"])
+    sizes = []
+    for fr in frames[1:]:
+        sm.update(fr["T_gt"], fr["scan"][0], fr["scan"][3], fr["planar_sub"], fr["sphere_sub"])
+        sizes.append(sm.cloud(2).shape[0])
+        assert np.array_equal(sm.cloud(1), sm.cloud(2))          # sphere submap == planar window
+    n = [fr["planar_sub"].shape[0] for fr in frames[1:]]
+    assert sizes == [n[0], n[0] + n[1], n[0] + n[1] + n[2], n[1] + n[2] + n[3]]    # 3-frame window, frame 0 never enters
+
+
+@pytest.mark.gpu
+def test_gpu_voxel_down_sample_matches_oracle(oracle):
+    import tloam_b200
+    reg = tloam_b200.LocalRegistration()
+    rng = np.random.default_rng(1)
+    p = rng.uniform(-50, 50, (60000, 3)) * [1, 1, 0.05]
+    for voxel in (0.3, 0.45):
+        a = sort_rows(reg.voxel_down_sample(p, voxel))
+        b = sort_rows(oracle.voxel_down_sample(p, voxel))
+        assert a.shape == b.shape and np.allclose(a, b, atol=1e-10)
+    a1 = reg.voxel_down_sample(p, 0.3)
+    a2 = reg.voxel_down_sample(p, 0.3)
+    assert np.array_equal(sort_rows(a1), sort_rows(a2))           # fixed-point accumulation: bit-reproducible values
+    reg.close()
+
+
+@pytest.mark.gpu
+def test_gpu_submap_matches_oracle_over_a_stream(oracle):
+    import tloam_b200
+    frames = stream_inputs(5)
+    reg = tloam_b200.LocalRegistration()
+    sm = oracle.Submap()
+    f0 = frames[0]
+    reg.submap_init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    sm.init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    for c in range(4):
+        assert np.allclose(sort_rows(reg.submap_cloud(c)), sort_rows(sm.cloud(c)), atol=1e-10)
+    for fr in frames[1:]:
+        reg.set_input_source(fr["scan"])
+        pose = fr["T_gt"]                                          # stand-in for lidar_odom_pose
+        reg.submap_update(pose, fr["planar_sub"], fr["sphere_sub"])
+        sm.update(pose, fr["scan"][0], fr["scan"][3], fr["planar_sub"], fr["sphere_sub"])
+        for c in range(4):
+            a, b = sort_rows(reg.submap_cloud(c)), sort_rows(sm.cloud(c))
+            assert a.shape == b.shape, (c, a.shape, b.shape)
+            assert np.allclose(a, b, atol=1e-9), c
+    # registering against the device-maintained map == registering against the same clouds uploaded from the host
+    fr = frames[-1]
+    predict = fr["T_gt"] @ synth.se3_exp(synth.CONFIG1_PERTURB)
+    T_dev = reg.scan_matching(predict)
+    other = tloam_b200.LocalRegistration()
+    other.set_input_target([reg.submap_cloud(c) for c in range(4)])
+    other.set_input_source(fr["scan"])
+    T_host = other.scan_matching(predict)
+    assert np.array_equal(T_dev, T_host)
+    o = oracle.Oracle()
+    o.set_input_target(sm.clouds())
+    o.set_input_source(fr["scan"])
+    rc, T_or, _ = o.scan_matching(predict)
+    d = np.linalg.inv(T_or) @ T_dev
+    assert rc == 0 and np.linalg.norm(d[:3, 3]) < 1e-4
+    reg.close()
+    other.close()

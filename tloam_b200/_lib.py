@@ -27,6 +27,13 @@ class TlsConfig(C.Structure):
     ]
 
 
+class SubmapConfig(C.Structure):
+    """tloam_submap_config (ref: config/mapping/lidar_odometry.yaml:6-17)."""
+    _fields_ = [("ground_down_sample", C.c_double), ("ground_down_sample_submap", C.c_double),
+                ("edge_down_sample_submap", C.c_double), ("planar_frame_size", C.c_int), ("sphere_frame_size", C.c_int),
+                ("edge_crop_box_length", C.c_double), ("ground_crop_box_length", C.c_double)]
+
+
 class InnerTrace(C.Structure):
     _fields_ = [
         ("x_candidate", C.c_double * 6), ("candidate_cost", C.c_double), ("model_cost_change", C.c_double),
@@ -57,7 +64,7 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap")
 
 
 class Profile(C.Structure):
@@ -74,7 +81,8 @@ EXPORTS = [
     "tloam_b200_get_map_origin", "tloam_b200_knn", "tloam_b200_build_factors", "tloam_b200_eval_point_to_point",
     "tloam_b200_eval_point_to_line", "tloam_b200_eval_point_to_plane", "tloam_b200_se3_exp", "tloam_b200_se3_log",
     "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
-    "tloam_b200_get_profile", "tloam_b200_set_trace",
+    "tloam_b200_get_profile", "tloam_b200_set_trace", "tloam_b200_submap_default_config", "tloam_b200_submap_init",
+    "tloam_b200_submap_update", "tloam_b200_submap_sizes", "tloam_b200_submap_download", "tloam_b200_voxel_down_sample",
 ]
 
 _lib = None
@@ -132,5 +140,12 @@ def load():
     L.tloam_b200_set_profiling.argtypes = [vp, C.c_int]
     L.tloam_b200_get_profile.argtypes = [vp, C.POINTER(Profile)]
     L.tloam_b200_set_trace.argtypes = [vp, C.c_int]
+    L.tloam_b200_submap_default_config.argtypes = [C.POINTER(SubmapConfig)]
+    L.tloam_b200_submap_default_config.restype = None
+    L.tloam_b200_submap_init.argtypes = [vp, C.POINTER(SubmapConfig), dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t, dp, C.c_size_t]
+    L.tloam_b200_submap_update.argtypes = [vp, dp, dp, C.c_size_t, dp, C.c_size_t]
+    L.tloam_b200_submap_sizes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.tloam_b200_submap_download.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    L.tloam_b200_voxel_down_sample.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, C.POINTER(C.c_size_t)]
     _lib = L
     return L

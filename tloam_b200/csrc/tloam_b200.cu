@@ -10,6 +10,7 @@
 
 #include "registration.cuh"
 #include "solver.cuh"
+#include "submap.cuh"
 
 namespace tloam {
 
@@ -699,6 +700,17 @@ struct tloam_b200_handle {
   size_t ev_next = 0;
   tloam_b200_profile prof;
   unsigned long long* d_dbg = nullptr;
+  // ---- device-resident submap ((f)-1) ----
+  tloam_submap_config scfg;
+  bool submap_ready = false;
+  double* d_acc[2] = {nullptr, nullptr};   size_t cap_acc[2] = {0, 0}, n_acc[2] = {0, 0};     // edge, ground accumulators
+  double* d_acc_tmp = nullptr;             size_t cap_acc_tmp = 0;
+  std::vector<double*> ring;               std::vector<size_t> ring_n, ring_cap;               // planar sliding window
+  double* d_cat = nullptr;                 size_t cap_cat = 0, n_cat = 0;                       // concatenated planar window
+  double* d_sphere0 = nullptr;             size_t n_sphere0 = 0; bool sphere_is_init = false;  // frame-0 sphere submap
+  double* d_up = nullptr;                  size_t cap_up = 0;                                   // upload staging
+  unsigned char* d_vox = nullptr;          size_t cap_vox = 0;                                  // voxel hash scratch
+  double* d_pose = nullptr;
 };
 
 // launch bookkeeping: counts the kernel and, in profiling mode, brackets it with events
@@ -804,6 +816,9 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   cudaFree(h->d_stage_src); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
   cudaFree(h->d_partial); cudaFree(h->d_counter); cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
+  cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
+  cudaFree(h->d_up); cudaFree(h->d_vox); cudaFree(h->d_pose);
+  for (double* p : h->ring) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->h_predict) cudaFreeHost(h->h_predict);
@@ -1385,6 +1400,204 @@ int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double de
   double in[12];
   memcpy(in, x, 48); memcpy(in + 6, delta, 48);
   return run_se3(h, 2, in, 12, out, 6, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// (f)-1 device-side submap maintenance
+// ---------------------------------------------------------------------------------------------
+void tloam_b200_submap_default_config(tloam_submap_config* c) {   // ref: config/mapping/lidar_odometry.yaml:6-17
+  c->ground_down_sample = 0.3; c->ground_down_sample_submap = 0.45; c->edge_down_sample_submap = 0.3;
+  c->planar_frame_size = 3; c->sphere_frame_size = 3;
+  c->edge_crop_box_length = 100.0; c->ground_crop_box_length = 100.0;
+}
+
+static int ensure_dev(tloam_b200_handle* h, double** p, size_t* cap, size_t need_points, bool keep) {
+  if (need_points <= *cap) return TLOAM_B200_OK;
+  const size_t ncap = need_points + need_points / 2 + 1024;
+  double* q = nullptr;
+  CU_TRY(cudaMalloc(&q, ncap * 3 * sizeof(double)));
+  if (keep && *p && *cap) CU_TRY(cudaMemcpyAsync(q, *p, *cap * 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (*p) { CU_TRY(cudaStreamSynchronize(h->stream)); cudaFree(*p); }
+  *p = q; *cap = ncap;
+  return TLOAM_B200_OK;
+}
+
+// crop (inclusive box, lo > hi = no crop) + VoxelDownSample of d_in[0..n) into d_out; returns the voxel count.
+static int voxel_pipeline(tloam_b200_handle* h, const double* d_in, size_t n, const double* lo, const double* hi, double voxel,
+                          double* d_out, size_t* n_out) {
+  *n_out = 0;
+  if (n == 0) return TLOAM_B200_OK;
+  if (!(voxel > 0.0)) return TLOAM_B200_ERR_INVALID_ARG;
+  const unsigned tsize = next_pow2(2 * n + 1);
+  const size_t bytes = 256 + (size_t)tsize * (8 + 24 + 4);
+  if (bytes > h->cap_vox) {
+    cudaFree(h->d_vox);
+    h->cap_vox = bytes + bytes / 2;
+    CU_TRY(cudaMalloc(&h->d_vox, h->cap_vox));
+  }
+  VoxArgs a;
+  a.in = d_in; a.n = (unsigned)n; a.voxel = voxel;
+  for (int d = 0; d < 3; ++d) { a.lo[d] = lo ? lo[d] : -DBL_MAX; a.hi[d] = hi ? hi[d] : DBL_MAX; }
+  a.minenc = reinterpret_cast<unsigned long long*>(h->d_vox);            // [0..2] min, [3] out_count
+  a.out_count = reinterpret_cast<unsigned*>(h->d_vox + 32);
+  a.keys = reinterpret_cast<unsigned long long*>(h->d_vox + 256);
+  a.sums = reinterpret_cast<long long*>(h->d_vox + 256 + (size_t)tsize * 8);
+  a.cnt = reinterpret_cast<unsigned*>(h->d_vox + 256 + (size_t)tsize * 32);
+  a.mask = tsize - 1u;
+  a.out = d_out;
+  CU_TRY(cudaMemsetAsync(h->d_vox, 0xFF, 24, h->stream));               // min encodings = +max
+  CU_TRY(cudaMemsetAsync(h->d_vox + 24, 0, 256 - 24 + (size_t)tsize * 36, h->stream));
+  const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb);
+  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_min<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_accum<<<gb, tb, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_emit<<<(tsize + tb - 1) / tb, tb, 0, h->stream>>>(a)));
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(h->h_result + 28, a.out_count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  unsigned cnt;
+  memcpy(&cnt, h->h_result + 28, sizeof(cnt));
+  *n_out = cnt;
+  return TLOAM_B200_OK;
+}
+
+static int upload_points(tloam_b200_handle* h, const double* host, size_t n) {
+  int rc = ensure_dev(h, &h->d_up, &h->cap_up, n, false);
+  if (rc != TLOAM_B200_OK) return rc;
+  if (n) CU_TRY(cudaMemcpyAsync(h->d_up, host, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return TLOAM_B200_OK;
+}
+
+static int submap_set_target(tloam_b200_handle* h) {
+  // order at the ABI: edge, sphere, planar, ground.  After the first update the sphere map IS the planar window
+  // (ref: front_end.cpp:220-230 iterates submap_planar_buffer).
+  const double* xyz[4] = {h->d_acc[0], h->sphere_is_init ? h->d_sphere0 : h->d_cat, h->d_cat, h->d_acc[1]};
+  const size_t n[4] = {h->n_acc[0], h->sphere_is_init ? h->n_sphere0 : h->n_cat, h->n_cat, h->n_acc[1]};
+  return set_target_impl(h, xyz, n, true);
+}
+
+int tloam_b200_voxel_down_sample(tloam_b200_handle* h, const double* pts, size_t n, double voxel, double* out, size_t* n_out) {
+  if (!h || (!pts && n) || !out || !n_out) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  int rc = upload_points(h, pts, n);
+  if (rc != TLOAM_B200_OK) return rc;
+  rc = ensure_dev(h, &h->d_acc_tmp, &h->cap_acc_tmp, n, false);
+  if (rc != TLOAM_B200_OK) return rc;
+  rc = voxel_pipeline(h, h->d_up, n, nullptr, nullptr, voxel, h->d_acc_tmp, n_out);
+  if (rc != TLOAM_B200_OK) return rc;
+  if (*n_out) CU_TRY(cudaMemcpyAsync(out, h->d_acc_tmp, *n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_submap_init(tloam_b200_handle* h, const tloam_submap_config* cfg, const double* edge, size_t ne,
+                           const double* ground_raw, size_t ng, const double* planar_sub, size_t np,
+                           const double* sphere_sub, size_t ns) {
+  if (!h || !cfg || (!edge && ne) || (!ground_raw && ng) || (!planar_sub && np) || (!sphere_sub && ns)) return TLOAM_B200_ERR_INVALID_ARG;
+  if (cfg->planar_frame_size < 1 || cfg->planar_frame_size > 64) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  h->scfg = *cfg;
+  if (!h->d_pose) CU_TRY(cudaMalloc(&h->d_pose, 16 * sizeof(double)));
+  int rc;
+  // edge: raw copy (front_end.cpp:286)
+  if ((rc = ensure_dev(h, &h->d_acc[0], &h->cap_acc[0], ne, false)) != TLOAM_B200_OK) return rc;
+  if (ne) CU_TRY(cudaMemcpyAsync(h->d_acc[0], edge, ne * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->n_acc[0] = ne;
+  // ground: VoxelDownSample(ground_down_sample) (:287)
+  if ((rc = upload_points(h, ground_raw, ng)) != TLOAM_B200_OK) return rc;
+  if ((rc = ensure_dev(h, &h->d_acc[1], &h->cap_acc[1], ng, false)) != TLOAM_B200_OK) return rc;
+  if ((rc = voxel_pipeline(h, h->d_up, ng, nullptr, nullptr, cfg->ground_down_sample, h->d_acc[1], &h->n_acc[1])) != TLOAM_B200_OK) return rc;
+  // planar / sphere: the submap-index selections (:291-292); the sliding-window buffers stay empty (:285-305)
+  if ((rc = ensure_dev(h, &h->d_cat, &h->cap_cat, np, false)) != TLOAM_B200_OK) return rc;
+  if (np) CU_TRY(cudaMemcpyAsync(h->d_cat, planar_sub, np * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->n_cat = np;
+  cudaFree(h->d_sphere0); h->d_sphere0 = nullptr;
+  if (ns) {
+    CU_TRY(cudaMalloc(&h->d_sphere0, ns * 3 * sizeof(double)));
+    CU_TRY(cudaMemcpyAsync(h->d_sphere0, sphere_sub, ns * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  h->n_sphere0 = ns; h->sphere_is_init = true;
+  for (double* p : h->ring) cudaFree(p);
+  h->ring.clear(); h->ring_n.clear(); h->ring_cap.clear();
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->submap_ready = true;
+  return submap_set_target(h);
+}
+
+int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const double* planar_sub, size_t np,
+                             const double* sphere_sub, size_t ns) {
+  (void)sphere_sub; (void)ns;   // stored but never used by the reference (front_end.cpp:202-205, 220-230)
+  if (!h || !pose || (!planar_sub && np)) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->submap_ready || !h->have_src) return TLOAM_B200_ERR_NOT_READY;
+  CU_TRY(cudaSetDevice(h->device));
+  const tloam_submap_config& cf = h->scfg;
+  int rc;
+  memcpy(h->h_predict->m, pose, 16 * sizeof(double));
+  CU_TRY(cudaMemcpyAsync(h->d_pose, h->h_predict, 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const unsigned tb = 256;
+  // ---- planar sliding window (:207-217, 232-242): newest frame transformed by its pose ----
+  if ((rc = upload_points(h, planar_sub, np)) != TLOAM_B200_OK) return rc;
+  double* slot = nullptr; size_t slot_cap = 0;
+  if ((int)h->ring.size() >= cf.planar_frame_size) {            // recycle the oldest buffer
+    slot = h->ring.front(); slot_cap = h->ring_cap.front();
+    h->ring.erase(h->ring.begin()); h->ring_n.erase(h->ring_n.begin()); h->ring_cap.erase(h->ring_cap.begin());
+  }
+  if ((rc = ensure_dev(h, &slot, &slot_cap, np, false)) != TLOAM_B200_OK) return rc;
+  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, h->stream>>>(h->d_up, (unsigned)np, slot, h->d_pose)));
+  h->ring.push_back(slot); h->ring_n.push_back(np); h->ring_cap.push_back(slot_cap);
+  size_t tot = 0;
+  for (size_t k : h->ring_n) tot += k;
+  if ((rc = ensure_dev(h, &h->d_cat, &h->cap_cat, tot, false)) != TLOAM_B200_OK) return rc;
+  size_t off = 0;
+  for (size_t f = 0; f < h->ring.size(); ++f) {
+    if (h->ring_n[f]) CU_TRY(cudaMemcpyAsync(h->d_cat + 3 * off, h->ring[f], h->ring_n[f] * 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    off += h->ring_n[f];
+  }
+  h->n_cat = tot;
+  h->sphere_is_init = false;
+  // ---- edge / ground: append the current source features in the world frame (:245-246), crop (:248-264),
+  //      VoxelDownSample ----
+  const int src_cloud[2] = {0, 3};
+  const double vox[2] = {cf.edge_down_sample_submap, cf.ground_down_sample_submap};
+  const double len[2] = {cf.edge_crop_box_length, cf.ground_crop_box_length};
+  size_t soff[4], o = 0;
+  for (int c = 0; c < 4; ++c) { soff[c] = o; o += h->n_src[c]; }
+  for (int k = 0; k < 2; ++k) {
+    const size_t nadd = h->n_src[src_cloud[k]];
+    if ((rc = ensure_dev(h, &h->d_acc[k], &h->cap_acc[k], h->n_acc[k] + nadd, true)) != TLOAM_B200_OK) return rc;
+    if (nadd) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((nadd + tb - 1) / tb), tb, 0, h->stream>>>(
+        h->d_stage_src + 3 * soff[src_cloud[k]], (unsigned)nadd, h->d_acc[k] + 3 * h->n_acc[k], h->d_pose)));
+    const size_t nall = h->n_acc[k] + nadd;
+    const double lo[3] = {pose[12] - len[k], pose[13] - len[k], pose[14] - len[k]};
+    const double hi[3] = {pose[12] + len[k], pose[13] + len[k], pose[14] + len[k]};
+    if ((rc = ensure_dev(h, &h->d_acc_tmp, &h->cap_acc_tmp, nall, false)) != TLOAM_B200_OK) return rc;
+    size_t nout = 0;
+    if ((rc = voxel_pipeline(h, h->d_acc[k], nall, lo, hi, vox[k], h->d_acc_tmp, &nout)) != TLOAM_B200_OK) return rc;
+    // the down-sampled cloud becomes the accumulator (swap buffers)
+    double* t = h->d_acc[k]; h->d_acc[k] = h->d_acc_tmp; h->d_acc_tmp = t;
+    size_t tc = h->cap_acc[k]; h->cap_acc[k] = h->cap_acc_tmp; h->cap_acc_tmp = tc;
+    h->n_acc[k] = nout;
+  }
+  return submap_set_target(h);                                   // :267
+}
+
+int tloam_b200_submap_sizes(tloam_b200_handle* h, size_t n[4]) {
+  if (!h || !n) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->submap_ready) return TLOAM_B200_ERR_NOT_READY;
+  n[0] = h->n_acc[0]; n[1] = h->sphere_is_init ? h->n_sphere0 : h->n_cat; n[2] = h->n_cat; n[3] = h->n_acc[1];
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_submap_download(tloam_b200_handle* h, int cloud, double* out, size_t capacity_points) {
+  if (!h || !out || cloud < 0 || cloud > 3) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->submap_ready) return TLOAM_B200_ERR_NOT_READY;
+  size_t n[4];
+  tloam_b200_submap_sizes(h, n);
+  if (capacity_points < n[cloud]) return TLOAM_B200_ERR_INVALID_ARG;
+  const double* src = cloud == 0 ? h->d_acc[0] : cloud == 3 ? h->d_acc[1] : (cloud == 1 && h->sphere_is_init) ? h->d_sphere0 : h->d_cat;
+  CU_TRY(cudaSetDevice(h->device));
+  if (n[cloud]) CU_TRY(cudaMemcpyAsync(out, src, n[cloud] * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
 }
 
 int tloam_b200_host_alloc(void** p, size_t bytes) {

@@ -180,6 +180,36 @@ class LocalRegistration:
         self.last_dbg = [int(v) for v in p.dbg]
         return out
 
+    # ---- device-side submap maintenance ((f)-1, mirrors FrontEnd::updateSubmap) ----
+    def submap_init(self, edge, ground_raw, planar_sub, sphere_sub, **cfg_overrides):
+        cfg = _lib.SubmapConfig()
+        self._L.tloam_b200_submap_default_config(C.byref(cfg))
+        for k, v in cfg_overrides.items():
+            setattr(cfg, k, v)
+        a = [_f64(x).reshape(-1, 3) for x in (edge, ground_raw, planar_sub, sphere_sub)]
+        self._check(self._L.tloam_b200_submap_init(self._h, C.byref(cfg), _dp(a[0]), a[0].shape[0], _dp(a[1]), a[1].shape[0],
+                                                   _dp(a[2]), a[2].shape[0], _dp(a[3]), a[3].shape[0]), "submap_init")
+
+    def submap_update(self, pose, planar_sub, sphere_sub=None):
+        p = _f64(np.asarray(pose).T).reshape(16)
+        a = _f64(planar_sub).reshape(-1, 3)
+        b = _f64(sphere_sub if sphere_sub is not None else np.zeros((0, 3))).reshape(-1, 3)
+        self._check(self._L.tloam_b200_submap_update(self._h, _dp(p), _dp(a), a.shape[0], _dp(b), b.shape[0]), "submap_update")
+
+    def submap_cloud(self, cloud):
+        n = (C.c_size_t * 4)()
+        self._check(self._L.tloam_b200_submap_sizes(self._h, n), "submap_sizes")
+        out = np.zeros((n[cloud], 3))
+        self._check(self._L.tloam_b200_submap_download(self._h, cloud, _dp(out), n[cloud]), "submap_download")
+        return out
+
+    def voxel_down_sample(self, pts, voxel):
+        a = _f64(pts).reshape(-1, 3)
+        out = np.zeros_like(a)
+        n = C.c_size_t(0)
+        self._check(self._L.tloam_b200_voxel_down_sample(self._h, _dp(a), a.shape[0], float(voxel), _dp(out), C.byref(n)), "voxel_down_sample")
+        return out[:n.value].copy()
+
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):
         n = C.c_size_t(0)
