@@ -251,7 +251,7 @@ __device__ __noinline__ void end_of_solve(const SolverIO& io, int termination) {
   st->evalq = st->xq;
 }
 
-__device__ __noinline__ void install_model(FrameState* st, const GnModel& m) {
+__device__ __forceinline__ void install_model(FrameState* st, const GnModel& m) {
   for (int i = 0; i < 6; ++i) { st->d2[i] = m.d2[i]; st->y[i] = m.y[i]; }
   st->gn_norm = m.gn_norm;
   st->mu_lm = m.mu_lm;
@@ -301,7 +301,7 @@ __device__ __noinline__ bool compute_subspace(FrameState* st) {
 
 // Loop "compute step -> candidate" until a candidate needs a fresh evaluation (returns with
 // phase = kPhaseCand) or the solve terminates (end_of_solve called).
-__device__ __noinline__ void advance(const SolverIO& io) {
+__device__ __forceinline__ void advance(const SolverIO& io) {
   FrameState* st = io.st;
   const DeviceCtx& c = *io.ctx;
   while (true) {
@@ -470,7 +470,7 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
 
   // 0 = solve ended, 1 = go on with advance() and then the deferred gradient-tolerance test,
   // 2 = go on with advance(), no gradient test (step rejected)
-  int go = 0;
+  int go = 0, copy_hg = 0, trace_h0 = 0;
   if (lane == 0) {
     const double cost = tot[27];
     for (int k = 0; k < 4; ++k) st->slot_sum[k] = tot[28 + k];
@@ -489,16 +489,10 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
         if (ot) ot->n_factors[k] = nf;
       }
       st->x_cost = cost;
-      for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
-      for (int i = 0; i < 6; ++i) { st->g[i] = g[i]; st->scale[i] = sh->model.scale[i]; }
-      if (ot) {
-        ot->initial_cost = cost;
-        for (int i = 0; i < 6; ++i) {
-          ot->x_start[i] = st->x[i];
-          ot->g0[i] = st->g[i];
-          for (int j = 0; j < 6; ++j) ot->H0[i * 6 + j] = (i <= j) ? st->H[tri(i, j)] : st->H[tri(j, i)];
-        }
-      }
+      copy_hg = 1;                                                       // H, g <- tot (done by the whole warp below)
+      for (int i = 0; i < 6; ++i) st->scale[i] = sh->model.scale[i];
+      if (ot) ot->initial_cost = cost;
+      trace_h0 = ot != nullptr;
       st->mu_lm = 1e-8; st->reuse = 0; st->model_ok = 0;
       if (nf_total == 0) {
         end_of_solve(io, 5);                                             // no residual blocks
@@ -533,8 +527,7 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
           st->xq = st->candq;
           st->x_norm = norm6(st->x);
           st->x_cost = cost;
-          for (int i = 0; i < 21; ++i) st->H[i] = tot[i];
-          for (int i = 0; i < 6; ++i) st->g[i] = g[i];
+          copy_hg = 1;
           if (rel < 0.25) st->radius *= 0.5;                             // DoglegStrategy::StepAccepted
           if (rel > 0.75) st->radius = fmax(st->radius, 3.0 * st->step_norm);
           st->last_cand_valid = 0;
@@ -556,6 +549,18 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
     TL_STAMP(io, 11);
   }
   go = __shfl_sync(0xffffffffu, go, 0);
+  copy_hg = __shfl_sync(0xffffffffu, copy_hg, 0);
+  trace_h0 = __shfl_sync(0xffffffffu, trace_h0, 0);
+  if (copy_hg) {                                                         // lane-parallel: H (21) + g (6) <- tot
+    if (lane < 27) { if (lane < 21) st->H[lane] = tot[lane]; else st->g[lane - 21] = tot[lane]; }
+    __syncwarp();
+  }
+  if (trace_h0) {                                                        // lane-parallel trace of the iteration-0 system
+    tloam_b200_outer_trace* ot = outer_trace(io);
+    for (int e = lane; e < 36; e += 32) { const int i = e / 6, j = e % 6; ot->H0[e] = (i <= j) ? tot[tri(i, j)] : tot[tri(j, i)]; }
+    if (lane < 6) { ot->x_start[lane] = st->x[lane]; ot->g0[lane] = tot[21 + lane]; }
+    __syncwarp();
+  }
   if (go == 1) {                                                         // back up the state (warp-wide copy)
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh->backup);
