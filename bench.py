@@ -285,9 +285,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the registration path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the ONE JSON line: NCCL writes its version banner to fd 1 when the communicator is created,
+        # so fd 1 points at stderr until the result is printed
+        sys.stdout.flush()
+        _saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -418,7 +420,10 @@ def main():
             "what": "set_source (pinned host scan) + scan_match + tloam_b200_submap_update per frame; the map never leaves HBM"}
         if bcast:
             line["shared_map_broadcast"] = bcast
-        print(json.dumps(line))
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(_saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     reg.close()
     if world > 1:
         dist.destroy_process_group()
