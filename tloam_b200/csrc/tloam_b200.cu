@@ -158,6 +158,15 @@ __global__ void k_stage_source(const double* stage, DeviceCtx ctx, double* px, d
 // =================================================================================================
 struct Predict { double m[16]; };
 
+// Programmatic dependent launch: every frame kernel lets its successor start launching right away (its blocks
+// become resident while this grid is still running) and itself waits for its predecessor before touching
+// anything the predecessor may have written.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+
 // scanMatching prologue, ref: registration.cpp:879-886, 961-964, 1027-1033.
 __global__ void k_begin_frame(DeviceCtx ctx, const Predict* prp) {
   const Predict pr = *prp;
@@ -269,6 +278,7 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
 // Measured alternatives (config 2, us per launch): thread per feature 35-39; 8 lanes per feature with shuffle
 // merge 47, with shared-memory append + rank counting 54; two-pass selection in local memory 43.
 __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ DeviceCtx ctx) {
+  pdl_prologue();
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != kPhaseIter0) return;
   __shared__ unsigned s_beg[14][kBlk];
@@ -368,6 +378,7 @@ __device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int 
 
 template <bool kFirst>
 __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
+  pdl_prologue();
   FrameState* st = ctx.st;
   if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;
   __shared__ double s_red[kBlk / 32][32];
@@ -690,6 +701,7 @@ struct tloam_b200_handle {
   // whole-frame CUDA graph (re-captured only when the device context changes)
   Predict* h_predict = nullptr; Predict* d_predict = nullptr;
   cudaGraphExec_t gexec = nullptr; DeviceCtx gctx; bool gvalid = false; int glaunches = 0; bool use_graph = true;
+  bool use_pdl = false;     // programmatic dependent launch between the frame kernels: measured no faster inside the graph (opt-in)
   // optional per-kernel-class timing (CUDA events around every launch; off by default)
   bool profiling = false;
   bool traced_last = false;
@@ -731,6 +743,20 @@ struct LaunchScope {
 #define TL_LAUNCH(cls, ...) do { LaunchScope ls__(h, cls); __VA_ARGS__; } while (0)
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+template <typename K>
+static cudaError_t launch_pdl(K kernel, int grid, int block, cudaStream_t stream, const DeviceCtx& c, bool pdl) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, c);
+}
+
+
 
 extern "C" {
 
@@ -796,6 +822,7 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMallocHost(&h->h_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
+  { const char* e = getenv("TLOAM_B200_PDL"); h->use_pdl = (e && e[0] == '1'); }
   // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
   FrameState init;
   memset(&init, 0, sizeof(init));
@@ -1093,10 +1120,11 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
   TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, h->d_predict)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
-    TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<<<nb * 2, kBlk, 0, h->stream>>>(c)));
-    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true><<<ne, kBlk, 0, h->stream>>>(c)));
+    const bool pdl = h->use_pdl && !h->profiling;
+    TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (launch_pdl(k_correspond, nb * 2, kBlk, h->stream, c, pdl)));
+    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_pdl(k_eval<true>, ne, kBlk, h->stream, c, pdl)));
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
-      TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false><<<ne, kBlk, 0, h->stream>>>(c)));
+      TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
   }
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));
