@@ -72,6 +72,14 @@ struct FrameState {
   double curr_pose[16], last_pose[16];
 };
 
+// control block of the persistent solve kernel (k_solve)
+struct SolveCtl {
+  unsigned round;     // monotonically increasing pass counter (software grid barrier)
+  int cmd;            // 1 = another evaluation pass follows, 0 = the solve is over
+  int run_solve;      // written by k_correspond: does this outer iteration run at all
+  int pad;
+};
+
 struct DeviceCtx {
   GridDesc grid[4];
   const double* origin;         // -> MapHeader::origin inside the map blob (device memory)
@@ -93,6 +101,7 @@ struct DeviceCtx {
   unsigned* counter;            // last-block ticket
   int blk_cap;                  // stride between the two blk_count buffers
   unsigned long long* dbg;      // in-kernel timers (profiling mode only, else nullptr)
+  SolveCtl* ctl;
   FrameState* st;
   tloam_b200_stats* stats;      // device copy of the trace
 };

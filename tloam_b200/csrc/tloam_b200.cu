@@ -280,7 +280,11 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
 __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ DeviceCtx ctx) {
   pdl_prologue();
   const FrameState* st = ctx.st;
-  if (st->frame_done || st->phase != kPhaseIter0) return;
+  if (st->frame_done || st->phase != kPhaseIter0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctx.ctl->run_solve = 0;
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctx.ctl->run_solve = 1;
   __shared__ unsigned s_beg[14][kBlk];
   __shared__ unsigned s_cnt[14][kBlk];
   __shared__ float s_md[14][kBlk];
@@ -376,11 +380,11 @@ __device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int 
   return (flag & kFlagCand) && (prefix < ctx.maxnum[c]);
 }
 
+// One evaluation pass of the whole problem at st->evalq (all blocks) + reduction + solver (last block).
+// Returns true in the block that ran the solver (the state has been written back to global memory).
 template <bool kFirst>
-__global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
-  pdl_prologue();
+__device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
   FrameState* st = ctx.st;
-  if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;
   __shared__ double s_red[kBlk / 32][32];
   __shared__ int s_cnt[kBlk / 32][4];
   __shared__ double s_tot[kNRed];
@@ -394,7 +398,10 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
   int nact[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = 0.0;
-  const Rt T = pose_to_rt(st->evalq);
+  Pose7 ev;                      // read around L1: inside the persistent kernel the pose changes between passes
+  ev.qw = __ldcg(&st->evalq.qw); ev.qx = __ldcg(&st->evalq.qx); ev.qy = __ldcg(&st->evalq.qy); ev.qz = __ldcg(&st->evalq.qz);
+  ev.tx = __ldcg(&st->evalq.tx); ev.ty = __ldcg(&st->evalq.ty); ev.tz = __ldcg(&st->evalq.tz);
+  const Rt T = pose_to_rt(ev);
   // grid-stride over the 128-feature blocks (the grid is capped so that the final partial sum stays short)
   for (int fb = b; fb < ctx.blk_off[4]; fb += gridDim.x) {
     const int c = cloud_of_block(ctx, fb);
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
       act = compute_active(ctx, fb, c, ctx.flags[gi], s_warp);
       ctx.active[gi] = act ? 1 : 0;
     } else {
-      act = ctx.active[gi] != 0;
+      act = __ldcg(&ctx.active[gi]) != 0;
     }
     if (!act) continue;
     double cpt[3];
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
     s_last = (ticket == gridDim.x - 1u);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   // ---- last block: deterministic sum of the per-block partials, then the solver state machine ----
   __threadfence();
   unsigned long long tg1 = 0, tg2 = 0, tg3 = 0;
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
     // the state machine is a long dependent chain: run it on a shared-memory copy of the state
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_state);
-    for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = src[i];
+    for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = __ldcg(src + i);
   }
   if (threadIdx.x < 3 * kNRed) {
     // 3 row groups x 36 columns, 8 independent accumulators each; the summation tree is fixed => deterministic
@@ -550,6 +557,48 @@ __global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_state);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
     for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = src[i];
+  }
+  __syncthreads();
+  return true;
+}
+
+template <bool kFirst>
+__global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
+  pdl_prologue();
+  const FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;
+  eval_body<kFirst>(ctx);
+}
+
+// Persistent form of one Ceres solve: ONE launch runs the iteration-0 evaluation and every candidate evaluation
+// of an outer iteration.  Between passes all blocks wait on a round counter that the block which ran the solver
+// advances (software grid barrier; the launch is cooperative so that all blocks are co-resident).  Replaces
+// k_eval<true> + ceres_max_num_iterations x k_eval<false>: no kernel boundaries inside the solve, no no-op launches.
+__global__ void __launch_bounds__(kBlk) k_solve(const __grid_constant__ DeviceCtx ctx) {
+  SolveCtl* ctl = ctx.ctl;
+  if (__ldcg(&ctl->run_solve) == 0) return;             // launch-stable flag written by k_correspond
+  __shared__ unsigned s_r0;
+  __shared__ int s_cmd;
+  if (threadIdx.x == 0) s_r0 = atomicAdd(&ctl->round, 0u);   // consistent: nobody advances it before all blocks arrived
+  __syncthreads();
+  const unsigned r0 = s_r0;
+  bool last = eval_body<true>(ctx);
+  for (unsigned k = 1;; ++k) {
+    if (threadIdx.x == 0) {
+      if (last) {
+        const FrameState* st = ctx.st;
+        ctl->cmd = (__ldcg(&st->frame_done) == 0 && __ldcg(&st->phase) == kPhaseCand) ? 1 : 0;
+        __threadfence();
+        atomicExch(&ctl->round, r0 + k);
+      }
+      while (atomicAdd(&ctl->round, 0u) < r0 + k) __nanosleep(40);
+      s_cmd = __ldcg(&ctl->cmd);
+    }
+    __syncthreads();
+    const int cmd = s_cmd;
+    __syncthreads();
+    if (!cmd) break;
+    last = eval_body<false>(ctx);
   }
 }
 
@@ -701,6 +750,7 @@ struct tloam_b200_handle {
   // whole-frame CUDA graph (re-captured only when the device context changes)
   Predict* h_predict = nullptr; Predict* d_predict = nullptr;
   cudaGraphExec_t gexec = nullptr; DeviceCtx gctx; bool gvalid = false; int glaunches = 0; bool use_graph = true;
+  bool use_persistent = false; int solve_grid_cap = 0;  // persistent k_solve (cooperative launch): opt-in, measured no faster
   bool use_pdl = false;     // programmatic dependent launch between the frame kernels: measured no faster inside the graph (opt-in)
   // optional per-kernel-class timing (CUDA events around every launch; off by default)
   bool profiling = false;
@@ -743,6 +793,18 @@ struct LaunchScope {
 #define TL_LAUNCH(cls, ...) do { LaunchScope ls__(h, cls); __VA_ARGS__; } while (0)
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+template <typename K>
+static cudaError_t launch_coop(K kernel, int grid, int block, cudaStream_t stream, const DeviceCtx& c) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, c);
+}
 
 template <typename K>
 static cudaError_t launch_pdl(K kernel, int grid, int block, cudaStream_t stream, const DeviceCtx& c, bool pdl) {
@@ -823,6 +885,18 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_PDL"); h->use_pdl = (e && e[0] == '1'); }
+  { const char* e = getenv("TLOAM_B200_PERSISTENT"); h->use_persistent = (e && e[0] == '1'); }
+  {
+    int per_sm = 0, sms = 0, coop = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, kBlk, 0) != cudaSuccess || per_sm < 1 || !coop) {
+      cudaGetLastError();
+      h->use_persistent = false;
+      per_sm = 0;
+    }
+    h->solve_grid_cap = per_sm * sms;
+  }
   // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
   FrameState init;
   memset(&init, 0, sizeof(init));
@@ -869,7 +943,8 @@ static void fill_ctx_config(tloam_b200_handle* h) {
   c.edge_dir_thres = f.edge_dir_thres; c.cost_threshold = f.cost_threshold; c.gnc_factor = f.gnc_factor;
   c.noise_bound = f.noise_bound; c.fitness_thres = f.fitness_thres;
   for (int k = 0; k < 3; ++k) c.reinit_dir[k] = f.reinit_dir[k];
-  c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;   // stats may be nulled per call (no trace)
+  c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;
+  c.ctl = reinterpret_cast<SolveCtl*>(reinterpret_cast<char*>(h->d_counter) + 64);   // stats may be nulled per call (no trace)
 }
 
 static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
@@ -1122,9 +1197,14 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
     const bool pdl = h->use_pdl && !h->profiling;
     TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (launch_pdl(k_correspond, nb * 2, kBlk, h->stream, c, pdl)));
-    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_pdl(k_eval<true>, ne, kBlk, h->stream, c, pdl)));
-    for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
-      TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
+    if (h->use_persistent && !h->profiling) {
+      const int ns = ne < h->solve_grid_cap ? ne : h->solve_grid_cap;     // all blocks must be co-resident
+      TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_coop(k_solve, ns, kBlk, h->stream, c)));
+    } else {
+      TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_pdl(k_eval<true>, ne, kBlk, h->stream, c, pdl)));
+      for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
+        TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
+    }
   }
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));
@@ -1141,7 +1221,8 @@ int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) 
   memcpy(h->h_predict->m, predict, sizeof(Predict));
   DeviceCtx c = h->ctx;
   if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
-  const int per_frame = 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);
+  const int per_frame = (h->use_persistent && !h->profiling) ? 1 + h->cfg.max_iterations * 2
+                                                             : 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
