@@ -656,7 +656,7 @@ struct Oracle {
     }
     std::vector<unsigned char> cand(n), chk(n), cnt(n);
     std::vector<double> prims(6 * n);
-#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads())
+#pragma omp parallel for schedule(dynamic, 256) num_threads(std::min(nthreads(), 32))
     for (long long i = 0; i < static_cast<long long>(n); ++i) {
       int cap_checked, counted;
       cand[i] = static_cast<unsigned char>(correspond(c, static_cast<size_t>(i), T, &prims[6 * i], &cap_checked, &counted));
@@ -1065,7 +1065,8 @@ int scan_match(Oracle& O, const double predict[16], double result[16], oracle_st
   double noise_bound_sq = cfg.noise_bound * cfg.noise_bound;
   if (noise_bound_sq < 1e-16) noise_bound_sq = 1e-2;      // :963-964
 
-  const int nth = O.nthreads();
+  // small loops (40k features): more than ~32 OpenMP threads only adds fork/join cost on a 128-core host
+  const int nth = std::min(O.nthreads(), cfg.threads_mode == 1 ? 32 : O.nthreads());
   const bool par = cfg.threads_mode == 1;
   const int eval_threads = par ? nth : std::max(1, nth / 2);  // options.num_threads = num_threads_/2 (:1044)
   // factor_num -> which builders run (:979-1016): 4: planar,ground,edge,sphere; 3: -sphere; 2: planar,ground
