@@ -149,103 +149,15 @@ __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Thread-per-query search tuned for memory-level parallelism (used by k_correspond):
-//   stage 1: the 27 hash probes are issued as independent LDG.128 (9 per z-slab) before any is consumed; the
-//            non-empty cells are compacted into a per-thread list in shared memory (s_beg/s_cnt, [27][blockDim]);
-//   stage 2: the cells' point runs are streamed as one flattened sequence, 8 loads in flight per thread.
-// Same result as knn_search (exact, ordered by (d2, original index)).
-// ------------------------------------------------------------------------------------------------
-template <int K, int kThreads>
-__device__ __forceinline__ void knn_search_mlp(const GridDesc& g, double rx, double ry, double rz, double r2,
-                                               unsigned (*s_beg)[kThreads], unsigned (*s_cnt)[kThreads],
-                                               float (*s_md)[kThreads], TopK<K>& t) {
-  t.init();
-  if (g.n == 0u) return;
-  const int tid = threadIdx.x;
-  const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
-  // position of the query inside its cell -> lower bound of the distance to each neighbour cell
-  // (FP32 is enough for a bound that is rounded down by 1e-4 before use)
-  const float cellf = (float)g.cell, r2f = (float)r2;
-  const float fx = (float)(rx - (double)cx * g.cell), fy = (float)(ry - (double)cy * g.cell), fz = (float)(rz - (double)cz * g.cell);
-  const float lo[3] = {fx, fy, fz};
-  const float hi[3] = {cellf - fx, cellf - fy, cellf - fz};
-  int m = 0;
-  // visiting order: centre cell first, then by slab; the lower bounds let stage 2 skip cells that cannot
-  // improve a full list (dense maps: the centre cell alone usually fills it)
-#pragma unroll
-  for (int slab = 0; slab < 3; ++slab) {
-    const int dz = (slab == 0) ? 0 : (slab == 1 ? -1 : 1);
-    unsigned long long key[9];
-    uint4 e[9];
-    unsigned slot[9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const int jj = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);       // centre column first
-      key[j] = cell_key(cx + (jj % 3) - 1, cy + (jj / 3) - 1, cz + dz);
-      slot[j] = hash_key(key[j]) & g.mask;
-      e[j] = __ldg(&g.table[slot[j]]);
-    }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const int jj = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);
-      unsigned long long k = ((unsigned long long)e[j].y << 32) | e[j].x;
-      while (k != key[j] && k != 0ull) {          // collision (rare): keep probing
-        slot[j] = (slot[j] + 1u) & g.mask;
-        e[j] = __ldg(&g.table[slot[j]]);
-        k = ((unsigned long long)e[j].y << 32) | e[j].x;
-      }
-      if (k == key[j] && e[j].w != 0u) {
-        const int ox = (jj % 3) - 1, oy = (jj / 3) - 1;
-        const float mx = ox < 0 ? lo[0] : (ox > 0 ? hi[0] : 0.0f);
-        const float my = oy < 0 ? lo[1] : (oy > 0 ? hi[1] : 0.0f);
-        const float mz = dz < 0 ? lo[2] : (dz > 0 ? hi[2] : 0.0f);
-        // rounded DOWN so that FP32 arithmetic can never overstate the bound
-        const float md = fmaxf(mx * mx + my * my + mz * mz, 0.0f) * 0.9999f - 1e-12f;
-        if (md < r2f) {                           // otherwise no point of the cell lies inside the radius
-          s_md[m][tid] = md;
-          s_beg[m][tid] = e[j].z;
-          s_cnt[m][tid] = e[j].w;
-          ++m;
-        }
-      }
-    }
-  }
-  // stage 2: the cells' point runs are streamed as one flattened sequence, 8 loads in flight per thread
-  int ci = 0;
-  unsigned off = 0u, cb = 0u, cc = 0u;
-  if (m > 0) { cb = s_beg[0][tid]; cc = s_cnt[0][tid]; }
-  while (ci < m) {
-    float4 pt[8];
-    int pos[8];
-    const double worst = t.d2[K - 1];             // +inf until the list is full
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      pos[q] = -1;
-      if (ci < m) {
-        pos[q] = (int)(cb + off);
-        pt[q] = __ldg(&g.pts[pos[q]]);
-        if (++off == cc) {
-          ++ci; off = 0u;
-          while (ci < m && (double)s_md[ci][tid] > worst) ++ci;   // no point of that cell can enter the list
-          if (ci < m) { cb = s_beg[ci][tid]; cc = s_cnt[ci][tid]; }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (pos[q] >= 0) {
-        const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
-        const double d = ddx * ddx + ddy * ddy + ddz * ddz;
-        if (d < r2) t.insert(d, __float_as_int(pt[q].w), pos[q]);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Lane-pair variant of knn_search_mlp: lanes 2q and 2q+1 share query q, each visits every other cell of the
-// 27-cell neighbourhood (14 / 13 cells, centre first) with its own sorted list; lane 2q then merges the two
-// lists (K steps).  Twice the warps of the thread-per-query form for the same work: the kernel is latency-bound
+// Lane-pair search used by k_correspond: lanes 2q and 2q+1 share query q, each visits every other cell of the
+// 27-cell neighbourhood (14 / 13 cells, centre first):
+//   stage 1: the lane's hash probes are issued as two batches of 7 independent LDG.128 before any is consumed;
+//            the non-empty cells are compacted into a per-thread list in shared memory (s_beg/s_cnt/s_md,
+//            [14][blockDim]) together with a lower bound of the distance from the query to the cell;
+//   stage 2: the cells' point runs are streamed as one flattened sequence, 8 loads in flight per thread, cells
+//            whose lower bound exceeds the current K-th best distance are skipped;
+//   merge  : lane 2q pulls lane 2q+1's sorted list (K shuffle rounds).
+// Same result as knn_search (exact, ordered by (d2, original index)).  Twice the warps of the thread-per-query form for the same work: the kernel is latency-bound
 // at F = 40k (8.5 warps per SM), so the extra warps buy issue slots.  All 32 lanes must call this together.
 // On return the even lane holds the exact top-K.
 // ------------------------------------------------------------------------------------------------
@@ -346,174 +258,6 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
     if (half == 0 && op >= 0) t.insert(od, oi, op);
   }
   if (stamps) stamps[4] = clock64();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Cooperative variant: kLpq (8/16/32) consecutive lanes share one query. Lane `sub` probes cells
-// sub, sub+kLpq, ... of the 27-cell neighbourhood and scans their points into a private sorted list; the
-// lists are then merged with K rounds of a butterfly arg-min over the lane group.  Every lane of the group
-// ends with the same global top-K.  All 32 lanes of the warp must call this together.
-// ------------------------------------------------------------------------------------------------
-template <int K, int kLpq>
-__device__ __forceinline__ void knn_search_coop(const GridDesc& g, double rx, double ry, double rz, double r2, int sub,
-                                                TopK<K>& t) {
-  t.init();
-  const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
-  constexpr int kCells = (27 + kLpq - 1) / kLpq;
-  uint4 e[kCells];
-#pragma unroll
-  for (int u = 0; u < kCells; ++u) {
-    const int n = sub + u * kLpq;
-    e[u].z = 0u; e[u].w = 0u;
-    if (n < 27 && g.n != 0u) e[u] = probe_cell(g, cell_key(cx + (n % 3) - 1, cy + ((n / 3) % 3) - 1, cz + (n / 9) - 1));
-  }
-  // scan this lane's candidates, 4 loads in flight at a time (the cells' point runs are flattened)
-  unsigned total = 0;
-#pragma unroll
-  for (int u = 0; u < kCells; ++u) total += e[u].w;
-  for (unsigned base = 0; base < total; base += 4u) {
-    float4 m[4];
-    int pos[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      unsigned k = base + q;
-      pos[q] = -1;
-      if (k < total) {
-        unsigned addr = 0;
-        bool found = false;
-#pragma unroll
-        for (int u = 0; u < kCells; ++u) {
-          if (!found) {
-            if (k < e[u].w) { addr = e[u].z + k; found = true; }
-            else k -= e[u].w;
-          }
-        }
-        pos[q] = (int)addr;
-        m[q] = __ldg(&g.pts[addr]);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (pos[q] >= 0) {
-        const double ddx = (double)m[q].x - rx, ddy = (double)m[q].y - ry, ddz = (double)m[q].z - rz;
-        const double d = ddx * ddx + ddy * ddy + ddz * ddz;
-        if (d < r2) t.insert(d, __float_as_int(m[q].w), pos[q]);
-      }
-    }
-  }
-  // merge the kLpq private lists
-  TopK<K> out;
-#pragma unroll
-  for (int round = 0; round < K; ++round) {
-    double d = t.d2[0];
-    int i = t.idx[0], p = t.pos[0];
-#pragma unroll
-    for (int o = 1; o < kLpq; o <<= 1) {
-      const double od = __shfl_xor_sync(0xffffffffu, d, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-      const int op = __shfl_xor_sync(0xffffffffu, p, o);
-      if (od < d || (od == d && oi < i)) { d = od; i = oi; p = op; }
-    }
-    out.d2[round] = d; out.idx[round] = i; out.pos[round] = p;
-    if (t.idx[0] == i && t.pos[0] == p) {   // this lane owned the winner (points are unique per lane): pop it
-#pragma unroll
-      for (int j = 0; j + 1 < K; ++j) { t.d2[j] = t.d2[j + 1]; t.idx[j] = t.idx[j + 1]; t.pos[j] = t.pos[j + 1]; }
-      t.d2[K - 1] = __longlong_as_double(0x7FF0000000000000ll); t.idx[K - 1] = 0x7FFFFFFF; t.pos[K - 1] = -1;
-    }
-  }
-  t = out;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Lane-group search used by k_correspond: kLanes (8) consecutive lanes serve one query.
-//   1. each lane probes its share of the 27 cells (all its probes issued before any is consumed);
-//   2. in-radius points are APPENDED to the query's candidate buffer in shared memory (one smem atomic each);
-//   3. the lanes rank the candidates by counting (rank = number of candidates with a smaller (d2, idx) key) and
-//      scatter the K best into out_pos[] -- no sorted insertion, no shuffles, ~300 instructions per lane.
-// Exact; falls back (overflow flag) when more than kCap points lie inside the radius.
-// All lanes of the warp must call this together (it uses __syncwarp).
-// ------------------------------------------------------------------------------------------------
-constexpr int kCandCap = 40;
-struct CandBuf {
-  double d2[kCandCap];
-  int idx[kCandCap];
-  int pos[kCandCap];
-};
-
-template <int K, int kLanes>
-__device__ __forceinline__ void knn_group(const GridDesc& g, bool live, double rx, double ry, double rz, double r2,
-                                          int sub, CandBuf* buf, int* cnt, int* out_pos, double* out_d0, int* overflow) {
-  if (sub == 0) {
-    *cnt = 0;
-    *overflow = 0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) out_pos[j] = -1;
-    *out_d0 = __longlong_as_double(0x7FF0000000000000ll);
-  }
-  __syncwarp();
-  if (live && g.n != 0u) {
-    const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
-    constexpr int kCells = (27 + kLanes - 1) / kLanes;
-    unsigned long long key[kCells];
-    unsigned slot[kCells];
-    uint4 e[kCells];
-#pragma unroll
-    for (int u = 0; u < kCells; ++u) {
-      const int n = sub + u * kLanes;
-      key[u] = 0ull; e[u] = make_uint4(0u, 0u, 0u, 0u); slot[u] = 0u;
-      if (n < 27) {
-        key[u] = cell_key(cx + (n % 3) - 1, cy + ((n / 3) % 3) - 1, cz + (n / 9) - 1);
-        slot[u] = hash_key(key[u]) & g.mask;
-        e[u] = __ldg(&g.table[slot[u]]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kCells; ++u) {
-      if (key[u] == 0ull) continue;
-      unsigned long long k = ((unsigned long long)e[u].y << 32) | e[u].x;
-      while (k != key[u] && k != 0ull) {          // collision (rare): keep probing
-        slot[u] = (slot[u] + 1u) & g.mask;
-        e[u] = __ldg(&g.table[slot[u]]);
-        k = ((unsigned long long)e[u].y << 32) | e[u].x;
-      }
-      if (k != key[u]) continue;
-      const unsigned beg = e[u].z, num = e[u].w;
-      for (unsigned j0 = 0; j0 < num; j0 += 4u) {
-        float4 m[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (j0 + q < num) m[q] = __ldg(&g.pts[beg + j0 + q]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (j0 + q < num) {
-            const double ddx = (double)m[q].x - rx, ddy = (double)m[q].y - ry, ddz = (double)m[q].z - rz;
-            const double d = ddx * ddx + ddy * ddy + ddz * ddz;
-            if (d < r2) {
-              const int s = atomicAdd(cnt, 1);
-              if (s < kCandCap) { buf->d2[s] = d; buf->idx[s] = __float_as_int(m[q].w); buf->pos[s] = (int)(beg + j0 + q); }
-            }
-          }
-        }
-      }
-    }
-  }
-  __syncwarp();
-  const int total = *cnt;
-  if (total > kCandCap) { if (sub == 0) *overflow = 1; return; }
-  for (int j = sub; j < total; j += kLanes) {
-    const double dj = buf->d2[j];
-    const int ij = buf->idx[j];
-    int rank = 0;
-#pragma unroll 4
-    for (int t = 0; t < total; ++t) {
-      const double dt = buf->d2[t];
-      rank += (dt < dj || (dt == dj && buf->idx[t] < ij)) ? 1 : 0;
-    }
-    if (rank < K) {
-      out_pos[rank] = buf->pos[j];
-      if (rank == 0) *out_d0 = dj;
-    }
-  }
 }
 
 }  // namespace tloam

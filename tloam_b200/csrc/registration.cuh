@@ -29,8 +29,6 @@
 namespace tloam {
 
 constexpr int kBlk = 128;     // threads per block for all per-feature kernels
-constexpr int kLpq = 8;       // lanes cooperating on one feature's kNN in k_correspond
-constexpr int kQpb = 32;      // features per k_correspond thread block (kNN in kQpb*kLpq/kBlk rounds, fit by warp 0)
 constexpr int kNRed = 36;     // 21 (H upper) + 6 (g) + 1 (cost) + 4 (slot sum per cloud) + 4 (factors per cloud)
 constexpr int kEvalGridCap = 592;   // 148 SMs x 4: caps the rows of the final partial sum
 constexpr int kEdge = 0, kSphere = 1, kPlanar = 2, kGround = 3;
