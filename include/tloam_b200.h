@@ -54,7 +54,8 @@ typedef enum tloam_b200_status {
   TLOAM_B200_ERR_CUDA = 4,
   TLOAM_B200_ERR_NO_DEVICE = 5,
   TLOAM_B200_ERR_NOT_READY = 6,      /* scan_match before set_source / set_target */
-  TLOAM_B200_ERR_NUMERIC = 7         /* non-finite value met inside the solve */
+  TLOAM_B200_ERR_NUMERIC = 7,        /* non-finite value met inside the solve */
+  TLOAM_B200_ERR_MAP_DENSITY = 8     /* a map cell (edge = search radius) holds more than 65535 points */
 } tloam_b200_status;
 
 /* The "TLS:" YAML block (ref: config/mapping/lidar_odometry.yaml:23-39, read at registration.cpp:212-230)

@@ -343,3 +343,26 @@ def test_device_resident_inputs(small_scene):
     assert np.array_equal(a.scan_matching(small_scene["predict"]), b.scan_matching(small_scene["predict"]))
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+def test_map_cell_overflow_is_reported():
+    """More than 65535 map points in one grid cell cannot be represented by the brick table's u16 counters:
+    the frame must fail with ERR_MAP_DENSITY, never search a corrupt table."""
+    from tloam_b200 import _lib
+    from tloam_b200.registration import LocalRegistration, RegistrationError
+    rng = np.random.default_rng(5)
+    reg = LocalRegistration()
+    dense = 10.0 + 0.05 * rng.random((70000, 3))          # one 0.5 m cell
+    other = rng.uniform(-20, 20, (2000, 3))
+    src = [rng.uniform(-20, 20, (200, 3)) for _ in range(4)]
+    reg.set_input_source(src)
+    reg.set_input_target([other, other, dense, other])
+    with pytest.raises(RegistrationError) as ei:
+        reg.scan_matching(np.eye(4))
+    assert ei.value.status == _lib.ERR_MAP_DENSITY
+    with pytest.raises(RegistrationError):
+        reg.knn(2, np.zeros((4, 3)), 0.5, 5)
+    # the handle recovers with the next (sane) map
+    reg.set_input_target([other, other, other, other])
+    reg.scan_matching(np.eye(4))

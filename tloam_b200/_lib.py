@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libtloam_b200.so")
 MAX_OUTER = 16
 MAX_INNER = 8
 
-OK, ERR_INVALID_ARG, ERR_TOO_FEW_POINTS, ERR_BAD_POSE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC = range(8)
+OK, ERR_INVALID_ARG, ERR_TOO_FEW_POINTS, ERR_BAD_POSE, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_READY, ERR_NUMERIC, ERR_MAP_DENSITY = range(9)
 
 
 class TlsConfig(C.Structure):

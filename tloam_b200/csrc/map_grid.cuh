@@ -6,10 +6,13 @@
 //
 // One grid per cloud, cell edge == that cloud's search radius, so the 27 cells around a query contain
 // every point with |m - q| < r: the search is EXACT for radius-truncated kNN (no approximation).
-// Points are stored cell-sorted as float4 (x,y,z relative to a per-map origin, w = original index bits):
-// 16 B / point, one LDG.128 per candidate.  The hash table is open-addressing, 16 B / entry
-// {key 8 B, start 4 B, count 4 B}: one LDG.128 per probe.  All distance arithmetic is FP64 on the FP32
-// stored coordinates, ordering is (d2, original index) => results do not depend on the in-cell order.
+// Cells are grouped in 2x2x2 BRICKS and the hash table is keyed by brick: the 3x3x3 cell neighbourhood of
+// any query always lies in exactly 2x2x2 bricks, so a query costs 8 table probes instead of 27, and the
+// points of a brick are contiguous (sorted by brick, then by sub-cell), so the cells a query needs from one
+// brick share cache lines.  Points are float4 (x,y,z relative to a per-map origin, w = original index
+// bits): 16 B / point, one LDG.128 per candidate.  Table: open addressing, 32 B / entry (one sector)
+// {key 8 B, base 4 B, 8 x u16 sub-cell counts, pad}.  All distance arithmetic is FP64 on the FP32 stored
+// coordinates, ordering is (d2, original index) => results do not depend on the in-cell order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,7 +21,7 @@ namespace tloam {
 
 struct GridDesc {
   const float4* pts;    // [n] cell-sorted
-  const uint4* table;   // [mask+1] {key.lo, key.hi, start, count}; key == 0 => empty
+  const uint4* table;   // [mask+1] bricks, 2 x uint4 each (see brick_* below); key == 0 => empty
   unsigned mask;
   unsigned n;
   double inv_cell;
@@ -29,13 +32,14 @@ struct GridDesc {
 struct MapHeader {
   unsigned long long magic;
   unsigned n[4];
-  unsigned tsize[4];        // table entries (power of two)
+  unsigned tsize[4];        // table entries = bricks slots (power of two)
   unsigned long long pts_off[4], table_off[4];  // byte offsets inside the blob
   double origin[3];
   double cell[4];
   unsigned long long bbox_enc[6];  // ordered-uint encodings of min xyz / max xyz (build scratch)
   unsigned cursor[4];              // bump allocators (build scratch)
-  unsigned long long pad[4];
+  unsigned long long build_flags;  // bit 0: a cell holds more than kMaxCellPoints points (map unusable)
+  unsigned long long pad[3];
 };
 static_assert(sizeof(MapHeader) == 256, "MapHeader must be 256 bytes");
 constexpr unsigned long long kMapMagic = 0x544C4F414D423230ull;  // "TLOAMB20"
@@ -108,35 +112,64 @@ struct TopK {
   }
 };
 
-__device__ __forceinline__ uint4 probe_cell(const GridDesc& g, unsigned long long key) {
+// ------------------------------------------------------------------------------------------------
+// Brick entry: uint4 A = {key.lo, key.hi, base, cnt01}, uint4 B = {cnt23, cnt45, cnt67, pad}; cntXY packs the
+// u16 point counts of sub-cells X (low half) and Y (high half).  Sub-cell s = (cx&1) | (cy&1)<<1 | (cz&1)<<2,
+// the brick's points are stored sub-cell after sub-cell from `base`.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned kMaxCellPoints = 65535u;
+constexpr unsigned kBrickBytes = 32u;
+
+__host__ __device__ __forceinline__ int brick_of(int c) { return c >> 1; }    // floor(c / 2), also for c < 0
+__host__ __device__ __forceinline__ int subcell_of(int cx, int cy, int cz) { return (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2); }
+
+struct BrickEntry {
+  uint4 a, b;
+  __device__ __forceinline__ unsigned long long key() const { return ((unsigned long long)a.y << 32) | a.x; }
+  __device__ __forceinline__ unsigned word(int i) const { return i == 0 ? a.w : (i == 1 ? b.x : (i == 2 ? b.y : b.z)); }
+  __device__ __forceinline__ unsigned count(int s) const { return (word(s >> 1) >> (16 * (s & 1))) & 0xFFFFu; }
+};
+
+__device__ __forceinline__ BrickEntry load_brick(const GridDesc& g, unsigned slot) {
+  BrickEntry e;
+  e.a = __ldg(&g.table[2u * slot]);
+  e.b = __ldg(&g.table[2u * slot + 1u]);
+  return e;
+}
+
+// returns false if the brick is absent
+__device__ __forceinline__ bool probe_brick(const GridDesc& g, unsigned long long key, BrickEntry& e) {
   unsigned s = hash_key(key) & g.mask;
-  uint4 e = __ldg(&g.table[s]);
   while (true) {
-    const unsigned long long k = ((unsigned long long)e.y << 32) | e.x;
-    if (k == key) return e;
-    if (k == 0ull) { e.w = 0u; return e; }
+    e = load_brick(g, s);
+    const unsigned long long k = e.key();
+    if (k == key) return true;
+    if (k == 0ull) return false;
     s = (s + 1u) & g.mask;
-    e = __ldg(&g.table[s]);
   }
 }
 
 // Exact kNN of the query (rx,ry,rz) [coordinates RELATIVE to the map origin, FP64] restricted to
-// d2 < r2 (strict, like the std::lower_bound truncation in KDTreeFlann::SearchHybrid).
+// d2 < r2 (strict, like the std::lower_bound truncation in KDTreeFlann::SearchHybrid).  Plain
+// thread-per-query form (k_knn, k_fitness).
 template <int K>
 __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double ry, double rz, double r2, TopK<K>& t) {
   t.init();
   if (g.n == 0u) return;
   const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
+  const int bx0 = brick_of(cx - 1), by0 = brick_of(cy - 1), bz0 = brick_of(cz - 1);
 #pragma unroll 1
-  for (int dz = -1; dz <= 1; ++dz) {
-#pragma unroll 1
-    for (int dy = -1; dy <= 1; ++dy) {
-      uint4 e[3];
+  for (int ib = 0; ib < 8; ++ib) {
+    const int bx = bx0 + (ib & 1), by = by0 + ((ib >> 1) & 1), bz = bz0 + (ib >> 2);
+    BrickEntry e;
+    if (!probe_brick(g, cell_key(bx, by, bz), e)) continue;
+    unsigned beg = e.a.z;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) e[dx] = probe_cell(g, cell_key(cx + dx - 1, cy + dy, cz + dz));
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const unsigned beg = e[dx].z, cnt = e[dx].w;
+    for (int s = 0; s < 8; ++s) {
+      const unsigned cnt = e.count(s);
+      const int gx = 2 * bx + (s & 1), gy = 2 * by + ((s >> 1) & 1), gz = 2 * bz + (s >> 2);
+      const bool need = (abs(gx - cx) <= 1) && (abs(gy - cy) <= 1) && (abs(gz - cz) <= 1);
+      if (need) {
         for (unsigned j = 0; j < cnt; ++j) {
           const float4 m = __ldg(&g.pts[beg + j]);
           const double ddx = (double)m.x - rx, ddy = (double)m.y - ry, ddz = (double)m.z - rz;
@@ -144,23 +177,32 @@ __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double 
           if (d < r2) t.insert(d, __float_as_int(m.w), (int)(beg + j));
         }
       }
+      beg += cnt;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Lane-pair search used by k_correspond: lanes 2q and 2q+1 share query q, each visits every other cell of the
-// 27-cell neighbourhood (14 / 13 cells, centre first):
-//   stage 1: the lane's hash probes are issued as two batches of 7 independent LDG.128 before any is consumed;
-//            the non-empty cells are compacted into a per-thread list in shared memory (s_beg/s_cnt/s_md,
-//            [14][blockDim]) together with a lower bound of the distance from the query to the cell;
-//   stage 2: the cells' point runs are streamed as one flattened sequence, 8 loads in flight per thread, cells
-//            whose lower bound exceeds the current K-th best distance are skipped;
+// Lane-pair search used by k_correspond: lanes 2q and 2q+1 share query q; the lane takes the four bricks of one
+// z-layer of the 2x2x2 brick neighbourhood:
+//   stage 1: the lane's 4 brick probes (8 LDG.128) are issued together before any is consumed; the needed,
+//            non-empty sub-cells are compacted into a per-thread list in shared memory (s_beg/s_cnt/s_md,
+//            [kPairCells][blockDim]) together with a lower bound of the distance from the query to the cell; the
+//            nearest cell is moved to the front;
+//   stage 2: both lanes stream the pair's unified cell list as one flattened sequence, alternating points
+//            (adjacent 16 B loads), 8 loads in flight per thread; cells whose lower bound exceeds the K-th best
+//            distance known to either lane are skipped;
 //   merge  : lane 2q pulls lane 2q+1's sorted list (K shuffle rounds).
-// Same result as knn_search (exact, ordered by (d2, original index)).  Twice the warps of the thread-per-query form for the same work: the kernel is latency-bound
-// at F = 40k (8.5 warps per SM), so the extra warps buy issue slots.  All 32 lanes must call this together.
-// On return the even lane holds the exact top-K.
+// Same result as knn_search (exact, ordered by (d2, original index)).  Twice the warps of the thread-per-query
+// form for the same work: the kernel is latency-bound at F = 40k, so the extra warps buy issue slots.
+// All 32 lanes must call this together.  On return the even lane holds the exact top-K.
 // ------------------------------------------------------------------------------------------------
+#ifndef TLOAM_MERGE_RUNS
+#define TLOAM_MERGE_RUNS 1
+#endif
+constexpr bool kMergeRuns = TLOAM_MERGE_RUNS != 0;
+constexpr int kPairCells = 18;    // 3 x 3 x 2 cells at most in one z-layer of bricks
+
 template <int K, int kThreads>
 __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, double rx, double ry, double rz, double r2,
                                                 unsigned (*s_beg)[kThreads], unsigned (*s_cnt)[kThreads],
@@ -174,67 +216,116 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
     const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);
     const float cellf = (float)g.cell, r2f = (float)r2;
     const float fx = (float)(rx - (double)cx * g.cell), fy = (float)(ry - (double)cy * g.cell), fz = (float)(rz - (double)cz * g.cell);
+    const int bx0 = brick_of(cx - 1), by0 = brick_of(cy - 1), bz = brick_of(cz - 1) + half;
+    // per-axis lower bounds (squared, rounded DOWN) from the query to each of the 4 cell slabs the two bricks
+    // span; slabs outside the 3-cell neighbourhood get +big, so "md < r2" also rejects the cells not needed
+    float ax[4], ay[4], az[2];
 #pragma unroll
-    for (int batch = 0; batch < 2; ++batch) {
-      unsigned long long key[7];
-      uint4 e[7];
-      unsigned slot[7];
-      int off3[7];
+    for (int u = 0; u < 4; ++u) {
+      const int ox = 2 * bx0 + u - cx, oy = 2 * by0 + u - cy;
+      const float vx = ox < 0 ? fx : cellf - fx, vy = oy < 0 ? fy : cellf - fy;
+      ax[u] = (ox < -1 || ox > 1) ? 1.0e30f : (ox == 0 ? 0.0f : vx * vx * 0.9999f);
+      ay[u] = (oy < -1 || oy > 1) ? 1.0e30f : (oy == 0 ? 0.0f : vy * vy * 0.9999f);
+    }
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int n = 2 * (batch * 7 + j) + half;               // 0..27 ; 27 = none
-        const int mcell = (n + 13) % 27;                        // visiting order starts at the centre cell (13)
-        off3[j] = (n < 27) ? mcell : -1;
-        key[j] = 0ull; slot[j] = 0u; e[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (n < 27) {
-          key[j] = cell_key(cx + (mcell % 3) - 1, cy + ((mcell / 3) % 3) - 1, cz + (mcell / 9) - 1);
-          slot[j] = hash_key(key[j]) & g.mask;
-          e[j] = __ldg(&g.table[slot[j]]);
-        }
+    for (int u = 0; u < 2; ++u) {
+      const int oz = 2 * bz + u - cz;
+      const float vz = oz < 0 ? fz : cellf - fz;
+      az[u] = ((oz < -1 || oz > 1) ? 1.0e30f : (oz == 0 ? 0.0f : vz * vz * 0.9999f)) - 1e-12f;
+    }
+    float md_min = 3.0e38f;
+    int m_min = 0;
+    unsigned long long key[4];
+    unsigned slot[4];
+    BrickEntry e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      key[j] = cell_key(bx0 + (j & 1), by0 + (j >> 1), bz);
+      slot[j] = hash_key(key[j]) & g.mask;
+      e[j] = load_brick(g, slot[j]);
+    }
+    // runs that are contiguous in memory (neighbouring sub-cells of one brick) are merged into one list entry
+    bool open = false;
+    unsigned run_beg = 0u, run_cnt = 0u;
+    float run_md = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned long long k = e[j].key();
+      while (k != key[j] && k != 0ull) {          // collision (rare): keep probing
+        slot[j] = (slot[j] + 1u) & g.mask;
+        e[j] = load_brick(g, slot[j]);
+        k = e[j].key();
       }
+      if (stamps && j == 3) stamps[1] = stamps[2] = clock64();
+      if (k != key[j]) continue;
+      unsigned run = e[j].a.z;
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        if (off3[j] < 0) continue;
-        unsigned long long k = ((unsigned long long)e[j].y << 32) | e[j].x;
-        while (k != key[j] && k != 0ull) {          // collision (rare): keep probing
-          slot[j] = (slot[j] + 1u) & g.mask;
-          e[j] = __ldg(&g.table[slot[j]]);
-          k = ((unsigned long long)e[j].y << 32) | e[j].x;
-        }
-        if (stamps && j == 6) stamps[1 + batch] = clock64();
-        if (k == key[j] && e[j].w != 0u) {
-          const int ox = (off3[j] % 3) - 1, oy = ((off3[j] / 3) % 3) - 1, oz = (off3[j] / 9) - 1;
-          const float mx = ox < 0 ? fx : (ox > 0 ? cellf - fx : 0.0f);
-          const float my = oy < 0 ? fy : (oy > 0 ? cellf - fy : 0.0f);
-          const float mz = oz < 0 ? fz : (oz > 0 ? cellf - fz : 0.0f);
-          const float md = fmaxf(mx * mx + my * my + mz * mz, 0.0f) * 0.9999f - 1e-12f;   // rounded DOWN
-          if (md < r2f) {
-            s_md[m][tid] = md;
-            s_beg[m][tid] = e[j].z;
-            s_cnt[m][tid] = e[j].w;
+      for (int s = 0; s < 8; ++s) {
+        const unsigned cnt = e[j].count(s), beg = run;
+        run += cnt;
+        const float md = ax[2 * (j & 1) + (s & 1)] + ay[2 * (j >> 1) + ((s >> 1) & 1)] + az[s >> 2];
+        if (cnt == 0u || !(md < r2f)) continue;
+        if (kMergeRuns && open && run_beg + run_cnt == beg) {
+          run_cnt += cnt;
+          run_md = fminf(run_md, md);
+        } else {
+          if (open) {
+            if (run_md < md_min) { md_min = run_md; m_min = m; }
+            s_md[m][tid] = run_md; s_beg[m][tid] = run_beg; s_cnt[m][tid] = run_cnt;
             ++m;
           }
+          open = true; run_beg = beg; run_cnt = cnt; run_md = md;
         }
       }
     }
+    if (open) {
+      if (run_md < md_min) { md_min = run_md; m_min = m; }
+      s_md[m][tid] = run_md; s_beg[m][tid] = run_beg; s_cnt[m][tid] = run_cnt;
+      ++m;
+    }
+    if (m_min > 0) {                               // nearest cell first: it fills the list with good candidates
+      const float a0 = s_md[0][tid]; const unsigned b0 = s_beg[0][tid], c0 = s_cnt[0][tid];
+      s_md[0][tid] = s_md[m_min][tid]; s_beg[0][tid] = s_beg[m_min][tid]; s_cnt[0][tid] = s_cnt[m_min][tid];
+      s_md[m_min][tid] = a0; s_beg[m_min][tid] = b0; s_cnt[m_min][tid] = c0;
+    }
   }
+  // stage 2 walks the UNIFIED cell list of the pair (even lane's entries, then the odd lane's); in every run
+  // the even lane takes points 0,2,4.. and the odd lane 1,3,5..: the pair's two loads are adjacent (one 32 B
+  // sector), so a warp-wide load touches 16 lines instead of 32 -- this stage is bound by L1TEX wavefronts.
+  __syncwarp();
+  const int col0 = tid & ~1, col1 = tid | 1;
+  const unsigned pairmask = 3u << ((tid & 31) & ~1);
+  const int m_other = __shfl_xor_sync(0xffffffffu, m, 1);
+  const int m0 = half ? m_other : m;
+  const int mt = m + m_other;
   int ci = 0;
-  unsigned off = 0u, cb = 0u, cc = 0u;
-  if (m > 0) { cb = s_beg[0][tid]; cc = s_cnt[0][tid]; }
-  while (ci < m) {
+  unsigned off = (unsigned)half, cb = 0u, cc = 0u;
+  if (mt > 0) { const int col = (0 < m0) ? col0 : col1; cb = s_beg[0][col]; cc = s_cnt[0][col]; }
+  while (ci < mt) {
     float4 pt[8];
     int pos[8];
-    const double worst = t.d2[K - 1];             // +inf until the list is full
+    double worst = t.d2[K - 1];                   // +inf until the list is full
+    worst = fmin(worst, __shfl_xor_sync(pairmask, worst, 1));   // K candidates <= worst exist in one of the lists
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       pos[q] = -1;
-      if (ci < m) {
-        pos[q] = (int)(cb + off);
-        pt[q] = __ldg(&g.pts[pos[q]]);
-        if (++off == cc) {
-          ++ci; off = 0u;
-          while (ci < m && (double)s_md[ci][tid] > worst) ++ci;   // no point of that cell can enter the list
-          if (ci < m) { cb = s_beg[ci][tid]; cc = s_cnt[ci][tid]; }
+      if (ci < mt) {
+        if (off < cc) {
+          pos[q] = (int)(cb + off);
+          pt[q] = __ldg(&g.pts[pos[q]]);
+        }
+        off += 2u;
+        if (off - (unsigned)half >= cc) {          // pair-uniform: the run is exhausted
+          ++ci; off = (unsigned)half;
+          while (ci < mt) {                        // skip cells no point of which can enter the list
+            const float mdv = (ci < m0) ? s_md[ci][col0] : s_md[ci - m0][col1];
+            if (!((double)mdv > worst)) break;
+            ++ci;
+          }
+          if (ci < mt) {
+            const int col = (ci < m0) ? col0 : col1, row = (ci < m0) ? ci : ci - m0;
+            cb = s_beg[row][col]; cc = s_cnt[row][col];
+          }
         }
       }
     }

@@ -81,6 +81,7 @@ struct SolveCtl {
 struct DeviceCtx {
   GridDesc grid[4];
   const double* origin;         // -> MapHeader::origin inside the map blob (device memory)
+  const unsigned long long* map_flags;   // -> MapHeader::build_flags
   double r2[4];                 // squared search radius per cloud
   int n[4];                     // features per cloud
   int pad_off[4];               // first padded feature index of each cloud (multiple of kBlk)

@@ -76,38 +76,57 @@ __device__ __forceinline__ float3 rel_of(const MapBuildArgs& a, const MapHeader*
                      (float)(a.stage[3ull * i + 2] - h->origin[2]));
 }
 
+// cell of the STORED (FP32-rounded) coordinates, so that the 27-cell search is exact for what is stored
+__device__ __forceinline__ void cell_of_rel(const float3 r, double inv, int& cx, int& cy, int& cz) {
+  cx = (int)floor((double)r.x * inv); cy = (int)floor((double)r.y * inv); cz = (int)floor((double)r.z * inv);
+}
+
+// claims the point's brick (CAS on the key) and takes a rank inside its sub-cell (packed u16 counters)
 __global__ void k_map_insert(MapBuildArgs a) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.stage_off[4]) return;
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   const int c = cloud_of_point(a, i);
   const float3 r = rel_of(a, h, i);
-  const double inv = 1.0 / h->cell[c];
-  // cell of the STORED (FP32-rounded) coordinates, so that the 27-cell search is exact for what is stored
-  const int cx = (int)floor((double)r.x * inv), cy = (int)floor((double)r.y * inv), cz = (int)floor((double)r.z * inv);
-  const unsigned long long key = cell_key(cx, cy, cz);
+  int cx, cy, cz;
+  cell_of_rel(r, 1.0 / h->cell[c], cx, cy, cz);
+  const unsigned long long key = cell_key(brick_of(cx), brick_of(cy), brick_of(cz));
+  const int sub = subcell_of(cx, cy, cz);
   uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
   const unsigned mask = h->tsize[c] - 1u;
   unsigned s = hash_key(key) & mask;
   while (true) {
-    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&table[s]);
+    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&table[2u * s]);
     const unsigned long long prev = atomicCAS(kp, 0ull, key);
     if (prev == 0ull || prev == key) break;
     s = (s + 1u) & mask;
   }
+  // words 3..6 of the entry hold the 8 u16 counts
+  unsigned* words = reinterpret_cast<unsigned*>(&table[2u * s]) + 3;
+  const unsigned old = atomicAdd(&words[sub >> 1], (sub & 1) ? 0x10000u : 1u);
+  const unsigned rank = (sub & 1) ? (old >> 16) : (old & 0xFFFFu);
+  if (rank >= kMaxCellPoints) atomicOr(&h->build_flags, 1ull);    // the packed counter would wrap: map unusable
   a.slot_of[i] = s;
-  a.rank_of[i] = atomicAdd(&table[s].w, 1u);
+  a.rank_of[i] = rank;
 }
 
-// start offsets of the occupied cells: block-level exclusive scan of the counts + ONE atomic per block on the
-// cloud's bump allocator (table sizes are multiples of the block size, so a block never straddles two clouds)
+// base offsets of the occupied bricks: block-level exclusive scan of the brick totals + ONE atomic per block on
+// the cloud's bump allocator (table sizes are multiples of the block size, so a block never straddles two clouds)
 __global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0;
   while (c < 3 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
   uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
-  const unsigned cnt = (s < h->tsize[c]) ? table[s].w : 0u;
+  unsigned cnt = 0u;
+  if (s < h->tsize[c]) {
+    const uint4 ea = table[2u * s];
+    if ((ea.x | ea.y) != 0u) {
+      const uint4 eb = table[2u * s + 1u];
+      cnt = (ea.w & 0xFFFFu) + (ea.w >> 16) + (eb.x & 0xFFFFu) + (eb.x >> 16) + (eb.y & 0xFFFFu) + (eb.y >> 16) +
+            (eb.z & 0xFFFFu) + (eb.z >> 16);
+    }
+  }
   // warp inclusive scan
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned incl = cnt;
@@ -122,18 +141,28 @@ __global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
     s_base = (tot > 0u) ? atomicAdd(&h->cursor[c], tot) : 0u;
   }
   __syncthreads();
-  if (cnt > 0u) table[s].z = s_base + s_w[warp] + (incl - cnt);
+  if (cnt > 0u) table[2u * s].z = s_base + s_w[warp] + (incl - cnt);
 }
 
 __global__ void k_map_scatter(MapBuildArgs a) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.stage_off[4]) return;
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  if (h->build_flags & 1ull) return;               // counters wrapped: destinations are meaningless
   const int c = cloud_of_point(a, i);
   const float3 r = rel_of(a, h, i);
+  int cx, cy, cz;
+  cell_of_rel(r, 1.0 / h->cell[c], cx, cy, cz);
+  const int sub = subcell_of(cx, cy, cz);
   const uint4* table = reinterpret_cast<const uint4*>(a.blob + h->table_off[c]);
   float4* pts = reinterpret_cast<float4*>(a.blob + h->pts_off[c]);
-  const unsigned dst = table[a.slot_of[i]].z + a.rank_of[i];
+  const unsigned slot = a.slot_of[i];
+  const uint4 ea = table[2u * slot], eb = table[2u * slot + 1u];
+  const unsigned w[4] = {ea.w, eb.x, eb.y, eb.z};
+  unsigned dst = ea.z + a.rank_of[i];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < sub) dst += (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
   pts[dst] = make_float4(r.x, r.y, r.z, __int_as_float((int)(i - a.stage_off[c])));
 }
 
@@ -184,6 +213,12 @@ __global__ void k_begin_frame(DeviceCtx ctx, const Predict* prp) {
   *ctx.counter = 0u;
   for (int i = 0; i < 16; ++i) st->last_pose[i] = st->curr_pose[i];            // :882
   Pose7 p;
+  if (*ctx.map_flags & 1ull) {                   // a map cell overflowed its u16 counter at build time
+    st->status = TLOAM_B200_ERR_MAP_DENSITY;
+    for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
+    st->frame_done = 1;
+    return;
+  }
   if (!pose_from_matrix(pr.m, p)) {
     st->status = TLOAM_B200_ERR_BAD_POSE;
     for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
@@ -277,7 +312,10 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
 // outer iteration (ref: registration.cpp:858-876) and resets the residual slot (:1118-1121).
 // Measured alternatives (config 2, us per launch): thread per feature 35-39; 8 lanes per feature with shuffle
 // merge 47, with shared-memory append + rank counting 54; two-pass selection in local memory 43.
-__global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ DeviceCtx ctx) {
+#ifndef TLOAM_CORR_MINBLOCKS
+#define TLOAM_CORR_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kBlk, TLOAM_CORR_MINBLOCKS) k_correspond(const __grid_constant__ DeviceCtx ctx) {
   pdl_prologue();
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != kPhaseIter0) {
@@ -285,9 +323,9 @@ __global__ void __launch_bounds__(kBlk) k_correspond(const __grid_constant__ Dev
     return;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) ctx.ctl->run_solve = 1;
-  __shared__ unsigned s_beg[14][kBlk];
-  __shared__ unsigned s_cnt[14][kBlk];
-  __shared__ float s_md[14][kBlk];
+  __shared__ unsigned s_beg[kPairCells][kBlk];
+  __shared__ unsigned s_cnt[kPairCells][kBlk];
+  __shared__ float s_md[kPairCells][kBlk];
   constexpr int kQ = kBlk / 2;                 // features per thread block
   const int fb = blockIdx.x / 2, sb = blockIdx.x % 2;
   const int c = cloud_of_block(ctx, fb);
@@ -843,6 +881,7 @@ const char* tloam_b200_status_string(int s) {
     case TLOAM_B200_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
     case TLOAM_B200_ERR_NOT_READY: return "source or target not set";
     case TLOAM_B200_ERR_NUMERIC: return "non-finite value in the solve";
+    case TLOAM_B200_ERR_MAP_DENSITY: return "a map cell holds more than 65535 points";
     default: return "unknown status";
   }
 }
@@ -1027,11 +1066,11 @@ static int layout_map(tloam_b200_handle* h, const size_t n[4]) {
   size_t off = sizeof(MapHeader);
   for (int c = 0; c < 4; ++c) {
     hd.n[c] = (unsigned)n[c];
-    hd.tsize[c] = next_pow2(2 * n[c] + 1);
+    hd.tsize[c] = next_pow2(n[c] + 1);      // >= bricks + 1 even if every point sits in its own brick
     hd.cell[c] = radius_of(h->cfg, c);
     hd.pts_off[c] = off; off += round_up(n[c] * sizeof(float4), 256);
   }
-  for (int c = 0; c < 4; ++c) { hd.table_off[c] = off; off += (size_t)hd.tsize[c] * sizeof(uint4); }
+  for (int c = 0; c < 4; ++c) { hd.table_off[c] = off; off += (size_t)hd.tsize[c] * kBrickBytes; }
   for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
   h->blob_bytes = off;
   if (off > h->cap_blob) {
@@ -1053,17 +1092,23 @@ static void bind_map(tloam_b200_handle* h) {
     c.grid[k].inv_cell = 1.0 / h->hdr.cell[k];
   }
   c.origin = reinterpret_cast<const double*>(h->d_blob + offsetof(MapHeader, origin));
+  c.map_flags = reinterpret_cast<const unsigned long long*>(h->d_blob + offsetof(MapHeader, build_flags));
 }
 
 // the origin lives in the device header; fetch it once per map (tiny D2H) so that it can be passed by value
+// (and the build flags with it: a map whose cell counters overflowed must not be searched)
 static int fetch_origin(tloam_b200_handle* h) {
-  if (h->origin_known) return TLOAM_B200_OK;
-  CU_TRY(cudaMemcpyAsync(h->h_result + 24, h->d_blob + offsetof(MapHeader, origin), 3 * sizeof(double),
-                         cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(cudaStreamSynchronize(h->stream));
-  for (int d = 0; d < 3; ++d) h->hdr.origin[d] = h->h_result[24 + d];
-  h->origin_known = true;
-  return TLOAM_B200_OK;
+  if (!h->origin_known) {
+    CU_TRY(cudaMemcpyAsync(h->h_result + 24, h->d_blob + offsetof(MapHeader, origin), 3 * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->h_result + 27, h->d_blob + offsetof(MapHeader, build_flags), sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (int d = 0; d < 3; ++d) h->hdr.origin[d] = h->h_result[24 + d];
+    memcpy(&h->hdr.build_flags, h->h_result + 27, sizeof(unsigned long long));
+    h->origin_known = true;
+  }
+  return (h->hdr.build_flags & 1ull) ? TLOAM_B200_ERR_MAP_DENSITY : TLOAM_B200_OK;
 }
 
 static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
@@ -1160,7 +1205,7 @@ int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes)
   MapHeader hd;
   CU_TRY(cudaMemcpy(&hd, d_src, sizeof(hd), cudaMemcpyDeviceToHost));
   if (hd.magic != kMapMagic) return TLOAM_B200_ERR_INVALID_ARG;
-  size_t need = hd.table_off[3] + (size_t)hd.tsize[3] * sizeof(uint4);
+  size_t need = hd.table_off[3] + (size_t)hd.tsize[3] * kBrickBytes;
   if (bytes < need) return TLOAM_B200_ERR_INVALID_ARG;
   for (int c = 0; c < 4; ++c)
     if (hd.cell[c] != radius_of(h->cfg, c)) return TLOAM_B200_ERR_INVALID_ARG;   // grid cell must equal this handle's radius
@@ -1347,6 +1392,7 @@ int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse) {
   if (h->cfg.fitness_thres <= 0.0) return TLOAM_B200_OK;                 // ref: :258-261
   for (int c = 0; c < 4; ++c) if (h->cfg.fitness_thres > radius_of(h->cfg, c)) return TLOAM_B200_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(h->device));
+  { const int rc = fetch_origin(h); if (rc != TLOAM_B200_OK) return rc; }
   const int nb = h->total_blocks;
   double* d_out = nullptr;
   CU_TRY(cudaMalloc(&d_out, (size_t)nb * 2 * sizeof(double)));
@@ -1375,6 +1421,7 @@ int tloam_b200_knn(tloam_b200_handle* h, int cloud, const double* queries, size_
   if (!(radius > 0.0) || radius > h->hdr.cell[cloud] || (k != 1 && k != 3 && k != 5)) return TLOAM_B200_ERR_INVALID_ARG;
   if (nq == 0) return TLOAM_B200_OK;
   CU_TRY(cudaSetDevice(h->device));
+  { const int rc = fetch_origin(h); if (rc != TLOAM_B200_OK) return rc; }
   double *dq = nullptr, *dd = nullptr; int *di = nullptr, *dc = nullptr;
   cudaError_t e = cudaMalloc(&dq, nq * 3 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&dd, nq * k * sizeof(double));
@@ -1405,6 +1452,7 @@ int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6],
   if (!h->have_src || !h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
   if (n != h->n_src[cloud]) return TLOAM_B200_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(h->device));
+  { const int rc = fetch_origin(h); if (rc != TLOAM_B200_OK) return rc; }
   Predict pr;
   memset(&pr, 0, sizeof(pr));
   memcpy(pr.m, x, 6 * sizeof(double));
