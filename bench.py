@@ -345,9 +345,11 @@ def main():
     map_ms = sum(kern[k]["ms_per_frame"] for k in kern if k.startswith("map_"))
     dominant = max(("correspond", "eval", "eval_first"), key=lambda k: kern.get(k, {}).get("ms_per_frame", 0.0))
     peak, peak_src = measured_peak_hbm()
-    traffic = None
-    try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (cold cache)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v4_dram_traffic.json")))
+    traffic, traffic_file = None, None
+    try:   # DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` capture (cold cache)
+        import glob
+        traffic_file = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic.json")))[-1]
+        tr = json.load(open(traffic_file))
         key = {"correspond": "k_correspond(DeviceCtx)", "eval": "void k_eval<0>(DeviceCtx)", "eval_first": "void k_eval<1>(DeviceCtx)"}[dominant]
         traffic = tr[key]["dram_bytes_per_active_launch"]
     except Exception:
@@ -356,7 +358,7 @@ def main():
     achieved = alg[dominant] / (dom_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": {"correspond": "k_correspond", "eval": "k_eval<false>", "eval_first": "k_eval<true>"}[dominant],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/r1_v4_dram_traffic.json (ncu --set full, cold cache, active launches)",
+                "traffic_source": (os.path.relpath(traffic_file, ROOT) if traffic_file else "none") + " (ncu --set full, cold cache, active launches)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dominant], "avg_launch_us": dom_us,
                 "note": "single-frame launches at F=40k are latency-bound (working set is L2-resident); see DESIGN.md",
                 "kernels": kern, "map_build": {"ms_per_frame": map_ms, "achieved_GBps": alg["map_build"] / (map_ms * 1e-3) / 1e9 if map_ms > 0 else None}}

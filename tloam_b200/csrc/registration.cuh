@@ -31,6 +31,7 @@ namespace tloam {
 constexpr int kBlk = 128;     // threads per block for all per-feature kernels
 constexpr int kNRed = 36;     // 21 (H upper) + 6 (g) + 1 (cost) + 4 (slot sum per cloud) + 4 (factors per cloud)
 constexpr int kEvalGridCap = 592;   // 148 SMs x 4: caps the rows of the final partial sum
+constexpr int kEvalCluster = 8;     // k_eval runs in clusters of 8 blocks (portable maximum)
 constexpr int kEdge = 0, kSphere = 1, kPlanar = 2, kGround = 3;
 
 // flags per feature written by k_correspond
@@ -70,13 +71,6 @@ struct FrameState {
   double curr_pose[16], last_pose[16];
 };
 
-// control block of the persistent solve kernel (k_solve)
-struct SolveCtl {
-  unsigned round;     // monotonically increasing pass counter (software grid barrier)
-  int cmd;            // 1 = another evaluation pass follows, 0 = the solve is over
-  int run_solve;      // written by k_correspond: does this outer iteration run at all
-  int pad;
-};
 
 struct DeviceCtx {
   GridDesc grid[4];
@@ -100,7 +94,6 @@ struct DeviceCtx {
   unsigned* counter;            // last-block ticket
   int blk_cap;                  // stride between the two blk_count buffers
   unsigned long long* dbg;      // in-kernel timers (profiling mode only, else nullptr)
-  SolveCtl* ctl;
   FrameState* st;
   tloam_b200_stats* stats;      // device copy of the trace
 };

@@ -187,14 +187,26 @@ __global__ void k_stage_source(const double* stage, DeviceCtx ctx, double* px, d
 // =================================================================================================
 struct Predict { double m[16]; };
 
-// Programmatic dependent launch: every frame kernel lets its successor start launching right away (its blocks
-// become resident while this grid is still running) and itself waits for its predecessor before touching
-// anything the predecessor may have written.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
+// Programmatic dependent launch (opt-in, TLOAM_B200_PDL=1): a frame kernel waits for its predecessor before it
+// touches anything the predecessor may have written; the block that runs the serial tail of a k_eval (partial sum
+// + solver, ~10 us on one SM) releases the successor first, so that the successor's blocks are already resident
+// on the idle SMs when the tail ends.  (Releasing at kernel entry was measured slower: the successor's waiting
+// blocks take residency away from the running grid.)
+__device__ __forceinline__ void pdl_prologue() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// thread-block cluster barrier, split in its two halves (all threads of the block execute both, convergently)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+// store a double into the same shared-memory variable of block `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void dsmem_store(double* local_smem, unsigned rank, double v) {
+  const unsigned laddr = (unsigned)__cvta_generic_to_shared(local_smem);
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+}
 
 // scanMatching prologue, ref: registration.cpp:879-886, 961-964, 1027-1033.
 __global__ void k_begin_frame(DeviceCtx ctx, const Predict* prp) {
@@ -312,17 +324,12 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
 // outer iteration (ref: registration.cpp:858-876) and resets the residual slot (:1118-1121).
 // Measured alternatives (config 2, us per launch): thread per feature 35-39; 8 lanes per feature with shuffle
 // merge 47, with shared-memory append + rank counting 54; two-pass selection in local memory 43.
-#ifndef TLOAM_CORR_MINBLOCKS
-#define TLOAM_CORR_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(kBlk, TLOAM_CORR_MINBLOCKS) k_correspond(const __grid_constant__ DeviceCtx ctx) {
+// 5 blocks per SM (<= 102 registers): measured best; 6 (80 regs) and 8 (64 regs) spill and are 8% / 55% slower,
+// 4 (114 regs, what ptxas picks when unconstrained) is 28% slower
+__global__ void __launch_bounds__(kBlk, 5) k_correspond(const __grid_constant__ DeviceCtx ctx) {
   pdl_prologue();
   const FrameState* st = ctx.st;
-  if (st->frame_done || st->phase != kPhaseIter0) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctx.ctl->run_solve = 0;
-    return;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctx.ctl->run_solve = 1;
+  if (st->frame_done || st->phase != kPhaseIter0) return;
   __shared__ unsigned s_beg[kPairCells][kBlk];
   __shared__ unsigned s_cnt[kPairCells][kBlk];
   __shared__ float s_md[kPairCells][kBlk];
@@ -426,8 +433,10 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
   __shared__ double s_red[kBlk / 32][32];
   __shared__ int s_cnt[kBlk / 32][4];
   __shared__ double s_tot[kNRed];
+  __shared__ double s_gather[kEvalCluster][kNRed];   // only the cluster's block 0 receives (DSMEM stores of its peers)
   __shared__ int s_warp[1 + kBlk / 32];
   __shared__ bool s_last;
+  cluster_arrive();                                  // "I have started": peers may store into my shared memory
   unsigned long long tg0 = 0;
   if (ctx.dbg && threadIdx.x == 0) { tg0 = gtime_ns(); atomicMin(&ctx.dbg[0], tg0); }
   const int b = blockIdx.x;
@@ -525,6 +534,9 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
     }
   }
   __syncthreads();
+  // ---- cluster level: the 8 blocks of a cluster push their 36 block totals into block 0's shared memory ----
+  cluster_wait();                                     // every block of the cluster is running
+  const unsigned crank = cluster_rank();
   if (threadIdx.x < kNRed) {
     const int t = threadIdx.x;
     double s = 0.0;
@@ -535,17 +547,29 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
       for (int wi = 0; wi < kBlk / 32; ++wi) n += s_cnt[wi][t - 32];
       s = (double)n;
     }
-    ctx.partial[(size_t)b * kNRed + t] = s;
+    dsmem_store(&s_gather[crank][t], 0u, s);
+  }
+  cluster_arrive();                                   // release: my stores are visible to whoever waits
+  cluster_wait();
+  if (crank != 0u) return false;
+  const unsigned nclusters = gridDim.x / kEvalCluster;
+  if (threadIdx.x < kNRed) {
+    const int t = threadIdx.x;
+    double s = s_gather[0][t];
+#pragma unroll
+    for (int r = 1; r < kEvalCluster; ++r) s += s_gather[r][t];     // fixed order => deterministic
+    ctx.partial[(size_t)cluster_id() * kNRed + t] = s;
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned ticket = atomicAdd(ctx.counter, 1u);
-    s_last = (ticket == gridDim.x - 1u);
+    s_last = (ticket == nclusters - 1u);
   }
   __syncthreads();
   if (!s_last) return false;
-  // ---- last block: deterministic sum of the per-block partials, then the solver state machine ----
+  pdl_release();
+  // ---- last cluster leader: deterministic sum of the per-cluster partials, then the solver state machine ----
   __threadfence();
   unsigned long long tg1 = 0, tg2 = 0, tg3 = 0;
   if (ctx.dbg && threadIdx.x == 0) tg1 = gtime_ns();
@@ -561,15 +585,16 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
   if (threadIdx.x < 3 * kNRed) {
     // 3 row groups x 36 columns, 8 independent accumulators each; the summation tree is fixed => deterministic
     const int col = threadIdx.x % kNRed, grp = threadIdx.x / kNRed;
-    const int nb = gridDim.x;
+    const int nb = (int)nclusters;
     const double* P = ctx.partial + col;
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int r = grp;
-    for (; r + 21 < nb; r += 24) {
+    for (int r = grp; r < nb; r += 24) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += __ldcg(P + (size_t)(r + 3 * u) * kNRed);
+      for (int u = 0; u < 8; ++u) {
+        const int row = r + 3 * u;
+        if (row < nb) a[u] += __ldcg(P + (size_t)row * kNRed);
+      }
     }
-    for (; r < nb; r += 3) a[0] += __ldcg(P + (size_t)r * kNRed);
     s_part[grp][col] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   __syncthreads();
@@ -600,44 +625,14 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
   return true;
 }
 
+// Clusters of 8 blocks: the block totals are combined through distributed shared memory before they reach
+// global memory, so the serial tail sums 1/8 of the rows (40 instead of 315 at F = 40k).
 template <bool kFirst>
-__global__ void __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
+__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
   pdl_prologue();
   const FrameState* st = ctx.st;
-  if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;
+  if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;     // grid-uniform
   eval_body<kFirst>(ctx);
-}
-
-// Persistent form of one Ceres solve: ONE launch runs the iteration-0 evaluation and every candidate evaluation
-// of an outer iteration.  Between passes all blocks wait on a round counter that the block which ran the solver
-// advances (software grid barrier; the launch is cooperative so that all blocks are co-resident).  Replaces
-// k_eval<true> + ceres_max_num_iterations x k_eval<false>: no kernel boundaries inside the solve, no no-op launches.
-__global__ void __launch_bounds__(kBlk) k_solve(const __grid_constant__ DeviceCtx ctx) {
-  SolveCtl* ctl = ctx.ctl;
-  if (__ldcg(&ctl->run_solve) == 0) return;             // launch-stable flag written by k_correspond
-  __shared__ unsigned s_r0;
-  __shared__ int s_cmd;
-  if (threadIdx.x == 0) s_r0 = atomicAdd(&ctl->round, 0u);   // consistent: nobody advances it before all blocks arrived
-  __syncthreads();
-  const unsigned r0 = s_r0;
-  bool last = eval_body<true>(ctx);
-  for (unsigned k = 1;; ++k) {
-    if (threadIdx.x == 0) {
-      if (last) {
-        const FrameState* st = ctx.st;
-        ctl->cmd = (__ldcg(&st->frame_done) == 0 && __ldcg(&st->phase) == kPhaseCand) ? 1 : 0;
-        __threadfence();
-        atomicExch(&ctl->round, r0 + k);
-      }
-      while (atomicAdd(&ctl->round, 0u) < r0 + k) __nanosleep(40);
-      s_cmd = __ldcg(&ctl->cmd);
-    }
-    __syncthreads();
-    const int cmd = s_cmd;
-    __syncthreads();
-    if (!cmd) break;
-    last = eval_body<false>(ctx);
-  }
 }
 
 // ---- standalone caps kernel (used by the build_factors test entry point) ----
@@ -788,7 +783,6 @@ struct tloam_b200_handle {
   // whole-frame CUDA graph (re-captured only when the device context changes)
   Predict* h_predict = nullptr; Predict* d_predict = nullptr;
   cudaGraphExec_t gexec = nullptr; DeviceCtx gctx; bool gvalid = false; int glaunches = 0; bool use_graph = true;
-  bool use_persistent = false; int solve_grid_cap = 0;  // persistent k_solve (cooperative launch): opt-in, measured no faster
   bool use_pdl = false;     // programmatic dependent launch between the frame kernels: measured no faster inside the graph (opt-in)
   // optional per-kernel-class timing (CUDA events around every launch; off by default)
   bool profiling = false;
@@ -831,18 +825,6 @@ struct LaunchScope {
 #define TL_LAUNCH(cls, ...) do { LaunchScope ls__(h, cls); __VA_ARGS__; } while (0)
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
-
-template <typename K>
-static cudaError_t launch_coop(K kernel, int grid, int block, cudaStream_t stream, const DeviceCtx& c) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, c);
-}
 
 template <typename K>
 static cudaError_t launch_pdl(K kernel, int grid, int block, cudaStream_t stream, const DeviceCtx& c, bool pdl) {
@@ -924,18 +906,6 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_PDL"); h->use_pdl = (e && e[0] == '1'); }
-  { const char* e = getenv("TLOAM_B200_PERSISTENT"); h->use_persistent = (e && e[0] == '1'); }
-  {
-    int per_sm = 0, sms = 0, coop = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, kBlk, 0) != cudaSuccess || per_sm < 1 || !coop) {
-      cudaGetLastError();
-      h->use_persistent = false;
-      per_sm = 0;
-    }
-    h->solve_grid_cap = per_sm * sms;
-  }
   // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
   FrameState init;
   memset(&init, 0, sizeof(init));
@@ -983,7 +953,6 @@ static void fill_ctx_config(tloam_b200_handle* h) {
   c.noise_bound = f.noise_bound; c.fitness_thres = f.fitness_thres;
   for (int k = 0; k < 3; ++k) c.reinit_dir[k] = f.reinit_dir[k];
   c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;
-  c.ctl = reinterpret_cast<SolveCtl*>(reinterpret_cast<char*>(h->d_counter) + 64);   // stats may be nulled per call (no trace)
 }
 
 static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
@@ -1236,20 +1205,16 @@ static int check_ready(tloam_b200_handle* h) {
 // enqueues the frame's fixed launch sequence on h->stream (also used under stream capture)
 static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   const int nb = h->total_blocks;
-  const int ne = nb < kEvalGridCap ? nb : kEvalGridCap;   // k_eval is grid-stride over the feature blocks
+  // k_eval is grid-stride over the feature blocks; its grid is a whole number of clusters
+  const int ne = ((nb < kEvalGridCap ? nb : kEvalGridCap) + kEvalCluster - 1) / kEvalCluster * kEvalCluster;
   CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
   TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, h->d_predict)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
     const bool pdl = h->use_pdl && !h->profiling;
     TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (launch_pdl(k_correspond, nb * 2, kBlk, h->stream, c, pdl)));
-    if (h->use_persistent && !h->profiling) {
-      const int ns = ne < h->solve_grid_cap ? ne : h->solve_grid_cap;     // all blocks must be co-resident
-      TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_coop(k_solve, ns, kBlk, h->stream, c)));
-    } else {
-      TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_pdl(k_eval<true>, ne, kBlk, h->stream, c, pdl)));
-      for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
-        TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
-    }
+    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_pdl(k_eval<true>, ne, kBlk, h->stream, c, pdl)));
+    for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
+      TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
   }
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));
@@ -1266,8 +1231,7 @@ int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) 
   memcpy(h->h_predict->m, predict, sizeof(Predict));
   DeviceCtx c = h->ctx;
   if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
-  const int per_frame = (h->use_persistent && !h->profiling) ? 1 + h->cfg.max_iterations * 2
-                                                             : 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);
+  const int per_frame = 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
