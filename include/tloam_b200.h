@@ -165,7 +165,7 @@ int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double de
 enum {
   TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
-  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
@@ -207,6 +207,33 @@ int tloam_b200_submap_sizes(tloam_b200_handle* h, size_t n[4]);
 int tloam_b200_submap_download(tloam_b200_handle* h, int cloud, double* out, size_t capacity_points);
 /* PointCloud2::VoxelDownSample on the device (HOST in / out; out must hold n points). */
 int tloam_b200_voxel_down_sample(tloam_b200_handle* h, const double* pts, size_t n, double voxel, double* out, size_t* n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row (f)-2: PCA feature extraction on the device.  Replaces featureExtract::extractPlanarSphere /
+ * calculatePCAInfo (ref: src/models/feature_extraction/feature_extract.cpp:133-197, 47-122; called from
+ * FrontEnd::processCloud, src/front_end/front_end.cpp:194 and :289).  Bit-exact against oracle/feature_oracle.cpp.
+ * The handle is only used for its device, stream and scratch memory: no map or scan needs to be set. */
+typedef struct tloam_feature_config {   /* ref: config/mapping/feature.yaml */
+  double radius;                 /* 0.2  neighbour search radius */
+  int K;                         /* 20   neighbours per point (3 <= K <= 20 supported) */
+  int min_neigh;                 /* 10   points with <= min_neigh neighbours are skipped */
+  int planar_num, sphere_num;    /* 500, 300 */
+  double cvr_scan, cvr_submap;   /* 0.25, 0.15 */
+  double planar_scan_thres, planar_submap_thres, planar_vertic_thres;   /* 0.75, 0.65, 0.25 */
+} tloam_feature_config;
+void tloam_b200_feature_default_config(tloam_feature_config* c);
+/* extractPlanarSphere: xyz = the general cloud (HOST, n x 3 FP64).  Each index buffer must hold n entries; the four
+ * lists are what the reference's four std::vector<size_t> receive, INCLUDING its quirk that the two sphere lists
+ * hold ranks 0..count-1 instead of point indices (feature_extract.cpp:183-188).  sphere_candidates (optional, n
+ * entries) receives the point indices those ranks refer to (sphere candidates by descending flatness). */
+int tloam_b200_extract_planar_sphere(tloam_b200_handle* h, const tloam_feature_config* cfg, const double* xyz, size_t n,
+                                     size_t* planar_scan_index, size_t* n_planar_scan, size_t* planar_submap_index,
+                                     size_t* n_planar_submap, size_t* sphere_scan_index, size_t* n_sphere_scan,
+                                     size_t* sphere_submap_index, size_t* n_sphere_submap, size_t* sphere_candidates);
+/* calculatePCAInfo (inspection / tests): per point cvr, flatness, sphericity, normal (n x 3), num_sum and the
+ * neighbour list (n x K, ascending distance, -1 padded).  Any output pointer may be NULL. */
+int tloam_b200_pca_info(tloam_b200_handle* h, const tloam_feature_config* cfg, const double* xyz, size_t n, double* cvr,
+                        double* flatness, double* sphericity, double* normal, int* num_sum, int* neigh);
 
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);

@@ -33,6 +33,14 @@ class Config(C.Structure):
     ]
 
 
+class FeatureConfig(C.Structure):
+    """oracle_feature_config (ref: config/mapping/feature.yaml)."""
+    _fields_ = [("radius", C.c_double), ("K", C.c_int), ("min_neigh", C.c_int), ("planar_num", C.c_int),
+                ("sphere_num", C.c_int), ("cvr_scan", C.c_double), ("cvr_submap", C.c_double),
+                ("planar_scan_thres", C.c_double), ("planar_submap_thres", C.c_double),
+                ("planar_vertic_thres", C.c_double)]
+
+
 class SubmapConfig(C.Structure):
     _fields_ = [("ground_down_sample", C.c_double), ("ground_down_sample_submap", C.c_double),
                 ("edge_down_sample_submap", C.c_double), ("planar_frame_size", C.c_int), ("sphere_frame_size", C.c_int),
@@ -131,6 +139,13 @@ def lib():
         L.oracle_submap_size.restype = C.c_size_t
         L.oracle_submap_data.argtypes = [C.c_void_p, C.c_int]
         L.oracle_submap_data.restype = dp
+        szp, ip = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+        L.oracle_feature_default_config.argtypes = [C.POINTER(FeatureConfig)]
+        L.oracle_pca_info.argtypes = [dp, C.c_size_t, C.POINTER(FeatureConfig), dp, dp, dp, dp, ip, ip]
+        L.oracle_pca_info.restype = C.c_int
+        L.oracle_extract_planar_sphere.argtypes = [dp, C.c_size_t, C.POINTER(FeatureConfig), szp, szp, szp, szp, szp, szp,
+                                                   szp, szp, szp]
+        L.oracle_extract_planar_sphere.restype = C.c_int
         _lib = L
     return _lib
 
@@ -357,3 +372,43 @@ class Submap:
 
     def clouds(self):
         return [self.cloud(c) for c in range(4)]
+
+
+# ---- "next" row (f)-2: PCA feature extraction (ref: src/models/feature_extraction/feature_extract.cpp) ----
+def feature_config(**overrides):
+    c = FeatureConfig()
+    lib().oracle_feature_default_config(C.byref(c))
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+def pca_info(pts, **overrides):
+    """calculatePCAInfo: dict of per-point cvr / flatness / sphericity / normal (n,3) / num_sum / neigh (n,K)."""
+    a = _f64(pts).reshape(-1, 3)
+    c = feature_config(**overrides)
+    n = a.shape[0]
+    out = {"cvr": np.zeros(n), "flatness": np.zeros(n), "sphericity": np.zeros(n), "normal": np.zeros((n, 3)),
+           "num_sum": np.zeros(n, dtype=np.int32), "neigh": np.full((n, c.K), -1, dtype=np.int32)}
+    ip = C.POINTER(C.c_int)
+    rc = lib().oracle_pca_info(_dp(a), n, C.byref(c), _dp(out["cvr"]), _dp(out["flatness"]), _dp(out["sphericity"]),
+                               _dp(out["normal"]), out["num_sum"].ctypes.data_as(ip), out["neigh"].ctypes.data_as(ip))
+    if rc != 0:
+        raise ValueError("oracle_pca_info: empty cloud or bad configuration")
+    return out
+
+
+def extract_planar_sphere(pts, **overrides):
+    """extractPlanarSphere: (planar_scan, planar_submap, sphere_scan, sphere_submap, sphere_candidates)."""
+    a = _f64(pts).reshape(-1, 3)
+    c = feature_config(**overrides)
+    n = a.shape[0]
+    bufs = [np.zeros(max(n, 1), dtype=np.uintp) for _ in range(5)]
+    cnt = [C.c_size_t(0) for _ in range(4)]
+    szp = C.POINTER(C.c_size_t)
+    lib().oracle_extract_planar_sphere(_dp(a), n, C.byref(c), bufs[0].ctypes.data_as(szp), C.byref(cnt[0]),
+                                       bufs[1].ctypes.data_as(szp), C.byref(cnt[1]), bufs[2].ctypes.data_as(szp),
+                                       C.byref(cnt[2]), bufs[3].ctypes.data_as(szp), C.byref(cnt[3]),
+                                       bufs[4].ctypes.data_as(szp))
+    return (bufs[0][:cnt[0].value].copy(), bufs[1][:cnt[1].value].copy(), bufs[2][:cnt[2].value].copy(),
+            bufs[3][:cnt[3].value].copy(), bufs[4][:cnt[3].value].copy())

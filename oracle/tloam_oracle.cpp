@@ -367,7 +367,7 @@ struct KDTree {
       for (int i = nd.lo; i < nd.hi; ++i) {
         const int pi = perm[i];
         const double dx = pts[3 * pi] - q[0], dy = pts[3 * pi + 1] - q[1], dz = pts[3 * pi + 2] - q[2];
-        const double d = dx * dx + dy * dy + dz * dz;
+        const double d = std::fma(dz, dz, std::fma(dy, dy, dx * dx));   // spelled out: the GPU uses the same three operations
         if (d >= r2) continue;
         if (res.count < res.k || d < res.worst_d2 || (d == res.worst_d2 && pi < res.worst_idx)) res.insert(d, pi);
       }
@@ -396,7 +396,7 @@ int brute_hybrid(const double* pts, size_t n, const double q[3], double radius, 
   const double r2 = radius * radius;
   for (size_t i = 0; i < n; ++i) {
     const double dx = pts[3 * i] - q[0], dy = pts[3 * i + 1] - q[1], dz = pts[3 * i + 2] - q[2];
-    const double d = dx * dx + dy * dy + dz * dz;
+    const double d = std::fma(dz, dz, std::fma(dy, dy, dx * dx));   // spelled out: the GPU uses the same three operations
     if (d >= r2) continue;
     const int pi = static_cast<int>(i);
     if (res.count < res.k || d < res.worst_d2 || (d == res.worst_d2 && pi < res.worst_idx)) res.insert(d, pi);

@@ -163,6 +163,28 @@ int oracle_submap_update(void* s, const double pose[16], const double* edge_scan
 size_t oracle_submap_size(void* s, int cloud);
 const double* oracle_submap_data(void* s, int cloud);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row (f)-2: PCA feature extraction, featureExtract::calculatePCAInfo / extractPlanarSphere
+ * (ref: src/models/feature_extraction/feature_extract.cpp:47-122, 133-197; config/mapping/feature.yaml).
+ * Implemented in feature_oracle.cpp (compiled with -ffp-contract=off, see there). */
+typedef struct oracle_feature_config {
+  double radius;                 /* 0.2 */
+  int K;                         /* 20 */
+  int min_neigh;                 /* 10 */
+  int planar_num, sphere_num;    /* 500, 300 */
+  double cvr_scan, cvr_submap;   /* 0.25, 0.15 */
+  double planar_scan_thres, planar_submap_thres, planar_vertic_thres;   /* 0.75, 0.65, 0.25 */
+} oracle_feature_config;
+void oracle_feature_default_config(oracle_feature_config* c);
+/* per-point PCAInfo: normal is n*3, neigh is n*K (ascending distance, -1 padded). Returns 1 for an empty cloud. */
+int oracle_pca_info(const double* pts, size_t n, const oracle_feature_config* c, double* cvr, double* flatness,
+                    double* sphericity, double* normal, int* num_sum, int* neigh);
+/* the four index lists of extractPlanarSphere (each buffer holds n entries); sphere_candidates may be NULL. */
+int oracle_extract_planar_sphere(const double* pts, size_t n, const oracle_feature_config* c, size_t* planar_scan,
+                                 size_t* n_planar_scan, size_t* planar_submap, size_t* n_planar_submap,
+                                 size_t* sphere_scan, size_t* n_sphere_scan, size_t* sphere_submap,
+                                 size_t* n_sphere_submap, size_t* sphere_candidates);
+
 #ifdef __cplusplus
 }
 #endif

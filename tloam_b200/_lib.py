@@ -64,7 +64,15 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval", "submap")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature")
+
+
+class FeatureConfig(C.Structure):
+    """tloam_feature_config (include/tloam_b200.h)."""
+    _fields_ = [("radius", C.c_double), ("K", C.c_int), ("min_neigh", C.c_int), ("planar_num", C.c_int),
+                ("sphere_num", C.c_int), ("cvr_scan", C.c_double), ("cvr_submap", C.c_double),
+                ("planar_scan_thres", C.c_double), ("planar_submap_thres", C.c_double),
+                ("planar_vertic_thres", C.c_double)]
 
 
 class Profile(C.Structure):
@@ -83,6 +91,7 @@ EXPORTS = [
     "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
     "tloam_b200_get_profile", "tloam_b200_set_trace", "tloam_b200_submap_default_config", "tloam_b200_submap_init",
     "tloam_b200_submap_update", "tloam_b200_submap_sizes", "tloam_b200_submap_download", "tloam_b200_voxel_down_sample",
+    "tloam_b200_feature_default_config", "tloam_b200_extract_planar_sphere", "tloam_b200_pca_info",
 ]
 
 _lib = None
@@ -147,5 +156,12 @@ def load():
     L.tloam_b200_submap_sizes.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.tloam_b200_submap_download.argtypes = [vp, C.c_int, dp, C.c_size_t]
     L.tloam_b200_voxel_down_sample.argtypes = [vp, dp, C.c_size_t, C.c_double, dp, C.POINTER(C.c_size_t)]
+    szp = C.POINTER(C.c_size_t)
+    L.tloam_b200_feature_default_config.argtypes = [C.POINTER(FeatureConfig)]
+    L.tloam_b200_feature_default_config.restype = None
+    L.tloam_b200_extract_planar_sphere.argtypes = [vp, C.POINTER(FeatureConfig), dp, C.c_size_t, szp, szp, szp, szp, szp,
+                                                   szp, szp, szp, szp]
+    L.tloam_b200_pca_info.argtypes = [vp, C.POINTER(FeatureConfig), dp, C.c_size_t, dp, dp, dp, dp,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L

@@ -1,0 +1,303 @@
+// feature_extract.cuh -- "next" row (f)-2: PCA feature extraction on the device.
+//
+// Replaces featureExtract::calculatePCAInfo / extractPlanarSphere
+// (ref: src/models/feature_extraction/feature_extract.cpp:47-122, 133-197; config/mapping/feature.yaml;
+//  caller FrontEnd::processCloud, src/front_end/front_end.cpp:181-199): for every point of the "general" cloud the
+// K = 20 nearest neighbours within r = 0.2 m, the 3x3 covariance from raw cumulants, its eigen-decomposition, the
+// curvature / flatness / sphericity measures, then the planar / sphere selection lists.
+//
+// Exactness: the output is INDEX LISTS, so this row is held to bit-exact parity with the CPU restatement
+// (oracle/feature_oracle.cpp).  Points are therefore stored as FP64 (32 B / point: x, y, z, original index) in the
+// brick-sorted order of map_grid.cuh, distances are the same three FP64 operations as the oracle's, neighbours are
+// ordered by (d2, index), and the PCA arithmetic below is written with explicit round-to-nearest intrinsics in the
+// oracle's operation order (no FMA contraction on either side).
+#pragma once
+#include "map_grid.cuh"
+
+namespace tloam {
+
+constexpr int kFeK = 20;                 // neighbour list capacity (feature.yaml: K = 20); smaller K = a prefix
+
+struct alignas(32) FePoint { double x, y, z; long long idx; };
+
+struct FeGrid {
+  const FePoint* pts;    // [n] brick-sorted
+  const uint4* table;    // brick table (map_grid.cuh layout)
+  unsigned mask, n;
+  double inv_cell, cell;
+  const double* origin;  // MapHeader::origin (device)
+};
+
+struct FeParams {
+  double r2;
+  int K, min_neigh;
+  double cvr_submap, planar_submap_thres, planar_vertic_thres;
+};
+
+struct FeOut {           // indexed by ORIGINAL point index
+  double *cvr, *flatness, *sphericity, *normal;   // normal: [n][3]
+  int *num_sum, *neigh;                           // neigh: [n][kFeK], ascending (d2, index), -1 padded
+};
+
+__device__ __forceinline__ FePoint fe_load(const FePoint* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1);
+  FePoint r;
+  r.x = a.x; r.y = a.y; r.z = b.x; r.idx = __double_as_longlong(b.y);
+  return r;
+}
+
+__device__ __forceinline__ void fe_cell(const double* origin, double inv, double x, double y, double z, int& cx, int& cy, int& cz) {
+  cx = (int)floor((x - origin[0]) * inv); cy = (int)floor((y - origin[1]) * inv); cz = (int)floor((z - origin[2]) * inv);
+}
+
+// ---- grid build (bbox / origin / offsets are the map kernels; cells come from the FP64 coordinates here) ----
+struct FeBuildArgs {
+  const double* stage;   // AoS xyz
+  unsigned n;
+  unsigned char* blob;   // MapHeader + FePoint[n] + brick table (cloud slot 0 of the header)
+  unsigned* slot_of;
+  unsigned* rank_of;
+};
+
+__global__ void k_fe_insert(FeBuildArgs a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  int cx, cy, cz;
+  fe_cell(h->origin, 1.0 / h->cell[0], a.stage[3ull * i], a.stage[3ull * i + 1], a.stage[3ull * i + 2], cx, cy, cz);
+  const unsigned long long key = cell_key(brick_of(cx), brick_of(cy), brick_of(cz));
+  const int sub = subcell_of(cx, cy, cz);
+  uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[0]);
+  const unsigned mask = h->tsize[0] - 1u;
+  unsigned s = hash_key(key) & mask;
+  while (true) {
+    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&table[2u * s]);
+    const unsigned long long prev = atomicCAS(kp, 0ull, key);
+    if (prev == 0ull || prev == key) break;
+    s = (s + 1u) & mask;
+  }
+  unsigned* words = reinterpret_cast<unsigned*>(&table[2u * s]) + 3;
+  const unsigned old = atomicAdd(&words[sub >> 1], (sub & 1) ? 0x10000u : 1u);
+  const unsigned rank = (sub & 1) ? (old >> 16) : (old & 0xFFFFu);
+  if (rank >= kMaxCellPoints) atomicOr(&h->build_flags, 1ull);
+  a.slot_of[i] = s;
+  a.rank_of[i] = rank;
+}
+
+__global__ void k_fe_scatter(FeBuildArgs a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  if (h->build_flags & 1ull) return;
+  const double x = a.stage[3ull * i], y = a.stage[3ull * i + 1], z = a.stage[3ull * i + 2];
+  int cx, cy, cz;
+  fe_cell(h->origin, 1.0 / h->cell[0], x, y, z, cx, cy, cz);
+  const int sub = subcell_of(cx, cy, cz);
+  const uint4* table = reinterpret_cast<const uint4*>(a.blob + h->table_off[0]);
+  FePoint* pts = reinterpret_cast<FePoint*>(a.blob + h->pts_off[0]);
+  const unsigned slot = a.slot_of[i];
+  const uint4 ea = table[2u * slot], eb = table[2u * slot + 1u];
+  const unsigned w[4] = {ea.w, eb.x, eb.y, eb.z};
+  unsigned dst = ea.z + a.rank_of[i];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < sub) dst += (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+  FePoint p;
+  p.x = x; p.y = y; p.z = z; p.idx = (long long)i;
+  pts[dst] = p;
+}
+
+// ---- explicit round-to-nearest arithmetic (mirrors oracle/feature_oracle.cpp built with -ffp-contract=off) ----
+__device__ __forceinline__ double fM(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double fA(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double fS(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double fD(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double fQ(double a) { return __dsqrt_rn(a); }
+
+// cyclic Jacobi, same sweep / rotation / update order as jacobi3() of the oracle
+__device__ __forceinline__ void fe_jacobi3(const double c[6], double eig[3], double nvec[3]) {
+  double a[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}};
+  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll 1
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    const double off = fA(fA(fM(a[0][1], a[0][1]), fM(a[0][2], a[0][2])), fM(a[1][2], a[1][2]));
+    const double diag = fA(fA(fM(a[0][0], a[0][0]), fM(a[1][1], a[1][1])), fM(a[2][2], a[2][2]));
+    if (off <= fM(1e-32, diag) || off == 0.0) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = fD(fS(a[q][q], a[p][p]), fM(2.0, a[p][q]));
+        const double t = fD(theta >= 0 ? 1.0 : -1.0, fA(fabs(theta), fQ(fA(fM(theta, theta), 1.0))));
+        const double cs = fD(1.0, fQ(fA(fM(t, t), 1.0))), sn = fM(t, cs);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double akp = a[k][p], akq = a[k][q];
+          a[k][p] = fS(fM(cs, akp), fM(sn, akq));
+          a[k][q] = fA(fM(sn, akp), fM(cs, akq));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double apk = a[p][k], aqk = a[q][k];
+          a[p][k] = fS(fM(cs, apk), fM(sn, aqk));
+          a[q][k] = fA(fM(sn, apk), fM(cs, aqk));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double vkp = v[k][p], vkq = v[k][q];
+          v[k][p] = fS(fM(cs, vkp), fM(sn, vkq));
+          v[k][q] = fA(fM(sn, vkp), fM(cs, vkq));
+        }
+      }
+  }
+  // ascending order by three compare-exchanges (ties keep the lower axis first), without dynamic indexing
+  double d0 = a[0][0], d1 = a[1][1], d2 = a[2][2];
+  double n0[3] = {v[0][0], v[1][0], v[2][0]}, n1[3] = {v[0][1], v[1][1], v[2][1]}, n2[3] = {v[0][2], v[1][2], v[2][2]};
+  auto cswap = [](double& da, double& db, double* na, double* nb) {
+    if (db < da) {
+      const double t = da; da = db; db = t;
+      for (int r = 0; r < 3; ++r) { const double u = na[r]; na[r] = nb[r]; nb[r] = u; }
+    }
+  };
+  cswap(d0, d1, n0, n1);
+  cswap(d1, d2, n1, n2);
+  cswap(d0, d1, n0, n1);
+  eig[0] = d0; eig[1] = d1; eig[2] = d2;
+  nvec[0] = n0[0]; nvec[1] = n0[1]; nvec[2] = n0[2];
+}
+
+// One thread per point, taken in brick-sorted order (neighbouring threads query neighbouring bricks).
+// calculatePCAInfo, ref: feature_extract.cpp:47-122.
+__global__ void __launch_bounds__(128) k_fe_pca(FeGrid g, FeParams prm, FeOut out) {
+  const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.n) return;
+  const FePoint me = fe_load(&g.pts[p]);
+  const long long i = me.idx;
+  TopK<kFeK> t;
+  t.init();
+  int cx, cy, cz;
+  fe_cell(g.origin, g.inv_cell, me.x, me.y, me.z, cx, cy, cz);
+  const int bx0 = brick_of(cx - 1), by0 = brick_of(cy - 1), bz0 = brick_of(cz - 1);
+#pragma unroll 1
+  for (int ib = 0; ib < 8; ++ib) {
+    const int bx = bx0 + (ib & 1), by = by0 + ((ib >> 1) & 1), bz = bz0 + (ib >> 2);
+    const unsigned long long key = cell_key(bx, by, bz);
+    unsigned s = hash_key(key) & g.mask;
+    BrickEntry e;
+    bool found = false;
+    while (true) {
+      e.a = __ldg(&g.table[2u * s]); e.b = __ldg(&g.table[2u * s + 1u]);
+      const unsigned long long k = e.key();
+      if (k == key) { found = true; break; }
+      if (k == 0ull) break;
+      s = (s + 1u) & g.mask;
+    }
+    if (!found) continue;
+    unsigned beg = e.a.z;
+#pragma unroll 1
+    for (int sc = 0; sc < 8; ++sc) {
+      const unsigned cnt = e.count(sc);
+      const int gx = 2 * bx + (sc & 1), gy = 2 * by + ((sc >> 1) & 1), gz = 2 * bz + (sc >> 2);
+      if (abs(gx - cx) <= 1 && abs(gy - cy) <= 1 && abs(gz - cz) <= 1) {
+        for (unsigned j = 0; j < cnt; ++j) {
+          const FePoint m = fe_load(&g.pts[beg + j]);
+          const double ddx = m.x - me.x, ddy = m.y - me.y, ddz = m.z - me.z;
+          const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
+          if (d < prm.r2) t.insert(d, (int)m.idx, (int)(beg + j));
+        }
+      }
+      beg += cnt;
+    }
+  }
+  // SearchHybrid(cur_pt, r, K): the K nearest of the (up to kFeK) found
+  int m = 0;
+#pragma unroll
+  for (int j = 0; j < kFeK; ++j) m += (j < prm.K && t.pos[j] >= 0) ? 1 : 0;
+  double cvr = 0.0, flat = 0.0, sph = 0.0, nv[3] = {0.0, 0.0, 0.0};
+  const bool keep = m > 0 && m > prm.min_neigh;                     // :67-71
+  if (keep) {
+    double cum[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int j = 0; j < m; ++j) {                                    // ascending distance, :77-88
+      int pos = t.pos[0];
+#pragma unroll
+      for (int q = 1; q < kFeK; ++q) pos = (q == j) ? t.pos[q] : pos;
+      const FePoint nb = fe_load(&g.pts[pos]);
+      cum[0] = fA(cum[0], nb.x); cum[1] = fA(cum[1], nb.y); cum[2] = fA(cum[2], nb.z);
+      cum[3] = fA(cum[3], fM(nb.x, nb.x)); cum[4] = fA(cum[4], fM(nb.x, nb.y)); cum[5] = fA(cum[5], fM(nb.x, nb.z));
+      cum[6] = fA(cum[6], fM(nb.y, nb.y)); cum[7] = fA(cum[7], fM(nb.y, nb.z)); cum[8] = fA(cum[8], fM(nb.z, nb.z));
+    }
+    const double dm = (double)m;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cum[k] = fD(cum[k], dm);             // :89
+    const double cov[6] = {fS(cum[3], fM(cum[0], cum[0])), fS(cum[4], fM(cum[0], cum[1])), fS(cum[5], fM(cum[0], cum[2])),
+                           fS(cum[6], fM(cum[1], cum[1])), fS(cum[7], fM(cum[1], cum[2])), fS(cum[8], fM(cum[2], cum[2]))};
+    double ev[3];
+    fe_jacobi3(cov, ev, nv);                                         // :100-104
+    const double sum = fA(fA(ev[0], ev[1]), ev[2]);
+    cvr = (sum == 0.0) ? 0.0 : fD(ev[0], sum);                       // :106-111
+    flat = fD(fS(ev[1], ev[0]), ev[2]);                              // :113
+    sph = fD(ev[0], ev[2]);                                          // :114
+  }
+  out.cvr[i] = cvr; out.flatness[i] = flat; out.sphericity[i] = sph;
+  out.normal[3 * i] = nv[0]; out.normal[3 * i + 1] = nv[1]; out.normal[3 * i + 2] = nv[2];
+  out.num_sum[i] = keep ? m : 0;
+#pragma unroll
+  for (int j = 0; j < kFeK; ++j) out.neigh[i * kFeK + j] = (keep && j < m) ? t.idx[j] : -1;
+}
+
+// Classification of extractPlanarSphere, ref: feature_extract.cpp:148-164.  Sort keys: order-preserving encoding
+// of the flatness for candidates, 0 for everything else (a descending stable sort then lists the candidates
+// first, ties in ascending point index).
+__global__ void k_fe_classify(unsigned n, FeParams prm, FeOut out, unsigned long long* key_planar,
+                              unsigned long long* key_sphere, unsigned* val, unsigned* counts) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool planar = false, sphere = false;
+  double f = 0.0;
+  if (i < n) {
+    f = out.flatness[i];
+    const double c = out.cvr[i];
+    if (f > prm.planar_submap_thres && fabs(out.normal[3ull * i + 2]) < prm.planar_vertic_thres) {
+      planar = true;
+    } else if (c > prm.cvr_submap) {
+      bool max_uniform = true;
+      for (int j = 0; j < kFeK; ++j) {
+        const int item = out.neigh[(size_t)i * kFeK + j];
+        if (item < 0) break;
+        if (c < out.cvr[item]) { max_uniform = false; break; }
+      }
+      sphere = max_uniform;
+    }
+    key_planar[i] = planar ? enc_ordered(f) : 0ull;
+    key_sphere[i] = sphere ? enc_ordered(f) : 0ull;
+    val[i] = i;
+  }
+  const int np = __syncthreads_count(planar), ns = __syncthreads_count(sphere);
+  if (threadIdx.x == 0) {
+    if (np) atomicAdd(&counts[0], (unsigned)np);
+    if (ns) atomicAdd(&counts[1], (unsigned)ns);
+  }
+}
+
+// scan-list lengths (:177-188): the lists are sorted by descending flatness, so "rank < num || flatness > thres" is a
+// prefix of length max(min(num, total), #{flatness > thres}).  counts: [0] planar, [1] sphere -> [2] planar_scan,
+// [3] sphere_scan.
+__global__ void k_fe_counts(const unsigned long long* key_planar, const unsigned long long* key_sphere, unsigned* counts,
+                            int planar_num, int sphere_num, double planar_scan_thres, double cvr_scan) {
+  if (threadIdx.x >= 2) return;
+  const unsigned long long* keys = threadIdx.x == 0 ? key_planar : key_sphere;
+  const unsigned total = counts[threadIdx.x];
+  const unsigned long long thr = enc_ordered(threadIdx.x == 0 ? planar_scan_thres : cvr_scan);
+  unsigned lo = 0, hi = total;              // first position whose key is NOT > thr
+  while (lo < hi) {
+    const unsigned mid = (lo + hi) / 2;
+    if (keys[mid] > thr) lo = mid + 1; else hi = mid;
+  }
+  const unsigned num = (unsigned)max(threadIdx.x == 0 ? planar_num : sphere_num, 0);
+  const unsigned base = num < total ? num : total;
+  counts[2 + threadIdx.x] = lo > base ? lo : base;
+}
+
+}  // namespace tloam

@@ -173,7 +173,7 @@ __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double 
         for (unsigned j = 0; j < cnt; ++j) {
           const float4 m = __ldg(&g.pts[beg + j]);
           const double ddx = (double)m.x - rx, ddy = (double)m.y - ry, ddz = (double)m.z - rz;
-          const double d = ddx * ddx + ddy * ddy + ddz * ddz;
+          const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
           if (d < r2) t.insert(d, __float_as_int(m.w), (int)(beg + j));
         }
       }
@@ -201,6 +201,7 @@ __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double 
 #define TLOAM_MERGE_RUNS 1
 #endif
 constexpr bool kMergeRuns = TLOAM_MERGE_RUNS != 0;
+constexpr unsigned kMergeMax = 16u;   // merged entry: at most this many points
 constexpr int kPairCells = 18;    // 3 x 3 x 2 cells at most in one z-layer of bricks
 
 template <int K, int kThreads>
@@ -244,7 +245,8 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
       slot[j] = hash_key(key[j]) & g.mask;
       e[j] = load_brick(g, slot[j]);
     }
-    // runs that are contiguous in memory (neighbouring sub-cells of one brick) are merged into one list entry
+    // short runs that are contiguous in memory (neighbouring sub-cells of one brick) are merged into one list entry;
+    // long runs stay separate so that dense cells can still be pruned one by one (config 3: 400 points per cell)
     bool open = false;
     unsigned run_beg = 0u, run_cnt = 0u;
     float run_md = 0.0f;
@@ -265,7 +267,7 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
         run += cnt;
         const float md = ax[2 * (j & 1) + (s & 1)] + ay[2 * (j >> 1) + ((s >> 1) & 1)] + az[s >> 2];
         if (cnt == 0u || !(md < r2f)) continue;
-        if (kMergeRuns && open && run_beg + run_cnt == beg) {
+        if (kMergeRuns && open && run_beg + run_cnt == beg && run_cnt + cnt <= kMergeMax) {
           run_cnt += cnt;
           run_md = fminf(run_md, md);
         } else {
@@ -333,7 +335,7 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
     for (int q = 0; q < 8; ++q) {
       if (pos[q] >= 0) {
         const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
-        const double d = ddx * ddx + ddy * ddy + ddz * ddz;
+        const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
         if (d < r2) t.insert(d, __float_as_int(pt[q].w), pos[q]);
       }
     }

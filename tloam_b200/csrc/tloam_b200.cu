@@ -11,6 +11,9 @@
 #include "registration.cuh"
 #include "solver.cuh"
 #include "submap.cuh"
+#include "feature_extract.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 namespace tloam {
 
@@ -804,6 +807,8 @@ struct tloam_b200_handle {
   double* d_sphere0 = nullptr;             size_t n_sphere0 = 0; bool sphere_is_init = false;  // frame-0 sphere submap
   double* d_up = nullptr;                  size_t cap_up = 0;                                   // upload staging
   unsigned char* d_vox = nullptr;          size_t cap_vox = 0;                                  // voxel hash scratch
+  // ---- PCA feature extraction ((f)-2): one arena, carved up per call ----
+  unsigned char* d_fe = nullptr;           size_t cap_fe = 0;
   double* d_pose = nullptr;
 };
 
@@ -927,7 +932,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   cudaFree(h->d_partial); cudaFree(h->d_counter); cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
   cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
-  cudaFree(h->d_up); cudaFree(h->d_vox); cudaFree(h->d_pose);
+  cudaFree(h->d_up); cudaFree(h->d_vox); cudaFree(h->d_pose); cudaFree(h->d_fe);
   for (double* p : h->ring) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stats) cudaFreeHost(h->h_stats);
@@ -1594,6 +1599,174 @@ static int submap_set_target(tloam_b200_handle* h) {
   const double* xyz[4] = {h->d_acc[0], h->sphere_is_init ? h->d_sphere0 : h->d_cat, h->d_cat, h->d_acc[1]};
   const size_t n[4] = {h->n_acc[0], h->sphere_is_init ? h->n_sphere0 : h->n_cat, h->n_cat, h->n_acc[1]};
   return set_target_impl(h, xyz, n, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// "next" row (f)-2: PCA feature extraction (feature_extract.cuh)
+// ---------------------------------------------------------------------------------------------
+void tloam_b200_feature_default_config(tloam_feature_config* c) {   // ref: config/mapping/feature.yaml
+  c->radius = 0.2; c->K = 20; c->min_neigh = 10; c->planar_num = 500; c->sphere_num = 300;
+  c->cvr_scan = 0.25; c->cvr_submap = 0.15; c->planar_scan_thres = 0.75; c->planar_submap_thres = 0.65;
+  c->planar_vertic_thres = 0.25;
+}
+
+namespace {
+struct FeArena {
+  double* stage; unsigned* scratch; unsigned char* blob; MapHeader hdr;
+  FeOut out;
+  unsigned long long *key_p, *key_s, *key_p_sorted, *key_s_sorted;
+  unsigned *val, *val_p_sorted, *val_s_sorted, *counts;
+  void* cub_tmp; size_t cub_bytes;
+};
+}  // namespace
+
+// carves the arena for n points and enqueues grid build + k_fe_pca (+ classification and sorts when `select`)
+static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const double* xyz, size_t n, bool select, FeArena& A) {
+  if (n == 0 || n > ((size_t)1 << 30)) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!(cfg->radius > 0.0) || cfg->K < 3 || cfg->K > kFeK) return TLOAM_B200_ERR_INVALID_ARG;   // :56 asserts K >= 3
+  CU_TRY(cudaSetDevice(h->device));
+  MapHeader& hd = A.hdr;
+  memset(&hd, 0, sizeof(hd));
+  hd.magic = kMapMagic;
+  size_t boff = sizeof(MapHeader);
+  for (int c = 0; c < 4; ++c) {
+    hd.n[c] = c == 0 ? (unsigned)n : 0u;
+    hd.tsize[c] = next_pow2((c == 0 ? n : 0) + 1);
+    hd.cell[c] = cfg->radius;                       // cell edge == search radius: the 27-cell search is exact
+    hd.pts_off[c] = boff; boff += round_up(hd.n[c] * sizeof(FePoint), 256);
+  }
+  for (int c = 0; c < 4; ++c) { hd.table_off[c] = boff; boff += (size_t)hd.tsize[c] * kBrickBytes; }
+  for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
+  A.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, A.cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                            (const unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 64, h->stream);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
+  const size_t o_stage = take(n * 3 * sizeof(double)), o_scr = take(n * 2 * sizeof(unsigned)), o_blob = take(boff);
+  const size_t o_cvr = take(n * 8), o_flat = take(n * 8), o_sph = take(n * 8), o_nrm = take(n * 24), o_num = take(n * 4),
+               o_nei = take(n * kFeK * 4);
+  const size_t o_kp = take(n * 8), o_ks = take(n * 8), o_kps = take(n * 8), o_kss = take(n * 8), o_val = take(n * 4),
+               o_vps = take(n * 4), o_vss = take(n * 4), o_cnt = take(256), o_cub = take(A.cub_bytes);
+  if (off > h->cap_fe) {
+    cudaFree(h->d_fe);
+    h->cap_fe = off + off / 4;
+    CU_TRY(cudaMalloc(&h->d_fe, h->cap_fe));
+  }
+  unsigned char* b = h->d_fe;
+  A.stage = (double*)(b + o_stage); A.scratch = (unsigned*)(b + o_scr); A.blob = b + o_blob;
+  A.out.cvr = (double*)(b + o_cvr); A.out.flatness = (double*)(b + o_flat); A.out.sphericity = (double*)(b + o_sph);
+  A.out.normal = (double*)(b + o_nrm); A.out.num_sum = (int*)(b + o_num); A.out.neigh = (int*)(b + o_nei);
+  A.key_p = (unsigned long long*)(b + o_kp); A.key_s = (unsigned long long*)(b + o_ks);
+  A.key_p_sorted = (unsigned long long*)(b + o_kps); A.key_s_sorted = (unsigned long long*)(b + o_kss);
+  A.val = (unsigned*)(b + o_val); A.val_p_sorted = (unsigned*)(b + o_vps); A.val_s_sorted = (unsigned*)(b + o_vss);
+  A.counts = (unsigned*)(b + o_cnt); A.cub_tmp = b + o_cub;
+
+  CU_TRY(cudaMemcpyAsync(A.stage, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaMemcpyAsync(A.blob, &hd, sizeof(MapHeader), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaMemsetAsync(A.blob + hd.table_off[0], 0, boff - hd.table_off[0], h->stream));
+  CU_TRY(cudaMemsetAsync(A.counts, 0, 256, h->stream));
+  MapBuildArgs ma;
+  ma.stage = A.stage; ma.blob = A.blob; ma.slot_of = A.scratch; ma.rank_of = A.scratch + n;
+  ma.stage_off[0] = 0;
+  for (int c = 1; c <= 4; ++c) ma.stage_off[c] = (unsigned)n;
+  FeBuildArgs fa;
+  fa.stage = A.stage; fa.n = (unsigned)n; fa.blob = A.blob; fa.slot_of = A.scratch; fa.rank_of = A.scratch + n;
+  const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb);
+  unsigned tslots = 0;
+  for (int c = 0; c < 4; ++c) tslots += hd.tsize[c];
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(ma)));
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_origin<<<1, 32, 0, h->stream>>>(ma)));
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_insert<<<gb, tb, 0, h->stream>>>(fa)));
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(ma)));
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_scatter<<<gb, tb, 0, h->stream>>>(fa)));
+  FeGrid g;
+  g.pts = reinterpret_cast<const FePoint*>(A.blob + hd.pts_off[0]);
+  g.table = reinterpret_cast<const uint4*>(A.blob + hd.table_off[0]);
+  g.mask = hd.tsize[0] - 1u; g.n = (unsigned)n; g.cell = cfg->radius; g.inv_cell = 1.0 / cfg->radius;
+  g.origin = reinterpret_cast<const double*>(A.blob + offsetof(MapHeader, origin));
+  FeParams prm;
+  prm.r2 = cfg->radius * cfg->radius; prm.K = cfg->K; prm.min_neigh = cfg->min_neigh;
+  prm.cvr_submap = cfg->cvr_submap; prm.planar_submap_thres = cfg->planar_submap_thres;
+  prm.planar_vertic_thres = cfg->planar_vertic_thres;
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_pca<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(g, prm, A.out)));
+  if (select) {
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_classify<<<gb, tb, 0, h->stream>>>((unsigned)n, prm, A.out, A.key_p, A.key_s, A.val, A.counts)));
+    // stable descending sorts: candidates first (by flatness, ties in ascending point index), the rest (key 0) last
+    size_t tmp = A.cub_bytes;
+    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(A.cub_tmp, tmp, A.key_p, A.key_p_sorted, A.val, A.val_p_sorted, (int)n, 0, 64, h->stream));
+    tmp = A.cub_bytes;
+    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(A.cub_tmp, tmp, A.key_s, A.key_s_sorted, A.val, A.val_s_sorted, (int)n, 0, 64, h->stream));
+    h->launches += 2;
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_counts<<<1, 32, 0, h->stream>>>(A.key_p_sorted, A.key_s_sorted, A.counts, cfg->planar_num,
+                                                                           cfg->sphere_num, cfg->planar_scan_thres, cfg->cvr_scan)));
+  }
+  CU_TRY(cudaGetLastError());
+  // counts + build flags -> pinned scratch (h_result[28..31])
+  CU_TRY(cudaMemcpyAsync(h->h_result + 28, A.counts, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->h_result + 30, A.blob + offsetof(MapHeader, build_flags), sizeof(unsigned long long),
+                         cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  unsigned long long flags;
+  memcpy(&flags, h->h_result + 30, sizeof(flags));
+  return (flags & 1ull) ? TLOAM_B200_ERR_MAP_DENSITY : TLOAM_B200_OK;
+}
+
+int tloam_b200_extract_planar_sphere(tloam_b200_handle* h, const tloam_feature_config* cfg, const double* xyz, size_t n,
+                                     size_t* planar_scan_index, size_t* n_planar_scan, size_t* planar_submap_index,
+                                     size_t* n_planar_submap, size_t* sphere_scan_index, size_t* n_sphere_scan,
+                                     size_t* sphere_submap_index, size_t* n_sphere_submap, size_t* sphere_candidates) {
+  if (!h || !cfg || !planar_scan_index || !n_planar_scan || !planar_submap_index || !n_planar_submap || !sphere_scan_index ||
+      !n_sphere_scan || !sphere_submap_index || !n_sphere_submap)
+    return TLOAM_B200_ERR_INVALID_ARG;
+  *n_planar_scan = *n_planar_submap = *n_sphere_scan = *n_sphere_submap = 0;
+  if (n == 0) return TLOAM_B200_OK;              // calculatePCAInfo fails on an empty cloud: nothing is selected (:49-54, :141)
+  if (!xyz) return TLOAM_B200_ERR_INVALID_ARG;
+  FeArena A;
+  const int rc = fe_run(h, cfg, xyz, n, true, A);
+  if (rc != TLOAM_B200_OK) return rc;
+  unsigned counts[4];
+  memcpy(counts, h->h_result + 28, sizeof(counts));
+  const unsigned np = counts[0], ns = counts[1], nps = counts[2], nss = counts[3];
+  std::vector<unsigned> tmp(np > ns ? np : ns);
+  if (np) {
+    CU_TRY(cudaMemcpyAsync(tmp.data(), A.val_p_sorted, np * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (unsigned i = 0; i < np; ++i) planar_submap_index[i] = tmp[i];                   // :180
+    for (unsigned i = 0; i < nps; ++i) planar_scan_index[i] = tmp[i];                    // :177-178
+  }
+  *n_planar_submap = np; *n_planar_scan = nps;
+  for (unsigned i = 0; i < ns; ++i) sphere_submap_index[i] = i;                          // :187 (rank, not index)
+  for (unsigned i = 0; i < nss; ++i) sphere_scan_index[i] = i;                           // :184-185
+  *n_sphere_submap = ns; *n_sphere_scan = nss;
+  if (sphere_candidates && ns) {
+    CU_TRY(cudaMemcpyAsync(tmp.data(), A.val_s_sorted, ns * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (unsigned i = 0; i < ns; ++i) sphere_candidates[i] = tmp[i];
+  }
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_pca_info(tloam_b200_handle* h, const tloam_feature_config* cfg, const double* xyz, size_t n, double* cvr,
+                        double* flatness, double* sphericity, double* normal, int* num_sum, int* neigh) {
+  if (!h || !cfg || !xyz || n == 0) return TLOAM_B200_ERR_INVALID_ARG;
+  FeArena A;
+  const int rc = fe_run(h, cfg, xyz, n, false, A);
+  if (rc != TLOAM_B200_OK) return rc;
+  if (cvr) CU_TRY(cudaMemcpyAsync(cvr, A.out.cvr, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (flatness) CU_TRY(cudaMemcpyAsync(flatness, A.out.flatness, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (sphericity) CU_TRY(cudaMemcpyAsync(sphericity, A.out.sphericity, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (normal) CU_TRY(cudaMemcpyAsync(normal, A.out.normal, n * 24, cudaMemcpyDeviceToHost, h->stream));
+  if (num_sum) CU_TRY(cudaMemcpyAsync(num_sum, A.out.num_sum, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<int> nb;
+  if (neigh) {
+    nb.resize(n * kFeK);
+    CU_TRY(cudaMemcpyAsync(nb.data(), A.out.neigh, n * kFeK * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if (neigh)
+    for (size_t i = 0; i < n; ++i)
+      for (int j = 0; j < cfg->K; ++j) neigh[i * cfg->K + j] = nb[i * kFeK + j];
+  return TLOAM_B200_OK;
 }
 
 int tloam_b200_voxel_down_sample(tloam_b200_handle* h, const double* pts, size_t n, double voxel, double* out, size_t* n_out) {

@@ -210,6 +210,45 @@ class LocalRegistration:
         self._check(self._L.tloam_b200_voxel_down_sample(self._h, _dp(a), a.shape[0], float(voxel), _dp(out), C.byref(n)), "voxel_down_sample")
         return out[:n.value].copy()
 
+    # ---- "next" row (f)-2: PCA feature extraction (ref: feature_extract.cpp:47-122, 133-197) ----
+    def _feature_config(self, overrides):
+        c = _lib.FeatureConfig()
+        self._L.tloam_b200_feature_default_config(C.byref(c))
+        for k, v in overrides.items():
+            setattr(c, k, v)
+        return c
+
+    def extract_planar_sphere(self, general_cloud, **overrides):
+        """featureExtract::extractPlanarSphere on the device.  Returns (planar_scan_index, planar_submap_index,
+        sphere_scan_index, sphere_submap_index, sphere_candidates); the two sphere lists hold ranks (reference quirk),
+        sphere_candidates the point indices those ranks refer to."""
+        a = _f64(general_cloud).reshape(-1, 3)
+        c = self._feature_config(overrides)
+        n = a.shape[0]
+        bufs = [np.zeros(max(n, 1), dtype=np.uintp) for _ in range(5)]
+        cnt = [C.c_size_t(0) for _ in range(4)]
+        szp = C.POINTER(C.c_size_t)
+        self._check(self._L.tloam_b200_extract_planar_sphere(
+            self._h, C.byref(c), _dp(a), n, bufs[0].ctypes.data_as(szp), C.byref(cnt[0]), bufs[1].ctypes.data_as(szp),
+            C.byref(cnt[1]), bufs[2].ctypes.data_as(szp), C.byref(cnt[2]), bufs[3].ctypes.data_as(szp), C.byref(cnt[3]),
+            bufs[4].ctypes.data_as(szp)), "extract_planar_sphere")
+        return (bufs[0][:cnt[0].value].copy(), bufs[1][:cnt[1].value].copy(), bufs[2][:cnt[2].value].copy(),
+                bufs[3][:cnt[3].value].copy(), bufs[4][:cnt[3].value].copy())
+
+    def pca_info(self, general_cloud, **overrides):
+        """featureExtract::calculatePCAInfo on the device: dict of cvr, flatness, sphericity, normal (n,3), num_sum, neigh (n,K)."""
+        a = _f64(general_cloud).reshape(-1, 3)
+        c = self._feature_config(overrides)
+        n = a.shape[0]
+        out = {"cvr": np.zeros(n), "flatness": np.zeros(n), "sphericity": np.zeros(n), "normal": np.zeros((n, 3)),
+               "num_sum": np.zeros(n, dtype=np.int32), "neigh": np.full((n, c.K), -1, dtype=np.int32)}
+        ip = C.POINTER(C.c_int)
+        self._check(self._L.tloam_b200_pca_info(self._h, C.byref(c), _dp(a), n, _dp(out["cvr"]), _dp(out["flatness"]),
+                                                _dp(out["sphericity"]), _dp(out["normal"]),
+                                                out["num_sum"].ctypes.data_as(ip), out["neigh"].ctypes.data_as(ip)),
+                    "pca_info")
+        return out
+
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):
         n = C.c_size_t(0)

@@ -357,3 +357,43 @@ class Stream:
         self.T = self.T @ se3_exp(self.motion[self.k % len(self.motion)])
         self.k += 1
         return out
+
+
+def general_cloud(n=50_000, seed=20260924 + 4242, noise=0.004):
+    """Synthetic "general" (non-ground, segmented) cloud for the PCA feature extraction, SENSOR frame, about n points:
+    vertical wall patches (planar features), horizontal slabs (flat but not vertical), Gaussian blobs (sphere
+    features), thin poles and isolated clutter (dropped by min_neigh).  Point spacing on the surfaces is 3-6 cm, so
+    that a 0.2 m neighbourhood holds more than K = 20 points near the patch centres and fewer at their borders
+    (ref for the consumer: src/models/feature_extraction/feature_extract.cpp:47-122)."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    parts = []
+
+    def patch(count, origin, eu, ev, su, sv):
+        uv = rng.random((count, 2)) * [su, sv]
+        return origin + uv[:, :1] * eu + uv[:, 1:] * ev
+
+    n_wall, n_slab, n_blob, n_pole = int(0.55 * n), int(0.15 * n), int(0.15 * n), int(0.10 * n)
+    walls = max(4, n_wall // 3000)
+    for w in range(walls):
+        ang = rng.uniform(0, np.pi)
+        eu = np.array([np.cos(ang), np.sin(ang), 0.0])
+        org = np.array([rng.uniform(-40, 40), rng.uniform(-40, 40), rng.uniform(-1.5, 0.0)])
+        parts.append(patch(n_wall // walls, org, eu, np.array([0.0, 0.0, 1.0]), 3.0, 1.8))
+    slabs = max(2, n_slab // 3000)
+    for s in range(slabs):
+        org = np.array([rng.uniform(-40, 40), rng.uniform(-40, 40), rng.uniform(0.5, 2.5)])
+        parts.append(patch(n_slab // slabs, org, np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0]), 2.5, 2.0))
+    blobs = max(8, n_blob // 150)
+    for b in range(blobs):
+        c = np.array([rng.uniform(-40, 40), rng.uniform(-40, 40), rng.uniform(-1.0, 2.0)])
+        parts.append(c + rng.normal(0.0, 0.07, (n_blob // blobs, 3)))
+    poles = max(4, n_pole // 400)
+    for p in range(poles):
+        c = np.array([rng.uniform(-40, 40), rng.uniform(-40, 40), -1.5])
+        th, z = rng.uniform(0, 2 * np.pi, n_pole // poles), rng.uniform(0, 3.0, n_pole // poles)
+        parts.append(c + np.c_[0.05 * np.cos(th), 0.05 * np.sin(th), z])
+    pts = np.vstack(parts)
+    pts = pts + rng.normal(0.0, noise, pts.shape)
+    clutter = np.c_[rng.uniform(-45, 45, (max(n - pts.shape[0], 0), 2)), rng.uniform(-1.5, 3.0, max(n - pts.shape[0], 0))]
+    pts = np.vstack([pts, clutter])
+    return np.ascontiguousarray(pts[rng.permutation(pts.shape[0])])
