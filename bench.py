@@ -405,6 +405,30 @@ def main():
                          "(4 KD-build + 4 factor threads, cores/2 solver threads)",
                "max_pose_diff_vs_gpu_m": worst}
 
+    # ---- (f)-2: PCA feature extraction of a 50k-point general cloud (informational; rank 0, N = 1 only) ----
+    feat = None
+    if rank == 0 and world == 1:
+        fpts = synth.general_cloud(50_000, seed=77)
+        for _ in range(3):
+            fout = reg.extract_planar_sphere(fpts)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            fout = reg.extract_planar_sphere(fpts)
+        f_ms = 1e3 * (time.perf_counter() - t0) / 10
+        feat = {"points": int(fpts.shape[0]), "gpu_ms_per_call": f_ms, "h2d_bytes": int(fpts.nbytes),
+                "lists": [int(len(x)) for x in fout[:4]],
+                "what": "tloam_b200_extract_planar_sphere through the C ABI, host cloud in / host index lists out"}
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle     # checker / CPU baseline leg only
+            pyoracle.build()
+            fref = pyoracle.extract_planar_sphere(fpts)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fref = pyoracle.extract_planar_sphere(fpts)
+            feat["cpu_port_ms_per_call"] = 1e3 * (time.perf_counter() - t0) / 3
+            feat["cpu_cores"] = os.cpu_count()
+            feat["identical_to_cpu_port"] = bool(all(np.array_equal(a, b) for a, b in zip(fout, fref)))
+
     if rank == 0:
         fps = world * args.steps / (ms_dev * 1e-3)
         fps_e2e = world * args.steps / (ms_e2e * 1e-3)
@@ -420,6 +444,8 @@ def main():
             "value": world * args.steps / (ms_sub * 1e-3), "unit": UNIT, "ms_per_step": ms_sub / args.steps,
             "h2d_bytes_per_step": h2d_sub, "err_vs_ground_truth_last_frame_m": err_sub,
             "what": "set_source (pinned host scan) + scan_match + tloam_b200_submap_update per frame; the map never leaves HBM"}
+        if feat:
+            line["feature_extraction"] = feat
         if bcast:
             line["shared_map_broadcast"] = bcast
         if world > 1:

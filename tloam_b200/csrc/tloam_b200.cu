@@ -808,7 +808,7 @@ struct tloam_b200_handle {
   double* d_up = nullptr;                  size_t cap_up = 0;                                   // upload staging
   unsigned char* d_vox = nullptr;          size_t cap_vox = 0;                                  // voxel hash scratch
   // ---- PCA feature extraction ((f)-2): one arena, carved up per call ----
-  unsigned char* d_fe = nullptr;           size_t cap_fe = 0;
+  unsigned char* d_fe = nullptr;           size_t cap_fe = 0;  bool fe_attr_set = false;
   double* d_pose = nullptr;
 };
 
@@ -1617,6 +1617,7 @@ struct FeArena {
   unsigned long long *key_p, *key_s, *key_p_sorted, *key_s_sorted;
   unsigned *val, *val_p_sorted, *val_s_sorted, *counts;
   void* cub_tmp; size_t cub_bytes;
+  unsigned *host_val_p = nullptr, *host_val_s = nullptr;   // optional: the sorted index lists land here (one sync)
 };
 }  // namespace
 
@@ -1685,10 +1686,15 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   g.mask = hd.tsize[0] - 1u; g.n = (unsigned)n; g.cell = cfg->radius; g.inv_cell = 1.0 / cfg->radius;
   g.origin = reinterpret_cast<const double*>(A.blob + offsetof(MapHeader, origin));
   FeParams prm;
+  prm.dbg = h->profiling ? h->d_dbg + 8 : nullptr;     // slots 8..11 (k_correspond uses them in frame profiling)
   prm.r2 = cfg->radius * cfg->radius; prm.K = cfg->K; prm.min_neigh = cfg->min_neigh;
   prm.cvr_submap = cfg->cvr_submap; prm.planar_submap_thres = cfg->planar_submap_thres;
   prm.planar_vertic_thres = cfg->planar_vertic_thres;
-  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_pca<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(g, prm, A.out)));
+  if (!h->fe_attr_set) {
+    CU_TRY(cudaFuncSetAttribute(k_fe_pca, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSmemBytes));
+    h->fe_attr_set = true;
+  }
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_pca<<<(unsigned)((n + kFeBlk - 1) / kFeBlk), kFeBlk, kFeSmemBytes, h->stream>>>(g, prm, A.out)));
   if (select) {
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_classify<<<gb, tb, 0, h->stream>>>((unsigned)n, prm, A.out, A.key_p, A.key_s, A.val, A.counts)));
     // stable descending sorts: candidates first (by flatness, ties in ascending point index), the rest (key 0) last
@@ -1705,6 +1711,8 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   CU_TRY(cudaMemcpyAsync(h->h_result + 28, A.counts, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaMemcpyAsync(h->h_result + 30, A.blob + offsetof(MapHeader, build_flags), sizeof(unsigned long long),
                          cudaMemcpyDeviceToHost, h->stream));
+  if (select && A.host_val_p) CU_TRY(cudaMemcpyAsync(A.host_val_p, A.val_p_sorted, n * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  if (select && A.host_val_s) CU_TRY(cudaMemcpyAsync(A.host_val_s, A.val_s_sorted, n * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   unsigned long long flags;
   memcpy(&flags, h->h_result + 30, sizeof(flags));
@@ -1722,27 +1730,20 @@ int tloam_b200_extract_planar_sphere(tloam_b200_handle* h, const tloam_feature_c
   if (n == 0) return TLOAM_B200_OK;              // calculatePCAInfo fails on an empty cloud: nothing is selected (:49-54, :141)
   if (!xyz) return TLOAM_B200_ERR_INVALID_ARG;
   FeArena A;
+  std::vector<unsigned> vp(n), vs(n);            // sorted point indices (candidates first), fetched with the counts
+  A.host_val_p = vp.data(); A.host_val_s = vs.data();
   const int rc = fe_run(h, cfg, xyz, n, true, A);
   if (rc != TLOAM_B200_OK) return rc;
   unsigned counts[4];
   memcpy(counts, h->h_result + 28, sizeof(counts));
   const unsigned np = counts[0], ns = counts[1], nps = counts[2], nss = counts[3];
-  std::vector<unsigned> tmp(np > ns ? np : ns);
-  if (np) {
-    CU_TRY(cudaMemcpyAsync(tmp.data(), A.val_p_sorted, np * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    for (unsigned i = 0; i < np; ++i) planar_submap_index[i] = tmp[i];                   // :180
-    for (unsigned i = 0; i < nps; ++i) planar_scan_index[i] = tmp[i];                    // :177-178
-  }
+  for (unsigned i = 0; i < np; ++i) planar_submap_index[i] = vp[i];                    // :180
+  for (unsigned i = 0; i < nps; ++i) planar_scan_index[i] = vp[i];                     // :177-178
   *n_planar_submap = np; *n_planar_scan = nps;
   for (unsigned i = 0; i < ns; ++i) sphere_submap_index[i] = i;                          // :187 (rank, not index)
   for (unsigned i = 0; i < nss; ++i) sphere_scan_index[i] = i;                           // :184-185
   *n_sphere_submap = ns; *n_sphere_scan = nss;
-  if (sphere_candidates && ns) {
-    CU_TRY(cudaMemcpyAsync(tmp.data(), A.val_s_sorted, ns * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    for (unsigned i = 0; i < ns; ++i) sphere_candidates[i] = tmp[i];
-  }
+  if (sphere_candidates) for (unsigned i = 0; i < ns; ++i) sphere_candidates[i] = vs[i];
   return TLOAM_B200_OK;
 }
 
