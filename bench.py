@@ -408,6 +408,7 @@ def main():
     # ---- (f)-2: PCA feature extraction of a 50k-point general cloud (informational; rank 0, N = 1 only) ----
     feat = None
     if rank == 0 and world == 1:
+        from tloam_b200 import synth
         fpts = synth.general_cloud(50_000, seed=77)
         for _ in range(3):
             fout = reg.extract_planar_sphere(fpts)
