@@ -1,7 +1,7 @@
 // Minimal stand-ins for the host-side types the C++ shim touches, so that it can be compiled and exercised in
 // an image without Eigen / Open3D / ROS.  Written for this repository's tests; only the members the shim uses
 // exist: Vector3d = 3 contiguous doubles with operator[], Isometry3d::matrix().data() = 16 doubles column-major,
-// PointCloud2::points_, Frame's five shared_ptrs, RegistrationInterface's four virtuals.
+// PointCloud2::points_, Frame's five shared_ptrs, CloudData::cloud_ptr, RegistrationInterface's four virtuals.
 #pragma once
 #include <array>
 #include <memory>
@@ -38,6 +38,11 @@ struct Frame {
             sphere_feature(new open3d::geometry::PointCloud2), planar_feature(new open3d::geometry::PointCloud2),
             ground_feature(new open3d::geometry::PointCloud2) {}
   std::shared_ptr<open3d::geometry::PointCloud2> scan_cloud, edge_feature, sphere_feature, planar_feature, ground_feature;
+};
+struct CloudData {   // ref: include/tloam/models/utils/sensor_data.hpp:17-43 (the members the shims touch)
+  CloudData() : time(0.0), cloud_ptr(new open3d::geometry::PointCloud2) {}
+  double time;
+  std::shared_ptr<open3d::geometry::PointCloud2> cloud_ptr;
 };
 class RegistrationInterface {
  public:

@@ -11,23 +11,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "mock", "_build", "shim_driver")
 
 
-def build_driver():
+def build_driver(name="shim_driver", header="local_registration_b200.hpp"):
     from tloam_b200 import build
     lib = build.build()
-    os.makedirs(os.path.dirname(EXE), exist_ok=True)
-    src = os.path.join(ROOT, "tests", "mock", "shim_driver.cpp")
-    hdr = os.path.join(ROOT, "include", "tloam_b200", "local_registration_b200.hpp")
-    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(p) for p in (src, hdr, lib)):
-        return EXE
+    exe = os.path.join(os.path.dirname(EXE), name)
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "mock", name + ".cpp")
+    hdr = os.path.join(ROOT, "include", "tloam_b200", header)
+    mock = os.path.join(ROOT, "tests", "mock", "mock_tloam.hpp")
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(p) for p in (src, hdr, mock, lib)):
+        return exe
     cmd = ["/usr/bin/g++", "-std=c++14", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "tests", "mock"), src,
-           "-o", EXE, lib, "-Wl,-rpath," + os.path.dirname(lib), "-ldl", "-lpthread", "-lrt"]
+           "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib), "-ldl", "-lpthread", "-lrt"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
-    return EXE
+    return exe
 
 
 def test_shim_compiles_as_cpp14_against_host_types():
     """C++14 like the reference (CMakeLists.txt:4); -Wall -Wextra clean."""
     assert os.path.exists(build_driver())
+    assert os.path.exists(build_driver("feature_driver", "feature_extract_b200.hpp"))
 
 
 def test_shim_fails_loudly_without_gpu():
@@ -70,3 +73,24 @@ def test_shim_matches_python_mirror():
     f_py = reg.get_fitness_score()
     assert np.allclose(vals[16:18], f_py, rtol=1e-12, atol=0)
     reg.close()
+
+
+@pytest.mark.gpu
+def test_feature_shim_matches_oracle(oracle):
+    """featureExtractB200::extractPlanarSphere appends exactly the lists of the CPU restatement."""
+    from tloam_b200 import synth
+    exe = build_driver("feature_driver", "feature_extract_b200.hpp")
+    pts = synth.general_cloud(20000, seed=9)
+    path = os.path.join(os.path.dirname(EXE), "cloud.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("Q", pts.shape[0]))
+        f.write(np.ascontiguousarray(pts, dtype=np.float64).tobytes())
+    res = subprocess.run([exe, path], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    vals = [int(x) for x in res.stdout.split()]
+    ref = oracle.extract_planar_sphere(pts)
+    k = 0
+    for r in ref[:4]:
+        n = vals[k]; lst = vals[k + 1:k + 1 + n]; k += 1 + n
+        assert lst[0] == 987654321 and np.array_equal(np.asarray(lst[1:], dtype=np.uintp), r)
+    assert k == len(vals)

@@ -39,7 +39,9 @@ struct MapHeader {
   unsigned long long bbox_enc[6];  // ordered-uint encodings of min xyz / max xyz (build scratch)
   unsigned cursor[4];              // bump allocators (build scratch)
   unsigned long long build_flags;  // bit 0: a cell holds more than kMaxCellPoints points (map unusable)
-  unsigned long long pad[3];
+  unsigned bbox_ticket;            // blocks of k_map_bbox that have contributed (build scratch)
+  unsigned pad32;
+  unsigned long long pad[2];
 };
 static_assert(sizeof(MapHeader) == 256, "MapHeader must be 256 bytes");
 constexpr unsigned long long kMapMagic = 0x544C4F414D423230ull;  // "TLOAMB20"

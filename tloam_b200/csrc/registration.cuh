@@ -17,6 +17,7 @@
 // Every kernel exits immediately when the state says its work is not needed (solve terminated early,
 // frame converged), so the launch sequence is static and graph-capturable.
 #pragma once
+#include <stddef.h>
 #include <cuda_runtime.h>
 #include <float.h>
 #include <math.h>
@@ -55,8 +56,8 @@ struct FrameState {
   Pose7 evalq;        // pose the next k_eval evaluates at
   // ---- trust-region state (Ceres TrustRegionMinimizer + DoglegStrategy) ----
   int phase, iter, num_invalid, reuse;
-  int frame_done, status, sub_1d, used_gn;
-  int last_cand_valid, outer, sub_valid, model_ok;
+  int sub_1d, used_gn, last_cand_valid, outer;
+  int sub_valid, model_ok, pad0, pad1;
   double radius, mu_lm, x_cost, x_norm, model_cost_change, step_norm, gn_norm;
   double scale[6], H[21], g[6];
   double d2[6], y[6];                        // Gauss-Newton model (see solver.cuh: GnModel)
@@ -68,8 +69,11 @@ struct FrameState {
   double slot_sum[4];
   // ---- outputs ----
   double result[16];
+  int frame_done, status;   // directly after `result`: the host fetches the three with ONE copy
   double curr_pose[16], last_pose[16];
 };
+static_assert(offsetof(FrameState, frame_done) == offsetof(FrameState, result) + 16 * sizeof(double), "result + flags must be contiguous");
+static_assert(sizeof(FrameState) % 8 == 0, "FrameState is copied in 8-byte words");
 
 
 struct DeviceCtx {

@@ -21,8 +21,8 @@ namespace tloam {
 // Map build kernels (voxel hash, once per set_target)
 // =================================================================================================
 struct MapBuildArgs {
-  const double* stage;          // AoS xyz of the 4 clouds, concatenated
-  unsigned stage_off[5];        // point offsets of each cloud in `stage`
+  const double* src[4];         // AoS xyz of each cloud (the staging buffer for host input, the caller's arrays for device input)
+  unsigned stage_off[5];        // global point index of each cloud's first point
   unsigned char* blob;          // MapHeader + pts + tables
   unsigned* slot_of;            // scratch [total]
   unsigned* rank_of;            // scratch [total]
@@ -31,14 +31,20 @@ struct MapBuildArgs {
 __device__ __forceinline__ int cloud_of_point(const MapBuildArgs& a, unsigned i) {
   return (i >= a.stage_off[3]) ? 3 : (i >= a.stage_off[2]) ? 2 : (i >= a.stage_off[1]) ? 1 : 0;
 }
+__device__ __forceinline__ const double* point_of(const MapBuildArgs& a, unsigned i) {
+  const int c = cloud_of_point(a, i);
+  const double* base = c == 0 ? a.src[0] : c == 1 ? a.src[1] : c == 2 ? a.src[2] : a.src[3];
+  return base + 3ull * (i - a.stage_off[c]);
+}
 
 __global__ void k_map_bbox(MapBuildArgs a) {
   const unsigned total = a.stage_off[4];
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const double* pt = point_of(a, i);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const double v = a.stage[3ull * i + d];
+      const double v = pt[d];
       mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v);
     }
   }
@@ -54,29 +60,37 @@ __global__ void k_map_bbox(MapBuildArgs a) {
     for (int d = 0; d < 3; ++d) { s_mn[threadIdx.x >> 5][d] = mn[d]; s_mx[threadIdx.x >> 5][d] = mx[d]; }
   }
   __syncthreads();
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   if (threadIdx.x < 3) {                       // 6 atomics per block (same-address atomics serialise in L2)
     const int d = threadIdx.x;
     double lo = s_mn[0][d], hi = s_mx[0][d];
     for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) { lo = fmin(lo, s_mn[wi][d]); hi = fmax(hi, s_mx[wi][d]); }
-    MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
     atomicMin(&h->bbox_enc[d], enc_ordered(lo));
     atomicMax(&h->bbox_enc[3 + d], enc_ordered(hi));
   }
-}
-
-// origin = integer-rounded centre of the bounding box (exactly representable; |rel| stays small so the
-// FP32 storage keeps ~8e-6 m resolution at 100 m)
-__global__ void k_map_origin(MapBuildArgs a) {
-  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
-  if (threadIdx.x < 3) {
-    const double lo = dec_ordered(h->bbox_enc[threadIdx.x]), hi = dec_ordered(h->bbox_enc[3 + threadIdx.x]);
-    h->origin[threadIdx.x] = (a.stage_off[4] > 0) ? rint(0.5 * (lo + hi)) : 0.0;
+  // the last block to arrive turns the bounding box into the map origin = integer-rounded centre of the box
+  // (exactly representable; |rel| stays small so the FP32 storage keeps ~8e-6 m resolution at 100 m)
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&h->bbox_ticket, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (s_last && threadIdx.x < 3) {
+    __threadfence();
+    const double lo = dec_ordered(atomicMin(&h->bbox_enc[threadIdx.x], ~0ull)), hi = dec_ordered(atomicMax(&h->bbox_enc[3 + threadIdx.x], 0ull));
+    h->origin[threadIdx.x] = rint(0.5 * (lo + hi));
   }
 }
 
+// empty map: origin 0
+__global__ void k_map_origin(MapBuildArgs a) {
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  if (threadIdx.x < 3) h->origin[threadIdx.x] = 0.0;
+}
+
 __device__ __forceinline__ float3 rel_of(const MapBuildArgs& a, const MapHeader* h, unsigned i) {
-  return make_float3((float)(a.stage[3ull * i] - h->origin[0]), (float)(a.stage[3ull * i + 1] - h->origin[1]),
-                     (float)(a.stage[3ull * i + 2] - h->origin[2]));
+  const double* pt = point_of(a, i);
+  return make_float3((float)(pt[0] - h->origin[0]), (float)(pt[1] - h->origin[1]), (float)(pt[2] - h->origin[2]));
 }
 
 // cell of the STORED (FP32-rounded) coordinates, so that the 27-cell search is exact for what is stored
@@ -170,16 +184,16 @@ __global__ void k_map_scatter(MapBuildArgs a) {
 }
 
 // AoS FP64 staging -> padded SoA feature arrays
-__global__ void k_stage_source(const double* stage, DeviceCtx ctx, double* px, double* py, double* pz, unsigned soff0,
-                               unsigned soff1, unsigned soff2, unsigned soff3) {
+__global__ void k_stage_source(const double* s0, const double* s1, const double* s2, const double* s3, DeviceCtx ctx,
+                               double* px, double* py, double* pz) {
   const int b = blockIdx.x;
   const int c = cloud_of_block(ctx, b);
   const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
   const int gi = ctx.pad_off[c] + il;
-  const unsigned soff = (c == 0) ? soff0 : (c == 1) ? soff1 : (c == 2) ? soff2 : soff3;
+  const double* src = (c == 0) ? s0 : (c == 1) ? s1 : (c == 2) ? s2 : s3;
   double x = 0, y = 0, z = 0;
   if (il < ctx.n[c]) {
-    const double* p = stage + 3ull * (soff + il);
+    const double* p = src + 3ull * il;
     x = p[0]; y = p[1]; z = p[2];
   }
   px[gi] = x; py[gi] = y; pz[gi] = z;
@@ -973,7 +987,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   }
   if (pad == 0) pad = kBlk;
   blocks = (int)(pad / kBlk);
-  if (total > h->cap_stage_src) {
+  if (!on_device && total > h->cap_stage_src) {
     cudaFree(h->d_stage_src);
     h->cap_stage_src = total + total / 4 + 1024;
     CU_TRY(cudaMalloc(&h->d_stage_src, h->cap_stage_src * 3 * sizeof(double)));
@@ -994,13 +1008,13 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   DeviceCtx& c = h->ctx;
   fill_ctx_config(h);
   size_t off = 0, poff = 0;
-  unsigned soff[4];
+  const double* src[4];
   c.blk_off[0] = 0;
   for (int k = 0; k < 4; ++k) {
-    soff[k] = (unsigned)off;
-    if (n[k] > 0)
-      CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    // host input is staged; device input is read in place by k_stage_source (stream-ordered, no extra copy)
+    src[k] = on_device ? xyz[k] : h->d_stage_src + 3 * off;
+    if (n[k] > 0 && !on_device)
+      CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     c.n[k] = (int)n[k];
     c.pad_off[k] = (int)poff;
     off += n[k];
@@ -1016,7 +1030,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   c.blk_count = h->d_blk_count; c.blk_cap = (int)h->cap_blocks; c.partial = h->d_partial;
   h->total_blocks = c.blk_off[4];
   if (h->total_blocks > 0) {
-    TL_LAUNCH(TLOAM_B200_K_STAGE_SOURCE, (k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(h->d_stage_src, c, f, f + cp, f + 2 * cp, soff[0], soff[1], soff[2], soff[3])));
+    TL_LAUNCH(TLOAM_B200_K_STAGE_SOURCE, (k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(src[0], src[1], src[2], src[3], c, f, f + cp, f + 2 * cp)));
     CU_TRY(cudaGetLastError());
   }
   h->have_src = true;
@@ -1094,22 +1108,27 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     if (n[c] > (size_t)1 << 30) return TLOAM_B200_ERR_INVALID_ARG;
     total += n[c];
   }
-  if (total > h->cap_stage_tgt) {
-    cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch);
+  if (total > h->cap_scratch) {
+    cudaFree(h->d_scratch);
+    h->cap_scratch = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_scratch, h->cap_scratch * 2 * sizeof(unsigned)));
+  }
+  if (!on_device && total > h->cap_stage_tgt) {
+    cudaFree(h->d_stage_tgt);
     h->cap_stage_tgt = total + total / 4 + 1024;
     CU_TRY(cudaMalloc(&h->d_stage_tgt, h->cap_stage_tgt * 3 * sizeof(double)));
-    CU_TRY(cudaMalloc(&h->d_scratch, h->cap_stage_tgt * 2 * sizeof(unsigned)));
   }
   int rc = layout_map(h, n);
   if (rc != TLOAM_B200_OK) return rc;
   MapBuildArgs a;
-  a.stage = h->d_stage_tgt; a.blob = h->d_blob; a.slot_of = h->d_scratch; a.rank_of = h->d_scratch + h->cap_stage_tgt;
+  a.blob = h->d_blob; a.slot_of = h->d_scratch; a.rank_of = h->d_scratch + h->cap_scratch;
   size_t off = 0;
   for (int c = 0; c < 4; ++c) {
     a.stage_off[c] = (unsigned)off;
-    if (n[c] > 0)
-      CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * off, xyz[c], n[c] * 3 * sizeof(double),
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    // host input is staged; device input is read in place by the build kernels (stream-ordered, no extra copy)
+    a.src[c] = on_device ? xyz[c] : h->d_stage_tgt + 3 * off;
+    if (n[c] > 0 && !on_device)
+      CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * off, xyz[c], n[c] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     off += n[c];
     h->n_tgt[c] = n[c];
   }
@@ -1123,8 +1142,7 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     const unsigned gb = (unsigned)((total + tb - 1) / tb);
     unsigned tslots = 0;
     for (int c = 0; c < 4; ++c) tslots += h->hdr.tsize[c];
-    TL_LAUNCH(TLOAM_B200_K_MAP_BBOX, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));
-    TL_LAUNCH(TLOAM_B200_K_MAP_ORIGIN, (k_map_origin<<<1, 32, 0, h->stream>>>(a)));
+    TL_LAUNCH(TLOAM_B200_K_MAP_BBOX, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));   // + origin
     TL_LAUNCH(TLOAM_B200_K_MAP_INSERT, (k_map_insert<<<gb, tb, 0, h->stream>>>(a)));
     TL_LAUNCH(TLOAM_B200_K_MAP_OFFSETS, (k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(a)));
     TL_LAUNCH(TLOAM_B200_K_MAP_SCATTER, (k_map_scatter<<<gb, tb, 0, h->stream>>>(a)));
@@ -1221,9 +1239,8 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
       TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
   }
-  CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double),
-                         cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(cudaMemcpyAsync(h->h_result + 16, (const char*)h->d_state + offsetof(FrameState, frame_done), 2 * sizeof(int),
+  // result[16] + {frame_done, status}: contiguous in FrameState
+  CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double) + 2 * sizeof(int),
                          cudaMemcpyDeviceToHost, h->stream));
   return TLOAM_B200_OK;
 }
@@ -1667,7 +1684,8 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   CU_TRY(cudaMemsetAsync(A.blob + hd.table_off[0], 0, boff - hd.table_off[0], h->stream));
   CU_TRY(cudaMemsetAsync(A.counts, 0, 256, h->stream));
   MapBuildArgs ma;
-  ma.stage = A.stage; ma.blob = A.blob; ma.slot_of = A.scratch; ma.rank_of = A.scratch + n;
+  ma.blob = A.blob; ma.slot_of = A.scratch; ma.rank_of = A.scratch + n;
+  for (int c = 0; c < 4; ++c) ma.src[c] = A.stage;
   ma.stage_off[0] = 0;
   for (int c = 1; c <= 4; ++c) ma.stage_off[c] = (unsigned)n;
   FeBuildArgs fa;
@@ -1675,8 +1693,7 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb);
   unsigned tslots = 0;
   for (int c = 0; c < 4; ++c) tslots += hd.tsize[c];
-  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(ma)));
-  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_origin<<<1, 32, 0, h->stream>>>(ma)));
+  TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(ma)));   // + origin
   TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_insert<<<gb, tb, 0, h->stream>>>(fa)));
   TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(ma)));
   TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_scatter<<<gb, tb, 0, h->stream>>>(fa)));
