@@ -111,7 +111,9 @@ int tloam_b200_destroy(tloam_b200_handle* h);
 /* HOST buffers (pageable or pinned). set_target also builds the voxel-hash grids on the device. */
 int tloam_b200_set_source(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]);
 int tloam_b200_set_target(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4]);
-/* DEVICE buffers (inputs already resident in HBM), same layout. Enqueued on the handle's stream. */
+/* DEVICE buffers (inputs already resident in HBM), same layout.  Returns without waiting: the buffers are read IN
+ * PLACE (no staging copy) by kernels enqueued on the handle's stream, so they must stay unchanged until that work
+ * has run (tloam_b200_synchronize, or the get_result of the frame that follows). */
 int tloam_b200_set_source_device(tloam_b200_handle* h, const double* const d_xyz[4], const size_t n[4]);
 int tloam_b200_set_target_device(tloam_b200_handle* h, const double* const d_xyz[4], const size_t n[4]);
 

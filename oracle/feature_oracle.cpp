@@ -19,6 +19,8 @@
 #include <numeric>
 #include <vector>
 
+#include <omp.h>
+
 #include "tloam_oracle.h"
 
 namespace {
@@ -82,7 +84,7 @@ int oracle_pca_info(const double* pts, size_t n, const oracle_feature_config* c,
   std::vector<int> idx(n * K), cnt(n);
   std::vector<double> d2(n * K);
   oracle_knn(pts, n, pts, n, c->radius, K, idx.data(), d2.data(), cnt.data(), 0);   // SearchHybrid(cur_pt, r, K), :67
-#pragma omp parallel for schedule(dynamic, 256)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(std::min(omp_get_max_threads(), 32))
   for (long long i = 0; i < (long long)n; ++i) {
     cvr[i] = flatness[i] = sphericity[i] = 0.0;
     normal[3 * i] = normal[3 * i + 1] = normal[3 * i + 2] = 0.0;
