@@ -1,4 +1,4 @@
-# usage: bash tools/scratch/profile.sh v5   (inside gpurun) -- refreshes every artefact kept under profiles/
+# usage: bash tools/profile.sh v5   (inside gpurun) -- refreshes every artefact kept under profiles/
 V=$1
 export PYTHONUNBUFFERED=1
 TLOAM_B200_NO_GRAPH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1$V.csv python tools/profile_frame.py 3 > gpurun_out/ncu_a.log 2>&1
