@@ -26,8 +26,9 @@ def quantize_map(clouds, origin):
 
 
 def bbox_origin(clouds):
-    allp = np.concatenate(clouds, axis=0)
-    return np.rint(0.5 * (allp.min(0) + allp.max(0)))
+    """The map origin rule: integer-rounded centre of the bounding box of the first non-empty cloud."""
+    first = next(np.asarray(c).reshape(-1, 3) for c in clouds if len(c))
+    return np.rint(0.5 * (first.min(0) + first.max(0)))
 
 
 def rot_angle(R):

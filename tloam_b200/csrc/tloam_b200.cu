@@ -26,6 +26,8 @@ struct MapBuildArgs {
   unsigned char* blob;          // MapHeader + pts + tables
   unsigned* slot_of;            // scratch [total]
   unsigned* rank_of;            // scratch [total]
+  unsigned i_beg, i_end;        // global point range this launch works on (one cloud in the pipelined host path)
+  int only_cloud;               // k_map_offsets: table of this cloud only (-1 = all four)
 };
 
 __device__ __forceinline__ int cloud_of_point(const MapBuildArgs& a, unsigned i) {
@@ -37,10 +39,11 @@ __device__ __forceinline__ const double* point_of(const MapBuildArgs& a, unsigne
   return base + 3ull * (i - a.stage_off[c]);
 }
 
+// bounding box of the points [i_beg, i_end) -- the first non-empty cloud: the origin must be known before any
+// point can be inserted, and the host path inserts cloud c while cloud c+1 is still crossing PCIe
 __global__ void k_map_bbox(MapBuildArgs a) {
-  const unsigned total = a.stage_off[4];
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  for (unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x; i < a.i_end; i += gridDim.x * blockDim.x) {
     const double* pt = point_of(a, i);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -100,8 +103,8 @@ __device__ __forceinline__ void cell_of_rel(const float3 r, double inv, int& cx,
 
 // claims the point's brick (CAS on the key) and takes a rank inside its sub-cell (packed u16 counters)
 __global__ void k_map_insert(MapBuildArgs a) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.stage_off[4]) return;
+  const unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.i_end) return;
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   const int c = cloud_of_point(a, i);
   const float3 r = rel_of(a, h, i);
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0;
-  while (c < 3 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
+  if (a.only_cloud >= 0) c = a.only_cloud;
+  else while (c < 3 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
   uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
   unsigned cnt = 0u;
   if (s < h->tsize[c]) {
@@ -162,8 +166,8 @@ __global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
 }
 
 __global__ void k_map_scatter(MapBuildArgs a) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.stage_off[4]) return;
+  const unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.i_end) return;
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   if (h->build_flags & 1ull) return;               // counters wrapped: destinations are meaningless
   const int c = cloud_of_point(a, i);
@@ -772,6 +776,8 @@ struct tloam_b200_handle {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;              // H2D of the map clouds, overlapped with the build (set_target)
+  cudaEvent_t ev_copy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   char last_error[512] = {0};
   long long launches = 0;
   int launches_frame = 0;
@@ -916,6 +922,9 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
     h->own_stream = true;
   }
   if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  for (int i = 0; i < 5; ++i)
+    if (cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_state, sizeof(FrameState)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_counter, 256) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
@@ -956,6 +965,8 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 5; ++i) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return TLOAM_B200_OK;
@@ -1122,13 +1133,14 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
   if (rc != TLOAM_B200_OK) return rc;
   MapBuildArgs a;
   a.blob = h->d_blob; a.slot_of = h->d_scratch; a.rank_of = h->d_scratch + h->cap_scratch;
+  a.only_cloud = -1;
   size_t off = 0;
+  int first = -1;                                  // first non-empty cloud: its bounding box defines the origin
   for (int c = 0; c < 4; ++c) {
     a.stage_off[c] = (unsigned)off;
     // host input is staged; device input is read in place by the build kernels (stream-ordered, no extra copy)
     a.src[c] = on_device ? xyz[c] : h->d_stage_tgt + 3 * off;
-    if (n[c] > 0 && !on_device)
-      CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * off, xyz[c], n[c] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (first < 0 && n[c] > 0) first = c;
     off += n[c];
     h->n_tgt[c] = n[c];
   }
@@ -1137,18 +1149,52 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
   CU_TRY(cudaMemcpyAsync(h->d_blob, &h->hdr, sizeof(MapHeader), cudaMemcpyHostToDevice, h->stream));
   const size_t tables_bytes = h->blob_bytes - h->hdr.table_off[0];
   CU_TRY(cudaMemsetAsync(h->d_blob + h->hdr.table_off[0], 0, tables_bytes, h->stream));
-  if (total > 0) {
-    const unsigned tb = 256;
-    const unsigned gb = (unsigned)((total + tb - 1) / tb);
+  const unsigned tb = 256;
+  auto blocks_for = [&](size_t cnt) { return (unsigned)((cnt + tb - 1) / tb); };
+  if (total == 0) {
+    TL_LAUNCH(TLOAM_B200_K_MAP_ORIGIN, (k_map_origin<<<1, 32, 0, h->stream>>>(a)));
+  } else if (on_device) {
+    // inputs already in HBM: one pass over all clouds per kernel
+    MapBuildArgs ab = a;
+    ab.i_beg = a.stage_off[first]; ab.i_end = a.stage_off[first + 1];
+    const unsigned gbb = blocks_for(n[first]);
+    TL_LAUNCH(TLOAM_B200_K_MAP_BBOX, (k_map_bbox<<<(gbb < 592u ? gbb : 592u), tb, 0, h->stream>>>(ab)));   // + origin
+    a.i_beg = 0; a.i_end = (unsigned)total;
+    const unsigned gb = blocks_for(total);
     unsigned tslots = 0;
     for (int c = 0; c < 4; ++c) tslots += h->hdr.tsize[c];
-    TL_LAUNCH(TLOAM_B200_K_MAP_BBOX, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));   // + origin
     TL_LAUNCH(TLOAM_B200_K_MAP_INSERT, (k_map_insert<<<gb, tb, 0, h->stream>>>(a)));
     TL_LAUNCH(TLOAM_B200_K_MAP_OFFSETS, (k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(a)));
     TL_LAUNCH(TLOAM_B200_K_MAP_SCATTER, (k_map_scatter<<<gb, tb, 0, h->stream>>>(a)));
     CU_TRY(cudaGetLastError());
   } else {
-    TL_LAUNCH(TLOAM_B200_K_MAP_ORIGIN, (k_map_origin<<<1, 32, 0, h->stream>>>(a)));
+    // host inputs: the clouds cross PCIe one after the other on a copy stream; cloud c is inserted, offset and
+    // scattered on the compute stream while cloud c+1 is still in flight.  The origin cloud goes first, then the
+    // others by descending size, so that the build left exposed after the last copy is the smallest one.
+    int order[4], m = 0;
+    order[m++] = first;
+    for (int c = 0; c < 4; ++c) if (c != first && n[c] > 0) order[m++] = c;
+    for (int i = 2; i < m; ++i)
+      for (int j = i; j > 1 && n[order[j]] > n[order[j - 1]]; --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    CU_TRY(cudaEventRecord(h->ev_copy[0], h->stream));                  // the staging buffer is free once earlier work is done
+    CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_copy[0], 0));
+    for (int k = 0; k < m; ++k) {
+      const int c = order[k];
+      CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * (size_t)a.stage_off[c], xyz[c], n[c] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      CU_TRY(cudaEventRecord(h->ev_copy[1 + c], h->copy_stream));
+    }
+    for (int k = 0; k < m; ++k) {
+      const int c = order[k];
+      CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[1 + c], 0));
+      MapBuildArgs ac = a;
+      ac.i_beg = a.stage_off[c]; ac.i_end = a.stage_off[c + 1]; ac.only_cloud = c;
+      const unsigned gb = blocks_for(n[c]);
+      if (k == 0) TL_LAUNCH(TLOAM_B200_K_MAP_BBOX, (k_map_bbox<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(ac)));   // + origin
+      TL_LAUNCH(TLOAM_B200_K_MAP_INSERT, (k_map_insert<<<gb, tb, 0, h->stream>>>(ac)));
+      TL_LAUNCH(TLOAM_B200_K_MAP_OFFSETS, (k_map_offsets<<<(h->hdr.tsize[c] + tb - 1) / tb, tb, 0, h->stream>>>(ac)));
+      TL_LAUNCH(TLOAM_B200_K_MAP_SCATTER, (k_map_scatter<<<gb, tb, 0, h->stream>>>(ac)));
+    }
+    CU_TRY(cudaGetLastError());
   }
   bind_map(h);
   h->origin_known = false;
@@ -1685,6 +1731,7 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   CU_TRY(cudaMemsetAsync(A.counts, 0, 256, h->stream));
   MapBuildArgs ma;
   ma.blob = A.blob; ma.slot_of = A.scratch; ma.rank_of = A.scratch + n;
+  ma.i_beg = 0; ma.i_end = (unsigned)n; ma.only_cloud = -1;
   for (int c = 0; c < 4; ++c) ma.src[c] = A.stage;
   ma.stage_off[0] = 0;
   for (int c = 1; c <= 4; ++c) ma.stage_off[c] = (unsigned)n;
