@@ -649,7 +649,7 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
 // Clusters of 8 blocks: the block totals are combined through distributed shared memory before they reach
 // global memory, so the serial tail sums 1/8 of the rows (40 instead of 315 at F = 40k).
 template <bool kFirst>
-__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk) k_eval(const __grid_constant__ DeviceCtx ctx) {
+__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk, 3) k_eval(const __grid_constant__ DeviceCtx ctx) {
   pdl_prologue();
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;     // grid-uniform
