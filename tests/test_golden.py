@@ -75,3 +75,33 @@ def test_gpu_reproduces_golden(gold):
     r, J, c = reg.eval_point_to_plane(g["f_x"], g["f_p"], g["f_n"], g["f_d"], g["f_w"])
     assert np.allclose(r, g["pn_r"], atol=1e-12) and np.allclose(J, g["pn_J"], atol=1e-12) and np.allclose(c, g["pn_c"], rtol=1e-12)
     reg.close()
+
+
+# ---- (f)-2: PCA feature extraction (tests/golden/feature_small.npz, made by tools/make_golden.py) ----
+FE_LISTS = ("planar_scan", "planar_submap", "sphere_scan", "sphere_submap", "sphere_candidates")
+
+
+@pytest.fixture(scope="module")
+def fgold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "feature_small.npz"))
+
+
+def check_feature(fgold, info, lists):
+    for k in ("cvr", "flatness", "sphericity", "normal", "num_sum"):
+        assert np.array_equal(info[k], fgold[k], equal_nan=True), k
+    assert np.array_equal(info["neigh"], fgold["neigh"].astype(np.int32))
+    for name, lst in zip(FE_LISTS, lists):
+        assert np.array_equal(np.asarray(lst, dtype=np.int64), fgold[name].astype(np.int64)), name
+    assert len(fgold["planar_submap"]) > 100 and len(fgold["sphere_submap"]) > 3
+
+
+def test_oracle_reproduces_feature_golden(oracle, fgold):
+    check_feature(fgold, oracle.pca_info(fgold["points"]), oracle.extract_planar_sphere(fgold["points"]))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_feature_golden(fgold):
+    import tloam_b200
+    reg = tloam_b200.LocalRegistration()
+    check_feature(fgold, reg.pca_info(fgold["points"]), reg.extract_planar_sphere(fgold["points"]))
+    reg.close()

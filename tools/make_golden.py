@@ -22,7 +22,7 @@ def main():
     T_gt = synth.se3_exp([12.0, -7.0, 0.03, 0.004, -0.006, 0.9])
     predict = T_gt @ synth.se3_exp([0.05, -0.03, 0.01, 0.004, -0.003, 0.006])
     mp = synth.make_map(cfg, T_gt)
-    origin = np.rint(0.5 * (np.concatenate(mp).min(0) + np.concatenate(mp).max(0)))
+    origin = np.rint(0.5 * (mp[0].min(0) + mp[0].max(0)))     # the library's rule: bounding box of the first cloud
     mp = [origin + (c - origin).astype(np.float32).astype(np.float64) for c in mp]   # float-representable map
     scan = synth.make_scan(cfg, T_gt, 0)
     out = {"T_gt": T_gt, "predict": predict, "origin": origin}
@@ -71,6 +71,22 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "tls_small.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes; factors per outer:", out["n_factors"].tolist())
+    feature_golden()
+
+
+def feature_golden():
+    """tests/golden/feature_small.npz: a 3000-point general cloud + what oracle/feature_oracle.cpp computes for it
+    ((f)-2, featureExtract::calculatePCAInfo / extractPlanarSphere)."""
+    pts = synth.general_cloud(3000, seed=20260924)
+    info = pyoracle.pca_info(pts)
+    lists = pyoracle.extract_planar_sphere(pts)
+    out = {"points": pts, "cvr": info["cvr"], "flatness": info["flatness"], "sphericity": info["sphericity"],
+           "normal": info["normal"], "num_sum": info["num_sum"], "neigh": info["neigh"].astype(np.int16)}
+    for name, lst in zip(("planar_scan", "planar_submap", "sphere_scan", "sphere_submap", "sphere_candidates"), lists):
+        out[name] = lst.astype(np.int32)
+    path = os.path.join(ROOT, "tests", "golden", "feature_small.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; lists:", [len(x) for x in lists])
 
 
 if __name__ == "__main__":
