@@ -122,6 +122,13 @@ int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double
 /* Split form: enqueue only / wait + fetch. Lets one host thread drive several handles (one per GPU). */
 int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]);
 int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_stats* stats);
+/* "Next" row (f)-3: constant-velocity prediction on the device (ref: src/front_end/front_end.cpp:329-330:
+ * step = last^-1 * pose; predict = pose * step).  The frame is enqueued with NO host input: the prediction is computed
+ * by the frame's first kernel from the two last results, which live in device memory (the pose returned by frame k
+ * and the one returned by frame k-1; identity before the first frame).  set_pose_history seeds / overrides them. */
+int tloam_b200_scan_match_predicted_async(tloam_b200_handle* h);
+int tloam_b200_scan_match_predicted(tloam_b200_handle* h, double result[16], tloam_b200_stats* stats);
+int tloam_b200_set_pose_history(tloam_b200_handle* h, const double last_pose[16], const double curr_pose[16]);
 /* The per-iteration trace in tloam_b200_stats costs device time; scan_match records it iff stats != NULL, the
  * async form iff it was switched on here (default off; without it get_result fills only gpu_launches / gpu_ms). */
 int tloam_b200_set_trace(tloam_b200_handle* h, int on);

@@ -84,6 +84,16 @@ class LocalRegistrationB200 : public RegistrationInterface {
     return true;
   }
 
+  // (f)-3: scanMatching with the front end's constant-velocity prediction (ref: front_end.cpp:329-330) computed on
+  // the device from the two last results; `FrontEnd::updateLidarOdometry` then needs no predicate_pose at all.
+  bool scanMatchingPredicted(Eigen::Isometry3d& result_pose_) {
+    double result[16];
+    const int rc = tloam_b200_scan_match_predicted(h_, result, nullptr);
+    if (rc != TLOAM_B200_OK) return report(rc, "scanMatchingPredicted");
+    for (int i = 0; i < 16; ++i) result_pose_.matrix().data()[i] = result[i];
+    return true;
+  }
+
   std::pair<double, double> getFitnessScore() override {   // ref: registration.cpp:257-296
     double f = 0.0, e = 0.0;
     report(tloam_b200_fitness(h_, &f, &e), "getFitnessScore");

@@ -97,3 +97,32 @@ def test_default_caps_at_full_size(full, oracle):
     dt, dr = pose_err(T, To)
     assert dt < 1e-4 and dr < 1e-5, (dt, dr)
     assert [list(st.outer[i].n_factors) for i in range(st.n_outer)] == [list(so.outer[i].n_factors) for i in range(so.n_outer)]
+
+
+@pytest.mark.gpu
+def test_device_side_constant_velocity_prediction():
+    """(f)-3: tloam_b200_scan_match_predicted == scan_match with predict = T_k (T_{k-1}^-1 T_k) computed on the host
+    (ref: src/front_end/front_end.cpp:329-330); the two last results live in device memory."""
+    import tloam_b200
+    from tloam_b200 import synth
+    st = synth.Stream(cfg=synth.scaled(0.03, seed=17), seq="00", start=200)
+    frames = [st.frame() for _ in range(5)]
+    a, b = tloam_b200.LocalRegistration(), tloam_b200.LocalRegistration()
+    T0 = frames[0]["T_gt"]
+    # frame 0 seeds the history on both handles: last = curr = its result would make a zero step, so seed explicitly
+    prev = T0 @ np.linalg.inv(synth.se3_exp(st.motion[(200 - 1) % len(st.motion)]))
+    a.set_pose_history(prev, T0)
+    last, cur = prev, T0
+    for fr in frames[1:]:
+        predict = cur @ (np.linalg.inv(last) @ cur)
+        for r in (a, b):
+            r.set_input_target(fr["map"])
+            r.set_input_source(fr["scan"])
+        Ta = a.scan_matching_predicted()
+        Tb = b.scan_matching(predict)
+        assert np.allclose(Ta, Tb, atol=1e-9), np.abs(Ta - Tb).max()
+        assert np.linalg.norm(Ta[:3, 3] - fr["T_gt"][:3, 3]) < 0.05
+        b.set_pose_history(cur, Tb)            # keep b's history irrelevant but valid
+        last, cur = cur, Tb                    # the reference chains on its own results
+        # handle `a` chains on the device: its state already holds (last, cur) = (previous result, this result)
+    a.close(); b.close()

@@ -91,6 +91,7 @@ EXPORTS = [
     "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
     "tloam_b200_get_profile", "tloam_b200_set_trace", "tloam_b200_submap_default_config", "tloam_b200_submap_init",
     "tloam_b200_submap_update", "tloam_b200_submap_sizes", "tloam_b200_submap_download", "tloam_b200_voxel_down_sample",
+    "tloam_b200_scan_match_predicted_async", "tloam_b200_scan_match_predicted", "tloam_b200_set_pose_history",
     "tloam_b200_feature_default_config", "tloam_b200_extract_planar_sphere", "tloam_b200_pca_info",
 ]
 
@@ -126,6 +127,9 @@ def load():
     L.tloam_b200_scan_match.argtypes = [vp, dp, dp, C.POINTER(Stats)]
     L.tloam_b200_scan_match_async.argtypes = [vp, dp]
     L.tloam_b200_get_result.argtypes = [vp, dp, C.POINTER(Stats)]
+    L.tloam_b200_scan_match_predicted_async.argtypes = [vp]
+    L.tloam_b200_scan_match_predicted.argtypes = [vp, dp, C.POINTER(Stats)]
+    L.tloam_b200_set_pose_history.argtypes = [vp, dp, dp]
     L.tloam_b200_fitness.argtypes = [vp, dp, dp]
     L.tloam_b200_get_transform.argtypes = [vp, dp]
     L.tloam_b200_get_pose_increment.argtypes = [vp, dp]

@@ -206,7 +206,7 @@ __global__ void k_stage_source(const double* s0, const double* s1, const double*
 // =================================================================================================
 // Frame kernels
 // =================================================================================================
-struct Predict { double m[16]; };
+struct Predict { double m[16]; double from_state; };   // from_state != 0: constant-velocity prediction on the device
 
 // Programmatic dependent launch (opt-in, TLOAM_B200_PDL=1): a frame kernel waits for its predecessor before it
 // touches anything the predecessor may have written; the block that runs the serial tail of a k_eval (partial sum
@@ -230,8 +230,32 @@ __device__ __forceinline__ void dsmem_store(double* local_smem, unsigned rank, d
 }
 
 // scanMatching prologue, ref: registration.cpp:879-886, 961-964, 1027-1033.
+// 4x4 column-major helpers for the constant-velocity prediction (ref: src/front_end/front_end.cpp:329-330)
+__device__ __forceinline__ void mat4_mul(const double* A, const double* B, double* C) {
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) {
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) s += A[k * 4 + r] * B[c * 4 + k];
+      C[c * 4 + r] = s;
+    }
+}
+__device__ __forceinline__ void isometry_inverse(const double* T, double* out) {   // Eigen::Isometry3d::inverse(): R^T, -R^T t
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) out[c * 4 + r] = T[r * 4 + c];
+  for (int r = 0; r < 3; ++r) out[12 + r] = -(out[r] * T[12] + out[4 + r] * T[13] + out[8 + r] * T[14]);
+  out[3] = out[7] = out[11] = 0.0; out[15] = 1.0;
+}
+
 __global__ void k_begin_frame(DeviceCtx ctx, const Predict* prp) {
-  const Predict pr = *prp;
+  Predict pr = *prp;
+  if (pr.from_state != 0.0) {
+    // step = last^-1 * curr ; predict = curr * step, from the two last results kept in the frame state
+    // (every thread computes the same 16 values: the state is rewritten further down by thread 0 only)
+    double inv[16], step[16];
+    isometry_inverse(ctx.st->last_pose, inv);
+    mat4_mul(inv, ctx.st->curr_pose, step);
+    mat4_mul(ctx.st->curr_pose, step, pr.m);
+  }
   // zero the trace
   {
     unsigned* w = reinterpret_cast<unsigned*>(ctx.stats);
@@ -1291,12 +1315,40 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
   return TLOAM_B200_OK;
 }
 
+static int scan_match_enqueue(tloam_b200_handle* h, const double* predict);
+
 int tloam_b200_scan_match_async(tloam_b200_handle* h, const double predict[16]) {
   if (!h || !predict) return TLOAM_B200_ERR_INVALID_ARG;
+  return scan_match_enqueue(h, predict);
+}
+
+// (f)-3: the frame is predicted on the device from the two last results (no host input at all)
+int tloam_b200_scan_match_predicted_async(tloam_b200_handle* h) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  return scan_match_enqueue(h, nullptr);
+}
+
+int tloam_b200_scan_match_predicted(tloam_b200_handle* h, double result[16], tloam_b200_stats* stats) {
+  const int rc = tloam_b200_scan_match_predicted_async(h);
+  if (rc != TLOAM_B200_OK) return rc;
+  return tloam_b200_get_result(h, result, stats);
+}
+
+int tloam_b200_set_pose_history(tloam_b200_handle* h, const double last_pose[16], const double curr_pose[16]) {
+  if (!h || !last_pose || !curr_pose) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  CU_TRY(cudaMemcpy((char*)h->d_state + offsetof(FrameState, last_pose), last_pose, 16 * sizeof(double), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy((char*)h->d_state + offsetof(FrameState, curr_pose), curr_pose, 16 * sizeof(double), cudaMemcpyHostToDevice));
+  return TLOAM_B200_OK;
+}
+
+static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   const int rc = check_ready(h);
   if (rc != TLOAM_B200_OK) return rc;
   CU_TRY(cudaSetDevice(h->device));
-  memcpy(h->h_predict->m, predict, sizeof(Predict));
+  if (predict) { memcpy(h->h_predict->m, predict, 16 * sizeof(double)); h->h_predict->from_state = 0.0; }
+  else h->h_predict->from_state = 1.0;
   DeviceCtx c = h->ctx;
   if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
   const int per_frame = 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);

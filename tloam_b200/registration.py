@@ -136,6 +136,21 @@ class LocalRegistration:
         T = out.reshape(4, 4).T.copy()
         return (T, st) if want_stats else T
 
+    def scan_matching_predicted(self, want_stats=False):
+        """(f)-3: scanMatching with the constant-velocity prediction of FrontEnd::updateLidarOdometry
+        (ref: front_end.cpp:329-330) computed on the device from the two last results."""
+        out = np.zeros(16)
+        st = _lib.Stats() if want_stats else None
+        rc = self._L.tloam_b200_scan_match_predicted(self._h, _dp(out), C.byref(st) if st is not None else None)
+        self._check(rc, "scan_matching_predicted")
+        T = out.reshape(4, 4).T.copy()
+        return (T, st) if want_stats else T
+
+    def set_pose_history(self, last_pose, curr_pose):
+        a = _f64(np.asarray(last_pose).T).reshape(16)
+        b = _f64(np.asarray(curr_pose).T).reshape(16)
+        self._check(self._L.tloam_b200_set_pose_history(self._h, _dp(a), _dp(b)), "set_pose_history")
+
     def scan_matching_async(self, predict_pose):
         p = _f64(np.asarray(predict_pose).T).reshape(16)
         self._check(self._L.tloam_b200_scan_match_async(self._h, _dp(p)), "scan_matching_async")
