@@ -1356,7 +1356,6 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
     if (!h->gvalid || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0) {
-      if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
       h->gvalid = false;
       cudaGraph_t graph = nullptr;
       CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1370,7 +1369,15 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
         snprintf(h->last_error, sizeof(h->last_error), "graph capture failed: %s", cudaGetErrorString(ce));
         return TLOAM_B200_ERR_CUDA;
       }
-      ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+      // same topology, new kernel parameters / grid sizes (cloud sizes change from frame to frame in a real
+      // stream): update the instantiated graph in place, which is much cheaper than instantiating a new one
+      bool updated = false;
+      if (h->gexec) {
+        cudaGraphExecUpdateResultInfo info;
+        updated = cudaGraphExecUpdate(h->gexec, graph, &info) == cudaSuccess;
+        if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+      }
+      if (!updated) ce = cudaGraphInstantiate(&h->gexec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
       h->gctx = c;
