@@ -10,9 +10,10 @@
 //   for outer in 0..max_iterations-1:
 //     k_correspond                     lazy GNC weight update + T*p + voxel-hash kNN + line/plane fit
 //     k_eval<first>                    caps (prefix over index order) + residual/Jacobian/Cauchy + 6x6
-//                                      normal-equation reduction; the LAST block to finish sums the
-//                                      per-block partials in a fixed order and advances the trust-region
-//                                      state machine (one thread), producing the next candidate pose
+//                                      normal-equation reduction (warp butterfly -> block -> cluster of 8 through
+//                                      distributed shared memory); the LAST cluster leader to finish sums the
+//                                      per-cluster partials in a fixed order and advances the trust-region
+//                                      state machine (solver.cuh), producing the next candidate pose
 //     k_eval x ceres_max_num_iterations  same kernel at the candidate pose (accept / reject / converge)
 // Every kernel exits immediately when the state says its work is not needed (solve terminated early,
 // frame converged), so the launch sequence is static and graph-capturable.

@@ -18,7 +18,7 @@
 namespace tloam {
 
 // =================================================================================================
-// Map build kernels (voxel hash, once per set_target)
+// Map build kernels (brick-keyed voxel hash, once per set_target)
 // =================================================================================================
 struct MapBuildArgs {
   const double* src[4];         // AoS xyz of each cloud (the staging buffer for host input, the caller's arrays for device input)
@@ -363,12 +363,11 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
   return kFlagCand | kFlagCounted;                          // surf_num++ / ground_num++
 }
 
-// Correspondence search + primitive fit.  A LANE PAIR serves one feature (knn_search_pair: each lane visits
-// every other cell, the even lane merges and fits), so a 128-thread block serves 64 features and a 128-feature
-// block of one cloud is served by two thread blocks.  Also applies the lazy GNC weight update of the previous
-// outer iteration (ref: registration.cpp:858-876) and resets the residual slot (:1118-1121).
-// Measured alternatives (config 2, us per launch): thread per feature 35-39; 8 lanes per feature with shuffle
-// merge 47, with shared-memory append + rank counting 54; two-pass selection in local memory 43.
+// Correspondence search + primitive fit.  A LANE PAIR serves one feature (knn_search_pair: each lane probes one
+// z-layer of bricks, both lanes stream the candidate runs interleaved, the even lane merges and fits), so a
+// 128-thread block serves 64 features and a 128-feature block of one cloud is served by two thread blocks.  Also
+// applies the lazy GNC weight update of the previous outer iteration (ref: registration.cpp:858-876) and resets the
+// residual slot (:1118-1121).  Measured alternatives: DESIGN.md section 4.
 // 5 blocks per SM (<= 102 registers): measured best; 6 (80 regs) and 8 (64 regs) spill and are 8% / 55% slower,
 // 4 (114 regs, what ptxas picks when unconstrained) is 28% slower
 __global__ void __launch_bounds__(kBlk, 5) k_correspond(const __grid_constant__ DeviceCtx ctx) {
@@ -490,7 +489,7 @@ __device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
   int nact[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = 0.0;
-  Pose7 ev;                      // read around L1: inside the persistent kernel the pose changes between passes
+  Pose7 ev;                      // read around L1 (written by the previous launch's solver block)
   ev.qw = __ldcg(&st->evalq.qw); ev.qx = __ldcg(&st->evalq.qx); ev.qy = __ldcg(&st->evalq.qy); ev.qz = __ldcg(&st->evalq.qz);
   ev.tx = __ldcg(&st->evalq.tx); ev.ty = __ldcg(&st->evalq.ty); ev.tz = __ldcg(&st->evalq.tz);
   const Rt T = pose_to_rt(ev);
