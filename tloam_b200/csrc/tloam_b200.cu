@@ -801,6 +801,8 @@ struct tloam_b200_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t copy_stream = nullptr;              // H2D of the map clouds, overlapped with the build (set_target)
   cudaEvent_t ev_copy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int last_uploaded = 0;
+  cudaEvent_t ev_src = nullptr;                    // set_source: the H2D copies have landed
   char last_error[512] = {0};
   long long launches = 0;
   int launches_frame = 0;
@@ -948,6 +950,7 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 5; ++i)
     if (cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_src, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_state, sizeof(FrameState)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_counter, 256) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
@@ -989,6 +992,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 5; ++i) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+  if (h->ev_src) cudaEventDestroy(h->ev_src);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1063,12 +1067,13 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   c.flags = h->d_flags; c.active = h->d_flags + cp;
   c.blk_count = h->d_blk_count; c.blk_cap = (int)h->cap_blocks; c.partial = h->d_partial;
   h->total_blocks = c.blk_off[4];
+  if (!on_device) CU_TRY(cudaEventRecord(h->ev_src, h->stream));      // the uploads are in; the caller's buffers are free
   if (h->total_blocks > 0) {
     TL_LAUNCH(TLOAM_B200_K_STAGE_SOURCE, (k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(src[0], src[1], src[2], src[3], c, f, f + cp, f + 2 * cp)));
     CU_TRY(cudaGetLastError());
   }
   h->have_src = true;
-  if (!on_device) CU_TRY(cudaStreamSynchronize(h->stream));   // caller buffers may be freed on return
+  if (!on_device) CU_TRY(cudaEventSynchronize(h->ev_src));    // caller buffers may be freed on return
   return TLOAM_B200_OK;
 }
 
@@ -1205,6 +1210,7 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
       const int c = order[k];
       CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * (size_t)a.stage_off[c], xyz[c], n[c] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
       CU_TRY(cudaEventRecord(h->ev_copy[1 + c], h->copy_stream));
+      h->last_uploaded = c;
     }
     for (int k = 0; k < m; ++k) {
       const int c = order[k];
@@ -1222,7 +1228,9 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
   bind_map(h);
   h->origin_known = false;
   h->have_tgt = true;
-  if (!on_device) CU_TRY(cudaStreamSynchronize(h->stream));
+  // host path: the caller's buffers are free once the LAST upload has landed; the build of the last cloud may
+  // still be running on the compute stream (everything that follows is ordered behind it on that stream)
+  if (!on_device && total > 0) CU_TRY(cudaEventSynchronize(h->ev_copy[1 + h->last_uploaded]));
   return TLOAM_B200_OK;
 }
 
