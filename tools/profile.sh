@@ -8,4 +8,5 @@ timeout 300 python bench.py --steps 30 --warmup 3 2>gpurun_out/bench_$V.err > gp
 timeout 400 python bench.py --impl reference --steps 6 --warmup 1 2>gpurun_out/bench_ref_$V.err > gpurun_out/bench_ref_$V.json
 timeout 300 python tools/config3.py 1.0 > gpurun_out/config3_$V.json 2>gpurun_out/config3_$V.err
 timeout 300 python tools/multi_stream.py 1 2 4 8 > gpurun_out/multi_stream_$V.json 2>gpurun_out/multi_stream_$V.err
+timeout 300 python tools/multi_stream.py --e2e 1 2 4 8 >> gpurun_out/multi_stream_$V.json 2>>gpurun_out/multi_stream_$V.err
 tail -c 600 gpurun_out/bench_$V.json; tail -c 400 gpurun_out/bench_ref_$V.json; tail -3 gpurun_out/multi_stream_$V.json
