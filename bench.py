@@ -20,6 +20,10 @@ frame (ref: src/front_end/front_end.cpp:278-337).
           ncclBroadcast of config 4 is timed separately and reported under "shared_map_broadcast".
   --impl reference : the CPU restatement of the reference path (oracle, kind "port" -- the reference itself
           cannot be built in this image) on the box's host cores, same workload / metric / unit.
+
+Informational keys besides the contract's: "stream_device_submap" ((f)-1: the map is maintained on the device, only
+the scan crosses PCIe), "feature_extraction" ((f)-2: PCA feature extraction of a 50k-point cloud, N = 1 only),
+"shared_map_broadcast" (N > 1).
 """
 import argparse
 import json
