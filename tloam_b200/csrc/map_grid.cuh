@@ -199,10 +199,7 @@ __device__ __forceinline__ void knn_search(const GridDesc& g, double rx, double 
 // form for the same work: the kernel is latency-bound at F = 40k, so the extra warps buy issue slots.
 // All 32 lanes must call this together.  On return the even lane holds the exact top-K.
 // ------------------------------------------------------------------------------------------------
-#ifndef TLOAM_MERGE_RUNS
-#define TLOAM_MERGE_RUNS 1
-#endif
-constexpr bool kMergeRuns = TLOAM_MERGE_RUNS != 0;
+constexpr bool kMergeRuns = true;     // measured: 28.2 us per launch with merging, 29.2 without (config 2)
 constexpr unsigned kMergeMax = 16u;   // merged entry: at most this many points
 constexpr int kPairCells = 18;    // 3 x 3 x 2 cells at most in one z-layer of bricks
 

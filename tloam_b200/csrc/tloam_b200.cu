@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(kBlk, 5) k_correspond(const __grid_constant__ 
                              (ctx.dbg && threadIdx.x == 0) ? stamps : nullptr);
     if (ctx.dbg) tk1 = clock64();
     if (ctx.dbg && threadIdx.x == 0 && live) {
-      atomicAdd(&ctx.dbg[11], (unsigned long long)(stamps[1] - stamps[0]));   // probe batch 1
-      atomicAdd(&ctx.dbg[12], (unsigned long long)(stamps[2] - stamps[1]));   // probe batch 2
+      atomicAdd(&ctx.dbg[11], (unsigned long long)(stamps[1] - stamps[0]));   // brick probes + cell list
+      atomicAdd(&ctx.dbg[12], (unsigned long long)(stamps[2] - stamps[1]));   // (unused)
       atomicAdd(&ctx.dbg[13], (unsigned long long)(stamps[3] - stamps[2]));   // candidate streaming
       atomicAdd(&ctx.dbg[14], (unsigned long long)(stamps[4] - stamps[3]));   // merge
     }
