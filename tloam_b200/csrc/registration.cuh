@@ -33,7 +33,10 @@ namespace tloam {
 constexpr int kBlk = 128;     // threads per block for all per-feature kernels
 constexpr int kNRed = 36;     // 21 (H upper) + 6 (g) + 1 (cost) + 4 (slot sum per cloud) + 4 (factors per cloud)
 constexpr int kEvalGridCap = 592;   // 148 SMs x 4: caps the rows of the final partial sum
-constexpr int kEvalCluster = 8;     // k_eval runs in clusters of 8 blocks (portable maximum)
+#ifndef TLOAM_EVAL_CLUSTER
+#define TLOAM_EVAL_CLUSTER 8
+#endif
+constexpr int kEvalCluster = TLOAM_EVAL_CLUSTER;     // k_eval runs in clusters of 8 blocks (portable maximum)
 constexpr int kEdge = 0, kSphere = 1, kPlanar = 2, kGround = 3;
 
 // flags per feature written by k_correspond

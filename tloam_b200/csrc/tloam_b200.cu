@@ -960,6 +960,11 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_PDL"); h->use_pdl = (e && e[0] == '1'); }
+  if (kEvalCluster > 8) {                          // cluster sizes above 8 are "non-portable": opt in per kernel
+    if (cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+      return fail(TLOAM_B200_ERR_CUDA);
+  }
   // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
   FrameState init;
   memset(&init, 0, sizeof(init));
