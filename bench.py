@@ -413,7 +413,7 @@ def main():
     feat = None
     if rank == 0 and world == 1:
         from tloam_b200 import synth
-        fpts = synth.general_cloud(50_000, seed=77)
+        fpts = torch.from_numpy(synth.general_cloud(50_000, seed=77)).pin_memory().numpy()   # pinned like the e2e inputs
         for _ in range(3):
             fout = reg.extract_planar_sphere(fpts)
         t0 = time.perf_counter()
@@ -422,7 +422,7 @@ def main():
         f_ms = 1e3 * (time.perf_counter() - t0) / 10
         feat = {"points": int(fpts.shape[0]), "gpu_ms_per_call": f_ms, "h2d_bytes": int(fpts.nbytes),
                 "lists": [int(len(x)) for x in fout[:4]],
-                "what": "tloam_b200_extract_planar_sphere through the C ABI, host cloud in / host index lists out"}
+                "what": "tloam_b200_extract_planar_sphere through the C ABI, pinned host cloud in / host index lists out"}
         if not args.no_cpu_baseline:
             from oracle import pyoracle     # checker / CPU baseline leg only
             pyoracle.build()
