@@ -119,3 +119,31 @@ def test_gpu_submap_matches_oracle_over_a_stream(oracle):
     assert rc == 0 and np.linalg.norm(d[:3, 3]) < 1e-4
     reg.close()
     other.close()
+
+
+@pytest.mark.gpu
+def test_gpu_submap_with_device_resident_scans(oracle):
+    """The scan features may also be handed over as DEVICE arrays (set_input_source_device); the submap update then
+    appends the copies the library staged, not the caller's buffers (which may be gone by then)."""
+    import torch
+    import tloam_b200
+    frames = stream_inputs(4)
+    reg = tloam_b200.LocalRegistration()
+    sm = oracle.Submap()
+    f0 = frames[0]
+    reg.submap_init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    sm.init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    for fr in frames[1:]:
+        dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for c in fr["scan"]]
+        torch.cuda.synchronize()
+        reg.set_input_source_device(dev)
+        reg.synchronize()
+        for t in dev:
+            t.zero_()                                              # the caller's buffers are free again
+        del dev
+        reg.submap_update(fr["T_gt"], fr["planar_sub"], fr["sphere_sub"])
+        sm.update(fr["T_gt"], fr["scan"][0], fr["scan"][3], fr["planar_sub"], fr["sphere_sub"])
+        for c in range(4):
+            a, b = sort_rows(reg.submap_cloud(c)), sort_rows(sm.cloud(c))
+            assert a.shape == b.shape and np.allclose(a, b, atol=1e-9), c
+    reg.close()

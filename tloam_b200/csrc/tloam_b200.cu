@@ -1030,7 +1030,10 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   }
   if (pad == 0) pad = kBlk;
   blocks = (int)(pad / kBlk);
-  if (!on_device && total > h->cap_stage_src) {
+  // host input is staged; device input is read in place -- unless the device-side submap is in use, whose update
+  // appends the staged edge / ground features after the frame (tloam_b200_submap_update)
+  const bool stage = !on_device || h->submap_ready;
+  if (stage && total > h->cap_stage_src) {
     cudaFree(h->d_stage_src);
     h->cap_stage_src = total + total / 4 + 1024;
     CU_TRY(cudaMalloc(&h->d_stage_src, h->cap_stage_src * 3 * sizeof(double)));
@@ -1054,10 +1057,10 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   const double* src[4];
   c.blk_off[0] = 0;
   for (int k = 0; k < 4; ++k) {
-    // host input is staged; device input is read in place by k_stage_source (stream-ordered, no extra copy)
-    src[k] = on_device ? xyz[k] : h->d_stage_src + 3 * off;
-    if (n[k] > 0 && !on_device)
-      CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    src[k] = stage ? h->d_stage_src + 3 * off : xyz[k];
+    if (n[k] > 0 && stage)
+      CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     c.n[k] = (int)n[k];
     c.pad_off[k] = (int)poff;
     off += n[k];
