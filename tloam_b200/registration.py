@@ -119,11 +119,13 @@ class LocalRegistration:
         ptrs, ns = self._device_args(tensors)
         self._check(self._L.tloam_b200_set_source_device(self._h, ptrs, ns), "set_input_source_device")
         self.n_source = [int(t.shape[0]) for t in tensors]
+        self._keep_source = list(tensors)     # read in place by kernels still in flight: keep them alive until replaced
         return True
 
     def set_input_target_device(self, tensors):
         ptrs, ns = self._device_args(tensors)
         self._check(self._L.tloam_b200_set_target_device(self._h, ptrs, ns), "set_input_target_device")
+        self._keep_target = list(tensors)     # idem
         return True
 
     def scan_matching(self, predict_pose, want_stats=False):
