@@ -71,6 +71,8 @@ typedef struct tloam_tls_config {
   /* extras */
   int ceres_max_num_iterations; /* options.max_num_iterations, registration.cpp:1043 */
   double reinit_dir[3];  /* replaces the unseeded Eigen::Vector3d::Random() of registration.cpp:885 */
+  double initial_trust_region_radius; /* Ceres Solver::Options default 1e4 (the reference does not set it,
+                          * registration.cpp:1036-1047); smaller values force the dogleg / rejected-step branches (tests) */
 } tloam_tls_config;
 
 typedef struct tloam_b200_inner_trace {
@@ -133,6 +135,35 @@ int tloam_b200_set_pose_history(tloam_b200_handle* h, const double last_pose[16]
  * async form iff it was switched on here (default off; without it get_result fills only gpu_launches / gpu_ms). */
 int tloam_b200_set_trace(tloam_b200_handle* h, int on);
 
+/* ---- batched registration: S independent sequences (one handle each: own map, scan, pose history, submap) whose
+ * frames are registered TOGETHER -- one launch sequence per batch frame instead of S.  The reference runs one
+ * LocalRegistration per nodelet; this is S of them stepped in lock-step on one GPU (a single
+ * 40k-feature frame cannot fill 148 SMs).  Per-sequence poses are bit-identical to the un-batched calls.
+ * All sequences share `cfg`.  Feed the sequences through tloam_b200_batch_handle(b, i) (any per-handle set_* /
+ * submap_* entry point) or the batch_set_* forms: xyz = S*4 pointers, n = S*4 counts, sequence-major, cloud order
+ * edge, sphere, planar, ground. ---- */
+typedef struct tloam_b200_batch tloam_b200_batch;
+int tloam_b200_batch_create(const tloam_tls_config* cfg, int device, int S, tloam_b200_batch** out);   /* 1 <= S <= 32 */
+int tloam_b200_batch_destroy(tloam_b200_batch* b);
+int tloam_b200_batch_size(tloam_b200_batch* b);
+tloam_b200_handle* tloam_b200_batch_handle(tloam_b200_batch* b, int i);   /* owned by the batch: do not destroy */
+int tloam_b200_batch_set_target(tloam_b200_batch* b, const double* const* xyz, const size_t* n);          /* HOST */
+int tloam_b200_batch_set_source(tloam_b200_batch* b, const double* const* xyz, const size_t* n);
+int tloam_b200_batch_set_target_device(tloam_b200_batch* b, const double* const* d_xyz, const size_t* n); /* DEVICE */
+int tloam_b200_batch_set_source_device(tloam_b200_batch* b, const double* const* d_xyz, const size_t* n);
+/* predicts: S x 16 doubles (column-major 4x4 each) or NULL = constant-velocity prediction on the device per sequence
+ * (front_end.cpp:329-330).  results: S x 16; statuses (optional): S tloam_b200_status values.  Returns OK iff every
+ * sequence returned OK, else the first failing status. */
+int tloam_b200_batch_scan_match(tloam_b200_batch* b, const double* predicts, double* results, int* statuses);
+int tloam_b200_batch_scan_match_async(tloam_b200_batch* b, const double* predicts);
+int tloam_b200_batch_get_results(tloam_b200_batch* b, double* results, int* statuses, float* gpu_ms /* optional */);
+long long tloam_b200_batch_launch_count(tloam_b200_batch* b);   /* kernels launched by the batch and its handles */
+const char* tloam_b200_batch_last_error(tloam_b200_batch* b);
+/* per-kernel-class timing of the batch frame kernels (see tloam_b200_set_profiling; declared below) */
+struct tloam_b200_profile;
+int tloam_b200_batch_set_profiling(tloam_b200_batch* b, int on);
+int tloam_b200_batch_get_profile(tloam_b200_batch* b, struct tloam_b200_profile* out);
+
 int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse);
 int tloam_b200_get_transform(tloam_b200_handle* h, double pose[16]);
 int tloam_b200_get_pose_increment(tloam_b200_handle* h, double pose[16]);
@@ -174,7 +205,8 @@ int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double de
 enum {
   TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
-  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_FIRST,
+  TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];

@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("fitness_thres", C.c_double),
         ("ceres_max_num_iterations", C.c_int),
         ("reinit_dir", C.c_double * 3),
+        ("initial_trust_region_radius", C.c_double),
         ("threads_mode", C.c_int), ("num_threads", C.c_int),
     ]
 

@@ -849,7 +849,7 @@ void ceres_solve(Oracle& O, int eval_threads, oracle_outer_trace* tr) {
   eval_grad_jac(true);  // IterationZero
   if (tr) tr->initial_cost = x_cost;
   // iteration 0 is "successful": parameters <- x (unchanged)
-  double radius = 1e4, mu = 1e-8;
+  double radius = O.cfg.initial_trust_region_radius, mu = 1e-8;
   const double min_mu = 1e-8, max_mu = 1.0;
   bool reuse = false;
   double D[6], sgrad[6], gn[6];  // diagonal_, gradient_ (scaled), gauss_newton_step_ (scaled)
@@ -1154,6 +1154,7 @@ void oracle_default_config(oracle_config* c) {  // ref: config/mapping/lidar_odo
   c->fitness_thres = 0.02;
   c->ceres_max_num_iterations = 4;
   c->reinit_dir[0] = 1.0; c->reinit_dir[1] = 1.0; c->reinit_dir[2] = 1.0;
+  c->initial_trust_region_radius = 1e4;
   c->threads_mode = 0; c->num_threads = 0;
 }
 

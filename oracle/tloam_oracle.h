@@ -44,6 +44,7 @@ typedef struct oracle_config {
   /* --- extras (not in the YAML) --- */
   int ceres_max_num_iterations; /* registration.cpp:1043 (4) */
   double reinit_dir[3];    /* Q1: replaces Eigen::Vector3d::Random(); normalised inside */
+  double initial_trust_region_radius; /* Ceres default 1e4 (not set by the reference); tests shrink it */
   int threads_mode;        /* 0 = reference-faithful thread structure, 1 = all cores */
   int num_threads;         /* 0 = omp_get_max_threads() */
 } oracle_config;

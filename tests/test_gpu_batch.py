@@ -1,0 +1,142 @@
+"""Batched registration (tloam_b200_batch_*) and the fused first evaluation (k_first): the batch must give every
+sequence the pose it gets alone (bit-identical: same per-sequence reduction tree), the fused kernel must agree with the
+un-fused kernel pair, and both must stay within parity of the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from tloam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+BIG = 10 ** 9
+CAPS = dict(edge_maxnum=BIG, sphere_maxnum=BIG, planar_maxnum=BIG, ground_maxnum=BIG)
+
+
+def pose_err(A, B):
+    d = np.linalg.inv(A) @ B
+    return np.linalg.norm(d[:3, 3]), np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))
+
+
+def scenes(S):
+    """S small scenes of DIFFERENT sizes and poses (ragged batch)."""
+    out = []
+    for i in range(S):
+        cfg = synth.scaled(0.02 + 0.01 * (i % 3), seed=500 + i)
+        T_gt = synth.se3_exp([1.0 + i, 0.5 * i, 0.0, 0.01, -0.01 * i, 0.1 + 0.05 * i])
+        predict = T_gt @ synth.se3_exp(np.asarray(synth.CONFIG1_PERTURB) * (0.5 + 0.25 * i))
+        out.append(dict(map=synth.make_map(cfg, T_gt), scan=synth.make_scan(cfg, T_gt, i), predict=predict, T_gt=T_gt))
+    return out
+
+
+def run_single(sc, **cfg):
+    import tloam_b200
+    r = tloam_b200.LocalRegistration(**cfg)
+    r.set_input_target(sc["map"])
+    r.set_input_source(sc["scan"])
+    T = r.scan_matching(sc["predict"])
+    r.close()
+    return T
+
+
+@pytest.mark.parametrize("caps", [CAPS, {}], ids=["caps_free_fused", "default_caps_unfused"])
+def test_batch_is_bit_identical_to_single(caps):
+    import tloam_b200
+    S = 5
+    sc = scenes(S)
+    singles = [run_single(s, **caps) for s in sc]
+    b = tloam_b200.BatchRegistration(S, **caps)
+    b.set_input_target(b.pack_host([s["map"] for s in sc]))
+    b.set_input_source(b.pack_host([s["scan"] for s in sc]))
+    for rep in range(2):                      # second round: the instantiated graph is reused
+        T, st = b.scan_matching(np.stack([s["predict"] for s in sc]))
+        assert np.all(st == 0)
+        for i in range(S):
+            assert np.array_equal(T[i], singles[i]), (rep, i, pose_err(T[i], singles[i]))
+    b.close()
+
+
+def test_batch_with_per_sequence_handles_and_device_prediction():
+    """Sequences are fed through their own handles; frame 2 is predicted on the device from the pose history."""
+    import tloam_b200
+    S = 3
+    sc = scenes(S)
+    b = tloam_b200.BatchRegistration(S, **CAPS)
+    singles = []
+    for i, s in enumerate(sc):
+        b.seq[i].set_input_target(s["map"])
+        b.seq[i].set_input_source(s["scan"])
+        r = tloam_b200.LocalRegistration(**CAPS)
+        r.set_input_target(s["map"])
+        r.set_input_source(s["scan"])
+        T1 = r.scan_matching(s["predict"])
+        T2 = r.scan_matching_predicted()
+        singles.append((T1, T2))
+        r.close()
+    T1, st = b.scan_matching(np.stack([s["predict"] for s in sc]))
+    T2, st2 = b.scan_matching(None)
+    assert np.all(st == 0) and np.all(st2 == 0)
+    for i in range(S):
+        assert np.array_equal(T1[i], singles[i][0])
+        assert np.array_equal(T2[i], singles[i][1])
+        assert np.array_equal(b.seq[i].get_transform(), T2[i])
+    b.close()
+
+
+def test_batch_reports_a_bad_sequence_without_disturbing_the_others():
+    import tloam_b200
+    S = 3
+    sc = scenes(S)
+    b = tloam_b200.BatchRegistration(S, **CAPS)
+    b.set_input_target(b.pack_host([s["map"] for s in sc]))
+    b.set_input_source(b.pack_host([s["scan"] for s in sc]))
+    pred = np.stack([s["predict"] for s in sc])
+    pred[1][0, 0] = 2.0                        # not a rigid transform
+    out = np.zeros((S, 16))
+    st = np.zeros(S, dtype=np.int32)
+    import ctypes as C
+    from tloam_b200 import _lib
+    p = np.ascontiguousarray(np.transpose(pred, (0, 2, 1))).reshape(-1)
+    rc = _lib.load().tloam_b200_batch_scan_match(b._b, p.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 out.ctypes.data_as(C.POINTER(C.c_double)), st.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == _lib.ERR_BAD_POSE and list(st) == [0, _lib.ERR_BAD_POSE, 0]
+    T = np.transpose(out.reshape(S, 4, 4), (0, 2, 1))
+    for i in (0, 2):
+        assert np.array_equal(T[i], run_single(sc[i], **CAPS))
+    b.close()
+
+
+def test_fused_first_evaluation_matches_the_unfused_kernels(oracle):
+    """k_first (search + fit + first evaluation) against k_correspond + k_eval<first>: same factors, same normal
+    equations up to the summation tree (64- vs 128-feature blocks), and both within parity of the oracle."""
+    import tloam_b200
+    sc = scenes(1)[0]
+    T_f, st_f = None, None
+    res = {}
+    for mode in ("fused", "unfused"):
+        if mode == "unfused":
+            os.environ["TLOAM_B200_NO_FUSE"] = "1"
+        try:
+            r = tloam_b200.LocalRegistration(**CAPS)
+        finally:
+            os.environ.pop("TLOAM_B200_NO_FUSE", None)
+        r.set_input_target(sc["map"])
+        r.set_input_source(sc["scan"])
+        res[mode] = r.scan_matching(sc["predict"], want_stats=True)
+        r.close()
+    (Tf, sf), (Tu, su) = res["fused"], res["unfused"]
+    assert sf.gpu_launches == 1 + 4 * 5 and su.gpu_launches == 1 + 4 * 6
+    assert sf.n_outer == su.n_outer
+    for o in range(sf.n_outer):
+        a, c = sf.outer[o], su.outer[o]
+        assert list(a.n_factors) == list(c.n_factors)
+        assert np.allclose(np.array(a.H0), np.array(c.H0), rtol=1e-12, atol=1e-9)
+        assert a.n_inner == c.n_inner and a.termination == c.termination
+    dt, dr = pose_err(Tf, Tu)
+    assert dt < 1e-9 and dr < 1e-10, (dt, dr)
+    o = oracle.Oracle(**CAPS)
+    o.set_input_target(sc["map"])
+    o.set_input_source(sc["scan"])
+    rc, To, _ = o.scan_matching(sc["predict"])
+    dt, dr = pose_err(Tf, To)
+    assert rc == 0 and dt < 1e-4 and dr < 1e-5, (dt, dr)

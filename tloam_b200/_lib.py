@@ -24,6 +24,7 @@ class TlsConfig(C.Structure):
         ("fitness_thres", C.c_double),
         ("ceres_max_num_iterations", C.c_int),
         ("reinit_dir", C.c_double * 3),
+        ("initial_trust_region_radius", C.c_double),
     ]
 
 
@@ -64,7 +65,7 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first")
 
 
 class FeatureConfig(C.Structure):
@@ -93,6 +94,11 @@ EXPORTS = [
     "tloam_b200_submap_update", "tloam_b200_submap_sizes", "tloam_b200_submap_download", "tloam_b200_voxel_down_sample",
     "tloam_b200_scan_match_predicted_async", "tloam_b200_scan_match_predicted", "tloam_b200_set_pose_history",
     "tloam_b200_feature_default_config", "tloam_b200_extract_planar_sphere", "tloam_b200_pca_info",
+    "tloam_b200_batch_create", "tloam_b200_batch_destroy", "tloam_b200_batch_size", "tloam_b200_batch_handle",
+    "tloam_b200_batch_set_target", "tloam_b200_batch_set_source", "tloam_b200_batch_set_target_device",
+    "tloam_b200_batch_set_source_device", "tloam_b200_batch_scan_match", "tloam_b200_batch_scan_match_async",
+    "tloam_b200_batch_get_results", "tloam_b200_batch_launch_count", "tloam_b200_batch_last_error",
+    "tloam_b200_batch_set_profiling", "tloam_b200_batch_get_profile",
 ]
 
 _lib = None
@@ -167,5 +173,22 @@ def load():
                                                    szp, szp, szp, szp]
     L.tloam_b200_pca_info.argtypes = [vp, C.POINTER(FeatureConfig), dp, C.c_size_t, dp, dp, dp, dp,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.tloam_b200_batch_create.argtypes = [C.POINTER(TlsConfig), C.c_int, C.c_int, C.POINTER(vp)]
+    L.tloam_b200_batch_destroy.argtypes = [vp]
+    L.tloam_b200_batch_size.argtypes = [vp]
+    L.tloam_b200_batch_handle.argtypes = [vp, C.c_int]
+    L.tloam_b200_batch_handle.restype = vp
+    for name in ("set_target", "set_source"):
+        getattr(L, "tloam_b200_batch_" + name).argtypes = [vp, C.POINTER(dp), szp]
+        getattr(L, "tloam_b200_batch_" + name + "_device").argtypes = [vp, C.POINTER(vp), szp]
+    L.tloam_b200_batch_scan_match.argtypes = [vp, dp, dp, ip]
+    L.tloam_b200_batch_scan_match_async.argtypes = [vp, dp]
+    L.tloam_b200_batch_get_results.argtypes = [vp, dp, ip, C.POINTER(C.c_float)]
+    L.tloam_b200_batch_launch_count.argtypes = [vp]
+    L.tloam_b200_batch_launch_count.restype = C.c_longlong
+    L.tloam_b200_batch_last_error.argtypes = [vp]
+    L.tloam_b200_batch_last_error.restype = C.c_char_p
+    L.tloam_b200_batch_set_profiling.argtypes = [vp, C.c_int]
+    L.tloam_b200_batch_get_profile.argtypes = [vp, C.POINTER(Profile)]
     _lib = L
     return L

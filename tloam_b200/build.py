@@ -12,8 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtloam_b200.so")
 SOURCES = [os.path.join(CSRC, "tloam_b200.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("registration.cuh", "solver.cuh", "map_grid.cuh", "se3.cuh")] + [
-    os.path.join(HERE, "..", "include", "tloam_b200.h")]
+import glob
+# every header the translation unit can include: editing any of them triggers a rebuild
+HEADERS = sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                 glob.glob(os.path.join(HERE, "..", "include", "**", "*.h"), recursive=True))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

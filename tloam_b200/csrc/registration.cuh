@@ -92,6 +92,7 @@ struct DeviceCtx {
   int factor_num, max_iterations, ceres_max_it, pad_;
   double edge_dir_thres, cost_threshold, gnc_factor, noise_bound, fitness_thres;
   double reinit_dir[3];
+  double initial_radius;        // Ceres options.initial_trust_region_radius (default 1e4; a test knob otherwise)
   // per-feature SoA (padded)
   const double *px, *py, *pz;
   double *w, *slot;

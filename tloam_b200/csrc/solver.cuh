@@ -481,7 +481,7 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
     } else if (iter0) {
       // ---- IterationZero ----
       st->iter = 0; st->num_invalid = 0; st->last_cand_valid = 0;
-      st->radius = 1e4;                                                  // initial_trust_region_radius
+      st->radius = ctx.initial_radius;                                   // initial_trust_region_radius
       int nf_total = 0;
       for (int k = 0; k < 4; ++k) {
         const int nf = (int)(tot[32 + k] + 0.5);

@@ -10,773 +10,13 @@
 
 #include "registration.cuh"
 #include "solver.cuh"
+#include "map_build.cuh"
+#include "frame_kernels.cuh"
 #include "submap.cuh"
 #include "feature_extract.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
-namespace tloam {
-
-// =================================================================================================
-// Map build kernels (brick-keyed voxel hash, once per set_target)
-// =================================================================================================
-struct MapBuildArgs {
-  const double* src[4];         // AoS xyz of each cloud (the staging buffer for host input, the caller's arrays for device input)
-  unsigned stage_off[5];        // global point index of each cloud's first point
-  unsigned char* blob;          // MapHeader + pts + tables
-  unsigned* slot_of;            // scratch [total]
-  unsigned* rank_of;            // scratch [total]
-  unsigned i_beg, i_end;        // global point range this launch works on (one cloud in the pipelined host path)
-  int only_cloud;               // k_map_offsets: table of this cloud only (-1 = all four)
-};
-
-__device__ __forceinline__ int cloud_of_point(const MapBuildArgs& a, unsigned i) {
-  return (i >= a.stage_off[3]) ? 3 : (i >= a.stage_off[2]) ? 2 : (i >= a.stage_off[1]) ? 1 : 0;
-}
-__device__ __forceinline__ const double* point_of(const MapBuildArgs& a, unsigned i) {
-  const int c = cloud_of_point(a, i);
-  const double* base = c == 0 ? a.src[0] : c == 1 ? a.src[1] : c == 2 ? a.src[2] : a.src[3];
-  return base + 3ull * (i - a.stage_off[c]);
-}
-
-// bounding box of the points [i_beg, i_end) -- the first non-empty cloud: the origin must be known before any
-// point can be inserted, and the host path inserts cloud c while cloud c+1 is still crossing PCIe
-__global__ void k_map_bbox(MapBuildArgs a) {
-  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-  for (unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x; i < a.i_end; i += gridDim.x * blockDim.x) {
-    const double* pt = point_of(a, i);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const double v = pt[d];
-      mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v);
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
-      mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
-    }
-  __shared__ double s_mn[8][3], s_mx[8][3];
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { s_mn[threadIdx.x >> 5][d] = mn[d]; s_mx[threadIdx.x >> 5][d] = mx[d]; }
-  }
-  __syncthreads();
-  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
-  if (threadIdx.x < 3) {                       // 6 atomics per block (same-address atomics serialise in L2)
-    const int d = threadIdx.x;
-    double lo = s_mn[0][d], hi = s_mx[0][d];
-    for (int wi = 1; wi < (int)(blockDim.x >> 5); ++wi) { lo = fmin(lo, s_mn[wi][d]); hi = fmax(hi, s_mx[wi][d]); }
-    atomicMin(&h->bbox_enc[d], enc_ordered(lo));
-    atomicMax(&h->bbox_enc[3 + d], enc_ordered(hi));
-  }
-  // the last block to arrive turns the bounding box into the map origin = integer-rounded centre of the box
-  // (exactly representable; |rel| stays small so the FP32 storage keeps ~8e-6 m resolution at 100 m)
-  __shared__ bool s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&h->bbox_ticket, 1u) == gridDim.x - 1u;
-  __syncthreads();
-  if (s_last && threadIdx.x < 3) {
-    __threadfence();
-    const double lo = dec_ordered(atomicMin(&h->bbox_enc[threadIdx.x], ~0ull)), hi = dec_ordered(atomicMax(&h->bbox_enc[3 + threadIdx.x], 0ull));
-    h->origin[threadIdx.x] = rint(0.5 * (lo + hi));
-  }
-}
-
-// empty map: origin 0
-__global__ void k_map_origin(MapBuildArgs a) {
-  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
-  if (threadIdx.x < 3) h->origin[threadIdx.x] = 0.0;
-}
-
-__device__ __forceinline__ float3 rel_of(const MapBuildArgs& a, const MapHeader* h, unsigned i) {
-  const double* pt = point_of(a, i);
-  return make_float3((float)(pt[0] - h->origin[0]), (float)(pt[1] - h->origin[1]), (float)(pt[2] - h->origin[2]));
-}
-
-// cell of the STORED (FP32-rounded) coordinates, so that the 27-cell search is exact for what is stored
-__device__ __forceinline__ void cell_of_rel(const float3 r, double inv, int& cx, int& cy, int& cz) {
-  cx = (int)floor((double)r.x * inv); cy = (int)floor((double)r.y * inv); cz = (int)floor((double)r.z * inv);
-}
-
-// claims the point's brick (CAS on the key) and takes a rank inside its sub-cell (packed u16 counters)
-__global__ void k_map_insert(MapBuildArgs a) {
-  const unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.i_end) return;
-  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
-  const int c = cloud_of_point(a, i);
-  const float3 r = rel_of(a, h, i);
-  int cx, cy, cz;
-  cell_of_rel(r, 1.0 / h->cell[c], cx, cy, cz);
-  const unsigned long long key = cell_key(brick_of(cx), brick_of(cy), brick_of(cz));
-  const int sub = subcell_of(cx, cy, cz);
-  uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
-  const unsigned mask = h->tsize[c] - 1u;
-  unsigned s = hash_key(key) & mask;
-  while (true) {
-    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&table[2u * s]);
-    const unsigned long long prev = atomicCAS(kp, 0ull, key);
-    if (prev == 0ull || prev == key) break;
-    s = (s + 1u) & mask;
-  }
-  // words 3..6 of the entry hold the 8 u16 counts
-  unsigned* words = reinterpret_cast<unsigned*>(&table[2u * s]) + 3;
-  const unsigned old = atomicAdd(&words[sub >> 1], (sub & 1) ? 0x10000u : 1u);
-  const unsigned rank = (sub & 1) ? (old >> 16) : (old & 0xFFFFu);
-  if (rank >= kMaxCellPoints) atomicOr(&h->build_flags, 1ull);    // the packed counter would wrap: map unusable
-  a.slot_of[i] = s;
-  a.rank_of[i] = rank;
-}
-
-// base offsets of the occupied bricks: block-level exclusive scan of the brick totals + ONE atomic per block on
-// the cloud's bump allocator (table sizes are multiples of the block size, so a block never straddles two clouds)
-__global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
-  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
-  unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
-  int c = 0;
-  if (a.only_cloud >= 0) c = a.only_cloud;
-  else while (c < 3 && s >= h->tsize[c]) { s -= h->tsize[c]; ++c; }
-  uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
-  unsigned cnt = 0u;
-  if (s < h->tsize[c]) {
-    const uint4 ea = table[2u * s];
-    if ((ea.x | ea.y) != 0u) {
-      const uint4 eb = table[2u * s + 1u];
-      cnt = (ea.w & 0xFFFFu) + (ea.w >> 16) + (eb.x & 0xFFFFu) + (eb.x >> 16) + (eb.y & 0xFFFFu) + (eb.y >> 16) +
-            (eb.z & 0xFFFFu) + (eb.z >> 16);
-    }
-  }
-  // warp inclusive scan
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned incl = cnt;
-  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  __shared__ unsigned s_w[8];
-  __shared__ unsigned s_base;
-  if (lane == 31) s_w[warp] = incl;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned tot = 0;
-    for (int wi = 0; wi < 8; ++wi) { const unsigned v = s_w[wi]; s_w[wi] = tot; tot += v; }
-    s_base = (tot > 0u) ? atomicAdd(&h->cursor[c], tot) : 0u;
-  }
-  __syncthreads();
-  if (cnt > 0u) table[2u * s].z = s_base + s_w[warp] + (incl - cnt);
-}
-
-__global__ void k_map_scatter(MapBuildArgs a) {
-  const unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.i_end) return;
-  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
-  if (h->build_flags & 1ull) return;               // counters wrapped: destinations are meaningless
-  const int c = cloud_of_point(a, i);
-  const float3 r = rel_of(a, h, i);
-  int cx, cy, cz;
-  cell_of_rel(r, 1.0 / h->cell[c], cx, cy, cz);
-  const int sub = subcell_of(cx, cy, cz);
-  const uint4* table = reinterpret_cast<const uint4*>(a.blob + h->table_off[c]);
-  float4* pts = reinterpret_cast<float4*>(a.blob + h->pts_off[c]);
-  const unsigned slot = a.slot_of[i];
-  const uint4 ea = table[2u * slot], eb = table[2u * slot + 1u];
-  const unsigned w[4] = {ea.w, eb.x, eb.y, eb.z};
-  unsigned dst = ea.z + a.rank_of[i];
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    if (q < sub) dst += (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
-  pts[dst] = make_float4(r.x, r.y, r.z, __int_as_float((int)(i - a.stage_off[c])));
-}
-
-// AoS FP64 staging -> padded SoA feature arrays
-__global__ void k_stage_source(const double* s0, const double* s1, const double* s2, const double* s3, DeviceCtx ctx,
-                               double* px, double* py, double* pz) {
-  const int b = blockIdx.x;
-  const int c = cloud_of_block(ctx, b);
-  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
-  const int gi = ctx.pad_off[c] + il;
-  const double* src = (c == 0) ? s0 : (c == 1) ? s1 : (c == 2) ? s2 : s3;
-  double x = 0, y = 0, z = 0;
-  if (il < ctx.n[c]) {
-    const double* p = src + 3ull * il;
-    x = p[0]; y = p[1]; z = p[2];
-  }
-  px[gi] = x; py[gi] = y; pz[gi] = z;
-}
-
-// =================================================================================================
-// Frame kernels
-// =================================================================================================
-struct Predict { double m[16]; double from_state; };   // from_state != 0: constant-velocity prediction on the device
-
-// Programmatic dependent launch (opt-in, TLOAM_B200_PDL=1): a frame kernel waits for its predecessor before it
-// touches anything the predecessor may have written; the block that runs the serial tail of a k_eval (partial sum
-// + solver, ~10 us on one SM) releases the successor first, so that the successor's blocks are already resident
-// on the idle SMs when the tail ends.  (Releasing at kernel entry was measured slower: the successor's waiting
-// blocks take residency away from the running grid.)
-__device__ __forceinline__ void pdl_prologue() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// thread-block cluster barrier, split in its two halves (all threads of the block execute both, convergently)
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ unsigned cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-// store a double into the same shared-memory variable of block `rank` of this cluster (distributed shared memory)
-__device__ __forceinline__ void dsmem_store(double* local_smem, unsigned rank, double v) {
-  const unsigned laddr = (unsigned)__cvta_generic_to_shared(local_smem);
-  unsigned raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
-}
-
-// scanMatching prologue, ref: registration.cpp:879-886, 961-964, 1027-1033.
-// 4x4 column-major helpers for the constant-velocity prediction (ref: src/front_end/front_end.cpp:329-330)
-__device__ __forceinline__ void mat4_mul(const double* A, const double* B, double* C) {
-  for (int c = 0; c < 4; ++c)
-    for (int r = 0; r < 4; ++r) {
-      double s = 0.0;
-      for (int k = 0; k < 4; ++k) s += A[k * 4 + r] * B[c * 4 + k];
-      C[c * 4 + r] = s;
-    }
-}
-__device__ __forceinline__ void isometry_inverse(const double* T, double* out) {   // Eigen::Isometry3d::inverse(): R^T, -R^T t
-  for (int c = 0; c < 3; ++c)
-    for (int r = 0; r < 3; ++r) out[c * 4 + r] = T[r * 4 + c];
-  for (int r = 0; r < 3; ++r) out[12 + r] = -(out[r] * T[12] + out[4 + r] * T[13] + out[8 + r] * T[14]);
-  out[3] = out[7] = out[11] = 0.0; out[15] = 1.0;
-}
-
-__global__ void k_begin_frame(DeviceCtx ctx, const Predict* prp) {
-  Predict pr = *prp;
-  if (pr.from_state != 0.0) {
-    // step = last^-1 * curr ; predict = curr * step, from the two last results kept in the frame state
-    // (every thread computes the same 16 values: the state is rewritten further down by thread 0 only)
-    double inv[16], step[16];
-    isometry_inverse(ctx.st->last_pose, inv);
-    mat4_mul(inv, ctx.st->curr_pose, step);
-    mat4_mul(ctx.st->curr_pose, step, pr.m);
-  }
-  // zero the trace
-  {
-    unsigned* w = reinterpret_cast<unsigned*>(ctx.stats);
-    if (w) for (unsigned i = threadIdx.x; i < sizeof(tloam_b200_stats) / 4; i += blockDim.x) w[i] = 0u;
-    for (int i = threadIdx.x; i < ctx.blk_off[4]; i += blockDim.x) ctx.blk_count[i] = 0;   // buffer 0 (outer 0)
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  FrameState* st = ctx.st;
-  st->status = TLOAM_B200_OK;
-  st->frame_done = 0;
-  *ctx.counter = 0u;
-  for (int i = 0; i < 16; ++i) st->last_pose[i] = st->curr_pose[i];            // :882
-  Pose7 p;
-  if (*ctx.map_flags & 1ull) {                   // a map cell overflowed its u16 counter at build time
-    st->status = TLOAM_B200_ERR_MAP_DENSITY;
-    for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
-    st->frame_done = 1;
-    return;
-  }
-  if (!pose_from_matrix(pr.m, p)) {
-    st->status = TLOAM_B200_ERR_BAD_POSE;
-    for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
-    st->frame_done = 1;
-    return;
-  }
-  se3_log(p, st->x);                                                            // :881
-  const double wn = sqrt(st->x[3] * st->x[3] + st->x[4] * st->x[4] + st->x[5] * st->x[5]);
-  if (wn < 1e-2) {                                                              // :884-886 (explicit direction)
-    const double* d = ctx.reinit_dir;
-    const double nn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    for (int j = 0; j < 3; ++j) st->x[3 + j] = d[j] / nn * 1e-4;
-  }
-  if (ctx.stats) for (int i = 0; i < 6; ++i) ctx.stats->x_init[i] = st->x[i];
-  st->xq = se3_exp(st->x);
-  st->evalq = st->xq;
-  st->phase = kPhaseIter0;
-  st->outer = 0;
-  st->planar_prev = __longlong_as_double(0x7FF0000000000000ll);                 // +inf, :956
-  double c2 = ctx.noise_bound * ctx.noise_bound;                                // :962-964
-  if (c2 < 1e-16) c2 = 1e-2;
-  st->c2 = c2;
-  // :1027-1033 -- mu is derived from the residual slots BEFORE the first solve, when they are all zero
-  const double max_residual = 0.0;
-  double mu = 1.0 / (2.0 * max_residual / c2 - 1.0);
-  if (mu <= 0.0) mu = 1e-10;
-  st->mu = mu; st->mu_used = mu; st->th1 = 0.0; st->th2 = 0.0;
-  for (int k = 0; k < 4; ++k) st->slot_sum[k] = 0.0;
-}
-
-// Primitive fit + validity tests of one feature given its (already merged) neighbour list.
-// ref: registration.cpp:445-493 (edge), 536-551 (sphere), 589-625 (planar), 732-768 (ground).
-template <int K>
-__device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, const TopK<K>& t, double prim[6]) {
-  const GridDesc& g = ctx.grid[c];
-  const double o0 = ctx.origin[0], o1 = ctx.origin[1], o2 = ctx.origin[2];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) prim[j] = 0.0;
-  if (K == 1) {                                            // sphere
-    if (t.pos[0] < 0) return kFlagCounted;                 // not found: sphere_sum++ (:551)
-    if (t.d2[0] > 0.2) return 0;                           // squared distance vs 0.2, `continue` (:536)
-    const float4 m = __ldg(&g.pts[t.pos[0]]);
-    prim[0] = o0 + (double)m.x; prim[1] = o1 + (double)m.y; prim[2] = o2 + (double)m.z;
-    return kFlagCand | kFlagCounted;
-  }
-  const int k = t.count();
-  if (k <= 0) return 0;
-  double nb[K][3];
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    if (j < k) {
-      const float4 m = __ldg(&g.pts[t.pos[j]]);
-      nb[j][0] = o0 + (double)m.x; nb[j][1] = o1 + (double)m.y; nb[j][2] = o2 + (double)m.z;
-    } else {
-      nb[j][0] = nb[j][1] = nb[j][2] = 0.0;
-    }
-  }
-  if (c == kEdge) {
-    if (k <= 3) return 0;                                  // :445
-    // mean + covariance from raw cumulants (:451-474)
-    double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j = 0; j < k; ++j) {
-      const double x = nb[j][0], y = nb[j][1], z = nb[j][2];
-      cu[0] += x; cu[1] += y; cu[2] += z;
-      cu[3] += x * x; cu[4] += x * y; cu[5] += x * z; cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
-    }
-    const double kn = (double)k;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) cu[j] /= kn;
-    double ev[3], dir[3];
-    sym_eig3_max(cu[3] - cu[0] * cu[0], cu[4] - cu[0] * cu[1], cu[5] - cu[0] * cu[2], cu[6] - cu[1] * cu[1],
-                 cu[7] - cu[1] * cu[2], cu[8] - cu[2] * cu[2], ev, dir);
-    if (!(ev[2] > 3.0 * ev[1] && fabs(dir[2]) > ctx.edge_dir_thres)) return 0;   // :481
-    prim[0] = 0.1 * dir[0] + cu[0]; prim[1] = 0.1 * dir[1] + cu[1]; prim[2] = 0.1 * dir[2] + cu[2];
-    prim[3] = -0.1 * dir[0] + cu[0]; prim[4] = -0.1 * dir[1] + cu[1]; prim[5] = -0.1 * dir[2] + cu[2];
-    return kFlagCand | kFlagCounted;                        // edge_num++ (:492)
-  }
-  if (k <= 4) return 0;                                     // :589 / :732
-  double nd[4];
-  fit_best_plane(nb, K, nd);                                // :600 / :743
-#pragma unroll
-  for (int j = 0; j < K; ++j)
-    if (nd[0] * nb[j][0] + nd[1] * nb[j][1] + nd[2] * nb[j][2] + nd[3] > 0.2) return 0;   // one-sided, :605-613
-  prim[0] = nd[0]; prim[1] = nd[1]; prim[2] = nd[2]; prim[3] = nd[3];
-  return kFlagCand | kFlagCounted;                          // surf_num++ / ground_num++
-}
-
-// Correspondence search + primitive fit.  A LANE PAIR serves one feature (knn_search_pair: each lane probes one
-// z-layer of bricks, both lanes stream the candidate runs interleaved, the even lane merges and fits), so a
-// 128-thread block serves 64 features and a 128-feature block of one cloud is served by two thread blocks.  Also
-// applies the lazy GNC weight update of the previous outer iteration (ref: registration.cpp:858-876) and resets the
-// residual slot (:1118-1121).  Measured alternatives: DESIGN.md section 4.
-// 5 blocks per SM (<= 102 registers): measured best; 6 (80 regs) and 8 (64 regs) spill and are 8% / 55% slower,
-// 4 (114 regs, what ptxas picks when unconstrained) is 28% slower
-__global__ void __launch_bounds__(kBlk, 5) k_correspond(const __grid_constant__ DeviceCtx ctx) {
-  pdl_prologue();
-  const FrameState* st = ctx.st;
-  if (st->frame_done || st->phase != kPhaseIter0) return;
-  __shared__ unsigned s_beg[kPairCells][kBlk];
-  __shared__ unsigned s_cnt[kPairCells][kBlk];
-  __shared__ float s_md[kPairCells][kBlk];
-  constexpr int kQ = kBlk / 2;                 // features per thread block
-  const int fb = blockIdx.x / 2, sb = blockIdx.x % 2;
-  const int c = cloud_of_block(ctx, fb);
-  const int il = (fb - ctx.blk_off[c]) * kBlk + sb * kQ + (int)(threadIdx.x >> 1);
-  const int gi = ctx.pad_off[c] + il;
-  const bool live = (il < ctx.n[c]) && cloud_enabled(ctx, c);
-  const bool even = (threadIdx.x & 1) == 0;
-  const int buf = st->outer & 1;
-  if (threadIdx.x == 0 && sb == 0) ctx.blk_count[(buf ^ 1) * ctx.blk_cap + fb] = 0;   // for the next outer iteration
-  long long tk0 = 0, tk1 = 0;
-  if (ctx.dbg) tk0 = clock64();
-  double rx = 0.0, ry = 0.0, rz = 0.0;
-  if (live) {
-    const Rt T = pose_to_rt(st->xq);
-    double qx, qy, qz;
-    rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
-    rx = qx - ctx.origin[0]; ry = qy - ctx.origin[1]; rz = qz - ctx.origin[2];
-  }
-  unsigned char flag = 0;
-  double prim[6];
-  if (c == kSphere) {
-    TopK<1> t;
-    knn_search_pair<1, kBlk>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t);
-    if (ctx.dbg) tk1 = clock64();
-    if (live && even) flag = fit_one<1>(ctx, c, t, prim);
-  } else {
-    TopK<5> t;
-    long long stamps[5] = {0, 0, 0, 0, 0};
-    knn_search_pair<5, kBlk>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], s_beg, s_cnt, s_md, t,
-                             (ctx.dbg && threadIdx.x == 0) ? stamps : nullptr);
-    if (ctx.dbg) tk1 = clock64();
-    if (ctx.dbg && threadIdx.x == 0 && live) {
-      atomicAdd(&ctx.dbg[11], (unsigned long long)(stamps[1] - stamps[0]));   // brick probes + cell list
-      atomicAdd(&ctx.dbg[12], (unsigned long long)(stamps[2] - stamps[1]));   // (unused)
-      atomicAdd(&ctx.dbg[13], (unsigned long long)(stamps[3] - stamps[2]));   // candidate streaming
-      atomicAdd(&ctx.dbg[14], (unsigned long long)(stamps[4] - stamps[3]));   // merge
-    }
-    if (live && even) flag = fit_one<5>(ctx, c, t, prim);
-  }
-  if (even) {
-    if (live) {
-      if (st->outer == 0) {
-        ctx.w[gi] = 1.0;                                                          // :931-949
-      } else {
-        const double res = ctx.slot[gi];
-        if (res != 0.0) {
-          double wv;
-          if (res >= st->th1) wv = 0.0;
-          else if (res <= st->th2) wv = 1.0;
-          else wv = sqrt(st->c2 * st->mu_used * (st->mu_used + 1.0) / res) - st->mu_used;
-          ctx.w[gi] = wv;
-        }
-      }
-      ctx.slot[gi] = 0.0;
-#pragma unroll
-      for (int j = 0; j < 6; ++j) ctx.prim[j][gi] = prim[j];
-    }
-    ctx.flags[gi] = flag;
-  }
-  if (ctx.dbg && threadIdx.x == 0 && live) {
-    atomicAdd(&ctx.dbg[8], (unsigned long long)(tk1 - tk0));
-    atomicAdd(&ctx.dbg[10], (unsigned long long)(clock64() - tk1));
-    atomicAdd(&ctx.dbg[9], 1ull);
-  }
-  const int cnt = __syncthreads_count(even && (flag & kFlagCounted) != 0);
-  if (threadIdx.x == 0 && cnt > 0) atomicAdd(&ctx.blk_count[buf * ctx.blk_cap + fb], cnt);
-}
-
-// `*_maxnum` caps in feature-index order (Q8): factor i is active iff it is a candidate and the number of
-// counted features before it is < maxnum (the reference `return`s at the first cap-checked feature
-// after the counter reached the cap, ref: :448-449, 538-539, 592-593, 735-736).
-__device__ __forceinline__ bool compute_active(const DeviceCtx& ctx, int b, int c, unsigned char flag, int* s_warp) {
-  if (ctx.maxnum[c] >= ctx.n[c]) return (flag & kFlagCand) != 0;   // the cap cannot bind (block-uniform branch)
-  // counted features in previous blocks of this cloud
-  int before = 0;
-  if (threadIdx.x < 32) {
-    const int* cntbuf = ctx.blk_count + (ctx.st->outer & 1) * ctx.blk_cap;
-    for (int bb = ctx.blk_off[c] + (int)threadIdx.x; bb < b; bb += 32) before += cntbuf[bb];
-    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-  }
-  const unsigned ballot = __ballot_sync(0xffffffffu, (flag & kFlagCounted) != 0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_warp[1 + warp] = __popc(ballot);
-  if (threadIdx.x == 0) s_warp[0] = before;
-  __syncthreads();
-  int prefix = s_warp[0];
-  for (int wi = 0; wi < warp; ++wi) prefix += s_warp[1 + wi];
-  prefix += __popc(ballot & ((1u << lane) - 1u));
-  __syncthreads();                                   // s_warp is reused by the next feature block of the caller's loop
-  return (flag & kFlagCand) && (prefix < ctx.maxnum[c]);
-}
-
-// One evaluation pass of the whole problem at st->evalq (all blocks) + reduction + solver (last block).
-// Returns true in the block that ran the solver (the state has been written back to global memory).
-template <bool kFirst>
-__device__ __forceinline__ bool eval_body(const DeviceCtx& ctx) {
-  FrameState* st = ctx.st;
-  __shared__ double s_red[kBlk / 32][32];
-  __shared__ int s_cnt[kBlk / 32][4];
-  __shared__ double s_tot[kNRed];
-  __shared__ double s_gather[kEvalCluster][kNRed];   // only the cluster's block 0 receives (DSMEM stores of its peers)
-  __shared__ int s_warp[1 + kBlk / 32];
-  __shared__ bool s_last;
-  cluster_arrive();                                  // "I have started": peers may store into my shared memory
-  unsigned long long tg0 = 0;
-  if (ctx.dbg && threadIdx.x == 0) { tg0 = gtime_ns(); atomicMin(&ctx.dbg[0], tg0); }
-  const int b = blockIdx.x;
-  // per-thread accumulators: H (21), g (6), cost, slot sum per cloud (4); factor count per cloud (ints)
-  double v[32];
-  int nact[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = 0.0;
-  Pose7 ev;                      // read around L1 (written by the previous launch's solver block)
-  ev.qw = __ldcg(&st->evalq.qw); ev.qx = __ldcg(&st->evalq.qx); ev.qy = __ldcg(&st->evalq.qy); ev.qz = __ldcg(&st->evalq.qz);
-  ev.tx = __ldcg(&st->evalq.tx); ev.ty = __ldcg(&st->evalq.ty); ev.tz = __ldcg(&st->evalq.tz);
-  const Rt T = pose_to_rt(ev);
-  // grid-stride over the 128-feature blocks (the grid is capped so that the final partial sum stays short)
-  for (int fb = b; fb < ctx.blk_off[4]; fb += gridDim.x) {
-    const int c = cloud_of_block(ctx, fb);
-    const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
-    const int gi = ctx.pad_off[c] + il;
-    bool act;
-    if (kFirst) {
-      act = compute_active(ctx, fb, c, ctx.flags[gi], s_warp);
-      ctx.active[gi] = act ? 1 : 0;
-    } else {
-      act = __ldcg(&ctx.active[gi]) != 0;
-    }
-    if (!act) continue;
-    double cpt[3];
-    rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], cpt[0], cpt[1], cpt[2]);
-    const double w = ctx.w[gi];
-    double r[3], J[18];
-    int nr;
-    double slot;
-    if (c == kPlanar || c == kGround) {
-      const double n[3] = {ctx.prim[0][gi], ctx.prim[1][gi], ctx.prim[2][gi]};
-      functor_plane(cpt, n, ctx.prim[3][gi], w, r[0], J);
-      nr = 1;
-      slot = r[0] * r[0];                                                    // :101
-    } else if (c == kEdge) {
-      const double a[3] = {ctx.prim[0][gi], ctx.prim[1][gi], ctx.prim[2][gi]};
-      const double bb[3] = {ctx.prim[3][gi], ctx.prim[4][gi], ctx.prim[5][gi]};
-      functor_line(cpt, a, bb, w, r, J);
-      nr = 3;
-      const double s3 = r[0] + r[1] + r[2];
-      slot = s3 * s3;                                                        // :69 (Q3)
-    } else {
-      const double q[3] = {ctx.prim[0][gi], ctx.prim[1][gi], ctx.prim[2][gi]};
-      functor_point(cpt, q, w, r, J);
-      nr = 3;
-      const double s3 = r[0] + r[1] + r[2];
-      slot = s3 * s3;                                                        // :32 (Q3)
-    }
-    ctx.slot[gi] = slot;                                                     // *cost side effect (Q5)
-    double sq = 0.0;
-    for (int k = 0; k < nr; ++k) sq += r[k] * r[k];
-    // CauchyLoss(1.0): rho = log(1+s), rho' = 1/(1+s), rho'' < 0 => residual and Jacobian scaled by sqrt(rho')
-    const double sum = 1.0 + sq;
-    const double rho1 = fmax(DBL_MIN, 1.0 / sum);
-    const double sc = sqrt(rho1);
-    v[27] += 0.5 * log(sum);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { v[28 + k] += (k == c) ? slot : 0.0; nact[k] += (k == c) ? 1 : 0; }
-    for (int k = 0; k < nr; ++k) {
-      double row[6];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) row[j] = J[k * 6 + j] * sc;
-      const double rk = r[k] * sc;
-      int t = 0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = i; j < 6; ++j) v[t++] += row[i] * row[j];
-        v[21 + i] += row[i] * rk;
-      }
-    }
-  }
-  // ---- block reduction (fixed shape => run-to-run bit-reproducible) ----
-  // warp level: butterfly "transpose" reduction -- 32 values across 32 lanes in 16+8+4+2+1 = 31 shuffles
-  // (instead of 5 per value); afterwards lane L holds the warp total of value L.
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const bool up = (lane & o) != 0;
-#pragma unroll
-      for (int i = 0; i < o; ++i) {
-        const double send = up ? v[i] : v[i + o];
-        const double keep = up ? v[i + o] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-      }
-    }
-    s_red[warp][lane] = v[0];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int tot_k = __reduce_add_sync(0xffffffffu, nact[k]);
-      if (lane == 0) s_cnt[warp][k] = tot_k;
-    }
-  }
-  __syncthreads();
-  // ---- cluster level: the 8 blocks of a cluster push their 36 block totals into block 0's shared memory ----
-  cluster_wait();                                     // every block of the cluster is running
-  const unsigned crank = cluster_rank();
-  if (threadIdx.x < kNRed) {
-    const int t = threadIdx.x;
-    double s = 0.0;
-    if (t < 32) {
-      for (int wi = 0; wi < kBlk / 32; ++wi) s += s_red[wi][t];
-    } else {
-      int n = 0;
-      for (int wi = 0; wi < kBlk / 32; ++wi) n += s_cnt[wi][t - 32];
-      s = (double)n;
-    }
-    dsmem_store(&s_gather[crank][t], 0u, s);
-  }
-  cluster_arrive();                                   // release: my stores are visible to whoever waits
-  cluster_wait();
-  if (crank != 0u) return false;
-  const unsigned nclusters = gridDim.x / kEvalCluster;
-  if (threadIdx.x < kNRed) {
-    const int t = threadIdx.x;
-    double s = s_gather[0][t];
-#pragma unroll
-    for (int r = 1; r < kEvalCluster; ++r) s += s_gather[r][t];     // fixed order => deterministic
-    ctx.partial[(size_t)cluster_id() * kNRed + t] = s;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(ctx.counter, 1u);
-    s_last = (ticket == nclusters - 1u);
-  }
-  __syncthreads();
-  if (!s_last) return false;
-  pdl_release();
-  // ---- last cluster leader: deterministic sum of the per-cluster partials, then the solver state machine ----
-  __threadfence();
-  unsigned long long tg1 = 0, tg2 = 0, tg3 = 0;
-  if (ctx.dbg && threadIdx.x == 0) tg1 = gtime_ns();
-  __shared__ double s_part[3][kNRed];
-  __shared__ FrameState s_state;
-  __shared__ SolverShared s_solver;
-  {
-    // the state machine is a long dependent chain: run it on a shared-memory copy of the state
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_state);
-    for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = __ldcg(src + i);
-  }
-  if (threadIdx.x < 3 * kNRed) {
-    // 3 row groups x 36 columns, 8 independent accumulators each; the summation tree is fixed => deterministic
-    const int col = threadIdx.x % kNRed, grp = threadIdx.x / kNRed;
-    const int nb = (int)nclusters;
-    const double* P = ctx.partial + col;
-    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = grp; r < nb; r += 24) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = r + 3 * u;
-        if (row < nb) a[u] += __ldcg(P + (size_t)row * kNRed);
-      }
-    }
-    s_part[grp][col] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-  }
-  __syncthreads();
-  if (threadIdx.x < kNRed) s_tot[threadIdx.x] = (s_part[0][threadIdx.x] + s_part[1][threadIdx.x]) + s_part[2][threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *ctx.counter = 0u;
-    if (ctx.dbg) tg2 = gtime_ns();
-  }
-  solver_on_eval(ctx, &s_state, s_tot, &s_solver);      // all threads enter (3 helper warps + thread 0)
-  if (threadIdx.x == 0) {
-    if (ctx.dbg) {
-      tg3 = gtime_ns();
-      ctx.dbg[1] += tg1 - ctx.dbg[0];   // parallel phase: first block start -> last block arrives
-      ctx.dbg[2] += tg2 - tg1;          // final partial sum
-      ctx.dbg[3] += tg3 - tg2;          // solver state machine
-      ctx.dbg[4] += 1ull;
-      ctx.dbg[0] = ~0ull;
-    }
-  }
-  __syncthreads();
-  {
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&s_state);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st);
-    for (unsigned i = threadIdx.x; i < sizeof(FrameState) / 8; i += kBlk) dst[i] = src[i];
-  }
-  __syncthreads();
-  return true;
-}
-
-// Clusters of 8 blocks: the block totals are combined through distributed shared memory before they reach
-// global memory, so the serial tail sums 1/8 of the rows (40 instead of 315 at F = 40k).
-template <bool kFirst>
-__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk, 3) k_eval(const __grid_constant__ DeviceCtx ctx) {
-  pdl_prologue();
-  const FrameState* st = ctx.st;
-  if (st->frame_done || st->phase != (kFirst ? kPhaseIter0 : kPhaseCand)) return;     // grid-uniform
-  eval_body<kFirst>(ctx);
-}
-
-// ---- standalone caps kernel (used by the build_factors test entry point) ----
-__global__ void __launch_bounds__(kBlk) k_caps(const __grid_constant__ DeviceCtx ctx) {
-  __shared__ int s_warp[1 + kBlk / 32];
-  const int b = blockIdx.x;
-  const int c = cloud_of_block(ctx, b);
-  const int gi = ctx.pad_off[c] + (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
-  ctx.active[gi] = compute_active(ctx, b, c, ctx.flags[gi], s_warp) ? 1 : 0;
-}
-
-__global__ void k_set_pose(DeviceCtx ctx, Predict x6) {   // x6.m[0..5] = tangent
-  for (int i = threadIdx.x; i < ctx.blk_off[4]; i += blockDim.x) ctx.blk_count[i] = 0;
-  if (threadIdx.x != 0) return;
-  FrameState* st = ctx.st;
-  for (int i = 0; i < 6; ++i) st->x[i] = x6.m[i];
-  st->xq = se3_exp(st->x);
-  st->evalq = st->xq;
-  st->frame_done = 0; st->phase = kPhaseIter0; st->outer = 0; st->status = 0;
-}
-
-// ---- piecewise test kernels ----
-template <int K>
-__global__ void k_knn(GridDesc g, const double* origin, const double* q, unsigned nq, double r2, int* idx,
-                      double* d2, int* count) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  TopK<K> t;
-  knn_search<K>(g, q[3ull * i] - origin[0], q[3ull * i + 1] - origin[1], q[3ull * i + 2] - origin[2], r2, t);
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    idx[(size_t)i * K + j] = (t.pos[j] >= 0) ? t.idx[j] : -1;
-    d2[(size_t)i * K + j] = t.d2[j];
-  }
-  count[i] = t.count();
-}
-
-// getFitnessScore, ref: registration.cpp:257-296: 1-NN of the UNTRANSFORMED scan points within fitness_thres.
-__global__ void __launch_bounds__(kBlk) k_fitness(const __grid_constant__ DeviceCtx ctx, double r2, double* out /*[blocks][2]*/) {
-  const int b = blockIdx.x;
-  const int c = cloud_of_block(ctx, b);
-  const int il = (b - ctx.blk_off[c]) * kBlk + threadIdx.x;
-  const int gi = ctx.pad_off[c] + il;
-  double err = 0.0, cnt = 0.0;
-  if (il < ctx.n[c]) {
-    TopK<1> t;
-    knn_search<1>(ctx.grid[c], ctx.px[gi] - ctx.origin[0], ctx.py[gi] - ctx.origin[1], ctx.pz[gi] - ctx.origin[2], r2, t);
-    if (t.pos[0] >= 0) { err = t.d2[0]; cnt = 1.0; }
-  }
-  __shared__ double s_e[kBlk / 32], s_c[kBlk / 32];
-  for (int o = 16; o > 0; o >>= 1) { err += __shfl_xor_sync(0xffffffffu, err, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-  if ((threadIdx.x & 31) == 0) { s_e[threadIdx.x >> 5] = err; s_c[threadIdx.x >> 5] = cnt; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double e = 0, n = 0;
-    for (int wi = 0; wi < kBlk / 32; ++wi) { e += s_e[wi]; n += s_c[wi]; }
-    out[2 * b] = e; out[2 * b + 1] = n;
-  }
-}
-
-__global__ void k_functor(int type, Predict x6, unsigned m, const double* p, const double* a, const double* bq,
-                          const double* w, double* r, double* J, double* cost) {
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const Rt T = pose_to_rt(se3_exp(x6.m));
-  double c[3];
-  rt_apply(T, p[3ull * i], p[3ull * i + 1], p[3ull * i + 2], c[0], c[1], c[2]);
-  if (type == 0) {          // point-to-point: a = target q
-    double rr[3], JJ[18];
-    const double q[3] = {a[3ull * i], a[3ull * i + 1], a[3ull * i + 2]};
-    functor_point(c, q, w[i], rr, JJ);
-    for (int k = 0; k < 3; ++k) r[3ull * i + k] = rr[k];
-    for (int k = 0; k < 18; ++k) J[18ull * i + k] = JJ[k];
-    cost[i] = (rr[0] + rr[1] + rr[2]) * (rr[0] + rr[1] + rr[2]);
-  } else if (type == 1) {   // point-to-line: a, bq = line points
-    double rr[3], JJ[18];
-    const double la[3] = {a[3ull * i], a[3ull * i + 1], a[3ull * i + 2]};
-    const double lb[3] = {bq[3ull * i], bq[3ull * i + 1], bq[3ull * i + 2]};
-    functor_line(c, la, lb, w[i], rr, JJ);
-    for (int k = 0; k < 3; ++k) r[3ull * i + k] = rr[k];
-    for (int k = 0; k < 18; ++k) J[18ull * i + k] = JJ[k];
-    cost[i] = (rr[0] + rr[1] + rr[2]) * (rr[0] + rr[1] + rr[2]);
-  } else {                  // point-to-plane: a = normal, bq = d
-    double rr, JJ[6];
-    const double n[3] = {a[3ull * i], a[3ull * i + 1], a[3ull * i + 2]};
-    functor_plane(c, n, bq[i], w[i], rr, JJ);
-    r[i] = rr;
-    for (int k = 0; k < 6; ++k) J[6ull * i + k] = JJ[k];
-    cost[i] = rr * rr;
-  }
-}
-
-__global__ void k_se3(int op, Predict in, double* out) {
-  if (threadIdx.x != 0) return;
-  if (op == 0) { pose_to_matrix(se3_exp(in.m), out); }
-  else if (op == 1) { Pose7 p; const bool ok = pose_from_matrix(in.m, p); se3_log(p, out); out[6] = ok ? 1.0 : 0.0; }
-  else { se3_log(se3_mul(se3_exp(in.m + 6), se3_exp(in.m)), out); }   // plus: in.m[0..5] = x, in.m[6..11] = delta
-}
-
-}  // namespace tloam
 
 // =================================================================================================
 // Host side: handle + C ABI
@@ -814,7 +54,7 @@ struct tloam_b200_handle {
   unsigned char* d_flags = nullptr;                             // flags + active
   int* d_blk_count = nullptr; double* d_partial = nullptr; size_t cap_blocks = 0;
   unsigned* d_counter = nullptr;
-  FrameState* d_state = nullptr;
+  FrameState* d_state = nullptr; bool own_state = true;         // a batch owns the states of its handles (one array)
   tloam_b200_stats* d_stats = nullptr;
   // target
   size_t n_tgt[4] = {0, 0, 0, 0};
@@ -831,7 +71,8 @@ struct tloam_b200_handle {
   // whole-frame CUDA graph (re-captured only when the device context changes)
   Predict* h_predict = nullptr; Predict* d_predict = nullptr;
   cudaGraphExec_t gexec = nullptr; DeviceCtx gctx; bool gvalid = false; int glaunches = 0; bool use_graph = true;
-  bool use_pdl = false;     // programmatic dependent launch between the frame kernels: measured no faster inside the graph (opt-in)
+  bool use_fused = true;    // k_first (search + fit + first evaluation in one kernel) whenever no cap can bind
+  bool gfused = false;      // topology of the instantiated graph
   // optional per-kernel-class timing (CUDA events around every launch; off by default)
   bool profiling = false;
   bool traced_last = false;
@@ -876,19 +117,13 @@ struct LaunchScope {
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
-template <typename K>
-static cudaError_t launch_pdl(K kernel, int grid, int block, cudaStream_t stream, const DeviceCtx& c, bool pdl) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, c);
+// per-sequence grids (the same function of the cloud sizes in single and batched mode => identical reduction trees)
+static int eval_grid_of(int nb) {      // k_eval: grid-stride over the feature blocks, a whole number of clusters
+  return ((nb < kEvalGridCap ? nb : kEvalGridCap) + kEvalCluster - 1) / kEvalCluster * kEvalCluster;
 }
-
-
+static int first_grid_of(int nb) {     // k_first: one block per 64 features, rounded up to the cluster size
+  return (2 * nb + kEvalCluster - 1) / kEvalCluster * kEvalCluster;
+}
 
 extern "C" {
 
@@ -901,6 +136,7 @@ void tloam_b200_default_config(tloam_tls_config* c) {   // ref: config/mapping/l
   c->fitness_thres = 0.02;
   c->ceres_max_num_iterations = 4;
   c->reinit_dir[0] = 1.0; c->reinit_dir[1] = 1.0; c->reinit_dir[2] = 1.0;
+  c->initial_trust_region_radius = 1e4;
 }
 
 const char* tloam_b200_status_string(int s) {
@@ -927,7 +163,7 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   *out = nullptr;
   if (cfg->factor_num < 2 || cfg->factor_num > 4 || cfg->max_iterations < 1 ||
       cfg->max_iterations > TLOAM_B200_MAX_OUTER || cfg->ceres_max_num_iterations < 0 ||
-      cfg->ceres_max_num_iterations > TLOAM_B200_MAX_INNER)
+      cfg->ceres_max_num_iterations > TLOAM_B200_MAX_INNER || !(cfg->initial_trust_region_radius > 0.0))
     return TLOAM_B200_ERR_INVALID_ARG;
   for (int c = 0; c < 4; ++c) if (!(radius_of(*cfg, c) > 0.0)) return TLOAM_B200_ERR_INVALID_ARG;
   int ndev = 0;
@@ -959,10 +195,14 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMallocHost(&h->h_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
-  { const char* e = getenv("TLOAM_B200_PDL"); h->use_pdl = (e && e[0] == '1'); }
+  { const char* e = getenv("TLOAM_B200_NO_FUSE"); h->use_fused = !(e && e[0] == '1'); }
   if (kEvalCluster > 8) {                          // cluster sizes above 8 are "non-portable": opt in per kernel
-    if (cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-        cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_eval<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_eval<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_eval<true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_eval<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_first<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+        cudaFuncSetAttribute(k_first<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
       return fail(TLOAM_B200_ERR_CUDA);
   }
   // identity curr/last pose (the reference leaves them uninitialised until the first scanMatching)
@@ -983,7 +223,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_stage_src); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
-  cudaFree(h->d_partial); cudaFree(h->d_counter); cudaFree(h->d_state); cudaFree(h->d_stats);
+  cudaFree(h->d_partial); cudaFree(h->d_counter); if (h->own_state) cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
   cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
   cudaFree(h->d_up); cudaFree(h->d_vox); cudaFree(h->d_pose); cudaFree(h->d_fe);
@@ -1014,6 +254,7 @@ static void fill_ctx_config(tloam_b200_handle* h) {
   c.edge_dir_thres = f.edge_dir_thres; c.cost_threshold = f.cost_threshold; c.gnc_factor = f.gnc_factor;
   c.noise_bound = f.noise_bound; c.fitness_thres = f.fitness_thres;
   for (int k = 0; k < 3; ++k) c.reinit_dir[k] = f.reinit_dir[k];
+  c.initial_radius = f.initial_trust_region_radius;
   c.st = h->d_state; c.stats = h->d_stats; c.counter = h->d_counter;
 }
 
@@ -1310,19 +551,34 @@ static int check_ready(tloam_b200_handle* h) {
   return TLOAM_B200_OK;
 }
 
+// true when no `*_maxnum` cap can bind for any enabled cloud: the fused first evaluation (k_first) applies
+static bool caps_cannot_bind(const tloam_b200_handle* h) {
+  const DeviceCtx& c = h->ctx;
+  for (int k = 0; k < 4; ++k) {
+    const bool enabled = (k == kPlanar || k == kGround) ? true : (k == kEdge ? c.factor_num >= 3 : c.factor_num == 4);
+    if (enabled && c.maxnum[k] < c.n[k]) return false;
+  }
+  return true;
+}
+
+static BatchTab no_batch() { BatchTab t; memset(&t, 0, sizeof(t)); t.S = 1; return t; }
+
 // enqueues the frame's fixed launch sequence on h->stream (also used under stream capture)
-static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c) {
+static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c, bool fused) {
   const int nb = h->total_blocks;
-  // k_eval is grid-stride over the feature blocks; its grid is a whole number of clusters
-  const int ne = ((nb < kEvalGridCap ? nb : kEvalGridCap) + kEvalCluster - 1) / kEvalCluster * kEvalCluster;
+  const int ne = eval_grid_of(nb), nf = first_grid_of(nb);
+  const BatchTab nt = no_batch();
   CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
-  TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<<<1, 256, 0, h->stream>>>(c, h->d_predict)));
+  TL_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<false><<<1, 256, 0, h->stream>>>(c, nt, h->d_predict)));
   for (int outer = 0; outer < h->cfg.max_iterations; ++outer) {
-    const bool pdl = h->use_pdl && !h->profiling;
-    TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (launch_pdl(k_correspond, nb * 2, kBlk, h->stream, c, pdl)));
-    TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (launch_pdl(k_eval<true>, ne, kBlk, h->stream, c, pdl)));
+    if (fused) {
+      TL_LAUNCH(TLOAM_B200_K_FIRST, (k_first<false><<<nf, kBlk, 0, h->stream>>>(c, nt)));
+    } else {
+      TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<false><<<nb * 2, kBlk, 0, h->stream>>>(c, nt)));
+      TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true, false><<<ne, kBlk, 0, h->stream>>>(c, nt)));
+    }
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
-      TL_LAUNCH(TLOAM_B200_K_EVAL, (launch_pdl(k_eval<false>, ne, kBlk, h->stream, c, pdl)));
+      TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false, false><<<ne, kBlk, 0, h->stream>>>(c, nt)));
   }
   // result[16] + {frame_done, status}: contiguous in FrameState
   CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double) + 2 * sizeof(int),
@@ -1366,16 +622,17 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   else h->h_predict->from_state = 1.0;
   DeviceCtx c = h->ctx;
   if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
-  const int per_frame = 1 + h->cfg.max_iterations * (2 + h->cfg.ceres_max_num_iterations);
+  const bool fused = h->use_fused && caps_cannot_bind(h);
+  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + h->cfg.ceres_max_num_iterations);
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
-    if (!h->gvalid || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0) {
+    if (!h->gvalid || h->gfused != fused || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0) {
       h->gvalid = false;
       cudaGraph_t graph = nullptr;
       CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       const long long l0 = h->launches;
-      const int erc = enqueue_frame(h, c);
+      const int erc = enqueue_frame(h, c, fused);
       h->launches = l0;                           // capture does not execute anything
       cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       if (erc != TLOAM_B200_OK || ce != cudaSuccess || !graph) {
@@ -1387,7 +644,7 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       // same topology, new kernel parameters / grid sizes (cloud sizes change from frame to frame in a real
       // stream): update the instantiated graph in place, which is much cheaper than instantiating a new one
       bool updated = false;
-      if (h->gexec) {
+      if (h->gexec && h->gfused == fused) {
         cudaGraphExecUpdateResultInfo info;
         updated = cudaGraphExecUpdate(h->gexec, graph, &info) == cudaSuccess;
         if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -1396,12 +653,13 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
       h->gctx = c;
+      h->gfused = fused;
       h->gvalid = true;
     }
     CU_TRY(cudaGraphLaunch(h->gexec, h->stream));
     h->launches += per_frame;
   } else {
-    const int erc = enqueue_frame(h, c);
+    const int erc = enqueue_frame(h, c, fused);
     if (erc != TLOAM_B200_OK) return erc;
     CU_TRY(cudaGetLastError());
   }
@@ -1491,6 +749,298 @@ int tloam_b200_get_pose_increment(tloam_b200_handle* h, double pose[16]) {   // 
   return TLOAM_B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Batched registration: S independent sequences stepped together, ONE launch sequence per batch frame.
+// A single 40k-feature frame is 8.5 warps per SM and every evaluation ends in a ~9 us serial tail on one SM
+// (DESIGN.md section 4); batching fills the machine with the sequences' parallel phases and runs their tails
+// concurrently.  Each sequence keeps its own handle (map, scan, pose history, submap); only the frame kernels
+// are shared.  Poses are bit-identical to registering each sequence alone (same per-sequence reduction tree).
+// ---------------------------------------------------------------------------------------------
+struct tloam_b200_batch {
+  int S = 0, device = 0;
+  std::vector<tloam_b200_handle*> hs;
+  cudaStream_t stream = nullptr;
+  FrameState* d_states = nullptr;
+  DeviceCtx* d_ctxs = nullptr;
+  std::vector<DeviceCtx> ctx_sent;   bool ctx_valid = false;
+  Predict* h_pred = nullptr; Predict* d_pred = nullptr;
+  unsigned char* h_results = nullptr;          // pinned [S][kResultBytes]
+  cudaEvent_t ev_done = nullptr, ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_ready;
+  cudaGraphExec_t gexec = nullptr;
+  BatchTab g_first, g_corr, g_eval; bool gfused = false, gvalid = false;
+  bool use_graph = true, use_fused = true, pending = false;
+  long long launches = 0; int launches_frame = 0;
+  char last_error[512] = {0};
+  // optional per-kernel-class timing (CUDA events around every launch of the batch frame; no graph in this mode)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_next = 0;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  tloam_b200_profile prof;
+};
+struct BatchLaunchScope {
+  tloam_b200_batch* b; int cls; cudaEvent_t a = nullptr, e = nullptr;
+  BatchLaunchScope(tloam_b200_batch* bb, int c) : b(bb), cls(c) {
+    if (b->profiling) {
+      while (b->ev_pool.size() < b->ev_next + 2) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) { b->profiling = false; return; } b->ev_pool.push_back(ev); }
+      a = b->ev_pool[b->ev_next++]; e = b->ev_pool[b->ev_next++];
+      cudaEventRecord(a, b->stream);
+    }
+  }
+  ~BatchLaunchScope() { if (a && e) { cudaEventRecord(e, b->stream); b->spans.push_back({cls, a, e}); } }
+};
+#define TLB_LAUNCH(cls, ...) do { BatchLaunchScope ls__(b, cls); __VA_ARGS__; } while (0)
+static constexpr size_t kResultBytes = 16 * sizeof(double) + 2 * sizeof(int);   // result + {frame_done, status}
+
+#define CUB_TRY(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      snprintf(b->last_error, sizeof(b->last_error), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+               __FILE__, __LINE__);                                                                    \
+      return TLOAM_B200_ERR_CUDA;                                                                      \
+    }                                                                                                  \
+  } while (0)
+
+int tloam_b200_batch_destroy(tloam_b200_batch* b) {
+  if (!b) return TLOAM_B200_OK;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (tloam_b200_handle* h : b->hs) tloam_b200_destroy(h);
+  if (b->gexec) cudaGraphExecDestroy(b->gexec);
+  cudaFree(b->d_states); cudaFree(b->d_ctxs); cudaFree(b->d_pred);
+  if (b->h_pred) cudaFreeHost(b->h_pred);
+  if (b->h_results) cudaFreeHost(b->h_results);
+  for (cudaEvent_t e : b->ev_ready) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
+  if (b->ev_done) cudaEventDestroy(b->ev_done);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_batch_create(const tloam_tls_config* cfg, int device, int S, tloam_b200_batch** out) {
+  if (!cfg || !out || S < 1 || S > kMaxBatch) return TLOAM_B200_ERR_INVALID_ARG;
+  *out = nullptr;
+  tloam_b200_batch* b = new (std::nothrow) tloam_b200_batch();
+  if (!b) return TLOAM_B200_ERR_INVALID_ARG;
+  b->S = S; b->device = device;
+  auto fail = [&](int code) { tloam_b200_batch_destroy(b); return code; };
+  for (int s = 0; s < S; ++s) {
+    tloam_b200_handle* h = nullptr;
+    const int rc = tloam_b200_create(cfg, device, nullptr, &h);     // own non-blocking stream: map builds of the sequences overlap
+    if (rc != TLOAM_B200_OK) return fail(rc);
+    b->hs.push_back(h);
+  }
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMalloc(&b->d_states, S * sizeof(FrameState)) != cudaSuccess || cudaMalloc(&b->d_ctxs, S * sizeof(DeviceCtx)) != cudaSuccess ||
+      cudaMalloc(&b->d_pred, S * sizeof(Predict)) != cudaSuccess || cudaMallocHost(&b->h_pred, S * sizeof(Predict)) != cudaSuccess ||
+      cudaMallocHost(&b->h_results, S * kResultBytes) != cudaSuccess)
+    return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&b->ev0) != cudaSuccess ||
+      cudaEventCreate(&b->ev1) != cudaSuccess)
+    return fail(TLOAM_B200_ERR_CUDA);
+  for (int s = 0; s < S; ++s) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+    b->ev_ready.push_back(e);
+    // the sequences' frame states live in ONE array (one strided D2H copy fetches every result)
+    tloam_b200_handle* h = b->hs[s];
+    if (cudaMemcpy(b->d_states + s, h->d_state, sizeof(FrameState), cudaMemcpyDeviceToDevice) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+    cudaFree(h->d_state);
+    h->d_state = b->d_states + s; h->own_state = false;
+  }
+  { const char* e = getenv("TLOAM_B200_NO_GRAPH"); b->use_graph = !(e && e[0] == '1'); }
+  { const char* e = getenv("TLOAM_B200_NO_FUSE"); b->use_fused = !(e && e[0] == '1'); }
+  *out = b;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_batch_size(tloam_b200_batch* b) { return b ? b->S : 0; }
+tloam_b200_handle* tloam_b200_batch_handle(tloam_b200_batch* b, int i) { return (b && i >= 0 && i < b->S) ? b->hs[i] : nullptr; }
+const char* tloam_b200_batch_last_error(tloam_b200_batch* b) { return b ? b->last_error : ""; }
+long long tloam_b200_batch_launch_count(tloam_b200_batch* b) {
+  if (!b) return 0;
+  long long n = b->launches;
+  for (tloam_b200_handle* h : b->hs) n += h->launches;
+  return n;
+}
+
+static int batch_set(tloam_b200_batch* b, const double* const* xyz, const size_t* n, bool target, bool on_device) {
+  if (!b || !xyz || !n) return TLOAM_B200_ERR_INVALID_ARG;
+  for (int s = 0; s < b->S; ++s) {
+    const int rc = target ? set_target_impl(b->hs[s], xyz + 4 * s, n + 4 * s, on_device) : set_source_impl(b->hs[s], xyz + 4 * s, n + 4 * s, on_device);
+    if (rc != TLOAM_B200_OK) {
+      snprintf(b->last_error, sizeof(b->last_error), "sequence %d: %.400s", s, b->hs[s]->last_error);
+      return rc;
+    }
+  }
+  return TLOAM_B200_OK;
+}
+int tloam_b200_batch_set_target(tloam_b200_batch* b, const double* const* xyz, const size_t* n) { return batch_set(b, xyz, n, true, false); }
+int tloam_b200_batch_set_source(tloam_b200_batch* b, const double* const* xyz, const size_t* n) { return batch_set(b, xyz, n, false, false); }
+int tloam_b200_batch_set_target_device(tloam_b200_batch* b, const double* const* xyz, const size_t* n) { return batch_set(b, xyz, n, true, true); }
+int tloam_b200_batch_set_source_device(tloam_b200_batch* b, const double* const* xyz, const size_t* n) { return batch_set(b, xyz, n, false, true); }
+
+static int batch_enqueue_frame(tloam_b200_batch* b, bool fused, const tloam_tls_config& cfg) {
+  static const DeviceCtx zero_ctx = {};
+  const int S = b->S;
+  CUB_TRY(cudaMemcpyAsync(b->d_pred, b->h_pred, S * sizeof(Predict), cudaMemcpyHostToDevice, b->stream));
+  TLB_LAUNCH(TLOAM_B200_K_BEGIN_FRAME, (k_begin_frame<true><<<S, 256, 0, b->stream>>>(zero_ctx, b->g_eval, b->d_pred)));
+  for (int outer = 0; outer < cfg.max_iterations; ++outer) {
+    if (fused) {
+      TLB_LAUNCH(TLOAM_B200_K_FIRST, (k_first<true><<<b->g_first.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_first)));
+    } else {
+      TLB_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<true><<<b->g_corr.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_corr)));
+      TLB_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true, true><<<b->g_eval.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_eval)));
+    }
+    for (int it = 0; it < cfg.ceres_max_num_iterations; ++it)
+      TLB_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false, true><<<b->g_eval.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_eval)));
+  }
+  CUB_TRY(cudaGetLastError());
+  // every sequence's result[16] + {frame_done, status} with ONE strided copy
+  CUB_TRY(cudaMemcpy2DAsync(b->h_results, kResultBytes, (const char*)b->d_states + offsetof(FrameState, result), sizeof(FrameState),
+                            kResultBytes, S, cudaMemcpyDeviceToHost, b->stream));
+  return TLOAM_B200_OK;
+}
+
+// predicts: S x 16 doubles (4x4 column-major each), or NULL = device-side constant-velocity prediction per sequence
+int tloam_b200_batch_scan_match_async(tloam_b200_batch* b, const double* predicts) {
+  if (!b) return TLOAM_B200_ERR_INVALID_ARG;
+  const int S = b->S;
+  for (int s = 0; s < S; ++s) {
+    const int rc = check_ready(b->hs[s]);
+    if (rc != TLOAM_B200_OK) { snprintf(b->last_error, sizeof(b->last_error), "sequence %d is not ready", s); return rc; }
+  }
+  CUB_TRY(cudaSetDevice(b->device));
+  const tloam_tls_config& cfg = b->hs[0]->cfg;
+  // the frame kernels run behind everything the sequences have enqueued on their own streams (map build, staging)
+  std::vector<DeviceCtx> ctxs(S);
+  BatchTab tf, tc, te;
+  memset(&tf, 0, sizeof(tf)); memset(&tc, 0, sizeof(tc)); memset(&te, 0, sizeof(te));
+  tf.S = tc.S = te.S = S; tf.ctxs = tc.ctxs = te.ctxs = b->d_ctxs;
+  bool fused = b->use_fused;
+  for (int s = 0; s < S; ++s) {
+    tloam_b200_handle* h = b->hs[s];
+    CUB_TRY(cudaEventRecord(b->ev_ready[s], h->stream));
+    CUB_TRY(cudaStreamWaitEvent(b->stream, b->ev_ready[s], 0));
+    ctxs[s] = h->ctx;
+    ctxs[s].stats = nullptr; ctxs[s].dbg = nullptr;
+    fused = fused && caps_cannot_bind(h);
+    const int nb = h->total_blocks;
+    tf.off[s + 1] = tf.off[s] + first_grid_of(nb);
+    tc.off[s + 1] = tc.off[s] + 2 * nb;
+    te.off[s + 1] = te.off[s] + eval_grid_of(nb);
+    if (predicts) { memcpy(b->h_pred[s].m, predicts + 16 * s, 16 * sizeof(double)); b->h_pred[s].from_state = 0.0; }
+    else b->h_pred[s].from_state = 1.0;
+  }
+  if (!b->ctx_valid || memcmp(b->ctx_sent.data(), ctxs.data(), S * sizeof(DeviceCtx)) != 0) {
+    CUB_TRY(cudaMemcpyAsync(b->d_ctxs, ctxs.data(), S * sizeof(DeviceCtx), cudaMemcpyHostToDevice, b->stream));   // pageable source: staged before return
+    b->ctx_sent = ctxs; b->ctx_valid = true;
+  }
+  const int per_frame = 1 + cfg.max_iterations * ((fused ? 1 : 2) + cfg.ceres_max_num_iterations);
+  CUB_TRY(cudaEventRecord(b->ev0, b->stream));
+  if (b->use_graph && !b->profiling) {
+    const bool same = b->gvalid && b->gfused == fused && memcmp(&b->g_first, &tf, sizeof(tf)) == 0 &&
+                      memcmp(&b->g_corr, &tc, sizeof(tc)) == 0 && memcmp(&b->g_eval, &te, sizeof(te)) == 0;
+    if (!same) {
+      b->gvalid = false;
+      b->g_first = tf; b->g_corr = tc; b->g_eval = te;
+      cudaGraph_t graph = nullptr;
+      CUB_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+      const int erc = batch_enqueue_frame(b, fused, cfg);
+      cudaError_t ce = cudaStreamEndCapture(b->stream, &graph);
+      if (erc != TLOAM_B200_OK || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (erc == TLOAM_B200_OK) snprintf(b->last_error, sizeof(b->last_error), "graph capture failed: %s", cudaGetErrorString(ce));
+        return TLOAM_B200_ERR_CUDA;
+      }
+      bool updated = false;
+      if (b->gexec && b->gfused == fused) {
+        cudaGraphExecUpdateResultInfo info;
+        updated = cudaGraphExecUpdate(b->gexec, graph, &info) == cudaSuccess;
+        if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+      } else if (b->gexec) { cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
+      if (!updated) ce = cudaGraphInstantiate(&b->gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { snprintf(b->last_error, sizeof(b->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
+      b->gfused = fused; b->gvalid = true;
+    }
+    CUB_TRY(cudaGraphLaunch(b->gexec, b->stream));
+  } else {
+    b->g_first = tf; b->g_corr = tc; b->g_eval = te;
+    const int erc = batch_enqueue_frame(b, fused, cfg);
+    if (erc != TLOAM_B200_OK) return erc;
+  }
+  CUB_TRY(cudaEventRecord(b->ev1, b->stream));
+  // whatever the sequences enqueue next on their own streams (the next map build overwrites the map in use) waits
+  CUB_TRY(cudaEventRecord(b->ev_done, b->stream));
+  for (int s = 0; s < S; ++s) CUB_TRY(cudaStreamWaitEvent(b->hs[s]->stream, b->ev_done, 0));
+  b->launches += per_frame; b->launches_frame = per_frame;
+  b->pending = true;
+  return TLOAM_B200_OK;
+}
+
+// results: S x 16 doubles; statuses: S ints (tloam_b200_status per sequence).  Returns OK when every sequence is OK,
+// else the first non-OK status.
+int tloam_b200_batch_get_results(tloam_b200_batch* b, double* results, int* statuses, float* gpu_ms) {
+  if (!b || !results) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!b->pending) return TLOAM_B200_ERR_NOT_READY;
+  CUB_TRY(cudaSetDevice(b->device));
+  CUB_TRY(cudaStreamSynchronize(b->stream));
+  b->pending = false;
+  int worst = TLOAM_B200_OK;
+  for (int s = 0; s < b->S; ++s) {
+    const unsigned char* r = b->h_results + s * kResultBytes;
+    memcpy(results + 16 * s, r, 16 * sizeof(double));
+    int flags[2];
+    memcpy(flags, r + 16 * sizeof(double), sizeof(flags));
+    int st = flags[1];
+    if (st == TLOAM_B200_OK && !flags[0]) st = TLOAM_B200_ERR_CUDA;      // the frame did not complete
+    if (statuses) statuses[s] = st;
+    if (worst == TLOAM_B200_OK && st != TLOAM_B200_OK) worst = st;
+  }
+  if (gpu_ms) { float ms = 0.f; if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *gpu_ms = ms; }
+  return worst;
+}
+
+int tloam_b200_batch_set_profiling(tloam_b200_batch* b, int on) {
+  if (!b) return TLOAM_B200_ERR_INVALID_ARG;
+  CUB_TRY(cudaSetDevice(b->device));
+  CUB_TRY(cudaStreamSynchronize(b->stream));
+  b->profiling = on != 0;
+  b->spans.clear(); b->ev_next = 0;
+  memset(&b->prof, 0, sizeof(b->prof));
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_batch_get_profile(tloam_b200_batch* b, tloam_b200_profile* out) {
+  if (!b || !out) return TLOAM_B200_ERR_INVALID_ARG;
+  CUB_TRY(cudaSetDevice(b->device));
+  CUB_TRY(cudaStreamSynchronize(b->stream));
+  for (const auto& sp : b->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess && sp.cls >= 0 && sp.cls < TLOAM_B200_K_COUNT) {
+      b->prof.launches[sp.cls] += 1;
+      b->prof.total_ms[sp.cls] += ms;
+    }
+  }
+  b->spans.clear(); b->ev_next = 0;
+  *out = b->prof;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_batch_scan_match(tloam_b200_batch* b, const double* predicts, double* results, int* statuses) {
+  const int rc = tloam_b200_batch_scan_match_async(b, predicts);
+  if (rc != TLOAM_B200_OK) return rc;
+  return tloam_b200_batch_get_results(b, results, statuses, nullptr);
+}
+
 int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse) {
   if (!h || !fitness || !rmse) return TLOAM_B200_ERR_INVALID_ARG;
   *fitness = 0.0; *rmse = 0.0;
@@ -1565,7 +1115,7 @@ int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6],
   DeviceCtx c = h->ctx;
   c.factor_num = 4;   // build every cloud regardless of the configured subset
   k_set_pose<<<1, 256, 0, h->stream>>>(c, pr);
-  k_correspond<<<h->total_blocks * 2, kBlk, 0, h->stream>>>(c);
+  k_correspond<false><<<h->total_blocks * 2, kBlk, 0, h->stream>>>(c, no_batch());
   k_caps<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
   h->launches += 3;
   CU_TRY(cudaGetLastError());

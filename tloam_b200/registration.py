@@ -61,20 +61,25 @@ class Frame:
 
 
 class LocalRegistration:
-    def __init__(self, config=None, device=0, stream=None, **overrides):
+    def __init__(self, config=None, device=0, stream=None, _borrowed=None, **overrides):
         self._L = _lib.load()
         self.cfg = config if config is not None else default_config(**overrides)
-        h = C.c_void_p()
-        rc = self._L.tloam_b200_create(C.byref(self.cfg), int(device), C.c_void_p(stream or 0), C.byref(h))
-        if rc != _lib.OK:
-            raise RegistrationError(rc, "tloam_b200_create")
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            h = C.c_void_p()
+            rc = self._L.tloam_b200_create(C.byref(self.cfg), int(device), C.c_void_p(stream or 0), C.byref(h))
+            if rc != _lib.OK:
+                raise RegistrationError(rc, "tloam_b200_create")
+        else:
+            h = C.c_void_p(_borrowed)     # a sequence of a BatchRegistration: the batch owns the handle
         self._h = h
         self._keep = []
         self.n_source = [0, 0, 0, 0]
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.tloam_b200_destroy(self._h)
+            if self._owned:
+                self._L.tloam_b200_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -347,3 +352,96 @@ class LocalRegistration:
         out = np.zeros(6)
         self._check(self._L.tloam_b200_se3_plus(self._h, _dp(x), _dp(d), _dp(out)), "se3_plus")
         return out
+
+
+class BatchRegistration:
+    """S independent sequences registered together (tloam_b200_batch_*): one launch sequence per batch frame.
+    `self.seq[i]` is a LocalRegistration view of sequence i (set_input_*, submap_*, get_transform ... per sequence);
+    scan_matching() steps all of them.  Per-sequence poses are bit-identical to the un-batched path."""
+
+    def __init__(self, S, config=None, device=0, **overrides):
+        self._L = _lib.load()
+        self.cfg = config if config is not None else default_config(**overrides)
+        self.S = int(S)
+        b = C.c_void_p()
+        rc = self._L.tloam_b200_batch_create(C.byref(self.cfg), int(device), self.S, C.byref(b))
+        if rc != _lib.OK:
+            raise RegistrationError(rc, "tloam_b200_batch_create")
+        self._b = b
+        self.seq = [LocalRegistration(config=self.cfg, _borrowed=self._L.tloam_b200_batch_handle(b, i)) for i in range(self.S)]
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_b", None):
+            for r in self.seq:
+                r.close()
+            self._L.tloam_b200_batch_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, where):
+        if rc != _lib.OK:
+            raise RegistrationError(rc, where, self._L.tloam_b200_batch_last_error(self._b).decode())
+
+    def pack_device(self, per_seq_tensors):
+        """Marshal S x 4 CUDA tensors once (outside a timed loop); pass the result to set_input_*_device."""
+        flat = [t for seq in per_seq_tensors for t in seq]
+        assert len(flat) == 4 * self.S
+        ptrs = (C.c_void_p * (4 * self.S))(*[int(t.data_ptr()) for t in flat])
+        ns = (C.c_size_t * (4 * self.S))(*[int(t.shape[0]) for t in flat])
+        return ptrs, ns, flat
+
+    def pack_host(self, per_seq_clouds):
+        flat = [_f64(c).reshape(-1, 3) for seq in per_seq_clouds for c in seq]
+        assert len(flat) == 4 * self.S
+        ptrs = (C.POINTER(C.c_double) * (4 * self.S))(*[_dp(a) for a in flat])
+        ns = (C.c_size_t * (4 * self.S))(*[a.shape[0] for a in flat])
+        return ptrs, ns, flat
+
+    def _set(self, fn, packed, what):
+        ptrs, ns, flat = packed
+        self._check(fn(self._b, ptrs, ns), what)
+        self._keep[what] = flat            # device inputs are read in place: keep them alive until replaced
+        if what.startswith("source"):
+            for i, r in enumerate(self.seq):
+                r.n_source = [int(ns[4 * i + c]) for c in range(4)]
+
+    def set_input_target_device(self, packed):
+        self._set(self._L.tloam_b200_batch_set_target_device, packed, "target_device")
+
+    def set_input_source_device(self, packed):
+        self._set(self._L.tloam_b200_batch_set_source_device, packed, "source_device")
+
+    def set_input_target(self, packed):
+        self._set(self._L.tloam_b200_batch_set_target, packed, "target")
+
+    def set_input_source(self, packed):
+        self._set(self._L.tloam_b200_batch_set_source, packed, "source")
+
+    def scan_matching(self, predicts=None):
+        """predicts: (S,4,4) or None (device-side constant-velocity prediction).  Returns (S,4,4) poses, statuses."""
+        out = np.zeros((self.S, 16))
+        st = np.zeros(self.S, dtype=np.int32)
+        p = None
+        if predicts is not None:
+            p = _f64(np.transpose(np.asarray(predicts).reshape(self.S, 4, 4), (0, 2, 1))).reshape(-1)
+        rc = self._L.tloam_b200_batch_scan_match(self._b, _dp(p) if p is not None else None, _dp(out),
+                                                 st.ctypes.data_as(C.POINTER(C.c_int)))
+        self._check(rc, "batch_scan_matching")
+        return np.transpose(out.reshape(self.S, 4, 4), (0, 2, 1)).copy(), st
+
+    def launch_count(self):
+        return int(self._L.tloam_b200_batch_launch_count(self._b))
+
+    def set_profiling(self, on):
+        self._check(self._L.tloam_b200_batch_set_profiling(self._b, 1 if on else 0), "batch_set_profiling")
+
+    def get_profile(self):
+        p = _lib.Profile()
+        self._check(self._L.tloam_b200_batch_get_profile(self._b, C.byref(p)), "batch_get_profile")
+        return {k: (int(p.launches[i]), float(p.total_ms[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
