@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtloam_b200.so")
+# TLOAM_B200_LIB: alternative build of the same library (A/B experiments with -D variants); never a different backend
+LIB_PATH = os.environ.get("TLOAM_B200_LIB") or os.path.join(HERE, "libtloam_b200.so")
 
 MAX_OUTER = 16
 MAX_INNER = 8
@@ -65,7 +66,7 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense")
 
 
 class FeatureConfig(C.Structure):

@@ -1,0 +1,389 @@
+// dense_search.cuh -- correspondence search for DENSE map clouds (BASELINE config 3: ~400 points per 0.5 m cell),
+// with TMA-staged point tiles.
+//
+// The lane-pair search of map_grid.cuh streams every candidate of the 27 neighbour cells through L1/L2: at 400
+// points per cell that is ~4000 candidates per query (3.0 ms per launch at F = 500k).  Here the QUERIES are binned
+// by map cell first (exact FP64 cell of T*p, counting sort through a small hash table: k_qbin_*), so that a thread
+// block owns up to 128 queries of ONE cell and therefore ONE 27-cell neighbourhood:
+//   1. warp 0 probes the 8 bricks of the neighbourhood and lists the <= 27 contiguous point runs;
+//   2. the runs are copied global -> shared memory by the TMA engine (cp.async.bulk ... mbarrier::complete_tx::bytes,
+//      one bulk copy per run, SASS UBLKCP), in passes of at most kDenseCap points;
+//   3. the staged points are counting-sorted IN SHARED MEMORY into a 12 x 12 x 12 grid of fine cells (edge = r / 4)
+//      covering the 3 x 3 x 3 cells;
+//   4. every thread searches its query nearest-first: the 27 fine cells around it, then only the fine cells that can
+//      still hold a point closer than the K-th best (box of the current reach, per-row lower bounds);
+//   5. fit + weight update exactly as k_correspond.
+// The result is the same exact radius-truncated kNN, ordered by (d2, original index), with the same FP64 distance
+// expression -- the path taken (dense or lane-pair) never changes a pose.  A point is visited in exactly one pass,
+// the top-K list persists across passes, and pruning only ever uses the current K-th best distance, so any number of
+// passes is exact.
+#pragma once
+#include "frame_kernels.cuh"
+
+namespace tloam {
+
+constexpr int kDenseBlk = 128;             // threads per block = queries per work item
+constexpr int kFine = 4;                   // fine cells per cell edge
+constexpr int kBox = 3 * kFine;            // fine cells per axis of the staged box
+constexpr int kBoxCells = kBox * kBox * kBox;
+constexpr int kDenseCap = 5120;            // staged points per pass (80 KB)
+
+struct DenseWork { int cx, cy, cz; unsigned qbeg; unsigned short qcnt; unsigned short cloud; };
+
+struct DenseCloud {
+  unsigned long long* keys;    // [tmask+1] cell keys (0 = empty)
+  unsigned* cnt;               // [tmask+1] queries per cell
+  unsigned* base;              // [tmask+1] first position of the cell in q_order
+  unsigned* q_slot;            // [n]
+  unsigned* q_rank;            // [n]
+  unsigned* q_order;           // [n] query indices grouped by cell
+  unsigned tmask;
+  unsigned toff;               // first slot of this cloud in the concatenated slot space of k_qbin_offsets
+};
+struct DenseArgs {
+  DenseCloud cl[4];
+  DenseWork* work;             // [sum n]
+  unsigned* ctl;               // [0] nwork, [1] next work item, [2..5] q_order bump allocators
+  unsigned tslots;             // total slots over the dense clouds
+  int mask;                    // bit c: cloud c takes the dense path
+};
+
+__device__ __forceinline__ void decode_cell_key(unsigned long long key, int& cx, int& cy, int& cz) {
+  cx = (int)((key >> 42) & 0x1FFFFFull) - (1 << 20);
+  cy = (int)((key >> 21) & 0x1FFFFFull) - (1 << 20);
+  cz = (int)(key & 0x1FFFFFull) - (1 << 20);
+}
+
+// ---- query binning: counting sort of the queries by the map cell of T*p ----
+__global__ void __launch_bounds__(kBlk) k_qbin_count(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
+  const FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != kPhaseIter0) return;
+  const int fb = blockIdx.x;
+  const int c = cloud_of_block(ctx, fb);
+  if (!((a.mask >> c) & 1) || !cloud_enabled(ctx, c)) return;
+  const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  if (il >= ctx.n[c]) return;
+  const int gi = ctx.pad_off[c] + il;
+  const Rt T = pose_to_rt(st->xq);
+  double qx, qy, qz;
+  rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
+  const GridDesc& g = ctx.grid[c];
+  const double rx = qx - ctx.origin[0], ry = qy - ctx.origin[1], rz = qz - ctx.origin[2];
+  const int cx = (int)floor(rx * g.inv_cell), cy = (int)floor(ry * g.inv_cell), cz = (int)floor(rz * g.inv_cell);   // as knn_search
+  const unsigned long long key = cell_key(cx, cy, cz);
+  const DenseCloud& q = a.cl[c];
+  unsigned s = hash_key(key) & q.tmask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(&q.keys[s], 0ull, key);
+    if (prev == 0ull || prev == key) break;
+    s = (s + 1u) & q.tmask;
+  }
+  q.q_slot[il] = s;
+  q.q_rank[il] = atomicAdd(&q.cnt[s], 1u);
+}
+
+// base offsets of the occupied query cells + the work list (one item per <= kDenseBlk queries of a cell)
+__global__ void __launch_bounds__(256) k_qbin_offsets(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
+  const FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != kPhaseIter0) return;
+  unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.tslots) return;
+  int c = 0;
+  for (int k = 0; k < 4; ++k)
+    if (((a.mask >> k) & 1) && s >= a.cl[k].toff) c = k;
+  const DenseCloud& q = a.cl[c];
+  s -= q.toff;
+  const unsigned cnt = q.cnt[s];
+  if (cnt == 0u) return;
+  const unsigned base = atomicAdd(&a.ctl[2 + c], cnt);
+  q.base[s] = base;
+  const unsigned nitems = (cnt + kDenseBlk - 1) / kDenseBlk;
+  const unsigned w0 = atomicAdd(&a.ctl[0], nitems);
+  int cx, cy, cz;
+  decode_cell_key(q.keys[s], cx, cy, cz);
+  for (unsigned i = 0; i < nitems; ++i) {
+    DenseWork wk;
+    wk.cx = cx; wk.cy = cy; wk.cz = cz;
+    wk.qbeg = base + i * kDenseBlk;
+    const unsigned rem = cnt - i * kDenseBlk;
+    wk.qcnt = (unsigned short)(rem < (unsigned)kDenseBlk ? rem : (unsigned)kDenseBlk);
+    wk.cloud = (unsigned short)c;
+    a.work[w0 + i] = wk;
+  }
+}
+
+__global__ void __launch_bounds__(kBlk) k_qbin_scatter(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
+  const FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != kPhaseIter0) return;
+  const int fb = blockIdx.x;
+  const int c = cloud_of_block(ctx, fb);
+  if (!((a.mask >> c) & 1) || !cloud_enabled(ctx, c)) return;
+  const int il = (fb - ctx.blk_off[c]) * kBlk + threadIdx.x;
+  if (il >= ctx.n[c]) return;
+  const DenseCloud& q = a.cl[c];
+  q.q_order[q.base[q.q_slot[il]] + q.q_rank[il]] = (unsigned)il;
+}
+
+// ---- top-K list that keeps the neighbours' stored coordinates (no re-load for the fit) ----
+template <int K>
+struct TopKP {
+  double d2[K];
+  int idx[K];
+  float x[K], y[K], z[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < K; ++j) { d2[j] = __longlong_as_double(0x7FF0000000000000ll); idx[j] = 0x7FFFFFFF; x[j] = y[j] = z[j] = 0.f; }
+  }
+  __device__ __forceinline__ int count() const {
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) c += (idx[j] != 0x7FFFFFFF) ? 1 : 0;
+    return c;
+  }
+  __device__ __forceinline__ void insert(double d, int i, float px, float py, float pz) {
+    bool lt[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) lt[j] = (d < d2[j]) || (d == d2[j] && i < idx[j]);
+    if (!lt[K - 1]) return;
+#pragma unroll
+    for (int j = K - 1; j >= 0; --j) {
+      const bool shift = (j > 0) ? lt[j - 1] : false;
+      if (j > 0 && shift) { d2[j] = d2[j - 1]; idx[j] = idx[j - 1]; x[j] = x[j - 1]; y[j] = y[j - 1]; z[j] = z[j - 1]; }
+      else if (lt[j]) { d2[j] = d; idx[j] = i; x[j] = px; y[j] = py; z[j] = pz; }
+    }
+  }
+};
+
+struct DenseSmem {
+  float4 pts[kDenseCap];
+  unsigned short order[kDenseCap];
+  unsigned start[kBoxCells + 1];
+  unsigned cursor[kBoxCells];
+  unsigned run_beg[27], run_cnt[27];
+  unsigned cp_src[32], cp_dst[32], cp_n[32];
+  unsigned scan_tmp[kDenseBlk / 32];
+  int ncopy, fill, run_i;
+  unsigned run_o, work;
+  unsigned long long mbar;
+};
+constexpr size_t kDenseSmemBytes = sizeof(DenseSmem) + 128;
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TL_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TL_DONE_%=;\n"
+      "bra TL_WAIT_%=;\n"
+      "TL_DONE_%=:\n"
+      "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// Persistent blocks; one work item (<= 128 queries of one map cell) per iteration.
+__global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
+  const FrameState* st = ctx.st;
+  if (st->frame_done || st->phase != kPhaseIter0) return;
+  extern __shared__ unsigned char dense_raw[];
+  DenseSmem& sm = *reinterpret_cast<DenseSmem*>((reinterpret_cast<uintptr_t>(dense_raw) + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) mbar_init(&sm.mbar, 1u);
+  __syncthreads();
+  unsigned parity = 0u;
+  const Rt T = pose_to_rt(st->xq);
+  const int buf = st->outer & 1;
+  const unsigned nwork = a.ctl[0];
+  while (true) {
+    if (tid == 0) sm.work = atomicAdd(&a.ctl[1], 1u);
+    __syncthreads();
+    const unsigned w = sm.work;
+    if (w >= nwork) break;
+    const DenseWork wk = a.work[w];
+    const int c = wk.cloud;
+    const GridDesc& g = ctx.grid[c];
+    // ---- the <= 27 point runs of the neighbourhood (warp 0: 8 brick probes, then one cell per lane) ----
+    if (warp == 0) {
+      const int bx0 = brick_of(wk.cx - 1), by0 = brick_of(wk.cy - 1), bz0 = brick_of(wk.cz - 1);
+      BrickEntry e;
+      e.a = make_uint4(0, 0, 0, 0); e.b = make_uint4(0, 0, 0, 0);
+      int have = 0;
+      if (lane < 8 && g.n != 0u) have = probe_brick(g, cell_key(bx0 + (lane & 1), by0 + ((lane >> 1) & 1), bz0 + (lane >> 2)), e) ? 1 : 0;
+      const int l27 = lane < 27 ? lane : 0;
+      const int gx = wk.cx + (l27 % 3) - 1, gy = wk.cy + ((l27 / 3) % 3) - 1, gz = wk.cz + (l27 / 9) - 1;
+      const int ib = (brick_of(gx) - bx0) | ((brick_of(gy) - by0) << 1) | ((brick_of(gz) - bz0) << 2);
+      const int sub = subcell_of(gx, gy, gz);
+      const int h = __shfl_sync(0xffffffffu, have, ib);
+      const unsigned base = __shfl_sync(0xffffffffu, e.a.z, ib);
+      const unsigned w0 = __shfl_sync(0xffffffffu, e.a.w, ib), w1 = __shfl_sync(0xffffffffu, e.b.x, ib);
+      const unsigned w2 = __shfl_sync(0xffffffffu, e.b.y, ib), w3 = __shfl_sync(0xffffffffu, e.b.z, ib);
+      const unsigned wds[4] = {w0, w1, w2, w3};
+      unsigned beg = base, cnt = 0u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned cq = (wds[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+        if (q < sub) beg += cq;
+        if (q == sub) cnt = cq;
+      }
+      if (lane < 27) { sm.run_beg[lane] = beg; sm.run_cnt[lane] = h ? cnt : 0u; }
+      if (lane == 0) { sm.run_i = 0; sm.run_o = 0u; }
+    }
+    // ---- my query ----
+    const bool hasq = tid < (int)wk.qcnt;
+    int il = 0, gi = 0;
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    if (hasq) {
+      il = (int)a.cl[c].q_order[wk.qbeg + tid];
+      gi = ctx.pad_off[c] + il;
+      double qx, qy, qz;
+      rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
+      rx = qx - ctx.origin[0]; ry = qy - ctx.origin[1]; rz = qz - ctx.origin[2];
+    }
+    const double e = g.cell * (1.0 / kFine), inv_e = g.inv_cell * (double)kFine;
+    const double bx = (double)(wk.cx - 1) * g.cell, by = (double)(wk.cy - 1) * g.cell, bz = (double)(wk.cz - 1) * g.cell;
+    const double r2 = ctx.r2[c];
+    auto fclamp = [](double v) { int i = (int)floor(v); return i < 0 ? 0 : (i > kBox - 1 ? kBox - 1 : i); };
+    const int qi = fclamp((rx - bx) * inv_e), qj = fclamp((ry - by) * inv_e), qk = fclamp((rz - bz) * inv_e);
+    TopKP<5> t;
+    t.init();
+    __syncthreads();
+    // ---- passes over the neighbourhood ----
+    while (true) {
+      if (tid == 0) {
+        int n = 0, fill = 0, ri = sm.run_i;
+        unsigned ro = sm.run_o;
+        while (ri < 27 && fill < kDenseCap && n < 32) {
+          const unsigned rem = sm.run_cnt[ri] - ro;
+          if (rem == 0u) { ++ri; ro = 0u; continue; }
+          const unsigned take = rem < (unsigned)(kDenseCap - fill) ? rem : (unsigned)(kDenseCap - fill);
+          sm.cp_src[n] = sm.run_beg[ri] + ro; sm.cp_dst[n] = (unsigned)fill; sm.cp_n[n] = take;
+          ++n; fill += (int)take; ro += take;
+          if (ro == sm.run_cnt[ri]) { ++ri; ro = 0u; }
+        }
+        sm.run_i = ri; sm.run_o = ro; sm.ncopy = n; sm.fill = fill;
+        if (fill > 0) mbar_arrive_expect_tx(&sm.mbar, (unsigned)fill * 16u);
+      }
+      __syncthreads();
+      const int fill = sm.fill;
+      if (fill == 0) break;
+      if (tid < sm.ncopy) tma_bulk_g2s(&sm.pts[sm.cp_dst[tid]], g.pts + sm.cp_src[tid], sm.cp_n[tid] * 16u, &sm.mbar);
+      for (int i = tid; i < kBoxCells; i += kDenseBlk) sm.cursor[i] = 0u;      // while the copies are in flight
+      mbar_wait(&sm.mbar, parity);
+      parity ^= 1u;
+      __syncthreads();
+      // counting sort of the staged points into the fine grid (indices only: the points stay where TMA put them)
+      auto fine_id = [&](const float4& p) {
+        const int fi = fclamp(((double)p.x - bx) * inv_e), fj = fclamp(((double)p.y - by) * inv_e), fk = fclamp(((double)p.z - bz) * inv_e);
+        return (fk * kBox + fj) * kBox + fi;
+      };
+      for (int i = tid; i < fill; i += kDenseBlk) atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u);
+      __syncthreads();
+      {
+        constexpr int kPer = (kBoxCells + kDenseBlk - 1) / kDenseBlk;      // consecutive entries per thread
+        const int i0 = tid * kPer;
+        unsigned local = 0u;
+        for (int i = i0; i < i0 + kPer && i < kBoxCells; ++i) local += sm.cursor[i];
+        unsigned incl = local;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) sm.scan_tmp[warp] = incl;
+        __syncthreads();
+        unsigned run = incl - local;
+        for (int wi = 0; wi < warp; ++wi) run += sm.scan_tmp[wi];
+        for (int i = i0; i < i0 + kPer && i < kBoxCells; ++i) { const unsigned cn = sm.cursor[i]; sm.start[i] = run; sm.cursor[i] = run; run += cn; }
+        if (tid == kDenseBlk - 1) sm.start[kBoxCells] = (unsigned)fill;
+      }
+      __syncthreads();
+      for (int i = tid; i < fill; i += kDenseBlk) sm.order[atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u)] = (unsigned short)i;
+      __syncthreads();
+      if (hasq) {
+        auto scan = [&](unsigned b, unsigned en) {
+          for (unsigned u = b; u < en; ++u) {
+            const float4 p = sm.pts[sm.order[u]];
+            const double ddx = (double)p.x - rx, ddy = (double)p.y - ry, ddz = (double)p.z - rz;
+            const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
+            if (d < r2) t.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
+          }
+        };
+        // phase A: the 3 x 3 x 3 fine cells around the query
+        const int ai0 = qi > 0 ? qi - 1 : 0, ai1 = qi < kBox - 1 ? qi + 1 : kBox - 1;
+        for (int k = (qk > 0 ? qk - 1 : 0); k <= (qk < kBox - 1 ? qk + 1 : kBox - 1); ++k)
+          for (int j = (qj > 0 ? qj - 1 : 0); j <= (qj < kBox - 1 ? qj + 1 : kBox - 1); ++j) {
+            const int row = (k * kBox + j) * kBox;
+            scan(sm.start[row + ai0], sm.start[row + ai1 + 1]);
+          }
+        // phase B: whatever else can still hold a point closer than the K-th best (or inside the radius)
+        double reach2 = t.d2[4] < r2 ? t.d2[4] : r2;
+        const double reach = sqrt(reach2) + 1e-9;
+        const int i0 = fclamp((rx - reach - bx) * inv_e), i1 = fclamp((rx + reach - bx) * inv_e);
+        const int j0 = fclamp((ry - reach - by) * inv_e), j1 = fclamp((ry + reach - by) * inv_e);
+        const int k0 = fclamp((rz - reach - bz) * inv_e), k1 = fclamp((rz + reach - bz) * inv_e);
+        auto gap = [&](double q, double b0, int i, int qc) {      // lower bound of |q - p| along one axis for fine slab i
+          double gp = i > qc ? (b0 + (double)i * e) - q : (i < qc ? q - (b0 + (double)(i + 1) * e) : 0.0);
+          gp -= 1e-9;
+          return gp > 0.0 ? gp : 0.0;
+        };
+        for (int k = k0; k <= k1; ++k) {
+          const double gz = gap(rz, bz, k, qk);
+          for (int j = j0; j <= j1; ++j) {
+            const double gy = gap(ry, by, j, qj);
+            const double bound = t.d2[4] < r2 ? t.d2[4] : r2;
+            if (gz * gz + gy * gy > bound) continue;
+            const int row = (k * kBox + j) * kBox;
+            const bool in_a = (k >= qk - 1 && k <= qk + 1 && j >= qj - 1 && j <= qj + 1);
+            if (!in_a) {
+              scan(sm.start[row + i0], sm.start[row + i1 + 1]);
+            } else {
+              if (i0 < ai0) scan(sm.start[row + i0], sm.start[row + ai0]);
+              if (i1 > ai1) scan(sm.start[row + ai1 + 1], sm.start[row + i1 + 1]);
+            }
+          }
+        }
+      }
+      __syncthreads();                         // everybody is done with the staged points before the next pass
+    }
+    // ---- fit + lazy GNC weight update + outputs (as k_correspond) ----
+    if (hasq) {
+      const int k = t.count();
+      double nb[5][3];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        nb[j][0] = ctx.origin[0] + (double)t.x[j]; nb[j][1] = ctx.origin[1] + (double)t.y[j]; nb[j][2] = ctx.origin[2] + (double)t.z[j];
+        if (j >= k) nb[j][0] = nb[j][1] = nb[j][2] = 0.0;
+      }
+      double prim[6];
+      const unsigned char flag = fit_neighbours<5>(ctx, c, k, t.d2[0], nb, prim);
+      double wv = 1.0;
+      if (st->outer != 0) {
+        wv = ctx.w[gi];
+        const double res = ctx.slot[gi];
+        if (res != 0.0) {
+          if (res >= st->th1) wv = 0.0;
+          else if (res <= st->th2) wv = 1.0;
+          else wv = sqrt(st->c2 * st->mu_used * (st->mu_used + 1.0) / res) - st->mu_used;
+        }
+      }
+      ctx.w[gi] = wv;
+      ctx.slot[gi] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) ctx.prim[j][gi] = prim[j];
+      ctx.flags[gi] = flag;
+      if ((flag & kFlagCounted) && ctx.maxnum[c] < ctx.n[c])
+        atomicAdd(&ctx.blk_count[buf * ctx.blk_cap + ctx.blk_off[c] + il / kBlk], 1);
+    }
+  }
+}
+
+}  // namespace tloam

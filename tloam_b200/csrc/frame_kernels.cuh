@@ -147,33 +147,21 @@ __global__ void k_begin_frame(const __grid_constant__ DeviceCtx one, const __gri
   }
 }
 
-// Primitive fit + validity tests of one feature given its (already merged) neighbour list.
+// Primitive fit + validity tests of one feature given its k nearest neighbours (world coordinates, ascending
+// (d2, index); rows >= k are zero) and the squared distance of the nearest one.
 // ref: registration.cpp:445-493 (edge), 536-551 (sphere), 589-625 (planar), 732-768 (ground).
 template <int K>
-__device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, const TopK<K>& t, double prim[6]) {
-  const GridDesc& g = ctx.grid[c];
-  const double o0 = ctx.origin[0], o1 = ctx.origin[1], o2 = ctx.origin[2];
+__device__ __forceinline__ unsigned char fit_neighbours(const DeviceCtx& ctx, int c, int k, double d2_first, const double (*nb)[3],
+                                                        double prim[6]) {
 #pragma unroll
   for (int j = 0; j < 6; ++j) prim[j] = 0.0;
   if (K == 1) {                                            // sphere
-    if (t.pos[0] < 0) return kFlagCounted;                 // not found: sphere_sum++ (:551)
-    if (t.d2[0] > 0.2) return 0;                           // squared distance vs 0.2, `continue` (:536)
-    const float4 m = __ldg(&g.pts[t.pos[0]]);
-    prim[0] = o0 + (double)m.x; prim[1] = o1 + (double)m.y; prim[2] = o2 + (double)m.z;
+    if (k <= 0) return kFlagCounted;                       // not found: sphere_sum++ (:551)
+    if (d2_first > 0.2) return 0;                          // squared distance vs 0.2, `continue` (:536)
+    prim[0] = nb[0][0]; prim[1] = nb[0][1]; prim[2] = nb[0][2];
     return kFlagCand | kFlagCounted;
   }
-  const int k = t.count();
   if (k <= 0) return 0;
-  double nb[K][3];
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    if (j < k) {
-      const float4 m = __ldg(&g.pts[t.pos[j]]);
-      nb[j][0] = o0 + (double)m.x; nb[j][1] = o1 + (double)m.y; nb[j][2] = o2 + (double)m.z;
-    } else {
-      nb[j][0] = nb[j][1] = nb[j][2] = 0.0;
-    }
-  }
   if (c == kEdge) {
     if (k <= 3) return 0;                                  // :445
     // mean + covariance from raw cumulants (:451-474)
@@ -202,6 +190,25 @@ __device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, co
     if (nd[0] * nb[j][0] + nd[1] * nb[j][1] + nd[2] * nb[j][2] + nd[3] > 0.2) return 0;   // one-sided, :605-613
   prim[0] = nd[0]; prim[1] = nd[1]; prim[2] = nd[2]; prim[3] = nd[3];
   return kFlagCand | kFlagCounted;                          // surf_num++ / ground_num++
+}
+
+// the same, with the neighbours re-loaded from the map by their position in the cell-sorted array
+template <int K>
+__device__ __forceinline__ unsigned char fit_one(const DeviceCtx& ctx, int c, const TopK<K>& t, double prim[6]) {
+  const GridDesc& g = ctx.grid[c];
+  const double o0 = ctx.origin[0], o1 = ctx.origin[1], o2 = ctx.origin[2];
+  const int k = t.count();
+  double nb[K][3];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    if (j < k) {
+      const float4 m = __ldg(&g.pts[t.pos[j]]);
+      nb[j][0] = o0 + (double)m.x; nb[j][1] = o1 + (double)m.y; nb[j][2] = o2 + (double)m.z;
+    } else {
+      nb[j][0] = nb[j][1] = nb[j][2] = 0.0;
+    }
+  }
+  return fit_neighbours<K>(ctx, c, k, t.d2[0], nb, prim);
 }
 
 // shared memory of the lane-pair search (per-thread cell lists)
@@ -281,6 +288,14 @@ __global__ void __launch_bounds__(kBlk, 5) k_correspond(const __grid_constant__ 
   const int fb = lb / 2, sb = lb % 2;
   const int buf = st->outer & 1;
   if (threadIdx.x == 0 && sb == 0) ctx.blk_count[(buf ^ 1) * ctx.blk_cap + fb] = 0;   // for the next outer iteration
+  if (ctx.dense_mask) {                       // clouds served by k_correspond_dense: only the padding lanes are ours
+    const int cd = cloud_of_block(ctx, fb);
+    if ((ctx.dense_mask >> cd) & 1) {
+      const int ild = (fb - ctx.blk_off[cd]) * kBlk + sb * (kBlk / 2) + (int)(threadIdx.x >> 1);
+      if ((threadIdx.x & 1) == 0 && (ild >= ctx.n[cd] || !cloud_enabled(ctx, cd))) ctx.flags[ctx.pad_off[cd] + ild] = 0;
+      return;
+    }
+  }
   int c, gi; bool live; unsigned char flag; double prim[6], wv;
   search_and_fit(ctx, st, &s_search, fb, sb, c, gi, live, flag, prim, wv);
   const bool even = (threadIdx.x & 1) == 0;

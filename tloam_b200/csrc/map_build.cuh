@@ -140,11 +140,12 @@ __global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
   __shared__ unsigned s_w[8];
   __shared__ unsigned s_base;
   if (lane == 31) s_w[warp] = incl;
-  __syncthreads();
+  const int nocc = __syncthreads_count(cnt > 0u);
   if (threadIdx.x == 0) {
     unsigned tot = 0;
     for (int wi = 0; wi < 8; ++wi) { const unsigned v = s_w[wi]; s_w[wi] = tot; tot += v; }
     s_base = (tot > 0u) ? atomicAdd(&h->cursor[c], tot) : 0u;
+    if (nocc > 0) atomicAdd(&h->nbricks[c], (unsigned)nocc);
   }
   __syncthreads();
   if (cnt > 0u) table[2u * s].z = s_base + s_w[warp] + (incl - cnt);

@@ -41,7 +41,7 @@ struct MapHeader {
   unsigned long long build_flags;  // bit 0: a cell holds more than kMaxCellPoints points (map unusable)
   unsigned bbox_ticket;            // blocks of k_map_bbox that have contributed (build scratch)
   unsigned pad32;
-  unsigned long long pad[2];
+  unsigned nbricks[4];             // occupied bricks per cloud (k_map_offsets): points / bricks picks the search path
 };
 static_assert(sizeof(MapHeader) == 256, "MapHeader must be 256 bytes");
 constexpr unsigned long long kMapMagic = 0x544C4F414D423230ull;  // "TLOAMB20"

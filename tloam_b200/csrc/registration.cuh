@@ -89,7 +89,8 @@ struct DeviceCtx {
   int pad_off[4];               // first padded feature index of each cloud (multiple of kBlk)
   int blk_off[5];               // block ranges per cloud
   int maxnum[4];
-  int factor_num, max_iterations, ceres_max_it, pad_;
+  int factor_num, max_iterations, ceres_max_it;
+  int dense_mask;               // bit c: cloud c is searched by k_correspond_dense (dense map), not by k_correspond
   double edge_dir_thres, cost_threshold, gnc_factor, noise_bound, fitness_thres;
   double reinit_dir[3];
   double initial_radius;        // Ceres options.initial_trust_region_radius (default 1e4; a test knob otherwise)

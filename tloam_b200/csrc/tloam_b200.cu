@@ -12,6 +12,7 @@
 #include "solver.cuh"
 #include "map_build.cuh"
 #include "frame_kernels.cuh"
+#include "dense_search.cuh"
 #include "submap.cuh"
 #include "feature_extract.cuh"
 
@@ -96,6 +97,15 @@ struct tloam_b200_handle {
   // ---- PCA feature extraction ((f)-2): one arena, carved up per call ----
   unsigned char* d_fe = nullptr;           size_t cap_fe = 0;  bool fe_attr_set = false;
   double* d_pose = nullptr;
+  // ---- dense-map correspondence path (dense_search.cuh): query binning scratch + the search-path decision ----
+  unsigned char* d_dense = nullptr;        size_t cap_dense = 0, dense_zero_bytes = 0;
+  DenseArgs dargs, gdargs;                 // current / captured in the graph
+  unsigned* h_mapstats = nullptr;          // pinned: occupied bricks per cloud of the newest map
+  cudaEvent_t ev_stats = nullptr;          bool stats_pending = false, stats_known = false;
+  unsigned nbricks[4] = {0, 0, 0, 0};
+  int dense_mode = -1;                     // TLOAM_B200_DENSE: -1 auto (points per brick), 0 never, 1 always
+  bool dense_attr_set = false;
+  int num_sms = 148;
 };
 
 // launch bookkeeping: counts the kernel and, in profiling mode, brackets it with events
@@ -196,6 +206,11 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_NO_FUSE"); h->use_fused = !(e && e[0] == '1'); }
+  { const char* e = getenv("TLOAM_B200_DENSE"); if (e && (e[0] == '0' || e[0] == '1')) h->dense_mode = e[0] - '0'; }
+  if (cudaMallocHost(&h->h_mapstats, 4 * sizeof(unsigned)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_stats, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->num_sms = v; }
+  memset(&h->dargs, 0, sizeof(h->dargs)); memset(&h->gdargs, 0, sizeof(h->gdargs));
   if (kEvalCluster > 8) {                          // cluster sizes above 8 are "non-portable": opt in per kernel
     if (cudaFuncSetAttribute(k_eval<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
         cudaFuncSetAttribute(k_eval<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
@@ -231,6 +246,9 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->h_predict) cudaFreeHost(h->h_predict);
+  if (h->h_mapstats) cudaFreeHost(h->h_mapstats);
+  if (h->ev_stats) cudaEventDestroy(h->ev_stats);
+  cudaFree(h->d_dense);
   cudaFree(h->d_predict);
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -477,6 +495,11 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
   bind_map(h);
   h->origin_known = false;
   h->have_tgt = true;
+  // occupied bricks per cloud -> pinned host memory, harvested when it has landed (it picks the search path of LATER
+  // frames; both paths return the same exact neighbours, so the choice never changes a pose)
+  CU_TRY(cudaMemcpyAsync(h->h_mapstats, h->d_blob + offsetof(MapHeader, nbricks), 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaEventRecord(h->ev_stats, h->stream));
+  h->stats_pending = true;
   // host path: the caller's buffers are free once the LAST upload has landed; the build of the last cloud may
   // still be running on the compute stream (everything that follows is ordered behind it on that stream)
   if (!on_device && total > 0) CU_TRY(cudaEventSynchronize(h->ev_copy[1 + h->last_uploaded]));
@@ -540,6 +563,8 @@ int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes)
   bind_map(h);
   h->origin_known = true;
   h->have_tgt = true;
+  for (int c = 0; c < 4; ++c) h->nbricks[c] = hd.nbricks[c];
+  h->stats_known = true; h->stats_pending = false;
   CU_TRY(cudaStreamSynchronize(h->stream));
   return TLOAM_B200_OK;
 }
@@ -548,6 +573,86 @@ static int check_ready(tloam_b200_handle* h) {
   if (!h->have_src || !h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
   for (int c = 0; c < 4; ++c)
     if (h->n_src[c] < 10 || h->n_tgt[c] < 10) return TLOAM_B200_ERR_TOO_FEW_POINTS;   // ref: :928-929
+  return TLOAM_B200_OK;
+}
+
+
+// ---- dense-map path: decision + scratch ----
+static void harvest_map_stats(tloam_b200_handle* h, bool wait) {
+  if (!h->stats_pending) return;
+  if (wait) cudaEventSynchronize(h->ev_stats);
+  else if (cudaEventQuery(h->ev_stats) != cudaSuccess) { cudaGetLastError(); return; }
+  for (int c = 0; c < 4; ++c) h->nbricks[c] = h->h_mapstats[c];
+  h->stats_pending = false; h->stats_known = true;
+}
+
+constexpr double kDensePointsPerBrick = 256.0;   // config 2 maps: 8-25; config 3: ~1700
+constexpr size_t kDenseMinQueries = 2048;
+
+static int dense_mask_of(tloam_b200_handle* h) {
+  if (h->dense_mode == 0) return 0;
+  harvest_map_stats(h, !h->stats_known);         // the very first map of a handle: wait once for its statistics
+  int mask = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (c == kSphere) continue;                   // K = 1 search: lane-pair path only
+    const bool enabled = (c == kPlanar || c == kGround) ? true : h->cfg.factor_num >= 3;
+    if (!enabled || h->n_src[c] == 0 || h->n_tgt[c] == 0) continue;
+    const bool dense = h->nbricks[c] > 0 && (double)h->n_tgt[c] / (double)h->nbricks[c] >= kDensePointsPerBrick &&
+                       h->n_src[c] >= kDenseMinQueries;
+    if (h->dense_mode == 1 || dense) mask |= 1 << c;
+  }
+  return mask;
+}
+
+static int prepare_dense(tloam_b200_handle* h, int mask) {
+  DenseArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mask = mask;
+  size_t off = 256;                              // ctl words first
+  size_t total_q = 0;
+  unsigned toff = 0;
+  size_t o_keys[4] = {0, 0, 0, 0}, o_cnt[4] = {0, 0, 0, 0};
+  unsigned ts[4] = {0, 0, 0, 0};
+  for (int c = 0; c < 4; ++c) {
+    if (!((mask >> c) & 1)) continue;
+    ts[c] = next_pow2(2 * h->n_src[c] + 1);
+    o_keys[c] = off; off += (size_t)ts[c] * 8;
+    o_cnt[c] = off; off += (size_t)ts[c] * 4;
+    total_q += h->n_src[c];
+  }
+  const size_t zero_bytes = off;
+  size_t o_base[4], o_slot[4], o_rank[4], o_order[4];
+  for (int c = 0; c < 4; ++c) {
+    if (!((mask >> c) & 1)) continue;
+    o_base[c] = off; off += (size_t)ts[c] * 4;
+    o_slot[c] = off; off += round_up(h->n_src[c] * 4, 256);
+    o_rank[c] = off; off += round_up(h->n_src[c] * 4, 256);
+    o_order[c] = off; off += round_up(h->n_src[c] * 4, 256);
+  }
+  const size_t o_work = off; off += total_q * sizeof(DenseWork);
+  if (off > h->cap_dense) {
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_dense); h->d_dense = nullptr; h->cap_dense = 0;
+    CU_TRY(cudaMalloc(&h->d_dense, off + off / 4));
+    h->cap_dense = off + off / 4;
+  }
+  unsigned char* b = h->d_dense;
+  for (int c = 0; c < 4; ++c) {
+    if (!((mask >> c) & 1)) continue;
+    DenseCloud& q = a.cl[c];
+    q.keys = (unsigned long long*)(b + o_keys[c]); q.cnt = (unsigned*)(b + o_cnt[c]); q.base = (unsigned*)(b + o_base[c]);
+    q.q_slot = (unsigned*)(b + o_slot[c]); q.q_rank = (unsigned*)(b + o_rank[c]); q.q_order = (unsigned*)(b + o_order[c]);
+    q.tmask = ts[c] - 1u; q.toff = toff; toff += ts[c];
+  }
+  a.work = (DenseWork*)(b + o_work);
+  a.ctl = (unsigned*)b;
+  a.tslots = toff;
+  h->dargs = a;
+  h->dense_zero_bytes = zero_bytes;
+  if (!h->dense_attr_set) {
+    CU_TRY(cudaFuncSetAttribute(k_correspond_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmemBytes));
+    h->dense_attr_set = true;
+  }
   return TLOAM_B200_OK;
 }
 
@@ -563,6 +668,22 @@ static bool caps_cannot_bind(const tloam_b200_handle* h) {
 
 static BatchTab no_batch() { BatchTab t; memset(&t, 0, sizeof(t)); t.S = 1; return t; }
 
+// correspondence search + fit of one outer iteration as kernels of their own (un-fused sequence, build_factors)
+static int enqueue_correspond(tloam_b200_handle* h, const DeviceCtx& c) {
+  const int nb = h->total_blocks;
+  if (c.dense_mask) {
+    // dense map clouds: bin the queries by map cell, then the TMA-staged block-per-cell search (dense_search.cuh)
+    const DenseArgs& da = h->dargs;
+    CU_TRY(cudaMemsetAsync(h->d_dense, 0, h->dense_zero_bytes, h->stream));
+    TL_LAUNCH(TLOAM_B200_K_DENSE_BIN, (k_qbin_count<<<nb, kBlk, 0, h->stream>>>(c, da)));
+    TL_LAUNCH(TLOAM_B200_K_DENSE_BIN, (k_qbin_offsets<<<(da.tslots + 255) / 256, 256, 0, h->stream>>>(c, da)));
+    TL_LAUNCH(TLOAM_B200_K_DENSE_BIN, (k_qbin_scatter<<<nb, kBlk, 0, h->stream>>>(c, da)));
+    TL_LAUNCH(TLOAM_B200_K_DENSE, (k_correspond_dense<<<2 * h->num_sms, kDenseBlk, kDenseSmemBytes, h->stream>>>(c, da)));
+  }
+  TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<false><<<nb * 2, kBlk, 0, h->stream>>>(c, no_batch())));
+  return TLOAM_B200_OK;
+}
+
 // enqueues the frame's fixed launch sequence on h->stream (also used under stream capture)
 static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c, bool fused) {
   const int nb = h->total_blocks;
@@ -574,7 +695,8 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c, bool fused) {
     if (fused) {
       TL_LAUNCH(TLOAM_B200_K_FIRST, (k_first<false><<<nf, kBlk, 0, h->stream>>>(c, nt)));
     } else {
-      TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<false><<<nb * 2, kBlk, 0, h->stream>>>(c, nt)));
+      const int crc = enqueue_correspond(h, c);
+      if (crc != TLOAM_B200_OK) return crc;
       TL_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true, false><<<ne, kBlk, 0, h->stream>>>(c, nt)));
     }
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
@@ -622,12 +744,15 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   else h->h_predict->from_state = 1.0;
   DeviceCtx c = h->ctx;
   if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
-  const bool fused = h->use_fused && caps_cannot_bind(h);
-  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + h->cfg.ceres_max_num_iterations);
+  c.dense_mask = dense_mask_of(h);
+  if (c.dense_mask) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
+  const bool fused = h->use_fused && caps_cannot_bind(h) && c.dense_mask == 0;
+  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + (c.dense_mask ? 4 : 0) + h->cfg.ceres_max_num_iterations);
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
-    if (!h->gvalid || h->gfused != fused || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0) {
+    if (!h->gvalid || h->gfused != fused || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0 ||
+        (c.dense_mask && memcmp(&h->gdargs, &h->dargs, sizeof(DenseArgs)) != 0)) {
       h->gvalid = false;
       cudaGraph_t graph = nullptr;
       CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -644,7 +769,7 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       // same topology, new kernel parameters / grid sizes (cloud sizes change from frame to frame in a real
       // stream): update the instantiated graph in place, which is much cheaper than instantiating a new one
       bool updated = false;
-      if (h->gexec && h->gfused == fused) {
+      if (h->gexec && h->gfused == fused && h->gctx.dense_mask == c.dense_mask) {
         cudaGraphExecUpdateResultInfo info;
         updated = cudaGraphExecUpdate(h->gexec, graph, &info) == cudaSuccess;
         if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -653,6 +778,7 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
       h->gctx = c;
+      h->gdargs = h->dargs;
       h->gfused = fused;
       h->gvalid = true;
     }
@@ -678,6 +804,7 @@ int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_st
   if (stats && h->traced_last) CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(tloam_b200_stats), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   h->frame_pending = false;
+  harvest_map_stats(h, false);                 // the stream is idle: the newest map's statistics have landed
   memcpy(result, h->h_result, 16 * sizeof(double));
   int flags[2];
   memcpy(flags, h->h_result + 16, sizeof(flags));   // frame_done, status
@@ -1114,10 +1241,12 @@ int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6],
   memcpy(pr.m, x, 6 * sizeof(double));
   DeviceCtx c = h->ctx;
   c.factor_num = 4;   // build every cloud regardless of the configured subset
+  c.dense_mask = dense_mask_of(h);
+  if (c.dense_mask) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
   k_set_pose<<<1, 256, 0, h->stream>>>(c, pr);
-  k_correspond<false><<<h->total_blocks * 2, kBlk, 0, h->stream>>>(c, no_batch());
+  { const int crc = enqueue_correspond(h, c); if (crc != TLOAM_B200_OK) return crc; }
   k_caps<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
-  h->launches += 3;
+  h->launches += 2;
   CU_TRY(cudaGetLastError());
   std::vector<unsigned char> act(n);
   std::vector<double> col(n);
