@@ -26,7 +26,9 @@
  *     ref: include/tloam/open3d/PointCloud2.hpp:396); array index 0..3 = edge, sphere, planar, ground
  *     (order of registration.cpp:233-236).
  *   - poses: 4x4 FP64 COLUMN-major (Eigen::Isometry3d::matrix().data()).
- *   - the library copies inputs at set_*(); caller buffers may be freed on return.
+ *   - HOST inputs are copied at set_*(): caller buffers may be freed on return (unless tloam_b200_set_async_inputs).
+ *     DEVICE inputs (set_*_device) are read in place by kernels on the handle's stream: keep them unchanged until
+ *     that work has run, and order their producer with tloam_b200_wait_stream.
  *   - one handle = one CUDA device + one stream, single caller, not re-entrant (like the reference,
  *     ref: registration.hpp:327-329).  Distinct handles are independent.
  *   - no function aborts or throws; all return a tloam_b200_status.  There is NO CPU fallback: without a
@@ -118,6 +120,10 @@ int tloam_b200_set_target(tloam_b200_handle* h, const double* const xyz[4], cons
  * has run (tloam_b200_synchronize, or the get_result of the frame that follows). */
 int tloam_b200_set_source_device(tloam_b200_handle* h, const double* const d_xyz[4], const size_t n[4]);
 int tloam_b200_set_target_device(tloam_b200_handle* h, const double* const d_xyz[4], const size_t n[4]);
+/* Stream ordering of device inputs: makes the handle's stream wait (on the device) for everything enqueued so far on
+ * `producer_stream` (cudaStream_t; NULL = the legacy default stream).  Call it before set_*_device when the buffers were
+ * written on another stream; the handle's own stream (tloam_b200_create's `stream`) needs no call. */
+int tloam_b200_wait_stream(tloam_b200_handle* h, void* producer_stream);
 
 /* Blocking: enqueues the frame, waits, returns the pose (and optionally the trace). */
 int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double result[16], tloam_b200_stats* stats);
@@ -165,8 +171,22 @@ int tloam_b200_batch_set_profiling(tloam_b200_batch* b, int on);
 int tloam_b200_batch_get_profile(tloam_b200_batch* b, struct tloam_b200_profile* out);
 
 int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse);
+/* getFitnessScore as a per-frame health metric of the asynchronous flow (ref: registration.cpp:257-296; the reference
+ * declares it on the interface and never calls it): when switched on, every scan_match also scores its scan against
+ * the map (two kernels in the frame graph, no allocation, no extra synchronisation) and the pair comes back with the
+ * frame's result. */
+int tloam_b200_set_frame_fitness(tloam_b200_handle* h, int on);
+int tloam_b200_get_frame_fitness(tloam_b200_handle* h, double* fitness, double* rmse);   /* of the last fetched result */
+/* Pipelined use (front end one frame ahead of the GPU): set_source / submap_update return without waiting for their
+ * uploads -- the HOST buffers must stay valid until the frame's result has been fetched -- and get_result waits for the
+ * OLDEST un-fetched frame only (at most 2 frames in flight; no per-iteration trace in this mode). */
+int tloam_b200_set_async_inputs(tloam_b200_handle* h, int on);
 int tloam_b200_get_transform(tloam_b200_handle* h, double pose[16]);
 int tloam_b200_get_pose_increment(tloam_b200_handle* h, double pose[16]);
+/* self-check of the dense-map correspondence path (env TLOAM_B200_DENSE_CHECK=1 at create): every query it searches is
+ * searched again by the plain path and compared.  out: [0] queries, [1] differing kNN lists, [2] work items, [3] TMA
+ * staging passes, [4..7] details of the first mismatch; accumulated since creation. */
+int tloam_b200_dense_check_counters(tloam_b200_handle* h, unsigned out[8]);
 int tloam_b200_synchronize(tloam_b200_handle* h);
 /* total kernels launched by this handle so far */
 long long tloam_b200_launch_count(tloam_b200_handle* h);
@@ -199,6 +219,9 @@ int tloam_b200_eval_point_to_plane(tloam_b200_handle* h, const double x[6], size
 int tloam_b200_se3_exp(tloam_b200_handle* h, const double a[6], double T[16]);
 int tloam_b200_se3_log(tloam_b200_handle* h, const double T[16], double a[6]);
 int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double delta[6], double out[6]);
+/* the 2-D trust-region boundary problem of the subspace dogleg as the device solver runs it:
+ * minimise 0.5 y^T B y + g^T y on |y| = radius (B row-major 2x2) */
+int tloam_b200_min_on_boundary_2d(tloam_b200_handle* h, const double B[4], const double g[2], double radius, double y[2]);
 
 /* ---- per-kernel timing (off by default): CUDA events on the handle's stream around EVERY launch.  The
  * bracketing adds ~1-2 us of event overhead per launch, so profiled durations are upper bounds. ---- */
@@ -206,7 +229,7 @@ enum {
   TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
   TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_FIRST,
-  TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
@@ -243,7 +266,10 @@ int tloam_b200_submap_init(tloam_b200_handle* h, const tloam_submap_config* cfg,
  * interface parity and ignored, as in the reference (front_end.cpp:220-230 iterates the planar buffer). */
 int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const double* planar_sub, size_t np,
                              const double* sphere_sub, size_t ns);
-int tloam_b200_submap_sizes(tloam_b200_handle* h, size_t n[4]);
+/* Chained form: pose = the result of the frame that was just ENQUEUED on this handle (scan_match_async /
+ * scan_match_predicted_async), read on the device -- no host round trip between registration and map update. */
+int tloam_b200_submap_update_chained(tloam_b200_handle* h, const double* planar_sub, size_t np);
+int tloam_b200_submap_sizes(tloam_b200_handle* h, size_t n[4]);   /* exact sizes (synchronises) */
 /* copies map cloud `cloud` (0 edge, 1 sphere, 2 planar, 3 ground; world frame, FP64 AoS) to the host */
 int tloam_b200_submap_download(tloam_b200_handle* h, int cloud, double* out, size_t capacity_points);
 /* PointCloud2::VoxelDownSample on the device (HOST in / out; out must hold n points). */

@@ -126,6 +126,8 @@ def lib():
         L.oracle_build_factors.argtypes = [C.c_void_p, C.c_int, dp, C.POINTER(C.c_int), dp, C.c_size_t]
         L.oracle_build_factors.restype = C.c_int
         L.oracle_update_weight.argtypes = [dp, dp, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.oracle_min_on_boundary_2d.argtypes = [dp, dp, C.c_double, dp]
+        L.oracle_min_on_boundary_2d.restype = None
         L.oracle_submap_default_config.argtypes = [C.POINTER(SubmapConfig)]
         L.oracle_voxel_down_sample.argtypes = [dp, C.c_size_t, C.c_double, dp]
         L.oracle_voxel_down_sample.restype = C.c_size_t
@@ -413,3 +415,11 @@ def extract_planar_sphere(pts, **overrides):
                                        bufs[4].ctypes.data_as(szp))
     return (bufs[0][:cnt[0].value].copy(), bufs[1][:cnt[1].value].copy(), bufs[2][:cnt[2].value].copy(),
             bufs[3][:cnt[3].value].copy(), bufs[4][:cnt[3].value].copy())
+
+
+def min_on_boundary_2d(B, g, radius):
+    B = _f64(B).reshape(4)
+    g = _f64(g).reshape(2)
+    y = np.zeros(2)
+    lib().oracle_min_on_boundary_2d(_dp(B), _dp(g), float(radius), _dp(y))
+    return y

@@ -1300,6 +1300,11 @@ void oracle_update_weight(double* weights, const double* slots, size_t n, double
   }
 }
 
+// dogleg_strategy.cc FindMinimumOnTrustRegionBoundary (2-D subspace problem), exposed for the quartic-root pin
+void oracle_min_on_boundary_2d(const double B[4], const double g[2], double radius, double y[2]) {
+  min_on_boundary_2d(B, g, radius, y);
+}
+
 // ---------------------------------------------------------------------------------------------
 // (f)-1 submap maintenance
 // ---------------------------------------------------------------------------------------------

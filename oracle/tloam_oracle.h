@@ -130,6 +130,9 @@ void oracle_eval_point_to_plane(const double x[6], const double p[3], const doub
  * valid[i] in {0,1}; prim is n*6 doubles: plane (n,d,0,0), line (a,b), point (q,0,0,0). */
 int oracle_build_factors(void* h, int cloud, const double x[6], int* valid, double* prim, size_t n);
 
+/* minimise 0.5 y^T B y + g^T y on |y| = radius (B row-major 2x2): the boundary problem of the subspace dogleg */
+void oracle_min_on_boundary_2d(const double B[4], const double g[2], double radius, double y[2]);
+
 /* GNC weight update, registration.cpp:858-876. */
 void oracle_update_weight(double* weights, const double* slots, size_t n, double noise_bound_sq, double th1,
                           double th2, double mu);

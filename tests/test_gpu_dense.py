@@ -32,10 +32,12 @@ def quantized(sc):
 def make_reg(dense, **cfg):
     import tloam_b200
     os.environ["TLOAM_B200_DENSE"] = "1" if dense else "0"
+    os.environ["TLOAM_B200_DENSE_CHECK"] = "1"       # every dense query is re-searched by the plain path on the device
     try:
         return tloam_b200.LocalRegistration(**cfg)
     finally:
         os.environ.pop("TLOAM_B200_DENSE", None)
+        os.environ.pop("TLOAM_B200_DENSE_CHECK", None)
 
 
 def run(sc, dense, **cfg):
@@ -43,6 +45,12 @@ def run(sc, dense, **cfg):
     r.set_input_target(sc["map"])
     r.set_input_source(sc["scan"])
     T, st = r.scan_matching(sc["predict"], want_stats=True)
+    if dense:
+        cnt = r.dense_check_counters()
+        fn = cfg.get("factor_num", 4)
+        nq = sum(len(sc["scan"][c]) for c in ((2, 3) if fn == 2 else (0, 2, 3)))
+        assert cnt[1] == 0, f"dense kNN differs from the plain search for {cnt[1]} of {cnt[0]} queries: {cnt}"
+        assert cnt[0] == st.n_outer * nq, (cnt, st.n_outer, nq)        # every query searched exactly once per outer iteration
     r.close()
     return T, st
 

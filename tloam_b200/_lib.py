@@ -66,7 +66,7 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense", "fitness")
 
 
 class FeatureConfig(C.Structure):
@@ -90,7 +90,7 @@ EXPORTS = [
     "tloam_b200_launch_count", "tloam_b200_map_blob_size", "tloam_b200_map_export", "tloam_b200_map_import",
     "tloam_b200_get_map_origin", "tloam_b200_knn", "tloam_b200_build_factors", "tloam_b200_eval_point_to_point",
     "tloam_b200_eval_point_to_line", "tloam_b200_eval_point_to_plane", "tloam_b200_se3_exp", "tloam_b200_se3_log",
-    "tloam_b200_se3_plus", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
+    "tloam_b200_se3_plus", "tloam_b200_min_on_boundary_2d", "tloam_b200_host_alloc", "tloam_b200_host_free", "tloam_b200_set_profiling",
     "tloam_b200_get_profile", "tloam_b200_set_trace", "tloam_b200_submap_default_config", "tloam_b200_submap_init",
     "tloam_b200_submap_update", "tloam_b200_submap_sizes", "tloam_b200_submap_download", "tloam_b200_voxel_down_sample",
     "tloam_b200_scan_match_predicted_async", "tloam_b200_scan_match_predicted", "tloam_b200_set_pose_history",
@@ -100,6 +100,8 @@ EXPORTS = [
     "tloam_b200_batch_set_source_device", "tloam_b200_batch_scan_match", "tloam_b200_batch_scan_match_async",
     "tloam_b200_batch_get_results", "tloam_b200_batch_launch_count", "tloam_b200_batch_last_error",
     "tloam_b200_batch_set_profiling", "tloam_b200_batch_get_profile",
+    "tloam_b200_submap_update_chained", "tloam_b200_set_frame_fitness", "tloam_b200_get_frame_fitness",
+    "tloam_b200_set_async_inputs", "tloam_b200_wait_stream", "tloam_b200_dense_check_counters",
 ]
 
 _lib = None
@@ -155,6 +157,7 @@ def load():
     L.tloam_b200_se3_exp.argtypes = [vp, dp, dp]
     L.tloam_b200_se3_log.argtypes = [vp, dp, dp]
     L.tloam_b200_se3_plus.argtypes = [vp, dp, dp, dp]
+    L.tloam_b200_min_on_boundary_2d.argtypes = [vp, dp, dp, C.c_double, dp]
     L.tloam_b200_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.tloam_b200_host_free.argtypes = [vp]
     L.tloam_b200_set_profiling.argtypes = [vp, C.c_int]
@@ -190,6 +193,12 @@ def load():
     L.tloam_b200_batch_last_error.argtypes = [vp]
     L.tloam_b200_batch_last_error.restype = C.c_char_p
     L.tloam_b200_batch_set_profiling.argtypes = [vp, C.c_int]
+    L.tloam_b200_submap_update_chained.argtypes = [vp, dp, C.c_size_t]
+    L.tloam_b200_set_frame_fitness.argtypes = [vp, C.c_int]
+    L.tloam_b200_get_frame_fitness.argtypes = [vp, dp, dp]
+    L.tloam_b200_set_async_inputs.argtypes = [vp, C.c_int]
+    L.tloam_b200_wait_stream.argtypes = [vp, vp]
+    L.tloam_b200_dense_check_counters.argtypes = [vp, C.POINTER(C.c_uint)]
     L.tloam_b200_batch_get_profile.argtypes = [vp, C.POINTER(Profile)]
     _lib = L
     return L

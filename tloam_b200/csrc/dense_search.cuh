@@ -45,6 +45,8 @@ struct DenseArgs {
   DenseWork* work;             // [sum n]
   unsigned* ctl;               // [0] nwork, [1] next work item, [2..5] q_order bump allocators
   unsigned tslots;             // total slots over the dense clouds
+  unsigned* dbg;               // self-check counters (TLOAM_B200_DENSE_CHECK=1), else nullptr: [0] queries, [1] kNN
+                               // mismatches vs the plain search, [2] work items, [3] staging passes, [4] first bad gi
   int mask;                    // bit c: cloud c takes the dense path
 };
 
@@ -257,6 +259,8 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
     const double r2 = ctx.r2[c];
     auto fclamp = [](double v) { int i = (int)floor(v); return i < 0 ? 0 : (i > kBox - 1 ? kBox - 1 : i); };
     const int qi = fclamp((rx - bx) * inv_e), qj = fclamp((ry - by) * inv_e), qk = fclamp((rz - bz) * inv_e);
+    const float bxf = (float)bx, byf = (float)by, bzf = (float)bz;                    // exact (multiples of the cell edge)
+    const float qlx = (float)(rx - bx), qly = (float)(ry - by), qlz = (float)(rz - bz);
     TopKP<5> t;
     t.init();
     __syncthreads();
@@ -279,6 +283,7 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
       __syncthreads();
       const int fill = sm.fill;
       if (fill == 0) break;
+      if (a.dbg && tid == 0) atomicAdd(&a.dbg[3], 1u);
       if (tid < sm.ncopy) tma_bulk_g2s(&sm.pts[sm.cp_dst[tid]], g.pts + sm.cp_src[tid], sm.cp_n[tid] * 16u, &sm.mbar);
       for (int i = tid; i < kBoxCells; i += kDenseBlk) sm.cursor[i] = 0u;      // while the copies are in flight
       mbar_wait(&sm.mbar, parity);
@@ -309,51 +314,77 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
       for (int i = tid; i < fill; i += kDenseBlk) sm.order[atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u)] = (unsigned short)i;
       __syncthreads();
       if (hasq) {
+        // candidates are pre-filtered in FP32 on coordinates LOCAL to the staged box (p - box0 is exact in FP32: both are
+        // multiples of the point's ulp and the difference is < 2 cells), with a margin that covers the FP32 rounding of
+        // the query and of the arithmetic (< 1e-6 m^2 at cell <= 1 m); survivors get the exact FP64 expression
+        double bound = t.d2[4] < r2 ? t.d2[4] : r2;
+        float boundf = (float)bound * 1.00001f + 2e-6f;
         auto scan = [&](unsigned b, unsigned en) {
+#pragma unroll 4
           for (unsigned u = b; u < en; ++u) {
             const float4 p = sm.pts[sm.order[u]];
-            const double ddx = (double)p.x - rx, ddy = (double)p.y - ry, ddz = (double)p.z - rz;
-            const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
-            if (d < r2) t.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
+            const float fx = (p.x - bxf) - qlx, fy = (p.y - byf) - qly, fz = (p.z - bzf) - qlz;
+            const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+            if (df <= boundf) {
+              const double ddx = (double)p.x - rx, ddy = (double)p.y - ry, ddz = (double)p.z - rz;
+              const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
+              if (d < r2) {
+                t.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
+                bound = t.d2[4] < r2 ? t.d2[4] : r2;
+                boundf = (float)bound * 1.00001f + 2e-6f;
+              }
+            }
           }
         };
-        // phase A: the 3 x 3 x 3 fine cells around the query
-        const int ai0 = qi > 0 ? qi - 1 : 0, ai1 = qi < kBox - 1 ? qi + 1 : kBox - 1;
-        for (int k = (qk > 0 ? qk - 1 : 0); k <= (qk < kBox - 1 ? qk + 1 : kBox - 1); ++k)
-          for (int j = (qj > 0 ? qj - 1 : 0); j <= (qj < kBox - 1 ? qj + 1 : kBox - 1); ++j) {
-            const int row = (k * kBox + j) * kBox;
-            scan(sm.start[row + ai0], sm.start[row + ai1 + 1]);
-          }
-        // phase B: whatever else can still hold a point closer than the K-th best (or inside the radius)
-        double reach2 = t.d2[4] < r2 ? t.d2[4] : r2;
-        const double reach = sqrt(reach2) + 1e-9;
-        const int i0 = fclamp((rx - reach - bx) * inv_e), i1 = fclamp((rx + reach - bx) * inv_e);
-        const int j0 = fclamp((ry - reach - by) * inv_e), j1 = fclamp((ry + reach - by) * inv_e);
-        const int k0 = fclamp((rz - reach - bz) * inv_e), k1 = fclamp((rz + reach - bz) * inv_e);
         auto gap = [&](double q, double b0, int i, int qc) {      // lower bound of |q - p| along one axis for fine slab i
           double gp = i > qc ? (b0 + (double)i * e) - q : (i < qc ? q - (b0 + (double)(i + 1) * e) : 0.0);
           gp -= 1e-9;
           return gp > 0.0 ? gp : 0.0;
         };
-        for (int k = k0; k <= k1; ++k) {
-          const double gz = gap(rz, bz, k, qk);
-          for (int j = j0; j <= j1; ++j) {
-            const double gy = gap(ry, by, j, qj);
-            const double bound = t.d2[4] < r2 ? t.d2[4] : r2;
-            if (gz * gz + gy * gy > bound) continue;
-            const int row = (k * kBox + j) * kBox;
-            const bool in_a = (k >= qk - 1 && k <= qk + 1 && j >= qj - 1 && j <= qj + 1);
-            if (!in_a) {
-              scan(sm.start[row + i0], sm.start[row + i1 + 1]);
-            } else {
-              if (i0 < ai0) scan(sm.start[row + i0], sm.start[row + ai0]);
-              if (i1 > ai1) scan(sm.start[row + ai1 + 1], sm.start[row + i1 + 1]);
+        // nearest-first over Chebyshev shells of fine cells around the query: every cell of shell rho is at least
+        // (rho - 1) e away, so the walk stops as soon as that exceeds the K-th best distance (or the radius: shells
+        // 0..kFine cover it, and they lie inside the staged box because the query sits in its middle third)
+        for (int rho = 0; rho <= kFine; ++rho) {
+          if (rho >= 2) {
+            const double lb = (double)(rho - 1) * e - 1e-9;
+            if (lb * lb > bound) break;
+          }
+          for (int dk = -rho; dk <= rho; ++dk) {
+            const int k = qk + dk;
+            if (k < 0 || k >= kBox) continue;
+            const double gz = gap(rz, bz, k, qk);
+            for (int dj = -rho; dj <= rho; ++dj) {
+              const int j = qj + dj;
+              if (j < 0 || j >= kBox) continue;
+              const double gy = gap(ry, by, j, qj);
+              const double g2 = gz * gz + gy * gy;
+              if (g2 > bound) continue;
+              const int row = (k * kBox + j) * kBox;
+              const bool face = (dk == -rho || dk == rho || dj == -rho || dj == rho);
+              if (face) {                                      // the whole x-extent of the shell
+                const int i0 = qi - rho > 0 ? qi - rho : 0, i1 = qi + rho < kBox - 1 ? qi + rho : kBox - 1;
+                scan(sm.start[row + i0], sm.start[row + i1 + 1]);
+              } else {                                         // only the two end cells
+                const int il0 = qi - rho, ih0 = qi + rho;
+                if (il0 >= 0) { const double gx = gap(rx, bx, il0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + il0], sm.start[row + il0 + 1]); }
+                if (ih0 < kBox) { const double gx = gap(rx, bx, ih0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + ih0], sm.start[row + ih0 + 1]); }
+              }
             }
           }
         }
       }
       __syncthreads();                         // everybody is done with the staged points before the next pass
     }
+    if (a.dbg && hasq) {                       // self-check against the thread-per-query search of map_grid.cuh
+      TopK<5> ref;
+      knn_search<5>(g, rx, ry, rz, r2, ref);
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) bad = bad || (ref.idx[j] != t.idx[j]) || (ref.d2[j] != t.d2[j] && !(ref.pos[j] < 0 && t.idx[j] == 0x7FFFFFFF));
+      atomicAdd(&a.dbg[0], 1u);
+      if (bad) { if (atomicAdd(&a.dbg[1], 1u) == 0u) { a.dbg[4] = (unsigned)gi; a.dbg[5] = (unsigned)c; a.dbg[6] = (unsigned)t.count(); a.dbg[7] = (unsigned)ref.count(); } }
+    }
+    if (a.dbg && tid == 0) atomicAdd(&a.dbg[2], 1u);
     // ---- fit + lazy GNC weight update + outputs (as k_correspond) ----
     if (hasq) {
       const int k = t.count();

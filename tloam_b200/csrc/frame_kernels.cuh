@@ -102,6 +102,13 @@ __device__ __forceinline__ void begin_frame_body(const DeviceCtx& ctx, const Pre
     st->frame_done = 1;
     return;
   }
+  for (int c = 0; c < 4; ++c)
+    if (ctx.tgt_cnt[c] && *ctx.tgt_cnt[c] < 10u) {          // ref: :928-929, for map clouds counted on the device
+      st->status = TLOAM_B200_ERR_TOO_FEW_POINTS;
+      for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
+      st->frame_done = 1;
+      return;
+    }
   if (!pose_from_matrix(pr.m, p)) {
     st->status = TLOAM_B200_ERR_BAD_POSE;
     for (int i = 0; i < 16; ++i) st->result[i] = pr.m[i];
@@ -672,6 +679,19 @@ __global__ void __launch_bounds__(kBlk) k_fitness(const __grid_constant__ Device
   }
 }
 
+// sums the per-block partials of k_fitness per cloud and leaves (fitness, rmse) in the frame state
+// (ref: registration.cpp:278-284, 292-293: per type matched / total and sqrt(sum d2 / matched), summed over the types)
+__global__ void k_fitness_reduce(const __grid_constant__ DeviceCtx ctx, const double* part /*[blocks][2]*/) {
+  if (threadIdx.x != 0) return;
+  double fit = 0.0, rm = 0.0;
+  for (int c = 0; c < 4; ++c) {
+    double err = 0.0, cnt = 0.0;
+    for (int b = ctx.blk_off[c]; b < ctx.blk_off[c + 1]; ++b) { err += part[2 * b]; cnt += part[2 * b + 1]; }
+    if (cnt > 0.0) { fit += cnt / (double)ctx.n[c]; rm += sqrt(err / cnt); }
+  }
+  ctx.st->fitness = fit; ctx.st->rmse = rm;
+}
+
 __global__ void k_functor(int type, Predict x6, unsigned m, const double* p, const double* a, const double* bq,
                           const double* w, double* r, double* J, double* cost) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -708,7 +728,8 @@ __global__ void k_se3(int op, Predict in, double* out) {
   if (threadIdx.x != 0) return;
   if (op == 0) { pose_to_matrix(se3_exp(in.m), out); }
   else if (op == 1) { Pose7 p; const bool ok = pose_from_matrix(in.m, p); se3_log(p, out); out[6] = ok ? 1.0 : 0.0; }
-  else { se3_log(se3_mul(se3_exp(in.m + 6), se3_exp(in.m)), out); }   // plus: in.m[0..5] = x, in.m[6..11] = delta
+  else if (op == 2) { se3_log(se3_mul(se3_exp(in.m + 6), se3_exp(in.m)), out); }   // plus: in.m[0..5] = x, in.m[6..11] = delta
+  else { min_on_boundary_2d(in.m, in.m + 4, in.m[6], out); }              // in.m[0..3] = B, [4..5] = g, [6] = radius
 }
 
 }  // namespace tloam

@@ -13,7 +13,16 @@ struct MapBuildArgs {
   unsigned* rank_of;            // scratch [total]
   unsigned i_beg, i_end;        // global point range this launch works on (one cloud in the pipelined host path)
   int only_cloud;               // k_map_offsets: table of this cloud only (-1 = all four)
+  // device-resident point counts (sync-free submap chain): stage_off / i_end are then CAPACITY bounds known to the
+  // host, and cloud c really holds *n_dev[c] points (nullptr = the bound is exact)
+  const unsigned* n_dev[4];
 };
+
+// false for the slack between a cloud's device-side count and its host-side bound
+__device__ __forceinline__ bool map_point_live(const MapBuildArgs& a, unsigned i, int c) {
+  const unsigned* nd = c == 0 ? a.n_dev[0] : c == 1 ? a.n_dev[1] : c == 2 ? a.n_dev[2] : a.n_dev[3];
+  return nd == nullptr || (i - a.stage_off[c]) < *nd;
+}
 
 __device__ __forceinline__ int cloud_of_point(const MapBuildArgs& a, unsigned i) {
   return (i >= a.stage_off[3]) ? 3 : (i >= a.stage_off[2]) ? 2 : (i >= a.stage_off[1]) ? 1 : 0;
@@ -29,6 +38,7 @@ __device__ __forceinline__ const double* point_of(const MapBuildArgs& a, unsigne
 __global__ void k_map_bbox(MapBuildArgs a) {
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   for (unsigned i = a.i_beg + blockIdx.x * blockDim.x + threadIdx.x; i < a.i_end; i += gridDim.x * blockDim.x) {
+    if (!map_point_live(a, i, cloud_of_point(a, i))) break;         // one cloud per launch: the live points come first
     const double* pt = point_of(a, i);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -66,7 +76,7 @@ __global__ void k_map_bbox(MapBuildArgs a) {
   if (s_last && threadIdx.x < 3) {
     __threadfence();
     const double lo = dec_ordered(atomicMin(&h->bbox_enc[threadIdx.x], ~0ull)), hi = dec_ordered(atomicMax(&h->bbox_enc[3 + threadIdx.x], 0ull));
-    h->origin[threadIdx.x] = rint(0.5 * (lo + hi));
+    h->origin[threadIdx.x] = (lo <= hi) ? rint(0.5 * (lo + hi)) : 0.0;      // empty (device-counted) cloud: origin 0
   }
 }
 
@@ -92,6 +102,7 @@ __global__ void k_map_insert(MapBuildArgs a) {
   if (i >= a.i_end) return;
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   const int c = cloud_of_point(a, i);
+  if (!map_point_live(a, i, c)) return;
   const float3 r = rel_of(a, h, i);
   int cx, cy, cz;
   cell_of_rel(r, 1.0 / h->cell[c], cx, cy, cz);
@@ -157,6 +168,7 @@ __global__ void k_map_scatter(MapBuildArgs a) {
   MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
   if (h->build_flags & 1ull) return;               // counters wrapped: destinations are meaningless
   const int c = cloud_of_point(a, i);
+  if (!map_point_live(a, i, c)) return;
   const float3 r = rel_of(a, h, i);
   int cx, cy, cz;
   cell_of_rel(r, 1.0 / h->cell[c], cx, cy, cz);

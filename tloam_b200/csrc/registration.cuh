@@ -74,6 +74,7 @@ struct FrameState {
   // ---- outputs ----
   double result[16];
   int frame_done, status;   // directly after `result`: the host fetches the three with ONE copy
+  double fitness, rmse;     // getFitnessScore of this frame's scan (k_fitness_reduce), fetched with the same copy
   double curr_pose[16], last_pose[16];
 };
 static_assert(offsetof(FrameState, frame_done) == offsetof(FrameState, result) + 16 * sizeof(double), "result + flags must be contiguous");
@@ -84,6 +85,7 @@ struct DeviceCtx {
   GridDesc grid[4];
   const double* origin;         // -> MapHeader::origin inside the map blob (device memory)
   const unsigned long long* map_flags;   // -> MapHeader::build_flags
+  const unsigned* tgt_cnt[4];   // device-side point counts of the map clouds (sync-free submap chain), or nullptr
   double r2[4];                 // squared search radius per cloud
   int n[4];                     // features per cloud
   int pad_off[4];               // first padded feature index of each cloud (multiple of kBlk)

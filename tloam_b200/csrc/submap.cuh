@@ -32,15 +32,30 @@ struct VoxArgs {
   unsigned mask;
   double* out;                 // AoS xyz of the voxel averages
   unsigned* out_count;
+  // sync-free chain: the input count lives on the device (n = *n_dev + n_add; `n` is then only the host's bound) and the
+  // crop box is centred on a pose held in device memory (the result of the frame that was just enqueued)
+  const unsigned* n_dev;
+  unsigned n_add;
+  const double* box_pose;      // 4x4 column-major, or nullptr: lo / hi above
+  double box_len;
 };
 
+__device__ __forceinline__ unsigned vox_n(const VoxArgs& a) { return a.n_dev ? *a.n_dev + a.n_add : a.n; }
+
 __device__ __forceinline__ bool vox_in_box(const VoxArgs& a, double x, double y, double z) {
+  if (a.box_pose) {            // inclusive box pose.t +- len (ref: front_end.cpp:248-264)
+    const double cx = a.box_pose[12], cy = a.box_pose[13], cz = a.box_pose[14], L = a.box_len;
+    return x >= cx - L && x <= cx + L && y >= cy - L && y <= cy + L && z >= cz - L && z <= cz + L;
+  }
   return x >= a.lo[0] && x <= a.hi[0] && y >= a.lo[1] && y <= a.hi[1] && z >= a.lo[2] && z <= a.hi[2];
 }
 
-__global__ void k_transform_append(const double* in, unsigned n, double* out, const double* pose /*device, 16 col-major*/) {
+// out_off: device-side number of points already in `out` (nullptr = 0)
+__global__ void k_transform_append(const double* in, unsigned n, double* out, const double* pose /*device, 16 col-major*/,
+                                   const unsigned* out_off) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (out_off) out += 3ull * *out_off;
   const double x = in[3ull * i], y = in[3ull * i + 1], z = in[3ull * i + 2];
   out[3ull * i] = pose[0] * x + pose[4] * y + pose[8] * z + pose[12];
   out[3ull * i + 1] = pose[1] * x + pose[5] * y + pose[9] * z + pose[13];
@@ -49,7 +64,8 @@ __global__ void k_transform_append(const double* in, unsigned n, double* out, co
 
 __global__ void __launch_bounds__(256) k_vox_min(VoxArgs a) {
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+  const unsigned n = vox_n(a);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double x = a.in[3ull * i], y = a.in[3ull * i + 1], z = a.in[3ull * i + 2];
     if (vox_in_box(a, x, y, z)) { mn[0] = fmin(mn[0], x); mn[1] = fmin(mn[1], y); mn[2] = fmin(mn[2], z); }
   }
@@ -71,7 +87,7 @@ constexpr double kVoxFix = 1099511627776.0;   // 2^40
 
 __global__ void __launch_bounds__(256) k_vox_accum(VoxArgs a) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+  if (i >= vox_n(a)) return;
   const double p[3] = {a.in[3ull * i], a.in[3ull * i + 1], a.in[3ull * i + 2]};
   if (!vox_in_box(a, p[0], p[1], p[2])) return;
   int idx[3];
@@ -121,6 +137,11 @@ __global__ void __launch_bounds__(256) k_vox_emit(VoxArgs a) {
     const double mb = dec_ordered(a.minenc[d]) - a.voxel * 0.5;
     a.out[3ull * j + d] = mb + (double)idx[d] * a.voxel + ((double)a.sums[3ull * s + d] / kVoxFix) / (double)c;   // GetAveragePoint
   }
+}
+
+// host-known counts of the planar / sphere map clouds -> the device-side count array (cnt[c] = n)
+__global__ void k_set_counts(unsigned* cnt, int c0, unsigned n0, int c1, unsigned n1) {
+  if (threadIdx.x == 0) { if (c0 >= 0) cnt[c0] = n0; if (c1 >= 0) cnt[c1] = n1; }
 }
 
 }  // namespace tloam

@@ -89,6 +89,21 @@ struct tloam_b200_handle {
   bool submap_ready = false;
   double* d_acc[2] = {nullptr, nullptr};   size_t cap_acc[2] = {0, 0}, n_acc[2] = {0, 0};     // edge, ground accumulators
   double* d_acc_tmp = nullptr;             size_t cap_acc_tmp = 0;
+  // n_acc is the host's UPPER BOUND of each accumulator; the exact counts live on the device (no host round trip per
+  // frame): d_cnt[0..3] unused, [4 + 2k + acc_cur[k]] = points in accumulator k, [8] scratch
+  unsigned* d_cnt = nullptr;               int acc_cur[2] = {0, 0};
+  unsigned long long cum_add[2] = {0, 0}, known_cum[2] = {0, 0};  size_t known_cnt[2] = {0, 0};
+  struct CntProbe { cudaEvent_t ev = nullptr; unsigned* h_vals = nullptr; unsigned long long cum[2] = {0, 0}; bool pending = false; };
+  CntProbe probes[4];                      int probe_next = 0;
+  bool src_staged = false;                 // d_stage_src holds the current source (needed by submap_update)
+  // pipelined results (async_inputs): two pinned result slots + events, so that the host can stay one frame ahead
+  cudaEvent_t ev_res[2] = {nullptr, nullptr};
+  long long frames_enqueued = 0, frames_fetched = 0;
+  bool frame_fitness = false, gfitness = false;   // k_fitness + reduce appended to every frame (graph topology flag)
+  double last_fitness = 0.0, last_rmse = 0.0;
+  bool async_inputs = false;               // tloam_b200_set_async_inputs: host buffers stay valid until the next sync
+  // per-frame health metric (getFitnessScore) without allocation: block partials + the reduced pair in the state
+  double* d_fit = nullptr;                 size_t cap_fit = 0;
   std::vector<double*> ring;               std::vector<size_t> ring_n, ring_cap;               // planar sliding window
   double* d_cat = nullptr;                 size_t cap_cat = 0, n_cat = 0;                       // concatenated planar window
   double* d_sphere0 = nullptr;             size_t n_sphere0 = 0; bool sphere_is_init = false;  // frame-0 sphere submap
@@ -105,6 +120,7 @@ struct tloam_b200_handle {
   unsigned nbricks[4] = {0, 0, 0, 0};
   int dense_mode = -1;                     // TLOAM_B200_DENSE: -1 auto (points per brick), 0 never, 1 always
   bool dense_attr_set = false;
+  bool dense_check = false;                // TLOAM_B200_DENSE_CHECK=1: every dense query is re-searched by the plain path and compared
   int num_sms = 148;
 };
 
@@ -197,15 +213,24 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   for (int i = 0; i < 5; ++i)
     if (cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_src, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&h->ev_res[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMalloc(&h->d_cnt, 32 * sizeof(unsigned)) != cudaSuccess || cudaMemset(h->d_cnt, 0, 32 * sizeof(unsigned)) != cudaSuccess)
+    return fail(TLOAM_B200_ERR_CUDA);
+  for (auto& pr : h->probes) {
+    if (cudaEventCreateWithFlags(&pr.ev, cudaEventDisableTiming) != cudaSuccess || cudaMallocHost(&pr.h_vals, 2 * sizeof(unsigned)) != cudaSuccess)
+      return fail(TLOAM_B200_ERR_CUDA);
+  }
   if (cudaMalloc(&h->d_state, sizeof(FrameState)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_counter, 256) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
-  if (cudaMallocHost(&h->h_result, 32 * sizeof(double)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaMallocHost(&h->h_result, 64 * sizeof(double)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);   // [0..31] slot 0 + scratch, [32..63] slot 1
   if (cudaMallocHost(&h->h_stats, sizeof(tloam_b200_stats)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMallocHost(&h->h_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaMalloc(&h->d_predict, sizeof(Predict)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { const char* e = getenv("TLOAM_B200_NO_GRAPH"); h->use_graph = !(e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_NO_FUSE"); h->use_fused = !(e && e[0] == '1'); }
+  { const char* e = getenv("TLOAM_B200_DENSE_CHECK"); h->dense_check = (e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_DENSE"); if (e && (e[0] == '0' || e[0] == '1')) h->dense_mode = e[0] - '0'; }
   if (cudaMallocHost(&h->h_mapstats, 4 * sizeof(unsigned)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_stats, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
@@ -241,6 +266,8 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   cudaFree(h->d_partial); cudaFree(h->d_counter); if (h->own_state) cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
   cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
+  cudaFree(h->d_cnt); cudaFree(h->d_fit);
+  for (auto& pr : h->probes) { if (pr.ev) cudaEventDestroy(pr.ev); if (pr.h_vals) cudaFreeHost(pr.h_vals); }
   cudaFree(h->d_up); cudaFree(h->d_vox); cudaFree(h->d_pose); cudaFree(h->d_fe);
   for (double* p : h->ring) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
@@ -256,6 +283,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 5; ++i) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
   if (h->ev_src) cudaEventDestroy(h->ev_src);
+  for (int i = 0; i < 2; ++i) if (h->ev_res[i]) cudaEventDestroy(h->ev_res[i]);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -292,23 +320,31 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   // host input is staged; device input is read in place -- unless the device-side submap is in use, whose update
   // appends the staged edge / ground features after the frame (tloam_b200_submap_update)
   const bool stage = !on_device || h->submap_ready;
+  // (re)allocations: a pointer is nulled and its capacity zeroed right after the free, and the new capacity is only
+  // committed once the allocation succeeded, so a failed cudaMalloc leaves the handle consistent
+  h->have_src = false; h->src_staged = false;
   if (stage && total > h->cap_stage_src) {
-    cudaFree(h->d_stage_src);
-    h->cap_stage_src = total + total / 4 + 1024;
-    CU_TRY(cudaMalloc(&h->d_stage_src, h->cap_stage_src * 3 * sizeof(double)));
+    cudaFree(h->d_stage_src); h->d_stage_src = nullptr; h->cap_stage_src = 0;
+    const size_t ncap = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_stage_src, ncap * 3 * sizeof(double)));
+    h->cap_stage_src = ncap;
   }
   if (pad > h->cap_pad) {
-    cudaFree(h->d_feat); cudaFree(h->d_flags);
-    h->cap_pad = round_up(pad + pad / 4, kBlk);
-    CU_TRY(cudaMalloc(&h->d_feat, h->cap_pad * 11 * sizeof(double)));
-    CU_TRY(cudaMalloc(&h->d_flags, h->cap_pad * 2));
+    cudaFree(h->d_feat); cudaFree(h->d_flags); h->d_feat = nullptr; h->d_flags = nullptr; h->cap_pad = 0;
+    const size_t ncap = round_up(pad + pad / 4, kBlk);
+    CU_TRY(cudaMalloc(&h->d_feat, ncap * 11 * sizeof(double)));
+    CU_TRY(cudaMalloc(&h->d_flags, ncap * 2));
+    h->cap_pad = ncap;
   }
   if ((size_t)blocks > h->cap_blocks) {
-    cudaFree(h->d_blk_count); cudaFree(h->d_partial);
-    h->cap_blocks = h->cap_pad / kBlk + 8;
-    CU_TRY(cudaMalloc(&h->d_blk_count, 2 * h->cap_blocks * sizeof(int)));
-    CU_TRY(cudaMemsetAsync(h->d_blk_count, 0, 2 * h->cap_blocks * sizeof(int), h->stream));
-    CU_TRY(cudaMalloc(&h->d_partial, h->cap_blocks * kNRed * sizeof(double)));
+    cudaFree(h->d_blk_count); cudaFree(h->d_partial); cudaFree(h->d_fit);
+    h->d_blk_count = nullptr; h->d_partial = nullptr; h->d_fit = nullptr; h->cap_blocks = 0; h->cap_fit = 0;
+    const size_t ncap = h->cap_pad / kBlk + 8;
+    CU_TRY(cudaMalloc(&h->d_blk_count, 2 * ncap * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(h->d_blk_count, 0, 2 * ncap * sizeof(int), h->stream));
+    CU_TRY(cudaMalloc(&h->d_partial, ncap * kNRed * sizeof(double)));
+    CU_TRY(cudaMalloc(&h->d_fit, ncap * 2 * sizeof(double)));
+    h->cap_blocks = ncap; h->cap_fit = ncap;
   }
   DeviceCtx& c = h->ctx;
   fill_ctx_config(h);
@@ -340,7 +376,8 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
     CU_TRY(cudaGetLastError());
   }
   h->have_src = true;
-  if (!on_device) CU_TRY(cudaEventSynchronize(h->ev_src));    // caller buffers may be freed on return
+  h->src_staged = stage;
+  if (!on_device && !h->async_inputs) CU_TRY(cudaEventSynchronize(h->ev_src));    // caller buffers may be freed on return
   return TLOAM_B200_OK;
 }
 
@@ -368,9 +405,9 @@ static int layout_map(tloam_b200_handle* h, const size_t n[4]) {
   for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
   h->blob_bytes = off;
   if (off > h->cap_blob) {
-    cudaFree(h->d_blob);
+    cudaFree(h->d_blob); h->d_blob = nullptr; h->cap_blob = 0;
+    CU_TRY(cudaMalloc(&h->d_blob, off + off / 4));
     h->cap_blob = off + off / 4;
-    CU_TRY(cudaMalloc(&h->d_blob, h->cap_blob));
   }
   return TLOAM_B200_OK;
 }
@@ -405,7 +442,8 @@ static int fetch_origin(tloam_b200_handle* h) {
   return (h->hdr.build_flags & 1ull) ? TLOAM_B200_ERR_MAP_DENSITY : TLOAM_B200_OK;
 }
 
-static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device) {
+static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device,
+                           const unsigned* const* n_dev = nullptr) {
   if (!h || !xyz || !n) return TLOAM_B200_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(h->device));
   size_t total = 0;
@@ -414,21 +452,26 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     if (n[c] > (size_t)1 << 30) return TLOAM_B200_ERR_INVALID_ARG;
     total += n[c];
   }
+  h->have_tgt = false;
   if (total > h->cap_scratch) {
-    cudaFree(h->d_scratch);
-    h->cap_scratch = total + total / 4 + 1024;
-    CU_TRY(cudaMalloc(&h->d_scratch, h->cap_scratch * 2 * sizeof(unsigned)));
+    cudaFree(h->d_scratch); h->d_scratch = nullptr; h->cap_scratch = 0;
+    const size_t ncap = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_scratch, ncap * 2 * sizeof(unsigned)));
+    h->cap_scratch = ncap;
   }
   if (!on_device && total > h->cap_stage_tgt) {
-    cudaFree(h->d_stage_tgt);
-    h->cap_stage_tgt = total + total / 4 + 1024;
-    CU_TRY(cudaMalloc(&h->d_stage_tgt, h->cap_stage_tgt * 3 * sizeof(double)));
+    cudaFree(h->d_stage_tgt); h->d_stage_tgt = nullptr; h->cap_stage_tgt = 0;
+    const size_t ncap = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_stage_tgt, ncap * 3 * sizeof(double)));
+    h->cap_stage_tgt = ncap;
   }
   int rc = layout_map(h, n);
   if (rc != TLOAM_B200_OK) return rc;
   MapBuildArgs a;
   a.blob = h->d_blob; a.slot_of = h->d_scratch; a.rank_of = h->d_scratch + h->cap_scratch;
   a.only_cloud = -1;
+  for (int c = 0; c < 4; ++c) a.n_dev[c] = n_dev ? n_dev[c] : nullptr;
+  for (int c = 0; c < 4; ++c) h->ctx.tgt_cnt[c] = a.n_dev[c];
   size_t off = 0;
   int first = -1;                                  // first non-empty cloud: its bounding box defines the origin
   for (int c = 0; c < 4; ++c) {
@@ -586,6 +629,22 @@ static void harvest_map_stats(tloam_b200_handle* h, bool wait) {
   h->stats_pending = false; h->stats_known = true;
 }
 
+// exact accumulator counts (device) -> tighter host bounds, whenever an asynchronous read-back has landed
+static void harvest_counts(tloam_b200_handle* h) {
+  for (int i = 0; i < 4; ++i) {
+    tloam_b200_handle::CntProbe& pr = h->probes[i];
+    if (!pr.pending) continue;
+    if (cudaEventQuery(pr.ev) != cudaSuccess) { cudaGetLastError(); continue; }
+    pr.pending = false;
+    for (int k = 0; k < 2; ++k)
+      if (pr.cum[k] >= h->known_cum[k]) { h->known_cum[k] = pr.cum[k]; h->known_cnt[k] = pr.h_vals[k]; }
+  }
+  for (int k = 0; k < 2; ++k) {
+    const size_t bound = h->known_cnt[k] + (size_t)(h->cum_add[k] - h->known_cum[k]);
+    if (bound < h->n_acc[k]) h->n_acc[k] = bound;
+  }
+}
+
 constexpr double kDensePointsPerBrick = 256.0;   // config 2 maps: 8-25; config 3: ~1700
 constexpr size_t kDenseMinQueries = 2048;
 
@@ -647,6 +706,7 @@ static int prepare_dense(tloam_b200_handle* h, int mask) {
   a.work = (DenseWork*)(b + o_work);
   a.ctl = (unsigned*)b;
   a.tslots = toff;
+  a.dbg = h->dense_check ? h->d_cnt + 16 : nullptr;          // d_cnt[16..23]: self-check counters
   h->dargs = a;
   h->dense_zero_bytes = zero_bytes;
   if (!h->dense_attr_set) {
@@ -666,6 +726,7 @@ static bool caps_cannot_bind(const tloam_b200_handle* h) {
   return true;
 }
 
+static constexpr size_t kFrameResultBytes = 16 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(double);
 static BatchTab no_batch() { BatchTab t; memset(&t, 0, sizeof(t)); t.S = 1; return t; }
 
 // correspondence search + fit of one outer iteration as kernels of their own (un-fused sequence, build_factors)
@@ -702,9 +763,15 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c, bool fused) {
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
       TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false, false><<<ne, kBlk, 0, h->stream>>>(c, nt)));
   }
-  // result[16] + {frame_done, status}: contiguous in FrameState
-  CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), 16 * sizeof(double) + 2 * sizeof(int),
-                         cudaMemcpyDeviceToHost, h->stream));
+  if (h->frame_fitness && nb > 0) {              // per-frame health metric (ref: registration.cpp:257-296), no allocation
+    TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness<<<nb, kBlk, 0, h->stream>>>(c, h->cfg.fitness_thres * h->cfg.fitness_thres, h->d_fit)));
+    TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness_reduce<<<1, 32, 0, h->stream>>>(c, h->d_fit)));
+  }
+  // result[16] + {frame_done, status} + {fitness, rmse}: contiguous in FrameState.  Pipelined handles copy it after the
+  // graph launch into alternating slots instead (scan_match_enqueue)
+  if (!h->async_inputs)
+    CU_TRY(cudaMemcpyAsync(h->h_result, (const char*)h->d_state + offsetof(FrameState, result), kFrameResultBytes,
+                           cudaMemcpyDeviceToHost, h->stream));
   return TLOAM_B200_OK;
 }
 
@@ -739,6 +806,11 @@ int tloam_b200_set_pose_history(tloam_b200_handle* h, const double last_pose[16]
 static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   const int rc = check_ready(h);
   if (rc != TLOAM_B200_OK) return rc;
+  if (h->async_inputs && h->frames_enqueued - h->frames_fetched >= 2) return TLOAM_B200_ERR_NOT_READY;   // fetch a result first
+  if (h->frame_fitness) {
+    if (h->cfg.fitness_thres <= 0.0) return TLOAM_B200_ERR_INVALID_ARG;
+    for (int c = 0; c < 4; ++c) if (h->cfg.fitness_thres > radius_of(h->cfg, c)) return TLOAM_B200_ERR_INVALID_ARG;
+  }
   CU_TRY(cudaSetDevice(h->device));
   if (predict) { memcpy(h->h_predict->m, predict, 16 * sizeof(double)); h->h_predict->from_state = 0.0; }
   else h->h_predict->from_state = 1.0;
@@ -747,11 +819,12 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   c.dense_mask = dense_mask_of(h);
   if (c.dense_mask) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
   const bool fused = h->use_fused && caps_cannot_bind(h) && c.dense_mask == 0;
-  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + (c.dense_mask ? 4 : 0) + h->cfg.ceres_max_num_iterations);
+  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + (c.dense_mask ? 4 : 0) + h->cfg.ceres_max_num_iterations) +
+                        (h->frame_fitness ? 2 : 0);
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
-    if (!h->gvalid || h->gfused != fused || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0 ||
+    if (!h->gvalid || h->gfused != fused || h->gfitness != h->frame_fitness || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0 ||
         (c.dense_mask && memcmp(&h->gdargs, &h->dargs, sizeof(DenseArgs)) != 0)) {
       h->gvalid = false;
       cudaGraph_t graph = nullptr;
@@ -769,7 +842,7 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       // same topology, new kernel parameters / grid sizes (cloud sizes change from frame to frame in a real
       // stream): update the instantiated graph in place, which is much cheaper than instantiating a new one
       bool updated = false;
-      if (h->gexec && h->gfused == fused && h->gctx.dense_mask == c.dense_mask) {
+      if (h->gexec && h->gfused == fused && h->gfitness == h->frame_fitness && h->gctx.dense_mask == c.dense_mask) {
         cudaGraphExecUpdateResultInfo info;
         updated = cudaGraphExecUpdate(h->gexec, graph, &info) == cudaSuccess;
         if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -780,6 +853,7 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       h->gctx = c;
       h->gdargs = h->dargs;
       h->gfused = fused;
+      h->gfitness = h->frame_fitness;
       h->gvalid = true;
     }
     CU_TRY(cudaGraphLaunch(h->gexec, h->stream));
@@ -790,6 +864,13 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
     CU_TRY(cudaGetLastError());
   }
   CU_TRY(cudaEventRecord(h->ev1, h->stream));
+  if (h->async_inputs) {                         // pipelined: result -> slot (frame & 1), one event per slot
+    const int p = (int)(h->frames_enqueued & 1);
+    CU_TRY(cudaMemcpyAsync(h->h_result + 32 * p, (const char*)h->d_state + offsetof(FrameState, result), kFrameResultBytes,
+                           cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaEventRecord(h->ev_res[p], h->stream));
+  }
+  h->frames_enqueued++;
   h->launches_frame = per_frame;
   h->traced_last = h->trace;
   h->frame_pending = true;
@@ -801,13 +882,28 @@ int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_st
   if (!h->frame_pending) return TLOAM_B200_ERR_NOT_READY;
   CU_TRY(cudaSetDevice(h->device));
   if (stats && !h->traced_last) memset(h->h_stats, 0, sizeof(tloam_b200_stats));
-  if (stats && h->traced_last) CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(tloam_b200_stats), cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(cudaStreamSynchronize(h->stream));
-  h->frame_pending = false;
-  harvest_map_stats(h, false);                 // the stream is idle: the newest map's statistics have landed
-  memcpy(result, h->h_result, 16 * sizeof(double));
+  const double* slot = h->h_result;
+  if (h->async_inputs) {
+    // pipelined: the OLDEST un-fetched frame; waits for that frame only (the host may already have enqueued the next)
+    if (h->frames_fetched >= h->frames_enqueued) return TLOAM_B200_ERR_NOT_READY;
+    const int p = (int)(h->frames_fetched & 1);
+    CU_TRY(cudaEventSynchronize(h->ev_res[p]));
+    slot = h->h_result + 32 * p;
+    h->frames_fetched++;
+    h->frame_pending = h->frames_fetched < h->frames_enqueued;
+    if (stats) memset(h->h_stats, 0, sizeof(tloam_b200_stats));      // no per-iteration trace in pipelined mode
+  } else {
+    if (stats && h->traced_last) CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(tloam_b200_stats), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->frame_pending = false;
+    h->frames_fetched = h->frames_enqueued;
+  }
+  harvest_map_stats(h, false);                 // picks the newest map's statistics up once they have landed
+  harvest_counts(h);
+  memcpy(result, slot, 16 * sizeof(double));
   int flags[2];
-  memcpy(flags, h->h_result + 16, sizeof(flags));   // frame_done, status
+  memcpy(flags, slot + 16, sizeof(flags));   // frame_done, status
+  h->last_fitness = slot[17]; h->last_rmse = slot[18];
   if (stats) {
     *stats = *h->h_stats;
     stats->gpu_launches = h->launches_frame;
@@ -832,6 +928,28 @@ int tloam_b200_scan_match(tloam_b200_handle* h, const double predict[16], double
 int tloam_b200_set_trace(tloam_b200_handle* h, int on) {
   if (!h) return TLOAM_B200_ERR_INVALID_ARG;
   h->trace = on != 0;
+  return TLOAM_B200_OK;
+}
+
+// Orders the handle's stream behind everything enqueued so far on `producer_stream` (a cudaStream_t; NULL = the legacy
+// default stream): device inputs (set_*_device) are read IN PLACE by kernels on the handle's stream, so whoever
+// produced them on another stream must be waited for -- on the device, the host does not block.
+int tloam_b200_wait_stream(tloam_b200_handle* h, void* producer_stream) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  if ((cudaStream_t)producer_stream == h->stream) return TLOAM_B200_OK;
+  CU_TRY(cudaEventRecord(h->ev_src, (cudaStream_t)producer_stream));
+  CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_src, 0));
+  return TLOAM_B200_OK;
+}
+
+// self-check counters of the dense correspondence path (TLOAM_B200_DENSE_CHECK=1), accumulated since creation:
+// [0] queries searched, [1] kNN lists that differ from the plain search, [2] work items, [3] staging passes
+int tloam_b200_dense_check_counters(tloam_b200_handle* h, unsigned out[8]) {
+  if (!h || !out) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  CU_TRY(cudaMemcpy(out, h->d_cnt + 16, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return TLOAM_B200_OK;
 }
 
@@ -1174,23 +1292,43 @@ int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse) {
   if (!h->have_src || !h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
   if (h->cfg.fitness_thres <= 0.0) return TLOAM_B200_OK;                 // ref: :258-261
   for (int c = 0; c < 4; ++c) if (h->cfg.fitness_thres > radius_of(h->cfg, c)) return TLOAM_B200_ERR_INVALID_ARG;
-  CU_TRY(cudaSetDevice(h->device));
-  { const int rc = fetch_origin(h); if (rc != TLOAM_B200_OK) return rc; }
   const int nb = h->total_blocks;
-  double* d_out = nullptr;
-  CU_TRY(cudaMalloc(&d_out, (size_t)nb * 2 * sizeof(double)));
-  k_fitness<<<nb, kBlk, 0, h->stream>>>(h->ctx, h->cfg.fitness_thres * h->cfg.fitness_thres, d_out);
-  h->launches++;
-  std::vector<double> out((size_t)nb * 2);
-  cudaError_t e = cudaMemcpyAsync(out.data(), d_out, out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_out);
-  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "fitness: %s", cudaGetErrorString(e)); return TLOAM_B200_ERR_CUDA; }
-  for (int c = 0; c < 4; ++c) {
-    double err = 0.0, cnt = 0.0;
-    for (int b = h->ctx.blk_off[c]; b < h->ctx.blk_off[c + 1]; ++b) { err += out[2 * b]; cnt += out[2 * b + 1]; }
-    if (cnt > 0.0) { *fitness += cnt / (double)h->n_src[c]; *rmse += sqrt(err / cnt); }   // ref: :278-284, 292-293
-  }
+  if (nb == 0) return TLOAM_B200_OK;                                     // every source cloud is empty: nothing matches
+  CU_TRY(cudaSetDevice(h->device));
+  // block partials live in a buffer sized with the source (no allocation on this per-frame health metric); the
+  // per-cloud sums are formed on the device in block order and land in the frame state
+  TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness<<<nb, kBlk, 0, h->stream>>>(h->ctx, h->cfg.fitness_thres * h->cfg.fitness_thres, h->d_fit)));
+  TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness_reduce<<<1, 32, 0, h->stream>>>(h->ctx, h->d_fit)));
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaMemcpyAsync(h->h_result + 20, (const char*)h->d_state + offsetof(FrameState, fitness), 2 * sizeof(double),
+                         cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  *fitness = h->h_result[20]; *rmse = h->h_result[21];
+  return TLOAM_B200_OK;
+}
+
+// per-frame health metric in the asynchronous flow: every scan_match also evaluates getFitnessScore of its scan
+// (two more kernels in the frame graph, no allocation); the pair comes back with the frame's result
+int tloam_b200_set_frame_fitness(tloam_b200_handle* h, int on) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  h->frame_fitness = on != 0;
+  return TLOAM_B200_OK;
+}
+int tloam_b200_get_frame_fitness(tloam_b200_handle* h, double* fitness, double* rmse) {   // of the last fetched result
+  if (!h || !fitness || !rmse) return TLOAM_B200_ERR_INVALID_ARG;
+  *fitness = h->last_fitness; *rmse = h->last_rmse;
+  return TLOAM_B200_OK;
+}
+// Pipelined use: set_source / submap_update return without waiting for their uploads (the host buffers must then stay
+// valid until the frame's result has been fetched) and get_result waits for the OLDEST un-fetched frame only, so the
+// host can enqueue frame k+1 while the GPU still runs frame k (at most 2 frames in flight).
+int tloam_b200_set_async_inputs(tloam_b200_handle* h, int on) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  h->async_inputs = on != 0;
+  h->frames_fetched = h->frames_enqueued; h->frame_pending = false;
+  h->gvalid = false;                             // the frame graph holds (or not) the result copy
   return TLOAM_B200_OK;
 }
 
@@ -1344,6 +1482,12 @@ int tloam_b200_se3_plus(tloam_b200_handle* h, const double x[6], const double de
   return run_se3(h, 2, in, 12, out, 6, nullptr);
 }
 
+int tloam_b200_min_on_boundary_2d(tloam_b200_handle* h, const double B[4], const double g[2], double radius, double y[2]) {
+  if (!B || !g || !y) return TLOAM_B200_ERR_INVALID_ARG;
+  double in[7] = {B[0], B[1], B[2], B[3], g[0], g[1], radius};
+  return run_se3(h, 3, in, 7, y, 2, nullptr);
+}
+
 // ---------------------------------------------------------------------------------------------
 // (f)-1 device-side submap maintenance
 // ---------------------------------------------------------------------------------------------
@@ -1364,24 +1508,30 @@ static int ensure_dev(tloam_b200_handle* h, double** p, size_t* cap, size_t need
   return TLOAM_B200_OK;
 }
 
-// crop (inclusive box, lo > hi = no crop) + VoxelDownSample of d_in[0..n) into d_out; returns the voxel count.
-static int voxel_pipeline(tloam_b200_handle* h, const double* d_in, size_t n, const double* lo, const double* hi, double voxel,
-                          double* d_out, size_t* n_out) {
-  *n_out = 0;
-  if (n == 0) return TLOAM_B200_OK;
+// crop + VoxelDownSample of d_in into d_out, enqueued without any host round trip: the voxel count lands in
+// *out_count (device).  The input holds n_bound points at most; its exact count is n_bound itself (n_dev == nullptr)
+// or *n_dev + n_add.  The crop box is lo/hi (host values; nullptr = none) or pose.t +- box_len with the pose in
+// device memory.
+static int voxel_pipeline(tloam_b200_handle* h, const double* d_in, size_t n_bound, const unsigned* n_dev, unsigned n_add,
+                          const double* lo, const double* hi, const double* box_pose, double box_len, double voxel,
+                          double* d_out, unsigned* out_count) {
+  CU_TRY(cudaMemsetAsync(out_count, 0, sizeof(unsigned), h->stream));
+  if (n_bound == 0) return TLOAM_B200_OK;
   if (!(voxel > 0.0)) return TLOAM_B200_ERR_INVALID_ARG;
-  const unsigned tsize = next_pow2(2 * n + 1);
+  const unsigned tsize = next_pow2(2 * n_bound + 1);
   const size_t bytes = 256 + (size_t)tsize * (8 + 24 + 4);
   if (bytes > h->cap_vox) {
-    cudaFree(h->d_vox);
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_vox); h->d_vox = nullptr; h->cap_vox = 0;
+    CU_TRY(cudaMalloc(&h->d_vox, bytes + bytes / 2));
     h->cap_vox = bytes + bytes / 2;
-    CU_TRY(cudaMalloc(&h->d_vox, h->cap_vox));
   }
   VoxArgs a;
-  a.in = d_in; a.n = (unsigned)n; a.voxel = voxel;
+  a.in = d_in; a.n = (unsigned)n_bound; a.voxel = voxel;
+  a.n_dev = n_dev; a.n_add = n_add; a.box_pose = box_pose; a.box_len = box_len;
   for (int d = 0; d < 3; ++d) { a.lo[d] = lo ? lo[d] : -DBL_MAX; a.hi[d] = hi ? hi[d] : DBL_MAX; }
-  a.minenc = reinterpret_cast<unsigned long long*>(h->d_vox);            // [0..2] min, [3] out_count
-  a.out_count = reinterpret_cast<unsigned*>(h->d_vox + 32);
+  a.minenc = reinterpret_cast<unsigned long long*>(h->d_vox);            // [0..2] min bound
+  a.out_count = out_count;
   a.keys = reinterpret_cast<unsigned long long*>(h->d_vox + 256);
   a.sums = reinterpret_cast<long long*>(h->d_vox + 256 + (size_t)tsize * 8);
   a.cnt = reinterpret_cast<unsigned*>(h->d_vox + 256 + (size_t)tsize * 32);
@@ -1389,16 +1539,11 @@ static int voxel_pipeline(tloam_b200_handle* h, const double* d_in, size_t n, co
   a.out = d_out;
   CU_TRY(cudaMemsetAsync(h->d_vox, 0xFF, 24, h->stream));               // min encodings = +max
   CU_TRY(cudaMemsetAsync(h->d_vox + 24, 0, 256 - 24 + (size_t)tsize * 36, h->stream));
-  const unsigned tb = 256, gb = (unsigned)((n + tb - 1) / tb);
+  const unsigned tb = 256, gb = (unsigned)((n_bound + tb - 1) / tb);
   TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_min<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_accum<<<gb, tb, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_emit<<<(tsize + tb - 1) / tb, tb, 0, h->stream>>>(a)));
   CU_TRY(cudaGetLastError());
-  CU_TRY(cudaMemcpyAsync(h->h_result + 28, a.out_count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(cudaStreamSynchronize(h->stream));
-  unsigned cnt;
-  memcpy(&cnt, h->h_result + 28, sizeof(cnt));
-  *n_out = cnt;
   return TLOAM_B200_OK;
 }
 
@@ -1409,12 +1554,16 @@ static int upload_points(tloam_b200_handle* h, const double* host, size_t n) {
   return TLOAM_B200_OK;
 }
 
+static unsigned* acc_count(tloam_b200_handle* h, int k) { return h->d_cnt + 4 + 2 * k + h->acc_cur[k]; }
+
 static int submap_set_target(tloam_b200_handle* h) {
   // order at the ABI: edge, sphere, planar, ground.  After the first update the sphere map IS the planar window
-  // (ref: front_end.cpp:220-230 iterates submap_planar_buffer).
+  // (ref: front_end.cpp:220-230 iterates submap_planar_buffer).  Edge / ground: the host knows an upper bound, the
+  // exact counts are read on the device.
   const double* xyz[4] = {h->d_acc[0], h->sphere_is_init ? h->d_sphere0 : h->d_cat, h->d_cat, h->d_acc[1]};
   const size_t n[4] = {h->n_acc[0], h->sphere_is_init ? h->n_sphere0 : h->n_cat, h->n_cat, h->n_acc[1]};
-  return set_target_impl(h, xyz, n, true);
+  const unsigned* nd[4] = {acc_count(h, 0), nullptr, nullptr, acc_count(h, 1)};
+  return set_target_impl(h, xyz, n, true, nd);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1485,6 +1634,7 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   MapBuildArgs ma;
   ma.blob = A.blob; ma.slot_of = A.scratch; ma.rank_of = A.scratch + n;
   ma.i_beg = 0; ma.i_end = (unsigned)n; ma.only_cloud = -1;
+  for (int c = 0; c < 4; ++c) ma.n_dev[c] = nullptr;
   for (int c = 0; c < 4; ++c) ma.src[c] = A.stage;
   ma.stage_off[0] = 0;
   for (int c = 1; c <= 4; ++c) ma.stage_off[c] = (unsigned)n;
@@ -1594,9 +1744,14 @@ int tloam_b200_voxel_down_sample(tloam_b200_handle* h, const double* pts, size_t
   if (rc != TLOAM_B200_OK) return rc;
   rc = ensure_dev(h, &h->d_acc_tmp, &h->cap_acc_tmp, n, false);
   if (rc != TLOAM_B200_OK) return rc;
-  rc = voxel_pipeline(h, h->d_up, n, nullptr, nullptr, voxel, h->d_acc_tmp, n_out);
+  rc = voxel_pipeline(h, h->d_up, n, nullptr, 0u, nullptr, nullptr, nullptr, 0.0, voxel, h->d_acc_tmp, h->d_cnt + 8);
   if (rc != TLOAM_B200_OK) return rc;
-  if (*n_out) CU_TRY(cudaMemcpyAsync(out, h->d_acc_tmp, *n_out * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->h_result + 28, h->d_cnt + 8, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  unsigned cnt;
+  memcpy(&cnt, h->h_result + 28, sizeof(cnt));
+  *n_out = cnt;
+  if (cnt) CU_TRY(cudaMemcpyAsync(out, h->d_acc_tmp, (size_t)cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   return TLOAM_B200_OK;
 }
@@ -1610,14 +1765,17 @@ int tloam_b200_submap_init(tloam_b200_handle* h, const tloam_submap_config* cfg,
   h->scfg = *cfg;
   if (!h->d_pose) CU_TRY(cudaMalloc(&h->d_pose, 16 * sizeof(double)));
   int rc;
+  h->acc_cur[0] = h->acc_cur[1] = 0;
   // edge: raw copy (front_end.cpp:286)
   if ((rc = ensure_dev(h, &h->d_acc[0], &h->cap_acc[0], ne, false)) != TLOAM_B200_OK) return rc;
   if (ne) CU_TRY(cudaMemcpyAsync(h->d_acc[0], edge, ne * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->n_acc[0] = ne;
+  k_set_counts<<<1, 32, 0, h->stream>>>(h->d_cnt + 4, 0, (unsigned)ne, -1, 0u);
   // ground: VoxelDownSample(ground_down_sample) (:287)
   if ((rc = upload_points(h, ground_raw, ng)) != TLOAM_B200_OK) return rc;
   if ((rc = ensure_dev(h, &h->d_acc[1], &h->cap_acc[1], ng, false)) != TLOAM_B200_OK) return rc;
-  if ((rc = voxel_pipeline(h, h->d_up, ng, nullptr, nullptr, cfg->ground_down_sample, h->d_acc[1], &h->n_acc[1])) != TLOAM_B200_OK) return rc;
+  if ((rc = voxel_pipeline(h, h->d_up, ng, nullptr, 0u, nullptr, nullptr, nullptr, 0.0, cfg->ground_down_sample, h->d_acc[1],
+                           acc_count(h, 1))) != TLOAM_B200_OK) return rc;
   // planar / sphere: the submap-index selections (:291-292); the sliding-window buffers stay empty (:285-305)
   if ((rc = ensure_dev(h, &h->d_cat, &h->cap_cat, np, false)) != TLOAM_B200_OK) return rc;
   if (np) CU_TRY(cudaMemcpyAsync(h->d_cat, planar_sub, np * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1630,21 +1788,37 @@ int tloam_b200_submap_init(tloam_b200_handle* h, const tloam_submap_config* cfg,
   h->n_sphere0 = ns; h->sphere_is_init = true;
   for (double* p : h->ring) cudaFree(p);
   h->ring.clear(); h->ring_n.clear(); h->ring_cap.clear();
+  // once per sequence: wait for the uploads and read the exact ground count
+  CU_TRY(cudaMemcpyAsync(h->h_result + 28, acc_count(h, 1), sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  unsigned gcnt;
+  memcpy(&gcnt, h->h_result + 28, sizeof(gcnt));
+  h->n_acc[1] = gcnt;
+  for (int k = 0; k < 2; ++k) { h->cum_add[k] = h->known_cum[k] = 0; h->known_cnt[k] = h->n_acc[k]; }
+  for (auto& pr : h->probes) pr.pending = false;
   h->submap_ready = true;
   return submap_set_target(h);
 }
 
-int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const double* planar_sub, size_t np,
-                             const double* sphere_sub, size_t ns) {
-  (void)sphere_sub; (void)ns;   // stored but never used by the reference (front_end.cpp:202-205, 220-230)
-  if (!h || !pose || (!planar_sub && np)) return TLOAM_B200_ERR_INVALID_ARG;
+// FrontEnd::updateSubmap (ref: front_end.cpp:201-267) enqueued WITHOUT a host round trip: the voxel counts that size the
+// next map stay on the device (the host only tracks upper bounds, tightened by asynchronous read-backs), and in the
+// chained form the pose is the device-resident result of the frame that was just enqueued.
+static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, const double* planar_sub, size_t np) {
+  if (!h || (!planar_sub && np)) return TLOAM_B200_ERR_INVALID_ARG;
   if (!h->submap_ready || !h->have_src) return TLOAM_B200_ERR_NOT_READY;
+  if (!h->src_staged) return TLOAM_B200_ERR_NOT_READY;           // the staged source is what gets appended
   CU_TRY(cudaSetDevice(h->device));
+  harvest_counts(h);
   const tloam_submap_config& cf = h->scfg;
   int rc;
-  memcpy(h->h_predict->m, pose, 16 * sizeof(double));
-  CU_TRY(cudaMemcpyAsync(h->d_pose, h->h_predict, 16 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const double* d_pose = h->d_pose;
+  if (pose_host) {
+    double tmp[16];
+    memcpy(tmp, pose_host, sizeof(tmp));
+    CU_TRY(cudaMemcpyAsync(h->d_pose, tmp, sizeof(tmp), cudaMemcpyHostToDevice, h->stream));   // pageable source: staged before return
+  } else {
+    d_pose = reinterpret_cast<const double*>(reinterpret_cast<const char*>(h->d_state) + offsetof(FrameState, result));
+  }
   const unsigned tb = 256;
   // ---- planar sliding window (:207-217, 232-242): newest frame transformed by its pose ----
   if ((rc = upload_points(h, planar_sub, np)) != TLOAM_B200_OK) return rc;
@@ -1654,7 +1828,7 @@ int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const 
     h->ring.erase(h->ring.begin()); h->ring_n.erase(h->ring_n.begin()); h->ring_cap.erase(h->ring_cap.begin());
   }
   if ((rc = ensure_dev(h, &slot, &slot_cap, np, false)) != TLOAM_B200_OK) return rc;
-  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, h->stream>>>(h->d_up, (unsigned)np, slot, h->d_pose)));
+  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, h->stream>>>(h->d_up, (unsigned)np, slot, d_pose, nullptr)));
   h->ring.push_back(slot); h->ring_n.push_back(np); h->ring_cap.push_back(slot_cap);
   size_t tot = 0;
   for (size_t k : h->ring_n) tot += k;
@@ -1675,27 +1849,63 @@ int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const 
   for (int c = 0; c < 4; ++c) { soff[c] = o; o += h->n_src[c]; }
   for (int k = 0; k < 2; ++k) {
     const size_t nadd = h->n_src[src_cloud[k]];
-    if ((rc = ensure_dev(h, &h->d_acc[k], &h->cap_acc[k], h->n_acc[k] + nadd, true)) != TLOAM_B200_OK) return rc;
-    if (nadd) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((nadd + tb - 1) / tb), tb, 0, h->stream>>>(
-        h->d_stage_src + 3 * soff[src_cloud[k]], (unsigned)nadd, h->d_acc[k] + 3 * h->n_acc[k], h->d_pose)));
-    const size_t nall = h->n_acc[k] + nadd;
-    const double lo[3] = {pose[12] - len[k], pose[13] - len[k], pose[14] - len[k]};
-    const double hi[3] = {pose[12] + len[k], pose[13] + len[k], pose[14] + len[k]};
+    const size_t nall = h->n_acc[k] + nadd;                       // bound
+    if ((rc = ensure_dev(h, &h->d_acc[k], &h->cap_acc[k], nall, true)) != TLOAM_B200_OK) return rc;
     if ((rc = ensure_dev(h, &h->d_acc_tmp, &h->cap_acc_tmp, nall, false)) != TLOAM_B200_OK) return rc;
-    size_t nout = 0;
-    if ((rc = voxel_pipeline(h, h->d_acc[k], nall, lo, hi, vox[k], h->d_acc_tmp, &nout)) != TLOAM_B200_OK) return rc;
+    unsigned* cur = acc_count(h, k);
+    if (nadd) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((nadd + tb - 1) / tb), tb, 0, h->stream>>>(
+        h->d_stage_src + 3 * soff[src_cloud[k]], (unsigned)nadd, h->d_acc[k], d_pose, cur)));
+    h->acc_cur[k] ^= 1;
+    if ((rc = voxel_pipeline(h, h->d_acc[k], nall, cur, (unsigned)nadd, nullptr, nullptr, d_pose, len[k], vox[k], h->d_acc_tmp,
+                             acc_count(h, k))) != TLOAM_B200_OK) return rc;
     // the down-sampled cloud becomes the accumulator (swap buffers)
     double* t = h->d_acc[k]; h->d_acc[k] = h->d_acc_tmp; h->d_acc_tmp = t;
     size_t tc = h->cap_acc[k]; h->cap_acc[k] = h->cap_acc_tmp; h->cap_acc_tmp = tc;
-    h->n_acc[k] = nout;
+    h->n_acc[k] = nall;
+    h->cum_add[k] += nadd;
+  }
+  // asynchronous read-back of the two exact counts (tightens the bounds of later frames)
+  {
+    tloam_b200_handle::CntProbe& pr = h->probes[h->probe_next];
+    if (!pr.pending || cudaEventQuery(pr.ev) == cudaSuccess) {
+      if (pr.pending) { pr.pending = false; for (int k = 0; k < 2; ++k) if (pr.cum[k] >= h->known_cum[k]) { h->known_cum[k] = pr.cum[k]; h->known_cnt[k] = pr.h_vals[k]; } }
+      for (int k = 0; k < 2; ++k) {
+        CU_TRY(cudaMemcpyAsync(pr.h_vals + k, acc_count(h, k), sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        pr.cum[k] = h->cum_add[k];
+      }
+      CU_TRY(cudaEventRecord(pr.ev, h->stream));
+      pr.pending = true;
+      h->probe_next = (h->probe_next + 1) & 3;
+    } else {
+      cudaGetLastError();
+    }
   }
   return submap_set_target(h);                                   // :267
 }
 
+int tloam_b200_submap_update(tloam_b200_handle* h, const double pose[16], const double* planar_sub, size_t np,
+                             const double* sphere_sub, size_t ns) {
+  (void)sphere_sub; (void)ns;   // stored but never used by the reference (front_end.cpp:202-205, 220-230)
+  if (!pose) return TLOAM_B200_ERR_INVALID_ARG;
+  return submap_update_impl(h, pose, planar_sub, np);
+}
+
+// pose = the result of the frame that was just enqueued on this handle, read on the device: frames chain with no host
+// round trip (set_source -> scan_match_predicted_async -> submap_update_chained -> next frame)
+int tloam_b200_submap_update_chained(tloam_b200_handle* h, const double* planar_sub, size_t np) {
+  return submap_update_impl(h, nullptr, planar_sub, np);
+}
+
+// exact sizes (synchronises: inspection / tests)
 int tloam_b200_submap_sizes(tloam_b200_handle* h, size_t n[4]) {
   if (!h || !n) return TLOAM_B200_ERR_INVALID_ARG;
   if (!h->submap_ready) return TLOAM_B200_ERR_NOT_READY;
-  n[0] = h->n_acc[0]; n[1] = h->sphere_is_init ? h->n_sphere0 : h->n_cat; n[2] = h->n_cat; n[3] = h->n_acc[1];
+  CU_TRY(cudaSetDevice(h->device));
+  unsigned cnt[2];
+  for (int k = 0; k < 2; ++k) CU_TRY(cudaMemcpyAsync(h->h_result + 28 + k, acc_count(h, k), sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 2; ++k) memcpy(&cnt[k], h->h_result + 28 + k, sizeof(unsigned));
+  n[0] = cnt[0]; n[1] = h->sphere_is_init ? h->n_sphere0 : h->n_cat; n[2] = h->n_cat; n[3] = cnt[1];
   return TLOAM_B200_OK;
 }
 
@@ -1703,7 +1913,8 @@ int tloam_b200_submap_download(tloam_b200_handle* h, int cloud, double* out, siz
   if (!h || !out || cloud < 0 || cloud > 3) return TLOAM_B200_ERR_INVALID_ARG;
   if (!h->submap_ready) return TLOAM_B200_ERR_NOT_READY;
   size_t n[4];
-  tloam_b200_submap_sizes(h, n);
+  const int rc = tloam_b200_submap_sizes(h, n);
+  if (rc != TLOAM_B200_OK) return rc;
   if (capacity_points < n[cloud]) return TLOAM_B200_ERR_INVALID_ARG;
   const double* src = cloud == 0 ? h->d_acc[0] : cloud == 3 ? h->d_acc[1] : (cloud == 1 && h->sphere_is_init) ? h->d_sphere0 : h->d_cat;
   CU_TRY(cudaSetDevice(h->device));

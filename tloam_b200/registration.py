@@ -119,16 +119,27 @@ class LocalRegistration:
         ns = (C.c_size_t * 4)(*[int(t.shape[0]) for t in tensors])
         return ptrs, ns
 
-    def set_input_source_device(self, tensors):
+    def _order_after_producer(self, tensors, producer_stream):
+        """The tensors are read IN PLACE by kernels on the handle's stream: order that stream behind the stream that
+        produced them (default: torch's current stream on the tensors' device) -- a device-side wait, the host does not
+        block -- and tell torch's caching allocator that another stream uses the memory."""
+        if producer_stream is None:
+            import torch
+            producer_stream = torch.cuda.current_stream(tensors[0].device).cuda_stream
+        self._check(self._L.tloam_b200_wait_stream(self._h, C.c_void_p(int(producer_stream))), "wait_stream")
+
+    def set_input_source_device(self, tensors, producer_stream=None):
         """tensors: 4 CUDA float64 (n,3) contiguous torch tensors on this handle's device."""
         ptrs, ns = self._device_args(tensors)
+        self._order_after_producer(tensors, producer_stream)
         self._check(self._L.tloam_b200_set_source_device(self._h, ptrs, ns), "set_input_source_device")
         self.n_source = [int(t.shape[0]) for t in tensors]
         self._keep_source = list(tensors)     # read in place by kernels still in flight: keep them alive until replaced
         return True
 
-    def set_input_target_device(self, tensors):
+    def set_input_target_device(self, tensors, producer_stream=None):
         ptrs, ns = self._device_args(tensors)
+        self._order_after_producer(tensors, producer_stream)
         self._check(self._L.tloam_b200_set_target_device(self._h, ptrs, ns), "set_input_target_device")
         self._keep_target = list(tensors)     # idem
         return True
@@ -185,6 +196,11 @@ class LocalRegistration:
         self._check(self._L.tloam_b200_get_pose_increment(self._h, _dp(out)), "get_pose_increment")
         return out.reshape(4, 4).T.copy()
 
+    def dense_check_counters(self):
+        out = (C.c_uint * 8)()
+        self._check(self._L.tloam_b200_dense_check_counters(self._h, out), "dense_check_counters")
+        return [int(v) for v in out]
+
     def synchronize(self):
         self._check(self._L.tloam_b200_synchronize(self._h), "synchronize")
 
@@ -217,6 +233,26 @@ class LocalRegistration:
         a = _f64(planar_sub).reshape(-1, 3)
         b = _f64(sphere_sub if sphere_sub is not None else np.zeros((0, 3))).reshape(-1, 3)
         self._check(self._L.tloam_b200_submap_update(self._h, _dp(p), _dp(a), a.shape[0], _dp(b), b.shape[0]), "submap_update")
+
+    def submap_update_chained(self, planar_sub):
+        """FrontEnd::updateSubmap with the pose of the frame that was just enqueued, read on the device."""
+        a = _f64(planar_sub).reshape(-1, 3)
+        self._keep_planar = a
+        self._check(self._L.tloam_b200_submap_update_chained(self._h, _dp(a), a.shape[0]), "submap_update_chained")
+
+    def set_async_inputs(self, on):
+        self._check(self._L.tloam_b200_set_async_inputs(self._h, 1 if on else 0), "set_async_inputs")
+
+    def set_frame_fitness(self, on):
+        self._check(self._L.tloam_b200_set_frame_fitness(self._h, 1 if on else 0), "set_frame_fitness")
+
+    def get_frame_fitness(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._L.tloam_b200_get_frame_fitness(self._h, C.byref(a), C.byref(b)), "get_frame_fitness")
+        return a.value, b.value
+
+    def scan_matching_predicted_async(self):
+        self._check(self._L.tloam_b200_scan_match_predicted_async(self._h), "scan_matching_predicted_async")
 
     def submap_cloud(self, cloud):
         n = (C.c_size_t * 4)()
@@ -346,6 +382,12 @@ class LocalRegistration:
         a = np.zeros(6)
         self._check(self._L.tloam_b200_se3_log(self._h, _dp(t), _dp(a)), "se3_log")
         return a
+
+    def min_on_boundary_2d(self, B, g, radius):
+        B, g = _f64(B).reshape(4), _f64(g).reshape(2)
+        y = np.zeros(2)
+        self._check(self._L.tloam_b200_min_on_boundary_2d(self._h, _dp(B), _dp(g), float(radius), _dp(y)), "min_on_boundary_2d")
+        return y
 
     def se3_plus(self, x, d):
         x, d = _f64(x), _f64(d)
