@@ -251,10 +251,13 @@ def run_batch(breg, data, torch, warmup, steps, mode="device"):
 
 
 def run_stream_device_submap(reg, frames, prev_gt, torch, warmup, steps):
-    """(f)-1: the local map is maintained ON THE DEVICE (tloam_b200_submap_*), as FrontEnd::updateSubmap does on the
-    CPU (ref: src/front_end/front_end.cpp:201-267): per frame only the scan features (pinned host, ~1 MB) cross PCIe.
-    The map is seeded from frame 0's synthetic map and then grows from the registered scans.
-    Returns (ms_total_timed, h2d_bytes_per_step, final_err_m)."""
+    """(f)-1 + (f)-3: the CHAINED device flow -- the local map is maintained on the device (tloam_b200_submap_*), as
+    FrontEnd::updateSubmap does on the CPU (ref: src/front_end/front_end.cpp:201-267); the pose prediction is the
+    device-side constant-velocity model (:329-330); the map update reads the pose on the device
+    (submap_update_chained); getFitnessScore runs inside every frame; the host stays one frame ahead of the GPU
+    (pipelined results): no host synchronisation between registration and map update, only the scan features
+    (pinned host, ~1 MB) cross PCIe.  The map is seeded from frame 0's synthetic map and grows from the registered scans.
+    Returns (ms_total_timed, h2d_bytes_per_step, final_err_m, poses)."""
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     scans = [[pin(c) for c in fr["scan"]] for fr in frames]
     for sc in scans:
@@ -262,24 +265,36 @@ def run_stream_device_submap(reg, frames, prev_gt, torch, warmup, steps):
             torch.from_numpy(a).cuda(non_blocking=True)
     f0 = frames[0]
     reg.submap_init(f0["map"][0], f0["map"][3], f0["map"][2], f0["map"][1])
+    # pose history so that frame 0's device-side prediction is ground truth perturbed like first_predict()
+    p0 = first_predict(frames[0])
+    reg.set_pose_history(p0, p0)                     # last == curr: the first prediction is p0 itself
+    reg.set_async_inputs(True)
+    reg.set_frame_fitness(True)
     torch.cuda.synchronize()
-    last, cur = prev_gt.copy(), None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    err = 0.0
+    poses = []
     for k, fr in enumerate(frames):
         if k == warmup:
+            while len(poses) < k:
+                poses.append(reg.get_result())
             torch.cuda.synchronize()
             e0.record()
-        predict = first_predict(fr) if cur is None else predict_next(last, cur)
         reg.set_input_source(scans[k])
-        T = reg.scan_matching(predict)
-        reg.submap_update(T, scans[k][2], scans[k][1])          # planar window <- this frame's planar features
-        err = pose_err(T, fr["T_gt"])[0]
-        last, cur = (cur if cur is not None else prev_gt), T
+        reg.scan_matching_predicted_async()
+        reg.submap_update_chained(scans[k][2])          # planar window <- this frame's planar features
+        if k >= 1 and len(poses) < k:
+            poses.append(reg.get_result())              # frame k-1: the host is one frame ahead
+    while len(poses) < len(frames):
+        poses.append(reg.get_result())
+    reg.synchronize()
     e1.record()
     torch.cuda.synchronize()
+    fit = reg.get_frame_fitness()
+    reg.set_async_inputs(False)
+    reg.set_frame_fitness(False)
+    err = pose_err(poses[-1], frames[-1]["T_gt"])[0]
     h2d = sum(a.nbytes for a in scans[0]) + scans[0][2].nbytes
-    return e0.elapsed_time(e1), h2d, err
+    return e0.elapsed_time(e1), h2d, err, poses, fit
 
 
 def reference_arm(args, rank, world):
@@ -404,7 +419,7 @@ def main():
     gt_err = max(pose_err(T, fr["T_gt"])[0] for T, fr in zip(poses, frames))
 
     # ---- (f)-1: same stream with the map maintained on the device (informational; the headline stays `e2e`) ----
-    ms_sub, h2d_sub, err_sub = run_stream_device_submap(reg, frames, prev_gt, torch, args.warmup, args.steps)
+    ms_sub, h2d_sub, err_sub, poses_sub, fit_sub = run_stream_device_submap(reg, frames, prev_gt, torch, args.warmup, args.steps)
     barrier()
     if world > 1:
         t = torch.tensor([ms_sub], dtype=torch.float64, device="cuda")
@@ -571,7 +586,10 @@ def main():
         line["stream_device_submap"] = {
             "value": world * args.steps / (ms_sub * 1e-3), "unit": UNIT, "ms_per_step": ms_sub / args.steps,
             "h2d_bytes_per_step": h2d_sub, "err_vs_ground_truth_last_frame_m": err_sub,
-            "what": "set_source (pinned host scan) + scan_match + tloam_b200_submap_update per frame; the map never leaves HBM"}
+            "fraction_of_value": (world * args.steps / (ms_sub * 1e-3)) / fps, "fitness_last_frame": list(fit_sub),
+            "what": "chained device flow: set_source (pinned host scan, async) + scan_match_predicted_async (device-side prediction, "
+                    "getFitnessScore inside the frame) + submap_update_chained (pose and voxel counts stay on the device); the host runs one "
+                    "frame ahead (pipelined results), no host synchronisation between registration and map update; the map never leaves HBM"}
         if batched:
             line["batched"] = batched
         if feat:

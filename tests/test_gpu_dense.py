@@ -33,11 +33,12 @@ def make_reg(dense, **cfg):
     import tloam_b200
     os.environ["TLOAM_B200_DENSE"] = "1" if dense else "0"
     os.environ["TLOAM_B200_DENSE_CHECK"] = "1"       # every dense query is re-searched by the plain path on the device
+    os.environ["TLOAM_B200_NO_FUSE"] = "1"           # both runs take the un-fused kernel sequence: same reduction tree
     try:
         return tloam_b200.LocalRegistration(**cfg)
     finally:
-        os.environ.pop("TLOAM_B200_DENSE", None)
-        os.environ.pop("TLOAM_B200_DENSE_CHECK", None)
+        for k in ("TLOAM_B200_DENSE", "TLOAM_B200_DENSE_CHECK", "TLOAM_B200_NO_FUSE"):
+            os.environ.pop(k, None)
 
 
 def run(sc, dense, **cfg):
@@ -63,9 +64,9 @@ def same_trace(a, b):
         assert np.array_equal(np.array(a.outer[o].x_end), np.array(b.outer[o].x_end))
 
 
-def very_dense_scene(seed=5, n_floor=150_000, n_wall=100_000, n_scan=3000):
-    """A 4 x 4 m floor patch at ~9400 points / m^2 (2300 per 0.5 m cell, 21k in a 9-cell neighbourhood: several staging
-    passes of kDenseCap = 5120) and a wall."""
+def very_dense_scene(seed=5, n_floor=300_000, n_wall=120_000, n_scan=3000):
+    """A 4 x 4 m floor patch at ~18700 points / m^2 (4700 per 0.5 m cell, 42k in a 9-cell neighbourhood: several staging
+    passes of kDenseCap = 10240) and a wall."""
     rng = np.random.default_rng(seed)
     floor = np.stack([rng.uniform(0, 4, n_floor), rng.uniform(0, 4, n_floor), rng.normal(0, 0.002, n_floor)], 1)
     wall = np.stack([rng.normal(0, 0.002, n_wall), rng.uniform(0, 4, n_wall), rng.uniform(0, 2, n_wall)], 1)
@@ -124,9 +125,11 @@ def test_dense_path_is_picked_automatically_for_a_dense_map():
     T2, s2 = r.scan_matching(sc["predict"], want_stats=True)
     r.close()
     assert s2.gpu_launches == 1 + 4 * (2 + 4 + 4)      # un-fused + 3 binning kernels + the dense search per outer
-    assert np.array_equal(T1, T2)
-    Ts, _ = run(sc, False, **cfg)
-    assert np.array_equal(T1, Ts)
+    assert s1.gpu_launches == 1 + 4 * (1 + 4)          # frame 1: no statistics yet -> lane-pair search, fused
+    Ts, _ = run(sc, False, **cfg)                      # un-fused lane-pair search: same reduction tree as the dense frame
+    assert np.array_equal(T2, Ts)
+    d = np.linalg.inv(T1) @ T2                         # fused frame 1: other summation tree, same factors
+    assert np.linalg.norm(d[:3, 3]) < 1e-7
 
 
 def test_dense_path_on_a_sparse_outdoor_scene_and_with_binding_caps(oracle):

@@ -147,3 +147,77 @@ def test_gpu_submap_with_device_resident_scans(oracle):
             a, b = sort_rows(reg.submap_cloud(c)), sort_rows(sm.cloud(c))
             assert a.shape == b.shape and np.allclose(a, b, atol=1e-9), c
     reg.close()
+
+
+@pytest.mark.gpu
+def test_chained_device_flow_matches_the_oracle_over_12_frames(oracle):
+    """(f)-3: frames chain on the device -- set_source -> scan_match_predicted_async (constant-velocity prediction from
+    the device-resident pose history) -> submap_update_chained (pose read on the device, voxel counts never leave it) ->
+    next frame, with the host one frame ahead (pipelined results) and getFitnessScore evaluated inside every frame.
+    The CPU restatement runs the same loop (ref: src/front_end/front_end.cpp:278-337): per-frame pose parity, final
+    maps equal as sets."""
+    import tloam_b200
+    frames = stream_inputs(13)
+    caps = dict(fitness_thres=0.3)
+    reg = tloam_b200.LocalRegistration(**caps)
+    orc = oracle.Oracle(threads_mode=1, **caps)
+    sm = oracle.Submap()
+    f0 = frames[0]
+    reg.submap_init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    sm.init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    # pose history: frame 0 and its predecessor (ground truth), so that the first prediction is the constant-velocity one
+    prev = f0["T_gt"] @ np.linalg.inv(np.linalg.inv(f0["T_gt"]) @ frames[1]["T_gt"])
+    reg.set_pose_history(prev, f0["T_gt"])
+    reg.set_async_inputs(True)
+    reg.set_frame_fitness(True)
+    got, fits = [], []
+    for k, fr in enumerate(frames[1:]):
+        reg.set_input_source(fr["scan"])
+        reg.scan_matching_predicted_async()
+        reg.submap_update_chained(fr["planar_sub"])
+        if k >= 1:                                                 # the host stays one frame ahead of the GPU
+            got.append(reg.get_result())
+            fits.append(reg.get_frame_fitness())
+    got.append(reg.get_result())
+    fits.append(reg.get_frame_fitness())
+    reg.set_async_inputs(False)
+    # the same loop on the CPU restatement
+    last, cur = prev, f0["T_gt"]
+    for k, fr in enumerate(frames[1:]):
+        predict = cur @ (np.linalg.inv(last) @ cur)
+        orc.set_input_target(sm.clouds())
+        orc.set_input_source(fr["scan"])
+        fo = orc.fitness()
+        rc, T, _ = orc.scan_matching(predict)
+        assert rc == 0
+        d = np.linalg.inv(T) @ got[k]
+        dt, dr = np.linalg.norm(d[:3, 3]), np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1))
+        assert dt < 1e-4 and dr < 1e-5, (k, dt, dr)
+        # the two maps differ by the pose difference (<= 1e-4 m): a few of the matches within fitness_thres may flip
+        assert np.isclose(fits[k][0], fo[0], rtol=2e-3) and np.isclose(fits[k][1], fo[1], rtol=2e-2, atol=1e-6), (k, fits[k], fo)
+        sm.update(T, fr["scan"][0], fr["scan"][3], fr["planar_sub"], fr["sphere_sub"])
+        last, cur = cur, T
+    for c in range(4):
+        a, b = sort_rows(reg.submap_cloud(c)), sort_rows(sm.cloud(c))
+        assert a.shape == b.shape, (c, a.shape, b.shape)
+        assert np.allclose(a, b, atol=2e-4), c                     # maps built from poses that agree to 1e-4 m
+    assert max(np.linalg.norm(t[:3, 3] - fr["T_gt"][:3, 3]) for t, fr in zip(got, frames[1:])) < 0.1
+    reg.close()
+
+
+@pytest.mark.gpu
+def test_submap_update_needs_a_staged_source():
+    """set_source_device BEFORE submap_init leaves nothing staged to append: a status, not stale points."""
+    import torch
+    import tloam_b200
+    frames = stream_inputs(2)
+    reg = tloam_b200.LocalRegistration()
+    dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for c in frames[1]["scan"]]
+    torch.cuda.synchronize()
+    reg.set_input_source_device(dev)
+    f0 = frames[0]
+    reg.submap_init(f0["scan"][0], f0["ground_raw"], f0["planar_sub"], f0["sphere_sub"])
+    with pytest.raises(tloam_b200.RegistrationError) as e:
+        reg.submap_update(frames[1]["T_gt"], frames[1]["planar_sub"], frames[1]["sphere_sub"])
+    assert e.value.status == 6
+    reg.close()

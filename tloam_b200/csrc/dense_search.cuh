@@ -22,11 +22,13 @@
 
 namespace tloam {
 
-constexpr int kDenseBlk = 128;             // threads per block = queries per work item
+constexpr int kDenseBlk = 128;             // queries per work item
+constexpr int kDenseLanes = 4;             // lanes that share one query (they split every candidate run 4 ways)
+constexpr int kDenseThreads = kDenseBlk * kDenseLanes;   // 512 threads: 16 warps, one block per SM (128 registers, ~195 KB)
 constexpr int kFine = 4;                   // fine cells per cell edge
 constexpr int kBox = 3 * kFine;            // fine cells per axis of the staged box
 constexpr int kBoxCells = kBox * kBox * kBox;
-constexpr int kDenseCap = 5120;            // staged points per pass (80 KB)
+constexpr int kDenseCap = 10240;           // staged points per pass (160 KB; one block per SM)
 
 struct DenseWork { int cx, cy, cz; unsigned qbeg; unsigned short qcnt; unsigned short cloud; };
 
@@ -163,7 +165,7 @@ struct DenseSmem {
   unsigned cursor[kBoxCells];
   unsigned run_beg[27], run_cnt[27];
   unsigned cp_src[32], cp_dst[32], cp_n[32];
-  unsigned scan_tmp[kDenseBlk / 32];
+  unsigned scan_tmp[kDenseThreads / 32];
   int ncopy, fill, run_i;
   unsigned run_o, work;
   unsigned long long mbar;
@@ -197,7 +199,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 // Persistent blocks; one work item (<= 128 queries of one map cell) per iteration.
-__global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
+__global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != kPhaseIter0) return;
   extern __shared__ unsigned char dense_raw[];
@@ -243,12 +245,15 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
       if (lane < 27) { sm.run_beg[lane] = beg; sm.run_cnt[lane] = h ? cnt : 0u; }
       if (lane == 0) { sm.run_i = 0; sm.run_o = 0u; }
     }
-    // ---- my query ----
-    const bool hasq = tid < (int)wk.qcnt;
+    // ---- my query: a QUAD of lanes serves one query (the quad splits every candidate run four ways; more warps per
+    //      SM for the same shared-memory footprint -- the search is a latency-bound dependent chain per lane) ----
+    const int qid = tid >> 2, sub = tid & 3;
+    const unsigned quadmask = 0xFu << (lane & ~3);
+    const bool hasq = qid < (int)wk.qcnt;
     int il = 0, gi = 0;
     double rx = 0.0, ry = 0.0, rz = 0.0;
     if (hasq) {
-      il = (int)a.cl[c].q_order[wk.qbeg + tid];
+      il = (int)a.cl[c].q_order[wk.qbeg + qid];
       gi = ctx.pad_off[c] + il;
       double qx, qy, qz;
       rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
       if (fill == 0) break;
       if (a.dbg && tid == 0) atomicAdd(&a.dbg[3], 1u);
       if (tid < sm.ncopy) tma_bulk_g2s(&sm.pts[sm.cp_dst[tid]], g.pts + sm.cp_src[tid], sm.cp_n[tid] * 16u, &sm.mbar);
-      for (int i = tid; i < kBoxCells; i += kDenseBlk) sm.cursor[i] = 0u;      // while the copies are in flight
+      for (int i = tid; i < kBoxCells; i += kDenseThreads) sm.cursor[i] = 0u;      // while the copies are in flight
       mbar_wait(&sm.mbar, parity);
       parity ^= 1u;
       __syncthreads();
@@ -294,10 +299,10 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
         const int fi = fclamp(((double)p.x - bx) * inv_e), fj = fclamp(((double)p.y - by) * inv_e), fk = fclamp(((double)p.z - bz) * inv_e);
         return (fk * kBox + fj) * kBox + fi;
       };
-      for (int i = tid; i < fill; i += kDenseBlk) atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u);
+      for (int i = tid; i < fill; i += kDenseThreads) atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u);
       __syncthreads();
       {
-        constexpr int kPer = (kBoxCells + kDenseBlk - 1) / kDenseBlk;      // consecutive entries per thread
+        constexpr int kPer = (kBoxCells + kDenseThreads - 1) / kDenseThreads;      // consecutive entries per thread
         const int i0 = tid * kPer;
         unsigned local = 0u;
         for (int i = i0; i < i0 + kPer && i < kBoxCells; ++i) local += sm.cursor[i];
@@ -308,20 +313,20 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
         unsigned run = incl - local;
         for (int wi = 0; wi < warp; ++wi) run += sm.scan_tmp[wi];
         for (int i = i0; i < i0 + kPer && i < kBoxCells; ++i) { const unsigned cn = sm.cursor[i]; sm.start[i] = run; sm.cursor[i] = run; run += cn; }
-        if (tid == kDenseBlk - 1) sm.start[kBoxCells] = (unsigned)fill;
+        if (tid == kDenseThreads - 1) sm.start[kBoxCells] = (unsigned)fill;
       }
       __syncthreads();
-      for (int i = tid; i < fill; i += kDenseBlk) sm.order[atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u)] = (unsigned short)i;
+      for (int i = tid; i < fill; i += kDenseThreads) sm.order[atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u)] = (unsigned short)i;
       __syncthreads();
       if (hasq) {
         // candidates are pre-filtered in FP32 on coordinates LOCAL to the staged box (p - box0 is exact in FP32: both are
         // multiples of the point's ulp and the difference is < 2 cells), with a margin that covers the FP32 rounding of
         // the query and of the arithmetic (< 1e-6 m^2 at cell <= 1 m); survivors get the exact FP64 expression
-        double bound = t.d2[4] < r2 ? t.d2[4] : r2;
+        double bound = t.d2[4] < r2 ? t.d2[4] : r2;       // lane-local: 5 points within it exist in THIS lane's list
         float boundf = (float)bound * 1.00001f + 2e-6f;
         auto scan = [&](unsigned b, unsigned en) {
 #pragma unroll 4
-          for (unsigned u = b; u < en; ++u) {
+          for (unsigned u = b + (unsigned)sub; u < en; u += (unsigned)kDenseLanes) {
             const float4 p = sm.pts[sm.order[u]];
             const float fx = (p.x - bxf) - qlx, fy = (p.y - byf) - qly, fz = (p.z - bzf) - qlz;
             const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
@@ -345,9 +350,19 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
         // (rho - 1) e away, so the walk stops as soon as that exceeds the K-th best distance (or the radius: shells
         // 0..kFine cover it, and they lie inside the staged box because the query sits in its middle third)
         for (int rho = 0; rho <= kFine; ++rho) {
+          // control flow is QUAD-uniform: the bound that prunes shells / rows / cells is the quad minimum of the
+          // lane-local bounds (any lane's full list proves K points within its bound), refreshed once per shell
+          {
+            double ob = __shfl_xor_sync(quadmask, bound, 1);
+            bound = ob < bound ? ob : bound;
+            ob = __shfl_xor_sync(quadmask, bound, 2);
+            bound = ob < bound ? ob : bound;
+            boundf = (float)bound * 1.00001f + 2e-6f;
+          }
+          const double qb = bound;
           if (rho >= 2) {
             const double lb = (double)(rho - 1) * e - 1e-9;
-            if (lb * lb > bound) break;
+            if (lb * lb > qb) break;
           }
           for (int dk = -rho; dk <= rho; ++dk) {
             const int k = qk + dk;
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
               if (j < 0 || j >= kBox) continue;
               const double gy = gap(ry, by, j, qj);
               const double g2 = gz * gz + gy * gy;
-              if (g2 > bound) continue;
+              if (g2 > qb) continue;
               const int row = (k * kBox + j) * kBox;
               const bool face = (dk == -rho || dk == rho || dj == -rho || dj == rho);
               if (face) {                                      // the whole x-extent of the shell
@@ -366,8 +381,8 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
                 scan(sm.start[row + i0], sm.start[row + i1 + 1]);
               } else {                                         // only the two end cells
                 const int il0 = qi - rho, ih0 = qi + rho;
-                if (il0 >= 0) { const double gx = gap(rx, bx, il0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + il0], sm.start[row + il0 + 1]); }
-                if (ih0 < kBox) { const double gx = gap(rx, bx, ih0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + ih0], sm.start[row + ih0 + 1]); }
+                if (il0 >= 0) { const double gx = gap(rx, bx, il0, qi); if (g2 + gx * gx <= qb) scan(sm.start[row + il0], sm.start[row + il0 + 1]); }
+                if (ih0 < kBox) { const double gx = gap(rx, bx, ih0, qi); if (g2 + gx * gx <= qb) scan(sm.start[row + ih0], sm.start[row + ih0 + 1]); }
               }
             }
           }
@@ -375,7 +390,20 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
       }
       __syncthreads();                         // everybody is done with the staged points before the next pass
     }
-    if (a.dbg && hasq) {                       // self-check against the thread-per-query search of map_grid.cuh
+    // ---- merge the quad's four sorted lists into lane 0 of the quad (two rounds of pull + insert) ----
+#pragma unroll
+    for (int step = 1; step <= 2; step <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const double od = __shfl_xor_sync(0xffffffffu, t.d2[j], step);
+        const int oi = __shfl_xor_sync(0xffffffffu, t.idx[j], step);
+        const float ox = __shfl_xor_sync(0xffffffffu, t.x[j], step), oy = __shfl_xor_sync(0xffffffffu, t.y[j], step);
+        const float oz = __shfl_xor_sync(0xffffffffu, t.z[j], step);
+        if ((sub & (2 * step - 1)) == 0 && oi != 0x7FFFFFFF) t.insert(od, oi, ox, oy, oz);
+      }
+    }
+    const bool owner = hasq && sub == 0;
+    if (a.dbg && owner) {                      // self-check against the thread-per-query search of map_grid.cuh
       TopK<5> ref;
       knn_search<5>(g, rx, ry, rz, r2, ref);
       bool bad = false;
@@ -386,7 +414,7 @@ __global__ void __launch_bounds__(kDenseBlk, 2) k_correspond_dense(const __grid_
     }
     if (a.dbg && tid == 0) atomicAdd(&a.dbg[2], 1u);
     // ---- fit + lazy GNC weight update + outputs (as k_correspond) ----
-    if (hasq) {
+    if (owner) {
       const int k = t.count();
       double nb[5][3];
 #pragma unroll

@@ -739,7 +739,7 @@ static int enqueue_correspond(tloam_b200_handle* h, const DeviceCtx& c) {
     TL_LAUNCH(TLOAM_B200_K_DENSE_BIN, (k_qbin_count<<<nb, kBlk, 0, h->stream>>>(c, da)));
     TL_LAUNCH(TLOAM_B200_K_DENSE_BIN, (k_qbin_offsets<<<(da.tslots + 255) / 256, 256, 0, h->stream>>>(c, da)));
     TL_LAUNCH(TLOAM_B200_K_DENSE_BIN, (k_qbin_scatter<<<nb, kBlk, 0, h->stream>>>(c, da)));
-    TL_LAUNCH(TLOAM_B200_K_DENSE, (k_correspond_dense<<<2 * h->num_sms, kDenseBlk, kDenseSmemBytes, h->stream>>>(c, da)));
+    TL_LAUNCH(TLOAM_B200_K_DENSE, (k_correspond_dense<<<h->num_sms, kDenseThreads, kDenseSmemBytes, h->stream>>>(c, da)));
   }
   TL_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<false><<<nb * 2, kBlk, 0, h->stream>>>(c, no_batch())));
   return TLOAM_B200_OK;

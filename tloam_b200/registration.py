@@ -106,6 +106,7 @@ class LocalRegistration:
         arrs, ptrs, ns = self._host_args(frame)
         self._check(self._L.tloam_b200_set_source(self._h, ptrs, ns), "set_input_source")
         self.n_source = [a.shape[0] for a in arrs]
+        self._keep_source_host = arrs         # pipelined mode (set_async_inputs): the upload may still be reading them
         return True
 
     def set_input_target(self, frame):
