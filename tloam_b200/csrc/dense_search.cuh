@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
     if (w >= nwork) break;
     const DenseWork wk = a.work[w];
     const int c = wk.cloud;
+    long long tk0 = 0, tk1 = 0, tk_wait = 0, tk_sort = 0, tk_search = 0;     // self-check mode: SM cycles per phase (thread 0)
+    if (a.dbg && tid == 0) tk0 = clock64();
     const GridDesc& g = ctx.grid[c];
     // ---- the <= 27 point runs of the neighbourhood (warp 0: 8 brick probes, then one cell per lane) ----
     if (warp == 0) {
@@ -290,10 +292,12 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       if (fill == 0) break;
       if (a.dbg && tid == 0) atomicAdd(&a.dbg[3], 1u);
       if (tid < sm.ncopy) tma_bulk_g2s(&sm.pts[sm.cp_dst[tid]], g.pts + sm.cp_src[tid], sm.cp_n[tid] * 16u, &sm.mbar);
+      if (a.dbg && tid == 0) tk1 = clock64();
       for (int i = tid; i < kBoxCells; i += kDenseThreads) sm.cursor[i] = 0u;      // while the copies are in flight
       mbar_wait(&sm.mbar, parity);
       parity ^= 1u;
       __syncthreads();
+      if (a.dbg && tid == 0) { const long long t = clock64(); tk_wait += t - tk1; tk1 = t; }
       // counting sort of the staged points into the fine grid (indices only: the points stay where TMA put them)
       auto fine_id = [&](const float4& p) {
         const int fi = fclamp(((double)p.x - bx) * inv_e), fj = fclamp(((double)p.y - by) * inv_e), fk = fclamp(((double)p.z - bz) * inv_e);
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       __syncthreads();
       for (int i = tid; i < fill; i += kDenseThreads) sm.order[atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u)] = (unsigned short)i;
       __syncthreads();
+      if (a.dbg && tid == 0) { const long long t = clock64(); tk_sort += t - tk1; tk1 = t; }
       if (hasq) {
         // candidates are pre-filtered in FP32 on coordinates LOCAL to the staged box (p - box0 is exact in FP32: both are
         // multiples of the point's ulp and the difference is < 2 cells), with a margin that covers the FP32 rounding of
@@ -389,6 +394,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         }
       }
       __syncthreads();                         // everybody is done with the staged points before the next pass
+      if (a.dbg && tid == 0) { const long long t = clock64(); tk_search += t - tk1; tk1 = t; }
     }
     // ---- merge the quad's four sorted lists into lane 0 of the quad (two rounds of pull + insert) ----
 #pragma unroll
@@ -412,7 +418,13 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       atomicAdd(&a.dbg[0], 1u);
       if (bad) { if (atomicAdd(&a.dbg[1], 1u) == 0u) { a.dbg[4] = (unsigned)gi; a.dbg[5] = (unsigned)c; a.dbg[6] = (unsigned)t.count(); a.dbg[7] = (unsigned)ref.count(); } }
     }
-    if (a.dbg && tid == 0) atomicAdd(&a.dbg[2], 1u);
+    if (a.dbg && tid == 0) {
+      atomicAdd(&a.dbg[2], 1u);
+      // [8] total item cycles / 64 (before the self-check), [9] TMA wait, [10] fine sort, [11] search, [12] queries <= 8
+      atomicAdd(&a.dbg[8], (unsigned)((clock64() - tk0) >> 6)); atomicAdd(&a.dbg[9], (unsigned)(tk_wait >> 6));
+      atomicAdd(&a.dbg[10], (unsigned)(tk_sort >> 6)); atomicAdd(&a.dbg[11], (unsigned)(tk_search >> 6));
+      if (wk.qcnt <= 8) atomicAdd(&a.dbg[12], 1u);
+    }
     // ---- fit + lazy GNC weight update + outputs (as k_correspond) ----
     if (owner) {
       const int k = t.count();

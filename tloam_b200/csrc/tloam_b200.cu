@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -15,6 +16,7 @@
 #include "dense_search.cuh"
 #include "submap.cuh"
 #include "feature_extract.cuh"
+#include "ground_extract.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -112,6 +114,7 @@ struct tloam_b200_handle {
   // ---- PCA feature extraction ((f)-2): one arena, carved up per call ----
   unsigned char* d_fe = nullptr;           size_t cap_fe = 0;  bool fe_attr_set = false;
   double* d_pose = nullptr;
+  unsigned char* d_ge = nullptr;           size_t cap_ge = 0;   // ground extraction ((f)-4) arena
   // ---- dense-map correspondence path (dense_search.cuh): query binning scratch + the search-path decision ----
   unsigned char* d_dense = nullptr;        size_t cap_dense = 0, dense_zero_bytes = 0;
   DenseArgs dargs, gdargs;                 // current / captured in the graph
@@ -266,7 +269,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   cudaFree(h->d_partial); cudaFree(h->d_counter); if (h->own_state) cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
   cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
-  cudaFree(h->d_cnt); cudaFree(h->d_fit);
+  cudaFree(h->d_cnt); cudaFree(h->d_fit); cudaFree(h->d_ge);
   for (auto& pr : h->probes) { if (pr.ev) cudaEventDestroy(pr.ev); if (pr.h_vals) cudaFreeHost(pr.h_vals); }
   cudaFree(h->d_up); cudaFree(h->d_vox); cudaFree(h->d_pose); cudaFree(h->d_fe);
   for (double* p : h->ring) cudaFree(p);
@@ -945,11 +948,11 @@ int tloam_b200_wait_stream(tloam_b200_handle* h, void* producer_stream) {
 
 // self-check counters of the dense correspondence path (TLOAM_B200_DENSE_CHECK=1), accumulated since creation:
 // [0] queries searched, [1] kNN lists that differ from the plain search, [2] work items, [3] staging passes
-int tloam_b200_dense_check_counters(tloam_b200_handle* h, unsigned out[8]) {
+int tloam_b200_dense_check_counters(tloam_b200_handle* h, unsigned out[16]) {
   if (!h || !out) return TLOAM_B200_ERR_INVALID_ARG;
   CU_TRY(cudaSetDevice(h->device));
   CU_TRY(cudaStreamSynchronize(h->stream));
-  CU_TRY(cudaMemcpy(out, h->d_cnt + 16, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(out, h->d_cnt + 16, 16 * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return TLOAM_B200_OK;
 }
 
@@ -1920,6 +1923,114 @@ int tloam_b200_submap_download(tloam_b200_handle* h, int cloud, double* out, siz
   CU_TRY(cudaSetDevice(h->device));
   if (n[cloud]) CU_TRY(cudaMemcpyAsync(out, src, n[cloud] * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// "next" row (f)-4, first part: multi-region ground extraction (ground_extract.cuh)
+// ---------------------------------------------------------------------------------------------
+void tloam_b200_ground_default_config(tloam_ground_config* c) {   // ref: config/mapping/segmentation.yaml
+  c->sensor_model = 64; c->sensor_height = 1.73; c->vertical_res = 0.4; c->init_angle = -24.9;
+  c->sensor_min_range = 1.0; c->sensor_max_range = 120.0;
+  c->quadrant = 4; c->num_sec = 3; c->plane_dis = 0.3; c->max_iter = 3; c->ground_seed_num = 20;
+}
+
+// Segmentation::initSections, ref: segmentation.cpp:174-221 (host side: 64 iterations of scalar arithmetic).  Restated
+// literally: the `continue` at :203-206 also skips the angle increment, so the table stalls at the first >= 5 m jump and
+// only two section bounds are produced with the shipped configuration.
+static int ground_section_bounds(const tloam_ground_config& c, float out[4]) {
+  int nb = 0;
+  int boundary[4] = {0, 0, 0, 0};
+  const int section_width = static_cast<int>(std::ceil(1.0 * c.sensor_model) / c.num_sec);
+  for (int i = 0; i < c.num_sec; ++i) boundary[i] = section_width * (i + 1) - 1;
+  double prev_radius = 0.0, angle = c.init_angle;
+  int sec = 0;
+  for (int i = 0; i < c.sensor_model; ++i) {
+    if (c.sensor_model == 64 && i == 31) angle += 1.7;
+    double cur = c.sensor_height / std::tan(std::fabs(angle) / 180.0 * M_PI);
+    cur = cur < c.sensor_max_range ? cur : c.sensor_max_range;
+    if (i >= 1) {
+      const double dis = std::fabs(cur - prev_radius);
+      if (dis >= 5.0 || dis <= 0.0) continue;
+    }
+    if (sec < c.num_sec && i == boundary[sec] && sec <= 3) {
+      const double theta = std::fabs(angle / 180 * M_PI);
+      out[nb++] = (theta != 0 && i < c.sensor_model) ? static_cast<float>(c.sensor_height / std::tan(theta))
+                                                      : static_cast<float>(c.sensor_max_range);
+      ++sec;
+    }
+    prev_radius = cur;
+    angle += c.vertical_res;
+  }
+  return nb;
+}
+
+int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* cfg, const double* xyz, size_t n,
+                              size_t* ground_index, size_t* n_ground, size_t* object_index, size_t* n_object, int* beam,
+                              int* region, double* height_threshold, double* planes) {
+  if (!h || !cfg || !ground_index || !n_ground || !object_index || !n_object) return TLOAM_B200_ERR_INVALID_ARG;
+  *n_ground = *n_object = 0;
+  if (cfg->sensor_model != 64 || cfg->quadrant != 4 || cfg->num_sec < 1 || cfg->num_sec > 3 || cfg->max_iter < 1 ||
+      cfg->max_iter > kGeMaxIter || cfg->ground_seed_num < 1)
+    return TLOAM_B200_ERR_INVALID_ARG;                            // only the HDL-64E branch is built (:439-441)
+  if (planes) for (int i = 0; i < 12 * kGeMaxIter * 4; ++i) planes[i] = std::nan("");
+  if (n == 0) { if (height_threshold) *height_threshold = 1.0; return TLOAM_B200_OK; }   // :335-338
+  if (!xyz || n > ((size_t)1 << 30)) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  GeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = (unsigned)n; a.nchunk = (unsigned)((n + kGeChunk - 1) / kGeChunk);
+  a.sensor_model = cfg->sensor_model; a.num_sec = cfg->num_sec; a.max_iter = cfg->max_iter; a.seed_num = cfg->ground_seed_num;
+  a.sensor_height = cfg->sensor_height; a.min_range = cfg->sensor_min_range; a.max_range = cfg->sensor_max_range;
+  a.plane_dis = cfg->plane_dis;
+  a.nbounds = ground_section_bounds(*cfg, a.bounds);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
+  const size_t o_pts = take(n * 24), o_ct = take(a.nchunk * 4), o_cs = take(a.nchunk * 8), o_sc = take(64), o_beam = take(n * 4),
+               o_key = take(n), o_cc = take((size_t)a.nchunk * kGeKeys * 4), o_kb = take((kGeKeys + 1) * 4), o_ord = take(n * 4),
+               o_flag = take(n), o_lists = take(2 * n * 4), o_rc = take(12 * 2 * 4), o_pl = take(12 * kGeMaxIter * 4 * 8),
+               o_og = take(n * 4), o_oo = take(n * 4), o_oc = take(64);
+  if (off > h->cap_ge) {
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_ge); h->d_ge = nullptr; h->cap_ge = 0;
+    CU_TRY(cudaMalloc(&h->d_ge, off + off / 4));
+    h->cap_ge = off + off / 4;
+  }
+  unsigned char* b = h->d_ge;
+  a.pts = (const double*)(b + o_pts); a.chunk_trans = (unsigned*)(b + o_ct); a.chunk_sum = (double*)(b + o_cs);
+  a.scal = (double*)(b + o_sc); a.beam = (int*)(b + o_beam); a.key = b + o_key; a.chunk_cnt = (unsigned*)(b + o_cc);
+  a.key_base = (unsigned*)(b + o_kb); a.order = (unsigned*)(b + o_ord); a.flag = b + o_flag; a.lists = (unsigned*)(b + o_lists);
+  a.reg_cnt = (unsigned*)(b + o_rc); a.planes = (double*)(b + o_pl); a.out_ground = (unsigned*)(b + o_og);
+  a.out_object = (unsigned*)(b + o_oo); a.out_counts = (unsigned*)(b + o_oc);
+  CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_pre<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scan1<<<1, 1024, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_region<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scan2<<<1, 1024, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scatter<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_fit<<<4 * cfg->num_sec, kGeFitThreads, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_emit<<<dim3(32, 25), 256, 0, h->stream>>>(a)));
+  CU_TRY(cudaGetLastError());
+  // counts + threshold first (one small copy each, one synchronisation), then exactly the list prefixes
+  std::vector<unsigned> gi(n), oi(n);
+  CU_TRY(cudaMemcpyAsync(h->h_result + 28, a.out_counts, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaMemcpyAsync(h->h_result + 29, a.scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  unsigned counts[2];
+  memcpy(counts, h->h_result + 28, sizeof(counts));
+  if (height_threshold) *height_threshold = h->h_result[29];
+  if (counts[0]) CU_TRY(cudaMemcpyAsync(gi.data(), a.out_ground, counts[0] * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  if (counts[1]) CU_TRY(cudaMemcpyAsync(oi.data(), a.out_object, counts[1] * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  if (beam) CU_TRY(cudaMemcpyAsync(beam, a.beam, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<unsigned char> keys;
+  if (region) { keys.resize(n); CU_TRY(cudaMemcpyAsync(keys.data(), a.key, n, cudaMemcpyDeviceToHost, h->stream)); }
+  if (planes) CU_TRY(cudaMemcpyAsync(planes, a.planes, 12 * kGeMaxIter * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  for (unsigned i = 0; i < counts[0]; ++i) ground_index[i] = gi[i];
+  for (unsigned i = 0; i < counts[1]; ++i) object_index[i] = oi[i];
+  if (region) for (size_t i = 0; i < n; ++i) region[i] = keys[i];
+  *n_ground = counts[0]; *n_object = counts[1];
   return TLOAM_B200_OK;
 }
 

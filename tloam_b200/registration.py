@@ -198,7 +198,7 @@ class LocalRegistration:
         return out.reshape(4, 4).T.copy()
 
     def dense_check_counters(self):
-        out = (C.c_uint * 8)()
+        out = (C.c_uint * 16)()
         self._check(self._L.tloam_b200_dense_check_counters(self._h, out), "dense_check_counters")
         return [int(v) for v in out]
 
@@ -307,6 +307,29 @@ class LocalRegistration:
                                                 out["num_sum"].ctypes.data_as(ip), out["neigh"].ctypes.data_as(ip)),
                     "pca_info")
         return out
+
+    # ---- "next" row (f)-4, first part: ground extraction (ref: segmentation.cpp:738-770) ----
+    def ground_extract(self, scan, **overrides):
+        """Segmentation::groundRemove on the device.  Returns dict(ground, object, beam, region, height_threshold, planes)."""
+        a = _f64(scan).reshape(-1, 3)
+        n = a.shape[0]
+        c = _lib.GroundConfig()
+        self._L.tloam_b200_ground_default_config(C.byref(c))
+        for k, v in overrides.items():
+            setattr(c, k, v)
+        g = np.zeros(max(n, 1), dtype=np.uintp)
+        o = np.zeros(max(n, 1), dtype=np.uintp)
+        ng, no = C.c_size_t(0), C.c_size_t(0)
+        beam = np.zeros(max(n, 1), dtype=np.int32)
+        region = np.zeros(max(n, 1), dtype=np.int32)
+        thr = C.c_double(0)
+        planes = np.zeros((12, 8, 4))
+        szp, ip = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+        self._check(self._L.tloam_b200_ground_extract(self._h, C.byref(c), _dp(a), n, g.ctypes.data_as(szp), C.byref(ng),
+                                                      o.ctypes.data_as(szp), C.byref(no), beam.ctypes.data_as(ip),
+                                                      region.ctypes.data_as(ip), C.byref(thr), _dp(planes)), "ground_extract")
+        return dict(ground=g[:ng.value].copy(), object=o[:no.value].copy(), beam=beam[:n].copy(), region=region[:n].copy(),
+                    height_threshold=thr.value, planes=planes)
 
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):

@@ -397,3 +397,41 @@ def general_cloud(n=50_000, seed=20260924 + 4242, noise=0.004):
     clutter = np.c_[rng.uniform(-45, 45, (max(n - pts.shape[0], 0), 2)), rng.uniform(-1.5, 3.0, max(n - pts.shape[0], 0))]
     pts = np.vstack([pts, clutter])
     return np.ascontiguousarray(pts[rng.permutation(pts.shape[0])])
+
+
+def raw_scan(seed=20260924 + 5151, n_az=1875, noise=0.01, lane_half_width=8.0, drop=0.03):
+    """A raw HDL-64E-shaped scan in the sensor frame, in the point ORDER the reference's beam estimate assumes
+    (ref: src/models/segmentation/segmentation.cpp:341-384): beam after beam, every beam sweeping the azimuth from +x
+    counter-clockwise through the four quadrants; elevation angles -24.9 deg + 0.4 deg per beam with the 1.7 deg gap
+    after beam 31 (:194-196).  64 x 1875 = 120 000 rays are cast against a ground plane (z = -1.73 with gentle
+    undulation), two street-canyon walls and a few boxes; rays without a return within 120 m are dropped."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    elev = np.array([-24.9 + 0.4 * i + (1.7 if i >= 31 else 0.0) for i in range(64)]) * np.pi / 180.0
+    az = (np.arange(n_az) + 0.5) * (2 * np.pi / n_az)
+    el, a = np.meshgrid(elev, az, indexing="ij")
+    d = np.stack([np.cos(el) * np.cos(a), np.cos(el) * np.sin(a), np.sin(el)], axis=-1).reshape(-1, 3)
+    t = np.full(len(d), np.inf)
+    # ground
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tg = np.where(d[:, 2] < -1e-6, -1.73 / d[:, 2], np.inf)
+    t = np.minimum(t, tg)
+    # walls y = +-lane_half_width, 6 m high
+    for yw in (lane_half_width, -lane_half_width):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tw = np.where(d[:, 1] * yw > 1e-9, yw / d[:, 1], np.inf)
+        z = tw * d[:, 2]
+        t = np.minimum(t, np.where((z < 4.3) & (z > -1.73), tw, np.inf))
+    # boxes (cars): axis-aligned, slab test
+    for _ in range(12):
+        c = np.array([rng.uniform(-40, 40), rng.uniform(-6, 6), -1.73 + 0.75])
+        if abs(c[0]) < 4 and abs(c[1]) < 3:
+            continue
+        h = np.array([2.2, 0.9, 0.75])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t1, t2 = (c - h) / d, (c + h) / d
+        tn, tf = np.nanmax(np.minimum(t1, t2), axis=1), np.nanmin(np.maximum(t1, t2), axis=1)
+        t = np.minimum(t, np.where((tn <= tf) & (tn > 0), tn, np.inf))
+    keep = np.isfinite(t) & (t < 120.0) & (t > 3.0) & (rng.random(len(t)) >= drop)
+    p = d[keep] * t[keep, None]
+    p[:, 2] += 0.03 * np.sin(0.15 * p[:, 0]) * np.cos(0.11 * p[:, 1])           # gentle ground undulation
+    return np.ascontiguousarray(p + rng.normal(0, noise, p.shape))
