@@ -198,6 +198,19 @@ int tloam_b200_map_blob_size(tloam_b200_handle* h, size_t* bytes);
 int tloam_b200_map_export(tloam_b200_handle* h, void* d_dst, size_t bytes);       /* D2D copy out */
 int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes); /* D2D copy in, adopt */
 int tloam_b200_get_map_origin(tloam_b200_handle* h, double origin[3]);
+/* Zero-copy form (config 4: ONE collective per map epoch, no size handshake, no host synchronisation, no staging
+ * copies).  The blob layout is a pure function of the configuration and the four point counts, so every rank can lay
+ * the incoming blob out from n[4] alone.
+ *   sender:    tloam_b200_map_send_buffer  -> the built blob itself; order the stream of the collective behind the build
+ *              with tloam_b200_signal_stream(h, that_stream)
+ *   receiver:  tloam_b200_map_recv_buffer  -> a SECOND blob of the handle (frames keep registering against the active map
+ *              while the next one is in flight); enqueue the collective into it on any stream; then
+ *              tloam_b200_map_adopt(h, that_stream): device-side wait + pointer swap, nothing else */
+int tloam_b200_map_layout_bytes(tloam_b200_handle* h, const size_t n[4], size_t* bytes);
+int tloam_b200_map_send_buffer(tloam_b200_handle* h, void** d_ptr, size_t* bytes);
+int tloam_b200_map_recv_buffer(tloam_b200_handle* h, const size_t n[4], void** d_ptr, size_t* bytes);
+int tloam_b200_map_adopt(tloam_b200_handle* h, void* producer_stream);
+int tloam_b200_signal_stream(tloam_b200_handle* h, void* consumer_stream);
 
 /* ---- piecewise entry points (parity tests; host arrays in, host arrays out, computed on the GPU) ---- */
 /* Exact radius-truncated kNN on the built map of `cloud` (KDTreeFlann::SearchHybrid semantics): idx/d2 are

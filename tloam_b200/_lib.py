@@ -109,7 +109,8 @@ EXPORTS = [
     "tloam_b200_batch_set_profiling", "tloam_b200_batch_get_profile",
     "tloam_b200_submap_update_chained", "tloam_b200_set_frame_fitness", "tloam_b200_get_frame_fitness",
     "tloam_b200_set_async_inputs", "tloam_b200_wait_stream", "tloam_b200_dense_check_counters",
-    "tloam_b200_ground_default_config", "tloam_b200_ground_extract",
+    "tloam_b200_ground_default_config", "tloam_b200_ground_extract", "tloam_b200_map_layout_bytes",
+    "tloam_b200_map_send_buffer", "tloam_b200_map_recv_buffer", "tloam_b200_map_adopt", "tloam_b200_signal_stream",
 ]
 
 _lib = None
@@ -207,6 +208,11 @@ def load():
     L.tloam_b200_set_async_inputs.argtypes = [vp, C.c_int]
     L.tloam_b200_wait_stream.argtypes = [vp, vp]
     L.tloam_b200_dense_check_counters.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.tloam_b200_map_layout_bytes.argtypes = [vp, szp, szp]
+    L.tloam_b200_map_send_buffer.argtypes = [vp, C.POINTER(vp), szp]
+    L.tloam_b200_map_recv_buffer.argtypes = [vp, szp, C.POINTER(vp), szp]
+    L.tloam_b200_map_adopt.argtypes = [vp, vp]
+    L.tloam_b200_signal_stream.argtypes = [vp, vp]
     L.tloam_b200_ground_default_config.argtypes = [C.POINTER(GroundConfig)]
     L.tloam_b200_ground_default_config.restype = None
     L.tloam_b200_ground_extract.argtypes = [vp, C.POINTER(GroundConfig), dp, C.c_size_t, szp, szp, szp, szp, ip, ip, dp, dp]

@@ -23,8 +23,8 @@
 namespace tloam {
 
 constexpr int kDenseBlk = 128;             // queries per work item
-constexpr int kDenseLanes = 4;             // lanes that share one query (they split every candidate run 4 ways)
-constexpr int kDenseThreads = kDenseBlk * kDenseLanes;   // 512 threads: 16 warps, one block per SM (128 registers, ~195 KB)
+constexpr int kDenseThreads = 512;          // 16 warps, one block per SM (128 registers, ~215 KB): a GROUP of L = 4..32
+                                           // lanes serves one query, L = 512 / queries of the work item (power of two)
 constexpr int kFine = 4;                   // fine cells per cell edge
 constexpr int kBox = 3 * kFine;            // fine cells per axis of the staged box
 constexpr int kBoxCells = kBox * kBox * kBox;
@@ -161,6 +161,7 @@ struct TopKP {
 struct DenseSmem {
   float4 pts[kDenseCap];
   unsigned short order[kDenseCap];
+  unsigned short fid[kDenseCap];          // fine cell of each staged point (computed once, used by count and scatter)
   unsigned start[kBoxCells + 1];
   unsigned cursor[kBoxCells];
   unsigned run_beg[27], run_cnt[27];
@@ -249,8 +250,11 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
     }
     // ---- my query: a QUAD of lanes serves one query (the quad splits every candidate run four ways; more warps per
     //      SM for the same shared-memory footprint -- the search is a latency-bound dependent chain per lane) ----
-    const int qid = tid >> 2, sub = tid & 3;
-    const unsigned quadmask = 0xFu << (lane & ~3);
+    int lsh = 2;                                       // log2(L): as many lanes per query as 512 threads allow
+    while (lsh < 5 && ((int)wk.qcnt << (lsh + 1)) <= kDenseThreads) ++lsh;
+    const int L = 1 << lsh;
+    const int qid = tid >> lsh, sub = tid & (L - 1);
+    const unsigned quadmask = (L == 32) ? 0xffffffffu : (((1u << L) - 1u) << (lane & ~(L - 1)));
     const bool hasq = qid < (int)wk.qcnt;
     int il = 0, gi = 0;
     double rx = 0.0, ry = 0.0, rz = 0.0;
@@ -268,6 +272,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
     const int qi = fclamp((rx - bx) * inv_e), qj = fclamp((ry - by) * inv_e), qk = fclamp((rz - bz) * inv_e);
     const float bxf = (float)bx, byf = (float)by, bzf = (float)bz;                    // exact (multiples of the cell edge)
     const float qlx = (float)(rx - bx), qly = (float)(ry - by), qlz = (float)(rz - bz);
+    const float inv_ef = (float)inv_e;
     TopKP<5> t;
     t.init();
     __syncthreads();
@@ -298,12 +303,17 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       parity ^= 1u;
       __syncthreads();
       if (a.dbg && tid == 0) { const long long t = clock64(); tk_wait += t - tk1; tk1 = t; }
-      // counting sort of the staged points into the fine grid (indices only: the points stay where TMA put them)
-      auto fine_id = [&](const float4& p) {
-        const int fi = fclamp(((double)p.x - bx) * inv_e), fj = fclamp(((double)p.y - by) * inv_e), fk = fclamp(((double)p.z - bz) * inv_e);
-        return (fk * kBox + fj) * kBox + fi;
-      };
-      for (int i = tid; i < fill; i += kDenseThreads) atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u);
+      // counting sort of the staged points into the fine grid (indices only: the points stay where TMA put them).
+      // Fine cell from coordinates LOCAL to the box in FP32 (p - box0 is exact); a point within ~1e-7 m of a fine-cell
+      // face may land on either side, which the 1e-6 m slack of the lower bounds covers.
+      for (int i = tid; i < fill; i += kDenseThreads) {
+        const float4 p = sm.pts[i];
+        int fi = (int)floorf((p.x - bxf) * inv_ef), fj = (int)floorf((p.y - byf) * inv_ef), fk = (int)floorf((p.z - bzf) * inv_ef);
+        fi = fi < 0 ? 0 : (fi > kBox - 1 ? kBox - 1 : fi); fj = fj < 0 ? 0 : (fj > kBox - 1 ? kBox - 1 : fj); fk = fk < 0 ? 0 : (fk > kBox - 1 ? kBox - 1 : fk);
+        const int id = (fk * kBox + fj) * kBox + fi;
+        sm.fid[i] = (unsigned short)id;
+        atomicAdd(&sm.cursor[id], 1u);
+      }
       __syncthreads();
       {
         constexpr int kPer = (kBoxCells + kDenseThreads - 1) / kDenseThreads;      // consecutive entries per thread
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         if (tid == kDenseThreads - 1) sm.start[kBoxCells] = (unsigned)fill;
       }
       __syncthreads();
-      for (int i = tid; i < fill; i += kDenseThreads) sm.order[atomicAdd(&sm.cursor[fine_id(sm.pts[i])], 1u)] = (unsigned short)i;
+      for (int i = tid; i < fill; i += kDenseThreads) sm.order[atomicAdd(&sm.cursor[sm.fid[i]], 1u)] = (unsigned short)i;
       __syncthreads();
       if (a.dbg && tid == 0) { const long long t = clock64(); tk_sort += t - tk1; tk1 = t; }
       if (hasq) {
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         float boundf = (float)bound * 1.00001f + 2e-6f;
         auto scan = [&](unsigned b, unsigned en) {
 #pragma unroll 4
-          for (unsigned u = b + (unsigned)sub; u < en; u += (unsigned)kDenseLanes) {
+          for (unsigned u = b; u < en; ++u) {
             const float4 p = sm.pts[sm.order[u]];
             const float fx = (p.x - bxf) - qlx, fy = (p.y - byf) - qly, fz = (p.z - bzf) - qlz;
             const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
               const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
               if (d < r2) {
                 t.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
-                bound = t.d2[4] < r2 ? t.d2[4] : r2;
+                bound = t.d2[4] < bound ? t.d2[4] : bound;
                 boundf = (float)bound * 1.00001f + 2e-6f;
               }
             }
@@ -348,47 +358,44 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         };
         auto gap = [&](double q, double b0, int i, int qc) {      // lower bound of |q - p| along one axis for fine slab i
           double gp = i > qc ? (b0 + (double)i * e) - q : (i < qc ? q - (b0 + (double)(i + 1) * e) : 0.0);
-          gp -= 1e-9;
+          gp -= 1e-6;
           return gp > 0.0 ? gp : 0.0;
         };
         // nearest-first over Chebyshev shells of fine cells around the query: every cell of shell rho is at least
         // (rho - 1) e away, so the walk stops as soon as that exceeds the K-th best distance (or the radius: shells
-        // 0..kFine cover it, and they lie inside the staged box because the query sits in its middle third)
+        // 0..kFine cover it, and they lie inside the staged box because the query sits in its middle third).  The ROWS
+        // of a shell are dealt round-robin to the L lanes of the group (an outlier far from the surface walks 155
+        // rows: with one lane that is the latency of the whole block).
         for (int rho = 0; rho <= kFine; ++rho) {
-          // control flow is QUAD-uniform: the bound that prunes shells / rows / cells is the quad minimum of the
-          // lane-local bounds (any lane's full list proves K points within its bound), refreshed once per shell
-          {
-            double ob = __shfl_xor_sync(quadmask, bound, 1);
+          // shell-level control flow is GROUP-uniform: the pruning bound is the group minimum of the lane-local bounds
+          // (any lane's full list proves K points within its bound), refreshed once per shell
+          for (int o = 1; o < L; o <<= 1) {
+            const double ob = __shfl_xor_sync(quadmask, bound, o);
             bound = ob < bound ? ob : bound;
-            ob = __shfl_xor_sync(quadmask, bound, 2);
-            bound = ob < bound ? ob : bound;
-            boundf = (float)bound * 1.00001f + 2e-6f;
           }
-          const double qb = bound;
+          boundf = (float)bound * 1.00001f + 2e-6f;
           if (rho >= 2) {
-            const double lb = (double)(rho - 1) * e - 1e-9;
-            if (lb * lb > qb) break;
+            const double lb = (double)(rho - 1) * e - 1e-6;
+            if (lb * lb > bound) break;
           }
-          for (int dk = -rho; dk <= rho; ++dk) {
-            const int k = qk + dk;
-            if (k < 0 || k >= kBox) continue;
-            const double gz = gap(rz, bz, k, qk);
-            for (int dj = -rho; dj <= rho; ++dj) {
-              const int j = qj + dj;
-              if (j < 0 || j >= kBox) continue;
-              const double gy = gap(ry, by, j, qj);
-              const double g2 = gz * gz + gy * gy;
-              if (g2 > qb) continue;
-              const int row = (k * kBox + j) * kBox;
-              const bool face = (dk == -rho || dk == rho || dj == -rho || dj == rho);
-              if (face) {                                      // the whole x-extent of the shell
-                const int i0 = qi - rho > 0 ? qi - rho : 0, i1 = qi + rho < kBox - 1 ? qi + rho : kBox - 1;
-                scan(sm.start[row + i0], sm.start[row + i1 + 1]);
-              } else {                                         // only the two end cells
-                const int il0 = qi - rho, ih0 = qi + rho;
-                if (il0 >= 0) { const double gx = gap(rx, bx, il0, qi); if (g2 + gx * gx <= qb) scan(sm.start[row + il0], sm.start[row + il0 + 1]); }
-                if (ih0 < kBox) { const double gx = gap(rx, bx, ih0, qi); if (g2 + gx * gx <= qb) scan(sm.start[row + ih0], sm.start[row + ih0 + 1]); }
-              }
+          const int side = 2 * rho + 1;
+          for (int ri = sub; ri < side * side; ri += L) {
+            const int dk = ri / side - rho, dj = ri % side - rho;
+            const int k = qk + dk, j = qj + dj;
+            if (k < 0 || k >= kBox || j < 0 || j >= kBox) continue;
+            const int row = (k * kBox + j) * kBox;
+            const bool face = (dk == -rho || dk == rho || dj == -rho || dj == rho);
+            const int i0 = qi - rho > 0 ? qi - rho : 0, i1 = qi + rho < kBox - 1 ? qi + rho : kBox - 1;
+            if (sm.start[row + i1 + 1] == sm.start[row + i0]) continue;      // nothing staged in this row of the shell
+            const double gz = gap(rz, bz, k, qk), gy = gap(ry, by, j, qj);
+            const double g2 = gz * gz + gy * gy;
+            if (g2 > bound) continue;
+            if (face) {                                      // the whole x-extent of the shell
+              scan(sm.start[row + i0], sm.start[row + i1 + 1]);
+            } else {                                         // only the two end cells
+              const int il0 = qi - rho, ih0 = qi + rho;
+              if (il0 >= 0) { const double gx = gap(rx, bx, il0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + il0], sm.start[row + il0 + 1]); }
+              if (ih0 < kBox) { const double gx = gap(rx, bx, ih0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + ih0], sm.start[row + ih0 + 1]); }
             }
           }
         }
@@ -396,9 +403,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       __syncthreads();                         // everybody is done with the staged points before the next pass
       if (a.dbg && tid == 0) { const long long t = clock64(); tk_search += t - tk1; tk1 = t; }
     }
-    // ---- merge the quad's four sorted lists into lane 0 of the quad (two rounds of pull + insert) ----
-#pragma unroll
-    for (int step = 1; step <= 2; step <<= 1) {
+    // ---- merge the group's L sorted lists into its lane 0 (log2 L rounds of pull + insert) ----
+    for (int step = 1; step < L; step <<= 1) {
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         const double od = __shfl_xor_sync(0xffffffffu, t.d2[j], step);

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "registration.cuh"
@@ -64,6 +65,8 @@ struct tloam_b200_handle {
   double* d_stage_tgt = nullptr; size_t cap_stage_tgt = 0;
   unsigned* d_scratch = nullptr; size_t cap_scratch = 0;        // slot_of + rank_of
   unsigned char* d_blob = nullptr; size_t cap_blob = 0, blob_bytes = 0;
+  // second blob: a map being RECEIVED (shared-map broadcast) while frames still register against the active one
+  unsigned char* d_blob_in = nullptr; size_t cap_blob_in = 0, blob_in_bytes = 0; MapHeader hdr_in; bool blob_in_ready = false;
   MapHeader hdr;                                                // host copy of the layout (origin filled lazily)
   bool origin_known = false;
   // pinned host staging for results
@@ -267,7 +270,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_stage_src); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
   cudaFree(h->d_partial); cudaFree(h->d_counter); if (h->own_state) cudaFree(h->d_state); cudaFree(h->d_stats);
-  cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_dbg);
+  cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_blob_in); cudaFree(h->d_dbg);
   cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
   cudaFree(h->d_cnt); cudaFree(h->d_fit); cudaFree(h->d_ge);
   for (auto& pr : h->probes) { if (pr.ev) cudaEventDestroy(pr.ev); if (pr.h_vals) cudaFreeHost(pr.h_vals); }
@@ -393,19 +396,25 @@ int tloam_b200_set_source_device(tloam_b200_handle* h, const double* const xyz[4
 
 static unsigned next_pow2(size_t v) { unsigned p = 256; while ((size_t)p < v) p <<= 1; return p; }
 
-static int layout_map(tloam_b200_handle* h, const size_t n[4]) {
-  MapHeader& hd = h->hdr;
+// the blob layout is a pure function of the configuration and the four point counts (so every rank of a shared-map
+// broadcast can lay the incoming blob out without reading its header back)
+static size_t layout_header(const tloam_tls_config& cfg, const size_t n[4], MapHeader& hd) {
   memset(&hd, 0, sizeof(hd));
   hd.magic = kMapMagic;
   size_t off = sizeof(MapHeader);
   for (int c = 0; c < 4; ++c) {
     hd.n[c] = (unsigned)n[c];
     hd.tsize[c] = next_pow2(n[c] + 1);      // >= bricks + 1 even if every point sits in its own brick
-    hd.cell[c] = radius_of(h->cfg, c);
+    hd.cell[c] = radius_of(cfg, c);
     hd.pts_off[c] = off; off += round_up(n[c] * sizeof(float4), 256);
   }
   for (int c = 0; c < 4; ++c) { hd.table_off[c] = off; off += (size_t)hd.tsize[c] * kBrickBytes; }
   for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
+  return off;
+}
+
+static int layout_map(tloam_b200_handle* h, const size_t n[4]) {
+  const size_t off = layout_header(h->cfg, n, h->hdr);
   h->blob_bytes = off;
   if (off > h->cap_blob) {
     cudaFree(h->d_blob); h->d_blob = nullptr; h->cap_blob = 0;
@@ -612,6 +621,76 @@ int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes)
   for (int c = 0; c < 4; ++c) h->nbricks[c] = hd.nbricks[c];
   h->stats_known = true; h->stats_pending = false;
   CU_TRY(cudaStreamSynchronize(h->stream));
+  return TLOAM_B200_OK;
+}
+
+
+// ---- zero-copy shared-map transport (config 4): ONE collective, no size handshake, no host synchronisation ----
+// sender: the built blob itself (no export copy).  The consumer stream must be ordered behind the build:
+// tloam_b200_signal_stream(h, consumer_stream).
+int tloam_b200_map_send_buffer(tloam_b200_handle* h, void** d_ptr, size_t* bytes) {
+  if (!h || !d_ptr || !bytes) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->have_tgt) return TLOAM_B200_ERR_NOT_READY;
+  *d_ptr = h->d_blob; *bytes = h->blob_bytes;
+  return TLOAM_B200_OK;
+}
+
+int tloam_b200_map_layout_bytes(tloam_b200_handle* h, const size_t n[4], size_t* bytes) {
+  if (!h || !n || !bytes) return TLOAM_B200_ERR_INVALID_ARG;
+  MapHeader hd;
+  *bytes = layout_header(h->cfg, n, hd);
+  return TLOAM_B200_OK;
+}
+
+// receiver: where the broadcast of a map with these point counts must land -- a SECOND blob of the handle, so frames
+// keep registering against the active map while the next one is in flight.
+int tloam_b200_map_recv_buffer(tloam_b200_handle* h, const size_t n[4], void** d_ptr, size_t* bytes) {
+  if (!h || !n || !d_ptr || !bytes) return TLOAM_B200_ERR_INVALID_ARG;
+  for (int c = 0; c < 4; ++c) if (n[c] > (size_t)1 << 30) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  const size_t need = layout_header(h->cfg, n, h->hdr_in);
+  if (need > h->cap_blob_in) {
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_blob_in); h->d_blob_in = nullptr; h->cap_blob_in = 0;
+    CU_TRY(cudaMalloc(&h->d_blob_in, need + need / 4));
+    h->cap_blob_in = need + need / 4;
+  }
+  h->blob_in_bytes = need; h->blob_in_ready = true;
+  *d_ptr = h->d_blob_in; *bytes = need;
+  return TLOAM_B200_OK;
+}
+
+// receiver: the collective that fills the receive buffer has been ENQUEUED on producer_stream.  Orders the handle's
+// stream behind it (device-side wait) and makes the received blob the active map: no copy, no host synchronisation.
+int tloam_b200_map_adopt(tloam_b200_handle* h, void* producer_stream) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  if (!h->blob_in_ready) return TLOAM_B200_ERR_NOT_READY;
+  CU_TRY(cudaSetDevice(h->device));
+  if ((cudaStream_t)producer_stream != h->stream) {
+    CU_TRY(cudaEventRecord(h->ev_copy[0], (cudaStream_t)producer_stream));
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_copy[0], 0));
+  }
+  std::swap(h->d_blob, h->d_blob_in);
+  std::swap(h->cap_blob, h->cap_blob_in);
+  h->blob_bytes = h->blob_in_bytes;
+  h->hdr = h->hdr_in;
+  h->blob_in_ready = false;
+  for (int c = 0; c < 4; ++c) { h->n_tgt[c] = h->hdr.n[c]; h->ctx.tgt_cnt[c] = nullptr; }
+  fill_ctx_config(h);
+  bind_map(h);
+  h->origin_known = false;                 // lives in the received header on the device; fetched lazily if ever asked for
+  h->stats_pending = false;                // occupied-brick statistics stay those of the previous map
+  h->have_tgt = true;
+  return TLOAM_B200_OK;
+}
+
+// orders `consumer_stream` behind everything enqueued so far on the handle's stream (device-side wait)
+int tloam_b200_signal_stream(tloam_b200_handle* h, void* consumer_stream) {
+  if (!h) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  if ((cudaStream_t)consumer_stream == h->stream) return TLOAM_B200_OK;
+  CU_TRY(cudaEventRecord(h->ev_copy[1], h->stream));
+  CU_TRY(cudaStreamWaitEvent((cudaStream_t)consumer_stream, h->ev_copy[1], 0));
   return TLOAM_B200_OK;
 }
 

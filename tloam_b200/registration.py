@@ -343,6 +343,23 @@ class LocalRegistration:
     def map_import(self, dev_ptr, nbytes):
         self._check(self._L.tloam_b200_map_import(self._h, C.c_void_p(dev_ptr), nbytes), "map_import")
 
+    def map_send_buffer(self):
+        p, n = C.c_void_p(), C.c_size_t(0)
+        self._check(self._L.tloam_b200_map_send_buffer(self._h, C.byref(p), C.byref(n)), "map_send_buffer")
+        return p.value, n.value
+
+    def map_recv_buffer(self, n_map):
+        ns = (C.c_size_t * 4)(*[int(v) for v in n_map])
+        p, n = C.c_void_p(), C.c_size_t(0)
+        self._check(self._L.tloam_b200_map_recv_buffer(self._h, ns, C.byref(p), C.byref(n)), "map_recv_buffer")
+        return p.value, n.value
+
+    def map_adopt(self, producer_stream):
+        self._check(self._L.tloam_b200_map_adopt(self._h, C.c_void_p(int(producer_stream))), "map_adopt")
+
+    def signal_stream(self, consumer_stream):
+        self._check(self._L.tloam_b200_signal_stream(self._h, C.c_void_p(int(consumer_stream))), "signal_stream")
+
     def map_origin(self):
         o = np.zeros(3)
         self._check(self._L.tloam_b200_get_map_origin(self._h, _dp(o)), "map_origin")
