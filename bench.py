@@ -297,6 +297,107 @@ def run_stream_device_submap(reg, frames, prev_gt, torch, warmup, steps):
     return e0.elapsed_time(e1), h2d, err, poses, fit
 
 
+def run_shared_map(tloam_b200, torch, dist, multi, rank, world, local_rank, args, barrier):
+    """BASELINE config 4: every rank registers ITS OWN sequence (same route as sequence 00, its own lateral offset, scan
+    noise and outliers) against a local map that is SHARED: rank 0 builds it once per map epoch (E frames) on a side
+    stream and ONE ncclBroadcast moves the built blob into a second blob of every rank's handle while the frames of the
+    current epoch are still being registered; the switch is a device-side wait + pointer swap.  Then every rank repeats
+    its sequence alone (each epoch's map built locally): the poses must be bit-identical."""
+    from tloam_b200 import synth
+    dev = torch.device("cuda", local_rank)
+    E = 4
+    nfr = args.warmup + args.steps
+    nep = (nfr + E - 1) // E
+    cfg = synth.SceneConfig(seed=20260924 + 1000 * 4)
+    route = synth.Stream(cfg=cfg, seq="00", start=100)
+    poses_route = []
+    for _ in range(nfr):
+        poses_route.append(route.T.copy())
+        route.T = route.T @ synth.se3_exp(route.motion[route.k % len(route.motion)])
+        route.k += 1
+    off = synth.se3_exp([0.0, 0.3 * rank, 0.0, 0.0, 0.0, 0.002 * rank])
+    gt = [T @ off for T in poses_route]
+    scans = [[torch.from_numpy(c).cuda() for c in synth.make_scan(cfg, gt[k], k + 100000 * (rank + 1))] for k in range(nfr)]
+    maps_host = [synth.make_map(cfg, poses_route[e * E]) for e in range(nep)]        # every rank: needed for the 1-GPU re-run
+    n_map = [int(c.shape[0]) for c in maps_host[0]]
+    maps = [[torch.from_numpy(c).cuda() for c in m] for m in maps_host]
+    torch.cuda.synchronize()
+    reg = tloam_b200.LocalRegistration(device=local_rank, stream=torch.cuda.current_stream().cuda_stream, **CAPS)
+    chan = multi.SharedMapChannel(reg, src=0, device=dev)
+    builder = None
+    if rank == 0:
+        builder = tloam_b200.LocalRegistration(device=local_rank, stream=chan.side.cuda_stream, **CAPS)
+        chan.builder = builder
+
+    def kick(e):                       # next epoch's map: build (rank 0) + ONE collective, all on the side stream
+        if rank == 0:
+            builder.set_input_target_device(maps[e], producer_stream=torch.cuda.current_stream().cuda_stream)
+        return chan.broadcast(n_map)
+
+    def drive(shared):
+        last, cur, out = gt[0] @ np.linalg.inv(np.linalg.inv(gt[0]) @ gt[1]), None, []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if shared:
+            kick(0)
+            chan.adopt()
+        for k in range(nfr):
+            e = k // E
+            if k == args.warmup:
+                torch.cuda.synchronize()
+                if shared:
+                    barrier()
+                e0.record()
+            if k % E == 0:
+                if shared and e + 1 < nep:
+                    kick(e + 1)                                 # in flight under the frames of epoch e
+                if not shared:
+                    reg.set_input_target_device(maps[e])
+            predict = gt[0] @ synth.se3_exp(synth.CONFIG1_PERTURB) if cur is None else predict_next(last, cur)
+            reg.set_input_source_device(scans[k])
+            T = reg.scan_matching(predict)
+            out.append(T)
+            last, cur = (cur if cur is not None else last), T
+            if shared and (k + 1) % E == 0 and e + 1 < nep:
+                chan.adopt()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    barrier()
+    ms_sh, poses_sh = drive(True)
+    barrier()
+    ms_1, poses_1 = drive(False)
+    same = all(np.array_equal(a, b) for a, b in zip(poses_sh, poses_1))
+    err = max(pose_err(T, g)[0] for T, g in zip(poses_sh, gt))
+    # the collective alone (nothing else on the GPU), back to back on the side stream
+    barrier()
+    nb = 0
+    for _ in range(3):
+        nb = kick(0)
+    torch.cuda.synchronize()
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(chan.side):
+        b0.record()
+        for _ in range(10):
+            chan.broadcast(n_map)
+        b1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ms_sh, b0.elapsed_time(b1) / 10, 0.0 if same else 1.0, err], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"bytes": int(nb), "ms": float(t[1]), "GBps": nb / (float(t[1]) * 1e-3) / 1e9,
+           "what": "ONE ncclBroadcast of the built map blob per map epoch (no size handshake, no export / import copies, no host "
+                   "synchronisation), timed alone on the side stream, max over ranks",
+           "config4": {"value": world * args.steps / (float(t[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(t[0]) / args.steps,
+                       "frames_per_epoch": E, "bit_identical_to_1gpu": bool(float(t[2]) == 0.0), "max_err_vs_ground_truth_m": float(t[3]),
+                       "what": f"{world} sequences (one per GPU) registering against the SHARED map; rank 0 builds the next epoch's map on a "
+                               "side stream and the broadcast overlaps the current epoch's frames; inputs resident in HBM"}}
+    reg.close()
+    if builder is not None:
+        builder.close()
+    return out
+
+
 def reference_arm(args, rank, world):
     """CPU restatement of the reference path on the host cores (kind 'port')."""
     if rank != 0:
@@ -341,6 +442,103 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def bench_config3(args, rank, world, local_rank):
+    """BASELINE config 3 as a contract line: dense indoor scan, F = 500 032 features (planar + ground builders only,
+    factor_num = 2) against M = 2 000 032 map points, room 20 x 30 x 4 m at ~0.03 m spacing, 1 x B200.  One step = one frame
+    = set_target (2M-point voxel-hash build) + set_source + scan_match.  The correspondence search takes the dense-map
+    path (queries binned by map cell, TMA-staged tiles, dense_search.cuh)."""
+    import torch
+    import tloam_b200
+    from tloam_b200 import synth
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    f = synth.config3()
+    cfg = dict(factor_num=2, **CAPS)
+    reg = tloam_b200.LocalRegistration(device=local_rank, stream=torch.cuda.current_stream().cuda_stream, **cfg)
+    ncopy = 4                                       # 4 x 44 MB of inputs cycle through: larger than L2 (126 MB)
+    dev = [([torch.from_numpy(c).cuda() for c in f["map"]], [torch.from_numpy(c).cuda() for c in f["scan"]]) for _ in range(ncopy)]
+    pin = [([torch.from_numpy(c).pin_memory().numpy() for c in f["map"]], [torch.from_numpy(c).pin_memory().numpy() for c in f["scan"]]) for _ in range(2)]
+    for mp, sc in pin:
+        for a in mp + sc:
+            torch.from_numpy(a).cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def run(mode, warm, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        T, l0 = None, 0
+        for k in range(warm + steps):
+            if k == warm:
+                torch.cuda.synchronize()
+                l0 = reg.launch_count()
+                e0.record()
+            if mode == "device":
+                mp, sc = dev[k % ncopy]
+                reg.set_input_target_device(mp)
+                reg.set_input_source_device(sc)
+            else:
+                mp, sc = pin[k % 2]
+                reg.set_input_target(mp)
+                reg.set_input_source(sc)
+            T = reg.scan_matching(f["predict"])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), T, reg.launch_count() - l0
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    passes = []
+    for _ in range(max(1, args.repeats)):
+        ms, T, launches = run("device", args.warmup, args.steps)
+        passes.append(ms)
+    ms_e2e, T2, _ = run("host", args.warmup, args.steps)
+    clocks = sampler.stop()
+    assert np.array_equal(T, T2)
+    ms_dev = float(np.median(passes))
+    reg.set_profiling(True)
+    run("device", 0, 3)
+    prof = reg.get_profile()
+    reg.set_profiling(False)
+    n_feat = [int(c.shape[0]) for c in f["scan"]]
+    n_map = [int(c.shape[0]) for c in f["map"]]
+    alg = algorithmic_bytes(n_feat, n_map)
+    alg["dense"] = alg["correspond"]
+    kern = {k: {"launches_per_frame": n / 3, "avg_us": 1e3 * ms / n, "ms_per_frame": ms / 3} for k, (n, ms) in prof.items() if n > 0}
+    dominant = max(("dense", "correspond", "eval", "eval_first"), key=lambda k: kern.get(k, {}).get("ms_per_frame", 0.0))
+    peak, peak_src = measured_peak_hbm()
+    ach = alg[dominant] / (kern[dominant]["avg_us"] * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": {"dense": "k_correspond_dense", "correspond": "k_correspond", "eval": "k_eval<false>",
+                                           "eval_first": "k_eval<true>"}[dominant],
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dominant], "avg_launch_us": kern[dominant]["avg_us"], "kernels": kern,
+                "per_kernel_frac": {k: alg[k] / (kern[k]["avg_us"] * 1e-6) / 1e9 / peak for k in ("dense", "eval", "eval_first") if k in kern}}
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle
+        o = pyoracle.Oracle(threads_mode=1, **cfg)
+        t0 = time.perf_counter()
+        o.set_input_target(f["map"])
+        o.set_input_source(f["scan"])
+        rc, To, _ = o.scan_matching(f["predict"])
+        dt = time.perf_counter() - t0
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "1 frame (kNN / fits over all cores)",
+               "pose_diff_vs_gpu_m": pose_err(To, T)[0]}
+    h2d = (sum(n_map) + sum(n_feat)) * 24
+    line = {"metric": METRIC, "value": args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "repeats": len(passes), "passes_ms_per_step": [m / args.steps for m in passes],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config3: dense indoor scan, F=500032 features (planar 250000 + ground 250000, factor_num=2) vs "
+                                   "M=2000032-pt map (room 20x30x4 m, ~0.03 m spacing) rebuilt every frame, 4 outer x <=4 inner, caps=F",
+                       "features_per_frame": sum(n_feat), "map_points": sum(n_map),
+                       "l2_policy": "inputs larger than L2: 4 copies of the 44 MB inputs cycle through", "parallelism": "1 stream, 1 GPU"},
+            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 152,
+                    "ms_per_step": ms_e2e / args.steps, "host_memory": "pinned"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "err_vs_ground_truth_m": pose_err(T, f["T_gt"])[0]}
+    print(json.dumps(line), flush=True)
+    reg.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,6 +547,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=5, help="timed passes of K steps each; value = median pass")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE config: 2 = the headline stream (default); 3 = dense indoor scan, F=500k planar-only vs M=2M (N=1)")
     ap.add_argument("--batch", type=int, default=8, help="sequences per batched launch in the `batched` leg (0 = skip; N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -359,6 +559,9 @@ def main():
 
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.config == 3:
+        bench_config3(args, rank, world, local_rank)
         return
 
     import torch
@@ -500,23 +703,10 @@ def main():
                            f"{S} x (set_target_device + set_source_device) + ONE launch sequence; inputs resident in HBM (value) / pinned host (e2e)"}
         breg.close()
 
-    # ---- shared-map broadcast of config 4 (NCCL), timed separately ----
+    # ---- config 4: N sequences, one per GPU, registering against ONE shared map broadcast per map epoch ----
     bcast = None
     if world > 1:
-        dev = torch.device("cuda", local_rank)
-        for _ in range(3):
-            multi.broadcast_shared_map(reg, src=0, device=dev)        # warm-up (rank 0's last map)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            n = multi.broadcast_shared_map(reg, src=0, device=dev)    # size handshake + export + ncclBroadcast + import
-        e1.record()
-        torch.cuda.synchronize()
-        tb = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        bcast = {"bytes": n, "ms": float(tb[0]), "GBps": n / (float(tb[0]) * 1e-3) / 1e9,
-                 "what": "export (D2D) + ncclBroadcast + import (D2D) of the built map blob, max over ranks"}
+        bcast = run_shared_map(tloam_b200, torch, dist, multi, rank, world, local_rank, args, barrier)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None

@@ -113,8 +113,9 @@ def test_dense_path_with_many_staging_passes():
 
 
 def test_dense_path_is_picked_automatically_for_a_dense_map():
-    """points per occupied brick >= 256 and >= 2048 queries: frame 2 of the handle (statistics of map 1 harvested at
-    get_result) takes the dense path; the pose does not change."""
+    """points per occupied brick >= 256 and >= 2048 queries per cloud: the handle waits ONCE for the statistics of its
+    first map (later maps are judged by their predecessor's, read back asynchronously) and takes the dense path without
+    any environment override; the pose equals the lane-pair search's."""
     import tloam_b200
     sc = very_dense_scene()
     cfg = dict(factor_num=2, **CAPS)
@@ -122,14 +123,13 @@ def test_dense_path_is_picked_automatically_for_a_dense_map():
     r.set_input_target(sc["map"])
     r.set_input_source(sc["scan"])
     T1, s1 = r.scan_matching(sc["predict"], want_stats=True)
+    r.set_input_target(sc["map"])
     T2, s2 = r.scan_matching(sc["predict"], want_stats=True)
     r.close()
-    assert s2.gpu_launches == 1 + 4 * (2 + 4 + 4)      # un-fused + 3 binning kernels + the dense search per outer
-    assert s1.gpu_launches == 1 + 4 * (1 + 4)          # frame 1: no statistics yet -> lane-pair search, fused
-    Ts, _ = run(sc, False, **cfg)                      # un-fused lane-pair search: same reduction tree as the dense frame
-    assert np.array_equal(T2, Ts)
-    d = np.linalg.inv(T1) @ T2                         # fused frame 1: other summation tree, same factors
-    assert np.linalg.norm(d[:3, 3]) < 1e-7
+    for st in (s1, s2):
+        assert st.gpu_launches == 1 + 4 * (2 + 4 + 4)      # un-fused + 3 binning kernels + the dense search per outer
+    Ts, _ = run(sc, False, **cfg)                          # un-fused lane-pair search: same reduction tree
+    assert np.array_equal(T1, Ts) and np.array_equal(T2, Ts)
 
 
 def test_dense_path_on_a_sparse_outdoor_scene_and_with_binding_caps(oracle):

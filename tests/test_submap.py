@@ -210,7 +210,8 @@ def test_chained_device_flow_matches_the_oracle_over_12_frames(oracle):
         assert rc == 0 and dt < 1e-4 and dr < 1e-5, (k, dt, dr)
         fg = reg.get_frame_fitness()
         assert fg == fits[k]
-        assert np.isclose(fg[0], fo[0], rtol=1e-12) and np.isclose(fg[1], fo[1], rtol=1e-9), (k, fg, fo)
+        # the device stores map coordinates in FP32 relative to the map origin (<= 4e-6 m): same matches, d2 to ~1e-6
+        assert np.isclose(fg[0], fo[0], rtol=1e-12) and np.isclose(fg[1], fo[1], rtol=1e-5), (k, fg, fo)
         last, cur = cur, T
     for c in range(4):
         assert np.array_equal(sort_rows(reg.submap_cloud(c)), final_maps[c]), c

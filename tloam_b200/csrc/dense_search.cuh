@@ -28,7 +28,7 @@ constexpr int kDenseThreads = 512;          // 16 warps, one block per SM (128 r
 constexpr int kFine = 4;                   // fine cells per cell edge
 constexpr int kBox = 3 * kFine;            // fine cells per axis of the staged box
 constexpr int kBoxCells = kBox * kBox * kBox;
-constexpr int kDenseCap = 10240;           // staged points per pass (160 KB; one block per SM)
+constexpr int kDenseCap = 9216;            // staged points per pass (144 KB; one block per SM)
 
 struct DenseWork { int cx, cy, cz; unsigned qbeg; unsigned short qcnt; unsigned short cloud; };
 
@@ -158,6 +158,9 @@ struct TopKP {
   }
 };
 
+// a query that the 27 fine cells around it could not finish: position + its top-K so far
+struct HardRec { double q[3]; double d2[5]; int idx[5]; float x[5], y[5], z[5]; int pad; };
+
 struct DenseSmem {
   float4 pts[kDenseCap];
   unsigned short order[kDenseCap];
@@ -168,7 +171,8 @@ struct DenseSmem {
   unsigned cp_src[32], cp_dst[32], cp_n[32];
   unsigned scan_tmp[kDenseThreads / 32];
   int ncopy, fill, run_i;
-  unsigned run_o, work;
+  unsigned run_o, work, nhard;
+  HardRec hard[kDenseBlk];
   unsigned long long mbar;
 };
 constexpr size_t kDenseSmemBytes = sizeof(DenseSmem) + 128;
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
           ++n; fill += (int)take; ro += take;
           if (ro == sm.run_cnt[ri]) { ++ri; ro = 0u; }
         }
-        sm.run_i = ri; sm.run_o = ro; sm.ncopy = n; sm.fill = fill;
+        sm.run_i = ri; sm.run_o = ro; sm.ncopy = n; sm.fill = fill; sm.nhard = 0u;
         if (fill > 0) mbar_arrive_expect_tx(&sm.mbar, (unsigned)fill * 16u);
       }
       __syncthreads();
@@ -333,86 +337,129 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       for (int i = tid; i < fill; i += kDenseThreads) sm.order[atomicAdd(&sm.cursor[sm.fid[i]], 1u)] = (unsigned short)i;
       __syncthreads();
       if (a.dbg && tid == 0) { const long long t = clock64(); tk_sort += t - tk1; tk1 = t; }
+      // ---- phase 1: the 3 x 3 x 3 fine cells around the query, by the query's group of L lanes ----
+      // Lane 0 of the group carries the running top-K across passes; the other lanes start every pass empty.  Every row
+      // of the 27-cell neighbourhood is split L ways (lane `sub` takes candidates sub, sub + L, ...).  Candidates are
+      // pre-filtered in FP32 on coordinates LOCAL to the staged box (p - box0 is exact in FP32: both are multiples of the
+      // point's ulp and the difference is < 2 cells), with a margin that covers the FP32 rounding of the query and of the
+      // arithmetic (< 1e-6 m^2 at cell <= 1 m); survivors get the exact FP64 expression.
+      if (sub != 0) t.init();
+      double bound = t.d2[4] < r2 ? t.d2[4] : r2;                 // group-uniform after the broadcast below
+      bound = __shfl_sync(quadmask, bound, (lane & ~(L - 1)));
       if (hasq) {
-        // candidates are pre-filtered in FP32 on coordinates LOCAL to the staged box (p - box0 is exact in FP32: both are
-        // multiples of the point's ulp and the difference is < 2 cells), with a margin that covers the FP32 rounding of
-        // the query and of the arithmetic (< 1e-6 m^2 at cell <= 1 m); survivors get the exact FP64 expression
-        double bound = t.d2[4] < r2 ? t.d2[4] : r2;       // lane-local: 5 points within it exist in THIS lane's list
         float boundf = (float)bound * 1.00001f + 2e-6f;
-        auto scan = [&](unsigned b, unsigned en) {
-#pragma unroll 4
-          for (unsigned u = b; u < en; ++u) {
-            const float4 p = sm.pts[sm.order[u]];
-            const float fx = (p.x - bxf) - qlx, fy = (p.y - byf) - qly, fz = (p.z - bzf) - qlz;
-            const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
-            if (df <= boundf) {
-              const double ddx = (double)p.x - rx, ddy = (double)p.y - ry, ddz = (double)p.z - rz;
-              const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
-              if (d < r2) {
-                t.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
-                bound = t.d2[4] < bound ? t.d2[4] : bound;
-                boundf = (float)bound * 1.00001f + 2e-6f;
-              }
-            }
-          }
-        };
-        auto gap = [&](double q, double b0, int i, int qc) {      // lower bound of |q - p| along one axis for fine slab i
-          double gp = i > qc ? (b0 + (double)i * e) - q : (i < qc ? q - (b0 + (double)(i + 1) * e) : 0.0);
-          gp -= 1e-6;
-          return gp > 0.0 ? gp : 0.0;
-        };
-        // nearest-first over Chebyshev shells of fine cells around the query: every cell of shell rho is at least
-        // (rho - 1) e away, so the walk stops as soon as that exceeds the K-th best distance (or the radius: shells
-        // 0..kFine cover it, and they lie inside the staged box because the query sits in its middle third).  The ROWS
-        // of a shell are dealt round-robin to the L lanes of the group (an outlier far from the surface walks 155
-        // rows: with one lane that is the latency of the whole block).
-        for (int rho = 0; rho <= kFine; ++rho) {
-          // shell-level control flow is GROUP-uniform: the pruning bound is the group minimum of the lane-local bounds
-          // (any lane's full list proves K points within its bound), refreshed once per shell
-          for (int o = 1; o < L; o <<= 1) {
-            const double ob = __shfl_xor_sync(quadmask, bound, o);
-            bound = ob < bound ? ob : bound;
-          }
-          boundf = (float)bound * 1.00001f + 2e-6f;
-          if (rho >= 2) {
-            const double lb = (double)(rho - 1) * e - 1e-6;
-            if (lb * lb > bound) break;
-          }
-          const int side = 2 * rho + 1;
-          for (int ri = sub; ri < side * side; ri += L) {
-            const int dk = ri / side - rho, dj = ri % side - rho;
-            const int k = qk + dk, j = qj + dj;
-            if (k < 0 || k >= kBox || j < 0 || j >= kBox) continue;
+        for (int dk = -1; dk <= 1; ++dk) {
+          const int k = qk + dk;
+          if (k < 0 || k >= kBox) continue;
+          for (int dj = -1; dj <= 1; ++dj) {
+            const int j = qj + dj;
+            if (j < 0 || j >= kBox) continue;
             const int row = (k * kBox + j) * kBox;
-            const bool face = (dk == -rho || dk == rho || dj == -rho || dj == rho);
-            const int i0 = qi - rho > 0 ? qi - rho : 0, i1 = qi + rho < kBox - 1 ? qi + rho : kBox - 1;
-            if (sm.start[row + i1 + 1] == sm.start[row + i0]) continue;      // nothing staged in this row of the shell
-            const double gz = gap(rz, bz, k, qk), gy = gap(ry, by, j, qj);
-            const double g2 = gz * gz + gy * gy;
-            if (g2 > bound) continue;
-            if (face) {                                      // the whole x-extent of the shell
-              scan(sm.start[row + i0], sm.start[row + i1 + 1]);
-            } else {                                         // only the two end cells
-              const int il0 = qi - rho, ih0 = qi + rho;
-              if (il0 >= 0) { const double gx = gap(rx, bx, il0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + il0], sm.start[row + il0 + 1]); }
-              if (ih0 < kBox) { const double gx = gap(rx, bx, ih0, qi); if (g2 + gx * gx <= bound) scan(sm.start[row + ih0], sm.start[row + ih0 + 1]); }
+            const int i0 = qi - 1 > 0 ? qi - 1 : 0, i1 = qi + 1 < kBox - 1 ? qi + 1 : kBox - 1;
+            const unsigned en = sm.start[row + i1 + 1];
+#pragma unroll 2
+            for (unsigned u = sm.start[row + i0] + (unsigned)sub; u < en; u += (unsigned)L) {
+              const float4 p = sm.pts[sm.order[u]];
+              const float fx = (p.x - bxf) - qlx, fy = (p.y - byf) - qly, fz = (p.z - bzf) - qlz;
+              const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+              if (df <= boundf) {
+                const double ddx = (double)p.x - rx, ddy = (double)p.y - ry, ddz = (double)p.z - rz;
+                const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
+                if (d < r2) {
+                  t.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
+                  bound = t.d2[4] < bound ? t.d2[4] : bound;
+                  boundf = (float)bound * 1.00001f + 2e-6f;
+                }
+              }
             }
           }
         }
       }
-      __syncthreads();                         // everybody is done with the staged points before the next pass
-      if (a.dbg && tid == 0) { const long long t = clock64(); tk_search += t - tk1; tk1 = t; }
-    }
-    // ---- merge the group's L sorted lists into its lane 0 (log2 L rounds of pull + insert) ----
-    for (int step = 1; step < L; step <<= 1) {
+      // merge the group's L sorted lists into its lane 0 (log2 L rounds of pull + insert)
+      for (int step = 1; step < L; step <<= 1) {
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const double od = __shfl_xor_sync(0xffffffffu, t.d2[j], step);
-        const int oi = __shfl_xor_sync(0xffffffffu, t.idx[j], step);
-        const float ox = __shfl_xor_sync(0xffffffffu, t.x[j], step), oy = __shfl_xor_sync(0xffffffffu, t.y[j], step);
-        const float oz = __shfl_xor_sync(0xffffffffu, t.z[j], step);
-        if ((sub & (2 * step - 1)) == 0 && oi != 0x7FFFFFFF) t.insert(od, oi, ox, oy, oz);
+        for (int j = 0; j < 5; ++j) {
+          const double od = __shfl_xor_sync(0xffffffffu, t.d2[j], step);
+          const int oi = __shfl_xor_sync(0xffffffffu, t.idx[j], step);
+          const float ox = __shfl_xor_sync(0xffffffffu, t.x[j], step), oy = __shfl_xor_sync(0xffffffffu, t.y[j], step);
+          const float oz = __shfl_xor_sync(0xffffffffu, t.z[j], step);
+          if ((sub & (2 * step - 1)) == 0 && oi != 0x7FFFFFFF) t.insert(od, oi, ox, oy, oz);
+        }
       }
+      // Everything OUTSIDE the 27 fine cells is at least one fine-cell edge away: the query is finished with this pass iff
+      // its list is full and the K-th best is closer than that.  The rest (outliers hanging in free space, sparse spots)
+      // go to the block's hard list and are finished by a whole warp each, brute force over the staged points.
+      int hslot = -1;
+      if (hasq && sub == 0) {
+        const double bq = t.d2[4] < r2 ? t.d2[4] : r2;
+        const double lb = e - 1e-6;
+        if (!(lb * lb > bq)) {
+          hslot = (int)atomicAdd(&sm.nhard, 1u);
+          HardRec& hr = sm.hard[hslot];
+          hr.q[0] = rx; hr.q[1] = ry; hr.q[2] = rz;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) { hr.d2[j] = t.d2[j]; hr.idx[j] = t.idx[j]; hr.x[j] = t.x[j]; hr.y[j] = t.y[j]; hr.z[j] = t.z[j]; }
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: one warp per hard query, all staged points of this pass, 32 ways ----
+      const unsigned nhard = sm.nhard;
+      for (unsigned hq = (unsigned)warp; hq < nhard; hq += kDenseThreads / 32) {
+        HardRec& hr = sm.hard[hq];
+        const double hx = hr.q[0], hy = hr.q[1], hz = hr.q[2];
+        const float hlx = (float)(hx - bx), hly = (float)(hy - by), hlz = (float)(hz - bz);
+        TopKP<5> tl;
+        tl.init();
+        double hb = hr.d2[4] < r2 ? hr.d2[4] : r2;
+        float hbf = (float)hb * 1.00001f + 2e-6f;
+#pragma unroll 4
+        for (int i = lane; i < fill; i += 32) {
+          const float4 p = sm.pts[i];
+          const float fx = (p.x - bxf) - hlx, fy = (p.y - byf) - hly, fz = (p.z - bzf) - hlz;
+          const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
+          if (df <= hbf) {
+            const double ddx = (double)p.x - hx, ddy = (double)p.y - hy, ddz = (double)p.z - hz;
+            const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
+            if (d < r2) {
+              tl.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
+              hb = tl.d2[4] < hb ? tl.d2[4] : hb;
+              hbf = (float)hb * 1.00001f + 2e-6f;
+            }
+          }
+        }
+        for (int step = 1; step < 32; step <<= 1) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const double od = __shfl_xor_sync(0xffffffffu, tl.d2[j], step);
+            const int oi = __shfl_xor_sync(0xffffffffu, tl.idx[j], step);
+            const float ox = __shfl_xor_sync(0xffffffffu, tl.x[j], step), oy = __shfl_xor_sync(0xffffffffu, tl.y[j], step);
+            const float oz = __shfl_xor_sync(0xffffffffu, tl.z[j], step);
+            if ((lane & (2 * step - 1)) == 0 && oi != 0x7FFFFFFF) tl.insert(od, oi, ox, oy, oz);
+          }
+        }
+        if (lane == 0) {
+          // fold the phase-1 list in; the 27 cells were scanned twice, so equal (d2, index) pairs are dropped
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int oi = hr.idx[j];
+            if (oi == 0x7FFFFFFF) continue;
+            bool dup = false;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) dup = dup || tl.idx[m] == oi;
+            if (!dup) tl.insert(hr.d2[j], oi, hr.x[j], hr.y[j], hr.z[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) { hr.d2[j] = tl.d2[j]; hr.idx[j] = tl.idx[j]; hr.x[j] = tl.x[j]; hr.y[j] = tl.y[j]; hr.z[j] = tl.z[j]; }
+        }
+      }
+      __syncthreads();
+      if (hslot >= 0) {
+        const HardRec& hr = sm.hard[hslot];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) { t.d2[j] = hr.d2[j]; t.idx[j] = hr.idx[j]; t.x[j] = hr.x[j]; t.y[j] = hr.y[j]; t.z[j] = hr.z[j]; }
+      }
+      __syncthreads();                         // everybody is done with the staged points before the next pass
+      if (a.dbg && tid == 0) { const long long tt = clock64(); tk_search += tt - tk1; tk1 = tt; }
     }
     const bool owner = hasq && sub == 0;
     if (a.dbg && owner) {                      // self-check against the thread-per-query search of map_grid.cuh
