@@ -265,9 +265,11 @@ def run_stream_device_submap(reg, frames, prev_gt, torch, warmup, steps):
             torch.from_numpy(a).cuda(non_blocking=True)
     f0 = frames[0]
     reg.submap_init(f0["map"][0], f0["map"][3], f0["map"][2], f0["map"][1])
-    # pose history so that frame 0's device-side prediction is ground truth perturbed like first_predict()
+    # pose history such that (i) frame 0's device-side prediction curr * (last^-1 * curr) is first_predict(frames[0]) and
+    # (ii) the velocity model of frame 1 starts from the true previous pose, as in run_stream: curr = prev_gt,
+    # last = prev_gt * p0^-1 * prev_gt
     p0 = first_predict(frames[0])
-    reg.set_pose_history(p0, p0)                     # last == curr: the first prediction is p0 itself
+    reg.set_pose_history(prev_gt @ np.linalg.inv(p0) @ prev_gt, prev_gt)
     reg.set_async_inputs(True)
     reg.set_frame_fitness(True)
     torch.cuda.synchronize()

@@ -126,3 +126,16 @@ def test_device_side_constant_velocity_prediction():
         last, cur = cur, Tb                    # the reference chains on its own results
         # handle `a` chains on the device: its state already holds (last, cur) = (previous result, this result)
     a.close(); b.close()
+
+
+def test_decision_flips_under_one_ulp_perturbations():
+    """Error bar of the parity claim: +-1 ulp on every input coordinate flips at most a handful of the
+    40k outer-0 validity decisions and moves the pose far less than the 1e-4 m / 1e-5 rad parity bound."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("decision_flips", os.path.join(os.path.dirname(__file__), "..", "tools", "decision_flips.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    out = m.run(R=3)
+    assert out["max_validity_flips_outer0"] <= 40          # <= 0.1 % of 40k features
+    assert out["max_dt_m"] < 1e-4 and out["max_dr_rad"] < 1e-5, out

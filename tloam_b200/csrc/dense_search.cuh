@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
     if (w >= nwork) break;
     const DenseWork wk = a.work[w];
     const int c = wk.cloud;
-    long long tk0 = 0, tk1 = 0, tk_wait = 0, tk_sort = 0, tk_search = 0;     // self-check mode: SM cycles per phase (thread 0)
+    long long tk0 = 0, tk1 = 0, tk_wait = 0, tk_sort = 0, tk_search = 0, tk_p1 = 0, tk_p2 = 0, tk2 = 0;     // self-check mode: SM cycles per phase (thread 0)
     if (a.dbg && tid == 0) tk0 = clock64();
     const GridDesc& g = ctx.grid[c];
     // ---- the <= 27 point runs of the neighbourhood (warp 0: 8 brick probes, then one cell per lane) ----
@@ -402,8 +402,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         }
       }
       __syncthreads();
+      if (a.dbg && tid == 0) { tk2 = clock64(); tk_p1 += tk2 - tk1; }
       // ---- phase 2: one warp per hard query, all staged points of this pass, 32 ways ----
       const unsigned nhard = sm.nhard;
+      if (a.dbg && tid == 0) atomicAdd(&a.dbg[13], nhard);
       for (unsigned hq = (unsigned)warp; hq < nhard; hq += kDenseThreads / 32) {
         HardRec& hr = sm.hard[hq];
         const double hx = hr.q[0], hy = hr.q[1], hz = hr.q[2];
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         }
       }
       __syncthreads();
+      if (a.dbg && tid == 0) tk_p2 += clock64() - tk2;
       if (hslot >= 0) {
         const HardRec& hr = sm.hard[hslot];
 #pragma unroll
@@ -477,6 +480,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
       atomicAdd(&a.dbg[8], (unsigned)((clock64() - tk0) >> 6)); atomicAdd(&a.dbg[9], (unsigned)(tk_wait >> 6));
       atomicAdd(&a.dbg[10], (unsigned)(tk_sort >> 6)); atomicAdd(&a.dbg[11], (unsigned)(tk_search >> 6));
       if (wk.qcnt <= 8) atomicAdd(&a.dbg[12], 1u);
+      atomicAdd(&a.dbg[14], (unsigned)(tk_p1 >> 6)); atomicAdd(&a.dbg[15], (unsigned)(tk_p2 >> 6));
     }
     // ---- fit + lazy GNC weight update + outputs (as k_correspond) ----
     if (owner) {

@@ -94,6 +94,7 @@ __device__ __forceinline__ void begin_frame_body(const DeviceCtx& ctx, const Pre
   st->status = TLOAM_B200_OK;
   st->frame_done = 0;
   *ctx.counter = 0u;
+  for (int c = 0; c < 4; ++c) st->map_bricks[c] = ctx.map_bricks[c];   // map statistics ride home with the result
   for (int i = 0; i < 16; ++i) st->last_pose[i] = st->curr_pose[i];            // :882
   Pose7 p;
   if (*ctx.map_flags & 1ull) {                   // a map cell overflowed its u16 counter at build time

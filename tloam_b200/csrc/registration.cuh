@@ -75,6 +75,7 @@ struct FrameState {
   double result[16];
   int frame_done, status;   // directly after `result`: the host fetches the three with ONE copy
   double fitness, rmse;     // getFitnessScore of this frame's scan (k_fitness_reduce), fetched with the same copy
+  unsigned map_bricks[4];   // occupied bricks per cloud of the map this frame registered against (k_begin_frame), idem
   double curr_pose[16], last_pose[16];
 };
 static_assert(offsetof(FrameState, frame_done) == offsetof(FrameState, result) + 16 * sizeof(double), "result + flags must be contiguous");
@@ -86,6 +87,7 @@ struct DeviceCtx {
   const double* origin;         // -> MapHeader::origin inside the map blob (device memory)
   const unsigned long long* map_flags;   // -> MapHeader::build_flags
   const unsigned* tgt_cnt[4];   // device-side point counts of the map clouds (sync-free submap chain), or nullptr
+  const unsigned* map_bricks;   // -> MapHeader::nbricks
   double r2[4];                 // squared search radius per cloud
   int n[4];                     // features per cloud
   int pad_off[4];               // first padded feature index of each cloud (multiple of kBlk)

@@ -19,7 +19,6 @@
 #include "feature_extract.cuh"
 #include "ground_extract.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 
 
 // =================================================================================================
@@ -436,6 +435,7 @@ static void bind_map(tloam_b200_handle* h) {
   }
   c.origin = reinterpret_cast<const double*>(h->d_blob + offsetof(MapHeader, origin));
   c.map_flags = reinterpret_cast<const unsigned long long*>(h->d_blob + offsetof(MapHeader, build_flags));
+  c.map_bricks = reinterpret_cast<const unsigned*>(h->d_blob + offsetof(MapHeader, nbricks));
 }
 
 // the origin lives in the device header; fetch it once per map (tiny D2H) so that it can be passed by value
@@ -550,11 +550,14 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
   bind_map(h);
   h->origin_known = false;
   h->have_tgt = true;
-  // occupied bricks per cloud -> pinned host memory, harvested when it has landed (it picks the search path of LATER
-  // frames; both paths return the same exact neighbours, so the choice never changes a pose)
-  CU_TRY(cudaMemcpyAsync(h->h_mapstats, h->d_blob + offsetof(MapHeader, nbricks), 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(cudaEventRecord(h->ev_stats, h->stream));
-  h->stats_pending = true;
+  // occupied bricks per cloud pick the search path (points per brick).  They come home with every frame's result
+  // (FrameState::map_bricks); only the FIRST map of a handle is read back on its own, so that the very first frame can
+  // already be routed -- both paths return the same exact neighbours, so the choice never changes a pose
+  if (!h->stats_known) {
+    CU_TRY(cudaMemcpyAsync(h->h_mapstats, h->d_blob + offsetof(MapHeader, nbricks), 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaEventRecord(h->ev_stats, h->stream));
+    h->stats_pending = true;
+  }
   // host path: the caller's buffers are free once the LAST upload has landed; the build of the last cloud may
   // still be running on the compute stream (everything that follows is ordered behind it on that stream)
   if (!on_device && total > 0) CU_TRY(cudaEventSynchronize(h->ev_copy[1 + h->last_uploaded]));
@@ -808,7 +811,7 @@ static bool caps_cannot_bind(const tloam_b200_handle* h) {
   return true;
 }
 
-static constexpr size_t kFrameResultBytes = 16 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(double);
+static constexpr size_t kFrameResultBytes = 16 * sizeof(double) + 2 * sizeof(int) + 2 * sizeof(double) + 4 * sizeof(unsigned);
 static BatchTab no_batch() { BatchTab t; memset(&t, 0, sizeof(t)); t.S = 1; return t; }
 
 // correspondence search + fit of one outer iteration as kernels of their own (un-fused sequence, build_factors)
@@ -980,12 +983,13 @@ int tloam_b200_get_result(tloam_b200_handle* h, double result[16], tloam_b200_st
     h->frame_pending = false;
     h->frames_fetched = h->frames_enqueued;
   }
-  harvest_map_stats(h, false);                 // picks the newest map's statistics up once they have landed
   harvest_counts(h);
   memcpy(result, slot, 16 * sizeof(double));
   int flags[2];
   memcpy(flags, slot + 16, sizeof(flags));   // frame_done, status
   h->last_fitness = slot[17]; h->last_rmse = slot[18];
+  memcpy(h->nbricks, slot + 19, 4 * sizeof(unsigned));   // statistics of the map this frame used: route the next frames
+  h->stats_known = true; h->stats_pending = false;
   if (stats) {
     *stats = *h->h_stats;
     stats->gpu_launches = h->launches_frame;
@@ -1661,9 +1665,8 @@ namespace {
 struct FeArena {
   double* stage; unsigned* scratch; unsigned char* blob; MapHeader hdr;
   FeOut out;
-  unsigned long long *key_p, *key_s, *key_p_sorted, *key_s_sorted;
-  unsigned *val, *val_p_sorted, *val_s_sorted, *counts;
-  void* cub_tmp; size_t cub_bytes;
+  unsigned long long *key_p_sorted, *key_s_sorted;
+  unsigned *val_p_sorted, *val_s_sorted, *counts;
   unsigned *host_val_p = nullptr, *host_val_s = nullptr;   // optional: the sorted index lists land here (one sync)
 };
 }  // namespace
@@ -1685,16 +1688,14 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   }
   for (int c = 0; c < 4; ++c) { hd.table_off[c] = boff; boff += (size_t)hd.tsize[c] * kBrickBytes; }
   for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
-  A.cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, A.cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                            (const unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 64, h->stream);
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
   const size_t o_stage = take(n * 3 * sizeof(double)), o_scr = take(n * 2 * sizeof(unsigned)), o_blob = take(boff);
   const size_t o_cvr = take(n * 8), o_flat = take(n * 8), o_sph = take(n * 8), o_nrm = take(n * 24), o_num = take(n * 4),
                o_nei = take(n * kFeK * 4);
-  const size_t o_kp = take(n * 8), o_ks = take(n * 8), o_kps = take(n * 8), o_kss = take(n * 8), o_val = take(n * 4),
-               o_vps = take(n * 4), o_vss = take(n * 4), o_cnt = take(256), o_cub = take(A.cub_bytes);
+  size_t npad = 1;                                     // the bitonic network pads each candidate list to a power of two
+  while (npad < n) npad <<= 1;
+  const size_t o_kps = take(npad * 8), o_kss = take(npad * 8), o_vps = take(npad * 4), o_vss = take(npad * 4), o_cnt = take(256);
   if (off > h->cap_fe) {
     cudaFree(h->d_fe);
     h->cap_fe = off + off / 4;
@@ -1704,10 +1705,9 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   A.stage = (double*)(b + o_stage); A.scratch = (unsigned*)(b + o_scr); A.blob = b + o_blob;
   A.out.cvr = (double*)(b + o_cvr); A.out.flatness = (double*)(b + o_flat); A.out.sphericity = (double*)(b + o_sph);
   A.out.normal = (double*)(b + o_nrm); A.out.num_sum = (int*)(b + o_num); A.out.neigh = (int*)(b + o_nei);
-  A.key_p = (unsigned long long*)(b + o_kp); A.key_s = (unsigned long long*)(b + o_ks);
   A.key_p_sorted = (unsigned long long*)(b + o_kps); A.key_s_sorted = (unsigned long long*)(b + o_kss);
-  A.val = (unsigned*)(b + o_val); A.val_p_sorted = (unsigned*)(b + o_vps); A.val_s_sorted = (unsigned*)(b + o_vss);
-  A.counts = (unsigned*)(b + o_cnt); A.cub_tmp = b + o_cub;
+  A.val_p_sorted = (unsigned*)(b + o_vps); A.val_s_sorted = (unsigned*)(b + o_vss);
+  A.counts = (unsigned*)(b + o_cnt);
 
   CU_TRY(cudaMemcpyAsync(A.stage, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CU_TRY(cudaMemcpyAsync(A.blob, &hd, sizeof(MapHeader), cudaMemcpyHostToDevice, h->stream));
@@ -1745,13 +1745,10 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   }
   TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_pca<<<(unsigned)((n + kFeBlk - 1) / kFeBlk), kFeBlk, kFeSmemBytes, h->stream>>>(g, prm, A.out)));
   if (select) {
-    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_classify<<<gb, tb, 0, h->stream>>>((unsigned)n, prm, A.out, A.key_p, A.key_s, A.val, A.counts)));
-    // stable descending sorts: candidates first (by flatness, ties in ascending point index), the rest (key 0) last
-    size_t tmp = A.cub_bytes;
-    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(A.cub_tmp, tmp, A.key_p, A.key_p_sorted, A.val, A.val_p_sorted, (int)n, 0, 64, h->stream));
-    tmp = A.cub_bytes;
-    CU_TRY(cub::DeviceRadixSort::SortPairsDescending(A.cub_tmp, tmp, A.key_s, A.key_s_sorted, A.val, A.val_s_sorted, (int)n, 0, 64, h->stream));
-    h->launches += 2;
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_classify<<<gb, tb, 0, h->stream>>>((unsigned)n, prm, A.out, A.key_p_sorted, A.key_s_sorted, A.val_p_sorted,
+                                                                              A.val_s_sorted, A.counts)));
+    // candidates first compacted, then ordered by (flatness descending, point index ascending): hand-written bitonic sort
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_sort<<<2, 1024, 0, h->stream>>>(A.key_p_sorted, A.val_p_sorted, A.key_s_sorted, A.val_s_sorted, A.counts)));
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_counts<<<1, 32, 0, h->stream>>>(A.key_p_sorted, A.key_s_sorted, A.counts, cfg->planar_num,
                                                                            cfg->sphere_num, cfg->planar_scan_thres, cfg->cvr_scan)));
   }

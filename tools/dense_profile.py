@@ -20,5 +20,7 @@ c = reg.dense_check_counters()
 items = max(c[2], 1)
 print(json.dumps({"queries": c[0], "mismatches": c[1], "items": c[2], "passes": c[3], "items_le_8_queries": c[12],
                   "queries_per_item": c[0] / items, "kcycles_per_item": {"total": c[8] * 64 / items / 1e3, "tma_wait": c[9] * 64 / items / 1e3,
-                                                                           "fine_sort": c[10] * 64 / items / 1e3, "search": c[11] * 64 / items / 1e3},
+                                                                           "fine_sort": c[10] * 64 / items / 1e3, "search": c[11] * 64 / items / 1e3,
+                                                                           "phase1_27cells": c[14] * 64 / items / 1e3, "phase2_hard": c[15] * 64 / items / 1e3},
+                  "hard_queries": c[13],
                   "gpu_ms": st.gpu_ms}))
