@@ -53,6 +53,8 @@ class LocalRegistrationB200 : public RegistrationInterface {
     c.gnc_factor = node["gnc_factor"].as<double>();
     c.noise_bound = node["noise_bound"].as<double>();
     c.fitness_thres = node["fitness_thres"].as<double>();
+    // extras of the POD (not in the reference YAML): optional keys, Ceres defaults otherwise
+    if (node["initial_trust_region_radius"]) c.initial_trust_region_radius = node["initial_trust_region_radius"].as<double>();
     create(c, device, stream);
   }
 #endif

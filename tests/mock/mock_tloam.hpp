@@ -1,7 +1,7 @@
 // Minimal stand-ins for the host-side types the C++ shim touches, so that it can be compiled and exercised in
 // an image without Eigen / Open3D / ROS.  Written for this repository's tests; only the members the shim uses
 // exist: Vector3d = 3 contiguous doubles with operator[], Isometry3d::matrix().data() = 16 doubles column-major,
-// PointCloud2::points_, Frame's five shared_ptrs, CloudData::cloud_ptr, RegistrationInterface's four virtuals.
+// PointCloud2::points_ / intensity_, Frame's five shared_ptrs, CloudData::cloud_ptr, RegistrationInterface's four virtuals.
 #pragma once
 #include <array>
 #include <memory>
@@ -29,7 +29,7 @@ struct Isometry3d {
 }  // namespace Eigen
 
 namespace open3d { namespace geometry {
-struct PointCloud2 { std::vector<Eigen::Vector3d> points_; };
+struct PointCloud2 { std::vector<Eigen::Vector3d> points_; std::vector<double> intensity_; };   // ref: PointCloud2.hpp:396-408
 }}  // namespace open3d::geometry
 
 namespace tloam {

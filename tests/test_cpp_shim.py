@@ -31,6 +31,7 @@ def test_shim_compiles_as_cpp14_against_host_types():
     """C++14 like the reference (CMakeLists.txt:4); -Wall -Wextra clean."""
     assert os.path.exists(build_driver())
     assert os.path.exists(build_driver("feature_driver", "feature_extract_b200.hpp"))
+    assert os.path.exists(build_driver("ground_driver", "ground_extract_b200.hpp"))
 
 
 def test_shim_fails_loudly_without_gpu():
@@ -94,3 +95,32 @@ def test_feature_shim_matches_oracle(oracle):
         n = vals[k]; lst = vals[k + 1:k + 1 + n]; k += 1 + n
         assert lst[0] == 987654321 and np.array_equal(np.asarray(lst[1:], dtype=np.uintp), r)
     assert k == len(vals)
+
+
+@pytest.mark.gpu
+def test_ground_shim_matches_oracle(oracle):
+    """tloam::GroundExtractB200::groundRemove driven like Segmentation::spinOnce: ground_scan / object_scan receive (+=)
+    exactly the points the CPU restatement selects, in its order, with the intensities of the reference."""
+    from tloam_b200 import synth
+    exe = build_driver("ground_driver", "ground_extract_b200.hpp")
+    pts = synth.raw_scan(seed=4, n_az=600)
+    path = os.path.join(os.path.dirname(EXE), "scan.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("Q", pts.shape[0]))
+        f.write(np.ascontiguousarray(pts, dtype=np.float64).tobytes())
+    res = subprocess.run([exe, path], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.strip().split("\n")
+    ng, no, ncur, thr = lines[0].split()
+    ref = oracle.ground_extract(pts)
+    assert int(ng) == 1 + len(ref["ground"]) and int(no) == 1 + len(ref["object"]) and float(thr) == ref["height_threshold"]
+    assert int(ncur) == int(np.sum(ref["region"] != 12))
+    rows = [l.split() for l in lines[1:]]
+    xbits = pts[:, 0].copy().view(np.uint64)
+    g = rows[:int(ng)]
+    o = rows[int(ng):]
+    assert float(g[0][1]) == -1.0 and float(o[0][1]) == -1.0                     # the sentinels stay in front (+=)
+    assert [int(r[0]) for r in g[1:]] == [int(xbits[i]) for i in ref["ground"]]
+    assert all(float(r[1]) == 0.0 for r in g[1:])
+    assert [int(r[0]) for r in o[1:]] == [int(xbits[i]) for i in ref["object"]]
+    assert [float(r[1]) for r in o[1:]] == [float(ref["beam"][i]) for i in ref["object"]]

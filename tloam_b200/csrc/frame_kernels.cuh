@@ -581,8 +581,11 @@ k_eval(const __grid_constant__ DeviceCtx one, const __grid_constant__ BatchTab t
 // needs a prefix over ALL earlier features of the cloud, i.e. a grid-wide dependency); the host picks the unfused
 // sequence otherwise.  Per-sequence grid = 2 x feature blocks rounded up to the cluster size (padding blocks only
 // take part in the reduction).  The search arrays are dead when the reduction starts and share its memory.
+#ifndef TLOAM_FIRST_MINBLOCKS_BATCHED
+#define TLOAM_FIRST_MINBLOCKS_BATCHED 5
+#endif
 template <bool kBatched>
-__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk, 5)
+__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk, kBatched ? TLOAM_FIRST_MINBLOCKS_BATCHED : 5)
 k_first(const __grid_constant__ DeviceCtx one, const __grid_constant__ BatchTab tab) {
   TL_RESOLVE_CTX(one, tab);
   const FrameState* st = ctx.st;
