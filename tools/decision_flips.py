@@ -22,9 +22,15 @@ BIG = 10 ** 9
 CAPS = dict(edge_maxnum=BIG, sphere_maxnum=BIG, planar_maxnum=BIG, ground_maxnum=BIG)
 
 
-def ulp_jitter(a, rng):
+def ulp_jitter(a, rng, level="f64"):
+    """+-1 ulp in a random direction: of the FP64 value, or of its FP32 rounding (the device stores map coordinates in
+    FP32 relative to the map origin, so only an FP32-sized step reaches the search)."""
     a = np.ascontiguousarray(a, dtype=np.float64)
     up = rng.random(a.shape) < 0.5
+    if level == "f32":
+        f = a.astype(np.float32)
+        step = np.where(up, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))).astype(np.float64) - f.astype(np.float64)
+        return a + step
     return np.where(up, np.nextafter(a, np.inf), np.nextafter(a, -np.inf))
 
 
@@ -41,7 +47,7 @@ def register(mp, scan, predict, x0):
     return T, valid, trace
 
 
-def run(R=5, scale=1.0, seed=1):
+def run(R=5, scale=1.0, seed=1, level="f64"):
     f = synth.config1() if scale >= 1.0 else None
     if f is None:
         cfg = synth.scaled(scale, seed=20260924 + 1000)
@@ -54,8 +60,8 @@ def run(R=5, scale=1.0, seed=1):
     rng = np.random.default_rng(seed)
     rows = []
     for _ in range(R):
-        mp = [ulp_jitter(c, rng) for c in f["map"]]
-        sc = [ulp_jitter(c, rng) for c in f["scan"]]
+        mp = [ulp_jitter(c, rng, level) for c in f["map"]]
+        sc = [ulp_jitter(c, rng, level) for c in f["scan"]]
         T, v, tr = register(mp, sc, f["predict"], x0)
         d = np.linalg.inv(T0) @ T
         rows.append({"validity_flips_outer0": [int(np.sum(a != b)) for a, b in zip(v0, v)],
@@ -64,7 +70,7 @@ def run(R=5, scale=1.0, seed=1):
                      "dt_m": float(np.linalg.norm(d[:3, 3])),
                      "dr_rad": float(np.arccos(np.clip((np.trace(d[:3, :3]) - 1) / 2, -1, 1)))})
     nfeat = [int(len(c)) for c in f["scan"]]
-    return {"features": nfeat, "perturbation": "+-1 ulp on every scan and map coordinate (FP64), random sign", "runs": rows,
+    return {"features": nfeat, "perturbation": f"+-1 {level} ulp on every scan and map coordinate, random sign", "runs": rows,
             "max_validity_flips_outer0": int(max(sum(r["validity_flips_outer0"]) for r in rows)),
             "max_dt_m": max(r["dt_m"] for r in rows), "max_dr_rad": max(r["dr_rad"] for r in rows),
             "note": "map coordinates are stored in FP32 on the device, so a 1-ulp FP64 change of a map point only matters when it crosses "
@@ -72,4 +78,5 @@ def run(R=5, scale=1.0, seed=1):
 
 
 if __name__ == "__main__":
-    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 5)))
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+    print(json.dumps({"f64_ulp": run(R, level="f64"), "f32_ulp": run(R, level="f32")}))
