@@ -33,11 +33,10 @@ def make_reg(dense, **cfg):
     import tloam_b200
     os.environ["TLOAM_B200_DENSE"] = "1" if dense else "0"
     os.environ["TLOAM_B200_DENSE_CHECK"] = "1"       # every dense query is re-searched by the plain path on the device
-    os.environ["TLOAM_B200_NO_FUSE"] = "1"           # both runs take the un-fused kernel sequence: same reduction tree
     try:
         return tloam_b200.LocalRegistration(**cfg)
     finally:
-        for k in ("TLOAM_B200_DENSE", "TLOAM_B200_DENSE_CHECK", "TLOAM_B200_NO_FUSE"):
+        for k in ("TLOAM_B200_DENSE", "TLOAM_B200_DENSE_CHECK"):
             os.environ.pop(k, None)
 
 

@@ -207,8 +207,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __grid_constant__ DeviceCtx ctx, const __grid_constant__ DenseArgs a) {
   const FrameState* st = ctx.st;
   if (st->frame_done || st->phase != kPhaseIter0) return;
-  extern __shared__ unsigned char dense_raw[];
-  DenseSmem& sm = *reinterpret_cast<DenseSmem*>((reinterpret_cast<uintptr_t>(dense_raw) + 127) & ~(uintptr_t)127);
+  // NOTE: no integer round trip on this pointer -- an address rebuilt from a uintptr_t loses the shared state space and
+  // every access of the kernel becomes a generic LD / ATOM (measured: 0 LDS in the SASS, the search phases ran ~10x slower)
+  extern __shared__ __align__(128) unsigned char dense_raw[];
+  DenseSmem& sm = *reinterpret_cast<DenseSmem*>(dense_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) mbar_init(&sm.mbar, 1u);
   __syncthreads();
@@ -414,18 +416,30 @@ __global__ void __launch_bounds__(kDenseThreads, 1) k_correspond_dense(const __g
         tl.init();
         double hb = hr.d2[4] < r2 ? hr.d2[4] : r2;
         float hbf = (float)hb * 1.00001f + 2e-6f;
-#pragma unroll 4
-        for (int i = lane; i < fill; i += 32) {
-          const float4 p = sm.pts[i];
-          const float fx = (p.x - bxf) - hlx, fy = (p.y - byf) - hly, fz = (p.z - bzf) - hlz;
-          const float df = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
-          if (df <= hbf) {
-            const double ddx = (double)p.x - hx, ddy = (double)p.y - hy, ddz = (double)p.z - hz;
-            const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
-            if (d < r2) {
-              tl.insert(d, __float_as_int(p.w), p.x, p.y, p.z);
-              hb = tl.d2[4] < hb ? tl.d2[4] : hb;
-              hbf = (float)hb * 1.00001f + 2e-6f;
+        // software-pipelined by hand: 4 coalesced 16-byte loads in flight per lane, the 4 FP32 distances, then the tests
+        for (int i0 = lane; i0 < fill; i0 += 128) {
+          float4 p[4];
+          float df[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            p[u] = sm.pts[i < fill ? i : i0];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float fx = (p[u].x - bxf) - hlx, fy = (p[u].y - byf) - hly, fz = (p[u].z - bzf) - hlz;
+            df[u] = (i0 + 32 * u < fill) ? fmaf(fz, fz, fmaf(fy, fy, fx * fx)) : 3.0e38f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (df[u] <= hbf) {
+              const double ddx = (double)p[u].x - hx, ddy = (double)p[u].y - hy, ddz = (double)p[u].z - hz;
+              const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
+              if (d < r2) {
+                tl.insert(d, __float_as_int(p[u].w), p[u].x, p[u].y, p[u].z);
+                hb = tl.d2[4] < hb ? tl.d2[4] : hb;
+                hbf = (float)hb * 1.00001f + 2e-6f;
+              }
             }
           }
         }

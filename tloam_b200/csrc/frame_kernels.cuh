@@ -534,8 +534,11 @@ __device__ __forceinline__ Pose7 load_eval_pose(const FrameState* st) {   // rea
 // One evaluation pass of the whole problem at st->evalq + reduction + solver (last cluster leader).
 // Grid-stride over the 128-feature blocks of the sequence.  Clusters of 8 blocks: the block totals are combined
 // through distributed shared memory before they reach global memory, so the serial tail sums 1/8 of the rows.
+#ifndef TLOAM_EVAL_MINBLOCKS_BATCHED
+#define TLOAM_EVAL_MINBLOCKS_BATCHED 3
+#endif
 template <bool kFirst, bool kBatched>
-__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk, 3)
+__global__ void __cluster_dims__(kEvalCluster, 1, 1) __launch_bounds__(kBlk, kBatched ? TLOAM_EVAL_MINBLOCKS_BATCHED : 3)
 k_eval(const __grid_constant__ DeviceCtx one, const __grid_constant__ BatchTab tab) {
   TL_RESOLVE_CTX(one, tab);
   const FrameState* st = ctx.st;

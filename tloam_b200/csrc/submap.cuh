@@ -10,9 +10,12 @@
 //
 // VoxelDownSample on the device: voxel index = floor((p - (min_bound - voxel/2)) / voxel) like the reference;
 // the per-voxel average is accumulated in 64-bit FIXED POINT (offsets inside the voxel, 2^-40 m resolution), so
-// the result does not depend on the order of the atomics (bit-reproducible) and differs from the reference's
-// FP64 running sum by < 1e-12 m.  The output ORDER is the hash-table slot order (the reference's is
-// std::unordered_map iteration order -- implementation-defined; downstream results do not depend on it).
+// the VALUES do not depend on the order of the atomics (bit-reproducible) and differ from the reference's
+// FP64 running sum by < 1e-12 m.  The output ORDER is not reproducible: slots are claimed by CAS and k_vox_emit takes
+// its output base with one atomicAdd per block, so it follows block scheduling (the reference's own order is
+// std::unordered_map iteration order -- implementation-defined).  Downstream, point order only enters the kNN
+// tie-break (d2, original index): it can matter for EXACT distance ties between two averaged voxel centres, nowhere else
+// (tests compare maps as sets and registration results for equality).
 #pragma once
 #include <cuda_runtime.h>
 
