@@ -113,12 +113,16 @@ def test_dense_path_with_many_staging_passes():
 
 def test_dense_path_is_picked_automatically_for_a_dense_map():
     """points per occupied brick >= 256 and >= 2048 queries per cloud: the handle waits ONCE for the statistics of its
-    first map (later maps are judged by their predecessor's, read back asynchronously) and takes the dense path without
-    any environment override; the pose equals the lane-pair search's."""
+    first map (later maps are judged by the statistics that come home with every frame's result) and takes the dense path
+    under TLOAM_B200_DENSE=auto; the pose equals the lane-pair search's."""
     import tloam_b200
     sc = very_dense_scene()
     cfg = dict(factor_num=2, **CAPS)
-    r = tloam_b200.LocalRegistration(**cfg)
+    os.environ["TLOAM_B200_DENSE"] = "auto"
+    try:
+        r = tloam_b200.LocalRegistration(**cfg)
+    finally:
+        os.environ.pop("TLOAM_B200_DENSE", None)
     r.set_input_target(sc["map"])
     r.set_input_source(sc["scan"])
     T1, s1 = r.scan_matching(sc["predict"], want_stats=True)

@@ -123,7 +123,7 @@ struct tloam_b200_handle {
   unsigned* h_mapstats = nullptr;          // pinned: occupied bricks per cloud of the newest map
   cudaEvent_t ev_stats = nullptr;          bool stats_pending = false, stats_known = false;
   unsigned nbricks[4] = {0, 0, 0, 0};
-  int dense_mode = -1;                     // TLOAM_B200_DENSE: -1 auto (points per brick), 0 never, 1 always
+  int dense_mode = 0;                      // TLOAM_B200_DENSE: "auto" -> -1 (points per brick), unset -> 0 never, "1" always
   bool dense_attr_set = false;
   bool dense_check = false;                // TLOAM_B200_DENSE_CHECK=1: every dense query is re-searched by the plain path and compared
   int num_sms = 148;
@@ -239,7 +239,10 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   { const char* e = getenv("TLOAM_B200_FUSE"); h->use_fused = (e && e[0] == '1'); }
   { const char* e = getenv("TLOAM_B200_NO_FUSE"); if (e && e[0] == '1') h->use_fused = false; }
   { const char* e = getenv("TLOAM_B200_DENSE_CHECK"); h->dense_check = (e && e[0] == '1'); }
-  { const char* e = getenv("TLOAM_B200_DENSE"); if (e && (e[0] == '0' || e[0] == '1')) h->dense_mode = e[0] - '0'; }
+  // dense-map search path (dense_search.cuh): off unless asked for.  "1" = always for the K = 5 clouds, "auto" = by the
+  // points-per-brick statistics of the map.  Measured on config 3 it is still SLOWER than the lane-pair search (4.1 vs
+  // 3.0 ms per launch): correct and TMA-staged, not yet a win.
+  { const char* e = getenv("TLOAM_B200_DENSE"); h->dense_mode = 0; if (e && e[0] == '1') h->dense_mode = 1; else if (e && e[0] == 'a') h->dense_mode = -1; }
   if (cudaMallocHost(&h->h_mapstats, 4 * sizeof(unsigned)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_stats, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->num_sms = v; }
