@@ -33,25 +33,35 @@ __device__ __forceinline__ double norm6(const double* v) {
   return sqrt(s);
 }
 
-// LDL^T solve of the SPD 6x6 system A y = b, fully unrolled (registers only, ~160 FP64 instructions, six
-// reciprocals, no square roots).  Returns false if a pivot is not positive / finite.
-__device__ __forceinline__ bool ldlt_solve6(const double A[36], const double b[6], double y[6]) {
-  double L[36], d[6], dinv[6];
+// LDL^T solve of the SPD 6x6 system A y = b on the PACKED upper triangle (21 entries, tri(i,j), i <= j), IN PLACE: the
+// factor overwrites A (L(i,j), i > j, lands in a[tri(j,i)]).  Fully unrolled with compile-time indices only, so the
+// whole factorisation lives in registers: the previous full-matrix form kept A / L / H_s (3 x 36 doubles) in LOCAL
+// memory (221 LDL/STL in the SASS of k_eval, most of the 3.5k cycles of the Gauss-Newton model).  Same operations in
+// the same order as before (sum over k ascending, (L L) d), six reciprocals, no square roots.  Returns false if a
+// pivot is not positive / finite.
+__device__ __forceinline__ bool ldlt_solve6_packed(double a[21], const double b[6], double y[6]) {
+  // every loop runs over the constant range 0..5 with the triangular bounds as (compile-time) predicates: loops whose
+  // bounds depend on an outer unrolled variable were left rolled by the front end, which put `a` in local memory
+  double d[6], dinv[6];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double s = A[j * 6 + j];
+    double s = a[tri(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; ++k) s -= L[j * 6 + k] * L[j * 6 + k] * d[k];
+    for (int k = 0; k < 6; ++k)
+      if (k < j) s -= a[tri(k, j)] * a[tri(k, j)] * d[k];
     d[j] = s;
     ok = ok && (s > 0.0) && isfinite(s);
     dinv[j] = 1.0 / s;
 #pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double t = A[i * 6 + j];
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double t = a[tri(j, i)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) t -= L[i * 6 + k] * L[j * 6 + k] * d[k];
-      L[i * 6 + j] = t * dinv[j];
+        for (int k = 0; k < 6; ++k)
+          if (k < j) t -= a[tri(k, i)] * a[tri(k, j)] * d[k];
+        a[tri(j, i)] = t * dinv[j];
+      }
     }
   }
   if (!ok) return false;
@@ -60,14 +70,17 @@ __device__ __forceinline__ bool ldlt_solve6(const double A[36], const double b[6
   for (int i = 0; i < 6; ++i) {
     double t = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) t -= L[i * 6 + k] * z[k];
+    for (int k = 0; k < 6; ++k)
+      if (k < i) t -= a[tri(k, i)] * z[k];
     z[i] = t;
   }
 #pragma unroll
-  for (int i = 5; i >= 0; --i) {
+  for (int ii = 0; ii < 6; ++ii) {
+    const int i = 5 - ii;
     double t = z[i] * dinv[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) t -= L[k * 6 + i] * y[k];
+    for (int k = 0; k < 6; ++k)
+      if (k > i) t -= a[tri(i, k)] * y[k];
     y[i] = t;
   }
   bool fin = true;
@@ -129,27 +142,23 @@ struct GnModel {
 
 __device__ __forceinline__ void gn_model(const double H[21], const double g[6], const double scale[6], double mu_lm,
                                          GnModel& m) {
-  double Hs[36], gs[6], d2[6];
+  double gs[6], d2[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     gs[i] = scale[i] * g[i];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const double h = (i <= j) ? H[tri(i, j)] : H[tri(j, i)];
-      Hs[i * 6 + j] = scale[i] * h * scale[j];
-    }
+    d2[i] = fmin(fmax(scale[i] * H[tri(i, i)] * scale[i], 1e-6), 1e32);          // min/max_lm_diagonal of (S H S)_ii
   }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) d2[i] = fmin(fmax(Hs[i * 6 + i], 1e-6), 1e32);     // min/max_lm_diagonal
   bool ok = false;
   double y[6] = {0, 0, 0, 0, 0, 0};
   while (mu_lm < 1.0) {                                         // kMaxMu
-    double A[36];
+    double A[21];                                               // (S H S + mu D^2), packed upper triangle, rebuilt per try
 #pragma unroll
-    for (int i = 0; i < 36; ++i) A[i] = Hs[i];
+    for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) A[i * 6 + i] += mu_lm * d2[i];
-    if (ldlt_solve6(A, gs, y)) { ok = true; break; }
+      for (int j = i; j < 6; ++j) A[tri(i, j)] = scale[i] * H[tri(i, j)] * scale[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[tri(i, i)] += mu_lm * d2[i];
+    if (ldlt_solve6_packed(A, gs, y)) { ok = true; break; }
     mu_lm *= 10.0;                                              // mu_increase_factor_
   }
   double n2 = 0.0;
@@ -166,9 +175,17 @@ __device__ __forceinline__ void gn_model(const double H[21], const double g[6], 
 }
 
 // single out-of-line copies of the Lie-group routines (the solver is instruction-fetch bound: keep it small)
-__device__ __noinline__ void s_exp(const double a[6], Pose7* out) { *out = se3_exp(a); }
-__device__ __noinline__ void s_log(const Pose7* p, double out[6]) { se3_log(*p, out); }
-__device__ __noinline__ void s_mul(const Pose7* a, const Pose7* b, Pose7* out) { *out = se3_mul(*a, *b); }
+#ifndef TLOAM_SOLVER_INLINE_LIE
+#define TLOAM_SOLVER_INLINE_LIE 0
+#endif
+#if TLOAM_SOLVER_INLINE_LIE
+#define TL_LIE_INLINE __forceinline__
+#else
+#define TL_LIE_INLINE __noinline__
+#endif
+__device__ TL_LIE_INLINE void s_exp(const double a[6], Pose7* out) { *out = se3_exp(a); }
+__device__ TL_LIE_INLINE void s_log(const Pose7* p, double out[6]) { se3_log(*p, out); }
+__device__ TL_LIE_INLINE void s_mul(const Pose7* a, const Pose7* b, Pose7* out) { *out = se3_mul(*a, *b); }
 
 struct SolverIO {
   const DeviceCtx* ctx;

@@ -1,11 +1,11 @@
 #!/bin/bash
-# A/B: k_eval occupancy variants in batched mode
-for v in default emb4 emb5; do
+# A/B: solver variants (single stream, inputs in HBM)
+for v in default lie_inline before_ldlt default; do
   unset TLOAM_B200_LIB
   case $v in
-    emb4) export TLOAM_B200_LIB=$PWD/build/variants/eval_mb4.so ;;
-    emb5) export TLOAM_B200_LIB=$PWD/build/variants/eval_mb5.so ;;
+    lie_inline) export TLOAM_B200_LIB=$PWD/build/variants/lie_inline.so ;;
+    before_ldlt) export TLOAM_B200_LIB=$PWD/build/variants/before_ldlt.so ;;
   esac
   echo "== $v"
-  python tools/batch_bench.py 8 2>&1 | tail -1
+  python tools/multi_stream.py 1 2>&1 | tail -1
 done
