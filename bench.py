@@ -204,6 +204,48 @@ def run_stream(reg, frames, prev_gt, mode, torch, warmup, steps):
     return e0.elapsed_time(e1), poses, reg.launch_count() - launches0
 
 
+def run_batch_groups(bregs, data, torch, warmup, steps):
+    """G BatchRegistration objects (S/G sequences each) in flight together on one GPU: every batch frame is enqueued
+    asynchronously for all groups before any result is fetched, so one group's serial solver tails overlap the other
+    groups' parallel phases.  Inputs resident in HBM.  Returns (ms_total_timed, poses[s][k])."""
+    G = len(bregs)
+    per = bregs[0].S
+    nfr = warmup + steps
+    packs = []
+    for k in range(nfr):
+        row = []
+        for g, b in enumerate(bregs):
+            mp = [[torch.from_numpy(c).cuda() for c in data[g * per + s][0][k]["map"]] for s in range(per)]
+            sc = [[torch.from_numpy(c).cuda() for c in data[g * per + s][0][k]["scan"]] for s in range(per)]
+            row.append((b.pack_device(mp), b.pack_device(sc)))
+        packs.append(row)
+    torch.cuda.synchronize()
+    S = G * per
+    last = [data[s][1].copy() for s in range(S)]
+    cur = [None] * S
+    poses = [[] for _ in range(S)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(nfr):
+        if k == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        for g, b in enumerate(bregs):
+            predicts = np.stack([first_predict(data[g * per + s][0][k]) if cur[g * per + s] is None else
+                                 predict_next(last[g * per + s], cur[g * per + s]) for s in range(per)])
+            b.set_input_target_device(packs[k][g][0])
+            b.set_input_source_device(packs[k][g][1])
+            b.scan_matching_async(predicts)
+        for g, b in enumerate(bregs):
+            T, st = b.get_results()
+            for s in range(per):
+                i = g * per + s
+                poses[i].append(T[s])
+                last[i], cur[i] = (cur[i] if cur[i] is not None else data[i][1]), T[s]
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), poses
+
+
 def run_batch(breg, data, torch, warmup, steps, mode="device"):
     """S sequences stepped together through tloam_b200_batch_*: per batch frame S x (set_target + set_source) on the
     sequences' own streams, then ONE launch sequence for the S registrations.  data[s] = (frames, prev_gt).

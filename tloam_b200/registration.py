@@ -518,6 +518,22 @@ class BatchRegistration:
         self._check(rc, "batch_scan_matching")
         return np.transpose(out.reshape(self.S, 4, 4), (0, 2, 1)).copy(), st
 
+    def scan_matching_async(self, predicts=None):
+        """Enqueue only (several BatchRegistration objects can be in flight on one GPU: their serial solver tails then
+        overlap with the others' parallel phases); fetch with get_results()."""
+        p = None
+        if predicts is not None:
+            p = _f64(np.transpose(np.asarray(predicts).reshape(self.S, 4, 4), (0, 2, 1))).reshape(-1)
+            self._keep["predicts"] = p
+        self._check(self._L.tloam_b200_batch_scan_match_async(self._b, _dp(p) if p is not None else None), "batch_scan_matching_async")
+
+    def get_results(self):
+        out = np.zeros((self.S, 16))
+        st = np.zeros(self.S, dtype=np.int32)
+        rc = self._L.tloam_b200_batch_get_results(self._b, _dp(out), st.ctypes.data_as(C.POINTER(C.c_int)), None)
+        self._check(rc, "batch_get_results")
+        return np.transpose(out.reshape(self.S, 4, 4), (0, 2, 1)).copy(), st
+
     def launch_count(self):
         return int(self._L.tloam_b200_batch_launch_count(self._b))
 

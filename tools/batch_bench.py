@@ -25,3 +25,11 @@ for S in [int(a) for a in sys.argv[1:]] or [8]:
     print(json.dumps({"S": S, "frames_per_s": S * 12 / (np.median(ms) * 1e-3), "ms_per_batch_frame": float(np.median(ms)) / 12,
                       "avg_us": prof, "lib": os.environ.get("TLOAM_B200_LIB", "default")}), flush=True)
     b.close()
+    for G in (2, 4):
+        if S % G:
+            continue
+        bs = [tloam_b200.BatchRegistration(S // G, **bench.CAPS) for _ in range(G)]
+        msg = [bench.run_batch_groups(bs, data, torch, 3, 12)[0] for _ in range(3)]
+        print(json.dumps({"S": S, "groups": G, "frames_per_s": S * 12 / (np.median(msg) * 1e-3)}), flush=True)
+        for b in bs:
+            b.close()
