@@ -502,8 +502,9 @@ def reference_arm(args, rank, world):
 def bench_config3(args, rank, world, local_rank):
     """BASELINE config 3 as a contract line: dense indoor scan, F = 500 032 features (planar + ground builders only,
     factor_num = 2) against M = 2 000 032 map points, room 20 x 30 x 4 m at ~0.03 m spacing, 1 x B200.  One step = one frame
-    = set_target (2M-point voxel-hash build) + set_source + scan_match.  The correspondence search takes the dense-map
-    path (queries binned by map cell, TMA-staged tiles, dense_search.cuh)."""
+    = set_target (2M-point voxel-hash build incl. the second level of the dense cells) + set_source + scan_match.  The
+    correspondence search takes the two-level grid (fine_search.cuh) unless TLOAM_B200_FINE=0 / TLOAM_B200_DENSE=1 say
+    otherwise."""
     import torch
     import tloam_b200
     from tloam_b200 import synth
@@ -559,16 +560,18 @@ def bench_config3(args, rank, world, local_rank):
     n_feat = [int(c.shape[0]) for c in f["scan"]]
     n_map = [int(c.shape[0]) for c in f["map"]]
     alg = algorithmic_bytes(n_feat, n_map)
-    alg["dense"] = alg["correspond"]
+    alg["dense"] = alg["fine"] = alg["correspond"]
     kern = {k: {"launches_per_frame": n / 3, "avg_us": 1e3 * ms / n, "ms_per_frame": ms / 3} for k, (n, ms) in prof.items() if n > 0}
-    dominant = max(("dense", "correspond", "eval", "eval_first"), key=lambda k: kern.get(k, {}).get("ms_per_frame", 0.0))
+    dominant = max(("fine", "dense", "correspond", "eval", "eval_first"), key=lambda k: kern.get(k, {}).get("ms_per_frame", 0.0))
     peak, peak_src = measured_peak_hbm()
     ach = alg[dominant] / (kern[dominant]["avg_us"] * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": {"dense": "k_correspond_dense", "correspond": "k_correspond", "eval": "k_eval<false>",
-                                           "eval_first": "k_eval<true>"}[dominant],
+    roofline = {"bound": "hbm", "kernel": {"fine": "k_correspond_fine", "dense": "k_correspond_dense", "correspond": "k_correspond",
+                                           "eval": "k_eval<false>", "eval_first": "k_eval<true>"}[dominant],
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dominant], "avg_launch_us": kern[dominant]["avg_us"], "kernels": kern,
-                "per_kernel_frac": {k: alg[k] / (kern[k]["avg_us"] * 1e-6) / 1e9 / peak for k in ("dense", "eval", "eval_first") if k in kern}}
+                "per_kernel_frac": {k: alg[k] / (kern[k]["avg_us"] * 1e-6) / 1e9 / peak for k in ("fine", "dense", "eval", "eval_first") if k in kern},
+                "search_path": os.environ.get("TLOAM_B200_DENSE", "0") == "1" and "TMA-staged tiles (dense_search.cuh)" or
+                               (os.environ.get("TLOAM_B200_FINE", "auto") == "0" and "lane-pair (map_grid.cuh)" or "two-level grid (fine_search.cuh)")}
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import pyoracle

@@ -243,7 +243,8 @@ enum {
   TLOAM_B200_K_MAP_BBOX = 0, TLOAM_B200_K_MAP_ORIGIN, TLOAM_B200_K_MAP_INSERT, TLOAM_B200_K_MAP_OFFSETS,
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
   TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_FIRST,
-  TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_GROUND, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_GROUND, TLOAM_B200_K_MAP_FINE,
+  TLOAM_B200_K_FINE, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];

@@ -131,7 +131,8 @@ def test_fused_first_evaluation_matches_the_unfused_kernels(oracle):
     for o in range(sf.n_outer):
         a, c = sf.outer[o], su.outer[o]
         assert list(a.n_factors) == list(c.n_factors)
-        assert np.allclose(np.array(a.H0), np.array(c.H0), rtol=1e-9, atol=1e-9)   # same factors, different summation tree
+        Ha, Hc = np.array(a.H0), np.array(c.H0)                                  # same factors, different summation tree:
+        assert np.abs(Ha - Hc).max() <= 1e-11 * np.abs(Hc).max()                  # small entries are sums of large cancelling terms
         assert a.n_inner == c.n_inner and a.termination == c.termination
     dt, dr = pose_err(Tf, Tu)
     assert dt < 1e-7 and dr < 1e-8, (dt, dr)

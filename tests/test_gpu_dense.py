@@ -32,11 +32,12 @@ def quantized(sc):
 def make_reg(dense, **cfg):
     import tloam_b200
     os.environ["TLOAM_B200_DENSE"] = "1" if dense else "0"
+    os.environ["TLOAM_B200_FINE"] = "0"              # the reference side of every comparison is the plain lane-pair search
     os.environ["TLOAM_B200_DENSE_CHECK"] = "1"       # every dense query is re-searched by the plain path on the device
     try:
         return tloam_b200.LocalRegistration(**cfg)
     finally:
-        for k in ("TLOAM_B200_DENSE", "TLOAM_B200_DENSE_CHECK"):
+        for k in ("TLOAM_B200_DENSE", "TLOAM_B200_DENSE_CHECK", "TLOAM_B200_FINE"):
             os.environ.pop(k, None)
 
 

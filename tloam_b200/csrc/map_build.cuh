@@ -16,6 +16,9 @@ struct MapBuildArgs {
   // device-resident point counts (sync-free submap chain): stage_off / i_end are then CAPACITY bounds known to the
   // host, and cloud c really holds *n_dev[c] points (nullptr = the bound is exact)
   const unsigned* n_dev[4];
+  // second level (map_grid.cuh: kFineMin): clouds of fine_mask get their dense cells ordered by fine bin (k_map_fine)
+  int fine_mask;
+  float4* fine_tmp;             // scratch [total]: k_map_fine reorders a cell out of place
 };
 
 // false for the slack between a cloud's device-side count and its host-side bound
@@ -160,6 +163,108 @@ __global__ void __launch_bounds__(256) k_map_offsets(MapBuildArgs a) {
   }
   __syncthreads();
   if (cnt > 0u) table[2u * s].z = s_base + s_w[warp] + (incl - cnt);
+  // second level: consecutive tables for the brick's dense sub-cells; the first 8 bytes of a table carry its cell
+  // (slot, sub-cell) to k_map_fine, which overwrites them with the bin boundaries
+  if (!((a.fine_mask >> c) & 1)) return;           // block-uniform
+  unsigned nd = 0u, dmask = 0u;
+  if (cnt >= kFineMin) {
+    const uint4 ea = table[2u * s], eb = table[2u * s + 1u];
+    const unsigned w[4] = {ea.w, eb.x, eb.y, eb.z};
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (((w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu) >= kFineMin) { ++nd; dmask |= 1u << q; }
+  }
+  if (__syncthreads_count(nd > 0u) == 0) return;
+  unsigned incl2 = nd;
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl2, o); if (lane >= o) incl2 += v; }
+  if (lane == 31) s_w[warp] = incl2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+    for (int wi = 0; wi < 8; ++wi) { const unsigned v = s_w[wi]; s_w[wi] = tot; tot += v; }
+    s_base = atomicAdd(&h->fine_cursor[c], tot);
+  }
+  __syncthreads();
+  if (nd > 0u) {
+    unsigned fi = s_base + s_w[warp] + (incl2 - nd);
+    table[2u * s + 1u].w = fi + 1u;
+    unsigned char* fine = a.blob + h->fine_off[c];
+    for (int q = 0; q < 8; ++q)
+      if ((dmask >> q) & 1u) {
+        uint2* tag = reinterpret_cast<uint2*>(fine + (size_t)fi * kFineEntryBytes);
+        *tag = make_uint2(s, (unsigned)q);
+        ++fi;
+      }
+  }
+}
+
+// Second level of the dense cells: one block per dense cell (grid-stride over the cloud's work list = its tables).
+// Pass A copies the cell to scratch and counts the fine bins, pass B writes the points back bin after bin and the
+// table of inclusive bin boundaries.  Bin of a point: floor(4 * frac(stored coordinate / cell)) per axis, FP64.
+__global__ void __launch_bounds__(128) k_map_fine(MapBuildArgs a) {
+  MapHeader* h = reinterpret_cast<MapHeader*>(a.blob);
+  if (h->build_flags & 1ull) return;
+  __shared__ unsigned s_cnt[kFineBins], s_cur[kFineBins];
+  for (int c = 0; c < 4; ++c) {
+    if (!((a.fine_mask >> c) & 1)) continue;
+    const unsigned ncell = h->fine_cursor[c];
+    if (ncell == 0u) continue;
+    uint4* table = reinterpret_cast<uint4*>(a.blob + h->table_off[c]);
+    float4* pts = reinterpret_cast<float4*>(a.blob + h->pts_off[c]);
+    float4* tmp = a.fine_tmp + a.stage_off[c];
+    unsigned char* fine = a.blob + h->fine_off[c];
+    const double inv = 1.0 / h->cell[c];
+    for (unsigned e = blockIdx.x; e < ncell; e += gridDim.x) {
+      unsigned short* ft = reinterpret_cast<unsigned short*>(fine + (size_t)e * kFineEntryBytes);
+      const uint2 tag = *reinterpret_cast<const uint2*>(ft);
+      const unsigned slot = tag.x;
+      const int sub = (int)tag.y;
+      const uint4 ea = table[2u * slot], eb = table[2u * slot + 1u];
+      const unsigned w[4] = {ea.w, eb.x, eb.y, eb.z};
+      unsigned beg = ea.z, cnt = 0u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned cq = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+        if (q < sub) beg += cq;
+        if (q == sub) cnt = cq;
+      }
+      // integer cell coordinates from the brick key (21-bit fields biased by 2^20) and the sub-cell bits
+      const unsigned long long key = ((unsigned long long)ea.y << 32) | ea.x;
+      const int gx = 2 * ((int)((key >> 42) & 0x1FFFFFu) - (1 << 20)) + (sub & 1);
+      const int gy = 2 * ((int)((key >> 21) & 0x1FFFFFu) - (1 << 20)) + ((sub >> 1) & 1);
+      const int gz = 2 * ((int)(key & 0x1FFFFFu) - (1 << 20)) + (sub >> 2);
+      __syncthreads();                               // previous cell done with s_cnt / s_cur / its tag
+      if (threadIdx.x < kFineBins) s_cnt[threadIdx.x] = 0u;
+      __syncthreads();
+      auto bin_of = [&](const float4 p) {
+        int bx = (int)(((double)p.x * inv - (double)gx) * (double)kFineDiv), by = (int)(((double)p.y * inv - (double)gy) * (double)kFineDiv),
+            bz = (int)(((double)p.z * inv - (double)gz) * (double)kFineDiv);
+        bx = bx < 0 ? 0 : (bx > kFineDiv - 1 ? kFineDiv - 1 : bx);
+        by = by < 0 ? 0 : (by > kFineDiv - 1 ? kFineDiv - 1 : by);
+        bz = bz < 0 ? 0 : (bz > kFineDiv - 1 ? kFineDiv - 1 : bz);
+        return (bz * kFineDiv + by) * kFineDiv + bx;
+      };
+      for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const float4 p = pts[beg + i];
+        tmp[beg + i] = p;
+        atomicAdd(&s_cnt[bin_of(p)], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {                        // inclusive scan of the 64 bins: 2 per lane
+        const unsigned c0 = s_cnt[2 * threadIdx.x], c1 = s_cnt[2 * threadIdx.x + 1];
+        unsigned incl = c0 + c1;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += v; }
+        const unsigned excl = incl - (c0 + c1);
+        s_cur[2 * threadIdx.x] = excl; s_cur[2 * threadIdx.x + 1] = excl + c0;
+        ft[2 * threadIdx.x] = (unsigned short)(excl + c0); ft[2 * threadIdx.x + 1] = (unsigned short)incl;
+      }
+      __syncthreads();
+      for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const float4 p = tmp[beg + i];
+        pts[beg + atomicAdd(&s_cur[bin_of(p)], 1u)] = p;
+      }
+    }
+  }
 }
 
 __global__ void k_map_scatter(MapBuildArgs a) {

@@ -26,6 +26,7 @@ struct GridDesc {
   unsigned n;
   double inv_cell;
   double cell;
+  const unsigned short* fine;   // [n / kFineMin + 1][64] second-level index of the dense cells (see knn_search_fine)
 };
 
 // 256-byte header at the start of the map blob (host + device visible layout)
@@ -42,8 +43,12 @@ struct MapHeader {
   unsigned bbox_ticket;            // blocks of k_map_bbox that have contributed (build scratch)
   unsigned pad32;
   unsigned nbricks[4];             // occupied bricks per cloud (k_map_offsets): points / bricks picks the search path
+  unsigned long long fine_off[4];  // byte offset of each cloud's second-level tables (64 x u16 per dense cell)
+  unsigned fine_cursor[4];         // dense cells per cloud (bump allocator of k_map_offsets, work list of k_map_fine)
+  unsigned fine_build;             // bit c: cloud c was built with the second level (k_map_fine ran)
+  unsigned pad2[3];
 };
-static_assert(sizeof(MapHeader) == 256, "MapHeader must be 256 bytes");
+static_assert(sizeof(MapHeader) == 320, "MapHeader must be 320 bytes");
 constexpr unsigned long long kMapMagic = 0x544C4F414D423230ull;  // "TLOAMB20"
 
 __host__ __device__ __forceinline__ unsigned long long cell_key(int cx, int cy, int cz) {
@@ -115,12 +120,21 @@ struct TopK {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Brick entry: uint4 A = {key.lo, key.hi, base, cnt01}, uint4 B = {cnt23, cnt45, cnt67, pad}; cntXY packs the
+// Brick entry: uint4 A = {key.lo, key.hi, base, cnt01}, uint4 B = {cnt23, cnt45, cnt67, fine}; cntXY packs the
 // u16 point counts of sub-cells X (low half) and Y (high half).  Sub-cell s = (cx&1) | (cy&1)<<1 | (cz&1)<<2,
-// the brick's points are stored sub-cell after sub-cell from `base`.
+// the brick's points are stored sub-cell after sub-cell from `base`.  fine = 0: no second level in this brick; else
+// (index of the second-level table of the brick's FIRST dense sub-cell) + 1 -- its dense sub-cells (count >= kFineMin)
+// own consecutive tables in sub-cell order.
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned kMaxCellPoints = 65535u;
 constexpr unsigned kBrickBytes = 32u;
+// Second level: a cell with >= kFineMin points has them ordered by a 4 x 4 x 4 grid of fine bins (edge = cell / 4);
+// its table holds the INCLUSIVE prefix sums of the 64 bin counts (bin = bx + 4 by + 16 bz), so bin i is
+// [i ? table[i-1] : 0, table[i]) relative to the first point of the cell.
+constexpr unsigned kFineMin = 64u;
+constexpr int kFineDiv = 4;
+constexpr int kFineBins = kFineDiv * kFineDiv * kFineDiv;
+constexpr unsigned kFineEntryBytes = kFineBins * 2u;
 
 __host__ __device__ __forceinline__ int brick_of(int c) { return c >> 1; }    // floor(c / 2), also for c < 0
 __host__ __device__ __forceinline__ int subcell_of(int cx, int cy, int cz) { return (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2); }

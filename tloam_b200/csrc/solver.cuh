@@ -174,6 +174,110 @@ __device__ __forceinline__ void gn_model(const double H[21], const double g[6], 
   m.ok = ok ? 1 : 0;
 }
 
+// The same model by ONE WARP (all 32 lanes call; lanes 0..5 own one column of the packed upper triangle each, every
+// lane returns the full result).  Every element goes through the same operations in the same order as in
+// ldlt_solve6_packed / gn_model (sums over k ascending, (L L) d, six reciprocals), so the result is bit-identical; what
+// changes is that the 15 off-diagonal eliminations of a column, and the column's products, run side by side instead of
+// one after the other -- the serial form was 4.9k cycles of mostly instruction fetch and dependent FP64 latency.
+__device__ __forceinline__ void gn_model_warp(const double* Hs /* shared: packed H[21] */, const double g[6], const double scale[6],
+                                              double mu_lm, GnModel& m) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int me = lane < 6 ? lane : 5;                       // lanes >= 6 shadow lane 5 (their results are never read)
+  double gs[6], d2[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    gs[i] = scale[i] * g[i];
+    d2[i] = fmin(fmax(scale[i] * Hs[tri(i, i)] * scale[i], 1e-6), 1e32);          // min/max_lm_diagonal of (S H S)_ii
+  }
+  // my column of S H S: entries (k, me), k <= me
+  double hcol[6], sme = scale[0];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { hcol[k] = Hs[tri(k < me ? k : me, me)]; if (k == me) sme = scale[k]; }
+  bool ok = false;
+  double y[6] = {0, 0, 0, 0, 0, 0};
+  while (mu_lm < 1.0) {                                         // kMaxMu
+    double col[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      col[k] = scale[k] * hcol[k] * sme;                        // A[tri(k, me)] = scale[k] * H[tri(k, me)] * scale[me]
+      if (k == me) col[k] += mu_lm * d2[k];
+    }
+    double d[6], dinv[6];
+    bool pos = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      double s = col[j];                                        // lane j: its diagonal entry
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (k < j) s -= col[k] * col[k] * d[k];
+      d[j] = __shfl_sync(full, s, j);
+      pos = pos && (d[j] > 0.0) && isfinite(d[j]);
+      dinv[j] = 1.0 / d[j];
+      double t = col[j];                                        // lanes i > j: entry (j, i)
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        if (k < j) {
+          const double ljk = __shfl_sync(full, col[k], j);      // entry (k, j) = L(j, k)
+          t -= col[k] * ljk * d[k];
+        }
+      if (me > j) col[j] = t * dinv[j];
+    }
+    if (pos) {
+      // forward substitution: step i takes lane i's value
+      double z[6];
+      double mygs = gs[0];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k == me) mygs = gs[k];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double t = mygs;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k < i) t -= col[k] * z[k];
+        z[i] = __shfl_sync(full, t, i);
+      }
+      // row me of the factor: entry (me, k), k > me, lives in lane k's column
+      double rowv[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        rowv[k] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          if (i < k) { const double v = __shfl_sync(full, col[i], k); if (i == me) rowv[k] = v; }
+      }
+      double myz = z[0], mydinv = dinv[0];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k == me) { myz = z[k]; mydinv = dinv[k]; }
+#pragma unroll
+      for (int ii = 0; ii < 6; ++ii) {
+        const int i = 5 - ii;
+        double t = myz * mydinv;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (k > i) t -= rowv[k] * y[k];
+        y[i] = __shfl_sync(full, t, i);
+      }
+      bool fin = true;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) fin = fin && isfinite(y[i]);
+      if (fin) { ok = true; break; }
+    }
+    mu_lm *= 10.0;                                              // mu_increase_factor_
+  }
+  double n2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    m.scale[i] = scale[i];
+    m.d2[i] = d2[i];
+    m.y[i] = ok ? y[i] : 0.0;
+    n2 += d2[i] * m.y[i] * m.y[i];
+  }
+  m.gn_norm = sqrt(n2);
+  m.mu_lm = mu_lm;
+  m.ok = ok ? 1 : 0;
+}
+
 // single out-of-line copies of the Lie-group routines (the solver is instruction-fetch bound: keep it small)
 #ifndef TLOAM_SOLVER_INLINE_LIE
 #define TLOAM_SOLVER_INLINE_LIE 0
@@ -415,6 +519,11 @@ struct SolverShared {
   GnModel model;
   double proj[6];      // Plus(x, -g) for the state that becomes current if this evaluation is accepted
   double cand[6];      // log(candidate pose)
+  // speculative first trip through advance() for the state that becomes current if this evaluation is accepted and
+  // the Gauss-Newton step of the fresh model fits the trust region: model cost change and next candidate pose
+  double spec_mcc;
+  Pose7 spec_cq;
+  int spec_ok, pad;
   FrameState backup;   // state before advance(), for the (practically never taken) gradient-tolerance exit
 };
 
@@ -431,8 +540,15 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 //   warp 3 : cand = log(candidate pose)                                    -> named barrier 1
 //   warp 1 : proj = Plus(x', -g') = log(exp(-g') * P')                     -> named barrier 2
 //            (x', P', g' = tangent, pose, gradient of the state that is current after an accepted step)
-//   warp 0 : Gauss-Newton model from the fresh H, g (speculative)  | wait 1 | accept / reject / tolerances |
-//            advance(): dogleg step + next candidate pose           | wait 2 | gradient-tolerance test
+//   warp 2 : Gauss-Newton model from the fresh H, g, then -- still in registers -- the first trip through advance()
+//            that follows an accepted evaluation in the common case (Gauss-Newton step inside the trust region):
+//            model cost change and next candidate pose exp(delta) * P'     -> named barrier 3
+//            (everything speculative: used iff the evaluation is accepted, same operations in the same order
+//            as advance(), so the results are bit-identical to the serial path)
+//   warp 0 : wait 1 | tolerance tests, accept / reject | wait 3 | install the model, take the speculative step or
+//            fall back to advance() (rejected step, dogleg, invalid step) | wait 2 | gradient-tolerance test
+// Measured before the split (thread 0 did model -> decision -> advance() in sequence): 14k cycles per active
+// evaluation = 3.5k model + 2.1k decision + 6.2k advance() + tail.
 // The gradient-tolerance test (|x' - proj|_inf <= 1e-10) comes BEFORE advance() in Ceres; it practically never
 // fires (it needs |g| ~ 1e-10), so advance() runs first on a backed-up state and is undone if it does fire.
 __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st, const double* tot, SolverShared* sh) {
@@ -470,24 +586,55 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
     bar_arrive(2, 64);
     return;
   }
+  if (warp == 2) {
+    double sc[6];
+    for (int i = 0; i < 6; ++i)
+      sc[i] = iter0 ? 1.0 / (1.0 + sqrt(tot[tri(i, i)])) : st->scale[i];            // jacobi scaling (iteration 0 only)
+    const double mu0 = iter0 ? 1e-8 : fmax(1e-8, 2.0 * st->mu_lm / 10.0);          // kMinMu / StepAccepted
+#ifndef TLOAM_SOLVER_WARP_MODEL
+#define TLOAM_SOLVER_WARP_MODEL 0    // 1: gn_model_warp (measured: 6.1k cycles vs 4.9k for the serial form -- more instructions)
+#endif
+    GnModel m;
+    if (TLOAM_SOLVER_WARP_MODEL) gn_model_warp(tot, g, sc, mu0, m);               // the whole warp
+    if (lane == 0) {
+      double H[21];
+      for (int i = 0; i < 21; ++i) H[i] = tot[i];
+      if (!TLOAM_SOLVER_WARP_MODEL) gn_model(H, g, sc, mu0, m);
+      sh->model = m;
+      if (ctx.dbg) ctx.dbg[6] += (unsigned long long)(clock64() - ta0);
+      int ok = 0;
+      if (m.ok) {
+        // advance() for "accepted, Gauss-Newton step inside the radius": step = -y, model cost change, Plus
+        double step[6], v[6], lin = 0.0, quad = 0.0;
+        for (int i = 0; i < 6; ++i) step[i] = -m.y[i];
+        for (int i = 0; i < 6; ++i) { v[i] = sc[i] * step[i]; lin += g[i] * v[i]; }
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) quad += v[i] * ((i <= j) ? H[tri(i, j)] : H[tri(j, i)]) * v[j];
+        sh->spec_mcc = -(lin + 0.5 * quad);
+        double delta[6];
+        for (int i = 0; i < 6; ++i) delta[i] = step[i] * sc[i];
+        Pose7 ed, cq;
+        s_exp(delta, &ed);
+        s_mul(&ed, &P, &cq);
+        sh->spec_cq = cq;
+        ok = 1;
+      }
+      sh->spec_ok = ok;
+      if (ctx.dbg) ctx.dbg[13] += (unsigned long long)(clock64() - ta0);
+    }
+    __syncwarp();
+    bar_arrive(3, 64);
+    return;
+  }
   if (warp != 0) return;
 
   // ------------------------------- warp 0 -------------------------------
-  if (lane == 0) {
-    double H[21], sc[6];
-    for (int i = 0; i < 21; ++i) H[i] = tot[i];
-    for (int i = 0; i < 6; ++i)
-      sc[i] = iter0 ? 1.0 / (1.0 + sqrt(H[tri(i, i)])) : st->scale[i];          // jacobi scaling (iteration 0 only)
-    const double mu0 = iter0 ? 1e-8 : fmax(1e-8, 2.0 * st->mu_lm / 10.0);        // kMinMu / StepAccepted
-    gn_model(H, g, sc, mu0, sh->model);
-    if (ctx.dbg) { ctx.dbg[6] += (unsigned long long)(clock64() - ta0); ctx.dbg[15] = (unsigned long long)clock64(); }
-  }
-  __syncwarp();
+  if (lane == 0 && ctx.dbg) ctx.dbg[15] = (unsigned long long)clock64();
   bar_sync(1, 64);                                                       // cand is ready
 
   // 0 = solve ended, 1 = go on with advance() and then the deferred gradient-tolerance test,
   // 2 = go on with advance(), no gradient test (step rejected)
-  int go = 0, copy_hg = 0, trace_h0 = 0;
+  int go = 0, copy_hg = 0, trace_h0 = 0, take_scale = 0, take_model = 0;
   if (lane == 0) {
     const double cost = tot[27];
     for (int k = 0; k < 4; ++k) st->slot_sum[k] = tot[28 + k];
@@ -507,16 +654,15 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
       }
       st->x_cost = cost;
       copy_hg = 1;                                                       // H, g <- tot (done by the whole warp below)
-      for (int i = 0; i < 6; ++i) st->scale[i] = sh->model.scale[i];
       if (ot) ot->initial_cost = cost;
       trace_h0 = ot != nullptr;
       st->mu_lm = 1e-8; st->reuse = 0; st->model_ok = 0;
       if (nf_total == 0) {
+        take_scale = 1;                                                  // the scaling is part of the state either way
         end_of_solve(io, 5);                                             // no residual blocks
       } else {
         st->x_norm = norm6(st->x);
-        install_model(st, sh->model);
-        st->model_ok = sh->model.ok; st->reuse = 1;
+        take_scale = 1; take_model = 1;                                  // after barrier 3 (the model is warp 2's)
         go = 1;
       }
     } else {
@@ -549,8 +695,7 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
           if (rel > 0.75) st->radius = fmax(st->radius, 3.0 * st->step_norm);
           st->last_cand_valid = 0;
           if (it) it->accepted = 1;
-          install_model(st, sh->model);                                  // speculative model becomes current
-          st->model_ok = sh->model.ok; st->reuse = 1;
+          take_model = 1;                                                // speculative model becomes current (after barrier 3)
           go = 1;
         } else {
           st->radius *= 0.5; st->reuse = 1;                              // StepRejected
@@ -568,6 +713,8 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
   go = __shfl_sync(0xffffffffu, go, 0);
   copy_hg = __shfl_sync(0xffffffffu, copy_hg, 0);
   trace_h0 = __shfl_sync(0xffffffffu, trace_h0, 0);
+  take_scale = __shfl_sync(0xffffffffu, take_scale, 0);
+  take_model = __shfl_sync(0xffffffffu, take_model, 0);
   if (copy_hg) {                                                         // lane-parallel: H (21) + g (6) <- tot
     if (lane < 27) { if (lane < 21) st->H[lane] = tot[lane]; else st->g[lane - 21] = tot[lane]; }
     __syncwarp();
@@ -578,16 +725,49 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
     if (lane < 6) { ot->x_start[lane] = st->x[lane]; ot->g0[lane] = tot[21 + lane]; }
     __syncwarp();
   }
-  if (go == 1) {                                                         // back up the state (warp-wide copy)
+  if (go == 1) {
+    // back up the state (warp-wide copy) while warp 2 is still busy: everything the deferred gradient-tolerance exit
+    // needs (x, cost, radius, GNC bookkeeping) is final here; the Gauss-Newton model installed below is not part of it
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sh->backup);
     for (unsigned i = lane; i < sizeof(FrameState) / 8; i += 32) dst[i] = src[i];
     __syncwarp();
   }
+  bar_sync(3, 64);                                                       // model + speculative step are ready
+  if (take_scale && lane < 6) st->scale[lane] = sh->model.scale[lane];
+  if (take_model) {                                                      // install_model(), one lane per entry
+    if (lane < 6) { st->d2[lane] = sh->model.d2[lane]; st->y[lane] = sh->model.y[lane]; }
+    if (lane == 6) { st->gn_norm = sh->model.gn_norm; st->mu_lm = sh->model.mu_lm; }
+    if (lane == 7) { st->sub_valid = 0; st->model_ok = sh->model.ok; st->reuse = 1; }
+  }
+  __syncwarp();
   if (lane == 0 && go != 0) {
     // after an accepted step Ceres tests the radius AFTER the gradient tolerance; the gradient test is deferred
     // (below), so the radius test of the accepted branch is applied there as well
-    if (go == 2 || st->radius > 1e-32) advance(io);
+    if (go == 2 || st->radius > 1e-32) {
+      // the speculative step IS advance()'s first trip when: accepted (reuse = 1, no rejected candidate on record),
+      // iterations left, model solved, Gauss-Newton step inside the (updated) radius, valid step
+#ifndef TLOAM_SOLVER_NO_SPEC
+#define TLOAM_SOLVER_NO_SPEC 0       // 1: always take the serial advance() (A/B and bit-identity check of the speculative step)
+#endif
+      if (!TLOAM_SOLVER_NO_SPEC && go == 1 && st->iter < ctx.ceres_max_it && sh->spec_ok && st->model_ok && st->gn_norm <= st->radius &&
+          sh->spec_mcc > 0.0) {
+        st->iter += 1;
+        st->step_norm = st->gn_norm; st->used_gn = 1;
+        st->model_cost_change = sh->spec_mcc;
+        tloam_b200_inner_trace* it = inner_trace(io);
+        if (it) {
+          it->radius = st->radius; it->step_norm_scaled = st->step_norm; it->used_gauss_newton = 1;
+          it->model_cost_change = sh->spec_mcc; it->accepted = 0; it->relative_decrease = 0.0; it->candidate_cost = 0.0;
+        }
+        st->num_invalid = 0;
+        st->candq = sh->spec_cq;
+        st->evalq = sh->spec_cq;
+        st->phase = kPhaseCand;
+      } else {
+        advance(io);
+      }
+    }
     TL_STAMP(io, 12);
   }
   __syncwarp();

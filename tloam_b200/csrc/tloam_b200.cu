@@ -15,6 +15,7 @@
 #include "map_build.cuh"
 #include "frame_kernels.cuh"
 #include "dense_search.cuh"
+#include "fine_search.cuh"
 #include "submap.cuh"
 #include "feature_extract.cuh"
 #include "ground_extract.cuh"
@@ -124,6 +125,12 @@ struct tloam_b200_handle {
   cudaEvent_t ev_stats = nullptr;          bool stats_pending = false, stats_known = false;
   unsigned nbricks[4] = {0, 0, 0, 0};
   int dense_mode = 0;                      // TLOAM_B200_DENSE: "auto" -> -1 (points per brick), unset -> 0 never, "1" always
+  // two-level grid (fine_search.cuh): TLOAM_B200_FINE unset / "auto" -> -1 (by the density of the previous map),
+  // "0" never, "1" always.  map_fine_mask: clouds of the ACTIVE map that were built with the second level
+  int dense_kernel = 0, gdense_kernel = 0; // which kernel serves ctx.dense_mask: 1 = TMA-staged (dense_search.cuh), 2 = two-level grid
+  int fine_mode = -1;
+  int map_fine_mask = 0;
+  float4* d_fine_tmp = nullptr;            size_t cap_fine_tmp = 0;
   bool dense_attr_set = false;
   bool dense_check = false;                // TLOAM_B200_DENSE_CHECK=1: every dense query is re-searched by the plain path and compared
   int num_sms = 148;
@@ -243,6 +250,7 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   // points-per-brick statistics of the map.  Measured on config 3 it is still SLOWER than the lane-pair search (4.1 vs
   // 3.0 ms per launch): correct and TMA-staged, not yet a win.
   { const char* e = getenv("TLOAM_B200_DENSE"); h->dense_mode = 0; if (e && e[0] == '1') h->dense_mode = 1; else if (e && e[0] == 'a') h->dense_mode = -1; }
+  { const char* e = getenv("TLOAM_B200_FINE"); h->fine_mode = -1; if (e && e[0] == '1') h->fine_mode = 1; else if (e && e[0] == '0') h->fine_mode = 0; }
   if (cudaMallocHost(&h->h_mapstats, 4 * sizeof(unsigned)) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_stats, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->num_sms = v; }
@@ -287,6 +295,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->h_mapstats) cudaFreeHost(h->h_mapstats);
   if (h->ev_stats) cudaEventDestroy(h->ev_stats);
   cudaFree(h->d_dense);
+  cudaFree(h->d_fine_tmp);
   cudaFree(h->d_predict);
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -413,6 +422,8 @@ static size_t layout_header(const tloam_tls_config& cfg, const size_t n[4], MapH
     hd.cell[c] = radius_of(cfg, c);
     hd.pts_off[c] = off; off += round_up(n[c] * sizeof(float4), 256);
   }
+  // second-level tables: at most n / kFineMin dense cells per cloud (written by the build, never zeroed)
+  for (int c = 0; c < 4; ++c) { hd.fine_off[c] = off; off += round_up((n[c] / kFineMin + 1) * (size_t)kFineEntryBytes, 256); }
   for (int c = 0; c < 4; ++c) { hd.table_off[c] = off; off += (size_t)hd.tsize[c] * kBrickBytes; }
   for (int d = 0; d < 3; ++d) { hd.bbox_enc[d] = ~0ull; hd.bbox_enc[3 + d] = 0ull; }
   return off;
@@ -438,6 +449,7 @@ static void bind_map(tloam_b200_handle* h) {
     c.grid[k].n = h->hdr.n[k];
     c.grid[k].cell = h->hdr.cell[k];
     c.grid[k].inv_cell = 1.0 / h->hdr.cell[k];
+    c.grid[k].fine = reinterpret_cast<const unsigned short*>(h->d_blob + h->hdr.fine_off[k]);
   }
   c.origin = reinterpret_cast<const double*>(h->d_blob + offsetof(MapHeader, origin));
   c.map_flags = reinterpret_cast<const unsigned long long*>(h->d_blob + offsetof(MapHeader, build_flags));
@@ -458,6 +470,30 @@ static int fetch_origin(tloam_b200_handle* h) {
     h->origin_known = true;
   }
   return (h->hdr.build_flags & 1ull) ? TLOAM_B200_ERR_MAP_DENSITY : TLOAM_B200_OK;
+}
+
+static void harvest_map_stats(tloam_b200_handle* h, bool wait);
+
+// Which clouds of the map about to be built get the second level (map_grid.cuh: kFineMin, fine_search.cuh).  The
+// build kernel itself finds the dense cells; this only decides whether it is launched at all, so that sparse maps
+// (BASELINE config 2: 8-25 points per occupied brick) do not pay for an empty launch.  Either choice leaves every
+// search path exact.
+constexpr double kFinePointsPerBrick = 256.0;    // config 2 maps: 8-25; config 3: ~1700
+constexpr size_t kFineFirstMapPoints = 65536;     // no statistics yet (first map of a handle): big clouds only
+static int fine_build_mask(tloam_b200_handle* h, const size_t n[4]) {
+  if (h->fine_mode == 0) return 0;
+  harvest_map_stats(h, false);
+  int mask = 0;
+  for (int c = 0; c < 4; ++c) {
+    if (n[c] < kFineMin) continue;
+    bool on = h->fine_mode == 1;
+    if (!on) {
+      if (h->stats_known) on = h->nbricks[c] > 0 && (double)h->n_tgt[c] / (double)h->nbricks[c] >= kFinePointsPerBrick;   // previous map
+      else on = n[c] >= kFineFirstMapPoints;
+    }
+    if (on) mask |= 1 << c;
+  }
+  return mask;
 }
 
 static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], const size_t n[4], bool on_device,
@@ -483,9 +519,18 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     CU_TRY(cudaMalloc(&h->d_stage_tgt, ncap * 3 * sizeof(double)));
     h->cap_stage_tgt = ncap;
   }
+  const int fine_mask = fine_build_mask(h, n);
+  if (fine_mask && total > h->cap_fine_tmp) {
+    cudaFree(h->d_fine_tmp); h->d_fine_tmp = nullptr; h->cap_fine_tmp = 0;
+    const size_t ncap = total + total / 4 + 1024;
+    CU_TRY(cudaMalloc(&h->d_fine_tmp, ncap * sizeof(float4)));
+    h->cap_fine_tmp = ncap;
+  }
   int rc = layout_map(h, n);
   if (rc != TLOAM_B200_OK) return rc;
+  h->hdr.fine_build = (unsigned)fine_mask;
   MapBuildArgs a;
+  a.fine_mask = fine_mask; a.fine_tmp = h->d_fine_tmp;
   a.blob = h->d_blob; a.slot_of = h->d_scratch; a.rank_of = h->d_scratch + h->cap_scratch;
   a.only_cloud = -1;
   for (int c = 0; c < 4; ++c) a.n_dev[c] = n_dev ? n_dev[c] : nullptr;
@@ -522,6 +567,7 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     TL_LAUNCH(TLOAM_B200_K_MAP_INSERT, (k_map_insert<<<gb, tb, 0, h->stream>>>(a)));
     TL_LAUNCH(TLOAM_B200_K_MAP_OFFSETS, (k_map_offsets<<<(tslots + tb - 1) / tb, tb, 0, h->stream>>>(a)));
     TL_LAUNCH(TLOAM_B200_K_MAP_SCATTER, (k_map_scatter<<<gb, tb, 0, h->stream>>>(a)));
+    if (fine_mask) TL_LAUNCH(TLOAM_B200_K_MAP_FINE, (k_map_fine<<<4 * h->num_sms, 128, 0, h->stream>>>(a)));
     CU_TRY(cudaGetLastError());
   } else {
     // host inputs: the clouds cross PCIe one after the other on a copy stream; cloud c is inserted, offset and
@@ -550,10 +596,15 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
       TL_LAUNCH(TLOAM_B200_K_MAP_INSERT, (k_map_insert<<<gb, tb, 0, h->stream>>>(ac)));
       TL_LAUNCH(TLOAM_B200_K_MAP_OFFSETS, (k_map_offsets<<<(h->hdr.tsize[c] + tb - 1) / tb, tb, 0, h->stream>>>(ac)));
       TL_LAUNCH(TLOAM_B200_K_MAP_SCATTER, (k_map_scatter<<<gb, tb, 0, h->stream>>>(ac)));
+      if ((fine_mask >> c) & 1) {
+        ac.fine_mask = 1 << c;
+        TL_LAUNCH(TLOAM_B200_K_MAP_FINE, (k_map_fine<<<4 * h->num_sms, 128, 0, h->stream>>>(ac)));
+      }
     }
     CU_TRY(cudaGetLastError());
   }
   bind_map(h);
+  h->map_fine_mask = fine_mask;
   h->origin_known = false;
   h->have_tgt = true;
   // occupied bricks per cloud pick the search path (points per brick).  They come home with every frame's result
@@ -628,6 +679,7 @@ int tloam_b200_map_import(tloam_b200_handle* h, const void* d_src, size_t bytes)
   h->origin_known = true;
   h->have_tgt = true;
   for (int c = 0; c < 4; ++c) h->nbricks[c] = hd.nbricks[c];
+  h->map_fine_mask = (int)hd.fine_build;
   h->stats_known = true; h->stats_pending = false;
   CU_TRY(cudaStreamSynchronize(h->stream));
   return TLOAM_B200_OK;
@@ -687,6 +739,7 @@ int tloam_b200_map_adopt(tloam_b200_handle* h, void* producer_stream) {
   for (int c = 0; c < 4; ++c) { h->n_tgt[c] = h->hdr.n[c]; h->ctx.tgt_cnt[c] = nullptr; }
   fill_ctx_config(h);
   bind_map(h);
+  h->map_fine_mask = 0xF;                  // unknown without reading the header: bricks without a second level say so themselves
   h->origin_known = false;                 // lives in the received header on the device; fetched lazily if ever asked for
   h->stats_pending = false;                // occupied-brick statistics stay those of the previous map
   h->have_tgt = true;
@@ -739,8 +792,28 @@ static void harvest_counts(tloam_b200_handle* h) {
 constexpr double kDensePointsPerBrick = 256.0;   // config 2 maps: 8-25; config 3: ~1700
 constexpr size_t kDenseMinQueries = 2048;
 
+// clouds served by the two-level search (k_correspond_fine): built with the second level and dense (or not yet known)
+static int fine_mask_of(tloam_b200_handle* h) {
+  if (h->fine_mode == 0 || h->map_fine_mask == 0) return 0;
+  harvest_map_stats(h, false);
+  int mask = 0;
+  for (int c = 0; c < 4; ++c) {
+    const bool enabled = (c == kPlanar || c == kGround) ? true : (c == kEdge ? h->cfg.factor_num >= 3 : h->cfg.factor_num == 4);
+    if (!enabled || h->n_src[c] == 0 || h->n_tgt[c] == 0 || !((h->map_fine_mask >> c) & 1)) continue;
+    const bool dense = !h->stats_known || (h->nbricks[c] > 0 && (double)h->n_tgt[c] / (double)h->nbricks[c] >= kFinePointsPerBrick);
+    if (h->fine_mode == 1 || dense) mask |= 1 << c;
+  }
+  return mask;
+}
+
 static int dense_mask_of(tloam_b200_handle* h) {
-  if (h->dense_mode == 0) return 0;
+  h->dense_kernel = 0;
+  if (h->dense_mode == 0) {
+    const int fm = fine_mask_of(h);
+    if (fm) h->dense_kernel = 2;
+    return fm;
+  }
+  h->dense_kernel = 1;
   harvest_map_stats(h, !h->stats_known);         // the very first map of a handle: wait once for its statistics
   int mask = 0;
   for (int c = 0; c < 4; ++c) {
@@ -823,7 +896,10 @@ static BatchTab no_batch() { BatchTab t; memset(&t, 0, sizeof(t)); t.S = 1; retu
 // correspondence search + fit of one outer iteration as kernels of their own (un-fused sequence, build_factors)
 static int enqueue_correspond(tloam_b200_handle* h, const DeviceCtx& c) {
   const int nb = h->total_blocks;
-  if (c.dense_mask) {
+  if (c.dense_mask && h->dense_kernel == 2) {
+    // dense map clouds: two-level grid, one thread per feature (fine_search.cuh)
+    TL_LAUNCH(TLOAM_B200_K_FINE, (k_correspond_fine<false><<<nb, kBlk, kFineSmemBytes, h->stream>>>(c, no_batch(), h->dense_check ? h->d_cnt + 16 : nullptr)));
+  } else if (c.dense_mask) {
     // dense map clouds: bin the queries by map cell, then the TMA-staged block-per-cell search (dense_search.cuh)
     const DenseArgs& da = h->dargs;
     CU_TRY(cudaMemsetAsync(h->d_dense, 0, h->dense_zero_bytes, h->stream));
@@ -908,15 +984,16 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
   DeviceCtx c = h->ctx;
   if (!h->trace) c.stats = nullptr;             // skip the per-iteration trace (fewer instructions in the serial solver)
   c.dense_mask = dense_mask_of(h);
-  if (c.dense_mask) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
+  if (c.dense_mask && h->dense_kernel == 1) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
   const bool fused = h->use_fused && caps_cannot_bind(h) && c.dense_mask == 0;
-  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + (c.dense_mask ? 4 : 0) + h->cfg.ceres_max_num_iterations) +
+  const int per_frame = 1 + h->cfg.max_iterations * ((fused ? 1 : 2) + (c.dense_mask ? (h->dense_kernel == 1 ? 4 : 1) : 0) + h->cfg.ceres_max_num_iterations) +
                         (h->frame_fitness ? 2 : 0);
   CU_TRY(cudaEventRecord(h->ev0, h->stream));
   if (h->use_graph && !h->profiling) {
     // one graph launch per frame; the graph is re-captured only when the device context changed
     if (!h->gvalid || h->gfused != fused || h->gfitness != h->frame_fitness || memcmp(&h->gctx, &c, sizeof(DeviceCtx)) != 0 ||
-        (c.dense_mask && memcmp(&h->gdargs, &h->dargs, sizeof(DenseArgs)) != 0)) {
+        h->gdense_kernel != h->dense_kernel ||
+        (c.dense_mask && h->dense_kernel == 1 && memcmp(&h->gdargs, &h->dargs, sizeof(DenseArgs)) != 0)) {
       h->gvalid = false;
       cudaGraph_t graph = nullptr;
       CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -933,7 +1010,8 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       // same topology, new kernel parameters / grid sizes (cloud sizes change from frame to frame in a real
       // stream): update the instantiated graph in place, which is much cheaper than instantiating a new one
       bool updated = false;
-      if (h->gexec && h->gfused == fused && h->gfitness == h->frame_fitness && h->gctx.dense_mask == c.dense_mask) {
+      if (h->gexec && h->gfused == fused && h->gfitness == h->frame_fitness && h->gctx.dense_mask == c.dense_mask &&
+          h->gdense_kernel == h->dense_kernel) {
         cudaGraphExecUpdateResultInfo info;
         updated = cudaGraphExecUpdate(h->gexec, graph, &info) == cudaSuccess;
         if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
@@ -943,6 +1021,7 @@ static int scan_match_enqueue(tloam_b200_handle* h, const double* predict) {
       if (ce != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
       h->gctx = c;
       h->gdargs = h->dargs;
+      h->gdense_kernel = h->dense_kernel;
       h->gfused = fused;
       h->gfitness = h->frame_fitness;
       h->gvalid = true;
@@ -1106,7 +1185,8 @@ struct tloam_b200_batch {
   cudaEvent_t ev_done = nullptr, ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_ready;
   cudaGraphExec_t gexec = nullptr;
-  BatchTab g_first, g_corr, g_eval; bool gfused = false, gvalid = false;
+  BatchTab g_first, g_corr, g_eval, g_fine; bool gfused = false, gvalid = false;
+  bool any_fine = false, gany_fine = false;          // some sequence has clouds served by the two-level search
   bool use_graph = true, use_fused = false, pending = false;
   long long launches = 0; int launches_frame = 0;
   char last_error[512] = {0};
@@ -1233,6 +1313,7 @@ static int batch_enqueue_frame(tloam_b200_batch* b, bool fused, const tloam_tls_
     if (fused) {
       TLB_LAUNCH(TLOAM_B200_K_FIRST, (k_first<true><<<b->g_first.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_first)));
     } else {
+      if (b->any_fine) TLB_LAUNCH(TLOAM_B200_K_FINE, (k_correspond_fine<true><<<b->g_fine.off[S], kBlk, kFineSmemBytes, b->stream>>>(zero_ctx, b->g_fine, nullptr)));
       TLB_LAUNCH(TLOAM_B200_K_CORRESPOND, (k_correspond<true><<<b->g_corr.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_corr)));
       TLB_LAUNCH(TLOAM_B200_K_EVAL_FIRST, (k_eval<true, true><<<b->g_eval.off[S], kBlk, 0, b->stream>>>(zero_ctx, b->g_eval)));
     }
@@ -1258,18 +1339,22 @@ int tloam_b200_batch_scan_match_async(tloam_b200_batch* b, const double* predict
   const tloam_tls_config& cfg = b->hs[0]->cfg;
   // the frame kernels run behind everything the sequences have enqueued on their own streams (map build, staging)
   std::vector<DeviceCtx> ctxs(S);
-  BatchTab tf, tc, te;
-  memset(&tf, 0, sizeof(tf)); memset(&tc, 0, sizeof(tc)); memset(&te, 0, sizeof(te));
-  tf.S = tc.S = te.S = S; tf.ctxs = tc.ctxs = te.ctxs = b->d_ctxs;
+  BatchTab tf, tc, te, tq;
+  memset(&tf, 0, sizeof(tf)); memset(&tc, 0, sizeof(tc)); memset(&te, 0, sizeof(te)); memset(&tq, 0, sizeof(tq));
+  tf.S = tc.S = te.S = tq.S = S; tf.ctxs = tc.ctxs = te.ctxs = tq.ctxs = b->d_ctxs;
   bool fused = b->use_fused;
+  bool any_fine = false;
   for (int s = 0; s < S; ++s) {
     tloam_b200_handle* h = b->hs[s];
     CUB_TRY(cudaEventRecord(b->ev_ready[s], h->stream));
     CUB_TRY(cudaStreamWaitEvent(b->stream, b->ev_ready[s], 0));
     ctxs[s] = h->ctx;
     ctxs[s].stats = nullptr; ctxs[s].dbg = nullptr;
+    ctxs[s].dense_mask = fine_mask_of(h);            // dense map clouds: two-level search (the TMA-staged path is single-sequence only)
+    any_fine = any_fine || ctxs[s].dense_mask != 0;
     fused = fused && caps_cannot_bind(h);
     const int nb = h->total_blocks;
+    tq.off[s + 1] = tq.off[s] + nb;
     tf.off[s + 1] = tf.off[s] + first_grid_of(nb);
     tc.off[s + 1] = tc.off[s] + 2 * nb;
     te.off[s + 1] = te.off[s] + eval_grid_of(nb);
@@ -1280,14 +1365,16 @@ int tloam_b200_batch_scan_match_async(tloam_b200_batch* b, const double* predict
     CUB_TRY(cudaMemcpyAsync(b->d_ctxs, ctxs.data(), S * sizeof(DeviceCtx), cudaMemcpyHostToDevice, b->stream));   // pageable source: staged before return
     b->ctx_sent = ctxs; b->ctx_valid = true;
   }
-  const int per_frame = 1 + cfg.max_iterations * ((fused ? 1 : 2) + cfg.ceres_max_num_iterations);
+  if (any_fine) fused = false;
+  b->any_fine = any_fine;
+  const int per_frame = 1 + cfg.max_iterations * ((fused ? 1 : 2) + (any_fine ? 1 : 0) + cfg.ceres_max_num_iterations);
   CUB_TRY(cudaEventRecord(b->ev0, b->stream));
   if (b->use_graph && !b->profiling) {
-    const bool same = b->gvalid && b->gfused == fused && memcmp(&b->g_first, &tf, sizeof(tf)) == 0 &&
+    const bool same = b->gvalid && b->gfused == fused && b->gany_fine == any_fine && memcmp(&b->g_first, &tf, sizeof(tf)) == 0 &&
                       memcmp(&b->g_corr, &tc, sizeof(tc)) == 0 && memcmp(&b->g_eval, &te, sizeof(te)) == 0;
     if (!same) {
       b->gvalid = false;
-      b->g_first = tf; b->g_corr = tc; b->g_eval = te;
+      b->g_first = tf; b->g_corr = tc; b->g_eval = te; b->g_fine = tq;
       cudaGraph_t graph = nullptr;
       CUB_TRY(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
       const int erc = batch_enqueue_frame(b, fused, cfg);
@@ -1299,7 +1386,7 @@ int tloam_b200_batch_scan_match_async(tloam_b200_batch* b, const double* predict
         return TLOAM_B200_ERR_CUDA;
       }
       bool updated = false;
-      if (b->gexec && b->gfused == fused) {
+      if (b->gexec && b->gfused == fused && b->gany_fine == any_fine) {
         cudaGraphExecUpdateResultInfo info;
         updated = cudaGraphExecUpdate(b->gexec, graph, &info) == cudaSuccess;
         if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(b->gexec); b->gexec = nullptr; }
@@ -1307,11 +1394,11 @@ int tloam_b200_batch_scan_match_async(tloam_b200_batch* b, const double* predict
       if (!updated) ce = cudaGraphInstantiate(&b->gexec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) { snprintf(b->last_error, sizeof(b->last_error), "graph instantiate: %s", cudaGetErrorString(ce)); return TLOAM_B200_ERR_CUDA; }
-      b->gfused = fused; b->gvalid = true;
+      b->gfused = fused; b->gany_fine = any_fine; b->gvalid = true;
     }
     CUB_TRY(cudaGraphLaunch(b->gexec, b->stream));
   } else {
-    b->g_first = tf; b->g_corr = tc; b->g_eval = te;
+    b->g_first = tf; b->g_corr = tc; b->g_eval = te; b->g_fine = tq;
     const int erc = batch_enqueue_frame(b, fused, cfg);
     if (erc != TLOAM_B200_OK) return erc;
   }
@@ -1473,7 +1560,7 @@ int tloam_b200_build_factors(tloam_b200_handle* h, int cloud, const double x[6],
   DeviceCtx c = h->ctx;
   c.factor_num = 4;   // build every cloud regardless of the configured subset
   c.dense_mask = dense_mask_of(h);
-  if (c.dense_mask) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
+  if (c.dense_mask && h->dense_kernel == 1) { const int drc = prepare_dense(h, c.dense_mask); if (drc != TLOAM_B200_OK) return drc; }
   k_set_pose<<<1, 256, 0, h->stream>>>(c, pr);
   { const int crc = enqueue_correspond(h, c); if (crc != TLOAM_B200_OK) return crc; }
   k_caps<<<h->total_blocks, kBlk, 0, h->stream>>>(c);
@@ -1723,6 +1810,7 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   MapBuildArgs ma;
   ma.blob = A.blob; ma.slot_of = A.scratch; ma.rank_of = A.scratch + n;
   ma.i_beg = 0; ma.i_end = (unsigned)n; ma.only_cloud = -1;
+  ma.fine_mask = 0; ma.fine_tmp = nullptr;
   for (int c = 0; c < 4; ++c) ma.n_dev[c] = nullptr;
   for (int c = 0; c < 4; ++c) ma.src[c] = A.stage;
   ma.stage_off[0] = 0;
