@@ -89,6 +89,52 @@ __device__ __forceinline__ bool ldlt_solve6_packed(double a[21], const double b[
   return fin;
 }
 
+// The same factorisation with ROLLED loops on arrays in shared memory (w: 21 + 4 * 6 doubles of scratch).  Same
+// operations in the same order (bit-identical); ~10x fewer static instructions.  Built to test whether the unrolled form
+// is bound by instruction fetch (the solver runs once per launch on one SM with a cold instruction cache): it is not --
+// measured 11.3k cycles against 5.0k, every operand pays the shared-memory latency.  Kept for A/B only
+// (TLOAM_SOLVER_ROLLED_MODEL).
+__device__ __noinline__ bool ldlt_solve6_rolled(double* a, const double* b, double* yout, double* w) {
+  double* d = w; double* dinv = w + 6; double* z = w + 12;
+  bool ok = true;
+#pragma unroll 1
+  for (int j = 0; j < 6; ++j) {
+    double s = a[tri(j, j)];
+#pragma unroll 1
+    for (int k = 0; k < j; ++k) s -= a[tri(k, j)] * a[tri(k, j)] * d[k];
+    d[j] = s;
+    ok = ok && (s > 0.0) && isfinite(s);
+    const double di = 1.0 / s;
+    dinv[j] = di;
+#pragma unroll 1
+    for (int i = j + 1; i < 6; ++i) {
+      double t = a[tri(j, i)];
+#pragma unroll 1
+      for (int k = 0; k < j; ++k) t -= a[tri(k, i)] * a[tri(k, j)] * d[k];
+      a[tri(j, i)] = t * di;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll 1
+  for (int i = 0; i < 6; ++i) {
+    double t = b[i];
+#pragma unroll 1
+    for (int k = 0; k < i; ++k) t -= a[tri(k, i)] * z[k];
+    z[i] = t;
+  }
+  bool fin = true;
+#pragma unroll 1
+  for (int ii = 0; ii < 6; ++ii) {
+    const int i = 5 - ii;
+    double t = z[i] * dinv[i];
+#pragma unroll 1
+    for (int k = i + 1; k < 6; ++k) t -= a[tri(i, k)] * yout[k];
+    yout[i] = t;
+    fin = fin && isfinite(t);
+  }
+  return fin;
+}
+
 // minimise 0.5 y^T B y + g^T y on |y| = radius (2-D): the boundary problem of the subspace dogleg
 // (dogleg_strategy.cc FindMinimumOnTrustRegionBoundary). Angular bracketing + bisection on f'.
 __device__ __noinline__ void min_on_boundary_2d(const double B[4], const double g[2], double radius, double y[2]) {
@@ -159,6 +205,41 @@ __device__ __forceinline__ void gn_model(const double H[21], const double g[6], 
 #pragma unroll
     for (int i = 0; i < 6; ++i) A[tri(i, i)] += mu_lm * d2[i];
     if (ldlt_solve6_packed(A, gs, y)) { ok = true; break; }
+    mu_lm *= 10.0;                                              // mu_increase_factor_
+  }
+  double n2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    m.scale[i] = scale[i];
+    m.d2[i] = d2[i];
+    m.y[i] = ok ? y[i] : 0.0;
+    n2 += d2[i] * m.y[i] * m.y[i];
+  }
+  m.gn_norm = sqrt(n2);
+  m.mu_lm = mu_lm;
+  m.ok = ok ? 1 : 0;
+}
+
+// gn_model with the rolled factorisation; ws: 21 + 6 + 6 + 18 doubles of shared-memory scratch
+__device__ __forceinline__ void gn_model_rolled(const double H[21], const double g[6], const double scale[6], double mu_lm,
+                                                GnModel& m, double* ws) {
+  double* A = ws; double* gs = ws + 21; double* y = ws + 27; double* w = ws + 33;
+  double d2[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    gs[i] = scale[i] * g[i];
+    d2[i] = fmin(fmax(scale[i] * H[tri(i, i)] * scale[i], 1e-6), 1e32);          // min/max_lm_diagonal of (S H S)_ii
+    y[i] = 0.0;
+  }
+  bool ok = false;
+  while (mu_lm < 1.0) {                                         // kMaxMu
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) A[tri(i, j)] = scale[i] * H[tri(i, j)] * scale[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[tri(i, i)] += mu_lm * d2[i];
+    if (ldlt_solve6_rolled(A, gs, y, w)) { ok = true; break; }
     mu_lm *= 10.0;                                              // mu_increase_factor_
   }
   double n2 = 0.0;
@@ -524,6 +605,7 @@ struct SolverShared {
   double spec_mcc;
   Pose7 spec_cq;
   int spec_ok, pad;
+  double ldlt_ws[51];  // scratch of the rolled LDL^T (gn_model_rolled)
   FrameState backup;   // state before advance(), for the (practically never taken) gradient-tolerance exit
 };
 
@@ -599,7 +681,13 @@ __device__ __noinline__ void solver_on_eval(const DeviceCtx& ctx, FrameState* st
     if (lane == 0) {
       double H[21];
       for (int i = 0; i < 21; ++i) H[i] = tot[i];
-      if (!TLOAM_SOLVER_WARP_MODEL) gn_model(H, g, sc, mu0, m);
+#ifndef TLOAM_SOLVER_ROLLED_MODEL
+#define TLOAM_SOLVER_ROLLED_MODEL 0   // 1: gn_model_rolled (measured: 11.3k cycles vs 5.0k -- shared-memory latency on every operand)
+#endif
+      if (!TLOAM_SOLVER_WARP_MODEL) {
+        if (TLOAM_SOLVER_ROLLED_MODEL) gn_model_rolled(H, g, sc, mu0, m, sh->ldlt_ws);
+        else gn_model(H, g, sc, mu0, m);
+      }
       sh->model = m;
       if (ctx.dbg) ctx.dbg[6] += (unsigned long long)(clock64() - ta0);
       int ok = 0;
