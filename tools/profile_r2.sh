@@ -18,4 +18,12 @@ ncu --set full --clock-control none --import-source on -k regex:k_map_fine -s 1 
 # (3) dense path (config 3, reduced: the kernel is the same)
 TLOAM_B200_DENSE=1 ncu --set full --clock-control none --import-source on -k regex:k_correspond_dense -s 1 -c 2 -o gpurun_out/r2_dense python tools/config3.py 0.25 > gpurun_out/r2_dense.log 2>&1
 TLOAM_B200_DENSE=1 ncu --set full --clock-control none --import-source on -k regex:k_qbin -s 3 -c 3 -o gpurun_out/r2_qbin python tools/config3.py 0.25 > gpurun_out/r2_qbin.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# gpurun brings back at most 64 MiB: keep the raw metric tables and the per-source-line summaries, drop the reports
+for r in gpurun_out/r2_*.ncu-rep; do
+  b=${r%.ncu-rep}
+  ncu -i $r --page raw --csv > ${b}_raw.csv 2>/dev/null
+  python tools/ncu_lines.py $r 60 > ${b}_lines.txt 2>/dev/null
+  python tools/ncu_lines.py $r 40 smp > ${b}_lines_by_samples.txt 2>/dev/null
+  rm -f $r
+done
+ls -la gpurun_out/ | head -60

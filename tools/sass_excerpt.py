@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "tloam_b200", "libtloam_b200.so")
-WANT = ["k_first", "k_eval", "k_correspond_dense", "k_correspond", "k_begin_frame", "k_ge_fit", "k_fe_sort", "k_qbin_count"]
+WANT = ["k_first", "k_eval", "k_correspond_dense", "k_correspond_fine", "k_correspond", "k_map_fine", "k_begin_frame", "k_ge_fit", "k_fe_sort", "k_qbin_count"]
 
 
 def main():
