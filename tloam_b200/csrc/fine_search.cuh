@@ -76,6 +76,7 @@ struct FineSmem {
   unsigned jb[kFineCap][kBlk];        // first point of the segment
   unsigned cm[kFineCap][kBlk];        // count << 16 | upper half of the FP32 lower bound of its squared distance (rounded down)
   unsigned qu[kFineQueue][kBlk];      // positions of the candidates that may belong to the K best
+  unsigned done[kBlk];                // column c: the thread that adopted query c has finished scanning its first-pass list
 };
 
 __device__ __forceinline__ void fine_index_box(const FineConst& q, float w, int lo[3], int hi[3]) {
@@ -195,12 +196,17 @@ __device__ __forceinline__ void fine_list_own(const GridDesc& g, const FineConst
   }
 }
 
-// Continuation pass, the 32 lanes of a warp on ONE query (all arguments warp-uniform): lane l < 27 fetches cell l of the
-// 3 x 3 x 3 neighbourhood, then the 27 x 16 rows (row r = cell * 16 + z * 4 + y) are dealt to the lanes
-// and every lane lists the segments of its rows that intersect [lo, hi] and were not inside the previous box [plo, phi].
+// Continuation pass, the 32 lanes of a warp on ONE query (all arguments warp-uniform).  Lane l < 27 fetches cell l of the
+// 3 x 3 x 3 neighbourhood; the rows of the index box [lo, hi] (bins in y x bins in z x cells in x) are dealt to the lanes,
+// each lane works out the segments of its rows (minus the previous box [plo, phi], minus what the K-th best prunes) and
+// the segments are cut into chunks of `cs` points that go round-robin into the warp's 32 list columns (a warp-wide
+// prefix sum per step gives every chunk its slot): every lane ends up with the same number of chunks, whatever the
+// shape of the surfaces inside the box.  m = chunks in my column, -1 on overflow of the 28 x 32 slots.
 __device__ __forceinline__ void fine_list_coop(const GridDesc& g, const FineConst& q, const int lo[3], const int hi[3],
                                                const int plo[3], const int phi[3], float boundf, FineSmem* sm, int& m) {
+  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const int wbase = (int)threadIdx.x & ~31;
   // ---- my cell ----
   unsigned c_beg = 0u, c_cnt = 0u;
   int c_fidx = -1;
@@ -217,58 +223,117 @@ __device__ __forceinline__ void fine_list_coop(const GridDesc& g, const FineCons
         unsigned beg = e.a.z, nd = 0u;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-          const unsigned cs = e.count(s);
-          if (s < sub) { beg += cs; nd += (cs >= kFineMin) ? 1u : 0u; }
-          if (s == sub) c_cnt = cs;
+          const unsigned cs_ = e.count(s);
+          if (s < sub) { beg += cs_; nd += (cs_ >= kFineMin) ? 1u : 0u; }
+          if (s == sub) c_cnt = cs_;
         }
         c_beg = beg;
         if (e.b.w != 0u && c_cnt >= kFineMin) c_fidx = (int)(e.b.w - 1u + nd);
       }
     }
   }
-  // ---- my rows ----
-#pragma unroll 1
-  for (int k = 0; k < 14; ++k) {
-    // row = (slot * 37) mod 432: a bijection that scatters the rows one surface occupies (neighbours in y, z and cell
-    // differ by 1, 4 and 16) over the lanes; dealt in natural order they landed on 8 of the 32 lanes
-    const int slot = lane + 32 * k;
-    const int r = slot < 27 * 16 ? (slot * 37) % (27 * 16) : 27 * 16;
-    const int cell = r < 27 * 16 ? (r >> 4) : 0;
-    const unsigned cbeg = __shfl_sync(0xffffffffu, c_beg, cell), cnt = __shfl_sync(0xffffffffu, c_cnt, cell);
-    const int fidx = __shfl_sync(0xffffffffu, c_fidx, cell);
-    if (r >= 27 * 16 || cnt == 0u) continue;
-    const int ox = 4 * (cell % 3), oy = 4 * ((cell / 3) % 3), oz = 4 * (cell / 9);
-    const int y = r & 3, z = (r >> 2) & 3;
-    if (fidx < 0) {
-      // a sparse cell is one segment (its row 0): it belongs to the first pass whose box reaches it
-      if (y != 0 || z != 0) continue;
-      if (!(ox + 3 < plo[0] || ox > phi[0] || oy + 3 < plo[1] || oy > phi[1] || oz + 3 < plo[2] || oz > phi[2])) continue;
-      const float mds = fine_box_lb(q, ox, ox + 3, oy, oy + 3, oz, oz + 3);
-      if (mds < boundf) fine_push(sm, m, cbeg, cbeg + cnt, mds);
-      continue;
+  // chunk size: 8 points, doubled until the points of the box's cells (an upper bound of the candidates) fit ~600 slots
+  unsigned upper = c_cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) upper += __shfl_xor_sync(full, upper, o);
+  unsigned cs = 8u;
+  while (cs * 600u < upper) cs <<= 1;
+  int total = 0;                                                  // chunks listed so far (warp-uniform)
+  bool over = false;
+  // one step: every lane offers up to two segments; chunks get consecutive slots
+  auto publish = [&](unsigned jb0, unsigned n0, float md0, unsigned jb1, unsigned n1, float md1) {
+    const unsigned k0 = (n0 + cs - 1u) / cs, k1 = (n1 + cs - 1u) / cs;
+    unsigned incl = k0 + k1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(full, incl, o); if (lane >= o) incl += v; }
+    const unsigned step_total = __shfl_sync(full, incl, 31);
+    unsigned p = (unsigned)total + incl - (k0 + k1);
+    if ((unsigned)total + step_total > (unsigned)(kFineCap * 32)) { over = true; }
+    else {
+      for (unsigned c = 0; c < k0; ++c, ++p) {
+        const unsigned len = (n0 - c * cs < cs) ? n0 - c * cs : cs;
+        sm->jb[p >> 5][wbase + (p & 31u)] = jb0 + c * cs;
+        sm->cm[p >> 5][wbase + (p & 31u)] = (len << 16) | (__float_as_uint(md0) >> 16);
+      }
+      for (unsigned c = 0; c < k1; ++c, ++p) {
+        const unsigned len = (n1 - c * cs < cs) ? n1 - c * cs : cs;
+        sm->jb[p >> 5][wbase + (p & 31u)] = jb1 + c * cs;
+        sm->cm[p >> 5][wbase + (p & 31u)] = (len << 16) | (__float_as_uint(md1) >> 16);
+      }
+      total += (int)step_total;
     }
-    if (oy + y < lo[1] || oy + y > hi[1] || oz + z < lo[2] || oz + z > hi[2]) continue;
-    const int x0 = (lo[0] > ox ? lo[0] : ox) - ox, x1 = (hi[0] < ox + 3 ? hi[0] : ox + 3) - ox;
-    if (x0 > x1) continue;
-    fine_push_row(q, g.fine + (size_t)fidx * kFineBins, cbeg, ox, oy, oz, x0, x1, y, z, plo, phi, boundf, sm, m);
+  };
+  // ---- sparse cells: one segment each (a cell belongs to the first pass whose box reaches it) ----
+  {
+    unsigned n0 = 0u;
+    float md0 = 0.0f;
+    if (lane < 27 && c_cnt != 0u && c_fidx < 0) {
+      const int ox = 4 * (lane % 3), oy = 4 * ((lane / 3) % 3), oz = 4 * (lane / 9);
+      if (ox + 3 < plo[0] || ox > phi[0] || oy + 3 < plo[1] || oy > phi[1] || oz + 3 < plo[2] || oz > phi[2]) {
+        md0 = fine_box_lb(q, ox, ox + 3, oy, oy + 3, oz, oz + 3);
+        if (md0 < boundf) n0 = c_cnt;
+      }
+    }
+    if (__any_sync(full, n0 != 0u)) publish(c_beg, n0, md0, 0u, 0u, 0.0f);
   }
+  // ---- rows of the dense cells ----
+  const int cx0 = lo[0] >> 2, ncx = (hi[0] >> 2) - cx0 + 1;
+  const int ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1;
+  const int nrows = ncx * ny * nz;
+#pragma unroll 1
+  for (int base = 0; base < nrows; base += 32) {
+    const int r = base + lane;
+    const bool have = r < nrows;
+    const int xc = have ? r % ncx : 0, yy = have ? (r / ncx) % ny : 0, zz = have ? r / (ncx * ny) : 0;
+    const int gy = lo[1] + yy, gz = lo[2] + zz;
+    const int o3x = cx0 + xc, cell = (gz >> 2) * 9 + (gy >> 2) * 3 + o3x;
+    const unsigned cbeg = __shfl_sync(full, c_beg, cell), cnt = __shfl_sync(full, c_cnt, cell);
+    const int fidx = __shfl_sync(full, c_fidx, cell);
+    unsigned jb[2] = {0u, 0u}, n[2] = {0u, 0u};
+    float md[2] = {0.0f, 0.0f};
+    if (have && cnt != 0u && fidx >= 0) {
+      const int ox = 4 * o3x, oy = gy & ~3, oz = gz & ~3, y = gy & 3, z = gz & 3;
+      const int x0 = (lo[0] > ox ? lo[0] : ox) - ox, x1 = (hi[0] < ox + 3 ? hi[0] : ox + 3) - ox;
+      const unsigned short* ft = g.fine + (size_t)fidx * kFineBins;
+      const int row = (z * kFineDiv + y) * kFineDiv;
+      const bool cut = (gz >= plo[2] && gz <= phi[2] && gy >= plo[1] && gy <= phi[1]);
+#pragma unroll
+      for (int seg = 0; seg < 2; ++seg) {
+        int xa = x0, xb = x1;
+        if (cut) {
+          if (seg == 0) xb = (plo[0] - 1 - ox < x1) ? plo[0] - 1 - ox : x1;
+          else xa = (phi[0] + 1 - ox > x0) ? phi[0] + 1 - ox : x0;
+        } else if (seg == 1) {
+          continue;
+        }
+        if (xa > xb) continue;
+        const unsigned b = cbeg + ((row + xa) ? (unsigned)ft[row + xa - 1] : 0u), e = cbeg + (unsigned)ft[row + xb];
+        if (e <= b) continue;
+        const float mds = fine_box_lb(q, ox + xa, ox + xb, gy, gy, gz, gz);
+        if (mds >= boundf) continue;
+        jb[seg] = b; n[seg] = e - b; md[seg] = mds;
+      }
+    }
+    if (__any_sync(full, (n[0] | n[1]) != 0u)) publish(jb[0], n[0], md[0], jb[1], n[1], md[1]);
+  }
+  m = over ? -1 : (total + 31 - lane) / 32;
 }
 
 // Consumes the calling thread's segment list: exact top-K of its candidates merged into `t` (which may already hold
 // candidates of earlier passes; `bound` = min(r2, K-th best so far) on entry and on return).
 template <int K>
-__device__ __forceinline__ void fine_scan(const GridDesc& g, FineSmem* sm, int m, double rx, double ry, double rz,
+__device__ __forceinline__ void fine_scan(const GridDesc& g, FineSmem* sm, int col, int m, double rx, double ry, double rz,
                                           double r2, const float qa[3], double pf_abs, double& bound, TopK<K>& t) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x;               // my queue column; the segment list is column `col` (mine, or an adopted query's)
   // nearest segment first: it fills the threshold network with good candidates
   if (m > 1) {
     int best = 0;
-    unsigned bm = sm->cm[0][tid] & 0xFFFFu;
-    for (int i = 1; i < m; ++i) { const unsigned v = sm->cm[i][tid] & 0xFFFFu; if (v < bm) { bm = v; best = i; } }
+    unsigned bm = sm->cm[0][col] & 0xFFFFu;
+    for (int i = 1; i < m; ++i) { const unsigned v = sm->cm[i][col] & 0xFFFFu; if (v < bm) { bm = v; best = i; } }
     if (best != 0) {
-      const unsigned a = sm->jb[0][tid], b = sm->cm[0][tid];
-      sm->jb[0][tid] = sm->jb[best][tid]; sm->cm[0][tid] = sm->cm[best][tid];
-      sm->jb[best][tid] = a; sm->cm[best][tid] = b;
+      const unsigned a = sm->jb[0][col], b = sm->cm[0][col];
+      sm->jb[0][col] = sm->jb[best][col]; sm->cm[0][col] = sm->cm[best][col];
+      sm->jb[best][col] = a; sm->cm[best][col] = b;
     }
   }
   // FP32 threshold: the K smallest FP32 distances seen so far, ascending, in a branch-free network.  A candidate of the
@@ -284,8 +349,8 @@ __device__ __forceinline__ void fine_scan(const GridDesc& g, FineSmem* sm, int m
   unsigned off = 0u, cb = 0u, cc = 0u;
   auto load_entry = [&]() {
     while (ci < m) {
-      const unsigned cm = sm->cm[ci][tid];
-      if (!(__uint_as_float(cm << 16) >= thr)) { cb = sm->jb[ci][tid]; cc = cm >> 16; off = 0u; return; }
+      const unsigned cm = sm->cm[ci][col];
+      if (!(__uint_as_float(cm << 16) >= thr)) { cb = sm->jb[ci][col]; cc = cm >> 16; off = 0u; return; }
       ++ci;                                                       // nothing in this segment can belong to the K best
     }
   };
@@ -334,25 +399,69 @@ __device__ __forceinline__ void fine_scan(const GridDesc& g, FineSmem* sm, int m
   if (t.d2[K - 1] < bound) bound = t.d2[K - 1];
 }
 
-// The whole search.  ALL 32 lanes of a warp must call it together (lanes without a query: live = false).
+// Phase 1a, every thread for its OWN query: lists the segments of the first pass (w = one bin edge) in its column and
+// publishes the query for adoption (rows 24..31 of its queue column: coordinates, list length, sort key = candidates
+// << 7 | thread).  The thread block then sorts the keys (fine_sort_queries) and thread t ADOPTS the query of rank t:
+// the 32 queries a warp scans together have similar candidate counts (150 ... 450 on config 3: unsorted, a warp waited
+// for its largest query while the average lane was idle half of the time).
+__device__ __forceinline__ void fine_list_and_publish(const GridDesc& g, bool live, double rx, double ry, double rz, double r2, FineSmem* sm) {
+  const int tid = threadIdx.x;
+  int m = 0;
+  unsigned ncand = 0u;
+  if (live && g.n != 0u) {
+    const FineConst q = fine_const(g, rx, ry, rz);
+    int lo[3], hi[3];
+    fine_index_box(q, q.fe, lo, hi);
+    fine_list_own(g, q, lo, hi, fine_boundf(q.pf_abs, r2), sm, m);
+    for (int i = 0; i < m; ++i) ncand += sm->cm[i][tid] >> 16;
+    if (m < 0) ncand = 0xFFFFFu;                                 // list overflow: the warp does this query from scratch
+  } else {
+    m = -2;                                                       // no query
+  }
+  sm->qu[24][tid] = (unsigned)__double2loint(rx); sm->qu[25][tid] = (unsigned)__double2hiint(rx);
+  sm->qu[26][tid] = (unsigned)__double2loint(ry); sm->qu[27][tid] = (unsigned)__double2hiint(ry);
+  sm->qu[28][tid] = (unsigned)__double2loint(rz); sm->qu[29][tid] = (unsigned)__double2hiint(rz);
+  sm->done[tid] = 0u;
+  sm->qu[30][tid] = (unsigned)m;
+  sm->qu[31][tid] = ((ncand > 0xFFFFFu ? 0xFFFFFu : ncand) << 7) | (unsigned)tid;
+}
+
+// bitonic sort of the kBlk keys in row 31 of the queue array, descending (all threads of the block)
+__device__ __forceinline__ void fine_sort_queries(FineSmem* sm) {
+  const unsigned tid = threadIdx.x;
+  __syncthreads();
+#pragma unroll 1
+  for (unsigned k = 2; k <= (unsigned)kBlk; k <<= 1)
+#pragma unroll 1
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      const unsigned partner = tid ^ j;
+      if (partner > tid) {
+        const unsigned a = sm->qu[31][tid], b = sm->qu[31][partner];
+        const bool desc = (tid & k) == 0;                         // this run is sorted descending
+        if (desc ? (a < b) : (a > b)) { sm->qu[31][tid] = b; sm->qu[31][partner] = a; }
+      }
+      __syncthreads();
+    }
+}
+
+// Phase 1b + 2 for the ADOPTED query (thread `col` listed it): flat scan of its first-pass segments, then the
+// warp-cooperative continuation.  ALL 32 lanes of a warp must call it together (lanes without a query: live = false).
 template <int K>
-__device__ __forceinline__ void knn_search_fine(const GridDesc& g, bool live, double rx, double ry, double rz, double r2, TopK<K>& t,
-                                                FineSmem* sm) {
+__device__ __forceinline__ void knn_search_fine(const GridDesc& g, bool live, int col, int m, double rx, double ry, double rz, double r2,
+                                                TopK<K>& t, FineSmem* sm) {
   const unsigned lane = threadIdx.x & 31u;
   t.init();
   bool need = false;
   double bound = r2;
   float wdone = 0.0f;                                            // half-width of the box searched so far
   int lo[3] = {12, 12, 12}, hi[3] = {-1, -1, -1};
-  // ---- phase 1: my own query, first pass ----
+  // ---- phase 1: first pass of my (adopted) query ----
   {
-    int m = 0;
     float qa[3] = {0.f, 0.f, 0.f};
     double pf_abs = 0.0;
     if (live && g.n != 0u) {
       const FineConst q = fine_const(g, rx, ry, rz);
       fine_index_box(q, q.fe, lo, hi);
-      fine_list_own(g, q, lo, hi, fine_boundf(q.pf_abs, bound), sm, m);
       need = true;
       wdone = q.fe;
       qa[0] = q.qa[0]; qa[1] = q.qa[1]; qa[2] = q.qa[2]; pf_abs = q.pf_abs;
@@ -362,13 +471,25 @@ __device__ __forceinline__ void knn_search_fine(const GridDesc& g, bool live, do
         wdone = 0.5f * q.fe;
         m = 0;
       }
+    } else {
+      m = 0;
     }
-    fine_scan<K>(g, sm, m, rx, ry, rz, r2, qa, pf_abs, bound, t);
+    fine_scan<K>(g, sm, col, m, rx, ry, rz, r2, qa, pf_abs, bound, t);
+    // column `col` (another thread's, possibly another warp's) may be overwritten from here on
+    __threadfence_block();
+    reinterpret_cast<volatile unsigned*>(sm->done)[col] = 1u;
   }
   // complete iff everything within sqrt(bound) of the query lies inside the box just searched
   need = need && !((double)wdone * (double)wdone >= bound);
   // ---- phase 2: unfinished queries, one at a time, by the whole warp ----
   unsigned todo = __ballot_sync(0xffffffffu, need);
+  if (todo) {
+    // the continuation passes deal their chunks into THIS warp's 32 columns: wait until their adopters are done with them
+    // (a spin on shared-memory flags inside one resident block; adopters never wait for anything before they set theirs)
+    const volatile unsigned* dv = reinterpret_cast<const volatile unsigned*>(sm->done);
+    while (!__all_sync(0xffffffffu, dv[(threadIdx.x & ~31u) + lane] != 0u)) {}
+    __threadfence_block();
+  }
   while (todo) {
     const int src = __ffs(todo) - 1;
     todo &= todo - 1u;
@@ -385,14 +506,16 @@ __device__ __forceinline__ void knn_search_fine(const GridDesc& g, bool live, do
       w = wn < q.wmax ? wn : q.wmax;
       int nlo[3], nhi[3], m = 0;
       fine_index_box(q, w, nlo, nhi);
+      __syncwarp();                                              // the previous pass's lists have been consumed
       fine_list_coop(g, q, nlo, nhi, blo, bhi, fine_boundf(q.pf_abs, bnd), sm, m);
-      const bool over = __any_sync(0xffffffffu, m < 0);          // cannot happen (<= 14 rows x 2 segments per lane)
+      __syncwarp();                                              // chunks were written into each other's columns
+      const bool over = __any_sync(0xffffffffu, m < 0);          // more chunks than slots: pathological (tens of thousands of candidates)
       if (over) m = 0;
       TopK<K> tl;
       tl.init();
       if ((int)lane == src) tl = t;
       double pb = bnd;
-      fine_scan<K>(g, sm, m, bx, by, bz, r2, q.qa, q.pf_abs, pb, tl);
+      fine_scan<K>(g, sm, (int)threadIdx.x, m, bx, by, bz, r2, q.qa, q.pf_abs, pb, tl);
       // merge: K rounds of a warp-wide argmin over the heads of the 32 sorted private lists; lane src collects
       double kth = __longlong_as_double(0x7FF0000000000000ll);
 #pragma unroll
@@ -445,24 +568,39 @@ __global__ void __launch_bounds__(kBlk, 4) k_correspond_fine(const __grid_consta
   if (fb >= ctx.blk_off[4]) return;
   const int c = cloud_of_block(ctx, fb);
   if (!((ctx.dense_mask >> c) & 1)) return;
-  const int il = (fb - ctx.blk_off[c]) * kBlk + (int)threadIdx.x;
-  const int gi = ctx.pad_off[c] + il;
-  const bool live = il < ctx.n[c] && cloud_enabled(ctx, c);
+  extern __shared__ __align__(16) unsigned char fine_raw[];
+  FineSmem* s_fine = reinterpret_cast<FineSmem*>(fine_raw);
   unsigned char flag = 0;
   double rx = 0.0, ry = 0.0, rz = 0.0;
-  if (live) {
-    const Rt T = pose_to_rt(st->xq);
-    double qx, qy, qz;
-    rt_apply(T, ctx.px[gi], ctx.py[gi], ctx.pz[gi], qx, qy, qz);
-    rx = qx - ctx.origin[0]; ry = qy - ctx.origin[1]; rz = qz - ctx.origin[2];
+  {
+    // my OWN feature: transform, list the first pass, publish
+    const int il0 = (fb - ctx.blk_off[c]) * kBlk + (int)threadIdx.x;
+    const int gi0 = ctx.pad_off[c] + il0;
+    const bool live0 = il0 < ctx.n[c] && cloud_enabled(ctx, c);
+    if (live0) {
+      const Rt T = pose_to_rt(st->xq);
+      double qx, qy, qz;
+      rt_apply(T, ctx.px[gi0], ctx.py[gi0], ctx.pz[gi0], qx, qy, qz);
+      rx = qx - ctx.origin[0]; ry = qy - ctx.origin[1]; rz = qz - ctx.origin[2];
+    }
+    fine_list_and_publish(ctx.grid[c], live0, rx, ry, rz, ctx.r2[c], s_fine);
   }
+  fine_sort_queries(s_fine);
+  // the feature I ADOPT: rank threadIdx.x by candidate count
+  const int col = (int)(s_fine->qu[31][threadIdx.x] & 127u);
+  const int m_ad = (int)s_fine->qu[30][col];
+  rx = __hiloint2double((int)s_fine->qu[25][col], (int)s_fine->qu[24][col]);
+  ry = __hiloint2double((int)s_fine->qu[27][col], (int)s_fine->qu[26][col]);
+  rz = __hiloint2double((int)s_fine->qu[29][col], (int)s_fine->qu[28][col]);
+  __syncthreads();                                    // everybody has read its adoption record: the queue rows are free
+  const int il = (fb - ctx.blk_off[c]) * kBlk + col;
+  const int gi = ctx.pad_off[c] + il;
+  const bool live = m_ad != -2;
   double prim[6];
   TopK<1> t1;
   TopK<5> t5;
-  extern __shared__ __align__(16) unsigned char fine_raw[];
-  FineSmem* s_fine = reinterpret_cast<FineSmem*>(fine_raw);
-  if (c == kSphere) knn_search_fine<1>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], t1, s_fine);    // warp-cooperative: every lane calls
-  else knn_search_fine<5>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], t5, s_fine);
+  if (c == kSphere) knn_search_fine<1>(ctx.grid[c], live, col, m_ad, rx, ry, rz, ctx.r2[c], t1, s_fine);    // warp-cooperative: every lane calls
+  else knn_search_fine<5>(ctx.grid[c], live, col, m_ad, rx, ry, rz, ctx.r2[c], t5, s_fine);
   if (live) {
     if (c == kSphere) {
       TopK<1>& t = t1;
