@@ -244,7 +244,7 @@ enum {
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
   TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_FIRST,
   TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_GROUND, TLOAM_B200_K_MAP_FINE,
-  TLOAM_B200_K_FINE, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_FINE, TLOAM_B200_K_EDGE, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
@@ -342,6 +342,17 @@ void tloam_b200_ground_default_config(tloam_ground_config* c);
 int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* cfg, const double* xyz, size_t n,
                               size_t* ground_index, size_t* n_ground, size_t* object_index, size_t* n_object, int* beam,
                               int* region, double* height_threshold, double* planes);
+
+/* ---- "next" row (f)-4, second part: LOAM-style edge extraction of the segmentation nodelet,
+ * Segmentation::extractEdgePoint + extractFromSection (ref: src/models/segmentation/segmentation.cpp:1144-1304, called at
+ * :64 on the clustered object points).  xyz: n AoS points; intensity: the beam id of every point (the reference keeps it in
+ * the intensity channel, (int)intensity must lie in [0, sensor_model), sensor_model <= 64); beams with fewer than ring_min_num
+ * points are skipped (config/mapping/segmentation.yaml: 131).  Outputs are index lists into the input, in the order in which
+ * the reference appends the points: edge_index (capacity n) by (beam, sector, descending curvature), <= 20 per sector;
+ * non_edge_index (capacity n) by (beam, sector, ascending curvature).  Bit-exact against oracle/segmentation_oracle.cpp.
+ * A sector with more than 4096 curvature values (a beam with more than 24 586 points) is rejected: INVALID_ARG. */
+int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min_num, const double* xyz, const double* intensity,
+                            size_t n, size_t* edge_index, size_t* n_edge, size_t* non_edge_index, size_t* n_non_edge);
 
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);

@@ -162,6 +162,8 @@ def lib():
         L.oracle_ground_section_bounds.argtypes = [C.POINTER(GroundConfig), C.POINTER(C.c_float), C.c_int]
         L.oracle_ground_extract.argtypes = [dp, C.c_size_t, C.POINTER(GroundConfig), szp, szp, szp, szp, ip, ip, dp, dp]
         L.oracle_ground_extract.restype = C.c_int
+        L.oracle_extract_edge.argtypes = [dp, dp, C.c_size_t, C.c_int, C.c_int, C.c_int, szp, szp, szp, szp]
+        L.oracle_extract_edge.restype = C.c_int
         _lib = L
     return _lib
 
@@ -475,3 +477,21 @@ def ground_extract(pts, **overrides):
     assert rc == 0
     return dict(ground=g[:ng.value].copy(), object=o[:no.value].copy(), beam=beam[:n].copy(), region=region[:n].copy(),
                 height_threshold=thr.value, planes=planes)
+
+
+def extract_edge(pts, intensity, sensor_model=64, ring_min_num=16, max_section=4096):
+    """Segmentation::extractEdgePoint restated (ref: segmentation.cpp:1144-1304).  Returns dict(edge, non_edge) of index
+    lists into the input, in the reference's append order; None if a sector exceeds max_section (the device limit)."""
+    a = _f64(pts).reshape(-1, 3)
+    it = _f64(intensity).reshape(-1)
+    n = a.shape[0]
+    assert it.shape[0] == n
+    e = np.zeros(max(n, 1), dtype=np.uintp)
+    o = np.zeros(max(n, 1), dtype=np.uintp)
+    ne, no = C.c_size_t(0), C.c_size_t(0)
+    szp = C.POINTER(C.c_size_t)
+    rc = lib().oracle_extract_edge(_dp(a), _dp(it), n, sensor_model, ring_min_num, max_section, e.ctypes.data_as(szp), C.byref(ne),
+                                   o.ctypes.data_as(szp), C.byref(no))
+    if rc != 0:
+        return None
+    return dict(edge=e[:ne.value].copy(), non_edge=o[:no.value].copy())

@@ -276,3 +276,90 @@ int oracle_ground_extract(const double* pts, size_t n_, const oracle_ground_conf
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Edge extraction (ref: segmentation.cpp:1144-1304).  Compiled with -ffp-contract=off like the rest of this file: the
+// device side uses __dadd_rn / __dmul_rn, so curvatures, the 0.1 threshold and the 0.05 gap test are bit-exact.
+// Reference behaviour kept literally:
+//   * points are distributed to beams by (int)intensity in input order (:1230-1237);  a beam id equal to sensorModel
+//     passes the reference's `<=` test and writes one past the end of ringScans (undefined behaviour): dropped here;
+//   * beams with fewer than ringMinNum points are skipped (:1240);
+//   * curvature of ring point j (5 <= j < size - 5) = |sum of the 10 neighbours - 10 p_j|^2, summed left to right (:1248-1285);
+//   * six sectors per beam; the sub-range handed to extractFromSection ends ONE BEFORE sector_end (iterator end is
+//     exclusive, :1292), so the last curvature of every sector is in neither output;
+//   * per sector: ascending sort by curvature; from the top, up to 20 picks with curvature > 0.1 (the 21st candidate ends
+//     the loop), every pick marks its +-5 ring neighbours as picked until a gap^2 > 0.05 (:1153-1199); everything not
+//     picked goes to the non-edge list in ascending-curvature order (:1202-1209).
+// Left to the implementation by the reference and fixed here (identically on the device): std::sort is not stable ->
+// ties are ordered by ring position; an empty sector (cannot happen with ringMinNum >= 16) is skipped instead of
+// running the reference's `i <= size - 1` loop on an unsigned zero.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <algorithm>
+
+extern "C" int oracle_extract_edge(const double* pts, const double* intensity, size_t n, int sensor_model, int ring_min_num, int max_section,
+                                   size_t* edge_index, size_t* n_edge, size_t* non_edge_index, size_t* n_non_edge) {
+  *n_edge = 0; *n_non_edge = 0;
+  if (sensor_model <= 0) return 0;
+  std::vector<std::vector<size_t>> rings((size_t)sensor_model);
+  for (size_t i = 0; i < n; ++i) {
+    const int beam = (int)intensity[i];                                  // :1232
+    if (beam >= 0 && beam < sensor_model) rings[(size_t)beam].push_back(i);
+  }
+  for (int r = 0; r < sensor_model; ++r) {
+    const std::vector<size_t>& ring = rings[(size_t)r];
+    const int total = (int)ring.size();
+    if (total < ring_min_num) continue;                                  // :1240
+    const int total_points = total - 10;                                 // :1246
+    if (total_points <= 0) continue;
+    auto P = [&](int j, int d) { return pts[3 * ring[(size_t)j] + (size_t)d]; };
+    std::vector<double> curv((size_t)total_points);                      // curv[c] belongs to ring position c + 5
+    for (int j = 5; j < total - 5; ++j) {
+      double diff[3];
+      for (int d = 0; d < 3; ++d)
+        diff[d] = P(j - 5, d) + P(j - 4, d) + P(j - 3, d) + P(j - 2, d) + P(j - 1, d) - 10 * P(j, d) + P(j + 1, d) + P(j + 2, d) +
+                  P(j + 3, d) + P(j + 4, d) + P(j + 5, d);
+      curv[(size_t)(j - 5)] = diff[0] * diff[0] + diff[1] * diff[1] + diff[2] * diff[2];
+    }
+    for (int sct = 0; sct < 6; ++sct) {
+      const int sector_length = total_points / 6;                        // :1288
+      const int start = sector_length * sct;
+      const int end = sct != 5 ? sector_length * (sct + 1) - 1 : total_points - 1;
+      const int cnt = end - start;                                       // [start, end): exclusive end, :1292
+      if (cnt <= 0) continue;
+      if (max_section > 0 && cnt > max_section) return -1;
+      std::vector<std::pair<double, int>> sub((size_t)cnt);              // (curvature, ring position)
+      for (int c = 0; c < cnt; ++c) sub[(size_t)c] = {curv[(size_t)(start + c)], start + c + 5};
+      std::sort(sub.begin(), sub.end());                                 // ascending; ties by ring position
+      std::vector<char> picked((size_t)total, 0);
+      int largest = 0;
+      for (int i = cnt - 1; i >= 0; --i) {
+        const int id = sub[(size_t)i].second;
+        if (picked[(size_t)id]) continue;
+        if (sub[(size_t)i].first <= 0.1) break;                          // :1161
+        ++largest;
+        picked[(size_t)id] = 1;
+        if (largest <= 20) edge_index[(*n_edge)++] = ring[(size_t)id];   // :1169-1173
+        else break;
+        for (int k = 1; k <= 5; ++k) {                                   // :1177-1187
+          double g = 0.0;
+          {
+            const double dx = P(id + k, 0) - P(id + k - 1, 0), dy = P(id + k, 1) - P(id + k - 1, 1), dz = P(id + k, 2) - P(id + k - 1, 2);
+            g = dx * dx + dy * dy + dz * dz;
+          }
+          if (g > 0.05) break;
+          picked[(size_t)(id + k)] = 1;
+        }
+        for (int k = -1; k >= -5; --k) {                                 // :1189-1199
+          const double dx = P(id + k, 0) - P(id + k + 1, 0), dy = P(id + k, 1) - P(id + k + 1, 1), dz = P(id + k, 2) - P(id + k + 1, 2);
+          if (dx * dx + dy * dy + dz * dz > 0.05) break;
+          picked[(size_t)(id + k)] = 1;
+        }
+      }
+      for (int i = 0; i < cnt; ++i) {                                    // :1202-1209
+        const int id = sub[(size_t)i].second;
+        if (!picked[(size_t)id]) non_edge_index[(*n_non_edge)++] = ring[(size_t)id];
+      }
+    }
+  }
+  return 0;
+}

@@ -209,6 +209,15 @@ int oracle_ground_extract(const double* pts, size_t n, const oracle_ground_confi
                           size_t* n_ground, size_t* object_index, size_t* n_object, int* beam, int* region,
                           double* mean_height_out, double* planes);
 
+/* Segmentation::extractEdgePoint + extractFromSection (ref: src/models/segmentation/segmentation.cpp:1144-1304): LOAM-style
+ * edge features by the smoothness of the local surface, per beam and per sixth of a beam.  pts: AoS xyz; intensity: the
+ * beam id of every point (the reference keeps it in the intensity channel).  Outputs are INDEX lists into the input
+ * (the reference emits the points themselves): edge_index in (beam, sector, descending curvature) order, non_edge_index in
+ * (beam, sector, ascending curvature) order.  Returns 0, or -1 if a sector holds more than max_section curvature values
+ * (device limit mirrored so that both sides reject the same inputs; max_section <= 0: no limit). */
+int oracle_extract_edge(const double* pts, const double* intensity, size_t n, int sensor_model, int ring_min_num, int max_section,
+                        size_t* edge_index, size_t* n_edge, size_t* non_edge_index, size_t* n_non_edge);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@
 #include "submap.cuh"
 #include "feature_extract.cuh"
 #include "ground_extract.cuh"
+#include "edge_extract.cuh"
 
 
 
@@ -2202,6 +2203,71 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
   for (unsigned i = 0; i < counts[1]; ++i) object_index[i] = oi[i];
   if (region) for (size_t i = 0; i < n; ++i) region[i] = keys[i];
   *n_ground = counts[0]; *n_object = counts[1];
+  return TLOAM_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "next" row (f)-4, second part: LOAM-style edge extraction (edge_extract.cuh)
+// ---------------------------------------------------------------------------------------------
+int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min_num, const double* xyz, const double* intensity,
+                            size_t n, size_t* edge_index, size_t* n_edge, size_t* non_edge_index, size_t* n_non_edge) {
+  if (!h || !edge_index || !n_edge || !non_edge_index || !n_non_edge) return TLOAM_B200_ERR_INVALID_ARG;
+  *n_edge = *n_non_edge = 0;
+  if (sensor_model < 1 || sensor_model > kEeKeys || ring_min_num < 0) return TLOAM_B200_ERR_INVALID_ARG;
+  if (n == 0) return TLOAM_B200_OK;                                        // ref: :1222-1225 (empty input: nothing extracted)
+  if (!xyz || !intensity || n > ((size_t)1 << 30)) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  EeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = (unsigned)n; a.nchunk = (unsigned)((n + kEeChunk - 1) / kEeChunk);
+  a.sensor_model = sensor_model; a.ring_min = ring_min_num;
+  const int nsec = kEeKeys * kEeSectors;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
+  const size_t o_pts = take(n * 24), o_int = take(n * 8), o_key = take(n), o_cc = take((size_t)a.nchunk * kEeKeys * 4),
+               o_rb = take((kEeKeys + 1) * 4), o_ord = take(n * 4), o_se = take(n * 4), o_sn = take(n * 4), o_sc = take(nsec * 2 * 4),
+               o_so = take((nsec + 1) * 2 * 4), o_oe = take(n * 8), o_on = take(n * 8), o_st = take(64);
+  if (off > h->cap_ge) {                                                   // shares the segmentation arena
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_ge); h->d_ge = nullptr; h->cap_ge = 0;
+    CU_TRY(cudaMalloc(&h->d_ge, off + off / 4));
+    h->cap_ge = off + off / 4;
+  }
+  unsigned char* b = h->d_ge;
+  a.pts = (const double*)(b + o_pts); a.intensity = (const double*)(b + o_int); a.key = b + o_key;
+  a.chunk_cnt = (unsigned*)(b + o_cc); a.ring_base = (unsigned*)(b + o_rb); a.order = (unsigned*)(b + o_ord);
+  a.sec_edge = (unsigned*)(b + o_se); a.sec_non = (unsigned*)(b + o_sn); a.sec_cnt = (unsigned*)(b + o_sc);
+  a.sec_off = (unsigned*)(b + o_so); a.out_edge = (unsigned long long*)(b + o_oe); a.out_non = (unsigned long long*)(b + o_on);
+  a.status = (int*)(b + o_st);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(k_ee_section, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEeSmemBytes));
+    attr_set = true;
+  }
+  CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaMemcpyAsync(b + o_int, intensity, n * 8, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(cudaMemsetAsync(b + o_sc, 0, nsec * 2 * 4, h->stream));         // beams >= sensor_model have no sections
+  TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_key<<<a.nchunk, kEeChunk, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_scan<<<1, kEeKeys, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_scatter<<<a.nchunk, kEeChunk, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_section<<<dim3(kEeSectors, sensor_model), kEeThreads, kEeSmemBytes, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_offsets<<<1, 32, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_copy<<<dim3(kEeSectors, sensor_model), kEeThreads, 0, h->stream>>>(a)));
+  CU_TRY(cudaGetLastError());
+  unsigned tot[2];
+  int st = 0;
+  CU_TRY(cudaMemcpyAsync(tot, a.sec_off + 2 * (sensor_model * kEeSectors), sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaMemcpyAsync(&st, a.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  if (st != 0) {
+    snprintf(h->last_error, sizeof(h->last_error), "extract_edge: a beam sector holds more than %d curvature values", kEeMaxSection);
+    return TLOAM_B200_ERR_INVALID_ARG;
+  }
+  static_assert(sizeof(size_t) == sizeof(unsigned long long), "index lists are copied straight into size_t arrays");
+  if (tot[0]) CU_TRY(cudaMemcpyAsync(edge_index, a.out_edge, tot[0] * sizeof(size_t), cudaMemcpyDeviceToHost, h->stream));
+  if (tot[1]) CU_TRY(cudaMemcpyAsync(non_edge_index, a.out_non, tot[1] * sizeof(size_t), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
+  *n_edge = tot[0]; *n_non_edge = tot[1];
   return TLOAM_B200_OK;
 }
 

@@ -331,6 +331,23 @@ class LocalRegistration:
         return dict(ground=g[:ng.value].copy(), object=o[:no.value].copy(), beam=beam[:n].copy(), region=region[:n].copy(),
                     height_threshold=thr.value, planes=planes)
 
+    # ---- "next" row (f)-4, second part: edge extraction (ref: segmentation.cpp:1144-1304) ----
+    def extract_edge(self, points, intensity, sensor_model=64, ring_min_num=16):
+        """Segmentation::extractEdgePoint on the device.  intensity holds the beam id of every point (as groundRemove leaves
+        it).  Returns dict(edge, non_edge): index lists into the input in the reference's append order."""
+        a = _f64(points).reshape(-1, 3)
+        it = _f64(intensity).reshape(-1)
+        n = a.shape[0]
+        if it.shape[0] != n:
+            raise ValueError("one intensity (beam id) per point")
+        e = np.zeros(max(n, 1), dtype=np.uintp)
+        o = np.zeros(max(n, 1), dtype=np.uintp)
+        ne, no = C.c_size_t(0), C.c_size_t(0)
+        szp = C.POINTER(C.c_size_t)
+        self._check(self._L.tloam_b200_extract_edge(self._h, sensor_model, ring_min_num, _dp(a), _dp(it), n, e.ctypes.data_as(szp),
+                                                    C.byref(ne), o.ctypes.data_as(szp), C.byref(no)), "extract_edge")
+        return dict(edge=e[:ne.value].copy(), non_edge=o[:no.value].copy())
+
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):
         n = C.c_size_t(0)
