@@ -244,7 +244,7 @@ enum {
   TLOAM_B200_K_MAP_SCATTER, TLOAM_B200_K_STAGE_SOURCE, TLOAM_B200_K_BEGIN_FRAME, TLOAM_B200_K_CORRESPOND,
   TLOAM_B200_K_EVAL_FIRST, TLOAM_B200_K_EVAL, TLOAM_B200_K_SUBMAP, TLOAM_B200_K_FEATURE, TLOAM_B200_K_FIRST,
   TLOAM_B200_K_DENSE_BIN, TLOAM_B200_K_DENSE, TLOAM_B200_K_FITNESS, TLOAM_B200_K_GROUND, TLOAM_B200_K_MAP_FINE,
-  TLOAM_B200_K_FINE, TLOAM_B200_K_EDGE, TLOAM_B200_K_COUNT
+  TLOAM_B200_K_FINE, TLOAM_B200_K_EDGE, TLOAM_B200_K_OBJECT, TLOAM_B200_K_COUNT
 };
 typedef struct tloam_b200_profile {
   long long launches[TLOAM_B200_K_COUNT];
@@ -353,6 +353,32 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
  * A sector with more than 4096 curvature values (a beam with more than 24 586 points) is rejected: INVALID_ARG. */
 int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min_num, const double* xyz, const double* intensity,
                             size_t n, size_t* edge_index, size_t* n_edge, size_t* non_edge_index, size_t* n_non_edge);
+
+/* ---- "next" row (f)-4, third part: object segmentation = Dynamic Curved-Voxel Clustering of the non-ground points,
+ * Segmentation::objectSegmentation (ref: src/models/segmentation/segmentation.cpp:1085-1112) and what it calls:
+ * convertToPolar (:790-837), getPolarIndex (:777-784), createHashTable (:843-874), searchKNN (:886-908), DCVC (:915-990),
+ * labelAnalysis (:998-1025), colorSegmentation (:1032-1078).  The sequential labelling is replayed exactly (see
+ * tloam_b200/csrc/object_segment.cuh); integer outputs are bit-exact against oracle/segmentation_oracle.cpp given the
+ * same polar triples, the triples themselves agree with libm's asin / atan2 to <= 2 ulp. */
+typedef struct tloam_dcvc_config {      /* ref: config/mapping/segmentation.yaml (DCVC: / velodyne:) */
+  double start_r, delta_r, delta_p, delta_a;   /* 0.35, 0.0004, 1.2, 1.2 */
+  int min_seg;                                 /* 80: classes with <= min_seg points are filtered out */
+  double sensor_min_range, sensor_max_range;   /* 1.0, 120.0 */
+  /* the members minPitch / maxPitch / minPolar / maxPolar before the scan: resetParams() leaves 0.0
+   * (segmentation.cpp:1121-1123); on the very first frame the polar pair is 5.0 (segmentation.hpp:332-333) */
+  double min_pitch_init, max_pitch_init, min_polar_init, max_polar_init;
+} tloam_dcvc_config;
+void tloam_b200_dcvc_default_config(tloam_dcvc_config* c);
+/* xyz: the object scan (HOST, n x 3 FP64, finite).  seg_index (capacity n): indices of the reference's segmented_scan,
+ * cluster after cluster (size descending; equal sizes by smallest point index -- the reference leaves that to
+ * unordered_map order), index order inside a cluster; sizes (capacity n) / boxes (capacity n x 6: centre xyz,
+ * dimensions xyz) per cluster.  Optional outputs: root (n): smallest point index of the point's DCVC class (a canonical
+ * form of label_info); cluster (n): 1-based cluster number, 0 = filtered; voxel (n): the reference's voxelIndex;
+ * polar (3 n + 4): range / pitch / azimuth triples followed by minPitch, maxPitch, minPolar, maxPolar.
+ * More than 4096 polar rings (the default configuration has ~500 at 120 m): INVALID_ARG. */
+int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config* cfg, const double* xyz, size_t n,
+                                   size_t* seg_index, size_t* n_seg, int* n_clusters, int* sizes, double* boxes, int* root,
+                                   int* cluster, int* voxel, double* polar);
 
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);

@@ -48,6 +48,14 @@ class SubmapConfig(C.Structure):
                 ("edge_crop_box_length", C.c_double), ("ground_crop_box_length", C.c_double)]
 
 
+class DcvcConfig(C.Structure):
+    """oracle_dcvc_config (ref: config/mapping/segmentation.yaml DCVC + velodyne ranges)."""
+    _fields_ = [("start_r", C.c_double), ("delta_r", C.c_double), ("delta_p", C.c_double), ("delta_a", C.c_double),
+                ("min_seg", C.c_int), ("sensor_min_range", C.c_double), ("sensor_max_range", C.c_double),
+                ("min_pitch_init", C.c_double), ("max_pitch_init", C.c_double), ("min_polar_init", C.c_double),
+                ("max_polar_init", C.c_double)]
+
+
 class GroundConfig(C.Structure):
     """oracle_ground_config (ref: config/mapping/segmentation.yaml)."""
     _fields_ = [("sensor_model", C.c_int), ("sensor_height", C.c_double), ("vertical_res", C.c_double), ("init_angle", C.c_double),
@@ -164,6 +172,10 @@ def lib():
         L.oracle_ground_extract.restype = C.c_int
         L.oracle_extract_edge.argtypes = [dp, dp, C.c_size_t, C.c_int, C.c_int, C.c_int, szp, szp, szp, szp]
         L.oracle_extract_edge.restype = C.c_int
+        L.oracle_dcvc_default_config.argtypes = [C.POINTER(DcvcConfig)]
+        L.oracle_dcvc_polar.argtypes = [dp, C.c_size_t, C.POINTER(DcvcConfig), dp, dp]
+        L.oracle_dcvc_from_polar.argtypes = [dp, dp, dp, C.c_size_t, C.POINTER(DcvcConfig), C.c_int, ip, ip, ip, szp, szp, ip, ip, dp]
+        L.oracle_dcvc_from_polar.restype = C.c_int
         _lib = L
     return _lib
 
@@ -495,3 +507,57 @@ def extract_edge(pts, intensity, sensor_model=64, ring_min_num=16, max_section=4
     if rc != 0:
         return None
     return dict(edge=e[:ne.value].copy(), non_edge=o[:no.value].copy())
+
+
+def dcvc_config(**overrides):
+    c = DcvcConfig()
+    lib().oracle_dcvc_default_config(C.byref(c))
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+def dcvc_polar(pts, **overrides):
+    """convertToPolar's triples (range, pitch deg, azimuth deg; zeros for out-of-range points) and the 4 extrema."""
+    a = _f64(pts).reshape(-1, 3)
+    n = a.shape[0]
+    c = dcvc_config(**overrides)
+    polar = np.zeros((max(n, 1), 3))
+    ext = np.zeros(4)
+    lib().oracle_dcvc_polar(_dp(a), n, C.byref(c), _dp(polar), _dp(ext))
+    return polar[:n], ext
+
+
+def dcvc_from_polar(pts, polar, ext, max_bounds=0, **overrides):
+    """createHashTable + DCVC + labelAnalysis + colorSegmentation on given polar triples (literal restatement).  Returns
+    dict(voxel, root, cluster, segmented, sizes, boxes) or None if polarNum exceeds max_bounds."""
+    a = _f64(pts).reshape(-1, 3)
+    n = a.shape[0]
+    pol = _f64(polar).reshape(-1, 3)
+    if n == 0:
+        pol = np.zeros((1, 3))
+    ex = _f64(ext).reshape(4)
+    c = dcvc_config(**overrides)
+    szp, ip = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+    m = max(n, 1)
+    voxel, root, cluster, sizes = (np.zeros(m, dtype=np.int32) for _ in range(4))
+    seg = np.zeros(m, dtype=np.uintp)
+    boxes = np.zeros((m, 6))
+    nseg, ncl = C.c_size_t(0), C.c_int(0)
+    rc = lib().oracle_dcvc_from_polar(_dp(a), _dp(pol), _dp(ex), n, C.byref(c), max_bounds, voxel.ctypes.data_as(ip),
+                                      root.ctypes.data_as(ip), cluster.ctypes.data_as(ip), seg.ctypes.data_as(szp), C.byref(nseg),
+                                      C.byref(ncl), sizes.ctypes.data_as(ip), _dp(boxes))
+    if rc != 0:
+        return None
+    k = ncl.value
+    return dict(voxel=voxel[:n].copy(), root=root[:n].copy(), cluster=cluster[:n].copy(), segmented=seg[:nseg.value].copy(),
+                sizes=sizes[:k].copy(), boxes=boxes[:k].copy())
+
+
+def dcvc(pts, max_bounds=0, **overrides):
+    """Segmentation::objectSegmentation restated.  dict(polar, ext, voxel, root, cluster, segmented, sizes, boxes)."""
+    polar, ext = dcvc_polar(pts, **overrides)
+    r = dcvc_from_polar(pts, polar, ext, max_bounds=max_bounds, **overrides)
+    if r is not None:
+        r["polar"], r["ext"] = polar, ext
+    return r

@@ -363,3 +363,183 @@ extern "C" int oracle_extract_edge(const double* pts, const double* intensity, s
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Object segmentation: Dynamic Curved-Voxel Clustering (ref: segmentation.cpp:772-1112: getPolarIndex, convertToPolar,
+// createHashTable, searchKNN, DCVC, labelAnalysis, colorSegmentation, objectSegmentation).  LITERAL restatement: the
+// label vector is relabelled by full sweeps exactly like the reference (`for (auto& seg : label_info)`), the hash table
+// is an unordered_map from the reference's integer voxel index to the point list.  Kept literally:
+//   * min/max pitch and polar start from the member values left by resetParams (0.0; 5.0 for the polar pair on the very
+//     first frame, segmentation.hpp:330-333) -> cfg.{min,max}_{pitch,polar}_init;
+//   * points outside (sensorMinRange, sensorMaxRange) keep the value-initialised polar triple (0, 0, 0) and are still
+//     hashed and clustered (polarCor.resize leaves Eigen vectors uninitialised in the reference: zero here);
+//   * searchKNN: pitch layers > height and polar rings > polarNum are skipped, azimuth -1 wraps to width - 1 but
+//     azimuth > 300 is CLAMPED to the literal 300 (so a voxel can be listed twice, and a voxel in pitch layer height + 1
+//     is not its own neighbour);
+//   * DCVC visits only points that are still unlabelled; neighbours seen before the first labelled one stay unlabelled.
+// Fixed where the reference leaves the order to the implementation (std::sort over unordered_map iteration order):
+// clusters of equal size are ordered by their smallest point index.  Trigonometry is libm's (std::asin, std::atan2);
+// oracle_dcvc_from_polar takes the polar triples as input so that the integer part can be checked bit-exactly whatever
+// the last bit of asin / atan2 is.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <unordered_map>
+#include <limits>
+
+extern "C" {
+
+void oracle_dcvc_default_config(oracle_dcvc_config* c) {   // ref: config/mapping/segmentation.yaml
+  c->start_r = 0.35; c->delta_r = 0.0004; c->delta_p = 1.2; c->delta_a = 1.2; c->min_seg = 80;
+  c->sensor_min_range = 1.0; c->sensor_max_range = 120.0;
+  c->min_pitch_init = 0.0; c->max_pitch_init = 0.0; c->min_polar_init = 0.0; c->max_polar_init = 0.0;
+}
+
+// convertToPolar, first half (:790-822): polar triples + the four extrema.  polar: [n][3]; ext: minPitch, maxPitch, minPolar, maxPolar
+void oracle_dcvc_polar(const double* pts, size_t n, const oracle_dcvc_config* c, double* polar, double* ext) {
+  double min_pitch = c->min_pitch_init, max_pitch = c->max_pitch_init, min_polar = c->min_polar_init, max_polar = c->max_polar_init;
+  for (size_t i = 0; i < n; ++i) {
+    const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    const double r = std::sqrt((x * x + y * y) + z * z);                              // cur.norm()
+    const double pitch = std::asin(z / r) * 180.0 / M_PI;
+    const double angle = std::atan2(y, x);
+    const double az = angle > 0.0 ? angle * 180 / M_PI : (angle + 2 * M_PI) * 180 / M_PI;
+    polar[3 * i] = polar[3 * i + 1] = polar[3 * i + 2] = 0.0;
+    if (r >= c->sensor_max_range || r <= c->sensor_min_range) continue;                // :808-809
+    min_pitch = pitch < min_pitch ? pitch : min_pitch;
+    max_pitch = pitch > max_pitch ? pitch : max_pitch;
+    min_polar = r < min_polar ? r : min_polar;
+    max_polar = r > max_polar ? r : max_polar;
+    polar[3 * i] = r; polar[3 * i + 1] = pitch; polar[3 * i + 2] = az;
+  }
+  ext[0] = min_pitch; ext[1] = max_pitch; ext[2] = min_polar; ext[3] = max_polar;
+}
+
+// everything after the trigonometry.  root[i] = smallest point index of i's DCVC class (a canonical form of label_info);
+// cluster[i] = 1-based position of i's class in labelRecords, 0 if the class has <= minSeg points; seg_index = the
+// segmented scan (indices, cluster by cluster); sizes / boxes: [n_clusters], [n_clusters][6] (centre xyz, dimensions xyz).
+// Returns 0; -1 if polarNum exceeds max_bounds (device limit mirrored; <= 0: no limit).
+int oracle_dcvc_from_polar(const double* pts, const double* polar, const double* ext, size_t n_, const oracle_dcvc_config* c,
+                           int max_bounds, int* voxel, int* root, int* cluster, size_t* seg_index, size_t* n_seg, int* n_clusters,
+                           int* sizes, double* boxes) {
+  const int n = (int)n_;
+  *n_seg = 0; *n_clusters = 0;
+  if (n == 0) return 0;
+  const double min_pitch = ext[0], max_pitch = ext[1], min_polar = ext[2], max_polar = ext[3];
+  // convertToPolar, second half (:825-836)
+  int polar_num = 0;
+  std::vector<double> bounds;
+  const int width = (int)(std::round(360.0 / c->delta_a) + 1);
+  const int height = (int)((max_pitch - min_pitch) / c->delta_p);
+  {
+    double range = min_polar;
+    int step = 1;
+    while (range <= max_polar) {
+      range += (c->start_r - step * c->delta_r);
+      bounds.push_back(range);
+      polar_num++, step++;
+      if (max_bounds > 0 && polar_num > max_bounds) return -1;
+      if (polar_num > (1 << 24)) return -1;                                              // non-terminating configuration
+    }
+  }
+  auto polar_index = [&](double radius) {                                                // :777-784
+    for (int r = 0; r < polar_num; ++r)
+      if (radius < bounds[(size_t)r]) return r;
+    return polar_num - 1;
+  };
+  // createHashTable (:843-874)
+  std::unordered_map<int, std::vector<int>> voxel_map;
+  std::vector<int> pi((size_t)n), ti((size_t)n), ai((size_t)n), vi((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    pi[(size_t)i] = polar_index(polar[3 * i]);
+    ti[(size_t)i] = (int)std::round((polar[3 * i + 1] - min_pitch) / c->delta_p);
+    ai[(size_t)i] = (int)std::round(polar[3 * i + 2] / c->delta_a);
+    vi[(size_t)i] = (ai[(size_t)i] * (polar_num + 1) + pi[(size_t)i]) + ti[(size_t)i] * (polar_num + 1) * (width + 1);
+    voxel_map[vi[(size_t)i]].push_back(i);
+    if (voxel) voxel[i] = vi[(size_t)i];
+  }
+  // DCVC (:915-990)
+  std::vector<int> label((size_t)n, -1);
+  int label_count = 0;
+  std::vector<int> knn, neighbors;
+  for (int i = 0; i < n; ++i) {
+    if (label[(size_t)i] != -1) continue;
+    knn.clear(); neighbors.clear();
+    const int p = pi[(size_t)i], t = ti[(size_t)i], a = ai[(size_t)i];
+    for (int z = t - 1; z <= t + 1; ++z) {                                               // searchKNN (:886-908)
+      if (z < 0 || z > height) continue;
+      for (int y = p - 1; y <= p + 1; ++y) {
+        if (y < 0 || y > polar_num) continue;
+        for (int x = a - 1; x <= a + 1; ++x) {
+          int ax = x;
+          if (ax < 0) ax = width - 1;
+          if (ax > 300) ax = 300;
+          knn.push_back((ax * (polar_num + 1) + y) + z * (polar_num + 1) * (width + 1));
+        }
+      }
+    }
+    for (int k : knn) {
+      auto it = voxel_map.find(k);
+      if (it != voxel_map.end()) neighbors.insert(neighbors.end(), it->second.begin(), it->second.end());
+    }
+    for (int id : neighbors) {                                                           // :952-968
+      const int curr = label[(size_t)i], neigh = label[(size_t)id];
+      if (curr != -1 && neigh != -1 && curr != neigh) {
+        for (int& seg : label)
+          if (seg == curr) seg = neigh;
+      } else if (neigh != -1) {
+        label[(size_t)i] = neigh;
+      } else if (curr != -1) {
+        label[(size_t)id] = curr;
+      }
+    }
+    if (label[(size_t)i] == -1) {                                                        // :972-978
+      label_count++;
+      label[(size_t)i] = label_count;
+      for (int id : neighbors) label[(size_t)id] = label_count;
+    }
+  }
+  // labelAnalysis (:998-1025) with the tie rule of the header
+  std::unordered_map<int, std::vector<int>> hist;
+  for (int i = 0; i < n; ++i) hist[label[(size_t)i]].push_back(i);
+  if (root)
+    for (auto& kv : hist)
+      for (int i : kv.second) root[i] = kv.second.front();
+  std::vector<const std::vector<int>*> recs;
+  for (auto& kv : hist) recs.push_back(&kv.second);
+  std::sort(recs.begin(), recs.end(), [](const std::vector<int>* a, const std::vector<int>* b) {
+    return a->size() > b->size() || (a->size() == b->size() && a->front() < b->front());
+  });
+  if (cluster) std::fill(cluster, cluster + n, 0);
+  int count = 0;
+  for (const std::vector<int>* rec : recs) {
+    if (!((int)rec->size() > c->min_seg)) continue;                                      // :1016
+    // colorSegmentation (:1032-1078)
+    double mn[3] = {std::numeric_limits<double>::max(), std::numeric_limits<double>::max(), std::numeric_limits<double>::max()};
+    double mx[3] = {-std::numeric_limits<double>::max(), -std::numeric_limits<double>::max(), -std::numeric_limits<double>::max()};
+    for (int id : *rec) {
+      seg_index[(*n_seg)++] = (size_t)id;
+      if (cluster) cluster[id] = count + 1;
+      for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], pts[3 * id + d]); mx[d] = std::max(mx[d], pts[3 * id + d]); }
+    }
+    if (sizes) sizes[count] = (int)rec->size();
+    if (boxes)
+      for (int d = 0; d < 3; ++d) {
+        const double len = mx[d] - mn[d];
+        boxes[6 * count + d] = mn[d] + len / 2.0;
+        boxes[6 * count + 3 + d] = len < 0 ? -1 * len : len;
+      }
+    ++count;
+  }
+  *n_clusters = count;
+  return 0;
+}
+
+int oracle_dcvc(const double* pts, size_t n, const oracle_dcvc_config* c, int max_bounds, double* polar_out, int* voxel, int* root,
+                int* cluster, size_t* seg_index, size_t* n_seg, int* n_clusters, int* sizes, double* boxes) {
+  std::vector<double> polar(3 * n + 3);
+  double ext[4];
+  oracle_dcvc_polar(pts, n, c, polar.data(), ext);
+  if (polar_out) { std::memcpy(polar_out, polar.data(), sizeof(double) * 3 * n); std::memcpy(polar_out + 3 * n, ext, sizeof(ext)); }
+  return oracle_dcvc_from_polar(pts, polar.data(), ext, n, c, max_bounds, voxel, root, cluster, seg_index, n_seg, n_clusters, sizes, boxes);
+}
+
+}  // extern "C"

@@ -218,6 +218,23 @@ int oracle_ground_extract(const double* pts, size_t n, const oracle_ground_confi
 int oracle_extract_edge(const double* pts, const double* intensity, size_t n, int sensor_model, int ring_min_num, int max_section,
                         size_t* edge_index, size_t* n_edge, size_t* non_edge_index, size_t* n_non_edge);
 
+/* Segmentation::objectSegmentation = Dynamic Curved-Voxel Clustering (ref: src/models/segmentation/segmentation.cpp:772-1112;
+ * config/mapping/segmentation.yaml DCVC + velodyne ranges).  Literal restatement, see segmentation_oracle.cpp. */
+typedef struct oracle_dcvc_config {
+  double start_r, delta_r, delta_p, delta_a;   /* 0.35, 0.0004, 1.2, 1.2 */
+  int min_seg;                                 /* 80 */
+  double sensor_min_range, sensor_max_range;   /* 1.0, 120.0 */
+  double min_pitch_init, max_pitch_init, min_polar_init, max_polar_init;   /* member values left by resetParams: 0 (polar: 5.0 on the first frame) */
+} oracle_dcvc_config;
+void oracle_dcvc_default_config(oracle_dcvc_config* c);
+void oracle_dcvc_polar(const double* pts, size_t n, const oracle_dcvc_config* c, double* polar, double* ext);
+int oracle_dcvc_from_polar(const double* pts, const double* polar, const double* ext, size_t n, const oracle_dcvc_config* c,
+                           int max_bounds, int* voxel, int* root, int* cluster, size_t* seg_index, size_t* n_seg, int* n_clusters,
+                           int* sizes, double* boxes);
+/* polar_out (optional): [n][3] triples followed by the 4 extrema */
+int oracle_dcvc(const double* pts, size_t n, const oracle_dcvc_config* c, int max_bounds, double* polar_out, int* voxel, int* root,
+                int* cluster, size_t* seg_index, size_t* n_seg, int* n_clusters, int* sizes, double* boxes);
+
 #ifdef __cplusplus
 }
 #endif

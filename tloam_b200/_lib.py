@@ -66,7 +66,7 @@ class Stats(C.Structure):
 
 
 KERNEL_CLASSES = ("map_bbox", "map_origin", "map_insert", "map_offsets", "map_scatter", "stage_source",
-                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense", "fitness", "ground", "map_fine", "fine", "edge")
+                  "begin_frame", "correspond", "eval_first", "eval", "submap", "feature", "first", "dense_bin", "dense", "fitness", "ground", "map_fine", "fine", "edge", "object")
 
 
 class FeatureConfig(C.Structure):
@@ -75,6 +75,14 @@ class FeatureConfig(C.Structure):
                 ("sphere_num", C.c_int), ("cvr_scan", C.c_double), ("cvr_submap", C.c_double),
                 ("planar_scan_thres", C.c_double), ("planar_submap_thres", C.c_double),
                 ("planar_vertic_thres", C.c_double)]
+
+
+class DcvcConfig(C.Structure):
+    """tloam_dcvc_config (ref: config/mapping/segmentation.yaml DCVC + velodyne ranges)."""
+    _fields_ = [("start_r", C.c_double), ("delta_r", C.c_double), ("delta_p", C.c_double), ("delta_a", C.c_double),
+                ("min_seg", C.c_int), ("sensor_min_range", C.c_double), ("sensor_max_range", C.c_double),
+                ("min_pitch_init", C.c_double), ("max_pitch_init", C.c_double), ("min_polar_init", C.c_double),
+                ("max_polar_init", C.c_double)]
 
 
 class GroundConfig(C.Structure):
@@ -109,7 +117,7 @@ EXPORTS = [
     "tloam_b200_batch_set_profiling", "tloam_b200_batch_get_profile",
     "tloam_b200_submap_update_chained", "tloam_b200_set_frame_fitness", "tloam_b200_get_frame_fitness",
     "tloam_b200_set_async_inputs", "tloam_b200_wait_stream", "tloam_b200_dense_check_counters",
-    "tloam_b200_ground_default_config", "tloam_b200_ground_extract", "tloam_b200_extract_edge", "tloam_b200_map_layout_bytes",
+    "tloam_b200_ground_default_config", "tloam_b200_ground_extract", "tloam_b200_extract_edge", "tloam_b200_dcvc_default_config", "tloam_b200_object_segmentation", "tloam_b200_map_layout_bytes",
     "tloam_b200_map_send_buffer", "tloam_b200_map_recv_buffer", "tloam_b200_map_adopt", "tloam_b200_signal_stream",
 ]
 
@@ -217,6 +225,9 @@ def load():
     L.tloam_b200_ground_default_config.restype = None
     L.tloam_b200_ground_extract.argtypes = [vp, C.POINTER(GroundConfig), dp, C.c_size_t, szp, szp, szp, szp, ip, ip, dp, dp]
     L.tloam_b200_extract_edge.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_size_t, szp, szp, szp, szp]
+    L.tloam_b200_dcvc_default_config.argtypes = [C.POINTER(DcvcConfig)]
+    L.tloam_b200_dcvc_default_config.restype = None
+    L.tloam_b200_object_segmentation.argtypes = [vp, C.POINTER(DcvcConfig), dp, C.c_size_t, szp, szp, ip, ip, dp, ip, ip, ip, dp]
     L.tloam_b200_batch_get_profile.argtypes = [vp, C.POINTER(Profile)]
     _lib = L
     return L

@@ -20,6 +20,7 @@
 #include "feature_extract.cuh"
 #include "ground_extract.cuh"
 #include "edge_extract.cuh"
+#include "object_segment.cuh"
 
 
 
@@ -2268,6 +2269,131 @@ int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min
   if (tot[1]) CU_TRY(cudaMemcpyAsync(non_edge_index, a.out_non, tot[1] * sizeof(size_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
   *n_edge = tot[0]; *n_non_edge = tot[1];
+  return TLOAM_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "next" row (f)-4, third part: object segmentation = DCVC (object_segment.cuh)
+// ---------------------------------------------------------------------------------------------
+void tloam_b200_dcvc_default_config(tloam_dcvc_config* c) {                  // ref: config/mapping/segmentation.yaml
+  if (!c) return;
+  c->start_r = 0.35; c->delta_r = 0.0004; c->delta_p = 1.2; c->delta_a = 1.2; c->min_seg = 80;
+  c->sensor_min_range = 1.0; c->sensor_max_range = 120.0;
+  c->min_pitch_init = 0.0; c->max_pitch_init = 0.0; c->min_polar_init = 0.0; c->max_polar_init = 0.0;
+}
+
+int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config* cfg, const double* xyz, size_t n,
+                                   size_t* seg_index, size_t* n_seg, int* n_clusters, int* sizes, double* boxes, int* root,
+                                   int* cluster, int* voxel, double* polar) {
+  if (!h || !cfg || !seg_index || !n_seg || !n_clusters) return TLOAM_B200_ERR_INVALID_ARG;
+  *n_seg = 0; *n_clusters = 0;
+  if (!(cfg->delta_p > 0.0) || !(cfg->delta_a > 0.0)) return TLOAM_B200_ERR_INVALID_ARG;
+  if (n == 0) return TLOAM_B200_OK;                                         // ref: :1088-1093 (nothing to convert)
+  if (!xyz || n > ((size_t)1 << 26)) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  OsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = (unsigned)n; a.nchunk = (unsigned)((n + kOsChunk - 1) / kOsChunk);
+  a.start_r = cfg->start_r; a.delta_r = cfg->delta_r; a.delta_p = cfg->delta_p; a.delta_a = cfg->delta_a;
+  a.min_range = cfg->sensor_min_range; a.max_range = cfg->sensor_max_range; a.min_seg = cfg->min_seg;
+  a.init[0] = cfg->min_pitch_init; a.init[1] = cfg->max_pitch_init; a.init[2] = cfg->min_polar_init; a.init[3] = cfg->max_polar_init;
+  size_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;
+  a.cap_mask = (unsigned)(cap - 1);
+  const size_t n32 = round_up(n, 32);
+  const size_t state_words = (n + 15) / 16 + 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
+  const size_t o_pts = take(n * 24), o_pol = take(n * 24), o_enc = take(64), o_ext = take(64), o_par = take(64),
+               o_bnd = take(kOsMaxBounds * 8), o_key = take(n * 4), o_crd = take(n * 12), o_tab = take(cap * 8), o_sv = take(cap * 4),
+               o_ps = take(n * 4), o_vid = take(n * 4), o_f1 = take(n * 4), o_f2 = take(n * 4), o_vc = take(n * 12),
+               o_ek = take(n * 4), o_ept = take(n * 4), o_ei = take(n32 * 4), o_rows = take(n32 * kOsRow * 4), o_ep = take(n32),
+               o_stg = take(state_words * 4), o_par2 = take(n * 4), o_root = take(n * 4), o_cnt = take(n * 4), o_clr = take(n * 4),
+               o_crr = take(n * 4), o_cl = take(n * 4), o_sz = take(n * 4), o_pk = take(n * 4), o_box = take(n * 48),
+               o_cc = take((size_t)a.nchunk * kOsKeys * 4), o_kb = take((kOsKeys + 1) * 4), o_pa = take(n * 4), o_pb = take(n * 4),
+               o_seg = take(n * 8);
+  if (off > h->cap_ge) {                                                   // shares the segmentation arena
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_ge); h->d_ge = nullptr; h->cap_ge = 0;
+    CU_TRY(cudaMalloc(&h->d_ge, off + off / 4));
+    h->cap_ge = off + off / 4;
+  }
+  unsigned char* b = h->d_ge;
+  a.pts = (const double*)(b + o_pts); a.polar = (double*)(b + o_pol); a.ext_enc = (unsigned long long*)(b + o_enc);
+  a.ext = (double*)(b + o_ext); a.params = (int*)(b + o_par); a.bounds = (double*)(b + o_bnd); a.key = (int*)(b + o_key);
+  a.coord = (int*)(b + o_crd); a.table = (unsigned long long*)(b + o_tab); a.slot_vid = (int*)(b + o_sv); a.pslot = (int*)(b + o_ps);
+  a.vid = (int*)(b + o_vid); a.f1 = (int*)(b + o_f1); a.f2 = (int*)(b + o_f2); a.vcoord = (int*)(b + o_vc); a.evkey = (int*)(b + o_ek);
+  a.ev_pt = (int*)(b + o_ept); a.ev_info = (int*)(b + o_ei); a.rows = (int*)(b + o_rows); a.ev_p = (signed char*)(b + o_ep);
+  a.state_g = (unsigned*)(b + o_stg); a.parent = (int*)(b + o_par2); a.root = (int*)(b + o_root); a.cnt = (int*)(b + o_cnt);
+  a.cl_root = (int*)(b + o_clr); a.cl_rank_of_root = (int*)(b + o_crr); a.cluster = (int*)(b + o_cl); a.sizes = (int*)(b + o_sz);
+  a.pkey = (int*)(b + o_pk); a.boxes = (double*)(b + o_box); a.chunk_cnt = (unsigned*)(b + o_cc); a.key_base = (unsigned*)(b + o_kb);
+  a.perm_a = (int*)(b + o_pa); a.perm_b = (int*)(b + o_pb); a.out_seg = (unsigned long long*)(b + o_seg);
+  const size_t seq_fixed = 2 * 32 * kOsRow * sizeof(int);
+  const int use_smem = seq_fixed + state_words * 4 <= (size_t)kOsSeqSmemBytes ? 1 : 0;
+  const size_t seq_smem = seq_fixed + (use_smem ? state_words * 4 : 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(cudaFuncSetAttribute(k_os_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSeqSmemBytes));
+    attr_set = true;
+  }
+  cudaStream_t st = h->stream;
+  CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemsetAsync(b + o_tab, 0, cap * 8, st));
+  if (!use_smem) CU_TRY(cudaMemsetAsync(b + o_stg, 0, state_words * 4, st));
+  const unsigned ev_blocks = (unsigned)((n32 * 32 + 255) / 256);
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_init<<<1, 32, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_polar<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_bounds<<<1, 32, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_key<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_vid<<<(unsigned)(cap / 256), 256, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_first<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_second<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_evkey<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  auto partition = [&](const int* keys, const int* perm_in, int* perm_out, const int* n_items, int shift, int* total_out) {
+    OsPart p;
+    p.keys = keys; p.perm_in = perm_in; p.perm_out = perm_out; p.n_items = n_items; p.n_fixed = a.n; p.shift = shift;
+    p.chunk_cnt = a.chunk_cnt; p.key_base = a.key_base; p.nchunk = a.nchunk; p.total_out = total_out;
+    TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_part_hist<<<a.nchunk, kOsChunk, 0, st>>>(p)));
+    TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_part_scan<<<1, kOsKeys, 0, st>>>(p)));
+    TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_part_scatter<<<a.nchunk, kOsChunk, 0, st>>>(p)));
+    return 0;
+  };
+  partition(a.evkey, nullptr, a.ev_pt, nullptr, 0, a.params + 5);          // events in point order
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_rows<<<ev_blocks, 256, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_seq<<<1, 32, seq_smem, st>>>(a, use_smem)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_union<<<ev_blocks, 256, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_label<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_clusters<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  const size_t cl_bound = cfg->min_seg >= 0 ? n / ((size_t)cfg->min_seg + 1) + 1 : n;   // classes with > min_seg points
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_rank<<<(unsigned)((cl_bound + 255) / 256), 256, 0, st>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_pkey<<<a.nchunk, kOsChunk, 0, st>>>(a)));
+  partition(a.pkey, nullptr, a.perm_a, nullptr, 0, a.params + 7);           // stable LSD partition by cluster rank
+  const int* seg = a.perm_a;
+  if (cl_bound > 256) { partition(a.pkey, a.perm_a, a.perm_b, a.params + 7, 8, nullptr); seg = a.perm_b; }
+  if (cl_bound > 65536) { partition(a.pkey, a.perm_b, a.perm_a, a.params + 7, 16, nullptr); seg = a.perm_a; }
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_boxes<<<(unsigned)cl_bound, 256, 0, st>>>(a, seg)));
+  CU_TRY(cudaGetLastError());
+  int par[8];
+  CU_TRY(cudaMemcpyAsync(par, a.params, sizeof(par), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (par[3] != 0) {
+    snprintf(h->last_error, sizeof(h->last_error), "object_segmentation: more than %d polar rings", kOsMaxBounds);
+    return TLOAM_B200_ERR_INVALID_ARG;
+  }
+  static_assert(sizeof(size_t) == sizeof(unsigned long long), "index lists are copied straight into size_t arrays");
+  const size_t nc = (size_t)par[6], ns = (size_t)par[7];
+  if (ns) CU_TRY(cudaMemcpyAsync(seg_index, a.out_seg, ns * sizeof(size_t), cudaMemcpyDeviceToHost, st));
+  if (sizes && nc) CU_TRY(cudaMemcpyAsync(sizes, a.sizes, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (boxes && nc) CU_TRY(cudaMemcpyAsync(boxes, a.boxes, nc * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (root) CU_TRY(cudaMemcpyAsync(root, a.root, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (cluster) CU_TRY(cudaMemcpyAsync(cluster, a.cluster, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (voxel) CU_TRY(cudaMemcpyAsync(voxel, a.key, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (polar) {
+    CU_TRY(cudaMemcpyAsync(polar, a.polar, n * 24, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(polar + 3 * n, a.ext, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CU_TRY(cudaStreamSynchronize(st));
+  *n_seg = ns; *n_clusters = (int)nc;
   return TLOAM_B200_OK;
 }
 
