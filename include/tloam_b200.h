@@ -359,7 +359,7 @@ int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min
  * convertToPolar (:790-837), getPolarIndex (:777-784), createHashTable (:843-874), searchKNN (:886-908), DCVC (:915-990),
  * labelAnalysis (:998-1025), colorSegmentation (:1032-1078).  The sequential labelling is replayed exactly (see
  * tloam_b200/csrc/object_segment.cuh); integer outputs are bit-exact against oracle/segmentation_oracle.cpp given the
- * same polar triples, the triples themselves agree with libm's asin / atan2 to <= 2 ulp. */
+ * same polar triples, the triples themselves agree with libm's to <= 4 ulp. */
 typedef struct tloam_dcvc_config {      /* ref: config/mapping/segmentation.yaml (DCVC: / velodyne:) */
   double start_r, delta_r, delta_p, delta_a;   /* 0.35, 0.0004, 1.2, 1.2 */
   int min_seg;                                 /* 80: classes with <= min_seg points are filtered out */

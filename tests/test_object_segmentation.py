@@ -3,7 +3,7 @@ src/models/segmentation/segmentation.cpp:772-1112).
 
 * the LITERAL oracle (label vector relabelled by full sweeps, unordered_map of point lists) against `structural_dcvc`, an
   independent voxel-level restatement (labelled-prefix states + events + union-find) -- the model the device executes;
-* the device path against the oracle: polar triples within 2 ulp of libm's (libdevice asin / atan2), every integer
+* the device path against the oracle: polar triples within 4 ulp of libm's (libdevice asin / atan2, then the conversion to degrees), every integer
   output (voxel index, classes, cluster numbers, segmented scan, sizes) bit-exact, boxes bit-exact."""
 import numpy as np
 import pytest
@@ -186,10 +186,11 @@ def check_gpu_against_oracle(oracle, reg, p, **kw):
     g = reg.object_segmentation(p, **kw)
     o = oracle.dcvc(p, **kw)
     if len(p):
-        # trigonometry: libdevice vs libm, tolerance 2 ulp (range is sqrt of the same sums: exact)
+        # trigonometry: libdevice's asin / atan2 are within 2 ulp of libm's; the conversion to degrees (x 180, / pi) can
+        # stretch that across a binade boundary: tolerance 4 ulp on the triples (range is sqrt of the same sums: exact)
         assert np.array_equal(g["polar"][:, 0], o["polar"][:, 0])
-        assert ulp_diff(g["polar"][:, 1:], o["polar"][:, 1:]).max() <= 2
-        assert ulp_diff(g["ext"], o["ext"]).max() <= 2
+        assert ulp_diff(g["polar"][:, 1:], o["polar"][:, 1:]).max() <= 4
+        assert ulp_diff(g["ext"], o["ext"]).max() <= 4
     # everything downstream of the triples: bit-exact against the literal oracle run on the DEVICE's triples ...
     o2 = oracle.dcvc_from_polar(p, g["polar"], g["ext"], **kw)
     for k in ("voxel", "root", "cluster", "segmented", "sizes", "boxes"):

@@ -20,7 +20,7 @@
 // recorded (event, entry >= p) pairs; class sizes, the size-ordered cluster table, a stable LSD partition of the points
 // by cluster rank (= the segmented scan, index order inside a cluster) and the bounding boxes.
 // Integer outputs are bit-exact against oracle/segmentation_oracle.cpp given the same polar triples; the triples use
-// libdevice's asin / atan2 (<= 2 ulp from libm's, tests state the tolerance), every other FP64 operation is spelled
+// libdevice's asin / atan2 (triples within 4 ulp of libm's after the conversion to degrees, tests state the tolerance), every other FP64 operation is spelled
 // with round-to-nearest intrinsics in the oracle's order.
 #pragma once
 #include <cuda_runtime.h>
