@@ -23,6 +23,7 @@ frame (ref: src/front_end/front_end.cpp:278-337).
 
 Informational keys besides the contract's: "stream_device_submap" ((f)-1: the map is maintained on the device, only
 the scan crosses PCIe), "feature_extraction" ((f)-2: PCA feature extraction of a 50k-point cloud, N = 1 only),
+"segmentation" ((f)-4: groundRemove -> DCVC -> edge extraction of a raw 116k-point scan, N = 1 only),
 "shared_map_broadcast" (N > 1).
 """
 import argparse
@@ -837,6 +838,51 @@ def main():
             feat["cpu_cores"] = os.cpu_count()
             feat["identical_to_cpu_port"] = bool(all(np.array_equal(a, b) for a, b in zip(fout, fref)))
 
+    # ---- (f)-4: segmentation front half of a raw 64-beam scan: groundRemove -> objectSegmentation (DCVC) -> extractEdgePoint
+    #      (informational; rank 0, N = 1 only).  Every stage is fed by the previous DEVICE stage through the C ABI. ----
+    segm = None
+    if rank == 0 and world == 1:
+        from tloam_b200 import synth
+        raw = torch.from_numpy(synth.raw_scan()).pin_memory().numpy()
+
+        def seg_chain(ground_extract, object_segmentation, extract_edge):
+            t = [time.perf_counter()]
+            ge = ground_extract(raw)
+            t.append(time.perf_counter())
+            opts = np.ascontiguousarray(raw[ge["object"]])
+            obeam = ge["beam"][ge["object"]].astype(np.float64)
+            t.append(time.perf_counter())
+            os_ = object_segmentation(opts)
+            t.append(time.perf_counter())
+            spts = np.ascontiguousarray(opts[os_["segmented"]])
+            sbeam = obeam[os_["segmented"]]
+            t.append(time.perf_counter())
+            ee = extract_edge(spts, sbeam, ring_min_num=131)
+            t.append(time.perf_counter())
+            d = np.diff(t) * 1e3
+            return (ge["ground"], ge["object"], os_["segmented"], os_["sizes"], ee["edge"], ee["non_edge"]), (d[0], d[2], d[4])
+
+        for _ in range(3):
+            sout, _ = seg_chain(reg.ground_extract, reg.object_segmentation, reg.extract_edge)
+        st = np.array([seg_chain(reg.ground_extract, reg.object_segmentation, reg.extract_edge)[1] for _ in range(10)])
+        sm = np.median(st, axis=0)
+        segm = {"points": int(raw.shape[0]), "object_points": int(len(sout[1])), "segmented_points": int(len(sout[2])),
+                "clusters": int(len(sout[3])), "edge_points": int(len(sout[4])), "general_points": int(len(sout[5])),
+                "gpu_ms_per_call": {"ground_extract": float(sm[0]), "object_segmentation": float(sm[1]), "extract_edge": float(sm[2]),
+                                    "total": float(sm.sum())},
+                "what": "tloam_b200_ground_extract -> tloam_b200_object_segmentation -> tloam_b200_extract_edge through the C ABI "
+                        "(host clouds in, host index lists out, copies and the Python gather between the stages not counted); median of 10"}
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle     # checker / CPU baseline leg only
+            pyoracle.build()
+            ct = np.array([seg_chain(pyoracle.ground_extract, pyoracle.dcvc, pyoracle.extract_edge)[1] for _ in range(3)])
+            cref, _ = seg_chain(pyoracle.ground_extract, pyoracle.dcvc, pyoracle.extract_edge)
+            cm = np.median(ct, axis=0)
+            segm["cpu_port_ms_per_call"] = {"ground_extract": float(cm[0]), "object_segmentation": float(cm[1]), "extract_edge": float(cm[2]),
+                                            "total": float(cm.sum())}
+            segm["cpu_threads"] = 1
+            segm["identical_to_cpu_port"] = bool(all(np.array_equal(a, b) for a, b in zip(sout, cref)))
+
     if rank == 0:
         fps = world * args.steps / (ms_dev * 1e-3)
         fps_e2e = world * args.steps / (ms_e2e * 1e-3)
@@ -864,6 +910,8 @@ def main():
             line["batched"] = batched
         if feat:
             line["feature_extraction"] = feat
+        if segm:
+            line["segmentation"] = segm
         if bcast:
             line["shared_map_broadcast"] = bcast
         if world > 1:

@@ -92,6 +92,7 @@ class GroundExtractB200 {
 
   double heightThreshold() const { return height_threshold_; }
   int lastStatus() const { return last_status_; }
+  tloam_b200_handle* handle() const { return h_; }
 
  private:
   void attach(tloam_b200_handle* shared, int device) {

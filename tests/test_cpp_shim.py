@@ -32,6 +32,7 @@ def test_shim_compiles_as_cpp14_against_host_types():
     assert os.path.exists(build_driver())
     assert os.path.exists(build_driver("feature_driver", "feature_extract_b200.hpp"))
     assert os.path.exists(build_driver("ground_driver", "ground_extract_b200.hpp"))
+    assert os.path.exists(build_driver("segmentation_driver", "segmentation_b200.hpp"))
 
 
 def test_shim_fails_loudly_without_gpu():
@@ -124,3 +125,44 @@ def test_ground_shim_matches_oracle(oracle):
     assert all(float(r[1]) == 0.0 for r in g[1:])
     assert [int(r[0]) for r in o[1:]] == [int(xbits[i]) for i in ref["object"]]
     assert [float(r[1]) for r in o[1:]] == [float(ref["beam"][i]) for i in ref["object"]]
+
+
+@pytest.mark.gpu
+def test_segmentation_shim_chain_matches_oracle(oracle):
+    """tloam::SegmentationB200 driven like Segmentation::spinOnce for two frames (groundRemove -> objectSegmentation ->
+    extractEdgePoint): clouds, boxes and the final edge / general clouds equal the oracle chain's; frame 0 runs with the
+    members' initial polar extrema (5.0), frame 1 with what resetParams() leaves (0.0)."""
+    from tloam_b200 import synth
+    exe = build_driver("segmentation_driver", "segmentation_b200.hpp")
+    pts = synth.raw_scan(seed=4, n_az=1200)
+    path = os.path.join(os.path.dirname(EXE), "scan_seg.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("Q", pts.shape[0]))
+        f.write(np.ascontiguousarray(pts, dtype=np.float64).tobytes())
+    res = subprocess.run([exe, path], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.strip().split("\n")
+    ge = oracle.ground_extract(pts)
+    obj = np.ascontiguousarray(pts[ge["object"]])
+    beam = ge["beam"][ge["object"]].astype(np.float64)
+    pos = 0
+    for frame, init in enumerate((5.0, 0.0)):
+        seg = oracle.dcvc(obj, min_polar_init=init, max_polar_init=init)
+        sp, sb = np.ascontiguousarray(obj[seg["segmented"]]), beam[seg["segmented"]]
+        ee = oracle.extract_edge(sp, sb, ring_min_num=131)
+        ng, no, ns, nb, ne, nn = (int(v) for v in lines[pos].split())
+        pos += 1
+        assert (ng, no, ns, nb, ne, nn) == (len(ge["ground"]), len(ge["object"]), len(seg["segmented"]), len(seg["sizes"]),
+                                            len(ee["edge"]), len(ee["non_edge"]))
+        for c in range(nb):
+            v = lines[pos + c].split()
+            assert int(v[0]) == c + 1 and int(v[1]) == seg["sizes"][c]
+            assert [float(x) for x in v[2:]] == list(seg["boxes"][c])
+        pos += nb
+        rows = [l.split() for l in lines[pos:pos + ne + nn]]
+        pos += ne + nn
+        xbits = sp[:, 0].copy().view(np.uint64)
+        want = list(ee["edge"]) + list(ee["non_edge"])
+        assert [int(r[0]) for r in rows] == [int(xbits[i]) for i in want]
+        assert [float(r[1]) for r in rows] == [float(sb[i]) for i in want]
+    assert pos == len(lines)
