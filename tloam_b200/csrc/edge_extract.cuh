@@ -230,16 +230,25 @@ __global__ void __launch_bounds__(kEeThreads) k_ee_section(const __grid_constant
   if (tid == 0) { cnt_out[0] = (unsigned)sm.npick; cnt_out[1] = run; }
 }
 
-// one block: exclusive scan of the section counts in (beam, sector) order
+// one warp: exclusive scan of the section counts in (beam, sector) order (each lane owns a run of consecutive sections)
 __global__ void __launch_bounds__(32) k_ee_offsets(const __grid_constant__ EeArgs a) {
-  if (threadIdx.x != 0) return;
-  unsigned e = 0u, nn = 0u;
+  const int lane = threadIdx.x;
   const int nsec = a.sensor_model * kEeSectors;
-  for (int s = 0; s < nsec; ++s) {
-    a.sec_off[2 * s] = e; a.sec_off[2 * s + 1] = nn;
-    e += a.sec_cnt[2 * s]; nn += a.sec_cnt[2 * s + 1];
+  const int per = (nsec + 31) / 32;
+  const int s0 = min(lane * per, nsec), s1 = min(s0 + per, nsec);
+  unsigned e = 0u, nn = 0u;
+  for (int s = s0; s < s1; ++s) { e += a.sec_cnt[2 * s]; nn += a.sec_cnt[2 * s + 1]; }
+  unsigned ie = e, in = nn;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned ve = __shfl_up_sync(0xffffffffu, ie, o), vn = __shfl_up_sync(0xffffffffu, in, o);
+    if (lane >= o) { ie += ve; in += vn; }
   }
-  a.sec_off[2 * nsec] = e; a.sec_off[2 * nsec + 1] = nn;
+  unsigned oe = ie - e, on = in - nn;
+  for (int s = s0; s < s1; ++s) {
+    a.sec_off[2 * s] = oe; a.sec_off[2 * s + 1] = on;
+    oe += a.sec_cnt[2 * s]; on += a.sec_cnt[2 * s + 1];
+  }
+  if (lane == 31) { a.sec_off[2 * nsec] = ie; a.sec_off[2 * nsec + 1] = in; }
 }
 
 // grid (kEeSectors, sensor_model)

@@ -28,6 +28,7 @@ constexpr int kGeChunk = 256;          // points per chunk (k_ge_pre / k_ge_regi
 constexpr int kGeKeys = 14;            // 12 regions + above the height threshold (12) + dropped (13)
 constexpr int kGeFitThreads = 512;
 constexpr int kGeMaxIter = 8;
+constexpr int kGeSeedCache = 4096;     // seed candidates whose height is cached in shared memory (regions up to 40 960 points)
 
 struct GeArgs {
   const double* pts;                   // AoS xyz
@@ -225,31 +226,71 @@ __global__ void __launch_bounds__(kGeChunk) k_ge_scatter(const __grid_constant__
   if (key >= 0) a.order[a.key_base[key] + a.chunk_cnt[(size_t)blockIdx.x * kGeKeys + key] + rank] = i;
 }
 
-// findBestPlane (ref: :551-616) over the positions pos = first, first + step, ... of the region whose flag is 1, in
-// that order.  Run by warp 0; lane L owns accumulator L (sequential sums, like the reference's loops).
-__device__ __forceinline__ void ge_fit_plane(const GeArgs& a, unsigned base, unsigned cnt, unsigned step, double nsel, double plane[4]) {
-  const int lane = threadIdx.x & 31;
-  // centroid: lanes 0..2
+// findBestPlane (ref: :551-616) over the positions pos = 0, step, 2 step, ... of the region whose flag is 1, in that
+// order.  The reference's sums are sequential (left to right), and so are these: ONE lane per accumulator adds the terms in
+// order.  Everything around the additions is parallel: the whole block gathers a tile of candidates into shared memory
+// (coordinates for the centroid, the six centred products for the second moments; a candidate that is not selected
+// contributes +0.0, which leaves a running sum unchanged -- it can never be -0.0), then lanes 0..2 / 0..5 of warp 0 run
+// their chains over the tile out of shared memory.  (Round 2, first version: the lanes read pts[order[..]] behind the flag
+// test inside the chain, ~600 cycles of exposed latency per term, 2.5 ms per scan.)
+constexpr int kGeTile = 1024;
+
+__device__ __forceinline__ void ge_plane_from_moments(double cx, double cy, double cz, double xx, double xy, double xz, double yy, double yz,
+                                                      double zz, double plane[4]);
+
+__device__ __forceinline__ void ge_fit_plane(const GeArgs& a, unsigned base, unsigned cnt, unsigned step, double nsel, double* s_tile,
+                                             double* s_bc, double plane[4]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned ncand = (cnt + step - 1u) / step;
   double acc = 0.0;
-  if (lane < 3)
-    for (unsigned k = 0; k < cnt; k += step)
-      if (a.flag[base + k] == 1) acc = ge_add(acc, a.pts[3ull * a.order[base + k] + lane]);
-  acc = __ddiv_rn(acc, nsel);
-  const double cx = __shfl_sync(0xffffffffu, acc, 0), cy = __shfl_sync(0xffffffffu, acc, 1), cz = __shfl_sync(0xffffffffu, acc, 2);
-  // second moments xx xy xz yy yz zz: lanes 0..5
-  const int ia = lane < 3 ? 0 : (lane < 5 ? 1 : 2);
-  const int ib = lane < 3 ? lane : (lane < 5 ? lane - 2 : 2);
-  const double ca = ia == 0 ? cx : (ia == 1 ? cy : cz), cb = ib == 0 ? cx : (ib == 1 ? cy : cz);
-  double m = 0.0;
-  if (lane < 6)
-    for (unsigned k = 0; k < cnt; k += step)
+  for (unsigned c0 = 0; c0 < ncand; c0 += kGeTile) {
+    const unsigned m = min((unsigned)kGeTile, ncand - c0);
+    for (unsigned c = tid; c < m; c += kGeFitThreads) {
+      const unsigned k = (c0 + c) * step;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      if (a.flag[base + k] == 1) { const double* p = a.pts + 3ull * a.order[base + k]; v0 = p[0]; v1 = p[1]; v2 = p[2]; }
+      s_tile[c] = v0; s_tile[kGeTile + c] = v1; s_tile[2 * kGeTile + c] = v2;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < 3) {
+      const double* t = s_tile + lane * kGeTile;
+#pragma unroll 8
+      for (unsigned c = 0; c < m; ++c) acc = ge_add(acc, t[c]);
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && lane < 3) s_bc[lane] = __ddiv_rn(acc, nsel);
+  __syncthreads();
+  const double cx = s_bc[0], cy = s_bc[1], cz = s_bc[2];
+  acc = 0.0;
+  for (unsigned c0 = 0; c0 < ncand; c0 += kGeTile) {
+    const unsigned m = min((unsigned)kGeTile, ncand - c0);
+    for (unsigned c = tid; c < m; c += kGeFitThreads) {
+      const unsigned k = (c0 + c) * step;
+      double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (a.flag[base + k] == 1) {
         const double* p = a.pts + 3ull * a.order[base + k];
-        m = ge_add(m, ge_mul(ge_sub(p[ia], ca), ge_sub(p[ib], cb)));
+        const double rx = ge_sub(p[0], cx), ry = ge_sub(p[1], cy), rz = ge_sub(p[2], cz);
+        q[0] = ge_mul(rx, rx); q[1] = ge_mul(rx, ry); q[2] = ge_mul(rx, rz); q[3] = ge_mul(ry, ry); q[4] = ge_mul(ry, rz); q[5] = ge_mul(rz, rz);
       }
-  m = __ddiv_rn(m, nsel);
-  const double xx = __shfl_sync(0xffffffffu, m, 0), xy = __shfl_sync(0xffffffffu, m, 1), xz = __shfl_sync(0xffffffffu, m, 2);
-  const double yy = __shfl_sync(0xffffffffu, m, 3), yz = __shfl_sync(0xffffffffu, m, 4), zz = __shfl_sync(0xffffffffu, m, 5);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) s_tile[j * kGeTile + c] = q[j];
+    }
+    __syncthreads();
+    if (warp == 0 && lane < 6) {
+      const double* t = s_tile + lane * kGeTile;
+#pragma unroll 8
+      for (unsigned c = 0; c < m; ++c) acc = ge_add(acc, t[c]);
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && lane < 6) s_bc[3 + lane] = __ddiv_rn(acc, nsel);
+  __syncthreads();
+  if (tid == 0) ge_plane_from_moments(cx, cy, cz, s_bc[3], s_bc[4], s_bc[5], s_bc[6], s_bc[7], s_bc[8], plane);
+}
+
+__device__ __forceinline__ void ge_plane_from_moments(double cx, double cy, double cz, double xx, double xy, double xz, double yy, double yz,
+                                                      double zz, double plane[4]) {
   double wx = 0.0, wy = 0.0, wz = 0.0;
   auto dot3 = [](double ax, double ay, double az, double bx, double by, double bz) {
     return ge_add(ge_add(ge_mul(ax, bx), ge_mul(ay, by)), ge_mul(az, bz));
@@ -297,8 +338,11 @@ __global__ void __launch_bounds__(kGeFitThreads) k_ge_fit(const __grid_constant_
   __shared__ unsigned s_red[kGeFitThreads / 32];
   __shared__ double s_zmin[kGeFitThreads / 32];
   __shared__ unsigned s_kmin[kGeFitThreads / 32];
-  __shared__ double s_plane[4], s_lastz, s_sum;
+  __shared__ double s_plane[4], s_lastz, s_sum, s_bc[9];
   __shared__ unsigned s_lastk, s_found;
+  extern __shared__ __align__(16) unsigned char ge_raw[];
+  double* s_tile = reinterpret_cast<double*>(ge_raw);                      // [6][kGeTile]
+  double* s_cz = s_tile + 6 * kGeTile;                                     // [kGeSeedCache] candidate heights (DBL_MAX = not a candidate)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int it = tid; it < kGeMaxIter * 4; it += kGeFitThreads) a.planes[(size_t)rg * kGeMaxIter * 4 + it] = __longlong_as_double(0x7FF8000000000000ll);
   if (tid == 0) { a.reg_cnt[2 * rg] = 0u; a.reg_cnt[2 * rg + 1] = 0u; }
@@ -309,6 +353,11 @@ __global__ void __launch_bounds__(kGeFitThreads) k_ge_fit(const __grid_constant_
     const double r = __dsqrt_rn(ge_add(ge_add(ge_mul(p[0], p[0]), ge_mul(p[1], p[1])), ge_mul(p[2], p[2])));
     return z >= ge_mul(-1.5, a.sensor_height) && r >= a.min_range && r <= a.max_range;
   };
+  // heights of the first kGeSeedCache candidates are computed once (the 20 argmin rounds below re-read them)
+  for (unsigned j = tid; j < (unsigned)kGeSeedCache && j * 10u < cnt; j += kGeFitThreads) {
+    double z;
+    s_cz[j] = cand_z(j * 10u, z) ? z : DBL_MAX;
+  }
   // ---- the ground_seed_num lowest candidates, ascending (z, k); their sum in that order (:649-657) ----
   if (tid == 0) { s_sum = 0.0; s_lastz = -DBL_MAX; s_lastk = 0u; s_found = 0u; }
   __syncthreads();
@@ -321,7 +370,8 @@ __global__ void __launch_bounds__(kGeFitThreads) k_ge_fit(const __grid_constant_
     const bool first = round == 0;
     for (unsigned k = (unsigned)tid * 10u; k < cnt; k += (unsigned)kGeFitThreads * 10u) {
       double z;
-      if (!cand_z(k, z)) continue;
+      if (k < (unsigned)kGeSeedCache * 10u) { z = s_cz[k / 10u]; if (z == DBL_MAX) continue; }
+      else if (!cand_z(k, z)) continue;
       if (!first && !(z > lz || (z == lz && k > lk))) continue;            // already taken
       if (z < bz || (z == bz && k < bk)) { bz = z; bk = k; }
     }
@@ -348,7 +398,11 @@ __global__ void __launch_bounds__(kGeFitThreads) k_ge_fit(const __grid_constant_
   unsigned nsel = 0u;
   for (unsigned k = tid; k < cnt; k += kGeFitThreads) {
     unsigned char f = 0;
-    if (k % 10u == 0u) { double z; if (cand_z(k, z) && z < zlim) f = 1; }
+    if (k % 10u == 0u) {
+      double z;
+      if (k < (unsigned)kGeSeedCache * 10u) { z = s_cz[k / 10u]; if (z != DBL_MAX && z < zlim) f = 1; }
+      else if (cand_z(k, z) && z < zlim) f = 1;
+    }
     a.flag[base + k] = f;
     nsel += f;
   }
@@ -358,10 +412,10 @@ __global__ void __launch_bounds__(kGeFitThreads) k_ge_fit(const __grid_constant_
   unsigned step = 10u;
   for (int iter = 0; iter < a.max_iter; ++iter) {
     if (nsel <= 3u) continue;                                              // :670-672
-    if (warp == 0) {
+    {
       double plane[4];
-      ge_fit_plane(a, base, cnt, step, (double)nsel, plane);
-      if (lane == 0) {
+      ge_fit_plane(a, base, cnt, step, (double)nsel, s_tile, s_bc, plane);
+      if (tid == 0) {
         for (int j = 0; j < 4; ++j) { s_plane[j] = plane[j]; a.planes[((size_t)rg * kGeMaxIter + iter) * 4 + j] = plane[j]; }
       }
     }

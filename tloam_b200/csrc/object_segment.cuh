@@ -71,6 +71,7 @@ struct OsArgs {
   int* sizes;                             // [n] by rank
   int* pkey;                              // [n] partition key: rank or -1
   double* boxes;                          // [n][6] by rank
+  unsigned long long* box_enc;            // [n][6] by rank: encoded min xyz, max xyz
   // stable partition scratch
   unsigned* chunk_cnt;                    // [nchunk][kOsKeys]
   unsigned* key_base;                     // [kOsKeys + 1]
@@ -337,21 +338,29 @@ __global__ void __launch_bounds__(256) k_os_rows(const __grid_constant__ OsArgs 
 }
 
 // ---- 9. the sequential part: one warp replays the events in point order ----------------------------------------------
-// state: 2 bits per voxel: bit 0 = the first point is labelled, bit 1 = all points are labelled.
-__device__ __forceinline__ unsigned os_state(const unsigned* st, int v) {
+// state of a voxel: 0 = no point labelled, 1 = the first point is labelled, 2 (or 3) = all points are labelled.
+// kBytes: one byte per voxel in shared memory (plain stores: lanes that hit the same voxel write the same value);
+// otherwise 2 bits per voxel (shared memory up to ~800k voxels, else global memory), updated with atomicOr.
+template <bool kBytes>
+__device__ __forceinline__ unsigned os_state(const void* st, int v) {
+  if (kBytes) return reinterpret_cast<const volatile unsigned char*>(st)[v];
   return (reinterpret_cast<const volatile unsigned*>(st)[v >> 4] >> ((v & 15) * 2)) & 3u;
 }
 
+template <bool kBytes>
 __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a, const int use_smem) {
   extern __shared__ __align__(16) unsigned char os_raw[];
   constexpr int kRowInts = 32 * kOsRow;                                      // one chunk of 32 events: 864 ints = 3456 B
   int* s_rows = reinterpret_cast<int*>(os_raw);                              // [2][kRowInts]
-  unsigned* st = use_smem ? reinterpret_cast<unsigned*>(os_raw + 2 * kRowInts * sizeof(int)) : a.state_g;
+  void* st = (kBytes || use_smem) ? static_cast<void*>(os_raw + 2 * kRowInts * sizeof(int)) : static_cast<void*>(a.state_g);
   const int lane = threadIdx.x;
   const int nev = a.params[5], nvox = a.params[4];
   if (a.params[3] != 0) return;
-  if (use_smem)
-    for (int w = lane; w < (nvox + 15) / 16 + 1; w += 32) st[w] = 0u;
+  if (kBytes) {
+    for (int w = lane; w < (nvox + 3) / 4 + 1; w += 32) reinterpret_cast<unsigned*>(st)[w] = 0u;
+  } else if (use_smem) {
+    for (int w = lane; w < (nvox + 15) / 16 + 1; w += 32) reinterpret_cast<unsigned*>(st)[w] = 0u;
+  }
   __syncwarp();
   const int nchunks = (nev + 31) / 32;
   auto prefetch = [&](int c, int buf) {                                       // 216 x 16 B, rows of the chunk are contiguous
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
       if (cand) {
         if (my_kind == 2) fire = true;
         else {
-          const unsigned s = os_state(st, my_v);
+          const unsigned s = os_state<kBytes>(st, my_v);
           fire = my_kind == 0 ? (s == 0u) : (s == 1u);
           if (s & 2u) cand = false;                                           // a full voxel never fires again
         }
@@ -395,14 +404,18 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
       const int src = __ffs(m) - 1;
       const int v = __shfl_sync(0xffffffffu, my_v, src), kind = __shfl_sync(0xffffffffu, my_kind, src);
       const int nb = lane < kOsRow ? rows[src * kOsRow + lane] : -1;
-      const unsigned s_nb = nb >= 0 ? os_state(st, nb) : 0u;
+      const unsigned s_nb = nb >= 0 ? os_state<kBytes>(st, nb) : 0u;
       const unsigned lab = __ballot_sync(0xffffffffu, nb >= 0 && s_nb != 0u);
       const int p = lab ? __ffs(lab) - 1 : 0;
       const bool take = nb >= 0 && lane >= p;
-      __syncwarp();
-      if (take && !(s_nb & 2u)) atomicOr(st + (nb >> 4), 2u << ((nb & 15) * 2));
-      const unsigned covered = __ballot_sync(0xffffffffu, take && nb == v);
-      if (kind != 2 && covered == 0u && lane == 0) atomicOr(st + (v >> 4), 1u << ((v & 15) * 2));
+      const unsigned covered = __ballot_sync(0xffffffffu, take && nb == v);   // (also orders the reads above before the writes)
+      if (kBytes) {
+        if (take && !(s_nb & 2u)) reinterpret_cast<volatile unsigned char*>(st)[nb] = 2;
+        if (kind != 2 && covered == 0u && lane == 0) reinterpret_cast<volatile unsigned char*>(st)[v] = 1;
+      } else {
+        if (take && !(s_nb & 2u)) atomicOr(reinterpret_cast<unsigned*>(st) + (nb >> 4), 2u << ((nb & 15) * 2));
+        if (kind != 2 && covered == 0u && lane == 0) atomicOr(reinterpret_cast<unsigned*>(st) + (v >> 4), 1u << ((v & 15) * 2));
+      }
       if (lane == src) { my_p = p; cand = false; }
       __syncwarp();
     }
@@ -479,7 +492,10 @@ __global__ void __launch_bounds__(256) k_os_rank(const __grid_constant__ OsArgs 
     for (int k = 0; k < lim; ++k) rank += (s_cnt[k] > my_cnt || (s_cnt[k] == my_cnt && s_root[k] < my_root)) ? 1 : 0;
     __syncthreads();
   }
-  if (c < nc) { a.cl_rank_of_root[my_root] = rank + 1; a.sizes[rank] = my_cnt; }
+  if (c < nc) {
+    a.cl_rank_of_root[my_root] = rank + 1; a.sizes[rank] = my_cnt;
+    for (int d = 0; d < 3; ++d) { a.box_enc[6ull * rank + d] = ~0ull; a.box_enc[6ull * rank + 3 + d] = 0ull; }
+  }
 }
 
 __global__ void __launch_bounds__(kOsChunk) k_os_pkey(const __grid_constant__ OsArgs a) {
@@ -491,42 +507,44 @@ __global__ void __launch_bounds__(kOsChunk) k_os_pkey(const __grid_constant__ Os
 }
 
 // ---- 13. colorSegmentation (:1032-1078): the segmented scan as 64-bit indices + one box per cluster --------------------
-__global__ void __launch_bounds__(256) k_os_boxes(const __grid_constant__ OsArgs a, const int* __restrict__ seg) {
-  __shared__ double s_red[6][8];
-  __shared__ unsigned s_off;
-  const int r = blockIdx.x;
-  if (r >= a.params[6]) return;
-  unsigned part = 0u;
-  for (int k = threadIdx.x; k < r; k += 256) part += (unsigned)a.sizes[k];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if (threadIdx.x == 0) s_off = 0u;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) atomicAdd(&s_off, part);
-  __syncthreads();
-  const unsigned off = s_off, sz = (unsigned)a.sizes[r];
-  double mn[3] = {1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308};
-  double mx[3] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
-  for (unsigned k = threadIdx.x; k < sz; k += 256) {
-    const int id = seg[off + k];
-    a.out_seg[off + k] = (unsigned long long)id;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { const double v = a.pts[3ull * id + d]; mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v); }
+// One thread per position of the segmented scan; min / max through order-preserving 64-bit encodings (warp-aggregated when
+// the whole warp sits in one cluster, which is the common case: the scan is grouped by cluster).
+__global__ void __launch_bounds__(256) k_os_boxes_acc(const __grid_constant__ OsArgs a, const int* __restrict__ seg) {
+  const unsigned j = blockIdx.x * 256 + threadIdx.x;
+  const bool on = j < (unsigned)a.params[7];
+  int r = -1;
+  double v[3] = {0.0, 0.0, 0.0};
+  if (on) {
+    const int id = seg[j];
+    a.out_seg[j] = (unsigned long long)id;
+    r = a.cluster[id] - 1;
+    v[0] = a.pts[3ull * id]; v[1] = a.pts[3ull * id + 1]; v[2] = a.pts[3ull * id + 2];
   }
+  const unsigned active = __ballot_sync(0xffffffffu, on);
+  if (active == 0u) return;
+  const int r0 = __shfl_sync(0xffffffffu, r, __ffs(active) - 1);
+  const bool uniform = __all_sync(0xffffffffu, !on || r == r0);
+  if (uniform) {
+    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
 #pragma unroll
-  for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < 3; ++d) {
+      double lo = on ? v[d] : kInf, hi = on ? v[d] : -kInf;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o)); mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+      if ((threadIdx.x & 31) == 0) { atomicMin(a.box_enc + 6ull * r0 + d, os_encode(lo)); atomicMax(a.box_enc + 6ull * r0 + 3 + d, os_encode(hi)); }
     }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0)
-    for (int d = 0; d < 3; ++d) { s_red[d][warp] = mn[d]; s_red[3 + d][warp] = mx[d]; }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    const int d = threadIdx.x;
-    double lo = s_red[d][0], hi = s_red[3 + d][0];
-    for (int w = 1; w < 8; ++w) { lo = fmin(lo, s_red[d][w]); hi = fmax(hi, s_red[3 + d][w]); }
+  } else if (on) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { atomicMin(a.box_enc + 6ull * r + d, os_encode(v[d])); atomicMax(a.box_enc + 6ull * r + 3 + d, os_encode(v[d])); }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_os_boxes_fin(const __grid_constant__ OsArgs a) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= a.params[6]) return;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double lo = os_decode(a.box_enc[6ull * r + d]), hi = os_decode(a.box_enc[6ull * r + 3 + d]);
     const double len = __dsub_rn(hi, lo);
     a.boxes[6ull * r + d] = __dadd_rn(lo, __ddiv_rn(len, 2.0));
     a.boxes[6ull * r + 3 + d] = len < 0 ? __dmul_rn(-1.0, len) : len;

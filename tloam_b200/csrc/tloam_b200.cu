@@ -2182,7 +2182,13 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_region<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scan2<<<1, 1024, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scatter<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
-  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_fit<<<4 * cfg->num_sec, kGeFitThreads, 0, h->stream>>>(a)));
+  constexpr size_t kGeFitSmem = (6 * kGeTile + kGeSeedCache) * sizeof(double);
+  static bool ge_attr_set = false;
+  if (!ge_attr_set) {
+    CU_TRY(cudaFuncSetAttribute(k_ge_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGeFitSmem));
+    ge_attr_set = true;
+  }
+  TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_fit<<<4 * cfg->num_sec, kGeFitThreads, kGeFitSmem, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_emit<<<dim3(32, 25), 256, 0, h->stream>>>(a)));
   CU_TRY(cudaGetLastError());
   // counts + threshold first (one small copy each, one synchronisation), then exactly the list prefixes
@@ -2309,7 +2315,7 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
                o_ps = take(n * 4), o_vid = take(n * 4), o_f1 = take(n * 4), o_f2 = take(n * 4), o_vc = take(n * 12),
                o_ek = take(n * 4), o_ept = take(n * 4), o_ei = take(n32 * 4), o_rows = take(n32 * kOsRow * 4), o_ep = take(n32),
                o_stg = take(state_words * 4), o_par2 = take(n * 4), o_root = take(n * 4), o_cnt = take(n * 4), o_clr = take(n * 4),
-               o_crr = take(n * 4), o_cl = take(n * 4), o_sz = take(n * 4), o_pk = take(n * 4), o_box = take(n * 48),
+               o_crr = take(n * 4), o_cl = take(n * 4), o_sz = take(n * 4), o_pk = take(n * 4), o_box = take(n * 48), o_benc = take(n * 48),
                o_cc = take((size_t)a.nchunk * kOsKeys * 4), o_kb = take((kOsKeys + 1) * 4), o_pa = take(n * 4), o_pb = take(n * 4),
                o_seg = take(n * 8);
   if (off > h->cap_ge) {                                                   // shares the segmentation arena
@@ -2326,20 +2332,23 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   a.ev_pt = (int*)(b + o_ept); a.ev_info = (int*)(b + o_ei); a.rows = (int*)(b + o_rows); a.ev_p = (signed char*)(b + o_ep);
   a.state_g = (unsigned*)(b + o_stg); a.parent = (int*)(b + o_par2); a.root = (int*)(b + o_root); a.cnt = (int*)(b + o_cnt);
   a.cl_root = (int*)(b + o_clr); a.cl_rank_of_root = (int*)(b + o_crr); a.cluster = (int*)(b + o_cl); a.sizes = (int*)(b + o_sz);
-  a.pkey = (int*)(b + o_pk); a.boxes = (double*)(b + o_box); a.chunk_cnt = (unsigned*)(b + o_cc); a.key_base = (unsigned*)(b + o_kb);
+  a.pkey = (int*)(b + o_pk); a.boxes = (double*)(b + o_box); a.box_enc = (unsigned long long*)(b + o_benc); a.chunk_cnt = (unsigned*)(b + o_cc); a.key_base = (unsigned*)(b + o_kb);
   a.perm_a = (int*)(b + o_pa); a.perm_b = (int*)(b + o_pb); a.out_seg = (unsigned long long*)(b + o_seg);
   const size_t seq_fixed = 2 * 32 * kOsRow * sizeof(int);
-  const int use_smem = seq_fixed + state_words * 4 <= (size_t)kOsSeqSmemBytes ? 1 : 0;
-  const size_t seq_smem = seq_fixed + (use_smem ? state_words * 4 : 0);
+  const size_t state_bytes = round_up(n, 4) + 8;                           // one byte per voxel (at most n voxels)
+  const bool seq_bytes = seq_fixed + state_bytes <= (size_t)kOsSeqSmemBytes && !getenv("TLOAM_B200_DCVC_PACKED");
+  const int use_smem = seq_fixed + state_words * 4 <= (size_t)kOsSeqSmemBytes && !getenv("TLOAM_B200_DCVC_GLOBAL") ? 1 : 0;
+  const size_t seq_smem = seq_fixed + (seq_bytes ? state_bytes : (use_smem ? state_words * 4 : 0));
   static bool attr_set = false;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(k_os_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSeqSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k_os_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSeqSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k_os_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSeqSmemBytes));
     attr_set = true;
   }
   cudaStream_t st = h->stream;
   CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(b + o_tab, 0, cap * 8, st));
-  if (!use_smem) CU_TRY(cudaMemsetAsync(b + o_stg, 0, state_words * 4, st));
+  if (!seq_bytes && !use_smem) CU_TRY(cudaMemsetAsync(b + o_stg, 0, state_words * 4, st));
   const unsigned ev_blocks = (unsigned)((n32 * 32 + 255) / 256);
   TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_init<<<1, 32, 0, st>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_polar<<<a.nchunk, kOsChunk, 0, st>>>(a)));
@@ -2360,7 +2369,8 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   };
   partition(a.evkey, nullptr, a.ev_pt, nullptr, 0, a.params + 5);          // events in point order
   TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_rows<<<ev_blocks, 256, 0, st>>>(a)));
-  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_seq<<<1, 32, seq_smem, st>>>(a, use_smem)));
+  if (seq_bytes) TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_seq<true><<<1, 32, seq_smem, st>>>(a, 1)));
+  else TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_seq<false><<<1, 32, seq_smem, st>>>(a, use_smem)));
   TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_union<<<ev_blocks, 256, 0, st>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_label<<<a.nchunk, kOsChunk, 0, st>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_clusters<<<a.nchunk, kOsChunk, 0, st>>>(a)));
@@ -2371,7 +2381,8 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   const int* seg = a.perm_a;
   if (cl_bound > 256) { partition(a.pkey, a.perm_a, a.perm_b, a.params + 7, 8, nullptr); seg = a.perm_b; }
   if (cl_bound > 65536) { partition(a.pkey, a.perm_b, a.perm_a, a.params + 7, 16, nullptr); seg = a.perm_a; }
-  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_boxes<<<(unsigned)cl_bound, 256, 0, st>>>(a, seg)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_boxes_acc<<<a.nchunk, 256, 0, st>>>(a, seg)));
+  TL_LAUNCH(TLOAM_B200_K_OBJECT, (k_os_boxes_fin<<<(unsigned)((cl_bound + 255) / 256), 256, 0, st>>>(a)));
   CU_TRY(cudaGetLastError());
   int par[8];
   CU_TRY(cudaMemcpyAsync(par, a.params, sizeof(par), cudaMemcpyDeviceToHost, st));
