@@ -60,6 +60,7 @@ struct OsArgs {
   int* ev_pt;                             // [n] events in point order (output of the compaction)
   int* ev_info;                           // [n] vid * 4 + kind (0 first point, 1 second point, 2 voxel not in its own list)
   int* rows;                              // [n][27] neighbour vids per event, -1 = skipped / absent
+  signed char* ev_own;                    // [n] last position of the event's own voxel in its row, -1 = not listed
   signed char* ev_p;                      // [n] first labelled entry (27 = none: everything listed), -1 = the event did nothing
   unsigned* state_g;                      // 2-bit voxel states when they do not fit in shared memory
   int* parent;                            // [n]
@@ -320,21 +321,24 @@ __global__ void __launch_bounds__(256) k_os_rows(const __grid_constant__ OsArgs 
   const int v = a.vid[pt];
   const int pi = a.coord[3ull * pt], ti = a.coord[3ull * pt + 1], ai = a.coord[3ull * pt + 2];
   const int polar_num = a.params[0], width = a.params[1], height = a.params[2];
+  int nb = -1;
+  if (l < (unsigned)kOsRow) {
+    const int z = ti - 1 + (int)(l / 9), y = pi - 1 + (int)((l / 3) % 3), x = ai - 1 + (int)(l % 3);
+    if (!(z < 0 || z > height) && !(y < 0 || y > polar_num)) {
+      int ax = x;
+      if (ax < 0) ax = width - 1;
+      if (ax > 300) ax = 300;
+      nb = os_lookup(a, os_voxel_key(ax, y, z, polar_num, width));
+    }
+    a.rows[(size_t)j * kOsRow + l] = nb;
+  }
+  const unsigned own = __ballot_sync(0xffffffffu, nb == v);                 // the 32 threads of an event are one warp
   if (l == 31) {
     const int kind = !os_own_listed(ti, ai, height) ? 2 : (pt == a.f1[v] ? 0 : 1);
     a.ev_info[j] = v * 4 + kind;
+    a.ev_own[j] = (signed char)(own ? 31 - __clz(own) : -1);                 // LAST position of the own voxel in its row
     a.ev_p[j] = -1;
   }
-  if (l >= (unsigned)kOsRow) return;
-  const int z = ti - 1 + (int)(l / 9), y = pi - 1 + (int)((l / 3) % 3), x = ai - 1 + (int)(l % 3);
-  int nb = -1;
-  if (!(z < 0 || z > height) && !(y < 0 || y > polar_num)) {
-    int ax = x;
-    if (ax < 0) ax = width - 1;
-    if (ax > 300) ax = 300;
-    nb = os_lookup(a, os_voxel_key(ax, y, z, polar_num, width));
-  }
-  a.rows[(size_t)j * kOsRow + l] = nb;
 }
 
 // ---- 9. the sequential part: one warp replays the events in point order ----------------------------------------------
@@ -373,13 +377,15 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
   };
   if (nchunks > 0) prefetch(0, 0);
   int info_next = (lane < nev) ? a.ev_info[lane] : -1;
+  int own_next = (lane < nev) ? (int)a.ev_own[lane] : -1;
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
-    const int info = info_next;
+    const int info = info_next, my_own = own_next;
     if (c + 1 < nchunks) {
       prefetch(c + 1, buf ^ 1);
       const int jn = (c + 1) * 32 + lane;
       info_next = jn < nev ? a.ev_info[jn] : -1;
+      own_next = jn < nev ? (int)a.ev_own[jn] : -1;
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -390,6 +396,7 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
     bool cand = info >= 0;
     int my_p = -1;
     while (true) {
+      // which events of the chunk would act now?  (one shared-memory read of the own voxel's state per lane)
       bool fire = false;
       if (cand) {
         if (my_kind == 2) fire = true;
@@ -401,20 +408,19 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
       }
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (m == 0u) break;
-      const int src = __ffs(m) - 1;
-      const int v = __shfl_sync(0xffffffffu, my_v, src), kind = __shfl_sync(0xffffffffu, my_kind, src);
+      const int src = __ffs(m) - 1;                                           // the earliest one is the next in point order
       const int nb = lane < kOsRow ? rows[src * kOsRow + lane] : -1;
       const unsigned s_nb = nb >= 0 ? os_state<kBytes>(st, nb) : 0u;
-      const unsigned lab = __ballot_sync(0xffffffffu, nb >= 0 && s_nb != 0u);
+      const unsigned lab = __ballot_sync(0xffffffffu, nb >= 0 && s_nb != 0u);   // (all state reads are done once this returns)
       const int p = lab ? __ffs(lab) - 1 : 0;
-      const bool take = nb >= 0 && lane >= p;
-      const unsigned covered = __ballot_sync(0xffffffffu, take && nb == v);   // (also orders the reads above before the writes)
+      const bool take = nb >= 0 && lane >= p && !(s_nb & 2u);
+      const bool own_first = lane == src && my_kind != 2 && my_own < p;        // own voxel listed before p only: first point labelled
       if (kBytes) {
-        if (take && !(s_nb & 2u)) reinterpret_cast<volatile unsigned char*>(st)[nb] = 2;
-        if (kind != 2 && covered == 0u && lane == 0) reinterpret_cast<volatile unsigned char*>(st)[v] = 1;
+        if (take) reinterpret_cast<volatile unsigned char*>(st)[nb] = 2;
+        if (own_first) reinterpret_cast<volatile unsigned char*>(st)[my_v] = 1;
       } else {
-        if (take && !(s_nb & 2u)) atomicOr(reinterpret_cast<unsigned*>(st) + (nb >> 4), 2u << ((nb & 15) * 2));
-        if (kind != 2 && covered == 0u && lane == 0) atomicOr(reinterpret_cast<unsigned*>(st) + (v >> 4), 1u << ((v & 15) * 2));
+        if (take) atomicOr(reinterpret_cast<unsigned*>(st) + (nb >> 4), 2u << ((nb & 15) * 2));
+        if (own_first) atomicOr(reinterpret_cast<unsigned*>(st) + (my_v >> 4), 1u << ((my_v & 15) * 2));
       }
       if (lane == src) { my_p = p; cand = false; }
       __syncwarp();
