@@ -33,6 +33,9 @@ constexpr int kOsChunk = 256;
 constexpr int kOsMaxBounds = 4096;        // polar rings (default configuration: ~500 at 120 m)
 constexpr int kOsKeys = 256;              // digit of the stable partition
 constexpr int kOsRow = 27;                // searchKNN entries
+constexpr int kOsRowStride = 32;          // ints per event row: 27 neighbours, [27] last own position, [28] vid * 4 + kind, padding
+constexpr int kOsRowOwn = 27, kOsRowInfo = 28;
+constexpr int kOsSeqStages = 8;           // chunks of 32 event rows in flight towards shared memory (cp.async ring)
 constexpr int kOsSeqSmemBytes = 200 * 1024;
 
 struct OsArgs {
@@ -59,8 +62,7 @@ struct OsArgs {
   int* evkey;                             // [n] partition key of the event compaction: 0 = event, -1 = not
   int* ev_pt;                             // [n] events in point order (output of the compaction)
   int* ev_info;                           // [n] vid * 4 + kind (0 first point, 1 second point, 2 voxel not in its own list)
-  int* rows;                              // [n][27] neighbour vids per event, -1 = skipped / absent
-  signed char* ev_own;                    // [n] last position of the event's own voxel in its row, -1 = not listed
+  int* rows;                              // [n32 + 32 * kOsSeqStages][32] per event: 27 neighbour vids (-1 = skipped / absent), own position, info
   signed char* ev_p;                      // [n] first labelled entry (27 = none: everything listed), -1 = the event did nothing
   unsigned* state_g;                      // 2-bit voxel states when they do not fit in shared memory
   int* parent;                            // [n]
@@ -330,15 +332,14 @@ __global__ void __launch_bounds__(256) k_os_rows(const __grid_constant__ OsArgs 
       if (ax > 300) ax = 300;
       nb = os_lookup(a, os_voxel_key(ax, y, z, polar_num, width));
     }
-    a.rows[(size_t)j * kOsRow + l] = nb;
   }
   const unsigned own = __ballot_sync(0xffffffffu, nb == v);                 // the 32 threads of an event are one warp
-  if (l == 31) {
-    const int kind = !os_own_listed(ti, ai, height) ? 2 : (pt == a.f1[v] ? 0 : 1);
-    a.ev_info[j] = v * 4 + kind;
-    a.ev_own[j] = (signed char)(own ? 31 - __clz(own) : -1);                 // LAST position of the own voxel in its row
-    a.ev_p[j] = -1;
-  }
+  const int kind = !os_own_listed(ti, ai, height) ? 2 : (pt == a.f1[v] ? 0 : 1);
+  int word = nb;                                                            // entries 0..26: neighbour voxel ids
+  if (l == kOsRowOwn) word = own ? 31 - __clz(own) : -1;                    // LAST position of the own voxel in its row
+  if (l == kOsRowInfo) word = v * 4 + kind;
+  a.rows[(size_t)j * kOsRowStride + l] = word;
+  if (l == 31) { a.ev_info[j] = v * 4 + kind; a.ev_p[j] = -1; }
 }
 
 // ---- 9. the sequential part: one warp replays the events in point order ----------------------------------------------
@@ -354,44 +355,43 @@ __device__ __forceinline__ unsigned os_state(const void* st, int v) {
 template <bool kBytes>
 __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a, const int use_smem) {
   extern __shared__ __align__(16) unsigned char os_raw[];
-  constexpr int kRowInts = 32 * kOsRow;                                      // one chunk of 32 events: 864 ints = 3456 B
-  int* s_rows = reinterpret_cast<int*>(os_raw);                              // [2][kRowInts]
-  void* st = (kBytes || use_smem) ? static_cast<void*>(os_raw + 2 * kRowInts * sizeof(int)) : static_cast<void*>(a.state_g);
+  constexpr int kChunkInts = 32 * kOsRowStride;                              // one chunk of 32 events: 4 KB
+  int* s_rows = reinterpret_cast<int*>(os_raw);                              // [kOsSeqStages][kChunkInts]
+  void* st = (kBytes || use_smem) ? static_cast<void*>(os_raw + kOsSeqStages * kChunkInts * sizeof(int)) : static_cast<void*>(a.state_g);
   const int lane = threadIdx.x;
   const int nev = a.params[5], nvox = a.params[4];
   if (a.params[3] != 0) return;
+  const int nchunks = (nev + 31) / 32;
+  // rows of a chunk are contiguous (and the buffer is padded to whole chunks): 256 x 16 B per chunk, 8 per lane.  A
+  // group is committed for every stage, empty past the end, so that wait_group counts stay uniform.
+  auto prefetch = [&](int c) {
+    if (c < nchunks) {
+      const int* src = a.rows + (size_t)c * kChunkInts;
+      int* dst_base = s_rows + (c % kOsSeqStages) * kChunkInts;
+#pragma unroll
+      for (int q = 0; q < kChunkInts / 4 / 32; ++q) {
+        const int e = (q * 32 + lane) * 4;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(dst_base + e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + e) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  for (int c = 0; c < kOsSeqStages - 1; ++c) prefetch(c);
   if (kBytes) {
     for (int w = lane; w < (nvox + 3) / 4 + 1; w += 32) reinterpret_cast<unsigned*>(st)[w] = 0u;
   } else if (use_smem) {
     for (int w = lane; w < (nvox + 15) / 16 + 1; w += 32) reinterpret_cast<unsigned*>(st)[w] = 0u;
   }
   __syncwarp();
-  const int nchunks = (nev + 31) / 32;
-  auto prefetch = [&](int c, int buf) {                                       // 216 x 16 B, rows of the chunk are contiguous
-    const int* src = a.rows + (size_t)c * kRowInts;
-    for (int q = lane; q < kRowInts / 4; q += 32) {                          // (the rows buffer is padded to a whole chunk)
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(s_rows + buf * kRowInts + q * 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + q * 4) : "memory");
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-  if (nchunks > 0) prefetch(0, 0);
-  int info_next = (lane < nev) ? a.ev_info[lane] : -1;
-  int own_next = (lane < nev) ? (int)a.ev_own[lane] : -1;
   for (int c = 0; c < nchunks; ++c) {
-    const int buf = c & 1;
-    const int info = info_next, my_own = own_next;
-    if (c + 1 < nchunks) {
-      prefetch(c + 1, buf ^ 1);
-      const int jn = (c + 1) * 32 + lane;
-      info_next = jn < nev ? a.ev_info[jn] : -1;
-      own_next = jn < nev ? (int)a.ev_own[jn] : -1;
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
+    prefetch(c + kOsSeqStages - 1);                                           // its slot was consumed in iteration c - 1
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kOsSeqStages - 1) : "memory");
     __syncwarp();
-    const int* rows = s_rows + buf * kRowInts;
+    const int* rows = s_rows + (c % kOsSeqStages) * kChunkInts;
+    const int j = c * 32 + lane;
+    const int info = j < nev ? rows[lane * kOsRowStride + kOsRowInfo] : -1;
+    const int my_own = rows[lane * kOsRowStride + kOsRowOwn];
     const int my_v = info >> 2, my_kind = info & 3;
     bool cand = info >= 0;
     int my_p = -1;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (m == 0u) break;
       const int src = __ffs(m) - 1;                                           // the earliest one is the next in point order
-      const int nb = lane < kOsRow ? rows[src * kOsRow + lane] : -1;
+      const int nb = lane < kOsRow ? rows[src * kOsRowStride + lane] : -1;
       const unsigned s_nb = nb >= 0 ? os_state<kBytes>(st, nb) : 0u;
       const unsigned lab = __ballot_sync(0xffffffffu, nb >= 0 && s_nb != 0u);   // (all state reads are done once this returns)
       const int p = lab ? __ffs(lab) - 1 : 0;
@@ -425,9 +425,8 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
       if (lane == src) { my_p = p; cand = false; }
       __syncwarp();
     }
-    const int j = c * 32 + lane;
     if (j < nev && my_p >= 0) a.ev_p[j] = (signed char)my_p;
-    __syncwarp();
+    __syncwarp();                                                             // the slot may be refilled from the next iteration on
   }
 }
 
@@ -456,7 +455,7 @@ __global__ void __launch_bounds__(256) k_os_union(const __grid_constant__ OsArgs
   if (j >= (unsigned)a.params[5] || l >= (unsigned)kOsRow) return;
   const int p = a.ev_p[j];
   if (p < 0 || (int)l < p) return;
-  const int nb = a.rows[(size_t)j * kOsRow + l];
+  const int nb = a.rows[(size_t)j * kOsRowStride + l];
   if (nb < 0) return;
   const int info = a.ev_info[j];
   const int seed = (info & 3) == 2 ? a.ev_pt[j] : a.f1[info >> 2];

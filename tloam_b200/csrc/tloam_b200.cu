@@ -2313,7 +2313,7 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   const size_t o_pts = take(n * 24), o_pol = take(n * 24), o_enc = take(64), o_ext = take(64), o_par = take(64),
                o_bnd = take(kOsMaxBounds * 8), o_key = take(n * 4), o_crd = take(n * 12), o_tab = take(cap * 8), o_sv = take(cap * 4),
                o_ps = take(n * 4), o_vid = take(n * 4), o_f1 = take(n * 4), o_f2 = take(n * 4), o_vc = take(n * 12),
-               o_ek = take(n * 4), o_ept = take(n * 4), o_ei = take(n32 * 4), o_rows = take(n32 * kOsRow * 4), o_ep = take(n32), o_eo = take(n32),
+               o_ek = take(n * 4), o_ept = take(n * 4), o_ei = take(n32 * 4), o_rows = take((n32 + 32 * kOsSeqStages) * kOsRowStride * 4), o_ep = take(n32),
                o_stg = take(state_words * 4), o_par2 = take(n * 4), o_root = take(n * 4), o_cnt = take(n * 4), o_clr = take(n * 4),
                o_crr = take(n * 4), o_cl = take(n * 4), o_sz = take(n * 4), o_pk = take(n * 4), o_box = take(n * 48), o_benc = take(n * 48),
                o_cc = take((size_t)a.nchunk * kOsKeys * 4), o_kb = take((kOsKeys + 1) * 4), o_pa = take(n * 4), o_pb = take(n * 4),
@@ -2329,12 +2329,12 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   a.ext = (double*)(b + o_ext); a.params = (int*)(b + o_par); a.bounds = (double*)(b + o_bnd); a.key = (int*)(b + o_key);
   a.coord = (int*)(b + o_crd); a.table = (unsigned long long*)(b + o_tab); a.slot_vid = (int*)(b + o_sv); a.pslot = (int*)(b + o_ps);
   a.vid = (int*)(b + o_vid); a.f1 = (int*)(b + o_f1); a.f2 = (int*)(b + o_f2); a.vcoord = (int*)(b + o_vc); a.evkey = (int*)(b + o_ek);
-  a.ev_pt = (int*)(b + o_ept); a.ev_info = (int*)(b + o_ei); a.rows = (int*)(b + o_rows); a.ev_p = (signed char*)(b + o_ep); a.ev_own = (signed char*)(b + o_eo);
+  a.ev_pt = (int*)(b + o_ept); a.ev_info = (int*)(b + o_ei); a.rows = (int*)(b + o_rows); a.ev_p = (signed char*)(b + o_ep);
   a.state_g = (unsigned*)(b + o_stg); a.parent = (int*)(b + o_par2); a.root = (int*)(b + o_root); a.cnt = (int*)(b + o_cnt);
   a.cl_root = (int*)(b + o_clr); a.cl_rank_of_root = (int*)(b + o_crr); a.cluster = (int*)(b + o_cl); a.sizes = (int*)(b + o_sz);
   a.pkey = (int*)(b + o_pk); a.boxes = (double*)(b + o_box); a.box_enc = (unsigned long long*)(b + o_benc); a.chunk_cnt = (unsigned*)(b + o_cc); a.key_base = (unsigned*)(b + o_kb);
   a.perm_a = (int*)(b + o_pa); a.perm_b = (int*)(b + o_pb); a.out_seg = (unsigned long long*)(b + o_seg);
-  const size_t seq_fixed = 2 * 32 * kOsRow * sizeof(int);
+  const size_t seq_fixed = (size_t)kOsSeqStages * 32 * kOsRowStride * sizeof(int);
   const size_t state_bytes = round_up(n, 4) + 8;                           // one byte per voxel (at most n voxels)
   const bool seq_bytes = seq_fixed + state_bytes <= (size_t)kOsSeqSmemBytes && !getenv("TLOAM_B200_DCVC_PACKED");
   const int use_smem = seq_fixed + state_words * 4 <= (size_t)kOsSeqSmemBytes && !getenv("TLOAM_B200_DCVC_GLOBAL") ? 1 : 0;
