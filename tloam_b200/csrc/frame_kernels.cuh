@@ -688,15 +688,23 @@ __global__ void __launch_bounds__(kBlk) k_fitness(const __grid_constant__ Device
 
 // sums the per-block partials of k_fitness per cloud and leaves (fitness, rmse) in the frame state
 // (ref: registration.cpp:278-284, 292-293: per type matched / total and sqrt(sum d2 / matched), summed over the types)
-__global__ void k_fitness_reduce(const __grid_constant__ DeviceCtx ctx, const double* part /*[blocks][2]*/) {
-  if (threadIdx.x != 0) return;
-  double fit = 0.0, rm = 0.0;
-  for (int c = 0; c < 4; ++c) {
-    double err = 0.0, cnt = 0.0;
-    for (int b = ctx.blk_off[c]; b < ctx.blk_off[c + 1]; ++b) { err += part[2 * b]; cnt += part[2 * b + 1]; }
-    if (cnt > 0.0) { fit += cnt / (double)ctx.n[c]; rm += sqrt(err / cnt); }
+__global__ void __launch_bounds__(128) k_fitness_reduce(const __grid_constant__ DeviceCtx ctx, const double* part /*[blocks][2]*/) {
+  // one warp per cloud: lane-strided partial sums, then a butterfly (a fixed tree: the result does not depend on timing)
+  __shared__ double s_fit[4], s_rm[4];
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double err = 0.0, cnt = 0.0;
+  for (int b = ctx.blk_off[c] + lane; b < ctx.blk_off[c + 1]; b += 32) { err += part[2 * b]; cnt += part[2 * b + 1]; }
+  for (int o = 16; o > 0; o >>= 1) { err += __shfl_xor_sync(0xffffffffu, err, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+  if (lane == 0) {
+    const bool any = cnt > 0.0;
+    s_fit[c] = any ? cnt / (double)ctx.n[c] : 0.0;
+    s_rm[c] = any ? sqrt(err / cnt) : 0.0;
   }
-  ctx.st->fitness = fit; ctx.st->rmse = rm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctx.st->fitness = ((s_fit[0] + s_fit[1]) + s_fit[2]) + s_fit[3];
+    ctx.st->rmse = ((s_rm[0] + s_rm[1]) + s_rm[2]) + s_rm[3];
+  }
 }
 
 __global__ void k_functor(int type, Predict x6, unsigned m, const double* p, const double* a, const double* bq,

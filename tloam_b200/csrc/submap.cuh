@@ -28,7 +28,8 @@ struct VoxArgs {
   unsigned n;
   double lo[3], hi[3];         // crop box, inclusive (+-DBL_MAX = no crop)
   double voxel;
-  unsigned long long* minenc;  // [3] ordered-uint encodings of the min bound of the cropped cloud
+  unsigned long long* minenc;  // [3] COMPLEMENTED ordered-uint encodings of the min bound of the cropped cloud (0 = none yet:
+                               //     the whole scratch area is cleared by ONE memset; updated with atomicMax)
   unsigned long long* keys;    // [mask+1] 0 = empty
   long long* sums;             // [3*(mask+1)] fixed-point offset sums
   unsigned* cnt;               // [mask+1]
@@ -66,6 +67,7 @@ __global__ void k_transform_append(const double* in, unsigned n, double* out, co
 }
 
 __global__ void __launch_bounds__(256) k_vox_min(VoxArgs a) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.out_count = 0u;              // k_vox_emit (two launches later) counts into it
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
   const unsigned n = vox_n(a);
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) k_vox_min(VoxArgs a) {
   if (threadIdx.x < 3) {
     double lo = s_mn[0][threadIdx.x];
     for (int wi = 1; wi < 8; ++wi) lo = fmin(lo, s_mn[wi][threadIdx.x]);
-    atomicMin(&a.minenc[threadIdx.x], enc_ordered(lo));
+    atomicMax(&a.minenc[threadIdx.x], ~enc_ordered(lo));
   }
 }
 
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256) k_vox_accum(VoxArgs a) {
   long long q[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double mb = dec_ordered(a.minenc[d]) - a.voxel * 0.5;            // voxel_min_bound (:367)
+    const double mb = dec_ordered(~a.minenc[d]) - a.voxel * 0.5;            // voxel_min_bound (:367)
     const double ref = (p[d] - mb) / a.voxel;                              // :381
     idx[d] = (int)floor(ref);
     q[d] = llrint((p[d] - (mb + (double)idx[d] * a.voxel)) * kVoxFix);
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(256) k_vox_emit(VoxArgs a) {
   const int idx[3] = {(int)((key >> 42) & 0x1FFFFFu), (int)((key >> 21) & 0x1FFFFFu), (int)(key & 0x1FFFFFu)};
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double mb = dec_ordered(a.minenc[d]) - a.voxel * 0.5;
+    const double mb = dec_ordered(~a.minenc[d]) - a.voxel * 0.5;
     a.out[3ull * j + d] = mb + (double)idx[d] * a.voxel + ((double)a.sums[3ull * s + d] / kVoxFix) / (double)c;   // GetAveragePoint
   }
 }
