@@ -57,7 +57,15 @@ struct tloam_b200_handle {
   // source
   size_t n_src[4] = {0, 0, 0, 0};
   bool have_src = false, have_tgt = false, frame_pending = false;
-  double* d_stage_src = nullptr; size_t cap_stage_src = 0;      // points
+  double* d_stage_src = nullptr; size_t cap_stage_src = 0;      // points (the CURRENT staging buffer: one of d_stage_buf[])
+  // pipelined handles (set_async_inputs) upload scan k+1 on a stream of its own while frame k is still being registered:
+  // two staging buffers alternate; a buffer is free again once its last reader (k_stage_source, or the submap update
+  // that appends the staged edge / ground features) has run
+  double* d_stage_buf[2] = {nullptr, nullptr}; size_t cap_stage_buf[2] = {0, 0};
+  int stage_cur = 0;
+  cudaStream_t src_stream = nullptr;
+  cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
+  bool stage_free_valid[2] = {false, false};
   double* d_feat = nullptr; size_t cap_pad = 0;                 // 3 + 2 + 6 arrays of cap_pad doubles
   unsigned char* d_flags = nullptr;                             // flags + active
   int* d_blk_count = nullptr; double* d_partial = nullptr; size_t cap_blocks = 0;
@@ -230,6 +238,9 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
     if (cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_src, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->fit_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->src_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&h->ev_stage_free[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreateWithFlags(&h->ev_fit[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 2; ++i)
@@ -288,7 +299,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (!h) return TLOAM_B200_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_stage_src); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
+  cudaFree(h->d_stage_buf[0]); cudaFree(h->d_stage_buf[1]); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
   cudaFree(h->d_partial); cudaFree(h->d_counter); if (h->own_state) cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_blob_in); cudaFree(h->d_dbg);
   cudaFree(h->d_acc[0]); cudaFree(h->d_acc[1]); cudaFree(h->d_acc_tmp); cudaFree(h->d_cat); cudaFree(h->d_sphere0);
@@ -311,6 +322,8 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   for (int i = 0; i < 5; ++i) if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
   if (h->ev_src) cudaEventDestroy(h->ev_src);
   if (h->fit_stream) { cudaStreamSynchronize(h->fit_stream); cudaStreamDestroy(h->fit_stream); }
+  if (h->src_stream) { cudaStreamSynchronize(h->src_stream); cudaStreamDestroy(h->src_stream); }
+  for (int i = 0; i < 2; ++i) if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_fit[i]) cudaEventDestroy(h->ev_fit[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_res[i]) cudaEventDestroy(h->ev_res[i]);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -352,12 +365,19 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   // (re)allocations: a pointer is nulled and its capacity zeroed right after the free, and the new capacity is only
   // committed once the allocation succeeded, so a failed cudaMalloc leaves the handle consistent
   h->have_src = false; h->src_staged = false;
-  if (stage && total > h->cap_stage_src) {
-    cudaFree(h->d_stage_src); h->d_stage_src = nullptr; h->cap_stage_src = 0;
+  const bool prefetch = stage && !on_device && h->async_inputs;          // upload beside the frame that is still running
+  if (prefetch) h->stage_cur ^= 1;
+  const int sb = h->stage_cur;
+  if (stage && total > h->cap_stage_buf[sb]) {
+    cudaFree(h->d_stage_buf[sb]); h->d_stage_buf[sb] = nullptr; h->cap_stage_buf[sb] = 0;   // (cudaFree waits for its readers)
+    h->d_stage_src = nullptr; h->cap_stage_src = 0;
     const size_t ncap = total + total / 4 + 1024;
-    CU_TRY(cudaMalloc(&h->d_stage_src, ncap * 3 * sizeof(double)));
-    h->cap_stage_src = ncap;
+    CU_TRY(cudaMalloc(&h->d_stage_buf[sb], ncap * 3 * sizeof(double)));
+    h->cap_stage_buf[sb] = ncap;
   }
+  h->d_stage_src = h->d_stage_buf[sb]; h->cap_stage_src = h->cap_stage_buf[sb];
+  cudaStream_t up = prefetch ? h->src_stream : h->stream;
+  if (prefetch && h->stage_free_valid[sb]) CU_TRY(cudaStreamWaitEvent(up, h->ev_stage_free[sb], 0));
   if (pad > h->cap_pad) {
     cudaFree(h->d_feat); cudaFree(h->d_flags); h->d_feat = nullptr; h->d_flags = nullptr; h->cap_pad = 0;
     const size_t ncap = round_up(pad + pad / 4, kBlk);
@@ -384,7 +404,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
     src[k] = stage ? h->d_stage_src + 3 * off : xyz[k];
     if (n[k] > 0 && stage)
       CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, up));
     c.n[k] = (int)n[k];
     c.pad_off[k] = (int)poff;
     off += n[k];
@@ -399,11 +419,13 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   c.flags = h->d_flags; c.active = h->d_flags + cp;
   c.blk_count = h->d_blk_count; c.blk_cap = (int)h->cap_blocks; c.partial = h->d_partial;
   h->total_blocks = c.blk_off[4];
-  if (!on_device) CU_TRY(cudaEventRecord(h->ev_src, h->stream));      // the uploads are in; the caller's buffers are free
+  if (!on_device) CU_TRY(cudaEventRecord(h->ev_src, up));             // the uploads are in; the caller's buffers are free
+  if (prefetch) CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_src, 0));
   if (h->total_blocks > 0) {
     TL_LAUNCH(TLOAM_B200_K_STAGE_SOURCE, (k_stage_source<<<h->total_blocks, kBlk, 0, h->stream>>>(src[0], src[1], src[2], src[3], c, f, f + cp, f + 2 * cp)));
     CU_TRY(cudaGetLastError());
   }
+  if (stage) { CU_TRY(cudaEventRecord(h->ev_stage_free[sb], h->stream)); h->stage_free_valid[sb] = true; }
   h->have_src = true;
   h->src_staged = stage;
   if (!on_device && !h->async_inputs) CU_TRY(cudaEventSynchronize(h->ev_src));    // caller buffers may be freed on return
@@ -2057,6 +2079,7 @@ static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, con
     h->n_acc[k] = nall;
     h->cum_add[k] += nadd;
   }
+  CU_TRY(cudaEventRecord(h->ev_stage_free[h->stage_cur], h->stream));   // the staged source has been appended: its buffer is free
   // asynchronous read-back of the two exact counts (tightens the bounds of later frames)
   {
     tloam_b200_handle::CntProbe& pr = h->probes[h->probe_next];
