@@ -688,7 +688,9 @@ __global__ void __launch_bounds__(kBlk) k_fitness(const __grid_constant__ Device
 
 // sums the per-block partials of k_fitness per cloud and leaves (fitness, rmse) in the frame state
 // (ref: registration.cpp:278-284, 292-293: per type matched / total and sqrt(sum d2 / matched), summed over the types)
-__global__ void __launch_bounds__(128) k_fitness_reduce(const __grid_constant__ DeviceCtx ctx, const double* part /*[blocks][2]*/) {
+// `out` = {fitness, rmse}: NOT the frame state when the kernel runs beside the registration -- the solver block carries the
+// whole FrameState through shared memory and writes it back, which would clobber the two words.
+__global__ void __launch_bounds__(128) k_fitness_reduce(const __grid_constant__ DeviceCtx ctx, const double* part /*[blocks][2]*/, double* out) {
   // one warp per cloud: lane-strided partial sums, then a butterfly (a fixed tree: the result does not depend on timing)
   __shared__ double s_fit[4], s_rm[4];
   const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -702,8 +704,8 @@ __global__ void __launch_bounds__(128) k_fitness_reduce(const __grid_constant__ 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    ctx.st->fitness = ((s_fit[0] + s_fit[1]) + s_fit[2]) + s_fit[3];
-    ctx.st->rmse = ((s_rm[0] + s_rm[1]) + s_rm[2]) + s_rm[3];
+    out[0] = ((s_fit[0] + s_fit[1]) + s_fit[2]) + s_fit[3];
+    out[1] = ((s_rm[0] + s_rm[1]) + s_rm[2]) + s_rm[3];
   }
 }
 

@@ -365,7 +365,8 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   // (re)allocations: a pointer is nulled and its capacity zeroed right after the free, and the new capacity is only
   // committed once the allocation succeeded, so a failed cudaMalloc leaves the handle consistent
   h->have_src = false; h->src_staged = false;
-  const bool prefetch = stage && !on_device && h->async_inputs;          // upload beside the frame that is still running
+  static const bool no_prefetch = getenv("TLOAM_B200_NO_PREFETCH") != nullptr;   // A/B knob
+  const bool prefetch = stage && !on_device && h->async_inputs && !no_prefetch;   // upload beside the frame that is still running
   if (prefetch) h->stage_cur ^= 1;
   const int sb = h->stage_cur;
   if (stage && total > h->cap_stage_buf[sb]) {
@@ -392,7 +393,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
     CU_TRY(cudaMalloc(&h->d_blk_count, 2 * ncap * sizeof(int)));
     CU_TRY(cudaMemsetAsync(h->d_blk_count, 0, 2 * ncap * sizeof(int), h->stream));
     CU_TRY(cudaMalloc(&h->d_partial, ncap * kNRed * sizeof(double)));
-    CU_TRY(cudaMalloc(&h->d_fit, ncap * 2 * sizeof(double)));
+    CU_TRY(cudaMalloc(&h->d_fit, (ncap * 2 + 2) * sizeof(double)));   // + {fitness, rmse} of the side-stream reduction
     h->cap_blocks = ncap; h->cap_fit = ncap;
   }
   DeviceCtx& c = h->ctx;
@@ -953,14 +954,15 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c, bool fused) {
   // join inside the captured graph; the frame leaves 85 % of the SMs idle) and join before the result is copied.
   // With profiling on (events around every launch on h->stream) they stay in line.
   const bool fit = h->frame_fitness && nb > 0;
-  cudaStream_t fs = h->profiling ? h->stream : h->fit_stream;
+  static const bool fit_inline = getenv("TLOAM_B200_FIT_INLINE") != nullptr;      // A/B knob
+  cudaStream_t fs = (h->profiling || fit_inline) ? h->stream : h->fit_stream;
   if (fit) {
     if (fs != h->stream) {
       CU_TRY(cudaEventRecord(h->ev_fit[0], h->stream));
       CU_TRY(cudaStreamWaitEvent(fs, h->ev_fit[0], 0));
     }
     TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness<<<nb, kBlk, 0, fs>>>(c, h->cfg.fitness_thres * h->cfg.fitness_thres, h->d_fit)));
-    TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness_reduce<<<1, 128, 0, fs>>>(c, h->d_fit)));
+    TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness_reduce<<<1, 128, 0, fs>>>(c, h->d_fit, h->d_fit + 2 * h->cap_fit)));
     if (fs != h->stream) CU_TRY(cudaEventRecord(h->ev_fit[1], fs));
   }
   CU_TRY(cudaMemcpyAsync(h->d_predict, h->h_predict, sizeof(Predict), cudaMemcpyHostToDevice, h->stream));
@@ -976,7 +978,12 @@ static int enqueue_frame(tloam_b200_handle* h, const DeviceCtx& c, bool fused) {
     for (int it = 0; it < h->cfg.ceres_max_num_iterations; ++it)
       TL_LAUNCH(TLOAM_B200_K_EVAL, (k_eval<false, false><<<ne, kBlk, 0, h->stream>>>(c, nt)));
   }
-  if (fit && fs != h->stream) CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_fit[1], 0));   // join
+  if (fit) {
+    if (fs != h->stream) CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_fit[1], 0));        // join
+    // into the frame state only now: the solver blocks write the whole state back while the frame runs
+    CU_TRY(cudaMemcpyAsync((char*)h->d_state + offsetof(FrameState, fitness), h->d_fit + 2 * h->cap_fit, 2 * sizeof(double),
+                           cudaMemcpyDeviceToDevice, h->stream));
+  }
   // result[16] + {frame_done, status} + {fitness, rmse}: contiguous in FrameState.  Pipelined handles copy it after the
   // graph launch into alternating slots instead (scan_match_enqueue)
   if (!h->async_inputs)
@@ -1521,7 +1528,7 @@ int tloam_b200_fitness(tloam_b200_handle* h, double* fitness, double* rmse) {
   // block partials live in a buffer sized with the source (no allocation on this per-frame health metric); the
   // per-cloud sums are formed on the device in block order and land in the frame state
   TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness<<<nb, kBlk, 0, h->stream>>>(h->ctx, h->cfg.fitness_thres * h->cfg.fitness_thres, h->d_fit)));
-  TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness_reduce<<<1, 128, 0, h->stream>>>(h->ctx, h->d_fit)));
+  TL_LAUNCH(TLOAM_B200_K_FITNESS, (k_fitness_reduce<<<1, 128, 0, h->stream>>>(h->ctx, h->d_fit, reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_state) + offsetof(FrameState, fitness)))));
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaMemcpyAsync(h->h_result + 20, (const char*)h->d_state + offsetof(FrameState, fitness), 2 * sizeof(double),
                          cudaMemcpyDeviceToHost, h->stream));
