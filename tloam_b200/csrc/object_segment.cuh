@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(32) k_os_seq(const __grid_constant__ OsArgs a,
       const int p = lab ? __ffs(lab) - 1 : 0;
       const bool take = nb >= 0 && lane >= p && !(s_nb & 2u);
       const bool own_first = lane == src && my_kind != 2 && my_own < p;        // own voxel listed before p only: first point labelled
+      __syncwarp();                                                           // every state read above precedes the writes below
       if (kBytes) {
         if (take) reinterpret_cast<volatile unsigned char*>(st)[nb] = 2;
         if (own_first) reinterpret_cast<volatile unsigned char*>(st)[my_v] = 1;
