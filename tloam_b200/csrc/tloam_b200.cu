@@ -126,6 +126,15 @@ struct tloam_b200_handle {
   double* d_sphere0 = nullptr;             size_t n_sphere0 = 0; bool sphere_is_init = false;  // frame-0 sphere submap
   double* d_up = nullptr;                  size_t cap_up = 0;                                   // upload staging
   unsigned char* d_vox = nullptr;          size_t cap_vox = 0;                                  // voxel hash scratch
+  // submap update: the ground accumulator is cropped / down-sampled on a stream of its own beside the edge accumulator
+  // (own scratch and output buffer); the newest planar frame is uploaded on src_stream while the frame is registered
+  unsigned char* d_vox1 = nullptr;         size_t cap_vox1 = 0;
+  double* d_acc_tmp1 = nullptr;            size_t cap_acc_tmp1 = 0;
+  double* d_up_planar = nullptr;           size_t cap_up_planar = 0;
+  cudaStream_t sub_stream = nullptr;
+  cudaEvent_t ev_sub[2] = {nullptr, nullptr};
+  cudaEvent_t ev_planar_in = nullptr, ev_planar_free = nullptr;
+  bool planar_free_valid = false;
   // ---- PCA feature extraction ((f)-2): one arena, carved up per call ----
   unsigned char* d_fe = nullptr;           size_t cap_fe = 0;  bool fe_attr_set = false;
   double* d_pose = nullptr;
@@ -239,6 +248,11 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
   if (cudaEventCreateWithFlags(&h->ev_src, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->fit_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->src_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->sub_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&h->ev_sub[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_planar_in, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_planar_free, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreateWithFlags(&h->ev_stage_free[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 2; ++i)
@@ -323,6 +337,11 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->ev_src) cudaEventDestroy(h->ev_src);
   if (h->fit_stream) { cudaStreamSynchronize(h->fit_stream); cudaStreamDestroy(h->fit_stream); }
   if (h->src_stream) { cudaStreamSynchronize(h->src_stream); cudaStreamDestroy(h->src_stream); }
+  if (h->sub_stream) { cudaStreamSynchronize(h->sub_stream); cudaStreamDestroy(h->sub_stream); }
+  for (int i = 0; i < 2; ++i) if (h->ev_sub[i]) cudaEventDestroy(h->ev_sub[i]);
+  if (h->ev_planar_in) cudaEventDestroy(h->ev_planar_in);
+  if (h->ev_planar_free) cudaEventDestroy(h->ev_planar_free);
+  cudaFree(h->d_vox1); cudaFree(h->d_acc_tmp1); cudaFree(h->d_up_planar);
   for (int i = 0; i < 2; ++i) if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_fit[i]) cudaEventDestroy(h->ev_fit[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_res[i]) cudaEventDestroy(h->ev_res[i]);
@@ -1744,33 +1763,36 @@ static int ensure_dev(tloam_b200_handle* h, double** p, size_t* cap, size_t need
 // device memory.
 static int voxel_pipeline(tloam_b200_handle* h, const double* d_in, size_t n_bound, const unsigned* n_dev, unsigned n_add,
                           const double* lo, const double* hi, const double* box_pose, double box_len, double voxel,
-                          double* d_out, unsigned* out_count) {
-  if (n_bound == 0) { CU_TRY(cudaMemsetAsync(out_count, 0, sizeof(unsigned), h->stream)); return TLOAM_B200_OK; }
+                          double* d_out, unsigned* out_count, cudaStream_t stream = nullptr, int scratch = 0) {
+  if (!stream) stream = h->stream;
+  if (n_bound == 0) { CU_TRY(cudaMemsetAsync(out_count, 0, sizeof(unsigned), stream)); return TLOAM_B200_OK; }
   if (!(voxel > 0.0)) return TLOAM_B200_ERR_INVALID_ARG;
   const unsigned tsize = next_pow2(2 * n_bound + 1);
   const size_t bytes = 256 + (size_t)tsize * (8 + 24 + 4);
-  if (bytes > h->cap_vox) {
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_vox); h->d_vox = nullptr; h->cap_vox = 0;
-    CU_TRY(cudaMalloc(&h->d_vox, bytes + bytes / 2));
-    h->cap_vox = bytes + bytes / 2;
+  unsigned char*& d_vox = scratch ? h->d_vox1 : h->d_vox;
+  size_t& cap_vox = scratch ? h->cap_vox1 : h->cap_vox;
+  if (bytes > cap_vox) {
+    CU_TRY(cudaStreamSynchronize(stream));
+    cudaFree(d_vox); d_vox = nullptr; cap_vox = 0;
+    CU_TRY(cudaMalloc(&d_vox, bytes + bytes / 2));
+    cap_vox = bytes + bytes / 2;
   }
   VoxArgs a;
   a.in = d_in; a.n = (unsigned)n_bound; a.voxel = voxel;
   a.n_dev = n_dev; a.n_add = n_add; a.box_pose = box_pose; a.box_len = box_len;
   for (int d = 0; d < 3; ++d) { a.lo[d] = lo ? lo[d] : -DBL_MAX; a.hi[d] = hi ? hi[d] : DBL_MAX; }
-  a.minenc = reinterpret_cast<unsigned long long*>(h->d_vox);            // [0..2] min bound
+  a.minenc = reinterpret_cast<unsigned long long*>(d_vox);            // [0..2] min bound
   a.out_count = out_count;
-  a.keys = reinterpret_cast<unsigned long long*>(h->d_vox + 256);
-  a.sums = reinterpret_cast<long long*>(h->d_vox + 256 + (size_t)tsize * 8);
-  a.cnt = reinterpret_cast<unsigned*>(h->d_vox + 256 + (size_t)tsize * 32);
+  a.keys = reinterpret_cast<unsigned long long*>(d_vox + 256);
+  a.sums = reinterpret_cast<long long*>(d_vox + 256 + (size_t)tsize * 8);
+  a.cnt = reinterpret_cast<unsigned*>(d_vox + 256 + (size_t)tsize * 32);
   a.mask = tsize - 1u;
   a.out = d_out;
-  CU_TRY(cudaMemsetAsync(h->d_vox, 0, 256 + (size_t)tsize * 36, h->stream));   // ONE memset: min bound (complemented), keys, sums, counts
+  CU_TRY(cudaMemsetAsync(d_vox, 0, 256 + (size_t)tsize * 36, stream));   // ONE memset: min bound (complemented), keys, sums, counts
   const unsigned tb = 256, gb = (unsigned)((n_bound + tb - 1) / tb);
-  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_min<<<(gb < 592u ? gb : 592u), tb, 0, h->stream>>>(a)));
-  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_accum<<<gb, tb, 0, h->stream>>>(a)));
-  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_emit<<<(tsize + tb - 1) / tb, tb, 0, h->stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_min<<<(gb < 592u ? gb : 592u), tb, 0, stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_accum<<<gb, tb, 0, stream>>>(a)));
+  TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_vox_emit<<<(tsize + tb - 1) / tb, tb, 0, stream>>>(a)));
   CU_TRY(cudaGetLastError());
   return TLOAM_B200_OK;
 }
@@ -2043,14 +2065,42 @@ static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, con
   }
   const unsigned tb = 256;
   // ---- planar sliding window (:207-217, 232-242): newest frame transformed by its pose ----
-  if ((rc = upload_points(h, planar_sub, np)) != TLOAM_B200_OK) return rc;
+  // pipelined handles: the upload runs on src_stream (it does not depend on the frame that is still being registered);
+  // its buffer is free again once the transform below has read it
+  static const bool no_prefetch = getenv("TLOAM_B200_NO_PREFETCH") != nullptr;
+  const bool side = h->async_inputs && !h->profiling && !no_prefetch;
+  const double* d_planar_in = nullptr;
+  if (side) {
+    if (np > h->cap_up_planar) {
+      CU_TRY(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_up_planar); h->d_up_planar = nullptr; h->cap_up_planar = 0;
+      CU_TRY(cudaMalloc(&h->d_up_planar, (np + np / 2 + 1024) * 3 * sizeof(double)));
+      h->cap_up_planar = np + np / 2 + 1024;
+      h->planar_free_valid = false;
+    }
+    if (h->planar_free_valid) CU_TRY(cudaStreamWaitEvent(h->src_stream, h->ev_planar_free, 0));
+    if (np) CU_TRY(cudaMemcpyAsync(h->d_up_planar, planar_sub, np * 3 * sizeof(double), cudaMemcpyHostToDevice, h->src_stream));
+    CU_TRY(cudaEventRecord(h->ev_planar_in, h->src_stream));
+    d_planar_in = h->d_up_planar;
+  } else {
+    if ((rc = upload_points(h, planar_sub, np)) != TLOAM_B200_OK) return rc;
+    d_planar_in = h->d_up;
+  }
+  // ---- fork: the ground accumulator (k = 1 below) is appended, cropped and down-sampled on sub_stream ----
+  cudaStream_t gs = side ? h->sub_stream : h->stream;
+  if (side) {
+    CU_TRY(cudaEventRecord(h->ev_sub[0], h->stream));
+    CU_TRY(cudaStreamWaitEvent(gs, h->ev_sub[0], 0));
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_planar_in, 0));
+  }
   double* slot = nullptr; size_t slot_cap = 0;
   if ((int)h->ring.size() >= cf.planar_frame_size) {            // recycle the oldest buffer
     slot = h->ring.front(); slot_cap = h->ring_cap.front();
     h->ring.erase(h->ring.begin()); h->ring_n.erase(h->ring_n.begin()); h->ring_cap.erase(h->ring_cap.begin());
   }
   if ((rc = ensure_dev(h, &slot, &slot_cap, np, false)) != TLOAM_B200_OK) return rc;
-  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, h->stream>>>(h->d_up, (unsigned)np, slot, d_pose, nullptr)));
+  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, h->stream>>>(d_planar_in, (unsigned)np, slot, d_pose, nullptr)));
+  if (side) { CU_TRY(cudaEventRecord(h->ev_planar_free, h->stream)); h->planar_free_valid = true; }
   h->ring.push_back(slot); h->ring_n.push_back(np); h->ring_cap.push_back(slot_cap);
   size_t tot = 0;
   for (size_t k : h->ring_n) tot += k;
@@ -2072,19 +2122,26 @@ static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, con
   for (int k = 0; k < 2; ++k) {
     const size_t nadd = h->n_src[src_cloud[k]];
     const size_t nall = h->n_acc[k] + nadd;                       // bound
+    cudaStream_t ks = k == 1 ? gs : h->stream;                    // ground on the side stream, own scratch + output buffer
+    double*& tmp = (k == 1 && side) ? h->d_acc_tmp1 : h->d_acc_tmp;
+    size_t& tmp_cap = (k == 1 && side) ? h->cap_acc_tmp1 : h->cap_acc_tmp;
     if ((rc = ensure_dev(h, &h->d_acc[k], &h->cap_acc[k], nall, true)) != TLOAM_B200_OK) return rc;
-    if ((rc = ensure_dev(h, &h->d_acc_tmp, &h->cap_acc_tmp, nall, false)) != TLOAM_B200_OK) return rc;
+    if ((rc = ensure_dev(h, &tmp, &tmp_cap, nall, false)) != TLOAM_B200_OK) return rc;
     unsigned* cur = acc_count(h, k);
-    if (nadd) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((nadd + tb - 1) / tb), tb, 0, h->stream>>>(
+    if (nadd) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((nadd + tb - 1) / tb), tb, 0, ks>>>(
         h->d_stage_src + 3 * soff[src_cloud[k]], (unsigned)nadd, h->d_acc[k], d_pose, cur)));
     h->acc_cur[k] ^= 1;
-    if ((rc = voxel_pipeline(h, h->d_acc[k], nall, cur, (unsigned)nadd, nullptr, nullptr, d_pose, len[k], vox[k], h->d_acc_tmp,
-                             acc_count(h, k))) != TLOAM_B200_OK) return rc;
+    if ((rc = voxel_pipeline(h, h->d_acc[k], nall, cur, (unsigned)nadd, nullptr, nullptr, d_pose, len[k], vox[k], tmp,
+                             acc_count(h, k), ks, (k == 1 && side) ? 1 : 0)) != TLOAM_B200_OK) return rc;
     // the down-sampled cloud becomes the accumulator (swap buffers)
-    double* t = h->d_acc[k]; h->d_acc[k] = h->d_acc_tmp; h->d_acc_tmp = t;
-    size_t tc = h->cap_acc[k]; h->cap_acc[k] = h->cap_acc_tmp; h->cap_acc_tmp = tc;
+    double* t = h->d_acc[k]; h->d_acc[k] = tmp; tmp = t;
+    size_t tc = h->cap_acc[k]; h->cap_acc[k] = tmp_cap; tmp_cap = tc;
     h->n_acc[k] = nall;
     h->cum_add[k] += nadd;
+  }
+  if (side) {                                                     // join
+    CU_TRY(cudaEventRecord(h->ev_sub[1], gs));
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_sub[1], 0));
   }
   CU_TRY(cudaEventRecord(h->ev_stage_free[h->stage_cur], h->stream));   // the staged source has been appended: its buffer is free
   // asynchronous read-back of the two exact counts (tightens the bounds of later frames)
