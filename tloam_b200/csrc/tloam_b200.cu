@@ -133,7 +133,7 @@ struct tloam_b200_handle {
   double* d_up_planar = nullptr;           size_t cap_up_planar = 0;
   cudaStream_t sub_stream = nullptr;
   cudaEvent_t ev_sub[2] = {nullptr, nullptr};
-  cudaEvent_t ev_planar_in = nullptr, ev_planar_free = nullptr;
+  cudaEvent_t ev_planar_in = nullptr, ev_planar_free = nullptr, ev_planar_done = nullptr;
   bool planar_free_valid = false;
   // ---- PCA feature extraction ((f)-2): one arena, carved up per call ----
   unsigned char* d_fe = nullptr;           size_t cap_fe = 0;  bool fe_attr_set = false;
@@ -253,6 +253,7 @@ int tloam_b200_create(const tloam_tls_config* cfg, int device, void* stream, tlo
     if (cudaEventCreateWithFlags(&h->ev_sub[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_planar_in, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_planar_free, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_planar_done, cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 2; ++i)
     if (cudaEventCreateWithFlags(&h->ev_stage_free[i], cudaEventDisableTiming) != cudaSuccess) return fail(TLOAM_B200_ERR_CUDA);
   for (int i = 0; i < 2; ++i)
@@ -341,6 +342,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   for (int i = 0; i < 2; ++i) if (h->ev_sub[i]) cudaEventDestroy(h->ev_sub[i]);
   if (h->ev_planar_in) cudaEventDestroy(h->ev_planar_in);
   if (h->ev_planar_free) cudaEventDestroy(h->ev_planar_free);
+  if (h->ev_planar_done) cudaEventDestroy(h->ev_planar_done);
   cudaFree(h->d_vox1); cudaFree(h->d_acc_tmp1); cudaFree(h->d_up_planar);
   for (int i = 0; i < 2; ++i) if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_fit[i]) cudaEventDestroy(h->ev_fit[i]);
@@ -2086,12 +2088,15 @@ static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, con
     if ((rc = upload_points(h, planar_sub, np)) != TLOAM_B200_OK) return rc;
     d_planar_in = h->d_up;
   }
-  // ---- fork: the ground accumulator (k = 1 below) is appended, cropped and down-sampled on sub_stream ----
+  // ---- fork: the ground accumulator (k = 1 below) is appended, cropped and down-sampled on sub_stream, the planar
+  //      window is assembled on fit_stream (idle between frames), the edge accumulator stays on the handle's stream ----
   cudaStream_t gs = side ? h->sub_stream : h->stream;
+  cudaStream_t ps = side ? h->fit_stream : h->stream;
   if (side) {
     CU_TRY(cudaEventRecord(h->ev_sub[0], h->stream));
     CU_TRY(cudaStreamWaitEvent(gs, h->ev_sub[0], 0));
-    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_planar_in, 0));
+    CU_TRY(cudaStreamWaitEvent(ps, h->ev_sub[0], 0));
+    CU_TRY(cudaStreamWaitEvent(ps, h->ev_planar_in, 0));
   }
   double* slot = nullptr; size_t slot_cap = 0;
   if ((int)h->ring.size() >= cf.planar_frame_size) {            // recycle the oldest buffer
@@ -2099,17 +2104,18 @@ static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, con
     h->ring.erase(h->ring.begin()); h->ring_n.erase(h->ring_n.begin()); h->ring_cap.erase(h->ring_cap.begin());
   }
   if ((rc = ensure_dev(h, &slot, &slot_cap, np, false)) != TLOAM_B200_OK) return rc;
-  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, h->stream>>>(d_planar_in, (unsigned)np, slot, d_pose, nullptr)));
-  if (side) { CU_TRY(cudaEventRecord(h->ev_planar_free, h->stream)); h->planar_free_valid = true; }
+  if (np) TL_LAUNCH(TLOAM_B200_K_SUBMAP, (k_transform_append<<<(unsigned)((np + tb - 1) / tb), tb, 0, ps>>>(d_planar_in, (unsigned)np, slot, d_pose, nullptr)));
+  if (side) { CU_TRY(cudaEventRecord(h->ev_planar_free, ps)); h->planar_free_valid = true; }
   h->ring.push_back(slot); h->ring_n.push_back(np); h->ring_cap.push_back(slot_cap);
   size_t tot = 0;
   for (size_t k : h->ring_n) tot += k;
   if ((rc = ensure_dev(h, &h->d_cat, &h->cap_cat, tot, false)) != TLOAM_B200_OK) return rc;
   size_t off = 0;
   for (size_t f = 0; f < h->ring.size(); ++f) {
-    if (h->ring_n[f]) CU_TRY(cudaMemcpyAsync(h->d_cat + 3 * off, h->ring[f], h->ring_n[f] * 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->ring_n[f]) CU_TRY(cudaMemcpyAsync(h->d_cat + 3 * off, h->ring[f], h->ring_n[f] * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ps));
     off += h->ring_n[f];
   }
+  if (side) CU_TRY(cudaEventRecord(h->ev_planar_done, ps));     // the planar window is assembled
   h->n_cat = tot;
   h->sphere_is_init = false;
   // ---- edge / ground: append the current source features in the world frame (:245-246), crop (:248-264),
@@ -2142,6 +2148,7 @@ static int submap_update_impl(tloam_b200_handle* h, const double* pose_host, con
   if (side) {                                                     // join
     CU_TRY(cudaEventRecord(h->ev_sub[1], gs));
     CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_sub[1], 0));
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_planar_done, 0));
   }
   CU_TRY(cudaEventRecord(h->ev_stage_free[h->stage_cur], h->stream));   // the staged source has been appended: its buffer is free
   // asynchronous read-back of the two exact counts (tightens the bounds of later frames)
