@@ -904,8 +904,9 @@ def main():
             "h2d_bytes_per_step": h2d_sub, "err_vs_ground_truth_last_frame_m": err_sub,
             "fraction_of_value": (world * args.steps / (ms_sub * 1e-3)) / fps, "fitness_last_frame": list(fit_sub),
             "what": "chained device flow: set_source (pinned host scan, async) + scan_match_predicted_async (device-side prediction, "
-                    "getFitnessScore inside the frame) + submap_update_chained (pose and voxel counts stay on the device); the host runs one "
-                    "frame ahead (pipelined results), no host synchronisation between registration and map update; the map never leaves HBM"}
+                    "getFitnessScore inside the frame, on a side stream) + submap_update_chained (pose and voxel counts stay on the device; ground / "
+                    "planar / edge parts on three streams); the host runs one frame ahead (pipelined results, next scan uploaded beside the "
+                    "running frame), no host synchronisation between registration and map update; the map never leaves HBM"}
         if batched:
             line["batched"] = batched
         if feat:
