@@ -147,6 +147,18 @@ def test_gpu_extract_planar_sphere_bit_exact(reg, oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_extract_planar_sphere_long_lists_bit_exact(reg, oracle):
+    """More than 16 384 candidates in a list: the sort leaves its single shared-memory tile (distances >= the tile size in
+    global memory, the rest tile by tile)."""
+    pts = synth.general_cloud(160000, seed=8)
+    cfg = dict(CFG, planar_submap_thres=0.3, planar_vertic_thres=0.9, cvr_submap=0.01)
+    got, ref = reg.extract_planar_sphere(pts, **cfg), oracle.extract_planar_sphere(pts, **cfg)
+    assert len(ref[1]) > 16384
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+
+
+@pytest.mark.gpu
 def test_gpu_feature_far_from_origin_and_lattice_ties(reg, oracle):
     """Coordinates around 1 km (raw-moment cancellation is then ~1e-6 relative: still identical on both sides) and a
     regular lattice, where many neighbours are exactly equidistant (ordering by (d2, index))."""

@@ -385,11 +385,20 @@ __global__ void k_fe_classify(unsigned n, FeParams prm, FeOut out, unsigned long
 }
 
 // Hand-written sort of the compacted candidates: bitonic network over (key descending, index ascending), one block per
-// list (blockIdx.x: 0 planar, 1 sphere), padded to a power of two with sentinels that sort last.  ~10k candidates of a
-// 50k-point cloud: 105 compare-exchange steps of 4 pairs per thread.  Replaces two cub::DeviceRadixSort passes over ALL
-// n points with 64-bit keys (160 of the 280 us of kernels in round 1).
+// list (blockIdx.x: 0 planar, 1 sphere), padded to a power of two with sentinels that sort last.  The network runs in
+// SHARED memory: a tile of 16 384 (key, index) pairs (192 KB) is loaded once per merge level, all compare-exchange
+// distances below the tile size are done there, and only the distances >= the tile size (lists longer than 16 384
+// candidates) touch global memory.  ~10k candidates of a 50k-point cloud: one load, 105 steps in shared memory, one
+// store.  (First version of this round: every step in global memory, 295 us; round 1: two cub::DeviceRadixSort passes
+// over ALL n points with 64-bit keys, 160 us.)
+constexpr unsigned kFeSortTile = 16384u;
+constexpr size_t kFeSortSmemBytes = (size_t)kFeSortTile * (sizeof(unsigned long long) + sizeof(unsigned));
+
 __global__ void __launch_bounds__(1024) k_fe_sort(unsigned long long* key_planar, unsigned* val_planar, unsigned long long* key_sphere,
                                                   unsigned* val_sphere, const unsigned* counts) {
+  extern __shared__ __align__(16) unsigned char fe_sort_raw[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(fe_sort_raw);
+  unsigned* sval = reinterpret_cast<unsigned*>(fe_sort_raw + (size_t)kFeSortTile * sizeof(unsigned long long));
   unsigned long long* key = blockIdx.x == 0 ? key_planar : key_sphere;
   unsigned* val = blockIdx.x == 0 ? val_planar : val_sphere;
   const unsigned total = counts[blockIdx.x];
@@ -399,17 +408,48 @@ __global__ void __launch_bounds__(1024) k_fe_sort(unsigned long long* key_planar
   for (unsigned i = total + threadIdx.x; i < m; i += blockDim.x) { key[i] = 0ull; val[i] = 0xFFFFFFFFu; }   // sentinels: last
   __syncthreads();
   auto before = [](unsigned long long ka, unsigned va, unsigned long long kb, unsigned vb) { return ka > kb || (ka == kb && va < vb); };
-  for (unsigned k = 2u; k <= m; k <<= 1) {
-    for (unsigned j = k >> 1; j > 0u; j >>= 1) {
-      for (unsigned t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+  const unsigned tile = m < kFeSortTile ? m : kFeSortTile;
+  // compare-exchange distances j0, j0 / 2, ..., 1 of merge level k on the tile that starts at `base`, in shared memory
+  auto tile_steps = [&](unsigned base, unsigned k, unsigned j0) {
+    for (unsigned j = j0; j > 0u; j >>= 1) {
+      for (unsigned t = threadIdx.x; t < (tile >> 1); t += blockDim.x) {
         const unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));      // element whose bit j is clear
         const unsigned l = i | j;
-        const bool up = (i & k) == 0u;                                    // this sub-sequence ends up in final order
+        const bool up = ((base + i) & k) == 0u;                           // this sub-sequence ends up in final order
+        const unsigned long long ki = skey[i], kl = skey[l];
+        const unsigned vi = sval[i], vl = sval[l];
+        const bool swap = up ? before(kl, vl, ki, vi) : before(ki, vi, kl, vl);
+        if (swap) { skey[i] = kl; skey[l] = ki; sval[i] = vl; sval[l] = vi; }
+      }
+      __syncthreads();
+    }
+  };
+  if (m <= kFeSortTile) {                                                  // the whole list fits: one load, one store
+    for (unsigned i = threadIdx.x; i < m; i += blockDim.x) { skey[i] = key[i]; sval[i] = val[i]; }
+    __syncthreads();
+    for (unsigned k = 2u; k <= m; k <<= 1) tile_steps(0u, k, k >> 1);
+    for (unsigned i = threadIdx.x; i < m; i += blockDim.x) { key[i] = skey[i]; val[i] = sval[i]; }
+    return;
+  }
+  for (unsigned k = 2u; k <= m; k <<= 1) {
+    unsigned j = k >> 1;
+    for (; j >= kFeSortTile; j >>= 1) {                                    // distances that span tiles: global memory
+      for (unsigned t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+        const unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+        const unsigned l = i | j;
+        const bool up = (i & k) == 0u;
         const unsigned long long ki = key[i], kl = key[l];
         const unsigned vi = val[i], vl = val[l];
         const bool swap = up ? before(kl, vl, ki, vi) : before(ki, vi, kl, vl);
         if (swap) { key[i] = kl; key[l] = ki; val[i] = vl; val[l] = vi; }
       }
+      __syncthreads();
+    }
+    for (unsigned base = 0u; base < m; base += kFeSortTile) {              // the rest of the level, tile by tile
+      for (unsigned i = threadIdx.x; i < kFeSortTile; i += blockDim.x) { skey[i] = key[base + i]; sval[i] = val[base + i]; }
+      __syncthreads();
+      tile_steps(base, k, j);
+      for (unsigned i = threadIdx.x; i < kFeSortTile; i += blockDim.x) { key[base + i] = skey[i]; val[base + i] = sval[i]; }
       __syncthreads();
     }
   }

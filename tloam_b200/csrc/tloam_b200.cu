@@ -1915,7 +1915,12 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_classify<<<gb, tb, 0, h->stream>>>((unsigned)n, prm, A.out, A.key_p_sorted, A.key_s_sorted, A.val_p_sorted,
                                                                               A.val_s_sorted, A.counts)));
     // candidates first compacted, then ordered by (flatness descending, point index ascending): hand-written bitonic sort
-    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_sort<<<2, 1024, 0, h->stream>>>(A.key_p_sorted, A.val_p_sorted, A.key_s_sorted, A.val_s_sorted, A.counts)));
+    static bool fe_sort_attr = false;
+    if (!fe_sort_attr) {
+      CU_TRY(cudaFuncSetAttribute(k_fe_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSortSmemBytes));
+      fe_sort_attr = true;
+    }
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_sort<<<2, 1024, kFeSortSmemBytes, h->stream>>>(A.key_p_sorted, A.val_p_sorted, A.key_s_sorted, A.val_s_sorted, A.counts)));
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_counts<<<1, 32, 0, h->stream>>>(A.key_p_sorted, A.key_s_sorted, A.counts, cfg->planar_num,
                                                                            cfg->sphere_num, cfg->planar_scan_thres, cfg->cvr_scan)));
   }
