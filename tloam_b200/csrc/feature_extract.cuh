@@ -384,7 +384,53 @@ __global__ void k_fe_classify(unsigned n, FeParams prm, FeOut out, unsigned long
   if (sphere) { const unsigned d = s_bs + s_ws[warp] + __popc(bs & ((1u << lane) - 1u)); key_sphere[d] = enc_ordered(f); val_sphere[d] = i; }
 }
 
-// Hand-written sort of the compacted candidates: bitonic network over (key descending, index ascending), one block per
+// Sort of the compacted candidates by (key descending, index ascending), first form: RANK sort.  Lists of up to
+// kFeRankMax candidates (a 50k-point cloud has ~10k) are ordered by counting, for every candidate, how many come
+// before it -- n^2 comparisons, but spread over the whole GPU (one thread per candidate, the list streamed through shared
+// memory in tiles that every thread of the block reads at the same address), where the bitonic network below keeps ONE SM
+// per list busy for ~200 us.  (key, index) pairs are distinct, so the ranks are a permutation.  Longer lists are copied
+// through unchanged and sorted by k_fe_sort.  grid (blocks over the candidate bound, 2 lists).
+constexpr unsigned kFeRankMax = 32768u;
+constexpr int kFeRankTile = 1024;
+
+__global__ void __launch_bounds__(256) k_fe_ranksort(const unsigned long long* key_planar_raw, const unsigned* val_planar_raw,
+                                                     const unsigned long long* key_sphere_raw, const unsigned* val_sphere_raw,
+                                                     unsigned long long* key_planar, unsigned* val_planar, unsigned long long* key_sphere,
+                                                     unsigned* val_sphere, const unsigned* counts) {
+  __shared__ unsigned long long s_key[kFeRankTile];
+  __shared__ unsigned s_val[kFeRankTile];
+  const int list = blockIdx.y;
+  const unsigned long long* src_k = list == 0 ? key_planar_raw : key_sphere_raw;
+  const unsigned* src_v = list == 0 ? val_planar_raw : val_sphere_raw;
+  unsigned long long* dst_k = list == 0 ? key_planar : key_sphere;
+  unsigned* dst_v = list == 0 ? val_planar : val_sphere;
+  const unsigned total = counts[list];
+  if (blockIdx.x * 256u >= total) return;
+  const unsigned e = blockIdx.x * 256u + threadIdx.x;
+  const bool live = e < total;
+  const unsigned long long mk = live ? src_k[e] : 0ull;
+  const unsigned mv = live ? src_v[e] : 0xFFFFFFFFu;
+  if (total > kFeRankMax) {                                                // too long for n^2: k_fe_sort orders it in place
+    if (live) { dst_k[e] = mk; dst_v[e] = mv; }
+    return;
+  }
+  unsigned rank = 0u;
+  for (unsigned base = 0u; base < total; base += kFeRankTile) {
+    const unsigned cnt = min((unsigned)kFeRankTile, total - base);
+    __syncthreads();
+    for (unsigned t = threadIdx.x; t < cnt; t += 256u) { s_key[t] = src_k[base + t]; s_val[t] = src_v[base + t]; }
+    __syncthreads();
+#pragma unroll 8
+    for (unsigned t = 0u; t < cnt; ++t) {
+      const unsigned long long ok = s_key[t];
+      const unsigned ov = s_val[t];
+      rank += (ok > mk || (ok == mk && ov < mv)) ? 1u : 0u;
+    }
+  }
+  if (live) { dst_k[rank] = mk; dst_v[rank] = mv; }
+}
+
+// Second form, for lists longer than kFeRankMax: bitonic network over (key descending, index ascending), one block per
 // list (blockIdx.x: 0 planar, 1 sphere), padded to a power of two with sentinels that sort last.  The network runs in
 // SHARED memory: a tile of 16 384 (key, index) pairs (192 KB) is loaded once per merge level, all compare-exchange
 // distances below the tile size are done there, and only the distances >= the tile size (lists longer than 16 384
@@ -402,7 +448,7 @@ __global__ void __launch_bounds__(1024) k_fe_sort(unsigned long long* key_planar
   unsigned long long* key = blockIdx.x == 0 ? key_planar : key_sphere;
   unsigned* val = blockIdx.x == 0 ? val_planar : val_sphere;
   const unsigned total = counts[blockIdx.x];
-  if (total <= 1u) return;
+  if (total <= kFeRankMax) return;                                         // ordered by k_fe_ranksort already
   unsigned m = 1u;
   while (m < total) m <<= 1;
   for (unsigned i = total + threadIdx.x; i < m; i += blockDim.x) { key[i] = 0ull; val[i] = 0xFFFFFFFFu; }   // sentinels: last
