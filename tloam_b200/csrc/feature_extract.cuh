@@ -387,47 +387,65 @@ __global__ void k_fe_classify(unsigned n, FeParams prm, FeOut out, unsigned long
 // Sort of the compacted candidates by (key descending, index ascending), first form: RANK sort.  Lists of up to
 // kFeRankMax candidates (a 50k-point cloud has ~10k) are ordered by counting, for every candidate, how many come
 // before it -- n^2 comparisons, but spread over the whole GPU (one thread per candidate, the list streamed through shared
-// memory in tiles that every thread of the block reads at the same address), where the bitonic network below keeps ONE SM
-// per list busy for ~200 us.  (key, index) pairs are distinct, so the ranks are a permutation.  Longer lists are copied
-// through unchanged and sorted by k_fe_sort.  grid (blocks over the candidate bound, 2 lists).
+// memory in tiles that every thread of the block reads at the same address; 16 blocks share a candidate block's list and
+// add their partial ranks atomically), where the bitonic network below keeps ONE SM per list busy for ~200 us.  (key, index) pairs are distinct, so the ranks are a permutation.  Longer lists are copied
+// through unchanged and sorted by k_fe_sort.
 constexpr unsigned kFeRankMax = 32768u;
 constexpr int kFeRankTile = 1024;
 
-__global__ void __launch_bounds__(256) k_fe_ranksort(const unsigned long long* key_planar_raw, const unsigned* val_planar_raw,
-                                                     const unsigned long long* key_sphere_raw, const unsigned* val_sphere_raw,
-                                                     unsigned long long* key_planar, unsigned* val_planar, unsigned long long* key_sphere,
-                                                     unsigned* val_sphere, const unsigned* counts) {
+constexpr int kFeRankSplit = 16;       // slices of the list per candidate block: 16 x more blocks than candidates / 256
+
+// grid (blocks over the candidate bound, 2 lists, kFeRankSplit slices): partial rank of my 256 candidates against one slice
+__global__ void __launch_bounds__(256) k_fe_rank(const unsigned long long* key_planar_raw, const unsigned* val_planar_raw,
+                                                 const unsigned long long* key_sphere_raw, const unsigned* val_sphere_raw,
+                                                 unsigned* rank_planar, unsigned* rank_sphere, const unsigned* counts) {
   __shared__ unsigned long long s_key[kFeRankTile];
   __shared__ unsigned s_val[kFeRankTile];
   const int list = blockIdx.y;
   const unsigned long long* src_k = list == 0 ? key_planar_raw : key_sphere_raw;
   const unsigned* src_v = list == 0 ? val_planar_raw : val_sphere_raw;
-  unsigned long long* dst_k = list == 0 ? key_planar : key_sphere;
-  unsigned* dst_v = list == 0 ? val_planar : val_sphere;
+  unsigned* rank_out = list == 0 ? rank_planar : rank_sphere;
   const unsigned total = counts[list];
-  if (blockIdx.x * 256u >= total) return;
+  if (blockIdx.x * 256u >= total || total > kFeRankMax) return;
   const unsigned e = blockIdx.x * 256u + threadIdx.x;
   const bool live = e < total;
   const unsigned long long mk = live ? src_k[e] : 0ull;
   const unsigned mv = live ? src_v[e] : 0xFFFFFFFFu;
-  if (total > kFeRankMax) {                                                // too long for n^2: k_fe_sort orders it in place
-    if (live) { dst_k[e] = mk; dst_v[e] = mv; }
-    return;
-  }
-  unsigned rank = 0u;
-  for (unsigned base = 0u; base < total; base += kFeRankTile) {
-    const unsigned cnt = min((unsigned)kFeRankTile, total - base);
+  const unsigned per = (total + kFeRankSplit - 1u) / kFeRankSplit;
+  const unsigned lo = min(total, blockIdx.z * per), hi = min(total, lo + per);
+  unsigned r0 = 0u, r1 = 0u;
+  for (unsigned base = lo; base < hi; base += kFeRankTile) {
+    const unsigned cnt = min((unsigned)kFeRankTile, hi - base);
     __syncthreads();
     for (unsigned t = threadIdx.x; t < cnt; t += 256u) { s_key[t] = src_k[base + t]; s_val[t] = src_v[base + t]; }
+    for (unsigned t = cnt + threadIdx.x; t < ((cnt + 1u) & ~1u); t += 256u) { s_key[t] = 0ull; s_val[t] = 0xFFFFFFFFu; }   // pad to even: sorts last
     __syncthreads();
-#pragma unroll 8
-    for (unsigned t = 0u; t < cnt; ++t) {
-      const unsigned long long ok = s_key[t];
-      const unsigned ov = s_val[t];
-      rank += (ok > mk || (ok == mk && ov < mv)) ? 1u : 0u;
+#pragma unroll 4
+    for (unsigned t = 0u; t < cnt; t += 2u) {                              // two independent counters
+      const unsigned long long k0 = s_key[t], k1 = s_key[t + 1];
+      const unsigned v0 = s_val[t], v1 = s_val[t + 1];
+      r0 += (k0 > mk || (k0 == mk && v0 < mv)) ? 1u : 0u;
+      r1 += (k1 > mk || (k1 == mk && v1 < mv)) ? 1u : 0u;
     }
   }
-  if (live) { dst_k[rank] = mk; dst_v[rank] = mv; }
+  if (live && (r0 + r1)) atomicAdd(rank_out + e, r0 + r1);
+}
+
+// grid (blocks over the candidate bound, 2 lists): candidates to their ranks (or straight through when the list is too long)
+__global__ void __launch_bounds__(256) k_fe_rank_scatter(const unsigned long long* key_planar_raw, const unsigned* val_planar_raw,
+                                                         const unsigned long long* key_sphere_raw, const unsigned* val_sphere_raw,
+                                                         const unsigned* rank_planar, const unsigned* rank_sphere,
+                                                         unsigned long long* key_planar, unsigned* val_planar, unsigned long long* key_sphere,
+                                                         unsigned* val_sphere, const unsigned* counts) {
+  const int list = blockIdx.y;
+  const unsigned total = counts[list];
+  const unsigned e = blockIdx.x * 256u + threadIdx.x;
+  if (e >= total) return;
+  const unsigned long long k = (list == 0 ? key_planar_raw : key_sphere_raw)[e];
+  const unsigned v = (list == 0 ? val_planar_raw : val_sphere_raw)[e];
+  const unsigned d = total > kFeRankMax ? e : (list == 0 ? rank_planar : rank_sphere)[e];
+  (list == 0 ? key_planar : key_sphere)[d] = k;
+  (list == 0 ? val_planar : val_sphere)[d] = v;
 }
 
 // Second form, for lists longer than kFeRankMax: bitonic network over (key descending, index ascending), one block per

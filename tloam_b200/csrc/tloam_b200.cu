@@ -1863,6 +1863,7 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   while (npad < n) npad <<= 1;
   const size_t o_kps = take(npad * 8), o_kss = take(npad * 8), o_vps = take(npad * 4), o_vss = take(npad * 4), o_cnt = take(256);
   const size_t o_kpr = take(npad * 8), o_ksr = take(npad * 8), o_vpr = take(npad * 4), o_vsr = take(npad * 4);   // compacted, unsorted
+  const size_t o_rk = take(npad * 8);                  // ranks of the two lists
   if (off > h->cap_fe) {
     cudaFree(h->d_fe);
     h->cap_fe = off + off / 4;
@@ -1877,6 +1878,7 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
   A.counts = (unsigned*)(b + o_cnt);
   unsigned long long* key_p_raw = (unsigned long long*)(b + o_kpr); unsigned long long* key_s_raw = (unsigned long long*)(b + o_ksr);
   unsigned* val_p_raw = (unsigned*)(b + o_vpr); unsigned* val_s_raw = (unsigned*)(b + o_vsr);
+  unsigned* rank_p = (unsigned*)(b + o_rk); unsigned* rank_s = rank_p + npad;
 
   CU_TRY(cudaMemcpyAsync(A.stage, xyz, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CU_TRY(cudaMemcpyAsync(A.blob, &hd, sizeof(MapHeader), cudaMemcpyHostToDevice, h->stream));
@@ -1919,8 +1921,12 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
                                                                               A.counts)));
     // candidates first compacted, then ordered by (flatness descending, point index ascending): rank sort over the whole
     // GPU for lists up to 32 768 candidates, the shared-memory bitonic network for longer ones (each is a no-op otherwise)
-    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_ranksort<<<dim3(gb, 2), 256, 0, h->stream>>>(key_p_raw, val_p_raw, key_s_raw, val_s_raw, A.key_p_sorted,
-                                                                                        A.val_p_sorted, A.key_s_sorted, A.val_s_sorted, A.counts)));
+    CU_TRY(cudaMemsetAsync(rank_p, 0, npad * 8, h->stream));
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_rank<<<dim3(gb, 2, kFeRankSplit), 256, 0, h->stream>>>(key_p_raw, val_p_raw, key_s_raw, val_s_raw, rank_p,
+                                                                                                  rank_s, A.counts)));
+    TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_rank_scatter<<<dim3(gb, 2), 256, 0, h->stream>>>(key_p_raw, val_p_raw, key_s_raw, val_s_raw, rank_p, rank_s,
+                                                                                            A.key_p_sorted, A.val_p_sorted, A.key_s_sorted,
+                                                                                            A.val_s_sorted, A.counts)));
     static bool fe_sort_attr = false;
     if (!fe_sort_attr) {
       CU_TRY(cudaFuncSetAttribute(k_fe_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSortSmemBytes));
