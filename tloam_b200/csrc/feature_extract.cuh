@@ -421,11 +421,12 @@ __global__ void __launch_bounds__(256) k_fe_rank(const unsigned long long* key_p
     for (unsigned t = cnt + threadIdx.x; t < ((cnt + 1u) & ~1u); t += 256u) { s_key[t] = 0ull; s_val[t] = 0xFFFFFFFFu; }   // pad to even: sorts last
     __syncthreads();
 #pragma unroll 4
-    for (unsigned t = 0u; t < cnt; t += 2u) {                              // two independent counters
-      const unsigned long long k0 = s_key[t], k1 = s_key[t + 1];
-      const unsigned v0 = s_val[t], v1 = s_val[t + 1];
-      r0 += (k0 > mk || (k0 == mk && v0 < mv)) ? 1u : 0u;
-      r1 += (k1 > mk || (k1 == mk && v1 < mv)) ? 1u : 0u;
+    for (unsigned t = 0u; t < cnt; t += 2u) {                              // two independent counters; the index is only
+      const unsigned long long k0 = s_key[t], k1 = s_key[t + 1];           // looked at on a key tie (rare)
+      r0 += k0 > mk ? 1u : 0u;
+      r1 += k1 > mk ? 1u : 0u;
+      if (k0 == mk) r0 += s_val[t] < mv ? 1u : 0u;
+      if (k1 == mk) r1 += s_val[t + 1] < mv ? 1u : 0u;
     }
   }
   if (live && (r0 + r1)) atomicAdd(rank_out + e, r0 + r1);
