@@ -21,6 +21,7 @@
 #include "ground_extract.cuh"
 #include "edge_extract.cuh"
 #include "object_segment.cuh"
+#include "host_stage.h"
 
 
 
@@ -52,6 +53,7 @@ struct tloam_b200_handle {
   cudaStream_t fit_stream = nullptr;               // per-frame getFitnessScore runs beside the registration (fork / join in the frame graph)
   cudaEvent_t ev_fit[2] = {nullptr, nullptr};
   char last_error[512] = {0};
+  HostStage hstage;                                // pageable host inputs: chunked, multi-threaded staging through pinned slots
   long long launches = 0;
   int launches_frame = 0;
   // source
@@ -314,6 +316,8 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (!h) return TLOAM_B200_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  h->hstage.shutdown();
   cudaFree(h->d_stage_buf[0]); cudaFree(h->d_stage_buf[1]); cudaFree(h->d_feat); cudaFree(h->d_flags); cudaFree(h->d_blk_count);
   cudaFree(h->d_partial); cudaFree(h->d_counter); if (h->own_state) cudaFree(h->d_state); cudaFree(h->d_stats);
   cudaFree(h->d_stage_tgt); cudaFree(h->d_scratch); cudaFree(h->d_blob); cudaFree(h->d_blob_in); cudaFree(h->d_dbg);
@@ -425,8 +429,15 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
   for (int k = 0; k < 4; ++k) {
     src[k] = stage ? h->d_stage_src + 3 * off : xyz[k];
     if (n[k] > 0 && stage)
-      CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
-                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, up));
+    {
+      static const bool stage_pageable = getenv("TLOAM_B200_NO_HOST_STAGE") == nullptr;
+      if (!on_device && stage_pageable && n[k] * 24 >= (256u << 10) && HostStage::pageable(xyz[k])) {
+        CU_TRY(h->hstage.upload(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double), up));
+      } else {
+        CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
+                               on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, up));
+      }
+    }
     c.n[k] = (int)n[k];
     c.pad_off[k] = (int)poff;
     off += n[k];
@@ -560,6 +571,7 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
     total += n[c];
   }
   h->have_tgt = false;
+  bool all_staged = !on_device;                    // every host cloud went through the pageable staging ring
   if (total > h->cap_scratch) {
     cudaFree(h->d_scratch); h->d_scratch = nullptr; h->cap_scratch = 0;
     const size_t ncap = total + total / 4 + 1024;
@@ -633,9 +645,15 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
       for (int j = i; j > 1 && n[order[j]] > n[order[j - 1]]; --j) { const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
     CU_TRY(cudaEventRecord(h->ev_copy[0], h->stream));                  // the staging buffer is free once earlier work is done
     CU_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_copy[0], 0));
+    static const bool stage_pageable = getenv("TLOAM_B200_NO_HOST_STAGE") == nullptr;   // A/B knob
     for (int k = 0; k < m; ++k) {
       const int c = order[k];
-      CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * (size_t)a.stage_off[c], xyz[c], n[c] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      if (stage_pageable && HostStage::pageable(xyz[c])) {
+        CU_TRY(h->hstage.upload(h->d_stage_tgt + 3 * (size_t)a.stage_off[c], xyz[c], n[c] * 3 * sizeof(double), h->copy_stream));
+      } else {
+        CU_TRY(cudaMemcpyAsync(h->d_stage_tgt + 3 * (size_t)a.stage_off[c], xyz[c], n[c] * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        all_staged = false;
+      }
       CU_TRY(cudaEventRecord(h->ev_copy[1 + c], h->copy_stream));
       h->last_uploaded = c;
     }
@@ -670,7 +688,8 @@ static int set_target_impl(tloam_b200_handle* h, const double* const xyz[4], con
   }
   // host path: the caller's buffers are free once the LAST upload has landed; the build of the last cloud may
   // still be running on the compute stream (everything that follows is ordered behind it on that stream)
-  if (!on_device && total > 0) CU_TRY(cudaEventSynchronize(h->ev_copy[1 + h->last_uploaded]));
+  // (staged pageable inputs have been read completely already: nothing to wait for)
+  if (!on_device && total > 0 && !all_staged) CU_TRY(cudaEventSynchronize(h->ev_copy[1 + h->last_uploaded]));
   return TLOAM_B200_OK;
 }
 

@@ -15,7 +15,8 @@ import tloam_b200  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 23
 frames, prev_gt = bench.gen_frames("00", n)
 reg = tloam_b200.LocalRegistration(stream=torch.cuda.current_stream().cuda_stream, **bench.CAPS)
-pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+pageable = len(sys.argv) > 2 and sys.argv[2] == "pageable"
+pin = (lambda a: np.array(a, copy=True)) if pageable else (lambda a: torch.from_numpy(a).pin_memory().numpy())
 data = [([pin(c) for c in fr["map"]], [pin(c) for c in fr["scan"]]) for fr in frames]
 for mp, sc in data:
     for a in mp + sc:
@@ -36,6 +37,7 @@ for k, fr in enumerate(frames):
     rows.append((t1 - t0, t2 - t1, t3 - t2, t3 - t0))
     last, cur = (cur if cur is not None else prev_gt), T
 r = np.array(rows[3:]) * 1e3
+print("pageable" if pageable else "pinned", end=" ")
 print("median ms: set_target %.3f set_source %.3f scan_match %.3f total %.3f" % tuple(np.median(r, axis=0)))
 print("map points", [len(c) for c in data[0][0]], "scan points", [len(c) for c in data[0][1]])
 reg.close()
