@@ -4,12 +4,14 @@
 // cudaMemcpyAsync from pageable memory goes through the driver's own staging at ~10 GB/s (13 MB of map per frame: 1.2 ms of
 // the 1.6 ms frame).  Here the copy is cut into 2 MB chunks that a small pool of threads copies into a ring of pinned slots
 // (several threads: one core's memcpy is ~12 GB/s, PCIe 5 x16 moves 50+) while the DMA engine drains the slots filled
-// before; a slot is reused once the event recorded behind its DMA has fired.  The caller's buffer has been read completely
+// before (the workers poll for the next chunk while a burst lasts and sleep otherwise); a slot is reused once the event recorded behind its DMA has fired.  The caller's buffer has been read completely
 // when the call returns.  Pinned (or registered) caller memory never comes here: it is DMA'd directly.
 #pragma once
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -20,8 +22,9 @@ namespace tloam {
 class HostStage {
  public:
   static constexpr size_t kChunk = 2u << 20;     // bytes per pinned slot
-  static constexpr int kSlots = 6;
-  static constexpr int kWorkers = 3;             // + the calling thread
+  static constexpr int kSlots = 8;
+  static constexpr int kWorkers = 7;             // + the calling thread: one core's memcpy is ~10 GB/s, PCIe 5 x16 moves 50+
+  static constexpr long long kSpinNs = 400000;   // a worker keeps polling this long after its last task before it sleeps
 
   ~HostStage() { shutdown(); }
 
@@ -54,11 +57,11 @@ class HostStage {
   }
 
   void shutdown() {
+    stop_.store(true, std::memory_order_release);
     {
       std::unique_lock<std::mutex> lk(m_);
-      stop_ = true;
+      cv_work_.notify_all();
     }
-    cv_work_.notify_all();
     for (std::thread& t : workers_) if (t.joinable()) t.join();
     workers_.clear();
     if (pin_) {
@@ -66,7 +69,7 @@ class HostStage {
       cudaFreeHost(pin_);
       pin_ = nullptr;
     }
-    stop_ = false;
+    stop_.store(false, std::memory_order_release);
   }
 
  private:
@@ -85,42 +88,49 @@ class HostStage {
     return cudaSuccess;
   }
 
+  // workers poll the generation counter for kSpinNs after their last task (a frame's uploads arrive as a burst of chunks:
+  // a condition-variable wake-up per chunk costs more than copying it), then sleep
   void run(int w) {
     unsigned seen = 0;
+    auto last = std::chrono::steady_clock::now();
     while (true) {
-      Task t;
-      {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_work_.wait(lk, [&] { return stop_ || generation_ != seen; });
-        if (stop_) return;
-        seen = generation_;
-        t = tasks_[w];
+      unsigned g = generation_.load(std::memory_order_acquire);
+      if (g == seen) {
+        if (stop_.load(std::memory_order_acquire)) return;
+        if (std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - last).count() > kSpinNs) {
+          std::unique_lock<std::mutex> lk(m_);
+          sleepers_.fetch_add(1, std::memory_order_acq_rel);
+          cv_work_.wait(lk, [&] { return stop_.load(std::memory_order_acquire) || generation_.load(std::memory_order_acquire) != seen; });
+          sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+          if (stop_.load(std::memory_order_acquire)) return;
+          last = std::chrono::steady_clock::now();
+        }
+        continue;
       }
+      seen = g;
+      const Task t = tasks_[w];
       if (t.len) memcpy(t.dst, t.src, t.len);
-      {
-        std::unique_lock<std::mutex> lk(m_);
-        if (--pending_ == 0) cv_done_.notify_one();
-      }
+      done_.fetch_add(1, std::memory_order_acq_rel);
+      last = std::chrono::steady_clock::now();
     }
   }
 
   void parallel_copy(char* dst, const char* src, size_t len) {
-    if (len < (256u << 10)) { memcpy(dst, src, len); return; }            // small: not worth waking anyone
+    if (len < (128u << 10)) { memcpy(dst, src, len); return; }            // small: not worth a hand-off
     const size_t part = ((len / (kWorkers + 1)) + 4095) & ~(size_t)4095;
-    {
-      std::unique_lock<std::mutex> lk(m_);
-      for (int w = 0; w < kWorkers; ++w) {
-        const size_t o = part * (size_t)(w + 1);
-        const size_t l = o < len ? (len - o < part ? len - o : part) : 0;
-        tasks_[w] = Task{dst + o, src + o, l};
-      }
-      pending_ = kWorkers;
-      ++generation_;
+    for (int w = 0; w < kWorkers; ++w) {
+      const size_t o = part * (size_t)(w + 1);
+      const size_t l = o < len ? (len - o < part ? len - o : part) : 0;
+      tasks_[w] = Task{dst + o, src + o, l};
     }
-    cv_work_.notify_all();
+    done_.store(0, std::memory_order_release);
+    generation_.fetch_add(1, std::memory_order_acq_rel);                   // publishes the tasks
+    if (sleepers_.load(std::memory_order_acquire) > 0) {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_work_.notify_all();
+    }
     memcpy(dst, src, part < len ? part : len);                            // the caller's share
-    std::unique_lock<std::mutex> lk(m_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
+    while (done_.load(std::memory_order_acquire) < kWorkers) { /* spin: the others finish within microseconds */ }
   }
 
   char* pin_ = nullptr;
@@ -129,11 +139,11 @@ class HostStage {
   int next_ = 0;
   std::vector<std::thread> workers_;
   std::mutex m_;
-  std::condition_variable cv_work_, cv_done_;
+  std::condition_variable cv_work_;
   Task tasks_[kWorkers] = {};
-  int pending_ = 0;
-  unsigned generation_ = 0;
-  bool stop_ = false;
+  std::atomic<unsigned> generation_{0};
+  std::atomic<int> done_{0}, sleepers_{0};
+  std::atomic<bool> stop_{false};
 };
 
 }  // namespace tloam

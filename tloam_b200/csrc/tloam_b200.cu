@@ -431,7 +431,7 @@ static int set_source_impl(tloam_b200_handle* h, const double* const xyz[4], con
     if (n[k] > 0 && stage)
     {
       static const bool stage_pageable = getenv("TLOAM_B200_NO_HOST_STAGE") == nullptr;
-      if (!on_device && stage_pageable && n[k] * 24 >= (256u << 10) && HostStage::pageable(xyz[k])) {
+      if (!on_device && stage_pageable && n[k] * 24 >= (128u << 10) && HostStage::pageable(xyz[k])) {
         CU_TRY(h->hstage.upload(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double), up));
       } else {
         CU_TRY(cudaMemcpyAsync(h->d_stage_src + 3 * off, xyz[k], n[k] * 3 * sizeof(double),
