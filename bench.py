@@ -866,10 +866,19 @@ def main():
             sout, _ = seg_chain(reg.ground_extract, reg.object_segmentation, reg.extract_edge)
         st = np.array([seg_chain(reg.ground_extract, reg.object_segmentation, reg.extract_edge)[1] for _ in range(10)])
         sm = np.median(st, axis=0)
+        for _ in range(3):
+            one = reg.segment_scan(raw)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            one = reg.segment_scan(raw)
+        one_ms = 1e3 * (time.perf_counter() - t0) / 10
         segm = {"points": int(raw.shape[0]), "object_points": int(len(sout[1])), "segmented_points": int(len(sout[2])),
                 "clusters": int(len(sout[3])), "edge_points": int(len(sout[4])), "general_points": int(len(sout[5])),
                 "gpu_ms_per_call": {"ground_extract": float(sm[0]), "object_segmentation": float(sm[1]), "extract_edge": float(sm[2]),
-                                    "total": float(sm.sum())},
+                                    "total": float(sm.sum()), "single_call": one_ms},
+                "single_call_what": "tloam_b200_segment_scan: one upload, the three stages chained on the device, index lists into the original "
+                                    "scan home (edge / general lists equal to the chain's: "
+                                    + str(bool(np.array_equal(one["edge"], sout[1][sout[2]][sout[4]]) and np.array_equal(one["ground"], sout[0]))) + ")",
                 "what": "tloam_b200_ground_extract -> tloam_b200_object_segmentation -> tloam_b200_extract_edge through the C ABI "
                         "(host clouds in, host index lists out, copies and the Python gather between the stages not counted); median of 10"}
         if not args.no_cpu_baseline:

@@ -257,3 +257,31 @@ def test_gpu_segmentation_front_half_chain(oracle):
         assert np.array_equal(a, b)
     assert len(out["gpu"][4]) > 100 and len(out["gpu"][5]) > 5000
     reg.close()
+
+
+@pytest.mark.gpu
+def test_gpu_segment_scan_single_call_matches_the_chain(oracle):
+    """tloam_b200_segment_scan (one upload, stages fed on the device, indices into the ORIGINAL scan) against the three
+    separate calls with host gathers in between, on the oracle."""
+    import tloam_b200
+    reg = tloam_b200.LocalRegistration()
+    for scan, rmin, dc in ((synth.raw_scan(), 131, {}), (synth.raw_scan(seed=9, n_az=900), 60, dict(min_seg=30)),
+                           (synth.raw_scan(seed=4, n_az=300)[:4000], 16, dict(min_seg=5))):
+        got = reg.segment_scan(scan, ring_min_num=rmin, dcvc=dc)
+        ge = oracle.ground_extract(scan)
+        obj = np.ascontiguousarray(scan[ge["object"]])
+        beam = ge["beam"][ge["object"]].astype(np.float64)
+        os_ = oracle.dcvc(obj, **dc)
+        seg_orig = ge["object"][os_["segmented"]]
+        ee = oracle.extract_edge(np.ascontiguousarray(obj[os_["segmented"]]), beam[os_["segmented"]], ring_min_num=rmin)
+        assert np.array_equal(got["ground"], ge["ground"])
+        assert np.array_equal(got["edge"], seg_orig[ee["edge"]])
+        assert np.array_equal(got["general"], seg_orig[ee["non_edge"]])
+        assert np.array_equal(got["sizes"], os_["sizes"]) and np.array_equal(got["boxes"], os_["boxes"])
+    e = reg.segment_scan(np.zeros((0, 3)))
+    assert len(e["ground"]) == 0 and len(e["edge"]) == 0 and len(e["general"]) == 0
+    # the stage entry points are unaffected by a chained call before them
+    scan = synth.raw_scan(seed=4, n_az=300)
+    a, b = reg.ground_extract(scan), oracle.ground_extract(scan)
+    assert np.array_equal(a["ground"], b["ground"]) and np.array_equal(a["object"], b["object"])
+    reg.close()

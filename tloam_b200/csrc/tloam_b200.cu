@@ -54,6 +54,17 @@ struct tloam_b200_handle {
   cudaEvent_t ev_fit[2] = {nullptr, nullptr};
   char last_error[512] = {0};
   HostStage hstage;                                // pageable host inputs: chunked, multi-threaded staging through pinned slots
+  // tloam_b200_segment_scan: the three segmentation stages chained on the device.  A stage that finds `active` reads its
+  // input from dev_xyz / dev_intensity (no upload) and, instead of copying its index lists home, leaves the device
+  // pointers and counts here for the gather kernel that feeds the next stage.
+  struct SegChain {
+    bool active = false;
+    const double* dev_xyz = nullptr; const double* dev_intensity = nullptr;
+    const unsigned* ground = nullptr; const unsigned* object = nullptr; const int* beam = nullptr; unsigned n_ground = 0, n_object = 0;
+    const unsigned long long* seg = nullptr; unsigned n_seg = 0;
+    const unsigned long long* edge = nullptr; const unsigned long long* non_edge = nullptr; unsigned n_edge = 0, n_non = 0;
+  } seg;
+  unsigned char* d_chain = nullptr; size_t cap_chain = 0;
   long long launches = 0;
   int launches_frame = 0;
   // source
@@ -347,7 +358,7 @@ int tloam_b200_destroy(tloam_b200_handle* h) {
   if (h->ev_planar_in) cudaEventDestroy(h->ev_planar_in);
   if (h->ev_planar_free) cudaEventDestroy(h->ev_planar_free);
   if (h->ev_planar_done) cudaEventDestroy(h->ev_planar_done);
-  cudaFree(h->d_vox1); cudaFree(h->d_acc_tmp1); cudaFree(h->d_up_planar);
+  cudaFree(h->d_vox1); cudaFree(h->d_acc_tmp1); cudaFree(h->d_up_planar); cudaFree(h->d_chain);
   for (int i = 0; i < 2; ++i) if (h->ev_stage_free[i]) cudaEventDestroy(h->ev_stage_free[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_fit[i]) cudaEventDestroy(h->ev_fit[i]);
   for (int i = 0; i < 2; ++i) if (h->ev_res[i]) cudaEventDestroy(h->ev_res[i]);
@@ -2323,7 +2334,8 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
   a.key_base = (unsigned*)(b + o_kb); a.order = (unsigned*)(b + o_ord); a.flag = b + o_flag; a.lists = (unsigned*)(b + o_lists);
   a.reg_cnt = (unsigned*)(b + o_rc); a.planes = (double*)(b + o_pl); a.out_ground = (unsigned*)(b + o_og);
   a.out_object = (unsigned*)(b + o_oo); a.out_counts = (unsigned*)(b + o_oc);
-  CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  if (h->seg.active) a.pts = h->seg.dev_xyz;
+  else CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_pre<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scan1<<<1, 1024, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_region<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
@@ -2346,6 +2358,12 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
   unsigned counts[2];
   memcpy(counts, h->h_result + 28, sizeof(counts));
   if (height_threshold) *height_threshold = h->h_result[29];
+  if (h->seg.active) {                                                     // chained: the lists stay on the device
+    h->seg.ground = a.out_ground; h->seg.object = a.out_object; h->seg.beam = a.beam;
+    h->seg.n_ground = counts[0]; h->seg.n_object = counts[1];
+    *n_ground = counts[0]; *n_object = counts[1];
+    return TLOAM_B200_OK;
+  }
   if (counts[0]) CU_TRY(cudaMemcpyAsync(gi.data(), a.out_ground, counts[0] * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   if (counts[1]) CU_TRY(cudaMemcpyAsync(oi.data(), a.out_object, counts[1] * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   if (beam) CU_TRY(cudaMemcpyAsync(beam, a.beam, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -2398,8 +2416,11 @@ int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min
     CU_TRY(cudaFuncSetAttribute(k_ee_section, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEeSmemBytes));
     attr_set = true;
   }
-  CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
-  CU_TRY(cudaMemcpyAsync(b + o_int, intensity, n * 8, cudaMemcpyHostToDevice, h->stream));
+  if (h->seg.active) { a.pts = h->seg.dev_xyz; a.intensity = h->seg.dev_intensity; }
+  else {
+    CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(b + o_int, intensity, n * 8, cudaMemcpyHostToDevice, h->stream));
+  }
   CU_TRY(cudaMemsetAsync(b + o_sc, 0, nsec * 2 * 4, h->stream));         // beams >= sensor_model have no sections
   TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_key<<<a.nchunk, kEeChunk, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_EDGE, (k_ee_scan<<<1, kEeKeys, 0, h->stream>>>(a)));
@@ -2418,6 +2439,11 @@ int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min
     return TLOAM_B200_ERR_INVALID_ARG;
   }
   static_assert(sizeof(size_t) == sizeof(unsigned long long), "index lists are copied straight into size_t arrays");
+  if (h->seg.active) {                                                     // chained: the lists stay on the device
+    h->seg.edge = a.out_edge; h->seg.non_edge = a.out_non; h->seg.n_edge = tot[0]; h->seg.n_non = tot[1];
+    *n_edge = tot[0]; *n_non_edge = tot[1];
+    return TLOAM_B200_OK;
+  }
   if (tot[0]) CU_TRY(cudaMemcpyAsync(edge_index, a.out_edge, tot[0] * sizeof(size_t), cudaMemcpyDeviceToHost, h->stream));
   if (tot[1]) CU_TRY(cudaMemcpyAsync(non_edge_index, a.out_non, tot[1] * sizeof(size_t), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
@@ -2493,7 +2519,8 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
     attr_set = true;
   }
   cudaStream_t st = h->stream;
-  CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, st));
+  if (h->seg.active) a.pts = h->seg.dev_xyz;
+  else CU_TRY(cudaMemcpyAsync(b + o_pts, xyz, n * 24, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(b + o_tab, 0, cap * 8, st));
   if (!seq_bytes && !use_smem) CU_TRY(cudaMemsetAsync(b + o_stg, 0, state_words * 4, st));
   const unsigned ev_blocks = (unsigned)((n32 * 32 + 255) / 256);
@@ -2540,7 +2567,8 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   }
   static_assert(sizeof(size_t) == sizeof(unsigned long long), "index lists are copied straight into size_t arrays");
   const size_t nc = (size_t)par[6], ns = (size_t)par[7];
-  if (ns) CU_TRY(cudaMemcpyAsync(seg_index, a.out_seg, ns * sizeof(size_t), cudaMemcpyDeviceToHost, st));
+  if (h->seg.active) { h->seg.seg = a.out_seg; h->seg.n_seg = (unsigned)ns; }   // chained: the scan stays on the device
+  else if (ns) CU_TRY(cudaMemcpyAsync(seg_index, a.out_seg, ns * sizeof(size_t), cudaMemcpyDeviceToHost, st));
   if (sizes && nc) CU_TRY(cudaMemcpyAsync(sizes, a.sizes, nc * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (boxes && nc) CU_TRY(cudaMemcpyAsync(boxes, a.boxes, nc * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (root) CU_TRY(cudaMemcpyAsync(root, a.root, n * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -2552,6 +2580,115 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   }
   CU_TRY(cudaStreamSynchronize(st));
   *n_seg = ns; *n_clusters = (int)nc;
+  return TLOAM_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "next" row (f)-4: the three steps of Segmentation::spinOnce (ref: segmentation.cpp:47-66) as ONE call: the scan is
+// uploaded once, every stage is fed by a gather kernel from the previous stage's device-side index list, and only the
+// final lists come home -- as indices into the ORIGINAL scan.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_chain_gather_object(const double* pts, const int* beam, const unsigned* idx, unsigned n, double* out_pts,
+                                                             double* out_beam) {
+  const unsigned j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const unsigned i = idx[j];
+  out_pts[3ull * j] = pts[3ull * i]; out_pts[3ull * j + 1] = pts[3ull * i + 1]; out_pts[3ull * j + 2] = pts[3ull * i + 2];
+  out_beam[j] = (double)beam[i];                                           // the intensity channel carries the beam id (:707-709)
+}
+__global__ void __launch_bounds__(256) k_chain_gather_segmented(const double* obj_pts, const double* obj_beam, const unsigned* obj_idx,
+                                                                const unsigned long long* seg, unsigned n, double* out_pts, double* out_beam,
+                                                                unsigned* out_orig) {
+  const unsigned j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const unsigned i = (unsigned)seg[j];
+  out_pts[3ull * j] = obj_pts[3ull * i]; out_pts[3ull * j + 1] = obj_pts[3ull * i + 1]; out_pts[3ull * j + 2] = obj_pts[3ull * i + 2];
+  out_beam[j] = obj_beam[i];
+  out_orig[j] = obj_idx[i];
+}
+// blockIdx.y: 0 ground, 1 edge, 2 general -- index lists into the original scan, as 64-bit values
+__global__ void __launch_bounds__(256) k_chain_final(const unsigned* ground, unsigned n_ground, const unsigned long long* edge, unsigned n_edge,
+                                                     const unsigned long long* non_edge, unsigned n_non, const unsigned* seg_orig,
+                                                     unsigned long long* out_ground, unsigned long long* out_edge, unsigned long long* out_general) {
+  const unsigned j = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.y == 0) { if (j < n_ground) out_ground[j] = ground[j]; }
+  else if (blockIdx.y == 1) { if (j < n_edge) out_edge[j] = seg_orig[(unsigned)edge[j]]; }
+  else { if (j < n_non) out_general[j] = seg_orig[(unsigned)non_edge[j]]; }
+}
+}  // namespace
+
+int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcfg, const tloam_dcvc_config* dcfg, int ring_min_num,
+                            const double* xyz, size_t n, size_t* ground_index, size_t* n_ground, size_t* edge_index, size_t* n_edge,
+                            size_t* general_index, size_t* n_general, int* n_clusters, int* sizes, double* boxes) {
+  if (!h || !gcfg || !dcfg || !ground_index || !n_ground || !edge_index || !n_edge || !general_index || !n_general || !n_clusters)
+    return TLOAM_B200_ERR_INVALID_ARG;
+  *n_ground = *n_edge = *n_general = 0; *n_clusters = 0;
+  if (n == 0) return TLOAM_B200_OK;
+  if (!xyz || n > ((size_t)1 << 26)) return TLOAM_B200_ERR_INVALID_ARG;
+  CU_TRY(cudaSetDevice(h->device));
+  // chain buffer: what must outlive a stage's arena
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
+  const size_t o_scan = take(n * 24), o_gnd = take(n * 4), o_oidx = take(n * 4), o_opts = take(n * 24), o_obeam = take(n * 8),
+               o_spts = take(n * 24), o_sbeam = take(n * 8), o_sorig = take(n * 4), o_fg = take(n * 8), o_fe = take(n * 8), o_fn = take(n * 8);
+  if (off > h->cap_chain) {
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_chain); h->d_chain = nullptr; h->cap_chain = 0;
+    CU_TRY(cudaMalloc(&h->d_chain, off + off / 4));
+    h->cap_chain = off + off / 4;
+  }
+  unsigned char* c = h->d_chain;
+  double* d_scan = (double*)(c + o_scan);
+  unsigned* d_gnd = (unsigned*)(c + o_gnd); unsigned* d_oidx = (unsigned*)(c + o_oidx);
+  double* d_opts = (double*)(c + o_opts); double* d_obeam = (double*)(c + o_obeam);
+  double* d_spts = (double*)(c + o_spts); double* d_sbeam = (double*)(c + o_sbeam); unsigned* d_sorig = (unsigned*)(c + o_sorig);
+  unsigned long long* d_fg = (unsigned long long*)(c + o_fg); unsigned long long* d_fe = (unsigned long long*)(c + o_fe);
+  unsigned long long* d_fn = (unsigned long long*)(c + o_fn);
+  if (HostStage::pageable(xyz) && getenv("TLOAM_B200_NO_HOST_STAGE") == nullptr) CU_TRY(h->hstage.upload(d_scan, xyz, n * 24, h->stream));
+  else CU_TRY(cudaMemcpyAsync(d_scan, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  struct Reset { tloam_b200_handle* h; ~Reset() { h->seg = tloam_b200_handle::SegChain(); } } reset{h};
+  h->seg.active = true;
+  // ---- 1. groundRemove ----
+  h->seg.dev_xyz = d_scan;
+  size_t ng = 0, no = 0;
+  int rc = tloam_b200_ground_extract(h, gcfg, xyz, n, ground_index, &ng, general_index /*scratch: not written when chained*/, &no, nullptr, nullptr,
+                                     nullptr, nullptr);
+  if (rc != TLOAM_B200_OK) return rc;
+  if (ng) CU_TRY(cudaMemcpyAsync(d_gnd, h->seg.ground, ng * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if (no) {
+    CU_TRY(cudaMemcpyAsync(d_oidx, h->seg.object, no * 4, cudaMemcpyDeviceToDevice, h->stream));
+    k_chain_gather_object<<<(unsigned)((no + 255) / 256), 256, 0, h->stream>>>(d_scan, h->seg.beam, h->seg.object, (unsigned)no, d_opts, d_obeam);
+  }
+  size_t ne = 0, nn = 0;
+  if (no) {
+    // ---- 2. objectSegmentation ----
+    h->seg.dev_xyz = d_opts;
+    size_t ns = 0;
+    rc = tloam_b200_object_segmentation(h, dcfg, d_opts /*placeholder: read on the device*/, no, general_index, &ns, n_clusters, sizes, boxes, nullptr,
+                                        nullptr, nullptr, nullptr);
+    if (rc != TLOAM_B200_OK) return rc;
+    if (ns) {
+      k_chain_gather_segmented<<<(unsigned)((ns + 255) / 256), 256, 0, h->stream>>>(d_opts, d_obeam, d_oidx, h->seg.seg, (unsigned)ns, d_spts, d_sbeam,
+                                                                                     d_sorig);
+      // ---- 3. extractEdgePoint ----
+      h->seg.dev_xyz = d_spts; h->seg.dev_intensity = d_sbeam;
+      rc = tloam_b200_extract_edge(h, gcfg->sensor_model, ring_min_num, d_spts, d_sbeam, ns, edge_index, &ne, general_index, &nn);
+      if (rc != TLOAM_B200_OK) return rc;
+    }
+  }
+  const size_t most = ng > ne ? (ng > nn ? ng : nn) : (ne > nn ? ne : nn);
+  if (most) {
+    k_chain_final<<<dim3((unsigned)((most + 255) / 256), 3), 256, 0, h->stream>>>(d_gnd, (unsigned)ng, h->seg.edge, (unsigned)ne, h->seg.non_edge,
+                                                                                   (unsigned)nn, d_sorig, d_fg, d_fe, d_fn);
+    CU_TRY(cudaGetLastError());
+    static_assert(sizeof(size_t) == sizeof(unsigned long long), "index lists are copied straight into size_t arrays");
+    if (ng) CU_TRY(cudaMemcpyAsync(ground_index, d_fg, ng * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (ne) CU_TRY(cudaMemcpyAsync(edge_index, d_fe, ne * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (nn) CU_TRY(cudaMemcpyAsync(general_index, d_fn, nn * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+  }
+  *n_ground = ng; *n_edge = ne; *n_general = nn;
   return TLOAM_B200_OK;
 }
 
