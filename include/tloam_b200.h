@@ -385,11 +385,12 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
  * every stage is fed on the device from the previous stage's index list, only the final lists come home.  All three
  * lists index the ORIGINAL scan: ground_index = the reference's ground_scan, edge_index / general_index = its edge_scan /
  * general_scan (capacity n each), in the reference's order.  sizes / boxes (capacity n / n x 6, optional): per cluster as
- * in tloam_b200_object_segmentation.  Identical to calling the three functions one after the other with host gathers
- * in between (tests/test_object_segmentation.py). */
+ * in tloam_b200_object_segmentation; beam (capacity n, optional): the beam estimate of every point of the scan (what the
+ * reference keeps in the intensity channel of the object / segmented / edge / general clouds).  Identical to calling the
+ * three functions one after the other with host gathers in between (tests/test_object_segmentation.py). */
 int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcfg, const tloam_dcvc_config* dcfg, int ring_min_num,
                             const double* xyz, size_t n, size_t* ground_index, size_t* n_ground, size_t* edge_index, size_t* n_edge,
-                            size_t* general_index, size_t* n_general, int* n_clusters, int* sizes, double* boxes);
+                            size_t* general_index, size_t* n_general, int* n_clusters, int* sizes, double* boxes, int* beam);
 
 /* Pinned host memory helpers (optional; pinned inputs make set_* a direct DMA). */
 int tloam_b200_host_alloc(void** p, size_t bytes);

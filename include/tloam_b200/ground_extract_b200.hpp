@@ -93,6 +93,7 @@ class GroundExtractB200 {
   double heightThreshold() const { return height_threshold_; }
   int lastStatus() const { return last_status_; }
   tloam_b200_handle* handle() const { return h_; }
+  const tloam_ground_config& config() const { return cfg_; }
 
  private:
   void attach(tloam_b200_handle* shared, int device) {

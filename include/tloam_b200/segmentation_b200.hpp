@@ -112,6 +112,44 @@ class SegmentationB200 {
     return true;
   }
 
+  // The three steps above as ONE device pass (tloam_b200_segment_scan): the scan crosses PCIe once.  ground_scan / edge_scan /
+  // general_scan receive the points the three separate calls would have produced (same order, same intensities: 0 for
+  // ground points, the beam estimate for the others); `scan` is left untouched.
+  bool segmentScan(const CloudData& scan, CloudData& ground_scan, CloudData& edge_scan, CloudData& general_scan,
+                   std::vector<BoxB200>* boxes = nullptr) {
+    const auto& pts = scan.cloud_ptr->points_;
+    const size_t n = pts.size();
+    if (n == 0) return false;
+    seg_.resize(n); edge_.resize(n); non_.resize(n); sizes_.resize(n); boxes_.resize(6 * n); beam_.resize(n);
+    size_t ng = 0, ne = 0, nn = 0;
+    int nc = 0;
+    last_status_ = tloam_b200_segment_scan(h_, &ground_.config(), &dcvc_, ring_min_num_, reinterpret_cast<const double*>(pts.data()), n, seg_.data(),
+                                           &ng, edge_.data(), &ne, non_.data(), &nn, &nc, sizes_.data(), boxes_.data(), beam_.data());
+    if (last_status_ != TLOAM_B200_OK) {
+      std::fprintf(stderr, "[tloam_b200] segmentScan: %s %s\n", tloam_b200_status_string(last_status_), tloam_b200_last_error(h_));
+      return false;
+    }
+    auto append = [&](CloudData& out, const std::vector<size_t>& idx, size_t cnt, bool with_beam) {
+      for (size_t k = 0; k < cnt; ++k) {
+        out.cloud_ptr->points_.push_back(pts[idx[k]]);
+        out.cloud_ptr->intensity_.push_back(with_beam ? static_cast<double>(beam_[idx[k]]) : 0.0);
+      }
+    };
+    append(ground_scan, seg_, ng, false);
+    append(edge_scan, edge_, ne, true);
+    append(general_scan, non_, nn, true);
+    if (boxes)
+      for (int c = 0; c < nc; ++c) {
+        BoxB200 b;
+        b.label = c + 1; b.points = sizes_[c];
+        for (int d = 0; d < 3; ++d) { b.position[d] = boxes_[6 * c + d]; b.dimensions[d] = boxes_[6 * c + 3 + d]; }
+        boxes->push_back(b);
+      }
+    dcvc_.min_polar_init = dcvc_.max_polar_init = 0.0;         // resetParams() (:1121-1123)
+    dcvc_.min_pitch_init = dcvc_.max_pitch_init = 0.0;
+    return true;
+  }
+
   int lastStatus() const { return last_status_; }
   tloam_b200_handle* handle() const { return h_; }
 
@@ -122,7 +160,7 @@ class SegmentationB200 {
   tloam_b200_handle* h_ = nullptr;
   int last_status_ = TLOAM_B200_OK;
   std::vector<size_t> seg_, edge_, non_;
-  std::vector<int> sizes_;
+  std::vector<int> sizes_, beam_;
   std::vector<double> boxes_;
 };
 

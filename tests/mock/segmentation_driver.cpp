@@ -54,5 +54,22 @@ int main(int argc, char** argv) {
     dump(edge);
     dump(general);
   }
+  // the single-call form must hand out the same clouds as the last frame above (members as resetParams() leaves them)
+  {
+    tloam::CloudData scan, ground, edge, general;
+    scan.cloud_ptr->points_ = pts;
+    std::vector<tloam::BoxB200> boxes;
+    if (!seg->segmentScan(scan, ground, edge, general, &boxes)) return 7;
+    std::printf("%zu %zu %zu %zu\n", ground.cloud_ptr->points_.size(), boxes.size(), edge.cloud_ptr->points_.size(), general.cloud_ptr->points_.size());
+    auto dump = [](const tloam::CloudData& c) {
+      for (size_t i = 0; i < c.cloud_ptr->points_.size(); ++i) {
+        uint64_t bits;
+        std::memcpy(&bits, &c.cloud_ptr->points_[i].v[0], 8);
+        std::printf("%llu %.17g\n", (unsigned long long)bits, c.cloud_ptr->intensity_[i]);
+      }
+    };
+    dump(edge);
+    dump(general);
+  }
   return 0;
 }

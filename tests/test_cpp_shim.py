@@ -165,4 +165,11 @@ def test_segmentation_shim_chain_matches_oracle(oracle):
         want = list(ee["edge"]) + list(ee["non_edge"])
         assert [int(r[0]) for r in rows] == [int(xbits[i]) for i in want]
         assert [float(r[1]) for r in rows] == [float(sb[i]) for i in want]
+        last_rows, last_counts = rows, (ng, nb, ne, nn)
+    # third block: SegmentationB200::segmentScan (one device pass) = the clouds of frame 1
+    ng, nb, ne, nn = (int(v) for v in lines[pos].split())
+    assert (ng, nb, ne, nn) == last_counts
+    rows = [l.split() for l in lines[pos + 1:pos + 1 + ne + nn]]
+    assert rows == last_rows
+    pos += 1 + ne + nn
     assert pos == len(lines)

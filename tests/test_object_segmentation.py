@@ -278,6 +278,7 @@ def test_gpu_segment_scan_single_call_matches_the_chain(oracle):
         assert np.array_equal(got["edge"], seg_orig[ee["edge"]])
         assert np.array_equal(got["general"], seg_orig[ee["non_edge"]])
         assert np.array_equal(got["sizes"], os_["sizes"]) and np.array_equal(got["boxes"], os_["boxes"])
+        assert np.array_equal(got["beam"], ge["beam"])
     e = reg.segment_scan(np.zeros((0, 3)))
     assert len(e["ground"]) == 0 and len(e["edge"]) == 0 and len(e["general"]) == 0
     # the stage entry points are unaffected by a chained call before them

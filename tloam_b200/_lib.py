@@ -229,7 +229,7 @@ def load():
     L.tloam_b200_dcvc_default_config.restype = None
     L.tloam_b200_object_segmentation.argtypes = [vp, C.POINTER(DcvcConfig), dp, C.c_size_t, szp, szp, ip, ip, dp, ip, ip, ip, dp]
     L.tloam_b200_segment_scan.argtypes = [vp, C.POINTER(GroundConfig), C.POINTER(DcvcConfig), C.c_int, dp, C.c_size_t, szp, szp, szp, szp, szp, szp,
-                                          ip, ip, dp]
+                                          ip, ip, dp, ip]
     L.tloam_b200_batch_get_profile.argtypes = [vp, C.POINTER(Profile)]
     _lib = L
     return L

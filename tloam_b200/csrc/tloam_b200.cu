@@ -2620,7 +2620,7 @@ __global__ void __launch_bounds__(256) k_chain_final(const unsigned* ground, uns
 
 int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcfg, const tloam_dcvc_config* dcfg, int ring_min_num,
                             const double* xyz, size_t n, size_t* ground_index, size_t* n_ground, size_t* edge_index, size_t* n_edge,
-                            size_t* general_index, size_t* n_general, int* n_clusters, int* sizes, double* boxes) {
+                            size_t* general_index, size_t* n_general, int* n_clusters, int* sizes, double* boxes, int* beam) {
   if (!h || !gcfg || !dcfg || !ground_index || !n_ground || !edge_index || !n_edge || !general_index || !n_general || !n_clusters)
     return TLOAM_B200_ERR_INVALID_ARG;
   *n_ground = *n_edge = *n_general = 0; *n_clusters = 0;
@@ -2631,7 +2631,8 @@ int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcf
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
   const size_t o_scan = take(n * 24), o_gnd = take(n * 4), o_oidx = take(n * 4), o_opts = take(n * 24), o_obeam = take(n * 8),
-               o_spts = take(n * 24), o_sbeam = take(n * 8), o_sorig = take(n * 4), o_fg = take(n * 8), o_fe = take(n * 8), o_fn = take(n * 8);
+               o_spts = take(n * 24), o_sbeam = take(n * 8), o_sorig = take(n * 4), o_fg = take(n * 8), o_fe = take(n * 8), o_fn = take(n * 8),
+               o_beam = take(n * 4);
   if (off > h->cap_chain) {
     CU_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_chain); h->d_chain = nullptr; h->cap_chain = 0;
@@ -2656,6 +2657,7 @@ int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcf
                                      nullptr, nullptr);
   if (rc != TLOAM_B200_OK) return rc;
   if (ng) CU_TRY(cudaMemcpyAsync(d_gnd, h->seg.ground, ng * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if (beam) CU_TRY(cudaMemcpyAsync(c + o_beam, h->seg.beam, n * 4, cudaMemcpyDeviceToDevice, h->stream));
   if (no) {
     CU_TRY(cudaMemcpyAsync(d_oidx, h->seg.object, no * 4, cudaMemcpyDeviceToDevice, h->stream));
     k_chain_gather_object<<<(unsigned)((no + 255) / 256), 256, 0, h->stream>>>(d_scan, h->seg.beam, h->seg.object, (unsigned)no, d_opts, d_obeam);
@@ -2686,8 +2688,9 @@ int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcf
     if (ng) CU_TRY(cudaMemcpyAsync(ground_index, d_fg, ng * 8, cudaMemcpyDeviceToHost, h->stream));
     if (ne) CU_TRY(cudaMemcpyAsync(edge_index, d_fe, ne * 8, cudaMemcpyDeviceToHost, h->stream));
     if (nn) CU_TRY(cudaMemcpyAsync(general_index, d_fn, nn * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
   }
+  if (beam) CU_TRY(cudaMemcpyAsync(beam, c + o_beam, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(cudaStreamSynchronize(h->stream));
   *n_ground = ng; *n_edge = ne; *n_general = nn;
   return TLOAM_B200_OK;
 }

@@ -379,7 +379,7 @@ class LocalRegistration:
     # ---- "next" row (f)-4: the three segmentation steps as one call (ref: segmentation.cpp:47-66) ----
     def segment_scan(self, scan, ring_min_num=131, ground=None, dcvc=None):
         """groundRemove -> objectSegmentation -> extractEdgePoint chained on the device (one upload, one download).  Returns
-        dict(ground, edge, general, sizes, boxes): index lists into `scan` and the cluster table.  ground / dcvc: dicts of
+        dict(ground, edge, general, sizes, boxes, beam): index lists into `scan`, the cluster table, the beam estimate per point.  ground / dcvc: dicts of
         configuration overrides."""
         a = _f64(scan).reshape(-1, 3)
         n = a.shape[0]
@@ -395,14 +395,15 @@ class LocalRegistration:
         ng, ne, no = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
         ncl = C.c_int(0)
         sizes = np.zeros(m, dtype=np.int32)
+        beam = np.zeros(m, dtype=np.int32)
         boxes = np.zeros((m, 6))
         szp, ip = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
         self._check(self._L.tloam_b200_segment_scan(self._h, C.byref(gc), C.byref(dc), ring_min_num, _dp(a), n, g.ctypes.data_as(szp), C.byref(ng),
                                                     e.ctypes.data_as(szp), C.byref(ne), o.ctypes.data_as(szp), C.byref(no), C.byref(ncl),
-                                                    sizes.ctypes.data_as(ip), _dp(boxes)), "segment_scan")
+                                                    sizes.ctypes.data_as(ip), _dp(boxes), beam.ctypes.data_as(ip)), "segment_scan")
         k = ncl.value
         return dict(ground=g[:ng.value].copy(), edge=e[:ne.value].copy(), general=o[:no.value].copy(), sizes=sizes[:k].copy(),
-                    boxes=boxes[:k].copy())
+                    boxes=boxes[:k].copy(), beam=beam[:n].copy())
 
     # ---- shared map (multi-GPU) ----
     def map_blob_size(self):
