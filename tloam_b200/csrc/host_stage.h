@@ -84,7 +84,12 @@ class HostStage {
       if (e != cudaSuccess) return e;
       used_[i] = false;
     }
-    for (int w = 0; w < kWorkers; ++w) workers_.emplace_back([this, w] { run(w); });
+    try {
+      for (int w = 0; w < kWorkers; ++w) workers_.emplace_back([this, w] { run(w); });
+    } catch (...) {                                                         // no exception crosses the C ABI: fewer workers is an error
+      shutdown();
+      return cudaErrorUnknown;
+    }
     return cudaSuccess;
   }
 
