@@ -214,6 +214,7 @@ def test_gpu_object_segmentation_matches_the_oracle(oracle, obj):
     check_gpu_against_oracle(oracle, reg, obj, min_polar_init=5.0, max_polar_init=5.0)   # first frame
     check_gpu_against_oracle(oracle, reg, object_scan(oracle, seed=9, n_az=900))
     check_gpu_against_oracle(oracle, reg, synth.raw_scan())                             # 116k points, ground included
+    check_gpu_against_oracle(oracle, reg, synth.raw_scan(n_az=4200))                    # 260k points: 2-bit voxel states (no byte per voxel)
     check_gpu_against_oracle(oracle, reg, np.zeros((0, 3)))
     check_gpu_against_oracle(oracle, reg, np.array([[10.0, 0.0, 0.0]]), min_seg=0)
     reg.close()

@@ -166,6 +166,7 @@ struct tloam_b200_handle {
   int map_fine_mask = 0;
   float4* d_fine_tmp = nullptr;            size_t cap_fine_tmp = 0;
   bool dense_attr_set = false;
+  bool fe_sort_attr_set = false, ge_attr_set = false, ee_attr_set = false, os_attr_set = false;   // per handle: function attributes are per device
   bool dense_check = false;                // TLOAM_B200_DENSE_CHECK=1: every dense query is re-searched by the plain path and compared
   int num_sms = 148;
 };
@@ -1957,10 +1958,9 @@ static int fe_run(tloam_b200_handle* h, const tloam_feature_config* cfg, const d
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_rank_scatter<<<dim3(gb, 2), 256, 0, h->stream>>>(key_p_raw, val_p_raw, key_s_raw, val_s_raw, rank_p, rank_s,
                                                                                             A.key_p_sorted, A.val_p_sorted, A.key_s_sorted,
                                                                                             A.val_s_sorted, A.counts)));
-    static bool fe_sort_attr = false;
-    if (!fe_sort_attr) {
+    if (!h->fe_sort_attr_set) {
       CU_TRY(cudaFuncSetAttribute(k_fe_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFeSortSmemBytes));
-      fe_sort_attr = true;
+      h->fe_sort_attr_set = true;
     }
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_sort<<<2, 1024, kFeSortSmemBytes, h->stream>>>(A.key_p_sorted, A.val_p_sorted, A.key_s_sorted, A.val_s_sorted, A.counts)));
     TL_LAUNCH(TLOAM_B200_K_FEATURE, (k_fe_counts<<<1, 32, 0, h->stream>>>(A.key_p_sorted, A.key_s_sorted, A.counts, cfg->planar_num,
@@ -2342,10 +2342,9 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scan2<<<1, 1024, 0, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_scatter<<<a.nchunk, kGeChunk, 0, h->stream>>>(a)));
   constexpr size_t kGeFitSmem = (6 * kGeTile + kGeSeedCache) * sizeof(double);
-  static bool ge_attr_set = false;
-  if (!ge_attr_set) {
+  if (!h->ge_attr_set) {
     CU_TRY(cudaFuncSetAttribute(k_ge_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGeFitSmem));
-    ge_attr_set = true;
+    h->ge_attr_set = true;
   }
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_fit<<<4 * cfg->num_sec, kGeFitThreads, kGeFitSmem, h->stream>>>(a)));
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_emit<<<dim3(32, 25), 256, 0, h->stream>>>(a)));
@@ -2411,10 +2410,9 @@ int tloam_b200_extract_edge(tloam_b200_handle* h, int sensor_model, int ring_min
   a.sec_edge = (unsigned*)(b + o_se); a.sec_non = (unsigned*)(b + o_sn); a.sec_cnt = (unsigned*)(b + o_sc);
   a.sec_off = (unsigned*)(b + o_so); a.out_edge = (unsigned long long*)(b + o_oe); a.out_non = (unsigned long long*)(b + o_on);
   a.status = (int*)(b + o_st);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->ee_attr_set) {
     CU_TRY(cudaFuncSetAttribute(k_ee_section, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEeSmemBytes));
-    attr_set = true;
+    h->ee_attr_set = true;
   }
   if (h->seg.active) { a.pts = h->seg.dev_xyz; a.intensity = h->seg.dev_intensity; }
   else {
@@ -2512,11 +2510,10 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   const bool seq_bytes = seq_fixed + state_bytes <= (size_t)kOsSeqSmemBytes && !getenv("TLOAM_B200_DCVC_PACKED");
   const int use_smem = seq_fixed + state_words * 4 <= (size_t)kOsSeqSmemBytes && !getenv("TLOAM_B200_DCVC_GLOBAL") ? 1 : 0;
   const size_t seq_smem = seq_fixed + (seq_bytes ? state_bytes : (use_smem ? state_words * 4 : 0));
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!h->os_attr_set) {
     CU_TRY(cudaFuncSetAttribute(k_os_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSeqSmemBytes));
     CU_TRY(cudaFuncSetAttribute(k_os_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOsSeqSmemBytes));
-    attr_set = true;
+    h->os_attr_set = true;
   }
   cudaStream_t st = h->stream;
   if (h->seg.active) a.pts = h->seg.dev_xyz;
@@ -2661,6 +2658,7 @@ int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcf
   if (no) {
     CU_TRY(cudaMemcpyAsync(d_oidx, h->seg.object, no * 4, cudaMemcpyDeviceToDevice, h->stream));
     k_chain_gather_object<<<(unsigned)((no + 255) / 256), 256, 0, h->stream>>>(d_scan, h->seg.beam, h->seg.object, (unsigned)no, d_opts, d_obeam);
+    CU_TRY(cudaGetLastError());
   }
   size_t ne = 0, nn = 0;
   if (no) {
@@ -2673,6 +2671,7 @@ int tloam_b200_segment_scan(tloam_b200_handle* h, const tloam_ground_config* gcf
     if (ns) {
       k_chain_gather_segmented<<<(unsigned)((ns + 255) / 256), 256, 0, h->stream>>>(d_opts, d_obeam, d_oidx, h->seg.seg, (unsigned)ns, d_spts, d_sbeam,
                                                                                      d_sorig);
+      CU_TRY(cudaGetLastError());
       // ---- 3. extractEdgePoint ----
       h->seg.dev_xyz = d_spts; h->seg.dev_intensity = d_sbeam;
       rc = tloam_b200_extract_edge(h, gcfg->sensor_model, ring_min_num, d_spts, d_sbeam, ns, edge_index, &ne, general_index, &nn);
