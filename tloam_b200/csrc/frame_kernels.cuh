@@ -224,6 +224,11 @@ struct SearchSmem {
   unsigned beg[kPairCells][kBlk];
   unsigned cnt[kPairCells][kBlk];
   float md[kPairCells][kBlk];
+#if TLOAM_SEARCH_QUEUE
+  double q_d[kSearchQueue][kBlk];            // candidate queue of knn_search_pair (K = 5)
+  int q_i[kSearchQueue][kBlk];
+  int q_p[kSearchQueue][kBlk];
+#endif
 };
 
 // Correspondence search + primitive fit of the feature served by this lane pair (64 features per 128-thread block:
@@ -259,7 +264,11 @@ __device__ __forceinline__ void search_and_fit(const DeviceCtx& ctx, const Frame
     if (live && even) flag = fit_one<1>(ctx, c, t, prim);
   } else {
     TopK<5> t;
+#if TLOAM_SEARCH_QUEUE
+    knn_search_pair<5, kBlk>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], sm->beg, sm->cnt, sm->md, t, nullptr, sm->q_d, sm->q_i, sm->q_p);
+#else
     knn_search_pair<5, kBlk>(ctx.grid[c], live, rx, ry, rz, ctx.r2[c], sm->beg, sm->cnt, sm->md, t);
+#endif
     if (ctx.dbg) tk1 = clock64();
     if (live && even) flag = fit_one<5>(ctx, c, t, prim);
   }

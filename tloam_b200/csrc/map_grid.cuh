@@ -218,11 +218,21 @@ constexpr bool kMergeRuns = true;     // measured: 28.2 us per launch with mergi
 //  sequences, 2343 vs 2387 frames/s single stream -- the extra instructions cost more than the skipped FP64 ones)
 constexpr unsigned kMergeMax = 16u;   // merged entry: at most this many points
 constexpr int kPairCells = 18;    // 3 x 3 x 2 cells at most in one z-layer of bricks
+// candidate queue in front of the sorted insertion: built and measured in round 2 (second half), SLOWER for K = 5 --
+// 222 vs 171 us per batched launch of 8 sequences, 2 443 vs 2 562 frames/s single stream (the two-pass mask, the
+// shared-memory round trip and the warp-uniform loop cost more than the ~40-instruction insertion they avoid; at K = 20,
+// k_fe_pca, the same idea wins).  Kept behind the macro; poses are bit-identical either way.
+#ifndef TLOAM_SEARCH_QUEUE
+#define TLOAM_SEARCH_QUEUE 0
+#endif
+constexpr int kSearchQueue = 8;   // queued candidates per thread = one batch of loads
 
 template <int K, int kThreads>
 __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, double rx, double ry, double rz, double r2,
                                                 unsigned (*s_beg)[kThreads], unsigned (*s_cnt)[kThreads],
-                                                float (*s_md)[kThreads], TopK<K>& t, long long* stamps = nullptr) {
+                                                float (*s_md)[kThreads], TopK<K>& t, long long* stamps = nullptr,
+                                                double (*q_d)[kThreads] = nullptr, int (*q_i)[kThreads] = nullptr,
+                                                int (*q_p)[kThreads] = nullptr) {
   t.init();
   const int tid = threadIdx.x;
   const int half = tid & 1;
@@ -318,7 +328,29 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
   int ci = 0;
   unsigned off = (unsigned)half, cb = 0u, cc = 0u;
   if (mt > 0) { const int col = (0 < m0) ? col0 : col1; cb = s_beg[0][col]; cc = s_cnt[0][col]; }
+#if TLOAM_SEARCH_QUEUE
+  // Candidate queue (K > 1): once a lane's list is full, a candidate that beats the lane's K-th best (as of the last drain)
+  // is only QUEUED (shared memory, kSearchQueue per thread); the queues are drained into the sorted lists by all lanes
+  // together, when one of them could overflow on the next batch and once at the end.  The sorted insertion (~40
+  // instructions) then runs a few times per query with most lanes busy, instead of once per candidate batch slot
+  // whenever ANY lane of the warp has a candidate (k_fe_pca does the same for K = 20).  The set of candidates that
+  // reaches insert() is a superset of what the direct form inserts, and insert() orders by (d2, index): same result.
+  int qn = 0;
+  double kth = t.d2[K - 1];
+  auto drain = [&]() {
+    const int most = __reduce_max_sync(0xffffffffu, qn);
+    for (int e = 0; e < most; ++e)
+      if (e < qn) t.insert(q_d[e][tid], q_i[e][tid], q_p[e][tid]);
+    qn = 0;
+    kth = t.d2[K - 1];
+  };
+#endif
+#if TLOAM_SEARCH_QUEUE
+  // warp-uniform loop (the drain uses warp-wide collectives): lanes whose pair is done load nothing
+  while (__any_sync(0xffffffffu, ci < mt)) {
+#else
   while (ci < mt) {
+#endif
     float4 pt[8];
     int pos[8];
     double worst = t.d2[K - 1];                   // +inf until the list is full
@@ -346,15 +378,49 @@ __device__ __forceinline__ void knn_search_pair(const GridDesc& g, bool live, do
         }
       }
     }
+#if TLOAM_SEARCH_QUEUE
+    if (K > 1 && q_d != nullptr) {
+      const bool full = t.pos[K - 1] >= 0;
+      const double lim = full ? kth : r2;                      // list not full yet: everything inside the radius goes in directly
+      // pass 1: which of the 8 would be queued (a bit mask: the distances are recomputed for the few that are)
+      unsigned pass = 0u;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (pos[q] >= 0) {
-        const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
-        const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
-        if (d < r2) t.insert(d, __float_as_int(pt[q].w), pos[q]);
+      for (int q = 0; q < 8; ++q) {
+        if (pos[q] >= 0) {
+          const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
+          const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
+          if (d < r2) {
+            if (!full) t.insert(d, __float_as_int(pt[q].w), pos[q]);
+            else if (d <= lim) pass |= 1u << q;
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, qn + __popc(pass) > kSearchQueue)) drain();   // room first (the mask stays a superset)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if ((pass >> q) & 1u) {
+          const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
+          q_d[qn][tid] = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
+          q_i[qn][tid] = __float_as_int(pt[q].w); q_p[qn][tid] = pos[q];
+          ++qn;
+        }
+      }
+    } else
+#endif
+    {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (pos[q] >= 0) {
+          const double ddx = (double)pt[q].x - rx, ddy = (double)pt[q].y - ry, ddz = (double)pt[q].z - rz;
+          const double d = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));   // same three operations as the oracle
+          if (d < r2) t.insert(d, __float_as_int(pt[q].w), pos[q]);
+        }
       }
     }
   }
+#if TLOAM_SEARCH_QUEUE
+  if (K > 1 && q_d != nullptr && __any_sync(0xffffffffu, qn > 0)) drain();
+#endif
   if (stamps) stamps[3] = clock64();
   // merge: the even lane pulls the odd lane's list (sorted) and inserts its entries until one fails
   __syncwarp();
