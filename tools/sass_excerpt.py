@@ -11,7 +11,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "tloam_b200", "libtloam_b200.so")
-WANT = ["k_first", "k_eval", "k_correspond_dense", "k_correspond_fine", "k_correspond", "k_map_fine", "k_begin_frame", "k_ge_fit", "k_fe_sort", "k_qbin_count"]
+WANT = ["k_first", "k_eval", "k_correspond_dense", "k_correspond_fine", "k_correspond", "k_map_fine", "k_begin_frame", "k_ge_fit", "k_fe_sort", "k_fe_rank",
+        "k_qbin_count", "k_os_seq", "k_os_union", "k_ee_section"]
 
 
 def main():
@@ -31,7 +32,7 @@ def main():
               f"DADD: {hist.get('DADD', 0)}   DMUL: {hist.get('DMUL', 0)}   FFMA: {hist.get('FFMA', 0)}   LDG: {hist.get('LDG', 0)}   "
               f"LDS: {hist.get('LDS', 0)}   SHFL: {hist.get('SHFL', 0)}   BAR: {hist.get('BAR', 0)}")
         print("top mnemonics: " + ", ".join(f"{k} {v}" for k, v in hist.most_common(14)))
-        tma = [k for k in full if k.startswith(("UBLKCP", "SYNCS", "UTMA", "UCGABAR", "MEMBAR"))]
+        tma = [k for k in full if k.startswith(("UBLKCP", "SYNCS", "UTMA", "UCGABAR", "MEMBAR", "LDGSTS", "LDGDEPBAR", "DEPBAR", "ATOMS", "ATOMG", "VOTE", "MATCH"))]
         if tma:
             print("async-copy / barrier instructions: " + ", ".join(f"{k} x{full[k]}" for k in sorted(tma)))
             for line in b.split("\n"):
