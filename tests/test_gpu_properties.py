@@ -141,3 +141,42 @@ def test_decision_flips_under_one_ulp_perturbations():
     out = m.run(R=2, level="f32")                          # a step the FP32 map storage can see (~4e-6 m at 50 m)
     assert out["max_validity_flips_outer0"] <= 40          # <= 0.1 % of 40k features
     assert out["max_dt_m"] < 1e-4 and out["max_dr_rad"] < 1e-5, out
+
+
+@pytest.mark.gpu
+def test_pageable_inputs_staged_by_the_library_equal_pinned_inputs():
+    """Ordinary (pageable) host clouds go through the library's own staging (2 MB chunks copied by a thread pool into a ring
+    of 8 pinned slots, tloam_b200/csrc/host_stage.h); pinned clouds are DMA'd directly.  Same map either way: a 36 MB cloud
+    (18 chunks: the ring wraps twice and waits for its own DMAs), odd sizes that end inside a chunk, and a cloud below the
+    staging threshold; checked through the exact kNN of the map built from it and through a registration."""
+    import torch
+    import tloam_b200
+    rng = np.random.default_rng(12)
+    big = rng.uniform(-60, 60, (1_500_037, 3)) * np.array([1.0, 1.0, 0.05])
+    clouds = [big[:4001].copy(), big[:100_003].copy(), big, big[:777_777].copy()]          # edge, sphere, planar, ground
+    q = big[rng.integers(0, len(big), 4000)] + rng.normal(0, 0.05, (4000, 3))
+    out = []
+    for pinned in (False, True):
+        reg = tloam_b200.LocalRegistration()
+        cl = [torch.from_numpy(c).pin_memory().numpy() if pinned else np.array(c, copy=True) for c in clouds]
+        reg.set_input_target(cl)
+        res = [reg.knn(c, q, 0.3, 5) for c in range(4)]
+        out.append(res)
+        reg.close()
+    for a, b in zip(*out):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # and a whole frame: pageable scan + map vs pinned scan + map, bit-identical pose
+    cfg = synth.scaled(0.2, seed=7)
+    T_gt = synth.se3_exp([3.0, -1.0, 0.0, 0.0, 0.01, 0.4])
+    predict = T_gt @ synth.se3_exp(synth.CONFIG1_PERTURB)
+    mp, scan = synth.make_map(cfg, T_gt), synth.make_scan(cfg, T_gt, 0)
+    poses = []
+    for pinned in (False, True):
+        reg = tloam_b200.LocalRegistration()
+        conv = (lambda c: torch.from_numpy(np.ascontiguousarray(c)).pin_memory().numpy()) if pinned else (lambda c: np.array(c, copy=True))
+        reg.set_input_target([conv(c) for c in mp])
+        reg.set_input_source([conv(c) for c in scan])
+        poses.append(reg.scan_matching(predict))
+        reg.close()
+    assert np.array_equal(poses[0], poses[1])
