@@ -58,7 +58,6 @@ struct OsArgs {
   int* vid;                               // [n]
   int* f1;                                // [n] by vid: smallest point index (the voxel's node in the union-find)
   int* f2;                                // [n] by vid: second smallest
-  int* vcoord;                            // [n][3] by vid
   int* evkey;                             // [n] partition key of the event compaction: 0 = event, -1 = not
   int* ev_pt;                             // [n] events in point order (output of the compaction)
   int* ev_info;                           // [n] vid * 4 + kind (0 first point, 1 second point, 2 voxel not in its own list)
@@ -217,7 +216,6 @@ __global__ void __launch_bounds__(kOsChunk) k_os_first(const __grid_constant__ O
   const int v = a.slot_vid[a.pslot[i]];
   a.vid[i] = v;
   atomicMin(a.f1 + v, (int)i);
-  a.vcoord[3ull * v] = a.coord[3ull * i]; a.vcoord[3ull * v + 1] = a.coord[3ull * i + 1]; a.vcoord[3ull * v + 2] = a.coord[3ull * i + 2];
 }
 
 // ---- 6. second point -----------------------------------------------------------------------------------------------

@@ -2483,7 +2483,7 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
   const size_t o_pts = take(n * 24), o_pol = take(n * 24), o_enc = take(64), o_ext = take(64), o_par = take(64),
                o_bnd = take(kOsMaxBounds * 8), o_key = take(n * 4), o_crd = take(n * 12), o_tab = take(cap * 8), o_sv = take(cap * 4),
-               o_ps = take(n * 4), o_vid = take(n * 4), o_f1 = take(n * 4), o_f2 = take(n * 4), o_vc = take(n * 12),
+               o_ps = take(n * 4), o_vid = take(n * 4), o_f1 = take(n * 4), o_f2 = take(n * 4),
                o_ek = take(n * 4), o_ept = take(n * 4), o_ei = take(n32 * 4), o_rows = take((n32 + 32 * kOsSeqStages) * kOsRowStride * 4), o_ep = take(n32),
                o_stg = take(state_words * 4), o_par2 = take(n * 4), o_root = take(n * 4), o_cnt = take(n * 4), o_clr = take(n * 4),
                o_crr = take(n * 4), o_cl = take(n * 4), o_sz = take(n * 4), o_pk = take(n * 4), o_box = take(n * 48), o_benc = take(n * 48),
@@ -2499,7 +2499,7 @@ int tloam_b200_object_segmentation(tloam_b200_handle* h, const tloam_dcvc_config
   a.pts = (const double*)(b + o_pts); a.polar = (double*)(b + o_pol); a.ext_enc = (unsigned long long*)(b + o_enc);
   a.ext = (double*)(b + o_ext); a.params = (int*)(b + o_par); a.bounds = (double*)(b + o_bnd); a.key = (int*)(b + o_key);
   a.coord = (int*)(b + o_crd); a.table = (unsigned long long*)(b + o_tab); a.slot_vid = (int*)(b + o_sv); a.pslot = (int*)(b + o_ps);
-  a.vid = (int*)(b + o_vid); a.f1 = (int*)(b + o_f1); a.f2 = (int*)(b + o_f2); a.vcoord = (int*)(b + o_vc); a.evkey = (int*)(b + o_ek);
+  a.vid = (int*)(b + o_vid); a.f1 = (int*)(b + o_f1); a.f2 = (int*)(b + o_f2); a.evkey = (int*)(b + o_ek);
   a.ev_pt = (int*)(b + o_ept); a.ev_info = (int*)(b + o_ei); a.rows = (int*)(b + o_rows); a.ev_p = (signed char*)(b + o_ep);
   a.state_g = (unsigned*)(b + o_stg); a.parent = (int*)(b + o_par2); a.root = (int*)(b + o_root); a.cnt = (int*)(b + o_cnt);
   a.cl_root = (int*)(b + o_clr); a.cl_rank_of_root = (int*)(b + o_crr); a.cluster = (int*)(b + o_cl); a.sizes = (int*)(b + o_sz);
