@@ -863,8 +863,8 @@ def main():
             return (ge["ground"], ge["object"], os_["segmented"], os_["sizes"], ee["edge"], ee["non_edge"]), (d[0], d[2], d[4])
 
         for _ in range(3):
-            sout, _ = seg_chain(reg.ground_extract, reg.object_segmentation, reg.extract_edge)
-        st = np.array([seg_chain(reg.ground_extract, reg.object_segmentation, reg.extract_edge)[1] for _ in range(10)])
+            sout, _ = seg_chain(reg.ground_extract, (lambda pts: reg.object_segmentation(pts, details=False)), reg.extract_edge)
+        st = np.array([seg_chain(reg.ground_extract, (lambda pts: reg.object_segmentation(pts, details=False)), reg.extract_edge)[1] for _ in range(10)])
         sm = np.median(st, axis=0)
         for _ in range(3):
             one = reg.segment_scan(raw)

@@ -349,11 +349,11 @@ class LocalRegistration:
         return dict(edge=e[:ne.value].copy(), non_edge=o[:no.value].copy())
 
     # ---- "next" row (f)-4, third part: object segmentation = DCVC (ref: segmentation.cpp:772-1112) ----
-    def object_segmentation(self, points, **overrides):
-        """Segmentation::objectSegmentation on the device.  Returns dict(segmented, sizes, boxes, root, cluster, voxel,
-        polar, ext): the segmented scan as indices (cluster after cluster), cluster sizes / boxes, and per point the
-        smallest index of its DCVC class, its 1-based cluster number (0 = filtered), the reference's voxel index and the
-        polar triple."""
+    def object_segmentation(self, points, details=True, **overrides):
+        """Segmentation::objectSegmentation on the device.  Returns dict(segmented, sizes, boxes[, root, cluster, voxel,
+        polar, ext]): the segmented scan as indices (cluster after cluster), cluster sizes / boxes, and with `details` per
+        point the smallest index of its DCVC class, its 1-based cluster number (0 = filtered), the reference's voxel index
+        and the polar triple (four more downloads; the C++ shim does not ask for them)."""
         a = _f64(points).reshape(-1, 3)
         n = a.shape[0]
         c = _lib.DcvcConfig()
@@ -362,19 +362,25 @@ class LocalRegistration:
             setattr(c, k, v)
         m = max(n, 1)
         seg = np.zeros(m, dtype=np.uintp)
-        sizes, root, cluster, voxel = (np.zeros(m, dtype=np.int32) for _ in range(4))
+        sizes = np.zeros(m, dtype=np.int32)
         boxes = np.zeros((m, 6))
-        polar = np.zeros(3 * m + 4)
         nseg, ncl = C.c_size_t(0), C.c_int(0)
         szp, ip = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+        if details:
+            root, cluster, voxel = (np.zeros(m, dtype=np.int32) for _ in range(3))
+            polar = np.zeros(3 * m + 4)
+            extra = (root.ctypes.data_as(ip), cluster.ctypes.data_as(ip), voxel.ctypes.data_as(ip), _dp(polar))
+        else:
+            extra = (None, None, None, None)
         self._check(self._L.tloam_b200_object_segmentation(self._h, C.byref(c), _dp(a), n, seg.ctypes.data_as(szp), C.byref(nseg),
-                                                           C.byref(ncl), sizes.ctypes.data_as(ip), _dp(boxes), root.ctypes.data_as(ip),
-                                                           cluster.ctypes.data_as(ip), voxel.ctypes.data_as(ip), _dp(polar)),
+                                                           C.byref(ncl), sizes.ctypes.data_as(ip), _dp(boxes), *extra),
                     "object_segmentation")
         k = ncl.value
-        return dict(segmented=seg[:nseg.value].copy(), sizes=sizes[:k].copy(), boxes=boxes[:k].copy(), root=root[:n].copy(),
-                    cluster=cluster[:n].copy(), voxel=voxel[:n].copy(), polar=polar[:3 * n].reshape(-1, 3).copy(),
-                    ext=polar[3 * n:3 * n + 4].copy())
+        out = dict(segmented=seg[:nseg.value].copy(), sizes=sizes[:k].copy(), boxes=boxes[:k].copy())
+        if details:
+            out.update(root=root[:n].copy(), cluster=cluster[:n].copy(), voxel=voxel[:n].copy(),
+                       polar=polar[:3 * n].reshape(-1, 3).copy(), ext=polar[3 * n:3 * n + 4].copy())
+        return out
 
     # ---- "next" row (f)-4: the three segmentation steps as one call (ref: segmentation.cpp:47-66) ----
     def segment_scan(self, scan, ring_min_num=131, ground=None, dcvc=None):

@@ -16,7 +16,7 @@ for _ in range(2):
     ge = reg.ground_extract(scan)
     opts = np.ascontiguousarray(scan[ge["object"]])
     obeam = ge["beam"][ge["object"]].astype(np.float64)
-    os_ = reg.object_segmentation(opts)
+    os_ = reg.object_segmentation(opts, details=False)
     spts = np.ascontiguousarray(opts[os_["segmented"]])
     ee = reg.extract_edge(spts, obeam[os_["segmented"]], ring_min_num=131)
 print(len(scan), len(opts), len(spts), len(ee["edge"]), len(ee["non_edge"]))
