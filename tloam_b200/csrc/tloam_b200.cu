@@ -2350,7 +2350,6 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
   TL_LAUNCH(TLOAM_B200_K_GROUND, (k_ge_emit<<<dim3(32, 25), 256, 0, h->stream>>>(a)));
   CU_TRY(cudaGetLastError());
   // counts + threshold first (one small copy each, one synchronisation), then exactly the list prefixes
-  std::vector<unsigned> gi(n), oi(n);
   CU_TRY(cudaMemcpyAsync(h->h_result + 28, a.out_counts, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaMemcpyAsync(h->h_result + 29, a.scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(cudaStreamSynchronize(h->stream));
@@ -2363,6 +2362,7 @@ int tloam_b200_ground_extract(tloam_b200_handle* h, const tloam_ground_config* c
     *n_ground = counts[0]; *n_object = counts[1];
     return TLOAM_B200_OK;
   }
+  std::vector<unsigned> gi(counts[0]), oi(counts[1]);
   if (counts[0]) CU_TRY(cudaMemcpyAsync(gi.data(), a.out_ground, counts[0] * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   if (counts[1]) CU_TRY(cudaMemcpyAsync(oi.data(), a.out_object, counts[1] * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   if (beam) CU_TRY(cudaMemcpyAsync(beam, a.beam, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
