@@ -29,6 +29,12 @@ class HostStage {
   ~HostStage() { shutdown(); }
 
   // true if `p` is ordinary pageable memory (not pinned / registered / managed / device)
+  static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();                                   // be kind to the sibling hardware thread while polling
+#endif
+  }
+
   static bool pageable(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
@@ -101,6 +107,7 @@ class HostStage {
     while (true) {
       unsigned g = generation_.load(std::memory_order_acquire);
       if (g == seen) {
+        cpu_relax();
         if (stop_.load(std::memory_order_acquire)) return;
         if (std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - last).count() > kSpinNs) {
           std::unique_lock<std::mutex> lk(m_);
@@ -135,7 +142,7 @@ class HostStage {
       cv_work_.notify_all();
     }
     memcpy(dst, src, part < len ? part : len);                            // the caller's share
-    while (done_.load(std::memory_order_acquire) < kWorkers) { /* spin: the others finish within microseconds */ }
+    while (done_.load(std::memory_order_acquire) < kWorkers) cpu_relax();   // the others finish within microseconds
   }
 
   char* pin_ = nullptr;
