@@ -85,6 +85,86 @@ def structural_dcvc(polar, ext, start_r=0.35, delta_r=0.0004, delta_p=1.2, delta
     return root, key
 
 
+def python_dcvc_labels(polar, ext, start_r=0.35, delta_r=0.0004, delta_p=1.2, delta_a=1.2):
+    """Literal transcription of createHashTable + searchKNN + DCVC (:843-990) in plain Python: dict of point lists, the
+    label list relabelled by full sweeps.  Returns the raw label list (labels are arbitrary: compare partitions)."""
+    n = len(polar)
+    min_pitch, max_pitch, min_polar, max_polar = (float(v) for v in ext)
+    width = int(round(360.0 / delta_a) + 1)
+    height = int((max_pitch - min_pitch) / delta_p)
+    bounds, rng, step = [], min_polar, 1
+    while rng <= max_polar:
+        rng += (start_r - step * delta_r)
+        bounds.append(rng)
+        step += 1
+    polar_num = len(bounds)
+
+    def polar_index(radius):
+        for r in range(polar_num):
+            if radius < bounds[r]:
+                return r
+        return polar_num - 1
+
+    def c_round(x):                                    # std::round: half away from zero
+        return int(np.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)
+
+    idx3, voxel_map = [], {}
+    for i in range(n):
+        pi_, ti_, ai_ = polar_index(polar[i][0]), c_round((polar[i][1] - min_pitch) / delta_p), c_round(polar[i][2] / delta_a)
+        idx3.append((pi_, ti_, ai_))
+        voxel_map.setdefault((ai_ * (polar_num + 1) + pi_) + ti_ * (polar_num + 1) * (width + 1), []).append(i)
+    label, count = [-1] * n, 0
+    for i in range(n):
+        if label[i] != -1:
+            continue
+        pi_, ti_, ai_ = idx3[i]
+        neighbors = []
+        for z in range(ti_ - 1, ti_ + 2):
+            if z < 0 or z > height:
+                continue
+            for y in range(pi_ - 1, pi_ + 2):
+                if y < 0 or y > polar_num:
+                    continue
+                for x in range(ai_ - 1, ai_ + 2):
+                    ax = x
+                    if ax < 0:
+                        ax = width - 1
+                    if ax > 300:
+                        ax = 300
+                    neighbors += voxel_map.get((ax * (polar_num + 1) + y) + z * (polar_num + 1) * (width + 1), [])
+        for j in neighbors:
+            curr, neigh = label[i], label[j]
+            if curr != -1 and neigh != -1 and curr != neigh:
+                label = [neigh if s == curr else s for s in label]
+            elif neigh != -1:
+                label[i] = neigh
+            elif curr != -1:
+                label[j] = curr
+        if label[i] == -1:
+            count += 1
+            label[i] = count
+            for j in neighbors:
+                label[j] = count
+    return label
+
+
+def canonical(label):
+    first = {}
+    for i, l in enumerate(label):
+        first.setdefault(l, i)
+    return np.array([first[l] for l in label])
+
+
+def test_literal_oracle_against_a_literal_python_transcription(oracle):
+    """Second, independent pin of the C++ restatement: the reference's loops transcribed statement by statement in Python
+    (small clouds: the label sweeps are quadratic)."""
+    for p in random_clouds(16, seed=21, nmax=700):
+        for kw in ({}, dict(delta_a=0.6)):
+            r = oracle.dcvc(p, **kw)
+            lab = python_dcvc_labels(r["polar"], r["ext"], **kw)
+            assert np.array_equal(canonical(lab), r["root"]), kw
+
+
 def object_scan(oracle, seed=20260924 + 5151, **kw):
     scan = synth.raw_scan(seed=seed, **kw)
     g = oracle.ground_extract(scan)
