@@ -1,5 +1,9 @@
 /*
- * segmentation_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT) for "next" row SURVEY 8(f)-4, first part:
+ * segmentation_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT) for "next" row SURVEY 8(f)-4: the three compute
+ * steps of the segmentation nodelet.  Further down in this file: edge extraction (Segmentation::extractEdgePoint, ref:
+ * :1144-1304) and object segmentation (DCVC, ref: :772-1112), each with its own header; they are PARITY UNPINNED by the
+ * reference too, and pinned by literal Python transcriptions and an independent voxel-level model
+ * (tests/test_edge_extract.py, tests/test_object_segmentation.py).  First part:
  * the multi-region ground extraction of the segmentation nodelet,
  *   Segmentation::groundRemove                    ref: src/models/segmentation/segmentation.cpp:738-770
  *   -> initSections / getSection                  ref: :174-238
